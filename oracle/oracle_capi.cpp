@@ -1,0 +1,208 @@
+// oracle_capi.cpp -- C entry points of the CPU ORACLE for ctypes (test infrastructure only;
+// see the header of pnp_oracle.hpp).  Nothing under dune_pnp_b200/ may link or load this.
+#include "pnp_oracle.hpp"
+#include <chrono>
+#include <cstring>
+
+using namespace pnpo;
+
+namespace {
+thread_local std::string g_err;
+struct Params { Sysparams s; };
+OpCtx make_ctx(const Mesh* m, const Sysparams* s, int op, const double* aux0, const double* aux1,
+               double valency, int intorder) {
+  OpCtx c; c.op = op; c.s = s; c.m = m; c.valency = valency; c.intorder = intorder;
+  if (op == OP_POISSON) { c.cp = aux0; c.cm = aux1; }
+  if (op == OP_DIFFUSION) { c.uphi = aux0; }
+  return c;
+}
+int comp0_of(int op) { (void)op; return 0; }
+} // namespace
+
+#define ORA_TRY try {
+#define ORA_CATCH(rv) } catch (const std::exception& ex) { g_err = ex.what(); return rv; }
+
+extern "C" {
+
+const char* ora_last_error() { return g_err.c_str(); }
+
+void* ora_mesh_create(int nv, const double* x, const double* y, int nT, const int* tri, int nB,
+                      const int* ba, const int* bb, const int* bphys) {
+  ORA_TRY
+  Mesh* m = new Mesh;
+  m->x.assign(x, x + nv); m->y.assign(y, y + nv); m->tri.assign(tri, tri + 3 * nT);
+  m->ba.assign(ba, ba + nB); m->bb.assign(bb, bb + nB); m->bphys.assign(bphys, bphys + nB);
+  m->finalize();
+  return m;
+  ORA_CATCH(nullptr)
+}
+void* ora_mesh_read_gmsh(const char* path) {
+  ORA_TRY return new Mesh(read_gmsh(path)); ORA_CATCH(nullptr)
+}
+void* ora_mesh_refine(void* h) {
+  ORA_TRY return new Mesh(refine(*(Mesh*)h)); ORA_CATCH(nullptr)
+}
+void ora_mesh_sizes(void* h, int* nv, int* nT, int* nB) {
+  Mesh* m = (Mesh*)h; *nv = m->nv; *nT = m->nT; *nB = m->nB;
+}
+void ora_mesh_get(void* h, double* x, double* y, int* tri, int* ba, int* bb, int* bphys) {
+  Mesh* m = (Mesh*)h;
+  std::copy(m->x.begin(), m->x.end(), x); std::copy(m->y.begin(), m->y.end(), y);
+  std::copy(m->tri.begin(), m->tri.end(), tri);
+  std::copy(m->ba.begin(), m->ba.end(), ba); std::copy(m->bb.begin(), m->bb.end(), bb);
+  std::copy(m->bphys.begin(), m->bphys.end(), bphys);
+}
+void ora_mesh_free(void* h) { delete (Mesh*)h; }
+
+// flat parameter layout shared with the tests:
+//  sys[16]  = {n_surfaces, cylindrical, l_b, c0, PI, linearSolverIterations, newtonReassembleThreshold,
+//              newtonReduction, newtonMinLinearReduction, newtonMaxIterations,
+//              newtonLineSearchMaxIteration, tau, nSteps, outputFreq, potentialUpdateFreq, verbosity}
+//  surf[ns][9] = per component {btype, flux, dirichlet value}
+void* ora_params_read(const char* path) {
+  ORA_TRY Params* p = new Params; p->s = read_config(path); return p; ORA_CATCH(nullptr)
+}
+void* ora_params_create(const double* sys, const double* surf) {
+  ORA_TRY
+  Params* p = new Params; Sysparams& s = p->s;
+  s.n_surfaces = (int)sys[0]; s.cylindrical = sys[1] != 0; s.l_b = sys[2]; s.c0 = sys[3]; s.PI = sys[4];
+  s.linearSolverIterations = (int)sys[5]; s.newtonReassembleThreshold = sys[6]; s.newtonReduction = sys[7];
+  s.newtonMinLinearReduction = sys[8]; s.newtonMaxIterations = sys[9]; s.newtonLineSearchMaxIteration = sys[10];
+  s.tau = sys[11]; s.nSteps = (int)sys[12]; s.outputFreq = (int)sys[13]; s.potentialUpdateFreq = (int)sys[14];
+  s.verbosity = (int)sys[15];
+  s.surfaces.assign(s.n_surfaces, Surface());
+  for (int i = 0; i < s.n_surfaces; i++) {
+    const double* f = surf + 9 * i; Surface& q = s.surfaces[i];
+    q.coulombBtype = (int)f[0]; q.coulombFlux = f[1]; q.coulombPotential = f[2];
+    q.plusDiffusionBtype = (int)f[3]; q.plusDiffusionFlux = f[4]; q.plusDiffusionConcentration = f[5];
+    q.minusDiffusionBtype = (int)f[6]; q.minusDiffusionFlux = f[7]; q.minusDiffusionConcentration = f[8];
+  }
+  return p;
+  ORA_CATCH(nullptr)
+}
+int ora_params_nsurf(void* h) { return ((Params*)h)->s.n_surfaces; }
+void ora_params_get(void* h, double* sys, double* surf, char* meshfile, int meshfile_cap) {
+  const Sysparams& s = ((Params*)h)->s;
+  double v[16] = {(double)s.n_surfaces, (double)s.cylindrical, s.l_b, s.c0, s.PI, (double)s.linearSolverIterations,
+                  s.newtonReassembleThreshold, s.newtonReduction, s.newtonMinLinearReduction, s.newtonMaxIterations,
+                  s.newtonLineSearchMaxIteration, s.tau, (double)s.nSteps, (double)s.outputFreq,
+                  (double)s.potentialUpdateFreq, (double)s.verbosity};
+  std::copy(v, v + 16, sys);
+  for (int i = 0; i < s.n_surfaces; i++) {
+    const Surface& q = s.surfaces[i]; double* f = surf + 9 * i;
+    f[0] = q.coulombBtype; f[1] = q.coulombFlux; f[2] = q.coulombPotential;
+    f[3] = q.plusDiffusionBtype; f[4] = q.plusDiffusionFlux; f[5] = q.plusDiffusionConcentration;
+    f[6] = q.minusDiffusionBtype; f[7] = q.minusDiffusionFlux; f[8] = q.minusDiffusionConcentration;
+  }
+  if (meshfile && meshfile_cap > 0) { std::strncpy(meshfile, s.meshfile.c_str(), meshfile_cap - 1); meshfile[meshfile_cap - 1] = 0; }
+}
+void ora_params_free(void* h) { delete (Params*)h; }
+
+int ora_dirichlet(void* mh, void* ph, int fields, int comp0, char* out) {
+  ORA_TRY
+  Space sp = make_space(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
+  std::copy(sp.dirichlet.begin(), sp.dirichlet.end(), out);
+  return 0;
+  ORA_CATCH(-1)
+}
+// pattern: call with col == nullptr to get nnz
+long ora_pattern(void* mh, void* ph, int fields, int comp0, int* rowptr, int* col) {
+  ORA_TRY
+  Space sp = make_space(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
+  CSR A = make_pattern(sp);
+  if (rowptr) std::copy(A.rowptr.begin(), A.rowptr.end(), rowptr);
+  if (col) std::copy(A.col.begin(), A.col.end(), col);
+  return (long)A.col.size();
+  ORA_CATCH(-1)
+}
+int ora_residual(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1,
+                 double valency, int intorder, double* r, double* absr) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  Space sp = make_space(*m, *s, op_fields(op), comp0);
+  OpCtx c = make_ctx(m, s, op, aux0, aux1, valency, intorder);
+  residual(sp, c, u, r, absr);
+  return 0;
+  ORA_CATCH(-1)
+}
+// values are written in the pattern order of ora_pattern()
+int ora_jacobian(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1,
+                 double valency, int intorder, int mode, double eps, double* val, double* absval) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  Space sp = make_space(*m, *s, op_fields(op), comp0);
+  OpCtx c = make_ctx(m, s, op, aux0, aux1, valency, intorder);
+  CSR A = make_pattern(sp);
+  std::vector<double> ab;
+  jacobian(sp, c, u, A, mode, eps, absval ? &ab : nullptr);
+  std::copy(A.val.begin(), A.val.end(), val);
+  if (absval) std::copy(ab.begin(), ab.end(), absval);
+  return 0;
+  ORA_CATCH(-1)
+}
+int ora_interpolate(void* mh, void* ph, int comp, const double* pb, double* u) {
+  ORA_TRY interpolate_bcext(*(Mesh*)mh, ((Params*)ph)->s, comp, pb, u); return 0; ORA_CATCH(-1)
+}
+// result[8] = {converged, iterations, reduction, conv_rate, status, seconds, 0, 0}
+int ora_linsolve(int n, const int* rowptr, const int* col, const double* val, double* x, double* b,
+                 double reduction, int maxit, int solver, int prec, int steps, double* result) {
+  ORA_TRY
+  CSR A; A.n = n; A.rowptr.assign(rowptr, rowptr + n + 1); A.col.assign(col, col + rowptr[n]);
+  A.val.assign(val, val + rowptr[n]);
+  auto t0 = std::chrono::steady_clock::now();
+  LinResult lr = lin_solve(solver, A, x, b, reduction, maxit, prec, steps);
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  result[0] = lr.converged; result[1] = lr.iterations; result[2] = lr.reduction; result[3] = lr.conv_rate;
+  result[4] = lr.status; result[5] = sec;
+  return 0;
+  ORA_CATCH(-1)
+}
+void ora_spmv(int n, const int* rowptr, const int* col, const double* val, const double* x, double* y) {
+  for (int r = 0; r < n; r++) {
+    double s = 0.0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) s += val[k] * x[col[k]];
+    y[r] = s;
+  }
+}
+// opts[16] = {reduction, abs_limit, min_linear_reduction, reassemble_threshold, maxit, ls_maxit, damping,
+//             jac_mode, fd_eps, solver, prec, prec_steps, lin_maxit, verbosity}
+// result[16] = {status, converged, iterations, first_defect, defect, reduction, total_linear_iterations,
+//               total_ls_trials, jacobian_assemblies, residual_assemblies, seconds}
+// hist (optional, cap entries): defect history; lin_hist: linear iterations per step
+int ora_newton(void* mh, void* ph, int op, int comp0, double* u, const double* aux0, const double* aux1,
+               double valency, int intorder, const double* opts, double* result, double* hist, int* lin_hist, int cap) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  Space sp = make_space(*m, *s, op_fields(op), comp0);
+  OpCtx c = make_ctx(m, s, op, aux0, aux1, valency, intorder);
+  NewtonOpts o;
+  o.reduction = opts[0]; o.abs_limit = opts[1]; o.min_linear_reduction = opts[2]; o.reassemble_threshold = opts[3];
+  o.maxit = (int)opts[4]; o.ls_maxit = (int)opts[5]; o.damping = opts[6]; o.jac_mode = (int)opts[7]; o.fd_eps = opts[8];
+  o.solver = (int)opts[9]; o.prec = (int)opts[10]; o.prec_steps = (int)opts[11]; o.lin_maxit = (int)opts[12];
+  o.verbosity = (int)opts[13];
+  auto t0 = std::chrono::steady_clock::now();
+  NewtonResult R = newton(sp, c, u, o);
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  double v[11] = {(double)R.status, (double)R.converged, (double)R.iterations, R.first_defect, R.defect, R.reduction,
+                  (double)R.total_linear_iterations, (double)R.total_ls_trials, (double)R.jacobian_assemblies,
+                  (double)R.residual_assemblies, sec};
+  std::copy(v, v + 11, result);
+  if (hist) for (int i = 0; i < cap; i++) hist[i] = i < (int)R.defect_history.size() ? R.defect_history[i] : -1.0;
+  if (lin_hist) for (int i = 0; i < cap; i++) lin_hist[i] = i < (int)R.lin_iter_history.size() ? R.lin_iter_history[i] : -1;
+  return 0;
+  ORA_CATCH(-1)
+}
+int ora_slp(void* mh, void* ph, int op, int comp0, double* u, const double* aux0, const double* aux1, double valency,
+            int intorder, double reduction, int solver, int prec, int steps, int maxit, int jac_mode, double eps,
+            double* result) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  Space sp = make_space(*m, *s, op_fields(op), comp0);
+  OpCtx c = make_ctx(m, s, op, aux0, aux1, valency, intorder);
+  LinResult lr = slp_apply(sp, c, u, reduction, solver, prec, steps, maxit, jac_mode, eps);
+  result[0] = lr.converged; result[1] = lr.iterations; result[2] = lr.reduction; result[3] = lr.conv_rate; result[4] = lr.status;
+  return 0;
+  ORA_CATCH(-1)
+}
+
+} // extern "C"
