@@ -1,0 +1,269 @@
+"""Thin ctypes binding of libpnp_b200.so (C ABI: include/pnp_b200.h).
+
+This is harness plumbing for tests/ and bench.py; the product is the CUDA library.  There is no CPU
+path: loading works anywhere (so symbols can be checked), creating a context needs a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpnp_b200.so")
+
+OP_PB, OP_POISSON, OP_DIFFUSION, OP_MASS, OP_PNP = range(5)
+JAC_FD_FAITHFUL, JAC_ANALYTIC = 0, 1
+SOLVER_BCGS, SOLVER_CG = 0, 1
+PREC_NONE, PREC_JACOBI, PREC_SSOR, PREC_ILU0, PREC_AMG = range(5)
+STATUS = {0: "PNP_OK", 1: "PNP_E_NOT_CONVERGED", 2: "PNP_E_LINEAR_SOLVER", 3: "PNP_E_LINE_SEARCH", 4: "PNP_E_NAN",
+          5: "PNP_E_BREAKDOWN", 6: "PNP_E_CUDA", 7: "PNP_E_CONFIG", 8: "PNP_E_ARG", 9: "PNP_E_MESH"}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class LinResult(C.Structure):
+    _fields_ = [("converged", C.c_int), ("iterations", C.c_int), ("reduction", C.c_double), ("conv_rate", C.c_double),
+                ("seconds", C.c_double), ("status", C.c_int)]
+
+
+class NewtonOpts(C.Structure):
+    _fields_ = [("reduction", C.c_double), ("abs_limit", C.c_double), ("min_linear_reduction", C.c_double),
+                ("reassemble_threshold", C.c_double), ("max_iterations", C.c_int),
+                ("line_search_max_iterations", C.c_int), ("damping", C.c_double), ("jac_mode", C.c_int),
+                ("fd_epsilon", C.c_double), ("verbosity", C.c_int)]
+
+
+class NewtonResult(C.Structure):
+    _fields_ = [("converged", C.c_int), ("iterations", C.c_int), ("first_defect", C.c_double), ("defect", C.c_double),
+                ("reduction", C.c_double), ("linear_iterations", C.c_int), ("line_search_trials", C.c_int),
+                ("jacobian_assemblies", C.c_int), ("residual_assemblies", C.c_int), ("seconds_assembly", C.c_double),
+                ("seconds_solve", C.c_double), ("seconds_total", C.c_double), ("n_history", C.c_int),
+                ("defect_history", C.c_double * 64), ("linear_iterations_history", C.c_int * 64)]
+
+
+class PnpError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("%s: %s" % (STATUS.get(status, status), msg))
+        self.status = status
+
+
+_LIB = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (there is no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libpnp_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C dune_pnp_b200/csrc)")
+        L = C.CDLL(LIB_PATH)
+        L.pnp_last_error.restype = C.c_char_p
+        L.pnp_launch_count.restype = C.c_long
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+class Context:
+    """One GPU, one mesh.  Mirrors the C ABI one to one; numpy arrays in the reference's numbering."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        st = lib().pnp_ctx_create(device, C.byref(self._h))
+        if st != 0:
+            raise PnpError(st, "cannot create a context on CUDA device %d (no CPU fallback exists)" % device)
+
+    def close(self):
+        if self._h:
+            lib().pnp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise PnpError(st, lib().pnp_last_error(self._h).decode())
+
+    def launch_count(self):
+        return lib().pnp_launch_count(self._h)
+
+    # ---- mesh ----
+    def mesh_set(self, x, y, tri, ba, bb, bphys):
+        x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+        tri = np.ascontiguousarray(tri, dtype=np.int32); ba = np.ascontiguousarray(ba, dtype=np.int32)
+        bb = np.ascontiguousarray(bb, dtype=np.int32); bphys = np.ascontiguousarray(bphys, dtype=np.int32)
+        self._ck(lib().pnp_mesh_set(self._h, C.c_long(len(x)), _d(x), _d(y), C.c_long(len(tri)), _i(tri), C.c_long(len(ba)),
+                                    _i(ba), _i(bb), _i(bphys)))
+
+    def mesh_read_gmsh(self, path):
+        self._ck(lib().pnp_mesh_read_gmsh(self._h, path.encode()))
+
+    def mesh_refine(self, levels):
+        self._ck(lib().pnp_mesh_refine(self._h, levels))
+
+    def mesh_finalize(self, renumber=True):
+        self._ck(lib().pnp_mesh_finalize(self._h, int(renumber)))
+
+    def mesh_sizes(self):
+        v = [C.c_long() for _ in range(4)]
+        self._ck(lib().pnp_mesh_sizes(self._h, *[C.byref(a) for a in v]))
+        return dict(nv=v[0].value, nT=v[1].value, nB=v[2].value, nslots=v[3].value)
+
+    def mesh_get(self):
+        s = self.mesh_sizes()
+        x = np.zeros(s["nv"]); y = np.zeros(s["nv"]); tri = np.zeros((s["nT"], 3), dtype=np.int32)
+        ba = np.zeros(s["nB"], dtype=np.int32); bb = np.zeros(s["nB"], dtype=np.int32); ph = np.zeros(s["nB"], dtype=np.int32)
+        self._ck(lib().pnp_mesh_get(self._h, _d(x), _d(y), _i(tri), _i(ba), _i(bb), _i(ph)))
+        return dict(x=x, y=y, tri=tri, ba=ba, bb=bb, bphys=ph)
+
+    # ---- parameters ----
+    def params_set(self, sys, surf):
+        sys = np.ascontiguousarray(sys, dtype=np.float64); surf = np.ascontiguousarray(surf, dtype=np.float64)
+        self._ck(lib().pnp_params_set(self._h, _d(sys), _d(surf)))
+
+    def params_read(self, path):
+        self._ck(lib().pnp_params_read(self._h, path.encode()))
+
+    def params_get(self):
+        sys = np.zeros(16)
+        self._ck(lib().pnp_params_get(self._h, _d(sys), None, None, 0))
+        surf = np.zeros((int(sys[0]), 9)); buf = C.create_string_buffer(512)
+        self._ck(lib().pnp_params_get(self._h, _d(sys), _d(surf), buf, 512))
+        return sys, surf, buf.value.decode()
+
+    # ---- operators / vectors / matrices ----
+    def operator(self, op, comp0=0):
+        h = C.c_int()
+        self._ck(lib().pnp_operator_create(self._h, op, comp0, C.byref(h)))
+        return h.value
+
+    def operator_set_coefficient(self, op, which, vec):
+        self._ck(lib().pnp_operator_set_coefficient(self._h, op, which, vec))
+
+    def operator_set_valency(self, op, valency):
+        self._ck(lib().pnp_operator_set_valency(self._h, op, C.c_double(valency)))
+
+    def constraints(self, op, fields):
+        out = np.zeros(fields * self.mesh_sizes()["nv"], dtype=np.int8)
+        self._ck(lib().pnp_constraints_get(self._h, op, out.ctypes.data_as(C.c_char_p)))
+        return out.astype(bool)
+
+    def pattern(self, op, fields):
+        nv = self.mesh_sizes()["nv"]
+        nnz = C.c_long(); rowptr = np.zeros(fields * nv + 1, dtype=np.int32)
+        self._ck(lib().pnp_pattern_get(self._h, op, C.byref(nnz), _i(rowptr), None))
+        col = np.zeros(nnz.value, dtype=np.int32)
+        self._ck(lib().pnp_pattern_get(self._h, op, C.byref(nnz), _i(rowptr), _i(col)))
+        return rowptr, col
+
+    def vec(self, fields, host=None):
+        h = C.c_int()
+        self._ck(lib().pnp_vec_create(self._h, fields, C.byref(h)))
+        if host is not None:
+            self.upload(h.value, host)
+        return h.value
+
+    def vec_destroy(self, v):
+        self._ck(lib().pnp_vec_destroy(self._h, v))
+
+    def upload(self, v, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        self._ck(lib().pnp_vec_upload(self._h, v, _d(host)))
+
+    def download(self, v, fields):
+        out = np.zeros(fields * self.mesh_sizes()["nv"])
+        self._ck(lib().pnp_vec_download(self._h, v, _d(out)))
+        return out
+
+    def vec_set(self, v, value):
+        self._ck(lib().pnp_vec_set(self._h, v, C.c_double(value)))
+
+    def vec_copy(self, dst, src):
+        self._ck(lib().pnp_vec_copy(self._h, dst, src))
+
+    def axpy(self, y, a, x):
+        self._ck(lib().pnp_vec_axpy(self._h, y, C.c_double(a), x))
+
+    def norm(self, x):
+        out = C.c_double()
+        self._ck(lib().pnp_vec_norm(self._h, x, C.byref(out)))
+        return out.value
+
+    def dot(self, x, y):
+        out = C.c_double()
+        self._ck(lib().pnp_vec_dot(self._h, x, y, C.byref(out)))
+        return out.value
+
+    def pack3(self, dst3, phi, cp, cm):
+        self._ck(lib().pnp_vec_pack3(self._h, dst3, phi, cp, cm))
+
+    def extract(self, src3, field, dst1):
+        self._ck(lib().pnp_vec_extract(self._h, src3, field, dst1))
+
+    def matrix(self, op):
+        h = C.c_int()
+        self._ck(lib().pnp_matrix_create(self._h, op, C.byref(h)))
+        return h.value
+
+    def matrix_destroy(self, m):
+        self._ck(lib().pnp_matrix_destroy(self._h, m))
+
+    def residual(self, op, u, r):
+        self._ck(lib().pnp_residual(self._h, op, u, r))
+
+    def jacobian(self, op, u, A, mode=JAC_FD_FAITHFUL, eps=1e-11):
+        self._ck(lib().pnp_jacobian(self._h, op, u, A, mode, C.c_double(eps)))
+
+    def matrix_values(self, op, A, nnz):
+        val = np.zeros(nnz)
+        self._ck(lib().pnp_matrix_values_get(self._h, op, A, _d(val)))
+        return val
+
+    def spmv(self, A, x, y):
+        self._ck(lib().pnp_spmv(self._h, A, x, y))
+
+    # ---- solvers ----
+    def solver(self, kind=SOLVER_BCGS, prec=PREC_NONE, maxit=5000, prec_steps=1, verbosity=0):
+        h = C.c_int()
+        self._ck(lib().pnp_solver_create(self._h, kind, prec, maxit, prec_steps, verbosity, C.byref(h)))
+        return h.value
+
+    def solve(self, solver, A, z, r, reduction):
+        res = LinResult()
+        self._ck(lib().pnp_solver_apply(self._h, solver, A, z, r, C.c_double(reduction), C.byref(res)))
+        return res
+
+    def newton_opts(self, **kw):
+        o = NewtonOpts()
+        self._ck(lib().pnp_newton_opts_from_params(self._h, C.byref(o)))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def newton(self, op, u, solver, opts, check=True):
+        res = NewtonResult()
+        st = lib().pnp_newton_apply(self._h, op, u, solver, C.byref(opts), C.byref(res))
+        if check:
+            self._ck(st)
+        return st, res
+
+    def slp(self, op, u, solver, reduction, jac_mode=JAC_FD_FAITHFUL, eps=1e-11):
+        res = LinResult()
+        self._ck(lib().pnp_slp_apply(self._h, op, u, solver, C.c_double(reduction), jac_mode, C.c_double(eps), C.byref(res)))
+        return res
+
+    def interpolate_bcext(self, component, pb_vec, out_vec):
+        self._ck(lib().pnp_interpolate_bcext(self._h, component, -1 if pb_vec is None else pb_vec, out_vec))

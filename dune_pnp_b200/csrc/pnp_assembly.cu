@@ -1,0 +1,130 @@
+// pnp_assembly.cu -- residual and Jacobian assembly kernels (fp64, vertex-parallel gather).
+//
+// Replaces GridOperator::residual / GridOperator::jacobian driving the reference's local operators
+// (/root/reference/src/stationary_pnp.hh:240-246; instationary_pnp_from_pb_md.hh:183-186,343-366):
+// one thread owns one vertex row, walks the vertex star, recomputes the incident element integrals
+// for its own test function and writes each result exactly once.  HBM-bound: per vertex it streams
+// the ring (4 B/slot), gathers coordinates and coefficients (L1/L2 hits after the locality
+// renumbering) and writes F residual entries or NPLANES*rowlen matrix values.
+//
+// Compiled with -fmad=false: the FD-faithful path must round like the CPU restatement.
+#include "pnp_common.cuh"
+
+namespace pnp {
+
+namespace {
+
+template <int OP>
+__global__ void __launch_bounds__(128)
+k_residual(StarView M, PhysParams P, const double* __restrict__ u, const double* __restrict__ aux0,
+           const double* __restrict__ aux1, int comp0, double* __restrict__ r) {
+  constexpr int F = OpTraits<OP>::F;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < M.nv; v += gridDim.x * blockDim.x) {
+    double out[F];
+    residual_row<OP>(M, P, u, aux0, aux1, v, out);
+    const unsigned db = dir_bits<OP>(M, v, comp0);
+#pragma unroll
+    for (int k = 0; k < F; k++) r[(long)F * v + k] = ((db >> k) & 1u) ? 0.0 : out[k]; // constrain_residual
+  }
+}
+
+template <int OP, int MODE>
+__global__ void __launch_bounds__(128)
+k_jacobian(StarView M, PhysParams P, const double* __restrict__ u, const double* __restrict__ aux0,
+           const double* __restrict__ aux1, double eps, int comp0, double* __restrict__ vals, long stride) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < M.nv; v += gridDim.x * blockDim.x)
+    jacobian_row<OP, MODE>(M, P, u, aux0, aux1, eps, comp0, v, vals, stride);
+}
+
+// alpha_boundary: one thread per vertex that occurs in a boundary face (boundary_vertex_sum, pnp_star.cuh)
+__global__ void k_boundary(StarView M, PhysParams P, const BFace* __restrict__ faces, const int* __restrict__ bv,
+                           const int* __restrict__ ptr, const int* __restrict__ items, int n_bv,
+                           const double* __restrict__ surf_flux, const unsigned char* __restrict__ surf_dir, int F,
+                           int comp0, double* __restrict__ r) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_bv) return;
+  double acc[3];
+  boundary_vertex_sum(M, P, faces, items, ptr[t], ptr[t + 1], surf_flux, surf_dir, F, comp0, acc);
+  const int v = bv[t];
+  const unsigned m = M.dmask[v];
+  for (int k = 0; k < F; k++) {
+    const int comp = F == 3 ? k : comp0;
+    if (!((m >> comp) & 1u)) r[(long)F * v + k] += acc[k];
+  }
+}
+
+} // namespace
+
+static void coefficient_ptrs(Ctx& c, const Operator& op, const double** a0, const double** a1) {
+  *a0 = *a1 = nullptr;
+  const int need = op.op == OP_POISSON ? 2 : (op.op == OP_DIFFUSION ? 1 : 0);
+  if (need >= 1) {
+    PNP_REQUIRE(op.aux0 >= 0, PNP_E_ARG, "operator coefficient 0 not set");
+    PNP_REQUIRE(c.vec(op.aux0).fields == 1, PNP_E_ARG, "coefficient must be a 1-field vector");
+    *a0 = c.vec(op.aux0).d.p;
+  }
+  if (need >= 2) {
+    PNP_REQUIRE(op.aux1 >= 0, PNP_E_ARG, "operator coefficient 1 not set");
+    PNP_REQUIRE(c.vec(op.aux1).fields == 1, PNP_E_ARG, "coefficient must be a 1-field vector");
+    *a1 = c.vec(op.aux1).d.p;
+  }
+}
+
+void assemble_residual(Ctx& c, const Operator& op, const Vec& u, Vec& r) {
+  PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built (mesh finalized + parameters set?)");
+  const int F = op_fields(op.op);
+  PNP_REQUIRE(u.fields == F && r.fields == F, PNP_E_ARG, "vector field count does not match the operator");
+  const double *a0, *a1;
+  coefficient_ptrs(c, op, &a0, &a1);
+  const StarView M = c.star();
+  const PhysParams P = c.phys(op.valency);
+  const int block = 128, grid = grid_for(c.nv, block, c.sm_count * 16);
+  switch (op.op) {
+    case OP_PB: k_residual<OP_PB><<<grid, block, 0, c.stream>>>(M, P, u.d.p, a0, a1, op.comp0, r.d.p); break;
+    case OP_POISSON: k_residual<OP_POISSON><<<grid, block, 0, c.stream>>>(M, P, u.d.p, a0, a1, op.comp0, r.d.p); break;
+    case OP_DIFFUSION: k_residual<OP_DIFFUSION><<<grid, block, 0, c.stream>>>(M, P, u.d.p, a0, a1, op.comp0, r.d.p); break;
+    case OP_MASS: k_residual<OP_MASS><<<grid, block, 0, c.stream>>>(M, P, u.d.p, a0, a1, op.comp0, r.d.p); break;
+    case OP_PNP: k_residual<OP_PNP><<<grid, block, 0, c.stream>>>(M, P, u.d.p, a0, a1, op.comp0, r.d.p); break;
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
+  }
+  PNP_CHECK_LAUNCH(); c.launches++;
+  // doAlphaBoundary is false for the diffusion and mass operators (diffusion_operator.hh:34)
+  if ((op.op == OP_PB || op.op == OP_POISSON || op.op == OP_PNP) && c.n_bv > 0) {
+    // Poisson is constructed with the PB BCType (component 0): instationary_pnp_from_pb_md.hh:343-344
+    k_boundary<<<(c.n_bv + 127) / 128, 128, 0, c.stream>>>(M, P, c.d_bfaces.p, c.d_bv.p, c.d_bv_ptr.p, c.d_bv_items.p,
+                                                          c.n_bv, c.d_surf.p, c.d_surf_dir.p, F, op.comp0, r.d.p);
+    PNP_CHECK_LAUNCH(); c.launches++;
+  }
+}
+
+template <int OP>
+static void launch_jac(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A,
+                       int mode, double eps) {
+  const StarView M = c.star();
+  const PhysParams P = c.phys(op.valency);
+  const int block = 128, grid = grid_for(c.nv, block, c.sm_count * 16);
+  if (mode == JAC_FD_FAITHFUL)
+    k_jacobian<OP, JAC_FD_FAITHFUL><<<grid, block, 0, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, A.vals.p, c.nslots);
+  else
+    k_jacobian<OP, JAC_ANALYTIC><<<grid, block, 0, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, A.vals.p, c.nslots);
+  PNP_CHECK_LAUNCH(); c.launches++;
+}
+
+void assemble_jacobian(Ctx& c, const Operator& op, const Vec& u, Matrix& A, int mode, double eps) {
+  PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built (mesh finalized + parameters set?)");
+  PNP_REQUIRE(u.fields == op_fields(op.op), PNP_E_ARG, "vector field count does not match the operator");
+  PNP_REQUIRE(A.op == op.op, PNP_E_ARG, "matrix belongs to another operator type");
+  PNP_REQUIRE(mode == JAC_FD_FAITHFUL || mode == JAC_ANALYTIC, PNP_E_ARG, "unknown jacobian mode");
+  const double *a0, *a1;
+  coefficient_ptrs(c, op, &a0, &a1);
+  switch (op.op) {
+    case OP_PB: launch_jac<OP_PB>(c, op, u.d.p, a0, a1, A, mode, eps); break;
+    case OP_POISSON: launch_jac<OP_POISSON>(c, op, u.d.p, a0, a1, A, mode, eps); break;
+    case OP_DIFFUSION: launch_jac<OP_DIFFUSION>(c, op, u.d.p, a0, a1, A, mode, eps); break;
+    case OP_MASS: launch_jac<OP_MASS>(c, op, u.d.p, a0, a1, A, mode, eps); break;
+    case OP_PNP: launch_jac<OP_PNP>(c, op, u.d.p, a0, a1, A, mode, eps); break;
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
+  }
+}
+
+} // namespace pnp

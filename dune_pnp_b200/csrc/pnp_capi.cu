@@ -1,0 +1,341 @@
+// pnp_capi.cu -- extern "C" entry points declared in include/pnp_b200.h.  No exception leaves this file.
+#include <cstring>
+
+#include "pnp_common.cuh"
+
+namespace pnp {
+int newton_apply(Ctx&, const Operator&, Vec&, Solver&, const pnp_newton_opts&, pnp_newton_result&);
+LinResult slp_apply(Ctx&, const Operator&, Vec&, Solver&, double, int, double);
+namespace {
+__global__ void k_fill(double* x, long n, double v) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] = v;
+}
+__global__ void k_pack3(const double* a, const double* b, const double* c, long nv, double* out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
+    out[3 * i] = a[i]; out[3 * i + 1] = b[i]; out[3 * i + 2] = c[i];
+  }
+}
+__global__ void k_extract(const double* in, long nv, int field, double* out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) out[i] = in[3 * i + field];
+}
+void to_lin(const LinResult& lr, pnp_lin_result* out) {
+  if (!out) return;
+  out->converged = lr.converged; out->iterations = lr.iterations; out->reduction = lr.reduction;
+  out->conv_rate = lr.conv_rate; out->seconds = lr.seconds; out->status = lr.status;
+}
+} // namespace
+} // namespace pnp
+
+using namespace pnp;
+
+struct pnp_ctx { Ctx c; };
+
+#define API_BEGIN(ctx)                                  \
+  if (!(ctx)) return PNP_E_ARG;                         \
+  Ctx& c = (ctx)->c;                                    \
+  try {                                                 \
+    PNP_CUDA(cudaSetDevice(c.device));
+#define API_END                                                      \
+    return PNP_OK;                                                   \
+  } catch (const pnp::Error& e) { c.err = e.what(); return e.code; } \
+  catch (const std::exception& e) { c.err = e.what(); return PNP_E_ARG; }
+
+extern "C" {
+
+pnp_status pnp_ctx_create(int device, pnp_ctx** out) {
+  if (!out) return PNP_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  // no CPU fallback: without a CUDA device there is no context
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return PNP_E_CUDA;
+  pnp_ctx* h = new pnp_ctx;
+  h->c.device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&h->c.stream) != cudaSuccess) { delete h; return PNP_E_CUDA; }
+  cudaDeviceGetAttribute(&h->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  *out = h;
+  return PNP_OK;
+}
+void pnp_ctx_destroy(pnp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  if (ctx->c.h_red) cudaFreeHost(ctx->c.h_red);
+  cudaStream_t s = ctx->c.stream;
+  delete ctx;
+  if (s) cudaStreamDestroy(s);
+}
+const char* pnp_last_error(pnp_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
+long pnp_launch_count(pnp_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+pnp_status pnp_mesh_set(pnp_ctx* ctx, long nv, const double* x, const double* y, long nT, const int* tri, long nB,
+                        const int* ba, const int* bb, const int* bphys) {
+  API_BEGIN(ctx) mesh_set(c, nv, x, y, nT, tri, nB, ba, bb, bphys); API_END
+}
+pnp_status pnp_mesh_read_gmsh(pnp_ctx* ctx, const char* path) {
+  API_BEGIN(ctx)
+  std::vector<double> x, y; std::vector<int> tri, ba, bb, ph;
+  read_gmsh_file(path, x, y, tri, ba, bb, ph);
+  mesh_set(c, (long)x.size(), x.data(), y.data(), (long)tri.size() / 3, tri.data(), (long)ba.size(), ba.data(), bb.data(),
+           ph.data());
+  API_END
+}
+pnp_status pnp_mesh_refine(pnp_ctx* ctx, int levels) { API_BEGIN(ctx) mesh_refine(c, levels); API_END }
+pnp_status pnp_mesh_finalize(pnp_ctx* ctx, int renumber) { API_BEGIN(ctx) mesh_finalize(c, renumber != 0); API_END }
+pnp_status pnp_mesh_sizes(pnp_ctx* ctx, long* nv, long* nT, long* nB, long* nslots) {
+  API_BEGIN(ctx)
+  if (nv) *nv = c.nv; if (nT) *nT = c.nT; if (nB) *nB = c.nB; if (nslots) *nslots = c.finalized ? c.nslots : 0;
+  API_END
+}
+pnp_status pnp_mesh_get(pnp_ctx* ctx, double* x, double* y, int* tri, int* ba, int* bb, int* bphys) {
+  API_BEGIN(ctx)
+  if (x) c.cx.download(x, c.nv, c.stream);
+  if (y) c.cy.download(y, c.nv, c.stream);
+  if (tri) c.ctri.download(tri, 3 * c.nT, c.stream);
+  if (ba) c.cba.download(ba, c.nB, c.stream);
+  if (bb) c.cbb.download(bb, c.nB, c.stream);
+  if (bphys) c.cbphys.download(bphys, c.nB, c.stream);
+  API_END
+}
+
+pnp_status pnp_params_set(pnp_ctx* ctx, const double* sys, const double* surf) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(sys && (sys[0] == 0 || surf), PNP_E_ARG, "null parameter arrays");
+  HostParams p;
+  p.n_surfaces = (int)sys[0]; p.cylindrical = sys[1] != 0; p.l_b = sys[2]; p.c0 = sys[3]; p.PI = sys[4];
+  p.linearSolverIterations = (int)sys[5]; p.newtonReassembleThreshold = sys[6]; p.newtonReduction = sys[7];
+  p.newtonMinLinearReduction = sys[8]; p.newtonMaxIterations = sys[9]; p.newtonLineSearchMaxIteration = sys[10];
+  p.tau = sys[11]; p.nSteps = (int)sys[12]; p.outputFreq = (int)sys[13]; p.potentialUpdateFreq = (int)sys[14];
+  p.verbosity = (int)sys[15];
+  PNP_REQUIRE(p.n_surfaces >= 0, PNP_E_CONFIG, "n_surfaces must be non-negative");
+  p.surfaces.assign(p.n_surfaces, HostSurface());
+  for (int i = 0; i < p.n_surfaces; i++)
+    for (int k = 0; k < 3; k++) {
+      p.surfaces[i].btype[k] = (int)surf[9 * i + 3 * k];
+      p.surfaces[i].flux[k] = surf[9 * i + 3 * k + 1];
+      p.surfaces[i].dval[k] = surf[9 * i + 3 * k + 2];
+    }
+  p.set = true;
+  c.params = p;
+  c.constraints_built = false;
+  if (c.finalized) constraints_build(c);
+  API_END
+}
+pnp_status pnp_params_read(pnp_ctx* ctx, const char* cfg_path) {
+  API_BEGIN(ctx)
+  read_config_file(cfg_path, c.params);
+  c.constraints_built = false;
+  if (c.finalized) constraints_build(c);
+  API_END
+}
+pnp_status pnp_params_get(pnp_ctx* ctx, double* sys, double* surf, char* meshfile, int meshfile_cap) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.params.set, PNP_E_ARG, "parameters not set");
+  const HostParams& p = c.params;
+  const double v[16] = {(double)p.n_surfaces, (double)p.cylindrical, p.l_b, p.c0, p.PI, (double)p.linearSolverIterations,
+                        p.newtonReassembleThreshold, p.newtonReduction, p.newtonMinLinearReduction, p.newtonMaxIterations,
+                        p.newtonLineSearchMaxIteration, p.tau, (double)p.nSteps, (double)p.outputFreq,
+                        (double)p.potentialUpdateFreq, (double)p.verbosity};
+  if (sys) std::memcpy(sys, v, sizeof v);
+  if (surf)
+    for (int i = 0; i < p.n_surfaces; i++)
+      for (int k = 0; k < 3; k++) {
+        surf[9 * i + 3 * k] = p.surfaces[i].btype[k];
+        surf[9 * i + 3 * k + 1] = p.surfaces[i].flux[k];
+        surf[9 * i + 3 * k + 2] = p.surfaces[i].dval[k];
+      }
+  if (meshfile && meshfile_cap > 0) { std::strncpy(meshfile, p.meshfile.c_str(), meshfile_cap - 1); meshfile[meshfile_cap - 1] = 0; }
+  API_END
+}
+pnp_status pnp_constraints_build(pnp_ctx* ctx) { API_BEGIN(ctx) constraints_build(c); API_END }
+
+pnp_status pnp_operator_create(pnp_ctx* ctx, int op, int comp0, int* handle) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(op >= PNP_OP_PB && op <= PNP_OP_PNP && comp0 >= 0 && comp0 < 3 && handle, PNP_E_ARG, "bad operator arguments");
+  auto o = std::make_unique<Operator>();
+  o->op = op; o->comp0 = comp0;
+  c.ops.push_back(std::move(o));
+  *handle = (int)c.ops.size() - 1;
+  API_END
+}
+pnp_status pnp_operator_set_coefficient(pnp_ctx* ctx, int h, int which, int vec_handle) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(which == 0 || which == 1, PNP_E_ARG, "coefficient index must be 0 or 1");
+  c.vec(vec_handle);
+  (which == 0 ? c.oper(h).aux0 : c.oper(h).aux1) = vec_handle;
+  API_END
+}
+pnp_status pnp_operator_set_valency(pnp_ctx* ctx, int h, double valency) { API_BEGIN(ctx) c.oper(h).valency = valency; API_END }
+pnp_status pnp_constraints_get(pnp_ctx* ctx, int h, char* out) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built");
+  const Operator& op = c.oper(h);
+  const int F = op_fields(op.op);
+  std::vector<unsigned char> m = c.dmask.to_host(c.stream);
+  std::vector<int> i2e = c.int2ext.to_host(c.stream);
+  for (long v = 0; v < c.nv; v++)
+    for (int k = 0; k < F; k++) out[(long)k * c.nv + i2e[v]] = (char)((m[v] >> (F == 3 ? k : op.comp0)) & 1);
+  API_END
+}
+pnp_status pnp_pattern_get(pnp_ctx* ctx, int h, long* nnz, int* rowptr, int* col) {
+  API_BEGIN(ctx)
+  long n = pattern_export(c, h, rowptr, col);
+  if (nnz) *nnz = n;
+  API_END
+}
+
+pnp_status pnp_vec_create(pnp_ctx* ctx, int fields, int* handle) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
+  PNP_REQUIRE((fields == 1 || fields == 3) && handle, PNP_E_ARG, "fields must be 1 or 3");
+  auto v = std::make_unique<Vec>();
+  v->fields = fields; v->d.alloc((size_t)fields * c.nv); v->d.zero(c.stream);
+  c.vecs.push_back(std::move(v));
+  *handle = (int)c.vecs.size() - 1;
+  API_END
+}
+pnp_status pnp_vec_destroy(pnp_ctx* ctx, int h) { API_BEGIN(ctx) c.vec(h); c.vecs[h].reset(); API_END }
+pnp_status pnp_vec_upload(pnp_ctx* ctx, int h, const double* host) { API_BEGIN(ctx) vec_upload(c, c.vec(h), host); API_END }
+pnp_status pnp_vec_download(pnp_ctx* ctx, int h, double* host) { API_BEGIN(ctx) vec_download(c, c.vec(h), host); API_END }
+pnp_status pnp_vec_set(pnp_ctx* ctx, int h, double value) {
+  API_BEGIN(ctx)
+  Vec& v = c.vec(h);
+  k_fill<<<grid_for((long)v.d.n, 256), 256, 0, c.stream>>>(v.d.p, (long)v.d.n, value);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  API_END
+}
+pnp_status pnp_vec_copy(pnp_ctx* ctx, int dst, int src) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.vec(dst).d.n == c.vec(src).d.n, PNP_E_ARG, "vector sizes differ");
+  vec_copy(c, c.vec(src).d.p, c.vec(dst).d.p, (long)c.vec(src).d.n);
+  API_END
+}
+pnp_status pnp_vec_axpy(pnp_ctx* ctx, int y, double a, int x) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.vec(y).d.n == c.vec(x).d.n, PNP_E_ARG, "vector sizes differ");
+  vec_axpy(c, a, c.vec(x).d.p, c.vec(y).d.p, (long)c.vec(x).d.n);
+  API_END
+}
+pnp_status pnp_vec_norm(pnp_ctx* ctx, int x, double* out) {
+  API_BEGIN(ctx) *out = vec_norm(c, c.vec(x).d.p, (long)c.vec(x).d.n); API_END
+}
+pnp_status pnp_vec_dot(pnp_ctx* ctx, int x, int y, double* out) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.vec(y).d.n == c.vec(x).d.n, PNP_E_ARG, "vector sizes differ");
+  *out = vec_dot(c, c.vec(x).d.p, c.vec(y).d.p, (long)c.vec(x).d.n);
+  API_END
+}
+pnp_status pnp_vec_pack3(pnp_ctx* ctx, int dst3, int phi, int cp, int cm) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.vec(dst3).fields == 3 && c.vec(phi).fields == 1 && c.vec(cp).fields == 1 && c.vec(cm).fields == 1,
+              PNP_E_ARG, "pack3 needs one 3-field and three 1-field vectors");
+  k_pack3<<<grid_for(c.nv, 256), 256, 0, c.stream>>>(c.vec(phi).d.p, c.vec(cp).d.p, c.vec(cm).d.p, c.nv, c.vec(dst3).d.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  API_END
+}
+pnp_status pnp_vec_extract(pnp_ctx* ctx, int src3, int field, int dst1) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.vec(src3).fields == 3 && c.vec(dst1).fields == 1 && field >= 0 && field < 3, PNP_E_ARG, "bad extract arguments");
+  k_extract<<<grid_for(c.nv, 256), 256, 0, c.stream>>>(c.vec(src3).d.p, c.nv, field, c.vec(dst1).d.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  API_END
+}
+
+pnp_status pnp_matrix_create(pnp_ctx* ctx, int op_handle, int* handle) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.finalized && handle, PNP_E_ARG, "mesh not finalized");
+  auto m = std::make_unique<Matrix>();
+  m->op = c.oper(op_handle).op; m->nplanes = op_planes(m->op);
+  m->vals.alloc((size_t)m->nplanes * c.nslots); m->vals.zero(c.stream);
+  c.mats.push_back(std::move(m));
+  *handle = (int)c.mats.size() - 1;
+  API_END
+}
+pnp_status pnp_matrix_destroy(pnp_ctx* ctx, int h) { API_BEGIN(ctx) c.mat(h); c.mats[h].reset(); API_END }
+pnp_status pnp_residual(pnp_ctx* ctx, int op, int u, int r) {
+  API_BEGIN(ctx)
+  assemble_residual(c, c.oper(op), c.vec(u), c.vec(r));
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+pnp_status pnp_jacobian(pnp_ctx* ctx, int op, int u, int A, int mode, double eps) {
+  API_BEGIN(ctx)
+  assemble_jacobian(c, c.oper(op), c.vec(u), c.mat(A), mode, eps);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+pnp_status pnp_matrix_values_get(pnp_ctx* ctx, int op, int A, double* val) {
+  API_BEGIN(ctx) matrix_export(c, op, c.mat(A), val); API_END
+}
+pnp_status pnp_spmv(pnp_ctx* ctx, int A, int x, int y) {
+  API_BEGIN(ctx)
+  const Matrix& M = c.mat(A);
+  PNP_REQUIRE(c.vec(x).fields == (M.nplanes == 1 ? 1 : 3) && c.vec(y).fields == c.vec(x).fields && x != y, PNP_E_ARG,
+              "spmv operands do not match the matrix");
+  spmv(c, M, c.vec(x).d.p, c.vec(y).d.p);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+pnp_status pnp_solver_create(pnp_ctx* ctx, int kind, int prec, int maxit, int prec_steps, int verbosity, int* handle) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE((kind == PNP_SOLVER_BCGS || kind == PNP_SOLVER_CG) && prec >= PNP_PREC_NONE && prec <= PNP_PREC_AMG && handle,
+              PNP_E_ARG, "bad solver arguments");
+  auto s = std::make_unique<Solver>();
+  s->kind = kind; s->prec = prec; s->maxit = maxit; s->prec_steps = prec_steps; s->verbosity = verbosity;
+  c.solvers.push_back(std::move(s));
+  *handle = (int)c.solvers.size() - 1;
+  API_END
+}
+pnp_status pnp_solver_apply(pnp_ctx* ctx, int s, int A, int z, int r, double reduction, pnp_lin_result* out) {
+  API_BEGIN(ctx)
+  LinResult lr = solver_apply(c, c.solver(s), c.mat(A), c.vec(z), c.vec(r), reduction);
+  to_lin(lr, out);
+  if (lr.status == PNP_E_BREAKDOWN) { c.err = "BiCGSTAB breakdown (rho, omega or h vanished)"; return PNP_E_BREAKDOWN; }
+  if (lr.status == PNP_E_NAN) { c.err = "non-finite residual norm in the linear solver"; return PNP_E_NAN; }
+  API_END
+}
+
+void pnp_newton_opts_default(pnp_newton_opts* o) {
+  if (!o) return;
+  // PDELab Newton defaults
+  o->reduction = 1e-8; o->abs_limit = 1e-12; o->min_linear_reduction = 1e-3; o->reassemble_threshold = 0.0;
+  o->max_iterations = 40; o->line_search_max_iterations = 10; o->damping = 0.5;
+  o->jac_mode = PNP_JAC_FD_FAITHFUL; o->fd_epsilon = 1e-11; o->verbosity = 0;
+}
+pnp_status pnp_newton_opts_from_params(pnp_ctx* ctx, pnp_newton_opts* o) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.params.set && o, PNP_E_ARG, "parameters not set");
+  pnp_newton_opts_default(o);
+  o->reassemble_threshold = c.params.newtonReassembleThreshold;
+  o->reduction = c.params.newtonReduction;
+  o->min_linear_reduction = c.params.newtonMinLinearReduction;
+  o->max_iterations = (int)c.params.newtonMaxIterations;                       // stored as double (quirk B10)
+  o->line_search_max_iterations = (int)c.params.newtonLineSearchMaxIteration;
+  o->verbosity = c.params.verbosity;
+  API_END
+}
+pnp_status pnp_newton_apply(pnp_ctx* ctx, int op, int u, int solver, const pnp_newton_opts* o, pnp_newton_result* res) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(o && res, PNP_E_ARG, "null options/result");
+  int st = newton_apply(c, c.oper(op), c.vec(u), c.solver(solver), *o, *res);
+  if (st != PNP_OK) {
+    static const char* msg[] = {"", "Newton did not converge within max_iterations", "linear solver did not converge",
+                                "line search failed", "defect is not finite", "BiCGSTAB breakdown"};
+    c.err = msg[st <= 5 ? st : 0];
+    return st;
+  }
+  API_END
+}
+pnp_status pnp_slp_apply(pnp_ctx* ctx, int op, int u, int solver, double reduction, int jac_mode, double eps,
+                         pnp_lin_result* out) {
+  API_BEGIN(ctx)
+  LinResult lr = slp_apply(c, c.oper(op), c.vec(u), c.solver(solver), reduction, jac_mode, eps);
+  to_lin(lr, out);
+  API_END
+}
+pnp_status pnp_interpolate_bcext(pnp_ctx* ctx, int component, int pb_vec, int out_vec) {
+  API_BEGIN(ctx)
+  interpolate_bcext(c, component, pb_vec >= 0 ? &c.vec(pb_vec) : nullptr, c.vec(out_vec));
+  API_END
+}
+
+} // extern "C"

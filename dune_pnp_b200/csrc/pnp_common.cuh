@@ -1,0 +1,188 @@
+// pnp_common.cuh -- context, device buffers, error handling shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pnp_b200.h"
+#include "pnp_setup_algos.cuh"
+#include "pnp_star.cuh"
+
+namespace pnp {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PNP_CUDA(call)                                                                               \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      throw ::pnp::Error(PNP_E_CUDA, std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " +  \
+                                         #call + " -> " + cudaGetErrorString(e_));                   \
+  } while (0)
+#define PNP_CHECK_LAUNCH() PNP_CUDA(cudaGetLastError())
+#define PNP_REQUIRE(cond, code, msg)                                                                 \
+  do { if (!(cond)) throw ::pnp::Error(code, std::string(msg)); } while (0)
+
+// Plain owning device array.
+template <class T> struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  explicit DBuf(size_t n_) { alloc(n_); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  ~DBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t n_) {
+    release();
+    n = n_;
+    if (n) PNP_CUDA(cudaMalloc(&p, n * sizeof(T)));
+  }
+  void zero(cudaStream_t s) { if (n) PNP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const T* h, size_t cnt, cudaStream_t s) {
+    if (cnt) PNP_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void download(T* h, size_t cnt, cudaStream_t s) const {
+    if (cnt) PNP_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+  }
+  std::vector<T> to_host(cudaStream_t s) const { std::vector<T> h(n); download(h.data(), n, s); return h; }
+};
+
+inline int grid_for(long n, int block, int max_blocks = 148 * 32) {
+  long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  return (int)(g > max_blocks ? max_blocks : g);
+}
+
+// ---- host-side parameter set (Sysparams / Surface of the reference, sysparams.hh:10-57) ----
+struct HostSurface { int btype[3] = {1, 1, 1}; double flux[3] = {0, 0, 0}; double dval[3] = {0, 0, 0}; };
+struct HostParams {
+  bool set = false;
+  int n_surfaces = 0, verbosity = 0, cylindrical = 0;
+  double l_b = 1, c0 = 0.06, PI = 3.1415;
+  int linearSolverIterations = 50;
+  double newtonReassembleThreshold = 0, newtonReduction = 1e-5, newtonMinLinearReduction = 1e-5;
+  double newtonMaxIterations = 50, newtonLineSearchMaxIteration = 500, tau = 0.1;
+  int nSteps = 100, outputFreq = 1, potentialUpdateFreq = 1;
+  std::string meshfile;
+  std::vector<HostSurface> surfaces;
+};
+
+struct Vec {
+  int fields = 1;
+  DBuf<double> d; // vertex-blocked internal layout, fields*nv
+};
+struct Matrix {
+  int op = 0;
+  int nplanes = 1;
+  DBuf<double> vals; // nplanes * nslots
+};
+
+struct Operator {
+  int op = OP_PB;
+  int comp0 = 0;          // BC component of a scalar operator's BCType
+  double valency = 1.0;
+  int aux0 = -1, aux1 = -1; // vector handles of coefficient fields
+};
+
+struct Amg; // pnp_amg.cu
+
+struct Solver {
+  int kind = PNP_SOLVER_BCGS, prec = PNP_PREC_NONE, maxit = 5000, prec_steps = 1, verbosity = 0;
+  std::shared_ptr<Amg> amg;
+  DBuf<double> w[6]; // Krylov work vectors, sized on first use
+  DBuf<double> dinv; // Jacobi: inverse diagonal
+  void ensure(size_t n) { for (auto& b : w) if (b.n != n) b.alloc(n); if (dinv.n != n) dinv.alloc(n); }
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+  // canonical mesh, device resident (external numbering = Gmsh-compressed / refinement rule)
+  long nv = 0, nT = 0, nB = 0;
+  DBuf<double> cx, cy;
+  DBuf<int> ctri, cba, cbb, cbphys;
+  // star structure, internal numbering
+  bool finalized = false;
+  long nslots = 0;
+  DBuf<int> rp;
+  DBuf<unsigned> adj;
+  DBuf<XY> xy;
+  DBuf<unsigned char> dmask;
+  DBuf<int> int2ext, ext2int;
+  // boundary
+  std::vector<BFace> bfaces;           // host copy (O(sqrt N))
+  DBuf<BFace> d_bfaces;
+  DBuf<int> d_bv, d_bv_ptr, d_bv_items; // boundary-vertex incidence lists (vertex, ptr, face*4+role)
+  int n_bv = 0;
+  DBuf<double> d_surf;                 // per surface: flux[3]
+  DBuf<unsigned char> d_surf_dir;      // per surface: bit c = component c is Dirichlet there
+  HostParams params;
+  bool constraints_built = false;
+  long launches = 0;                   // kernels launched (bench.py reports gpu_launches)
+  // handle tables
+  std::vector<std::unique_ptr<Vec>> vecs;
+  std::vector<std::unique_ptr<Matrix>> mats;
+  std::vector<std::unique_ptr<Operator>> ops;
+  std::vector<std::unique_ptr<Solver>> solvers;
+  // scratch for reductions
+  DBuf<double> red_partial, red_out;
+  double* h_red = nullptr; // pinned
+
+  StarView star() const { return StarView{rp.p, adj.p, xy.p, dmask.p, (int)nv}; }
+  PhysParams phys(double valency) const {
+    PhysParams P; P.PI = params.PI; P.l_b = params.l_b; P.c0 = params.c0; P.valency = valency;
+    P.cylindrical = params.cylindrical; return P;
+  }
+  Vec& vec(int h) { PNP_REQUIRE(h >= 0 && h < (int)vecs.size() && vecs[h], PNP_E_ARG, "bad vector handle"); return *vecs[h]; }
+  Matrix& mat(int h) { PNP_REQUIRE(h >= 0 && h < (int)mats.size() && mats[h], PNP_E_ARG, "bad matrix handle"); return *mats[h]; }
+  Operator& oper(int h) { PNP_REQUIRE(h >= 0 && h < (int)ops.size() && ops[h], PNP_E_ARG, "bad operator handle"); return *ops[h]; }
+  Solver& solver(int h) { PNP_REQUIRE(h >= 0 && h < (int)solvers.size() && solvers[h], PNP_E_ARG, "bad solver handle"); return *solvers[h]; }
+};
+
+inline int op_fields(int op) { return op == OP_PNP ? 3 : 1; }
+inline int op_planes(int op) { return op == OP_PNP ? 7 : 1; }
+
+// ---- implemented across the translation units ----
+// pnp_setup.cu
+void mesh_set(Ctx&, long nv, const double* x, const double* y, long nT, const int* tri, long nB, const int* ba,
+              const int* bb, const int* bphys);
+void mesh_refine(Ctx&, int levels);
+void mesh_finalize(Ctx&, bool renumber);
+void constraints_build(Ctx&);
+void vec_upload(Ctx&, Vec&, const double* host_lex);
+void vec_download(Ctx&, const Vec&, double* host_lex);
+long pattern_export(Ctx&, int op_handle, int* rowptr, int* col);
+void matrix_export(Ctx&, int op_handle, const Matrix&, double* val);
+// pnp_host.cpp-like logic in pnp_hostside.cu
+void read_gmsh_file(const std::string& path, std::vector<double>& x, std::vector<double>& y, std::vector<int>& tri,
+                    std::vector<int>& ba, std::vector<int>& bb, std::vector<int>& bphys);
+void read_config_file(const std::string& path, HostParams& p);
+void interpolate_bcext(Ctx&, int comp, const Vec* pb, Vec& out);
+// pnp_assembly.cu
+void assemble_residual(Ctx&, const Operator&, const Vec& u, Vec& r);
+void assemble_jacobian(Ctx&, const Operator&, const Vec& u, Matrix& A, int mode, double eps);
+// pnp_linalg.cu
+void spmv(Ctx&, const Matrix& A, const double* x, double* y);
+double vec_norm(Ctx&, const double* x, long n);
+double vec_dot(Ctx&, const double* x, const double* y, long n);
+void vec_axpy(Ctx&, double a, const double* x, double* y, long n);
+void vec_copy(Ctx&, const double* x, double* y, long n);
+void vec_zero(Ctx&, double* x, long n);
+struct LinResult { bool converged = false; int iterations = 0; double reduction = 1, conv_rate = 1; int status = 0; double seconds = 0; };
+LinResult solver_apply(Ctx&, Solver&, const Matrix& A, Vec& z, Vec& r, double reduction);
+
+} // namespace pnp

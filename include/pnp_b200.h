@@ -1,0 +1,165 @@
+/* pnp_b200.h -- C ABI of the B200 backend for dune-pnp's Newton-step hot path.
+ *
+ * The reference (/root/reference, a DUNE/PDELab application) has no FFI: its drivers call C++
+ * templates of PDELab/ISTL directly.  Each entry point below names the reference call it stands in
+ * for (paths relative to /root/reference/src); INTEGRATION.md shows the PDELab-shaped C++ facade
+ * (include/pnp_b200/pdelab_facade.hh) a maintainer binds instead of the upstream templates.
+ *
+ * Conventions
+ *  - every function returns a pnp_status; the message of the last failure is pnp_last_error(ctx);
+ *    no C++ exception crosses this boundary.
+ *  - host arrays are copied; device memory is owned by the context; vectors/matrices/operators/
+ *    solvers are small integer handles valid for the life of the context.
+ *  - the numbering seen through this header is the reference's: vertex index = rank of the Gmsh node
+ *    id among nodes used by triangles (GmshReader), P1 dof = vertex index, 3-field dof =
+ *    field*nv + vertex (GridFunctionSpaceLexicographicMapper, stationary_pnp.hh:126-129).
+ *    Internally vertices are renumbered for locality and dofs are vertex-blocked.
+ *  - one context drives one GPU; calls are synchronous; a context is not re-entrant.
+ */
+#ifndef PNP_B200_H
+#define PNP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pnp_ctx pnp_ctx;
+typedef int pnp_status;
+
+enum {
+  PNP_OK = 0,
+  PNP_E_NOT_CONVERGED = 1, /* Dune::PDELab::NewtonNotConverged */
+  PNP_E_LINEAR_SOLVER = 2, /* NewtonLinearSolverError */
+  PNP_E_LINE_SEARCH = 3,   /* NewtonLineSearchError */
+  PNP_E_NAN = 4,           /* NewtonDefectError */
+  PNP_E_BREAKDOWN = 5,     /* Dune::ISTLError (BiCGSTAB rho/omega/h breakdown) */
+  PNP_E_CUDA = 6,
+  PNP_E_CONFIG = 7,        /* missing INI key / unreadable file (sysparams.cc:24-28) */
+  PNP_E_ARG = 8,
+  PNP_E_MESH = 9           /* degenerate / non-manifold / too large mesh */
+};
+
+/* local operators (files of the same name under /root/reference/src) */
+enum { PNP_OP_PB = 0, PNP_OP_POISSON = 1, PNP_OP_DIFFUSION = 2, PNP_OP_MASS = 3, PNP_OP_PNP = 4 };
+/* jacobian_volume flavour: the reference inherits NumericalJacobianVolume (pnp_operator.hh:24-27) */
+enum { PNP_JAC_FD_FAITHFUL = 0, PNP_JAC_ANALYTIC = 1 };
+/* ISTLBackend_NOVLP_* solver/preconditioner pairs (instationary_pnp_from_pb_md.hh:188-211) */
+enum { PNP_SOLVER_BCGS = 0, PNP_SOLVER_CG = 1 };
+enum { PNP_PREC_NONE = 0, PNP_PREC_JACOBI = 1, PNP_PREC_SSOR = 2, PNP_PREC_ILU0 = 3, PNP_PREC_AMG = 4 };
+
+/* ---- context ------------------------------------------------------------------------------ */
+pnp_status pnp_ctx_create(int device, pnp_ctx** out);
+void pnp_ctx_destroy(pnp_ctx* ctx);
+const char* pnp_last_error(pnp_ctx* ctx);
+/* number of CUDA kernels this context has launched so far */
+long pnp_launch_count(pnp_ctx* ctx);
+
+/* ---- mesh: GmshReader<UGGrid<2>>::read + createGrid (pnp_solver_main.cc:82-114) ---------- */
+pnp_status pnp_mesh_set(pnp_ctx*, long nv, const double* x, const double* y, long nT, const int* tri /*[nT][3]*/,
+                        long nB, const int* ba, const int* bb, const int* bphys);
+pnp_status pnp_mesh_read_gmsh(pnp_ctx*, const char* path);
+/* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
+pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
+/* builds the vertex-star structure; renumber != 0 reorders vertices internally for locality */
+pnp_status pnp_mesh_finalize(pnp_ctx*, int renumber);
+pnp_status pnp_mesh_sizes(pnp_ctx*, long* nv, long* nT, long* nB, long* nslots);
+pnp_status pnp_mesh_get(pnp_ctx*, double* x, double* y, int* tri, int* ba, int* bb, int* bphys);
+
+/* ---- parameters: Sysparams::readConfigFile (sysparams.cc:15-98) --------------------------- */
+/* sys[16] = {n_surfaces, cylindrical, l_b, c0, PI, linearSolverIterations, newtonReassembleThreshold,
+ *            newtonReduction, newtonMinLinearReduction, newtonMaxIterations,
+ *            newtonLineSearchMaxIteration, tau, nSteps, outputFreq, potentialUpdateFreq, verbosity}
+ * surf[n_surfaces][9] = per BC component {coulomb, plusDiffusion, minusDiffusion}: {Btype, Flux, Dirichlet value} */
+pnp_status pnp_params_set(pnp_ctx*, const double* sys, const double* surf);
+pnp_status pnp_params_read(pnp_ctx*, const char* cfg_path);
+pnp_status pnp_params_get(pnp_ctx*, double* sys, double* surf /* may be NULL */, char* meshfile, int meshfile_cap);
+/* constraints(bctype, gfs, cc) for all three BC components at once (btype.hh:21-53; stationary_pnp.hh:155) */
+pnp_status pnp_constraints_build(pnp_ctx*);
+
+/* ---- operators: LocalOperator + GridOperator (stationary_pnp.hh:218-241) ------------------ */
+/* comp0: BC component the scalar operator's BCType was instantiated with (ignored for PNP) */
+pnp_status pnp_operator_create(pnp_ctx*, int op, int comp0, int* op_handle);
+/* coefficient grid functions: Poisson which=0:c+ 1:c- (poisson_operator.hh:97-100); diffusion which=0: Phi */
+pnp_status pnp_operator_set_coefficient(pnp_ctx*, int op_handle, int which, int vec_handle);
+pnp_status pnp_operator_set_valency(pnp_ctx*, int op_handle, double valency);
+/* Dirichlet flags per dof, reference numbering */
+pnp_status pnp_constraints_get(pnp_ctx*, int op_handle, char* is_dirichlet);
+/* MatrixContainer pattern (ISTLBCRSMatrixBackend<1,1>): rows ascending, columns ascending, constrained rows
+ * reduced to the diagonal.  col == NULL: only *nnz (and rowptr if given) is produced. */
+pnp_status pnp_pattern_get(pnp_ctx*, int op_handle, long* nnz, int* rowptr, int* col);
+
+/* ---- vectors: ISTLVectorBackend<1> containers --------------------------------------------- */
+pnp_status pnp_vec_create(pnp_ctx*, int fields, int* vec_handle);
+pnp_status pnp_vec_destroy(pnp_ctx*, int vec_handle);
+pnp_status pnp_vec_upload(pnp_ctx*, int vec_handle, const double* host);
+pnp_status pnp_vec_download(pnp_ctx*, int vec_handle, double* host);
+pnp_status pnp_vec_set(pnp_ctx*, int vec_handle, double value);
+pnp_status pnp_vec_copy(pnp_ctx*, int dst, int src);
+pnp_status pnp_vec_axpy(pnp_ctx*, int y, double a, int x); /* y += a x */
+pnp_status pnp_vec_norm(pnp_ctx*, int x, double* two_norm);
+pnp_status pnp_vec_dot(pnp_ctx*, int x, int y, double* result);
+
+/* ---- assembly: GridOperator::residual / ::jacobian (stationary_pnp.hh:240-246) ------------ */
+pnp_status pnp_matrix_create(pnp_ctx*, int op_handle, int* mat_handle);
+pnp_status pnp_matrix_destroy(pnp_ctx*, int mat_handle);
+pnp_status pnp_residual(pnp_ctx*, int op_handle, int u, int r);
+pnp_status pnp_jacobian(pnp_ctx*, int op_handle, int u, int mat_handle, int mode, double fd_epsilon);
+/* values in the order of pnp_pattern_get() */
+pnp_status pnp_matrix_values_get(pnp_ctx*, int op_handle, int mat_handle, double* val);
+pnp_status pnp_spmv(pnp_ctx*, int mat_handle, int x, int y);
+
+/* ---- linear solvers: ISTLBackend_NOVLP_*::apply / result (instationary_pnp_from_pb_md.hh:188-211) */
+typedef struct {
+  int converged;
+  int iterations;
+  double reduction;
+  double conv_rate;
+  double seconds;
+  int status;
+} pnp_lin_result;
+pnp_status pnp_solver_create(pnp_ctx*, int kind, int prec, int maxit, int prec_steps, int verbosity, int* solver);
+/* z: initial guess in, solution out; r: right-hand side in, residual out (as ISTL does) */
+pnp_status pnp_solver_apply(pnp_ctx*, int solver, int mat_handle, int z, int r, double reduction, pnp_lin_result*);
+
+/* ---- Newton: Dune::PDELab::Newton (stationary_pnp.hh:280-294) ------------------------------ */
+typedef struct {
+  double reduction;             /* setReduction */
+  double abs_limit;             /* PDELab default 1e-12 */
+  double min_linear_reduction;  /* setMinLinearReduction */
+  double reassemble_threshold;  /* setReassembleThreshold */
+  int max_iterations;           /* setMaxIterations */
+  int line_search_max_iterations; /* setLineSearchMaxIterations */
+  double damping;               /* 0.5 */
+  int jac_mode;                 /* PNP_JAC_* */
+  double fd_epsilon;            /* NumericalJacobianVolume epsilon: 1e-11 (PDELab <= 1.1) */
+  int verbosity;
+} pnp_newton_opts;
+typedef struct {
+  int converged;
+  int iterations;
+  double first_defect, defect, reduction;
+  int linear_iterations, line_search_trials, jacobian_assemblies, residual_assemblies;
+  double seconds_assembly, seconds_solve, seconds_total;
+  int n_history;
+  double defect_history[64];
+  int linear_iterations_history[64];
+} pnp_newton_result;
+void pnp_newton_opts_default(pnp_newton_opts*);
+/* fills opts as the reference drivers do from Sysparams (stationary_pnp_from_pb.hh:344-351) */
+pnp_status pnp_newton_opts_from_params(pnp_ctx*, pnp_newton_opts*);
+pnp_status pnp_newton_apply(pnp_ctx*, int op_handle, int u, int solver, const pnp_newton_opts*, pnp_newton_result*);
+/* StationaryLinearProblemSolver::apply (instationary_pnp_from_pb_md.hh:349-350) */
+pnp_status pnp_slp_apply(pnp_ctx*, int op_handle, int u, int solver, double reduction, int jac_mode, double fd_epsilon,
+                         pnp_lin_result*);
+
+/* ---- initial guess / Dirichlet values: interpolate(BCExtension) (dirichlet_bc.hh:54-123) --- */
+/* component 0: phi, 1: c+, 2: c-; pb_vec < 0 means a zero PB field; out is a 1-field vector */
+pnp_status pnp_interpolate_bcext(pnp_ctx*, int component, int pb_vec, int out_vec);
+/* packs three 1-field vectors into a 3-field vector / extracts one field */
+pnp_status pnp_vec_pack3(pnp_ctx*, int dst3, int phi, int cp, int cm);
+pnp_status pnp_vec_extract(pnp_ctx*, int src3, int field, int dst1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,188 @@
+// harness.cpp -- TEST INFRASTRUCTURE: runs the product's __host__ __device__ per-item functions
+// (dune_pnp_b200/csrc/pnp_elem.cuh, pnp_star.cuh, pnp_setup_algos.cuh) in plain host loops so their
+// logic can be compared with the CPU oracle on a machine without a GPU.  It is compiled by
+// tests/conftest.py with g++ -ffp-contract=off and is never linked into libpnp_b200.so; the
+// product has no CPU path.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../dune_pnp_b200/csrc/pnp_star.cuh"
+
+using namespace pnp;
+
+namespace {
+struct Star {
+  long nv = 0, nT = 0;
+  std::vector<int> rp, int2ext, ext2int;
+  std::vector<unsigned> adj;
+  std::vector<XY> xy;
+  std::vector<unsigned char> dmask;
+  std::vector<BFace> bfaces;
+  std::vector<int> bv, bv_ptr, bv_items;
+  std::vector<double> surf_flux;
+  std::vector<unsigned char> surf_dir;
+  StarView view() const { return StarView{rp.data(), adj.data(), xy.data(), dmask.data(), (int)nv}; }
+};
+} // namespace
+
+// phys[5] = {PI, l_b, c0, valency, cylindrical}; vectors in INTERNAL blocked layout
+static PhysParams mkphys(const double* p) { PhysParams P; P.PI = p[0]; P.l_b = p[1]; P.c0 = p[2]; P.valency = p[3]; P.cylindrical = (int)p[4]; return P; }
+
+template <int OP> static void residual_t(Star* S, const PhysParams& P, const double* u, const double* a0, const double* a1,
+                                         int comp0, double* r) {
+  constexpr int F = OpTraits<OP>::F;
+  const StarView M = S->view();
+  for (int v = 0; v < M.nv; v++) {
+    double out[F];
+    residual_row<OP>(M, P, u, a0, a1, v, out);
+    const unsigned db = dir_bits<OP>(M, v, comp0);
+    for (int k = 0; k < F; k++) r[(long)F * v + k] = ((db >> k) & 1u) ? 0.0 : out[k];
+  }
+  if (OP == OP_PB || OP == OP_POISSON || OP == OP_PNP)
+    for (size_t t = 0; t < S->bv.size(); t++) {
+      double acc[3];
+      boundary_vertex_sum(M, P, S->bfaces.data(), S->bv_items.data(), S->bv_ptr[t], S->bv_ptr[t + 1], S->surf_flux.data(),
+                          S->surf_dir.data(), F, comp0, acc);
+      const int v = S->bv[t];
+      for (int k = 0; k < F; k++) {
+        const int comp = F == 3 ? k : comp0;
+        if (!((M.dmask[v] >> comp) & 1u)) r[(long)F * v + k] += acc[k];
+      }
+    }
+}
+template <int OP> static void jacobian_t(Star* S, const PhysParams& P, const double* u, const double* a0, const double* a1,
+                                         int comp0, int mode, double eps, double* vals) {
+  const StarView M = S->view();
+  const long stride = (long)S->adj.size();
+  for (int v = 0; v < M.nv; v++) {
+    if (mode == JAC_FD_FAITHFUL) jacobian_row<OP, JAC_FD_FAITHFUL>(M, P, u, a0, a1, eps, comp0, v, vals, stride);
+    else jacobian_row<OP, JAC_ANALYTIC>(M, P, u, a0, a1, eps, comp0, v, vals, stride);
+  }
+}
+extern "C" {
+
+// refinement with the product's per-item functions; outputs must be sized by the caller:
+// x,y: nv+nE (call with out arrays NULL to get nE)
+long hh_refine(long nv, const double* x, const double* y, long nT, const int* tri, long nB, const int* ba, const int* bb,
+               const int* bphys, double* ox, double* oy, int* otri, int* oba, int* obb, int* obphys) {
+  std::vector<uint64_t> keys(3 * nT);
+  for (long i = 0; i < 3 * nT; i++) keys[i] = tri_edge_key(tri, i);
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  const long nE = (long)keys.size();
+  if (!ox) return nE;
+  std::copy(x, x + nv, ox); std::copy(y, y + nv, oy);
+  for (long k = 0; k < nE; k++) {
+    int a = (int)(keys[k] >> 32), b = (int)(keys[k] & 0xffffffffu);
+    ox[nv + k] = 0.5 * (x[a] + x[b]); oy[nv + k] = 0.5 * (y[a] + y[b]);
+  }
+  for (long t = 0; t < nT; t++) refine_children(tri, t, keys.data(), nE, nv, otri + 12 * t);
+  for (long s = 0; s < nB; s++) {
+    int m = (int)(nv + lower_bound_u64(keys.data(), nE, edge_key(ba[s], bb[s])));
+    oba[2 * s] = ba[s]; obb[2 * s] = m; obphys[2 * s] = bphys[s];
+    oba[2 * s + 1] = m; obb[2 * s + 1] = bb[s]; obphys[2 * s + 1] = bphys[s];
+  }
+  return nE;
+}
+
+// builds the star exactly as mesh_finalize()/constraints_build() do (same per-item functions)
+// surf_btype[ns][3], surf_flux[ns][3]; returns NULL on a mesh error (code in *err)
+void* hh_star_build(long nv, const double* x, const double* y, long nT, const int* tri, long nB, const int* ba,
+                    const int* bb, const int* bphys, int renumber, int ns, const int* surf_btype, const double* surf_flux,
+                    int* err) {
+  Star* S = new Star; S->nv = nv; S->nT = nT; *err = 0;
+  S->int2ext.resize(nv); S->ext2int.resize(nv);
+  if (renumber) {
+    std::vector<long> first(nv, 0x7fffffff);
+    for (long i = 0; i < 3 * nT; i++) first[tri[i]] = std::min(first[tri[i]], i);
+    std::iota(S->int2ext.begin(), S->int2ext.end(), 0);
+    std::stable_sort(S->int2ext.begin(), S->int2ext.end(), [&](int a, int b) { return first[a] < first[b]; });
+  } else std::iota(S->int2ext.begin(), S->int2ext.end(), 0);
+  for (long i = 0; i < nv; i++) S->ext2int[S->int2ext[i]] = (int)i;
+  S->xy.resize(nv);
+  for (long i = 0; i < nv; i++) S->xy[i] = XY{x[S->int2ext[i]], y[S->int2ext[i]]};
+  const long nrec = 3 * nT;
+  std::vector<uint64_t> keys(nrec); std::vector<unsigned> pay(nrec);
+  for (long t = 0; t < nT; t++)
+    if (!corner_records(tri, t, S->ext2int.data(), x, y, &keys[3 * t], &pay[3 * t])) *err = 1;
+  std::vector<long> order(nrec);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](long a, long b) { return keys[a] < keys[b]; });
+  std::vector<uint64_t> sk(nrec); std::vector<unsigned> sp(nrec);
+  for (long i = 0; i < nrec; i++) { sk[i] = keys[order[i]]; sp[i] = pay[order[i]]; }
+  std::vector<int> start(nv + 1);
+  for (long v = 0; v <= nv; v++) start[v] = (int)lower_bound_u64(sk.data(), nrec, (uint64_t)v << 32);
+  S->rp.assign(nv + 1, 0);
+  for (long v = 0; v < nv; v++) {
+    int open, bad;
+    fan_start(sk.data(), sp.data(), start[v], start[v + 1], &open, &bad);
+    if (bad) *err = 2;
+    S->rp[v + 1] = S->rp[v] + 1 + (start[v + 1] - start[v]) + open;
+  }
+  S->adj.assign(S->rp[nv], 0);
+  for (long v = 0; v < nv; v++)
+    if (!ring_fill(sk.data(), sp.data(), start[v], start[v + 1], (int)v, &S->adj[S->rp[v]])) *err = 2;
+  if (*err) { delete S; return nullptr; }
+  long nopen = 0;
+  for (long v = 0; v < nv; v++) if (!(S->adj[S->rp[v + 1] - 1] & STAR_HAS_TRI)) nopen++;
+  S->bfaces.resize(nB);
+  for (long s = 0; s < nB; s++) {
+    if (!boundary_face_of(S->rp.data(), S->adj.data(), S->ext2int[ba[s]], S->ext2int[bb[s]], &S->bfaces[s])) *err = 3;
+    S->bfaces[s].phys = bphys[s]; S->bfaces[s].seg = (int)s;
+  }
+  if (nopen != nB && !*err) *err = 4;
+  if (*err) { delete S; return nullptr; }
+  // constraints + boundary incidence lists (mirrors constraints_build)
+  S->dmask.assign(nv, 0);
+  S->surf_flux.assign(surf_flux, surf_flux + 3 * ns);
+  S->surf_dir.assign(ns, 0);
+  for (int i = 0; i < ns; i++) for (int k = 0; k < 3; k++) if (surf_btype[3 * i + k] == 0) S->surf_dir[i] |= (1u << k);
+  std::vector<std::vector<int>> items(nv);
+  for (long s = 0; s < nB; s++) {
+    const BFace& b = S->bfaces[s];
+    for (int l = 0; l < 2; l++) S->dmask[b.v[face_v(b.f, l)]] |= S->surf_dir[b.phys];
+    for (int r = 0; r < 3; r++) items[b.v[r]].push_back((int)s * 4 + r);
+  }
+  S->bv_ptr.push_back(0);
+  for (long v = 0; v < nv; v++) if (!items[v].empty()) {
+    S->bv.push_back((int)v);
+    std::sort(items[v].begin(), items[v].end());
+    S->bv_items.insert(S->bv_items.end(), items[v].begin(), items[v].end());
+    S->bv_ptr.push_back((int)S->bv_items.size());
+  }
+  return S;
+}
+void hh_star_free(void* h) { delete (Star*)h; }
+long hh_star_nslots(void* h) { return (long)((Star*)h)->adj.size(); }
+void hh_star_get(void* h, int* rp, unsigned* adj, int* int2ext, unsigned char* dmask) {
+  Star* S = (Star*)h;
+  std::copy(S->rp.begin(), S->rp.end(), rp); std::copy(S->adj.begin(), S->adj.end(), adj);
+  std::copy(S->int2ext.begin(), S->int2ext.end(), int2ext); std::copy(S->dmask.begin(), S->dmask.end(), dmask);
+}
+
+void hh_residual(void* h, int op, const double* phys, const double* u, const double* a0, const double* a1, int comp0,
+                 double* r) {
+  Star* S = (Star*)h; const PhysParams P = mkphys(phys);
+  switch (op) {
+    case OP_PB: residual_t<OP_PB>(S, P, u, a0, a1, comp0, r); break;
+    case OP_POISSON: residual_t<OP_POISSON>(S, P, u, a0, a1, comp0, r); break;
+    case OP_DIFFUSION: residual_t<OP_DIFFUSION>(S, P, u, a0, a1, comp0, r); break;
+    case OP_MASS: residual_t<OP_MASS>(S, P, u, a0, a1, comp0, r); break;
+    case OP_PNP: residual_t<OP_PNP>(S, P, u, a0, a1, comp0, r); break;
+  }
+}
+void hh_jacobian(void* h, int op, const double* phys, const double* u, const double* a0, const double* a1, int comp0,
+                 int mode, double eps, double* vals) {
+  Star* S = (Star*)h; const PhysParams P = mkphys(phys);
+  switch (op) {
+    case OP_PB: jacobian_t<OP_PB>(S, P, u, a0, a1, comp0, mode, eps, vals); break;
+    case OP_POISSON: jacobian_t<OP_POISSON>(S, P, u, a0, a1, comp0, mode, eps, vals); break;
+    case OP_DIFFUSION: jacobian_t<OP_DIFFUSION>(S, P, u, a0, a1, comp0, mode, eps, vals); break;
+    case OP_MASS: jacobian_t<OP_MASS>(S, P, u, a0, a1, comp0, mode, eps, vals); break;
+    case OP_PNP: jacobian_t<OP_PNP>(S, P, u, a0, a1, comp0, mode, eps, vals); break;
+  }
+}
+
+} // extern "C"

