@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- one PNP Newton step (Jacobian assembly + preconditioned BiCGSTAB solve + line search) on the
+uniformly refined pore mesh (BASELINE.json configs[4]: test/pore_pnp refined to >= 50 M dofs).
+
+A "step" is one Newton iteration of the monolithic 3-field PNP system (stationary_pnp.hh:280-294) started from
+the same state u_s every time: u_s is the PNP solution converged on refinement level `--coarse-level` (reference
+flow: PB Newton -> interpolate(BCExtension) -> PNP Newton) and carried to the fine mesh by P1 interpolation
+(nested iteration), i.e. a late Newton step of a production run.  value = dofs / step time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--levels L] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): see DESIGN.md "multi-GPU"; until the partitioned solver lands every rank
+runs the N = 1 problem and the line says so ("scaling": "replicas").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "newton_step_dofs_per_s"
+UNIT = "DOF/s"
+
+
+def load_case():
+    import util
+    return util.load_mesh_arrays("pore"), util.cfg_path("pore")
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference's algorithm; the reference itself needs DUNE and cannot be built)
+# ------------------------------------------------------------------------------------------------------------
+def carry_numpy(m_coarse, u_lex, F):
+    """P1 interpolation of nodal fields to the once-refined mesh (oracle's refinement rule)."""
+    tri = m_coarse.tri.astype(np.int64)
+    e = np.concatenate([tri[:, [0, 1]], tri[:, [0, 2]], tri[:, [1, 2]]])
+    lo, hi = e.min(1), e.max(1)
+    keys = np.unique((lo << 32) | hi)
+    a, b = (keys >> 32).astype(np.int64), (keys & 0xffffffff).astype(np.int64)
+    u = u_lex.reshape(F, m_coarse.nv)
+    return np.concatenate([u, 0.5 * (u[:, a] + u[:, b])], axis=1).reshape(-1)
+
+
+def cpu_newton_step(level=0, reps=1):
+    """One oracle Newton step of the reference flow on the pore mesh: the SECOND Newton iteration (start state =
+    state after the first iteration, stored in tests/golden/pore_solution.npz by scripts/make_golden_solutions.py),
+    optionally P1-interpolated `level` times.  Solver as the reference's default build: BiCGSTAB + SSOR(1)
+    (LINEARSOLVER=1, instationary_pnp_from_pb_md.hh:188-191), FD Jacobian (eps 1e-11), cfg Newton settings.
+    Level 0 (9 144 dofs) is the bounded sample: at level 1 the same step already needs ~20 000 Krylov iterations."""
+    from oracle import binding as ora
+    import util
+    a, cfg = load_case()
+    p = ora.Params.read(cfg)
+    m = ora.Mesh.from_arrays(**a)
+    u = np.load(os.path.join(util.GOLDEN, "pore_solution.npz"))["u1"]
+    for _ in range(level):
+        u = carry_numpy(m, u, 3)
+        m = m.refine(1)
+    opts1 = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, maxit=1)
+    ts, info = [], None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _, info = ora.newton(m, p, ora.OP_PNP, u, opts1)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    return dict(dofs=3 * m.nv, seconds=t, value=3 * m.nv / t, lin_its=info["total_linear_iterations"],
+                ls_trials=info["total_ls_trials"], level=level)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    res = [cpu_newton_step(args.cpu_level, reps=1) for _ in range(args.warmup + args.steps)][args.warmup:]
+    t = float(np.mean([r["seconds"] for r in res]))
+    r = res[-1]
+    sample = "pore mesh refined %d times (%d dofs), one Newton step: FD Jacobian + BiCGSTAB/SSOR(1) (%d its) + line search" % (
+        r["level"], r["dofs"], r["lin_its"])
+    line = {"impl": "reference", "metric": METRIC, "value": r["dofs"] / t, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "pore_pnp Newton step (CPU sample at refinement level %d)" % r["level"],
+                       "levels": r["level"], "dofs": r["dofs"]},
+            "cpu_baseline": {"value": r["dofs"] / t, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": r["dofs"] / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
+    """Reference flow on the coarse level, then nested iteration to the fine mesh. Returns (op, solver, u_s)."""
+    def solver():
+        return c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0)
+    c.mesh_refine(coarse_level); c.mesh_finalize(True)
+    hpb = c.operator(capi.OP_PB, 0)
+    vpb = c.vec(1)
+    c.newton(hpb, vpb, solver(), c.newton_opts(jac_mode=jac_mode))
+    f = [c.vec(1) for _ in range(3)]
+    for k in range(3):
+        c.interpolate_bcext(k, vpb, f[k])
+    vu = c.vec(3); c.pack3(vu, *f)
+    h = c.operator(capi.OP_PNP, 0)
+    st, r = c.newton(h, vu, solver(), c.newton_opts(jac_mode=jac_mode))
+    if verbose:
+        print("# coarse level %d: PNP Newton %d its, linear %s" % (coarse_level, r.iterations,
+              list(r.linear_iterations_history[:r.n_history])), file=sys.stderr, flush=True)
+    c.carry_set([vu])
+    c.mesh_refine(levels - coarse_level); c.mesh_finalize(True)
+    us = c.vec(3); c.carry_get(0, us)
+    return c.operator(capi.OP_PNP, 0), solver(), us
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from dune_pnp_b200 import capi
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    a, cfg = load_case()
+    c = capi.Context(local_rank)
+    c.mesh_set(**a); c.params_read(cfg)
+    jac_mode = capi.JAC_FD_FAITHFUL if args.jac == "fd" else capi.JAC_ANALYTIC
+    t_setup = time.perf_counter()
+    h, s, us = build_state(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, rank == 0 and args.verbose)
+    sizes = c.mesh_sizes()
+    nv, ns = sizes["nv"], sizes["nslots"]
+    ndof = 3 * nv
+    t_setup = time.perf_counter() - t_setup
+    u = c.vec(3)
+    opts = c.newton_opts(jac_mode=jac_mode, max_iterations=1)
+    # pinned host buffers for the end-to-end leg
+    h_in = torch.empty(ndof, dtype=torch.float64, pin_memory=True).numpy()
+    h_out = torch.empty(ndof, dtype=torch.float64, pin_memory=True).numpy()
+    h_in[:] = c.download(us, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(e2e):
+        if e2e:
+            c.upload(u, h_in)
+        else:
+            c.vec_copy(u, us)
+        st, r = c.newton(h, u, s, opts, check=False)
+        if st not in (0, 1):
+            raise RuntimeError("Newton step failed with status %d" % st)
+        if e2e:
+            lib = capi.lib()
+            c._ck(lib.pnp_vec_download(c._h, u, h_out.ctypes.data_as(capi._dp)))
+        return r
+
+    for _ in range(args.warmup):
+        r = step(False)
+    # ---- timed region: K steps, inputs resident in HBM ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    c.profile_spmv(True)
+    l0 = c.launch_count()
+    barrier()
+    c.timer_start()
+    t0 = time.perf_counter()
+    stats = [step(False) for _ in range(args.steps)]
+    ms_dev = c.timer_stop()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = c.launch_count() - l0
+    n_spmv, spmv_ms = c.profile_spmv_get()
+    c.profile_spmv(False)
+    clocks = sampler.stop() if sampler else None
+    # ---- end-to-end: same step through the C ABI with host buffers (H2D of u, D2H of the updated u) ----
+    step(True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    tmax = torch.tensor([ms_dev / 1e3, wall, wall_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    sec_dev, wall, wall_e2e = [float(v) for v in tmax.tolist()]
+    sec_step = max(sec_dev, 0.0) / args.steps
+    if rank != 0:
+        return
+    r = stats[-1]
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes of one fine-level 3-field SpMV (DESIGN.md "SpMV"): 7 value planes + column index per
+    # slot, row pointer + x read + y written per vertex
+    spmv_bytes = (7 * 8 + 4) * ns + (4 + 2 * 3 * 8) * nv
+    spmv_avg_s = spmv_ms / 1e3 / max(n_spmv, 1)
+    achieved = spmv_bytes / spmv_avg_s / 1e9
+    asm_s = float(np.mean([x.seconds_assembly for x in stats]))
+    cpu = cpu_newton_step(args.cpu_level) if not args.no_cpu else None
+    replicas = world if world > 1 else 1
+    line = {
+        "metric": METRIC, "value": replicas * ndof / sec_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True,
+        "scaling": "strong" if world == 1 else "replicas", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "test/pore_pnp (pore.msh + pore.cfg) uniformly refined %d times: one monolithic PNP Newton "
+                               "step (Jacobian assembly, BiCGSTAB + aggregation AMG, line search)" % args.levels,
+                   "levels": args.levels, "vertices": nv, "triangles": sizes["nT"], "dofs": ndof, "matrix_slots": ns,
+                   "jacobian": args.jac, "preconditioner": "AMG V(%d,%d) damped Jacobi" % (args.prec_steps, args.prec_steps),
+                   "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
+                   "l2_policy": "inputs larger than L2 (matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
+        "newton_step_s": sec_step, "assembled_dofs_per_s": ndof / asm_s if asm_s > 0 else None,
+        "krylov_iterations": int(r.linear_iterations), "line_search_trials": int(r.line_search_trials),
+        "defect_before": r.first_defect, "defect_after": r.defect,
+        "spmv_gbs": achieved, "spmv_launches_timed": n_spmv, "spmv_share_of_step": spmv_ms / 1e3 / max(sec_dev, 1e-30),
+        "setup_s": t_setup, "wall_s": wall,
+        "roofline": {"bound": "hbm", "kernel": "3-field SpMV on the vertex-star layout (k_spmv<7,*> / k_level_op<7,*>)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+                     "avg_launch_ms": spmv_avg_s * 1e3},
+        "cpu_baseline": None if cpu is None else {
+            "value": cpu["value"], "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle (CPU restatement), pore mesh refined %d times (%d dofs), one Newton step: FD Jacobian + "
+                      "BiCGSTAB/SSOR(1) (%d its) + line search, %.1f s" % (cpu["level"], cpu["dofs"], cpu["lin_its"], cpu["seconds"])},
+        "e2e": {"value": replicas * ndof / (wall_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 8 * ndof,
+                "d2h_bytes_per_step": 8 * ndof},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--levels", type=int, default=7, help="uniform refinements of pore.msh (7 -> 141 M dofs)")
+    ap.add_argument("--coarse-level", type=int, default=3)
+    ap.add_argument("--cpu-level", type=int, default=0)
+    ap.add_argument("--prec-steps", type=int, default=2)
+    ap.add_argument("--jac", choices=["analytic", "fd"], default="analytic")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,22 @@ class Context:
         if st != 0:
             raise PnpError(st, lib().pnp_last_error(self._h).decode())
 
+    def profile_spmv(self, enable):
+        self._ck(lib().pnp_profile_spmv(self._h, int(enable)))
+
+    def profile_spmv_get(self):
+        n = C.c_long(); ms = C.c_double()
+        self._ck(lib().pnp_profile_spmv_get(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def timer_start(self):
+        self._ck(lib().pnp_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(lib().pnp_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         return lib().pnp_launch_count(self._h)
 
@@ -113,6 +129,13 @@ class Context:
 
     def mesh_refine(self, levels):
         self._ck(lib().pnp_mesh_refine(self._h, levels))
+
+    def carry_set(self, vecs):
+        arr = (C.c_int * len(vecs))(*vecs)
+        self._ck(lib().pnp_carry_set(self._h, arr, len(vecs)))
+
+    def carry_get(self, index, vec):
+        self._ck(lib().pnp_carry_get(self._h, index, vec))
 
     def mesh_finalize(self, renumber=True):
         self._ck(lib().pnp_mesh_finalize(self._h, int(renumber)))

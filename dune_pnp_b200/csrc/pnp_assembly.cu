@@ -117,6 +117,7 @@ void assemble_jacobian(Ctx& c, const Operator& op, const Vec& u, Matrix& A, int 
   PNP_REQUIRE(mode == JAC_FD_FAITHFUL || mode == JAC_ANALYTIC, PNP_E_ARG, "unknown jacobian mode");
   const double *a0, *a1;
   coefficient_ptrs(c, op, &a0, &a1);
+  A.comp0 = op.comp0;
   switch (op.op) {
     case OP_PB: launch_jac<OP_PB>(c, op, u.d.p, a0, a1, A, mode, eps); break;
     case OP_POISSON: launch_jac<OP_POISSON>(c, op, u.d.p, a0, a1, A, mode, eps); break;

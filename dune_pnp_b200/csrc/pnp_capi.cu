@@ -63,6 +63,33 @@ void pnp_ctx_destroy(pnp_ctx* ctx) {
   delete ctx;
   if (s) cudaStreamDestroy(s);
 }
+pnp_status pnp_profile_spmv(pnp_ctx* ctx, int enable) {
+  API_BEGIN(ctx) c.prof = enable != 0; c.prof_used = 0; API_END
+}
+pnp_status pnp_profile_spmv_get(pnp_ctx* ctx, long* launches, double* total_ms) {
+  API_BEGIN(ctx)
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  double ms = 0;
+  for (size_t i = 0; i + 1 < c.prof_used; i += 2) { float t = 0; PNP_CUDA(cudaEventElapsedTime(&t, c.prof_ev[i], c.prof_ev[i + 1])); ms += t; }
+  if (launches) *launches = (long)(c.prof_used / 2);
+  if (total_ms) *total_ms = ms;
+  API_END
+}
+pnp_status pnp_timer_start(pnp_ctx* ctx) {
+  API_BEGIN(ctx)
+  if (!c.tm0) { PNP_CUDA(cudaEventCreate(&c.tm0)); PNP_CUDA(cudaEventCreate(&c.tm1)); }
+  PNP_CUDA(cudaEventRecord(c.tm0, c.stream));
+  API_END
+}
+pnp_status pnp_timer_stop(pnp_ctx* ctx, double* ms) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.tm0 && ms, PNP_E_ARG, "timer not started");
+  PNP_CUDA(cudaEventRecord(c.tm1, c.stream));
+  PNP_CUDA(cudaEventSynchronize(c.tm1));
+  float t = 0; PNP_CUDA(cudaEventElapsedTime(&t, c.tm0, c.tm1));
+  *ms = t;
+  API_END
+}
 const char* pnp_last_error(pnp_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
 long pnp_launch_count(pnp_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
@@ -79,6 +106,8 @@ pnp_status pnp_mesh_read_gmsh(pnp_ctx* ctx, const char* path) {
   API_END
 }
 pnp_status pnp_mesh_refine(pnp_ctx* ctx, int levels) { API_BEGIN(ctx) mesh_refine(c, levels); API_END }
+pnp_status pnp_carry_set(pnp_ctx* ctx, const int* vec_handles, int n) { API_BEGIN(ctx) carry_set(c, vec_handles, n); API_END }
+pnp_status pnp_carry_get(pnp_ctx* ctx, int index, int vec_handle) { API_BEGIN(ctx) carry_get(c, index, c.vec(vec_handle)); API_END }
 pnp_status pnp_mesh_finalize(pnp_ctx* ctx, int renumber) { API_BEGIN(ctx) mesh_finalize(c, renumber != 0); API_END }
 pnp_status pnp_mesh_sizes(pnp_ctx* ctx, long* nv, long* nT, long* nB, long* nslots) {
   API_BEGIN(ctx)

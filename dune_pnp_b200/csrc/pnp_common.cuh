@@ -86,6 +86,7 @@ struct Vec {
 struct Matrix {
   int op = 0;
   int nplanes = 1;
+  int comp0 = 0;  // BC component of the operator that assembled it (scalar operators)
   DBuf<double> vals; // nplanes * nslots
 };
 
@@ -133,11 +134,27 @@ struct Ctx {
   HostParams params;
   bool constraints_built = false;
   long launches = 0;                   // kernels launched (bench.py reports gpu_launches)
+  // optional CUDA-event profile of the fine-level SpMV launches (bench.py's roofline leg)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr; // pnp_timer_start/stop
+  void prof_mark() {
+    if (!prof) return;
+    if (prof_used == prof_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); }
+    cudaEventRecord(prof_ev[prof_used++], stream);
+  }
   // handle tables
   std::vector<std::unique_ptr<Vec>> vecs;
   std::vector<std::unique_ptr<Matrix>> mats;
   std::vector<std::unique_ptr<Operator>> ops;
   std::vector<std::unique_ptr<Solver>> solvers;
+  std::vector<Vec> carry;              // nodal fields in reference numbering, interpolated by mesh_refine()
+  // a new / refined mesh invalidates every object sized by it
+  void invalidate_mesh_objects() {
+    finalized = false; constraints_built = false;
+    vecs.clear(); mats.clear(); ops.clear(); solvers.clear();
+  }
   // scratch for reductions
   DBuf<double> red_partial, red_out;
   double* h_red = nullptr; // pinned
@@ -163,6 +180,8 @@ void mesh_set(Ctx&, long nv, const double* x, const double* y, long nT, const in
 void mesh_refine(Ctx&, int levels);
 void mesh_finalize(Ctx&, bool renumber);
 void constraints_build(Ctx&);
+void carry_set(Ctx&, const int* handles, int n);
+void carry_get(Ctx&, int i, Vec& out);
 void vec_upload(Ctx&, Vec&, const double* host_lex);
 void vec_download(Ctx&, const Vec&, double* host_lex);
 long pattern_export(Ctx&, int op_handle, int* rowptr, int* col);

@@ -211,6 +211,7 @@ void spmv_dots(Ctx& c, const Matrix& A, const double* x, double* y, int ndot, co
   const long nv = c.nv;
   const int grid = grid_for(nv * LANES, RED_BLOCK, c.sm_count * 8);
   const long st = c.nslots;
+  c.prof_mark();
 #define SPMV_CASE(NPv, ND)                                                                                      \
   k_spmv<NPv, ND, LANES><<<grid, RED_BLOCK, 0, c.stream>>>(c.rp.p, c.adj.p, A.vals.p, st, x, y, (int)nv, w1, \
                                                           c.red_partial.p)
@@ -218,6 +219,7 @@ void spmv_dots(Ctx& c, const Matrix& A, const double* x, double* y, int ndot, co
   else { if (ndot == 0) SPMV_CASE(7, 0); else if (ndot == 1) SPMV_CASE(7, 1); else SPMV_CASE(7, 2); }
 #undef SPMV_CASE
   PNP_CHECK_LAUNCH(); c.launches++;
+  c.prof_mark();
   if (ndot > 0) finish_reduce(c, grid, ndot, dots);
 }
 

@@ -28,6 +28,12 @@ __global__ void k_midpoints(const uint64_t* __restrict__ ukeys, long nE, long nv
     y[nv + k] = 0.5 * (y[a] + y[b]);
   }
 }
+__global__ void k_mid_field(const uint64_t* __restrict__ ukeys, long nE, long nv, double* __restrict__ u) {
+  for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < nE; k += (long)gridDim.x * blockDim.x) {
+    int a = (int)(ukeys[k] >> 32), b = (int)(ukeys[k] & 0xffffffffu);
+    u[nv + k] = 0.5 * (u[a] + u[b]);
+  }
+}
 __global__ void k_children(const int* __restrict__ tri, long nT, const uint64_t* __restrict__ ukeys, long nE, long nv,
                            int* __restrict__ out) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < nT; t += (long)gridDim.x * blockDim.x)
@@ -147,7 +153,9 @@ void mesh_set(Ctx& c, long nv, const double* x, const double* y, long nT, const 
   for (long i = 0; i < 3 * nT; i++) PNP_REQUIRE(tri[i] >= 0 && tri[i] < nv, PNP_E_MESH, "triangle vertex out of range");
   for (long i = 0; i < nB; i++)
     PNP_REQUIRE(ba[i] >= 0 && ba[i] < nv && bb[i] >= 0 && bb[i] < nv, PNP_E_MESH, "boundary vertex out of range");
-  c.nv = nv; c.nT = nT; c.nB = nB; c.finalized = false; c.constraints_built = false;
+  c.nv = nv; c.nT = nT; c.nB = nB;
+  c.invalidate_mesh_objects();
+  c.carry.clear();
   c.cx.alloc(nv); c.cy.alloc(nv); c.ctri.alloc(3 * nT); c.cba.alloc(nB); c.cbb.alloc(nB); c.cbphys.alloc(nB);
   c.cx.upload(x, nv, c.stream); c.cy.upload(y, nv, c.stream); c.ctri.upload(tri, 3 * nT, c.stream);
   c.cba.upload(ba, nB, c.stream); c.cbb.upload(bb, nB, c.stream); c.cbphys.upload(bphys, nB, c.stream);
@@ -177,6 +185,18 @@ void mesh_refine(Ctx& c, int levels) {
     PNP_CUDA(cudaMemcpyAsync(nx.p, c.cx.p, nv * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
     PNP_CUDA(cudaMemcpyAsync(ny.p, c.cy.p, nv * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
     LAUNCH(c, k_midpoints, nE, ukeys.p, nE, nv, nx.p, ny.p);
+    // carried nodal fields (nested iteration): P1 interpolation = the same midpoint rule, field by field
+    for (auto& cf : c.carry) {
+      const int F = cf.fields;
+      DBuf<double> nf((size_t)F * (nv + nE));
+      for (int k = 0; k < F; k++) {
+        PNP_CUDA(cudaMemcpyAsync(nf.p + (size_t)k * (nv + nE), cf.d.p + (size_t)k * nv, nv * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, c.stream));
+        LAUNCH(c, k_mid_field, nE, ukeys.p, nE, nv, nf.p + (size_t)k * (nv + nE));
+      }
+      PNP_CUDA(cudaStreamSynchronize(c.stream));
+      cf.d = std::move(nf);
+    }
     DBuf<int> ntri(12 * nT), na(2 * nB), nb(2 * nB), np(2 * nB);
     LAUNCH(c, k_children, nT, c.ctri.p, nT, ukeys.p, nE, nv, ntri.p);
     if (nB) LAUNCH(c, k_refine_bnd, nB, c.cba.p, c.cbb.p, c.cbphys.p, nB, ukeys.p, nE, nv, na.p, nb.p, np.p);
@@ -185,7 +205,28 @@ void mesh_refine(Ctx& c, int levels) {
     c.cba = std::move(na); c.cbb = std::move(nb); c.cbphys = std::move(np);
     c.nv = nv + nE; c.nT = 4 * nT; c.nB = 2 * nB;
   }
-  c.finalized = false; c.constraints_built = false;
+  c.invalidate_mesh_objects();
+}
+
+// Stores vectors in reference numbering so that the next mesh_refine() interpolates them to the finer mesh.
+void carry_set(Ctx& c, const int* handles, int n) {
+  PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
+  c.carry.clear();
+  for (int i = 0; i < n; i++) {
+    const Vec& v = c.vec(handles[i]);
+    Vec cf; cf.fields = v.fields; cf.d.alloc((size_t)v.fields * c.nv);
+    LAUNCH(c, k_vec_to_external, c.nv * v.fields, v.d.p, c.int2ext.p, c.nv, v.fields, cf.d.p);
+    c.carry.push_back(std::move(cf));
+  }
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+}
+void carry_get(Ctx& c, int i, Vec& out) {
+  PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
+  PNP_REQUIRE(i >= 0 && i < (int)c.carry.size(), PNP_E_ARG, "no such carried field");
+  PNP_REQUIRE(out.fields == c.carry[i].fields && c.carry[i].d.n == (size_t)out.fields * c.nv, PNP_E_ARG,
+              "carried field does not match the vector / current mesh");
+  LAUNCH(c, k_vec_to_internal, c.nv * out.fields, c.carry[i].d.p, c.int2ext.p, c.nv, out.fields, out.d.p);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 void mesh_finalize(Ctx& c, bool renumber) {

@@ -54,12 +54,25 @@ const char* pnp_last_error(pnp_ctx* ctx);
 /* number of CUDA kernels this context has launched so far */
 long pnp_launch_count(pnp_ctx* ctx);
 
+/* measurement hooks (bench.py): CUDA events on the context's stream.  pnp_profile_spmv(ctx,1) brackets every
+ * fine-level SpMV launch with an event pair; pnp_profile_spmv_get() returns their count and summed duration. */
+pnp_status pnp_profile_spmv(pnp_ctx*, int enable);
+pnp_status pnp_profile_spmv_get(pnp_ctx*, long* launches, double* total_ms);
+pnp_status pnp_timer_start(pnp_ctx*);
+pnp_status pnp_timer_stop(pnp_ctx*, double* elapsed_ms);
+
 /* ---- mesh: GmshReader<UGGrid<2>>::read + createGrid (pnp_solver_main.cc:82-114) ---------- */
 pnp_status pnp_mesh_set(pnp_ctx*, long nv, const double* x, const double* y, long nT, const int* tri /*[nT][3]*/,
                         long nB, const int* ba, const int* bb, const int* bphys);
 pnp_status pnp_mesh_read_gmsh(pnp_ctx*, const char* path);
 /* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
 pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
+/* nested iteration: pnp_carry_set() stores vectors in reference numbering; every later pnp_mesh_refine() level
+ * interpolates them (P1: midpoint average) to the finer mesh; after pnp_mesh_finalize() they are read back with
+ * pnp_carry_get() into freshly created vectors.  Setting or refining a mesh invalidates all vector, matrix,
+ * operator and solver handles. */
+pnp_status pnp_carry_set(pnp_ctx*, const int* vec_handles, int n);
+pnp_status pnp_carry_get(pnp_ctx*, int index, int vec_handle);
 /* builds the vertex-star structure; renumber != 0 reorders vertices internally for locality */
 pnp_status pnp_mesh_finalize(pnp_ctx*, int renumber);
 pnp_status pnp_mesh_sizes(pnp_ctx*, long* nv, long* nT, long* nB, long* nslots);

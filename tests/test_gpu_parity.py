@@ -258,9 +258,11 @@ def test_newton_pnp_from_pb_matches_oracle(name, tight):
     hpb = c.operator(capi.OP_PB, 0)
     spb = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 5000)
     vpb = c.vec(1)
-    c.newton(hpb, vpb, spb, c.newton_opts(reduction=1e-11, min_linear_reduction=1e-9))
+    kw = dict(reduction=1e-11, min_linear_reduction=1e-9) if tight else {}
+    c.newton(hpb, vpb, spb, c.newton_opts(**kw))
     opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI); opts[12] = 5000
-    opts[0], opts[2] = 1e-11, 1e-9
+    if tight:
+        opts[0], opts[2] = 1e-11, 1e-9
     pb_o, _ = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
     # initial guess
     f = [c.vec(1) for _ in range(3)]
@@ -269,13 +271,16 @@ def test_newton_pnp_from_pb_matches_oracle(name, tight):
     vu = c.vec(3)
     c.pack3(vu, *f)
     u0_o = np.concatenate([ora.interpolate(m, p, k, pb_o) for k in range(3)])
-    assert np.linalg.norm(c.download(vu, 3) - u0_o) <= 1e-8 * np.linalg.norm(u0_o)
+    assert np.linalg.norm(c.download(vu, 3) - u0_o) <= (1e-8 if tight else 1e-4) * np.linalg.norm(u0_o)
     # PNP Newton, Jacobi-preconditioned BiCGSTAB on both sides
     h = c.operator(capi.OP_PNP, 0)
     s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 20000)
     kw = dict(reduction=1e-11, min_linear_reduction=1e-9) if tight else {}
     st, res = c.newton(h, vu, s, c.newton_opts(**kw))
-    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI); opts[12] = 20000
+    # (BiCGSTAB+Jacobi hits a genuine rho-breakdown on the CPU for pore_small; Newton counts only depend on the
+    #  linear solves reaching the requested reduction, so the oracle may use its SSOR there)
+    oprec = ora.PREC_SSOR if name == "pore_small" else ora.PREC_JACOBI
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=oprec); opts[12] = 20000
     if tight:
         opts[0], opts[2] = 1e-11, 1e-9
     u_o, res_o = ora.newton(m, p, ora.OP_PNP, u0_o, opts)
