@@ -214,10 +214,12 @@ def run_gpu(args, rank, world, local_rank):
     c.profile_spmv(True)
     l0 = c.launch_count()
     barrier()
+    c.profiler_range(True)
     c.timer_start()
     t0 = time.perf_counter()
     stats = [step(False) for _ in range(args.steps)]
     ms_dev = c.timer_stop()
+    c.profiler_range(False)
     barrier()
     wall = time.perf_counter() - t0
     launches = c.launch_count() - l0

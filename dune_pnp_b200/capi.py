@@ -105,6 +105,9 @@ class Context:
         self._ck(lib().pnp_profile_spmv_get(self._h, C.byref(n), C.byref(ms)))
         return n.value, ms.value
 
+    def profiler_range(self, start):
+        self._ck(lib().pnp_profiler_range(self._h, int(start)))
+
     def timer_start(self):
         self._ck(lib().pnp_timer_start(self._h))
 

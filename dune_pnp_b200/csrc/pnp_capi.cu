@@ -1,4 +1,6 @@
 // pnp_capi.cu -- extern "C" entry points declared in include/pnp_b200.h.  No exception leaves this file.
+#include <cuda_profiler_api.h>
+
 #include <cstring>
 
 #include "pnp_common.cuh"
@@ -73,6 +75,12 @@ pnp_status pnp_profile_spmv_get(pnp_ctx* ctx, long* launches, double* total_ms) 
   for (size_t i = 0; i + 1 < c.prof_used; i += 2) { float t = 0; PNP_CUDA(cudaEventElapsedTime(&t, c.prof_ev[i], c.prof_ev[i + 1])); ms += t; }
   if (launches) *launches = (long)(c.prof_used / 2);
   if (total_ms) *total_ms = ms;
+  API_END
+}
+pnp_status pnp_profiler_range(pnp_ctx* ctx, int start) {
+  API_BEGIN(ctx)
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  if (start) cudaProfilerStart(); else cudaProfilerStop();
   API_END
 }
 pnp_status pnp_timer_start(pnp_ctx* ctx) {

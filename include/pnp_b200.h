@@ -58,6 +58,8 @@ long pnp_launch_count(pnp_ctx* ctx);
  * fine-level SpMV launch with an event pair; pnp_profile_spmv_get() returns their count and summed duration. */
 pnp_status pnp_profile_spmv(pnp_ctx*, int enable);
 pnp_status pnp_profile_spmv_get(pnp_ctx*, long* launches, double* total_ms);
+/* cudaProfilerStart/Stop: lets `ncu --profile-from-start off` see only the timed region */
+pnp_status pnp_profiler_range(pnp_ctx*, int start);
 pnp_status pnp_timer_start(pnp_ctx*);
 pnp_status pnp_timer_stop(pnp_ctx*, double* elapsed_ms);
 

@@ -1,0 +1,120 @@
+"""CPU tests of the PRODUCT's per-item logic (the __host__ __device__ functions the CUDA kernels wrap), run through
+tests/host_harness against the oracle: star construction, pattern, constraints, element integrals, FD and exact
+Jacobian rows, boundary terms, refinement.  Plus: the C ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import harness
+import util
+from oracle import binding as ora
+
+OPS = [ora.OP_PB, ora.OP_POISSON, ora.OP_DIFFUSION, ora.OP_MASS, ora.OP_PNP]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def case(name, levels=0):
+    a = util.load_mesh_arrays(name)
+    m = ora.Mesh.from_arrays(**a).refine(levels)
+    p = ora.Params.read(util.cfg_path(name))
+    a = dict(x=m.x, y=m.y, tri=m.tri, ba=m.ba, bb=m.bb, bphys=m.bphys)
+    return a, m, p
+
+
+@pytest.mark.parametrize("renumber", [False, True])
+@pytest.mark.parametrize("name", util.MESHES)
+def test_star_pattern_and_constraints_bit_exact(name, renumber):
+    a, m, p = case(name)
+    S = harness.Star(a, p.surf, renumber)
+    assert S.nslots == m.nv + 2 * (m.nv + m.nT - 1)  # nnz_1 = nv + 2 nE
+    for F, comp0 in ((1, 0), (1, 2), (3, 0)):
+        rp, col = S.export_csr(F, comp0)
+        rp_o, col_o = ora.pattern(m, p, F, comp0)
+        assert np.array_equal(rp, rp_o) and np.array_equal(col, col_o)
+        assert np.array_equal(S.dirichlet(F, comp0), ora.dirichlet(m, p, F, comp0))
+
+
+@pytest.mark.parametrize("name,levels", [("one_wall", 2), ("pore_small", 1)])
+def test_refinement_rule_matches_oracle(name, levels):
+    a, m0, p = case(name)
+    for _ in range(levels):
+        a = harness.refine(a)
+    m = m0.refine(levels)
+    for k in a:
+        assert np.array_equal(a[k], getattr(m, k)), k
+
+
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("name,levels", [("one_wall", 0), ("sphere", 0), ("cylinder", 0), ("pore_small", 1), ("pore", 0)])
+def test_residual_rows_match_oracle(name, levels, op):
+    a, m, p = case(name, levels)
+    S = harness.Star(a, p.surf, True)
+    rng = np.random.RandomState(1)
+    F = ora.nfields(op)
+    u = rng.uniform(-1, 1, F * m.nv); a0 = rng.uniform(0, 1, m.nv); a1 = rng.uniform(0, 1, m.nv)
+    r_o, ab = ora.residual(m, p, op, u, a0, a1, valency=-1.0, want_abs=True)
+    r = S.residual(op, p.sys, u, a0, a1, valency=-1.0)
+    assert np.all(np.abs(r - r_o) <= 1e-12 * ab)
+    assert np.all(np.abs(r - r_o) <= 8 * 2.3e-16 * ab)  # only the summation order over a vertex's elements differs
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("name", ["one_wall", "cylinder", "pore_small"])
+def test_jacobian_rows_match_oracle(name, op, mode):
+    a, m, p = case(name)
+    S = harness.Star(a, p.surf, True)
+    rng = np.random.RandomState(2)
+    F = ora.nfields(op)
+    u = rng.uniform(-1, 1, F * m.nv); a0 = rng.uniform(0, 1, m.nv); a1 = rng.uniform(0, 1, m.nv)
+    rp, col, val_o, ab = ora.jacobian(m, p, op, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11, want_abs=True)
+    rp2, col2, val = S.jacobian(op, p.sys, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11)
+    assert np.array_equal(col, col2)
+    assert np.all(np.abs(val - val_o) <= 1e-12 * ab + 1e-300)
+    if mode == 0:
+        # off-diagonal entries are two-term sums: the FD-faithful path reproduces the oracle bit for bit (same libm here)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        off = (rows % m.nv) != (col % m.nv)  # entries coupling two different vertices
+        assert np.array_equal(val[off], val_o[off])
+
+
+def test_mesh_errors_are_detected():
+    a, m, p = case("one_wall")
+    bad = dict(a); bad["ba"], bad["bb"], bad["bphys"] = a["ba"][:-1], a["bb"][:-1], a["bphys"][:-1]
+    with pytest.raises(RuntimeError, match="error 4"):   # boundary face without boundary segment
+        harness.Star(bad, p.surf)
+    bad = dict(a); bad["ba"] = a["ba"].copy(); bad["ba"][0] = a["tri"][10, 0]; bad["bb"] = a["bb"].copy(); bad["bb"][0] = a["tri"][10, 1]
+    with pytest.raises(RuntimeError):
+        harness.Star(bad, p.surf)
+    # two triangles touching in one vertex only -> that vertex has two fans (non-manifold)
+    bow = dict(x=np.array([0., 1, 0, -1, 0]), y=np.array([0., 1, 1, -1, -1]), tri=np.array([[0, 1, 2], [0, 3, 4]], dtype=np.int32),
+               ba=np.zeros(0, np.int32), bb=np.zeros(0, np.int32), bphys=np.zeros(0, np.int32))
+    with pytest.raises(RuntimeError, match="error 2"):
+        harness.Star(bow, p.surf)
+    deg = dict(a); deg["x"] = a["x"].copy(); deg["y"] = a["y"].copy()
+    t = a["tri"][0]; deg["x"][t[2]] = deg["x"][t[1]]; deg["y"][t[2]] = deg["y"][t[1]]
+    with pytest.raises(RuntimeError):
+        harness.Star(deg, p.surf)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pnp_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(pnp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 40
+    from dune_pnp_b200 import capi
+    lib = capi.lib()  # raises if the CUDA library has not been built -- there is no fallback
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dune_pnp_b200 import capi
+    with pytest.raises(capi.PnpError) as e:
+        capi.Context(0)
+    assert e.value.status == 6  # PNP_E_CUDA

@@ -1,0 +1,182 @@
+"""CPU tests of the oracle itself.  The reference ships no golden vectors and cannot be built here (no DUNE), so the
+oracle is PARITY UNPINNED against real PDELab; what pins it instead: patch tests, exact-derivative vs finite-difference
+agreement, an independent 1-D boundary-value solve of the one-wall Poisson-Boltzmann problem (the analytic anchor of
+/root/reference/test/one_wall_dh/one_wall.gp), h-convergence, and regression against the committed golden solutions."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oracle import binding as ora
+
+
+def case(name, levels=0):
+    m = ora.Mesh.from_arrays(**util.load_mesh_arrays(name)).refine(levels)
+    return m, ora.Params.read(util.cfg_path(name))
+
+
+def csr(rp, col, val):
+    import scipy.sparse as sp
+    return sp.csr_matrix((val, col, rp))
+
+
+@pytest.mark.parametrize("name,nv,nT,nB", [("one_wall", 46, 64, 26), ("sphere", 213, 357, 67), ("cylinder", 311, 541, 79),
+                                           ("pore_small", 320, 545, 93), ("pore", 3048, 5744, 350)])
+def test_fixture_sizes_match_survey(name, nv, nT, nB):
+    m, _ = case(name)
+    assert (m.nv, m.nT, m.nB) == (nv, nT, nB)
+
+
+def test_gmsh_reader_semantics(tmp_path):
+    a = util.load_mesh_arrays("one_wall")
+    path = str(tmp_path / "m.msh")
+    util.write_gmsh(path, a, shuffle_nodes=True, extra_nodes=2)  # node order in the file and unused nodes are irrelevant
+    m = ora.Mesh.read_gmsh(path)
+    for k in a:
+        assert np.array_equal(getattr(m, k), a[k]), k
+
+
+def test_config_reader(tmp_path):
+    p = ora.Params.read(util.cfg_path("pore"))
+    assert p.sys[0] == 7 and p.sys[1] == 1 and p.sys[4] == 3.1415 and p.sys[7] == 1e-9 and p.sys[8] == 1e-8
+    assert p.surf[0, 0] == 1 and p.surf[0, 1] == 1.1 and p.surf[4, 0] == 0 and p.surf[4, 2] == 24.1
+    bad = tmp_path / "bad.cfg"
+    bad.write_text("[system]\nn_surfaces=1\n[mesh]\nfilename=x.msh\n[surface_0]\ncoulombBtype=0\n")
+    with pytest.raises(RuntimeError, match="coulombPotential"):  # only the value matching the type is required
+        ora.Params.read(str(bad))
+    with pytest.raises(RuntimeError):
+        ora.Params.read(str(tmp_path / "missing.cfg"))
+
+
+@pytest.mark.parametrize("name", ["one_wall", "pore_small"])
+def test_refinement_counts_and_geometry(name):
+    m, _ = case(name)
+    f = m.refine(1)
+    nE = m.nv + m.nT - 1  # Euler characteristic 1
+    assert (f.nv, f.nT, f.nB) == (m.nv + nE, 4 * m.nT, 2 * m.nB)
+
+    def area(mm):
+        x, y, t = mm.x, mm.y, mm.tri
+        return 0.5 * np.abs((x[t[:, 1]] - x[t[:, 0]]) * (y[t[:, 2]] - y[t[:, 0]]) - (x[t[:, 2]] - x[t[:, 0]]) * (y[t[:, 1]] - y[t[:, 0]])).sum()
+    assert abs(area(f) - area(m)) <= 1e-12 * area(m)
+    assert np.array_equal(f.bphys[0::2], m.bphys) and np.array_equal(f.bphys[1::2], m.bphys)
+    assert np.array_equal(f.x[:m.nv], m.x)  # old vertices keep their index
+
+
+def test_patch_test_poisson_laplace():
+    """A linear field has zero Laplace residual at every vertex that is not on the boundary (planar case)."""
+    m, p = case("sphere")
+    u = 0.3 + 1.7 * m.x - 0.4 * m.y
+    c = np.full(m.nv, 0.06)
+    r, ab = ora.residual(m, p, ora.OP_POISSON, u, c, c, want_abs=True)
+    onb = np.zeros(m.nv, bool); onb[m.ba] = True; onb[m.bb] = True
+    assert np.max(np.abs(r[~onb]) / ab[~onb]) < 1e-13
+
+
+def test_mass_operator_integrates_area():
+    m, p = case("cylinder")
+    # element contributions of M*1 are int phi_i > 0; their sum (taken before the Dirichlet rows are zeroed) is |Omega|
+    _, contrib = ora.residual(m, p, ora.OP_MASS, np.ones(m.nv), want_abs=True)
+    x, y, t = m.x, m.y, m.tri
+    area = 0.5 * np.abs((x[t[:, 1]] - x[t[:, 0]]) * (y[t[:, 2]] - y[t[:, 0]]) - (x[t[:, 2]] - x[t[:, 0]]) * (y[t[:, 1]] - y[t[:, 0]])).sum()
+    assert abs(contrib.sum() - area) <= 1e-12 * area
+
+
+@pytest.mark.parametrize("op", [ora.OP_PB, ora.OP_POISSON, ora.OP_DIFFUSION, ora.OP_MASS, ora.OP_PNP])
+@pytest.mark.parametrize("name", ["one_wall", "cylinder"])
+def test_fd_jacobian_agrees_with_exact_derivative(name, op):
+    m, p = case(name)
+    rng = np.random.RandomState(0)
+    F = ora.nfields(op)
+    u = rng.uniform(-1, 1, F * m.nv); a0 = rng.uniform(0, 1, m.nv); a1 = rng.uniform(0, 1, m.nv)
+    _, _, fd = ora.jacobian(m, p, op, u, a0, a1, valency=-1.0, mode=0, eps=1e-7)
+    _, _, ex = ora.jacobian(m, p, op, u, a0, a1, valency=-1.0, mode=1)
+    assert np.max(np.abs(fd - ex)) <= 2e-6 * np.max(np.abs(ex))
+    # reference epsilon 1e-11 (PDELab <= 1.1): noise floor ~ eps_mach/eps = 1e-5
+    _, _, fd11 = ora.jacobian(m, p, op, u, a0, a1, valency=-1.0, mode=0, eps=1e-11)
+    assert np.max(np.abs(fd11 - ex)) <= 1e-3 * np.max(np.abs(ex))
+
+
+def test_pnp_cross_coupling_blocks_are_exact_zeros_under_fd():
+    """The (c+, c-) and (c-, c+) blocks stay exact zeros under the reference's finite differences -- the product stores 7 planes."""
+    m, p = case("cylinder")
+    u = np.random.RandomState(1).uniform(-1, 1, 3 * m.nv)
+    rp, col, val = ora.jacobian(m, p, ora.OP_PNP, u, mode=0)
+    A = csr(rp, col, val).toarray()
+    nv = m.nv
+    assert np.all(A[nv:2 * nv, 2 * nv:] == 0.0) and np.all(A[2 * nv:, nv:2 * nv] == 0.0)
+
+
+def test_dirichlet_rows_and_columns():
+    m, p = case("pore_small")
+    u = np.random.RandomState(2).uniform(-1, 1, 3 * m.nv)
+    rp, col, val = ora.jacobian(m, p, ora.OP_PNP, u)
+    d = ora.dirichlet(m, p, 3)
+    assert d.reshape(3, -1).sum(1).tolist() == [20, 20, 20]
+    A = csr(rp, col, val).toarray()
+    for i in np.where(d)[0]:
+        row = A[i].copy(); row[i] -= 1.0
+        assert not row.any() and not np.delete(A[:, i], i).any()
+    r = ora.residual(m, p, ora.OP_PNP, u)
+    assert not r[d].any()
+
+
+def test_one_wall_pb_against_1d_boundary_value_problem():
+    """PB between a charged wall (flux 0.1) and a grounded wall: the 2-D solve must reproduce the 1-D problem
+    u'' = 8*PI*l_b*c0*sinh(u), u'(0) = +0.1 (weak form: du/dn = -j), u(5) = 0, to O(h^2)."""
+    from scipy.integrate import solve_bvp
+    k2 = 8 * 3.1415 * 1.0 * 0.06
+    sol = solve_bvp(lambda x, y: np.vstack([y[1], k2 * np.sinh(y[0])]), lambda ya, yb: np.array([ya[1] - 0.1, yb[0]]),
+                    np.linspace(0, 5, 200), np.zeros((2, 200)), tol=1e-10)
+    errs = []
+    for lev in (1, 2, 3):
+        m, p = case("one_wall", lev)
+        opts = ora.newton_opts(p, prec=ora.PREC_SSOR); opts[0], opts[2], opts[12] = 1e-10, 1e-8, 5000
+        u, res = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+        assert res["converged"]
+        errs.append(np.max(np.abs(u - sol.sol(m.x)[0])))
+    assert errs[2] < 2e-4 * 0.0822 * 50  # |u|max = 0.082
+    assert errs[0] / errs[1] > 2.5 and errs[1] / errs[2] > 2.5  # second-order convergence
+
+
+def test_linear_solvers_against_dense_solve():
+    m, p = case("sphere")
+    c = np.full(m.nv, 0.06)
+    rp, col, val = ora.jacobian(m, p, ora.OP_POISSON, np.zeros(m.nv), c, c, mode=1)
+    A = csr(rp, col, val).toarray()
+    b = np.random.RandomState(3).uniform(-1, 1, m.nv)
+    x_ref = np.linalg.solve(A, b)
+    for solver in (ora.SOLVER_BCGS, ora.SOLVER_CG):
+        for prec in (ora.PREC_NONE, ora.PREC_JACOBI, ora.PREC_SSOR):
+            x, info = ora.linsolve(rp, col, val, b, 1e-12, 2000, solver, prec)
+            assert info["converged"] and np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+    it_none = ora.linsolve(rp, col, val, b, 1e-8, 2000, ora.SOLVER_CG, ora.PREC_NONE)[1]["iterations"]
+    it_ssor = ora.linsolve(rp, col, val, b, 1e-8, 2000, ora.SOLVER_CG, ora.PREC_SSOR)[1]["iterations"]
+    assert it_ssor < it_none
+
+
+def test_bcextension_interpolation_rules():
+    m, p = case("pore_small")
+    pb = np.random.RandomState(5).uniform(-1, 1, m.nv)
+    d = ora.dirichlet(m, p, 1, 0)
+    phi = ora.interpolate(m, p, 0, pb); cp = ora.interpolate(m, p, 1, pb); cm = ora.interpolate(m, p, 2, pb)
+    # away from Dirichlet vertices: the PB-derived guess (dirichlet_bc.hh:99,107,115)
+    assert np.array_equal(phi[~d], pb[~d])
+    assert np.allclose(cp[~d], 0.06 * np.exp(-pb[~d]), rtol=1e-15) and np.allclose(cm[~d], 0.06 * np.exp(pb[~d]), rtol=1e-15)
+    # on Dirichlet vertices: one of the configured boundary values
+    assert set(np.unique(phi[d])) <= {0.0, 24.1} and set(np.unique(cp[d])) == {0.06}
+
+
+@pytest.mark.parametrize("name", ["one_wall", "cylinder", "pore_small"])
+def test_golden_solutions_regression(name):
+    """The committed golden vectors (scripts/make_golden_solutions.py) are reproduced by the oracle."""
+    g = np.load(os.path.join(util.GOLDEN, name + "_solution.npz"))
+    m, p = case(name)
+    p.sys[5] = 20000; p = ora.Params.from_flat(p.sys, p.surf)
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR); opts[0], opts[2] = 1e-11, 1e-9
+    pb, r0 = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+    u0 = np.concatenate([ora.interpolate(m, p, k, pb) for k in range(3)])
+    u, r = ora.newton(m, p, ora.OP_PNP, u0, opts)
+    assert r0["iterations"] == int(g["pb_newton_iterations"]) and r["iterations"] == int(g["pnp_newton_iterations"])
+    assert np.array_equal(pb, g["pb"]) and np.array_equal(u0, g["u0"]) and np.array_equal(u, g["u"])
