@@ -9,8 +9,8 @@ flow: PB Newton -> interpolate(BCExtension) -> PNP Newton) and carried to the fi
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--levels L] [--impl reference]
 
-N > 1 (torchrun, one rank per GPU): see DESIGN.md "multi-GPU"; until the partitioned solver lands every rank
-runs the N = 1 problem and the line says so ("scaling": "replicas").
+N > 1 (torchrun, one rank per GPU): the SAME global problem is split into N subdomains (strong scaling); NCCL carries
+halo values and scalar sums only (DESIGN.md "multi-GPU").
 """
 import argparse
 import json
@@ -142,8 +142,8 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
-def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
-    """Reference flow on the coarse level, then nested iteration to the fine mesh. Returns (op, solver, u_s)."""
+def coarse_stage(c, capi, coarse_level, jac_mode, prec_steps, verbose):
+    """Reference flow on the coarse level: PB Newton -> interpolate(BCExtension) -> PNP Newton. Returns the 3-field vector."""
     def solver():
         return c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0)
     c.mesh_refine(coarse_level); c.mesh_finalize(True)
@@ -159,10 +159,53 @@ def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
     if verbose:
         print("# coarse level %d: PNP Newton %d its, linear %s" % (coarse_level, r.iterations,
               list(r.linear_iterations_history[:r.n_history])), file=sys.stderr, flush=True)
+    return vu
+
+
+def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
+    """N = 1: coarse solve, then nested iteration to the fine mesh on the device. Returns (op, solver, u_s)."""
+    vu = coarse_stage(c, capi, coarse_level, jac_mode, prec_steps, verbose)
     c.carry_set([vu])
     c.mesh_refine(levels - coarse_level); c.mesh_finalize(True)
     us = c.vec(3); c.carry_get(0, us)
-    return c.operator(capi.OP_PNP, 0), solver(), us
+    return c.operator(capi.OP_PNP, 0), c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0), us
+
+
+def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose, rank, world, dist):
+    """N > 1: every rank solves the (small) coarse problem, keeps its part of the coarse mesh plus one ghost layer,
+    refines it on its GPU carrying the coarse solution, trims the ghost layer, and builds the halo plan."""
+    from dune_pnp_b200 import partition
+    vu = coarse_stage(c, capi, coarse_level, jac_mode, prec_steps, verbose)
+    a0 = c.mesh_get()
+    u0 = c.download(vu, 3).reshape(3, -1)
+    tri = a0["tri"]
+    part = partition.rcb_partition(a0["x"][tri].mean(1), a0["y"][tri].mean(1), world)
+    lm = partition.extract_local(a0, part, rank, {"u": u0})
+    L = levels - coarse_level
+    c.mesh_set(lm.x, lm.y, lm.tri, lm.ba, lm.bb, lm.bphys)
+    c.carry_set_host(lm.fields["u"])
+    c.mesh_refine(L)
+    fine = c.mesh_get()
+    uf = c.carry_get_host(0, 3)
+    lmf = partition.LocalMesh(fine["x"], fine["y"], fine["tri"], np.repeat(lm.tag, 4 ** L), fine["ba"], fine["bb"],
+                              fine["bphys"], {"u": uf}).trim(rank)
+
+    def all_gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    plan = partition.finalize(lmf, rank, world, all_gather)
+    uid = [capi.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    c.mesh_set_local(plan.n_own, plan.x, plan.y, plan.tri, plan.ba, plan.bb, plan.bphys)
+    c.comm_init(rank, world, uid[0])
+    c.halo_set(plan.nbr, plan.send_ptr, plan.send_idx, plan.recv_ptr)
+    c.mesh_finalize(True)
+    us = c.vec(3, plan.fields["u"].reshape(-1))
+    if verbose:
+        print("# rank %d: %d owned + %d ghost vertices, %d neighbours" % (rank, plan.n_own, plan.nv - plan.n_own, len(plan.nbr)),
+              file=sys.stderr, flush=True)
+    return c.operator(capi.OP_PNP, 0), c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0), us
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -177,10 +220,19 @@ def run_gpu(args, rank, world, local_rank):
     c.mesh_set(**a); c.params_read(cfg)
     jac_mode = capi.JAC_FD_FAITHFUL if args.jac == "fd" else capi.JAC_ANALYTIC
     t_setup = time.perf_counter()
-    h, s, us = build_state(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, rank == 0 and args.verbose)
+    if world == 1:
+        h, s, us = build_state(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, args.verbose)
+    else:
+        h, s, us = build_state_partitioned(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, args.verbose,
+                                           rank, world, dist)
     sizes = c.mesh_sizes()
-    nv, ns = sizes["nv"], sizes["nslots"]
-    ndof = 3 * nv
+    nv, ns = sizes["nv"], sizes["nslots"]       # local vertices (owned + ghost), local matrix slots
+    n_own = c.mesh_owned()
+    ndof = 3 * nv                                # local vector length (host buffers of the end-to-end leg)
+    tot = torch.tensor([3 * n_own, ns, sizes["nT"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    gdof, gslots = int(tot[0].item()), int(tot[1].item())
     t_setup = time.perf_counter() - t_setup
     u = c.vec(3)
     opts = c.newton_opts(jac_mode=jac_mode, max_iterations=1)
@@ -245,23 +297,24 @@ def run_gpu(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     # algorithmic bytes of one fine-level 3-field SpMV (DESIGN.md "SpMV"): 7 value planes + column index per
     # slot, row pointer + x read + y written per vertex
-    spmv_bytes = (7 * 8 + 4) * ns + (4 + 2 * 3 * 8) * nv
+    spmv_bytes = (7 * 8 + 4) * ns + (4 + 2 * 3 * 8) * n_own   # rank 0's share
     spmv_avg_s = spmv_ms / 1e3 / max(n_spmv, 1)
     achieved = spmv_bytes / spmv_avg_s / 1e9
     asm_s = float(np.mean([x.seconds_assembly for x in stats]))
     cpu = cpu_newton_step(args.cpu_level) if not args.no_cpu else None
-    replicas = world if world > 1 else 1
     line = {
-        "metric": METRIC, "value": replicas * ndof / sec_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": gdof / sec_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True,
-        "scaling": "strong" if world == 1 else "replicas", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "test/pore_pnp (pore.msh + pore.cfg) uniformly refined %d times: one monolithic PNP Newton "
                                "step (Jacobian assembly, BiCGSTAB + aggregation AMG, line search)" % args.levels,
-                   "levels": args.levels, "vertices": nv, "triangles": sizes["nT"], "dofs": ndof, "matrix_slots": ns,
+                   "levels": args.levels, "dofs": gdof, "matrix_slots": gslots,
+                   "rank0_owned_vertices": n_own, "rank0_ghost_vertices": nv - n_own,
+                   "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the level-%d mesh), halo exchange + scalar allreduce over NCCL, block-Jacobi AMG" % (world, args.coarse_level),
                    "jacobian": args.jac, "preconditioner": "AMG V(%d,%d) damped Jacobi" % (args.prec_steps, args.prec_steps),
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
-                   "l2_policy": "inputs larger than L2 (matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
-        "newton_step_s": sec_step, "assembled_dofs_per_s": ndof / asm_s if asm_s > 0 else None,
+                   "l2_policy": "inputs larger than L2 (per GPU: matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
+        "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,
         "krylov_iterations": int(r.linear_iterations), "line_search_trials": int(r.line_search_trials),
         "defect_before": r.first_defect, "defect_after": r.defect,
         "spmv_gbs": achieved, "spmv_launches_timed": n_spmv, "spmv_share_of_step": spmv_ms / 1e3 / max(sec_dev, 1e-30),
@@ -274,8 +327,8 @@ def run_gpu(args, rank, world, local_rank):
             "value": cpu["value"], "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "oracle (CPU restatement), pore mesh refined %d times (%d dofs), one Newton step: FD Jacobian + "
                       "BiCGSTAB/SSOR(1) (%d its) + line search, %.1f s" % (cpu["level"], cpu["dofs"], cpu["lin_its"], cpu["seconds"])},
-        "e2e": {"value": replicas * ndof / (wall_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 8 * ndof,
-                "d2h_bytes_per_step": 8 * ndof},
+        "e2e": {"value": gdof / (wall_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 8 * ndof * world,
+                "d2h_bytes_per_step": 8 * ndof * world},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -58,6 +58,18 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise ImportError("libpnp_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(make -C dune_pnp_b200/csrc)")
+        # libpnp_b200.so needs libnccl.so.2.  PyTorch bundles a newer NCCL under the same soname; whichever copy is
+        # loaded first serves both, so load the bundled one first (otherwise a later `import torch` would find the
+        # older system copy already mapped and fail to resolve its newer symbols).
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            if spec is not None and spec.submodule_search_locations:
+                cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    C.CDLL(cand, mode=C.RTLD_GLOBAL)
+        except Exception:
+            pass
         L = C.CDLL(LIB_PATH)
         L.pnp_last_error.restype = C.c_char_p
         L.pnp_launch_count.restype = C.c_long
@@ -139,6 +151,45 @@ class Context:
 
     def carry_get(self, index, vec):
         self._ck(lib().pnp_carry_get(self._h, index, vec))
+
+    def carry_set_host(self, field):
+        field = np.ascontiguousarray(field, dtype=np.float64)
+        self._ck(lib().pnp_carry_set_host(self._h, field.shape[0] if field.ndim == 2 else 1, _d(field)))
+
+    def carry_get_host(self, index, fields):
+        out = np.zeros((fields, self.mesh_sizes()["nv"]))
+        self._ck(lib().pnp_carry_get_host(self._h, index, _d(out)))
+        return out
+
+    def mesh_set_local(self, n_own, x, y, tri, ba, bb, bphys):
+        x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+        tri = np.ascontiguousarray(tri, dtype=np.int32); ba = np.ascontiguousarray(ba, dtype=np.int32)
+        bb = np.ascontiguousarray(bb, dtype=np.int32); bphys = np.ascontiguousarray(bphys, dtype=np.int32)
+        self._ck(lib().pnp_mesh_set_local(self._h, C.c_long(len(x)), C.c_long(n_own), _d(x), _d(y), C.c_long(len(tri)), _i(tri),
+                                          C.c_long(len(ba)), _i(ba), _i(bb), _i(bphys)))
+
+    def mesh_owned(self):
+        n = C.c_long()
+        self._ck(lib().pnp_mesh_owned(self._h, C.byref(n)))
+        return n.value
+
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        if lib().pnp_comm_unique_id(buf) != 0:
+            raise PnpError(6, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def comm_init(self, rank, world, unique_id):
+        self._ck(lib().pnp_comm_init(self._h, rank, world, C.c_char_p(unique_id) if world > 1 else None))
+
+    def halo_set(self, nbr, send_ptr, send_idx, recv_ptr):
+        nbr = np.ascontiguousarray(nbr, dtype=np.int32); send_ptr = np.ascontiguousarray(send_ptr, dtype=np.int32)
+        send_idx = np.ascontiguousarray(send_idx, dtype=np.int32); recv_ptr = np.ascontiguousarray(recv_ptr, dtype=np.int32)
+        self._ck(lib().pnp_halo_set(self._h, len(nbr), _i(nbr), _i(send_ptr), _i(send_idx), _i(recv_ptr)))
+
+    def halo_exchange(self, vec):
+        self._ck(lib().pnp_halo_exchange(self._h, vec))
 
     def mesh_finalize(self, renumber=True):
         self._ck(lib().pnp_mesh_finalize(self._h, int(renumber)))

@@ -64,7 +64,7 @@ __global__ void k_mis_select(const int* __restrict__ rp, const unsigned* __restr
       bool win = true;
       for (int k = rp[v] + 1; k < rp[v + 1]; k++) {
         const int w = (int)(col[k] & STAR_VMASK);
-        if (w == v || st[w] != 0) continue;
+        if (w >= nv || w == v || st[w] != 0) continue; // (ghost columns take no part in the local hierarchy)
         const unsigned pw = hash32((unsigned)w);
         if (pw > pv || (pw == pv && w > v)) { win = false; break; }
       }
@@ -79,7 +79,10 @@ __global__ void k_mis_cover(const int* __restrict__ rp, const unsigned* __restri
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     if (st[v] != 0) continue;
     bool covered = false;
-    for (int k = rp[v] + 1; k < rp[v + 1]; k++) if (st[col[k] & STAR_VMASK] == 1) { covered = true; break; }
+    for (int k = rp[v] + 1; k < rp[v + 1]; k++) {
+      const int w = (int)(col[k] & STAR_VMASK);
+      if (w < nv && st[w] == 1) { covered = true; break; }
+    }
     if (covered) st[v] = 2; else local++;
   }
   if (local) atomicAdd(undecided, local);
@@ -96,7 +99,7 @@ __global__ void k_attach(const int* __restrict__ rp, const unsigned* __restrict_
     double best = -1.0; int bw = -1;
     for (int k = rp[v] + 1; k < rp[v + 1]; k++) {
       const int w = (int)(col[k] & STAR_VMASK);
-      if (st[w] != 1) continue;
+      if (w >= nv || st[w] != 1) continue;
       const double s = fabs(vals[k]);
       if (s > best || (s == best && w < bw)) { best = s; bw = w; }
     }
@@ -109,7 +112,9 @@ __global__ void k_coarse_keys(const int* __restrict__ rp, const unsigned* __rest
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     const unsigned I = (unsigned)agg[v];
     for (int k = rp[v]; k < rp[v + 1]; k++) {
-      const unsigned J = (unsigned)agg[col[k] & STAR_VMASK];
+      const unsigned w = col[k] & STAR_VMASK;
+      if (w >= (unsigned)nv) { keys[k] = ~0ull; slot_id[k] = k; continue; } // ghost column: dropped (block-Jacobi over ranks)
+      const unsigned J = (unsigned)agg[w];
       keys[k] = ((uint64_t)I << 32) | (J == I ? 0u : J + 1u);
       slot_id[k] = k;
     }
@@ -338,6 +343,12 @@ bool coarsen(Ctx& c, Amg& A, int li) {
     PNP_CUDA(cub::DeviceRunLengthEncode::Encode(A.temp(bytes), bytes, skeys.p, ukeys.p, counts.p, d_nu.p, (int)ns, c.stream));
     int nu = 0;
     d_nu.download(&nu, 1, c.stream);
+    { // the run of dropped ghost-column slots (key ~0) sorts last: leave it out
+      uint64_t lastkey = 0;
+      PNP_CUDA(cudaMemcpyAsync(&lastkey, ukeys.p + (nu - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+      PNP_CUDA(cudaStreamSynchronize(c.stream));
+      if (lastkey == ~0ull) nu--;
+    }
     nl->nv = nc; nl->nslots = nu;
     PNP_CUDA(cudaMemsetAsync(counts.p + nu, 0, sizeof(int), c.stream));
     f.seg_ptr.alloc((size_t)nu + 1);
@@ -403,12 +414,12 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
   Amg& A = *S.amg;
   const int comp0 = M.comp0;
   A.comp0 = comp0;
-  if (!A.symbolic || A.NP != M.nplanes || A.nv0 != c.nv || A.nslots0 != c.nslots) {
+  if (!A.symbolic || A.NP != M.nplanes || A.nv0 != c.n_own || A.nslots0 != c.nslots) {
     A.L.clear();
     A.NP = M.nplanes; A.F = M.nplanes == 1 ? 1 : 3;
-    A.nv0 = c.nv; A.nslots0 = c.nslots;
+    A.nv0 = c.n_own; A.nslots0 = c.nslots;
     auto l0 = std::make_unique<Level>();
-    l0->nv = (int)c.nv; l0->nslots = c.nslots; l0->rp = c.rp.p; l0->col = c.adj.p; l0->vals = M.vals.p;
+    l0->nv = (int)c.n_own; l0->nslots = c.nslots; l0->rp = c.rp.p; l0->col = c.adj.p; l0->vals = M.vals.p;
     A.L.push_back(std::move(l0));
     // the hierarchy's strength of connection is read from the current matrix values, level by level
     for (int li = 0; li < 24; li++) {
@@ -423,6 +434,12 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
         KL(c, k_galerkin<7>, n.nslots, f.seg_ptr.p, f.seg_items.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
     }
     for (auto& l : A.L) alloc_work(A, *l);
+    { // level 0 iterates are SpMV inputs whose ghost columns must read as zero
+      Level& l0r = *A.L[0];
+      const size_t nall = (size_t)A.F * c.nv;
+      l0r.x.alloc(nall); l0r.x2.alloc(nall);
+      l0r.x.zero(c.stream); l0r.x2.zero(c.stream);
+    }
     A.symbolic = true;
     if (S.verbosity > 0) {
       std::printf("AMG hierarchy:");

@@ -70,7 +70,7 @@ static void coefficient_ptrs(Ctx& c, const Operator& op, const double** a0, cons
   }
 }
 
-void assemble_residual(Ctx& c, const Operator& op, const Vec& u, Vec& r) {
+void assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built (mesh finalized + parameters set?)");
   const int F = op_fields(op.op);
   PNP_REQUIRE(u.fields == F && r.fields == F, PNP_E_ARG, "vector field count does not match the operator");
@@ -78,7 +78,8 @@ void assemble_residual(Ctx& c, const Operator& op, const Vec& u, Vec& r) {
   coefficient_ptrs(c, op, &a0, &a1);
   const StarView M = c.star();
   const PhysParams P = c.phys(op.valency);
-  const int block = 128, grid = grid_for(c.nv, block, c.sm_count * 16);
+  const int block = 128, grid = grid_for(c.n_own, block, c.sm_count * 16);
+  halo_exchange(c, u.d.p, F); // ghost values of the state (no-op on one GPU)
   switch (op.op) {
     case OP_PB: k_residual<OP_PB><<<grid, block, 0, c.stream>>>(M, P, u.d.p, a0, a1, op.comp0, r.d.p); break;
     case OP_POISSON: k_residual<OP_POISSON><<<grid, block, 0, c.stream>>>(M, P, u.d.p, a0, a1, op.comp0, r.d.p); break;
@@ -102,7 +103,7 @@ static void launch_jac(Ctx& c, const Operator& op, const double* u, const double
                        int mode, double eps) {
   const StarView M = c.star();
   const PhysParams P = c.phys(op.valency);
-  const int block = 128, grid = grid_for(c.nv, block, c.sm_count * 16);
+  const int block = 128, grid = grid_for(c.n_own, block, c.sm_count * 16);
   if (mode == JAC_FD_FAITHFUL)
     k_jacobian<OP, JAC_FD_FAITHFUL><<<grid, block, 0, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, A.vals.p, c.nslots);
   else
@@ -110,7 +111,7 @@ static void launch_jac(Ctx& c, const Operator& op, const double* u, const double
   PNP_CHECK_LAUNCH(); c.launches++;
 }
 
-void assemble_jacobian(Ctx& c, const Operator& op, const Vec& u, Matrix& A, int mode, double eps) {
+void assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, double eps) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built (mesh finalized + parameters set?)");
   PNP_REQUIRE(u.fields == op_fields(op.op), PNP_E_ARG, "vector field count does not match the operator");
   PNP_REQUIRE(A.op == op.op, PNP_E_ARG, "matrix belongs to another operator type");
@@ -118,6 +119,7 @@ void assemble_jacobian(Ctx& c, const Operator& op, const Vec& u, Matrix& A, int 
   const double *a0, *a1;
   coefficient_ptrs(c, op, &a0, &a1);
   A.comp0 = op.comp0;
+  halo_exchange(c, u.d.p, u.fields);
   switch (op.op) {
     case OP_PB: launch_jac<OP_PB>(c, op, u.d.p, a0, a1, A, mode, eps); break;
     case OP_POISSON: launch_jac<OP_POISSON>(c, op, u.d.p, a0, a1, A, mode, eps); break;

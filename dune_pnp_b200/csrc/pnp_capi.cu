@@ -103,23 +103,59 @@ long pnp_launch_count(pnp_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
 pnp_status pnp_mesh_set(pnp_ctx* ctx, long nv, const double* x, const double* y, long nT, const int* tri, long nB,
                         const int* ba, const int* bb, const int* bphys) {
-  API_BEGIN(ctx) mesh_set(c, nv, x, y, nT, tri, nB, ba, bb, bphys); API_END
+  API_BEGIN(ctx) mesh_set(c, nv, x, y, nT, tri, nB, ba, bb, bphys, nv); API_END
+}
+pnp_status pnp_mesh_set_local(pnp_ctx* ctx, long nv, long n_own, const double* x, const double* y, long nT, const int* tri,
+                              long nB, const int* ba, const int* bb, const int* bphys) {
+  API_BEGIN(ctx) mesh_set(c, nv, x, y, nT, tri, nB, ba, bb, bphys, n_own); API_END
+}
+pnp_status pnp_comm_unique_id(char* out128) {
+  try { comm_unique_id(out128); return PNP_OK; } catch (...) { return PNP_E_CUDA; }
+}
+pnp_status pnp_comm_init(pnp_ctx* ctx, int rank, int world, const char* unique_id128) {
+  API_BEGIN(ctx) comm_init(c, rank, world, unique_id128); API_END
+}
+pnp_status pnp_halo_set(pnp_ctx* ctx, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr) {
+  API_BEGIN(ctx) halo_set(c, n_nbr, nbr, send_ptr, send_idx, recv_ptr); API_END
+}
+pnp_status pnp_halo_exchange(pnp_ctx* ctx, int vec_handle) {
+  API_BEGIN(ctx)
+  halo_exchange(c, c.vec(vec_handle).d.p, c.vec(vec_handle).fields);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
 }
 pnp_status pnp_mesh_read_gmsh(pnp_ctx* ctx, const char* path) {
   API_BEGIN(ctx)
   std::vector<double> x, y; std::vector<int> tri, ba, bb, ph;
   read_gmsh_file(path, x, y, tri, ba, bb, ph);
   mesh_set(c, (long)x.size(), x.data(), y.data(), (long)tri.size() / 3, tri.data(), (long)ba.size(), ba.data(), bb.data(),
-           ph.data());
+           ph.data(), (long)x.size());
   API_END
 }
 pnp_status pnp_mesh_refine(pnp_ctx* ctx, int levels) { API_BEGIN(ctx) mesh_refine(c, levels); API_END }
 pnp_status pnp_carry_set(pnp_ctx* ctx, const int* vec_handles, int n) { API_BEGIN(ctx) carry_set(c, vec_handles, n); API_END }
 pnp_status pnp_carry_get(pnp_ctx* ctx, int index, int vec_handle) { API_BEGIN(ctx) carry_get(c, index, c.vec(vec_handle)); API_END }
+pnp_status pnp_carry_set_host(pnp_ctx* ctx, int fields, const double* host) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.nv > 0 && fields >= 1 && host, PNP_E_ARG, "no mesh / bad field count");
+  Vec cf; cf.fields = fields; cf.d.alloc((size_t)fields * c.nv);
+  cf.d.upload(host, (size_t)fields * c.nv, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.carry.clear();
+  c.carry.push_back(std::move(cf));
+  API_END
+}
+pnp_status pnp_carry_get_host(pnp_ctx* ctx, int index, double* host) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(index >= 0 && index < (int)c.carry.size() && host, PNP_E_ARG, "no such carried field");
+  c.carry[index].d.download(host, c.carry[index].d.n, c.stream);
+  API_END
+}
 pnp_status pnp_mesh_finalize(pnp_ctx* ctx, int renumber) { API_BEGIN(ctx) mesh_finalize(c, renumber != 0); API_END }
 pnp_status pnp_mesh_sizes(pnp_ctx* ctx, long* nv, long* nT, long* nB, long* nslots) {
   API_BEGIN(ctx)
-  if (nv) *nv = c.nv; if (nT) *nT = c.nT; if (nB) *nB = c.nB; if (nslots) *nslots = c.finalized ? c.nslots : 0;
+  if (nv) *nv = c.nv;
+  if (nT) *nT = c.nT; if (nB) *nB = c.nB; if (nslots) *nslots = c.finalized ? c.nslots : 0;
   API_END
 }
 pnp_status pnp_mesh_get(pnp_ctx* ctx, double* x, double* y, int* tri, int* ba, int* bb, int* bphys) {
@@ -252,12 +288,12 @@ pnp_status pnp_vec_axpy(pnp_ctx* ctx, int y, double a, int x) {
   API_END
 }
 pnp_status pnp_vec_norm(pnp_ctx* ctx, int x, double* out) {
-  API_BEGIN(ctx) *out = vec_norm(c, c.vec(x).d.p, (long)c.vec(x).d.n); API_END
+  API_BEGIN(ctx) *out = vec_norm(c, c.vec(x).d.p, c.n_own * c.vec(x).fields); API_END
 }
 pnp_status pnp_vec_dot(pnp_ctx* ctx, int x, int y, double* out) {
   API_BEGIN(ctx)
   PNP_REQUIRE(c.vec(y).d.n == c.vec(x).d.n, PNP_E_ARG, "vector sizes differ");
-  *out = vec_dot(c, c.vec(x).d.p, c.vec(y).d.p, (long)c.vec(x).d.n);
+  *out = vec_dot(c, c.vec(x).d.p, c.vec(y).d.p, c.n_own * c.vec(x).fields);
   API_END
 }
 pnp_status pnp_vec_pack3(pnp_ctx* ctx, int dst3, int phi, int cp, int cm) {
@@ -369,8 +405,10 @@ pnp_status pnp_slp_apply(pnp_ctx* ctx, int op, int u, int solver, double reducti
   to_lin(lr, out);
   API_END
 }
+pnp_status pnp_mesh_owned(pnp_ctx* ctx, long* n_own) { API_BEGIN(ctx) if (n_own) *n_own = c.n_own; API_END }
 pnp_status pnp_interpolate_bcext(pnp_ctx* ctx, int component, int pb_vec, int out_vec) {
   API_BEGIN(ctx)
+  PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "interpolate(BCExtension) follows the global element order: run it before partitioning");
   interpolate_bcext(c, component, pb_vec >= 0 ? &c.vec(pb_vec) : nullptr, c.vec(out_vec));
   API_END
 }

@@ -114,6 +114,15 @@ struct Ctx {
   int sm_count = 148;
   // canonical mesh, device resident (external numbering = Gmsh-compressed / refinement rule)
   long nv = 0, nT = 0, nB = 0;
+  // Rows exist for the first n_own vertices; on one GPU n_own == nv.  With a partitioned mesh the vertices
+  // [n_own, nv) are ghosts: columns of owned rows whose values arrive by halo exchange (pnp_comm.cu).
+  long n_own = 0;
+  int rank = 0, world = 1;
+  void* nccl = nullptr;                 // ncclComm_t
+  std::vector<int> halo_nbr, halo_send_ptr, halo_recv_ptr; // per neighbour rank: ranges into send list / ghost block
+  std::vector<int> halo_send_ext;       // send list in the caller's local numbering
+  DBuf<int> halo_send_idx;              // ... in internal numbering
+  DBuf<double> halo_send_buf;
   DBuf<double> cx, cy;
   DBuf<int> ctri, cba, cbb, cbphys;
   // star structure, internal numbering
@@ -159,7 +168,7 @@ struct Ctx {
   DBuf<double> red_partial, red_out;
   double* h_red = nullptr; // pinned
 
-  StarView star() const { return StarView{rp.p, adj.p, xy.p, dmask.p, (int)nv}; }
+  StarView star() const { return StarView{rp.p, adj.p, xy.p, dmask.p, (int)n_own}; }
   PhysParams phys(double valency) const {
     PhysParams P; P.PI = params.PI; P.l_b = params.l_b; P.c0 = params.c0; P.valency = valency;
     P.cylindrical = params.cylindrical; return P;
@@ -176,10 +185,17 @@ inline int op_planes(int op) { return op == OP_PNP ? 7 : 1; }
 // ---- implemented across the translation units ----
 // pnp_setup.cu
 void mesh_set(Ctx&, long nv, const double* x, const double* y, long nT, const int* tri, long nB, const int* ba,
-              const int* bb, const int* bphys);
+              const int* bb, const int* bphys, long n_own);
 void mesh_refine(Ctx&, int levels);
 void mesh_finalize(Ctx&, bool renumber);
 void constraints_build(Ctx&);
+// pnp_comm.cu
+void comm_init(Ctx&, int rank, int world, const char* unique_id128);
+void comm_unique_id(char* out128);
+void halo_set(Ctx&, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr);
+void halo_finalize(Ctx&);
+void halo_exchange(Ctx&, double* x, int fields);
+void allreduce_sum(Ctx&, double* dev, int n);
 void carry_set(Ctx&, const int* handles, int n);
 void carry_get(Ctx&, int i, Vec& out);
 void vec_upload(Ctx&, Vec&, const double* host_lex);
@@ -192,10 +208,10 @@ void read_gmsh_file(const std::string& path, std::vector<double>& x, std::vector
 void read_config_file(const std::string& path, HostParams& p);
 void interpolate_bcext(Ctx&, int comp, const Vec* pb, Vec& out);
 // pnp_assembly.cu
-void assemble_residual(Ctx&, const Operator&, const Vec& u, Vec& r);
-void assemble_jacobian(Ctx&, const Operator&, const Vec& u, Matrix& A, int mode, double eps);
+void assemble_residual(Ctx&, const Operator&, Vec& u, Vec& r);   // refreshes the ghost part of u
+void assemble_jacobian(Ctx&, const Operator&, Vec& u, Matrix& A, int mode, double eps);
 // pnp_linalg.cu
-void spmv(Ctx&, const Matrix& A, const double* x, double* y);
+void spmv(Ctx&, const Matrix& A, double* x, double* y); // refreshes the ghost part of x
 double vec_norm(Ctx&, const double* x, long n);
 double vec_dot(Ctx&, const double* x, const double* y, long n);
 void vec_axpy(Ctx&, double a, const double* x, double* y, long n);

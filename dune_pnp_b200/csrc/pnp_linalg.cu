@@ -199,16 +199,18 @@ void ensure_red(Ctx& c) {
 void finish_reduce(Ctx& c, int nblocks, int nr, double* out) {
   k_reduce_final<<<1, RED_BLOCK, 0, c.stream>>>(c.red_partial.p, nblocks, nr, c.red_out.p);
   PNP_CHECK_LAUNCH(); c.launches++;
+  allreduce_sum(c, c.red_out.p, nr); // sum over ranks (no-op on one GPU)
   PNP_CUDA(cudaMemcpyAsync(c.h_red, c.red_out.p, nr * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   for (int j = 0; j < nr; j++) out[j] = c.h_red[j];
 }
 
 // y = A x with optional fused dots; returns them in dots[0..ndot)
-void spmv_dots(Ctx& c, const Matrix& A, const double* x, double* y, int ndot, const double* w1, double* dots) {
+void spmv_dots(Ctx& c, const Matrix& A, double* x, double* y, int ndot, const double* w1, double* dots) {
   ensure_red(c);
+  halo_exchange(c, x, A.nplanes == 1 ? 1 : 3); // ghost columns of x (no-op on one GPU)
   constexpr int LANES = 8;
-  const long nv = c.nv;
+  const long nv = c.n_own;
   const int grid = grid_for(nv * LANES, RED_BLOCK, c.sm_count * 8);
   const long st = c.nslots;
   c.prof_mark();
@@ -225,7 +227,7 @@ void spmv_dots(Ctx& c, const Matrix& A, const double* x, double* y, int ndot, co
 
 } // namespace
 
-void spmv(Ctx& c, const Matrix& A, const double* x, double* y) { spmv_dots(c, A, x, y, 0, nullptr, nullptr); }
+void spmv(Ctx& c, const Matrix& A, double* x, double* y) { spmv_dots(c, A, x, y, 0, nullptr, nullptr); }
 
 double vec_dot(Ctx& c, const double* x, const double* y, long n) {
   ensure_red(c);
@@ -257,9 +259,9 @@ void prec_setup(Ctx& c, Solver& S, const Matrix& A) {
   switch (S.prec) {
     case PNP_PREC_NONE: break;
     case PNP_PREC_JACOBI: {
-      const int g = grid_for(c.nv, 256);
-      if (A.nplanes == 1) k_diag_inverse<1><<<g, 256, 0, c.stream>>>(c.rp.p, A.vals.p, c.nslots, (int)c.nv, S.dinv.p);
-      else k_diag_inverse<7><<<g, 256, 0, c.stream>>>(c.rp.p, A.vals.p, c.nslots, (int)c.nv, S.dinv.p);
+      const int g = grid_for(c.n_own, 256);
+      if (A.nplanes == 1) k_diag_inverse<1><<<g, 256, 0, c.stream>>>(c.rp.p, A.vals.p, c.nslots, (int)c.n_own, S.dinv.p);
+      else k_diag_inverse<7><<<g, 256, 0, c.stream>>>(c.rp.p, A.vals.p, c.nslots, (int)c.n_own, S.dinv.p);
       PNP_CHECK_LAUNCH(); c.launches++;
       break;
     }
@@ -387,8 +389,8 @@ LinResult cg(Ctx& c, Solver& S, const Matrix& A, double* x, double* b, long n, d
 LinResult solver_apply(Ctx& c, Solver& S, const Matrix& A, Vec& z, Vec& r, double reduction) {
   PNP_REQUIRE(z.fields == r.fields && z.fields == (A.nplanes == 1 ? 1 : 3), PNP_E_ARG,
               "vector field count does not match the matrix");
-  const long n = c.nv * z.fields;
-  S.ensure(n);
+  const long n = c.n_own * z.fields; // owned dofs: what dots, norms and updates run over
+  S.ensure((size_t)c.nv * z.fields);  // work vectors carry a ghost part for the SpMV input
   ensure_red(c);
   auto t0 = std::chrono::steady_clock::now();
   prec_setup(c, S, A);

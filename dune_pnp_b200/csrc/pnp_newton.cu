@@ -19,11 +19,12 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton_opts& o, pnp_newton_result& R) {
   const int F = op_fields(op.op);
   PNP_REQUIRE(u.fields == F, PNP_E_ARG, "vector field count does not match the operator");
-  const long n = c.nv * F;
+  const long n = c.n_own * F, nall = c.nv * F;
   R = pnp_newton_result();
   Vec r, z, prev_u;
   r.fields = z.fields = prev_u.fields = F;
-  r.d.alloc(n); z.d.alloc(n); prev_u.d.alloc(n);
+  r.d.alloc(nall); z.d.alloc(nall); prev_u.d.alloc(nall);
+  r.d.zero(c.stream); z.d.zero(c.stream);
   Matrix A; A.op = op.op; A.nplanes = op_planes(op.op);
   A.vals.alloc((size_t)A.nplanes * c.nslots);
   const double t_start = now();
@@ -127,8 +128,9 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
 LinResult slp_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, double reduction, int jac_mode, double eps) {
   const int F = op_fields(op.op);
   PNP_REQUIRE(u.fields == F, PNP_E_ARG, "vector field count does not match the operator");
-  const long n = c.nv * F;
-  Vec r, z; r.fields = z.fields = F; r.d.alloc(n); z.d.alloc(n);
+  const long n = c.n_own * F, nall = c.nv * F;
+  Vec r, z; r.fields = z.fields = F; r.d.alloc(nall); z.d.alloc(nall);
+  r.d.zero(c.stream); z.d.zero(c.stream);
   Matrix A; A.op = op.op; A.nplanes = op_planes(op.op);
   A.vals.alloc((size_t)A.nplanes * c.nslots);
   assemble_jacobian(c, op, u, A, jac_mode, eps);

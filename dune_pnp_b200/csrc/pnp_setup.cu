@@ -101,11 +101,18 @@ __global__ void k_ring_fill(const uint64_t* __restrict__ keys, const unsigned* _
 // one BFace per boundary segment
 __global__ void k_bfaces(const int* __restrict__ ba, const int* __restrict__ bb, const int* __restrict__ ph, long nB,
                          const int* __restrict__ ext2int, const int* __restrict__ rp, const unsigned* __restrict__ adj,
-                         BFace* __restrict__ out, int* __restrict__ err) {
+                         int n_own, bool partitioned, BFace* __restrict__ out, int* __restrict__ err) {
   for (long s = blockIdx.x * (long)blockDim.x + threadIdx.x; s < nB; s += (long)gridDim.x * blockDim.x) {
     BFace bf;
-    if (!boundary_face_of(rp, adj, ext2int[ba[s]], ext2int[bb[s]], &bf)) atomicExch(err, 3);
-    bf.phys = ph[s]; bf.seg = (int)s;
+    const int a = ext2int[ba[s]], b = ext2int[bb[s]];
+    bool ok;
+    // the face is reconstructed from the fan of an OWNED end vertex; a face between two ghosts only
+    // contributes its Dirichlet flags (v[] stays -1)
+    if (a < n_own) ok = boundary_face_of(rp, adj, a, b, &bf);
+    else if (b < n_own) ok = boundary_face_of(rp, adj, b, a, &bf);
+    else { bf.v[0] = bf.v[1] = bf.v[2] = -1; bf.f = 0; ok = partitioned; }
+    if (!ok) atomicExch(err, 3);
+    bf.a = a; bf.b = b; bf.phys = ph[s]; bf.seg = (int)s;
     out[s] = bf;
   }
 }
@@ -148,12 +155,14 @@ struct CubTemp {
   do { kern<<<grid_for((n), 256), 256, 0, (ctx).stream>>>(__VA_ARGS__); PNP_CHECK_LAUNCH(); (ctx).launches++; } while (0)
 
 void mesh_set(Ctx& c, long nv, const double* x, const double* y, long nT, const int* tri, long nB, const int* ba,
-              const int* bb, const int* bphys) {
+              const int* bb, const int* bphys, long n_own) {
   PNP_REQUIRE(nv > 0 && nT > 0, PNP_E_ARG, "empty mesh");
   for (long i = 0; i < 3 * nT; i++) PNP_REQUIRE(tri[i] >= 0 && tri[i] < nv, PNP_E_MESH, "triangle vertex out of range");
   for (long i = 0; i < nB; i++)
     PNP_REQUIRE(ba[i] >= 0 && ba[i] < nv && bb[i] >= 0 && bb[i] < nv, PNP_E_MESH, "boundary vertex out of range");
-  c.nv = nv; c.nT = nT; c.nB = nB;
+  PNP_REQUIRE(n_own > 0 && n_own <= nv, PNP_E_ARG, "owned vertex count out of range");
+  c.nv = nv; c.nT = nT; c.nB = nB; c.n_own = n_own;
+  c.halo_nbr.clear(); c.halo_send_ptr.clear(); c.halo_recv_ptr.clear(); c.halo_send_ext.clear();
   c.invalidate_mesh_objects();
   c.carry.clear();
   c.cx.alloc(nv); c.cy.alloc(nv); c.ctri.alloc(3 * nT); c.cba.alloc(nB); c.cbb.alloc(nB); c.cbphys.alloc(nB);
@@ -164,6 +173,7 @@ void mesh_set(Ctx& c, long nv, const double* x, const double* y, long nT, const 
 
 void mesh_refine(Ctx& c, int levels) {
   PNP_REQUIRE(c.nv > 0, PNP_E_ARG, "no mesh set");
+  PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "device refinement works on an unpartitioned mesh (refine before partitioning)");
   CubTemp tmp;
   for (int l = 0; l < levels; l++) {
     const long nT = c.nT, nv = c.nv, nB = c.nB, nk = 3 * nT;
@@ -203,7 +213,7 @@ void mesh_refine(Ctx& c, int levels) {
     PNP_CUDA(cudaStreamSynchronize(c.stream));
     c.cx = std::move(nx); c.cy = std::move(ny); c.ctri = std::move(ntri);
     c.cba = std::move(na); c.cbb = std::move(nb); c.cbphys = std::move(np);
-    c.nv = nv + nE; c.nT = 4 * nT; c.nB = 2 * nB;
+    c.nv = nv + nE; c.nT = 4 * nT; c.nB = 2 * nB; c.n_own = c.nv;
   }
   c.invalidate_mesh_objects();
 }
@@ -232,18 +242,20 @@ void carry_get(Ctx& c, int i, Vec& out) {
 void mesh_finalize(Ctx& c, bool renumber) {
   PNP_REQUIRE(c.nv > 0, PNP_E_ARG, "no mesh set");
   PNP_REQUIRE(c.nv < STAR_MAX_VERTICES, PNP_E_MESH, "more than 2^27 vertices on one GPU");
-  const long nv = c.nv, nT = c.nT, nB = c.nB, nrec = 3 * nT;
+  const long nv = c.nv, nT = c.nT, nB = c.nB, nrec = 3 * nT, no = c.n_own;
   PNP_REQUIRE(nrec < (1l << 31), PNP_E_MESH, "more than 2^31 triangle corners on one GPU");
   CubTemp tmp;
   size_t bytes = 0;
   c.int2ext.alloc(nv); c.ext2int.alloc(nv);
   if (renumber) {
+    // owned vertices are reordered by first touch; ghosts keep their place (grouped by owner rank by the caller)
     DBuf<int> first(nv), first_sorted(nv), ids(nv);
     LAUNCH(c, k_fill_int, nv, first.p, nv, 0x7fffffff);
     LAUNCH(c, k_first_touch, nrec, c.ctri.p, nT, first.p);
     LAUNCH(c, k_iota, nv, ids.p, nv);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, first.p, first_sorted.p, ids.p, c.int2ext.p, (int)nv, 0, 32, c.stream);
-    PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(bytes), bytes, first.p, first_sorted.p, ids.p, c.int2ext.p, (int)nv,
+    LAUNCH(c, k_iota, nv, c.int2ext.p, nv);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, first.p, first_sorted.p, ids.p, c.int2ext.p, (int)no, 0, 32, c.stream);
+    PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(bytes), bytes, first.p, first_sorted.p, ids.p, c.int2ext.p, (int)no,
                                             0, 32, c.stream));
     c.launches += 2;
   } else {
@@ -254,7 +266,7 @@ void mesh_finalize(Ctx& c, bool renumber) {
   LAUNCH(c, k_gather_xy, nv, c.int2ext.p, c.cx.p, c.cy.p, nv, c.xy.p);
 
   DBuf<int> err(1); err.zero(c.stream);
-  DBuf<int> start(nv + 1), rowlen(nv + 1);
+  DBuf<int> start(no + 1), rowlen(no + 1);
   {
     DBuf<uint64_t> keys(nrec), skeys(nrec);
     DBuf<unsigned> pay(nrec), spay(nrec);
@@ -264,19 +276,19 @@ void mesh_finalize(Ctx& c, bool renumber) {
                                             c.stream));
     c.launches += 2;
     keys.release(); pay.release();
-    LAUNCH(c, k_rec_start, nv + 1, skeys.p, nrec, nv, start.p);
+    LAUNCH(c, k_rec_start, no + 1, skeys.p, nrec, no, start.p);
     rowlen.zero(c.stream);
-    LAUNCH(c, k_ring_count, nv, skeys.p, spay.p, start.p, nv, rowlen.p, err.p);
-    c.rp.alloc(nv + 1);
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, rowlen.p, c.rp.p, (int)(nv + 1), c.stream);
-    PNP_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(bytes), bytes, rowlen.p, c.rp.p, (int)(nv + 1), c.stream));
+    LAUNCH(c, k_ring_count, no, skeys.p, spay.p, start.p, no, rowlen.p, err.p);
+    c.rp.alloc(no + 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, rowlen.p, c.rp.p, (int)(no + 1), c.stream);
+    PNP_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(bytes), bytes, rowlen.p, c.rp.p, (int)(no + 1), c.stream));
     c.launches += 1;
     int ns = 0;
-    PNP_CUDA(cudaMemcpyAsync(&ns, c.rp.p + nv, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PNP_CUDA(cudaMemcpyAsync(&ns, c.rp.p + no, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     PNP_CUDA(cudaStreamSynchronize(c.stream));
     c.nslots = ns;
     c.adj.alloc(c.nslots);
-    LAUNCH(c, k_ring_fill, nv, skeys.p, spay.p, start.p, nv, c.rp.p, c.adj.p, err.p);
+    LAUNCH(c, k_ring_fill, no, skeys.p, spay.p, start.p, no, c.rp.p, c.adj.p, err.p);
   }
   int herr = 0;
   err.download(&herr, 1, c.stream);
@@ -286,17 +298,18 @@ void mesh_finalize(Ctx& c, bool renumber) {
   // boundary faces
   c.d_bfaces.alloc(nB);
   DBuf<int> nopen(1); nopen.zero(c.stream);
-  LAUNCH(c, k_count_open, nv, c.rp.p, c.adj.p, nv, nopen.p);
-  if (nB) LAUNCH(c, k_bfaces, nB, c.cba.p, c.cbb.p, c.cbphys.p, nB, c.ext2int.p, c.rp.p, c.adj.p, c.d_bfaces.p, err.p);
+  LAUNCH(c, k_count_open, no, c.rp.p, c.adj.p, no, nopen.p);
+  if (nB) LAUNCH(c, k_bfaces, nB, c.cba.p, c.cbb.p, c.cbphys.p, nB, c.ext2int.p, c.rp.p, c.adj.p, (int)no, no < nv, c.d_bfaces.p, err.p);
   err.download(&herr, 1, c.stream);
   PNP_REQUIRE(herr == 0, PNP_E_MESH, "a boundary segment (Gmsh line element) is not a boundary edge of the mesh");
   int hopen = 0;
   nopen.download(&hopen, 1, c.stream);
-  PNP_REQUIRE(hopen == nB, PNP_E_MESH, "boundary face without boundary segment (or duplicate segment)");
+  PNP_REQUIRE(no < nv || hopen == nB, PNP_E_MESH, "boundary face without boundary segment (or duplicate segment)");
   c.bfaces = c.d_bfaces.to_host(c.stream);
   c.dmask.alloc(nv); c.dmask.zero(c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   c.finalized = true; c.constraints_built = false;
+  halo_finalize(c);
   if (c.params.set) constraints_build(c);
 }
 
@@ -306,7 +319,6 @@ void mesh_finalize(Ctx& c, bool renumber) {
 void constraints_build(Ctx& c) {
   PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
   PNP_REQUIRE(c.params.set, PNP_E_ARG, "parameters not set");
-  static const int FV[3][2] = {{0, 1}, {0, 2}, {1, 2}};
   std::map<int, unsigned char> bits;
   std::map<int, std::vector<int>> items;
   for (size_t i = 0; i < c.bfaces.size(); i++) {
@@ -316,8 +328,9 @@ void constraints_build(Ctx& c) {
     const HostSurface& s = c.params.surfaces[b.phys];
     unsigned char m = 0;
     for (int k = 0; k < 3; k++) if (s.btype[k] == 0) m |= (unsigned char)(1u << k);
-    for (int l = 0; l < 2; l++) bits[b.v[FV[b.f][l]]] |= m;
-    for (int r = 0; r < 3; r++) items[b.v[r]].push_back((int)i * 4 + r);
+    bits[b.a] |= m; bits[b.b] |= m;
+    if (b.v[0] < 0) continue; // face between two ghost vertices: flags only
+    for (int r = 0; r < 3; r++) if (b.v[r] < c.n_own) items[b.v[r]].push_back((int)i * 4 + r);
   }
   std::vector<int> vtx; std::vector<unsigned char> vb;
   for (auto& kv : bits) { vtx.push_back(kv.first); vb.push_back(kv.second); }
@@ -409,6 +422,7 @@ template <class Fn> long walk_pattern(Ctx& c, const Operator& op, const HostStar
 
 long pattern_export(Ctx& c, int op_handle, int* rowptr, int* col) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built");
+  PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "pattern export works on an unpartitioned mesh");
   const Operator& op = c.oper(op_handle);
   HostStar h = fetch_star(c);
   const long nv = c.nv;
@@ -420,6 +434,7 @@ long pattern_export(Ctx& c, int op_handle, int* rowptr, int* col) {
 
 void matrix_export(Ctx& c, int op_handle, const Matrix& A, double* val) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built");
+  PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "matrix export works on an unpartitioned mesh");
   const Operator& op = c.oper(op_handle);
   PNP_REQUIRE(A.op == op.op, PNP_E_ARG, "matrix belongs to another operator type");
   HostStar h = fetch_star(c);

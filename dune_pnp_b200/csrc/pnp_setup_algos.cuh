@@ -114,12 +114,13 @@ struct BFace {
   int f;      // DUNE face index 0:(0,1) 1:(0,2) 2:(1,2)
   int phys;   // physical tag = index of [surface_i]
   int seg;    // boundarySegmentIndex (file order of the line element)
+  int a, b;   // the segment's end vertices (internal ids), also valid when no owned vertex touches the face
 };
 // Boundary segment (a,b) (internal ids): finds the one element that owns the edge from a's open fan.
 // Returns false if (a,b) is not a boundary edge of the mesh.
 PNP_HD bool boundary_face_of(const int* rp, const unsigned* adj, int a, int b, BFace* bf) {
   const int s0 = rp[a] + 1, s1 = rp[a + 1];
-  bf->v[0] = bf->v[1] = bf->v[2] = -1; bf->f = 0;
+  bf->v[0] = bf->v[1] = bf->v[2] = -1; bf->f = 0; bf->a = a; bf->b = b;
   if (s1 - s0 < 2 || (adj[s1 - 1] & STAR_HAS_TRI)) return false; // a is not a boundary vertex
   int st;
   if ((int)(adj[s0] & STAR_VMASK) == b) st = s0;                // first edge of the open fan

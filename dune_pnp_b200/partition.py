@@ -1,0 +1,198 @@
+"""Host-side domain decomposition for the multi-GPU path (one process per GPU).
+
+Stands in for `grid->loadBalance()` (/root/reference/src/pnp_solver_main.cc:108) and PDELab's non-overlapping
+ghost bookkeeping (`compute_ghosts`, stationary_pnp.hh:131).  Plumbing only -- numpy on the host, torch.distributed
+object collectives for the one-off plan exchange; the data path (assembly, SpMV, Krylov) runs in the CUDA library.
+
+Scheme (DESIGN.md "multi-GPU"):
+  * every rank holds the same coarse mesh and computes the same partition of its TRIANGLES by recursive coordinate
+    bisection of the centroids;
+  * rank p keeps its triangles plus every triangle that touches a vertex of one of its triangles (one ghost layer),
+    refines that local mesh uniformly (same midpoint rule as everywhere else, so shared vertices get bit-identical
+    coordinates on all ranks) and trims the ghost layer back to one element after each level;
+  * a vertex is owned by the lowest rank among the triangles around it; owners are resolved and the halo plan is
+    built by matching the (bitwise) coordinates of ghost vertices against owned vertices of the other ranks.
+"""
+import numpy as np
+
+
+def rcb_partition(cx, cy, nparts):
+    """Recursive coordinate bisection of points (triangle centroids) into `nparts` equal-count parts."""
+    part = np.zeros(len(cx), dtype=np.int32)
+
+    def split(idx, lo, n):
+        if n == 1:
+            part[idx] = lo
+            return
+        nl = n // 2
+        x, y = cx[idx], cy[idx]
+        key = x if (x.max() - x.min()) >= (y.max() - y.min()) else y
+        order = np.argsort(key, kind="stable")
+        k = (len(idx) * nl) // n
+        split(idx[order[:k]], lo, nl)
+        split(idx[order[k:]], lo + nl, n - nl)
+
+    split(np.arange(len(cx)), 0, nparts)
+    return part
+
+
+def _edge_keys(tri):
+    t = tri.astype(np.int64)
+    e = np.concatenate([t[:, [0, 1]], t[:, [0, 2]], t[:, [1, 2]]])
+    return (e.min(1) << 32) | e.max(1)
+
+
+class LocalMesh:
+    """A rank's piece of the mesh in its own vertex numbering: x, y, tri, tag (owner rank of each triangle), boundary
+    segments ba/bb/bphys, carried nodal fields (dict name -> (F, nv) arrays)."""
+
+    def __init__(self, x, y, tri, tag, ba, bb, bphys, fields=None):
+        self.x, self.y, self.tri, self.tag = x, y, tri.astype(np.int32), tag.astype(np.int32)
+        self.ba, self.bb, self.bphys = ba.astype(np.int32), bb.astype(np.int32), bphys.astype(np.int32)
+        self.fields = dict(fields or {})
+
+    @property
+    def nv(self):
+        return len(self.x)
+
+    def _compact(self, keep_tri):
+        """Keeps the given triangles, the vertices they use, and the boundary segments that are edges of kept triangles."""
+        tri = self.tri[keep_tri]
+        used = np.zeros(self.nv, dtype=bool)
+        used[tri.ravel()] = True
+        new_id = np.cumsum(used) - 1
+        keys = np.unique(_edge_keys(tri))
+        bk = (np.minimum(self.ba, self.bb).astype(np.int64) << 32) | np.maximum(self.ba, self.bb).astype(np.int64)
+        pos = np.searchsorted(keys, bk)
+        keep_b = (pos < len(keys)) & (keys[np.minimum(pos, len(keys) - 1)] == bk) if len(keys) else np.zeros(len(bk), bool)
+        fields = {k: v[:, used] for k, v in self.fields.items()}
+        return LocalMesh(self.x[used], self.y[used], new_id[tri], self.tag[keep_tri], new_id[self.ba[keep_b]],
+                         new_id[self.bb[keep_b]], self.bphys[keep_b], fields)
+
+    def trim(self, me):
+        """One ghost layer: my triangles + every triangle touching a vertex of one of my triangles."""
+        mine_v = np.zeros(self.nv, dtype=bool)
+        mine_v[self.tri[self.tag == me].ravel()] = True
+        keep = (self.tag == me) | mine_v[self.tri].any(axis=1)
+        return self._compact(keep)
+
+    def refine(self):
+        """Uniform red refinement with the library's rule (new vertex = nv + rank of the edge key; children
+        (a,ab,ac)(ab,b,bc)(ac,bc,c)(ab,bc,ac)); fields are P1-interpolated; children inherit tag / physical tag."""
+        keys = np.unique(_edge_keys(self.tri))
+        a = (keys >> 32).astype(np.int64); b = (keys & 0xffffffff).astype(np.int64)
+        nv = self.nv
+        x = np.concatenate([self.x, 0.5 * (self.x[a] + self.x[b])]); y = np.concatenate([self.y, 0.5 * (self.y[a] + self.y[b])])
+        fields = {k: np.concatenate([v, 0.5 * (v[:, a] + v[:, b])], axis=1) for k, v in self.fields.items()}
+
+        def mid(p, q):
+            p = p.astype(np.int64); q = q.astype(np.int64)
+            return (nv + np.searchsorted(keys, (np.minimum(p, q) << 32) | np.maximum(p, q))).astype(np.int32)
+        t = self.tri
+        ab, ac, bc = mid(t[:, 0], t[:, 1]), mid(t[:, 0], t[:, 2]), mid(t[:, 1], t[:, 2])
+        tri = np.stack([t[:, 0], ab, ac, ab, t[:, 1], bc, ac, bc, t[:, 2], ab, bc, ac], axis=1).reshape(-1, 3)
+        m = mid(self.ba, self.bb)
+        ba = np.stack([self.ba, m], axis=1).reshape(-1); bb = np.stack([m, self.bb], axis=1).reshape(-1)
+        return LocalMesh(x, y, tri, np.repeat(self.tag, 4), ba, bb, np.repeat(self.bphys, 2), fields)
+
+
+def extract_local(a, part, me, fields=None):
+    """Rank `me`'s local mesh (with one ghost layer) from the global arrays `a` and the triangle partition `part`."""
+    f = {k: np.asarray(v, dtype=np.float64).reshape(-1, len(a["x"])) for k, v in (fields or {}).items()}
+    lm = LocalMesh(np.asarray(a["x"], float), np.asarray(a["y"], float), np.asarray(a["tri"]), part, np.asarray(a["ba"]),
+                   np.asarray(a["bb"]), np.asarray(a["bphys"]), f)
+    return lm.trim(me)
+
+
+def _coord_keys(x, y):
+    k = np.empty((len(x), 2), dtype=np.uint64)
+    k[:, 0] = np.ascontiguousarray(x, dtype=np.float64).view(np.uint64)
+    k[:, 1] = np.ascontiguousarray(y, dtype=np.float64).view(np.uint64)
+    return [r.tobytes() for r in k]
+
+
+class Plan:
+    """Result of finalize(): the local mesh reordered (owned vertices first, ghosts grouped by owner rank) and the
+    halo plan in the form pnp_halo_set() takes."""
+    pass
+
+
+def finalize(lm, me, world, all_gather=None):
+    """Ownership + halo plan.  `all_gather(obj) -> list over ranks` (torch.distributed.all_gather_object wrapper);
+    None for a single rank."""
+    nv = lm.nv
+    # owner of every vertex that touches one of my triangles: lowest tag around it (its star is complete locally)
+    mine_v = np.zeros(nv, dtype=bool)
+    mine_v[lm.tri[lm.tag == me].ravel()] = True
+    owner = np.full(nv, np.iinfo(np.int32).max, dtype=np.int32)
+    np.minimum.at(owner, lm.tri.ravel(), np.repeat(lm.tag, 3))
+    owned = mine_v & (owner == me)
+    ghost_ids = np.where(~owned)[0]
+    own_ids = np.where(owned)[0]
+    p = Plan()
+    if world == 1:
+        assert len(ghost_ids) == 0
+        order = own_ids
+        nbr, send_ptr, send_idx, recv_ptr = [], [0], np.zeros(0, np.int32), [0]
+    else:
+        gk = _coord_keys(lm.x[ghost_ids], lm.y[ghost_ids])
+        ghosts_all = all_gather(gk)
+        # owned vertices another rank may need: those touching a triangle that is not mine
+        foreign_v = np.zeros(nv, dtype=bool)
+        foreign_v[lm.tri[lm.tag != me].ravel()] = True
+        near_t = foreign_v[lm.tri].any(axis=1)   # triangles within one layer of another rank's triangles
+        near_v = np.zeros(nv, dtype=bool); near_v[lm.tri[near_t].ravel()] = True
+        cand = np.where(owned & near_v)[0]
+        lookup = dict(zip(_coord_keys(lm.x[cand], lm.y[cand]), cand.tolist()))
+        claims = []  # claims[q] = (positions in q's ghost list that I own, my local ids in that order)
+        for q in range(world):
+            if q == me:
+                claims.append((np.zeros(0, np.int64), np.zeros(0, np.int64))); continue
+            pos, ids = [], []
+            for i, k in enumerate(ghosts_all[q]):
+                v = lookup.get(k)
+                if v is not None:
+                    pos.append(i); ids.append(v)
+            claims.append((np.array(pos, dtype=np.int64), np.array(ids, dtype=np.int64)))
+        claimed_all = all_gather([c[0] for c in claims])  # claimed_all[r][q] = positions of q's ghosts owned by r
+        # my ghosts, grouped by owner rank in the order the owner will send them
+        ghost_order, recv_ptr, nbr_set = [], [0], []
+        seen = np.zeros(len(ghost_ids), dtype=np.int32)
+        for r in range(world):
+            pos = claimed_all[r][me] if r != me else np.zeros(0, np.int64)
+            seen[pos] += 1
+            if len(pos) or len(claims[r][0]):
+                nbr_set.append(r)
+                ghost_order.append(ghost_ids[pos])
+                recv_ptr.append(recv_ptr[-1] + len(pos))
+        if not np.all(seen == 1):
+            raise RuntimeError("halo plan: %d ghost vertices unclaimed, %d claimed twice" % ((seen == 0).sum(), (seen > 1).sum()))
+        order = np.concatenate([own_ids] + ghost_order) if ghost_order else own_ids
+        new_id = np.empty(nv, dtype=np.int64); new_id[order] = np.arange(nv)
+        nbr = nbr_set
+        send_ptr, send_idx = [0], []
+        for r in nbr:
+            send_idx.append(new_id[claims[r][1]])
+            send_ptr.append(send_ptr[-1] + len(claims[r][1]))
+        send_idx = np.concatenate(send_idx).astype(np.int32) if send_idx else np.zeros(0, np.int32)
+    new_id = np.empty(nv, dtype=np.int64); new_id[order] = np.arange(nv)
+    p.x, p.y = lm.x[order], lm.y[order]
+    p.tri = new_id[lm.tri].astype(np.int32)
+    p.ba, p.bb, p.bphys = new_id[lm.ba].astype(np.int32), new_id[lm.bb].astype(np.int32), lm.bphys
+    p.tag = lm.tag
+    p.fields = {k: v[:, order] for k, v in lm.fields.items()}
+    p.n_own, p.nv = len(own_ids), nv
+    p.nbr = np.array(nbr, dtype=np.int32); p.send_ptr = np.array(send_ptr, dtype=np.int32)
+    p.send_idx = send_idx; p.recv_ptr = np.array(recv_ptr, dtype=np.int32)
+    return p
+
+
+def build_local(a, nparts, me, levels, fields=None, all_gather=None):
+    """Partition the global mesh `a`, refine rank `me`'s part `levels` times, and build its halo plan."""
+    tri = np.asarray(a["tri"])
+    cx = np.asarray(a["x"])[tri].mean(1); cy = np.asarray(a["y"])[tri].mean(1)
+    part = rcb_partition(cx, cy, nparts)
+    lm = extract_local(a, part, me, fields)
+    for _ in range(levels):
+        lm = lm.refine().trim(me)
+    return finalize(lm, me, nparts, all_gather)

@@ -67,6 +67,20 @@ pnp_status pnp_timer_stop(pnp_ctx*, double* elapsed_ms);
 pnp_status pnp_mesh_set(pnp_ctx*, long nv, const double* x, const double* y, long nT, const int* tri /*[nT][3]*/,
                         long nB, const int* ba, const int* bb, const int* bphys);
 pnp_status pnp_mesh_read_gmsh(pnp_ctx*, const char* path);
+/* ---- multi-GPU: one context per rank owns a subdomain (replaces grid->loadBalance(), pnp_solver_main.cc:108, and the
+ * PDELab "nonoverlapping" machinery: GridOperator<...,true>, NonoverlappingOperator/ScalarProduct, stationary_pnp.hh:240).
+ * Local mesh: the first n_own vertices are owned (they get matrix rows), the rest are ghosts grouped by owner rank; all
+ * elements touching an owned vertex must be present.  pnp_halo_set(): per neighbour rank i, send_idx[send_ptr[i]:
+ * send_ptr[i+1]] are the owned local vertices whose values that rank needs, and the ghosts [n_own + recv_ptr[i],
+ * n_own + recv_ptr[i+1]) are received from it in the order that rank sends them.  NCCL carries only these halo values
+ * and the scalar sums of dot products / norms. */
+pnp_status pnp_mesh_set_local(pnp_ctx*, long nv, long n_own, const double* x, const double* y, long nT, const int* tri,
+                              long nB, const int* ba, const int* bb, const int* bphys);
+pnp_status pnp_mesh_owned(pnp_ctx*, long* n_own);
+pnp_status pnp_comm_unique_id(char* out128);                 /* ncclGetUniqueId on rank 0, broadcast by the launcher */
+pnp_status pnp_comm_init(pnp_ctx*, int rank, int world, const char* unique_id128);
+pnp_status pnp_halo_set(pnp_ctx*, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr);
+pnp_status pnp_halo_exchange(pnp_ctx*, int vec_handle);       /* refresh the ghost part of a vector */
 /* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
 pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
 /* nested iteration: pnp_carry_set() stores vectors in reference numbering; every later pnp_mesh_refine() level
@@ -75,6 +89,9 @@ pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
  * operator and solver handles. */
 pnp_status pnp_carry_set(pnp_ctx*, const int* vec_handles, int n);
 pnp_status pnp_carry_get(pnp_ctx*, int index, int vec_handle);
+/* same, for a field given / returned in reference numbering on the host ([fields][nv]); needs no finalized mesh */
+pnp_status pnp_carry_set_host(pnp_ctx*, int fields, const double* host);
+pnp_status pnp_carry_get_host(pnp_ctx*, int index, double* host);
 /* builds the vertex-star structure; renumber != 0 reorders vertices internally for locality */
 pnp_status pnp_mesh_finalize(pnp_ctx*, int renumber);
 pnp_status pnp_mesh_sizes(pnp_ctx*, long* nv, long* nT, long* nB, long* nslots);

@@ -60,7 +60,7 @@ def refine(a):
 
 
 class Star:
-    def __init__(self, a, surf, renumber=True):
+    def __init__(self, a, surf, renumber=True, n_own=None):
         """a: mesh arrays; surf: [ns][9] flat surface table (btype, flux, dirichlet) x 3 components."""
         self.a = {k: np.ascontiguousarray(v) for k, v in a.items()}
         x = self.a["x"].astype(np.float64); y = self.a["y"].astype(np.float64)
@@ -71,14 +71,15 @@ class Star:
         fl = np.ascontiguousarray(surf[:, 1::3], dtype=np.float64)
         err = C.c_int(0)
         self.nv, self.nT = len(x), len(tri)
+        self.n_own = self.nv if n_own is None else int(n_own)
         h = lib().hh_star_build(C.c_long(self.nv), _d(x), _d(y), C.c_long(self.nT), _i(tri), C.c_long(len(ba)), _i(ba), _i(bb),
-                                _i(ph), int(renumber), len(surf), _i(bt), _d(fl), C.byref(err))
+                                _i(ph), int(renumber), len(surf), _i(bt), _d(fl), C.c_long(self.n_own), C.byref(err))
         self.err = err.value
         if not h:
             raise RuntimeError("star build failed with mesh error %d" % err.value)
         self.h = C.c_void_p(h)
         self.nslots = lib().hh_star_nslots(self.h)
-        self.rp = np.zeros(self.nv + 1, dtype=np.int32); self.adj = np.zeros(self.nslots, dtype=np.uint32)
+        self.rp = np.zeros(self.n_own + 1, dtype=np.int32); self.adj = np.zeros(self.nslots, dtype=np.uint32)
         self.int2ext = np.zeros(self.nv, dtype=np.int32); self.dmask = np.zeros(self.nv, dtype=np.uint8)
         lib().hh_star_get(self.h, _i(self.rp), self.adj.ctypes.data_as(C.POINTER(C.c_uint)), _i(self.int2ext),
                           self.dmask.ctypes.data_as(C.POINTER(C.c_ubyte)))

@@ -14,7 +14,7 @@ using namespace pnp;
 
 namespace {
 struct Star {
-  long nv = 0, nT = 0;
+  long nv = 0, nT = 0, n_own = 0;
   std::vector<int> rp, int2ext, ext2int;
   std::vector<unsigned> adj;
   std::vector<XY> xy;
@@ -23,7 +23,7 @@ struct Star {
   std::vector<int> bv, bv_ptr, bv_items;
   std::vector<double> surf_flux;
   std::vector<unsigned char> surf_dir;
-  StarView view() const { return StarView{rp.data(), adj.data(), xy.data(), dmask.data(), (int)nv}; }
+  StarView view() const { return StarView{rp.data(), adj.data(), xy.data(), dmask.data(), (int)n_own}; }
 };
 } // namespace
 
@@ -91,14 +91,15 @@ long hh_refine(long nv, const double* x, const double* y, long nT, const int* tr
 // surf_btype[ns][3], surf_flux[ns][3]; returns NULL on a mesh error (code in *err)
 void* hh_star_build(long nv, const double* x, const double* y, long nT, const int* tri, long nB, const int* ba,
                     const int* bb, const int* bphys, int renumber, int ns, const int* surf_btype, const double* surf_flux,
-                    int* err) {
-  Star* S = new Star; S->nv = nv; S->nT = nT; *err = 0;
+                    long n_own, int* err) {
+  Star* S = new Star; S->nv = nv; S->nT = nT; S->n_own = n_own; *err = 0;
+  const long no = n_own;
   S->int2ext.resize(nv); S->ext2int.resize(nv);
   if (renumber) {
     std::vector<long> first(nv, 0x7fffffff);
     for (long i = 0; i < 3 * nT; i++) first[tri[i]] = std::min(first[tri[i]], i);
     std::iota(S->int2ext.begin(), S->int2ext.end(), 0);
-    std::stable_sort(S->int2ext.begin(), S->int2ext.end(), [&](int a, int b) { return first[a] < first[b]; });
+    std::stable_sort(S->int2ext.begin(), S->int2ext.begin() + no, [&](int a, int b) { return first[a] < first[b]; });
   } else std::iota(S->int2ext.begin(), S->int2ext.end(), 0);
   for (long i = 0; i < nv; i++) S->ext2int[S->int2ext[i]] = (int)i;
   S->xy.resize(nv);
@@ -112,27 +113,33 @@ void* hh_star_build(long nv, const double* x, const double* y, long nT, const in
   std::sort(order.begin(), order.end(), [&](long a, long b) { return keys[a] < keys[b]; });
   std::vector<uint64_t> sk(nrec); std::vector<unsigned> sp(nrec);
   for (long i = 0; i < nrec; i++) { sk[i] = keys[order[i]]; sp[i] = pay[order[i]]; }
-  std::vector<int> start(nv + 1);
-  for (long v = 0; v <= nv; v++) start[v] = (int)lower_bound_u64(sk.data(), nrec, (uint64_t)v << 32);
-  S->rp.assign(nv + 1, 0);
-  for (long v = 0; v < nv; v++) {
+  std::vector<int> start(no + 1);
+  for (long v = 0; v <= no; v++) start[v] = (int)lower_bound_u64(sk.data(), nrec, (uint64_t)v << 32);
+  S->rp.assign(no + 1, 0);
+  for (long v = 0; v < no; v++) {
     int open, bad;
     fan_start(sk.data(), sp.data(), start[v], start[v + 1], &open, &bad);
     if (bad) *err = 2;
     S->rp[v + 1] = S->rp[v] + 1 + (start[v + 1] - start[v]) + open;
   }
-  S->adj.assign(S->rp[nv], 0);
-  for (long v = 0; v < nv; v++)
+  S->adj.assign(S->rp[no], 0);
+  for (long v = 0; v < no; v++)
     if (!ring_fill(sk.data(), sp.data(), start[v], start[v + 1], (int)v, &S->adj[S->rp[v]])) *err = 2;
   if (*err) { delete S; return nullptr; }
   long nopen = 0;
-  for (long v = 0; v < nv; v++) if (!(S->adj[S->rp[v + 1] - 1] & STAR_HAS_TRI)) nopen++;
+  for (long v = 0; v < no; v++) if (!(S->adj[S->rp[v + 1] - 1] & STAR_HAS_TRI)) nopen++;
   S->bfaces.resize(nB);
-  for (long s = 0; s < nB; s++) {
-    if (!boundary_face_of(S->rp.data(), S->adj.data(), S->ext2int[ba[s]], S->ext2int[bb[s]], &S->bfaces[s])) *err = 3;
-    S->bfaces[s].phys = bphys[s]; S->bfaces[s].seg = (int)s;
+  for (long s = 0; s < nB; s++) { // mirrors k_bfaces
+    BFace& bf = S->bfaces[s];
+    const int a = S->ext2int[ba[s]], b = S->ext2int[bb[s]];
+    bool ok;
+    if (a < no) ok = boundary_face_of(S->rp.data(), S->adj.data(), a, b, &bf);
+    else if (b < no) ok = boundary_face_of(S->rp.data(), S->adj.data(), b, a, &bf);
+    else { bf.v[0] = bf.v[1] = bf.v[2] = -1; bf.f = 0; ok = no < nv; }
+    if (!ok) *err = 3;
+    bf.a = a; bf.b = b; bf.phys = bphys[s]; bf.seg = (int)s;
   }
-  if (nopen != nB && !*err) *err = 4;
+  if (no == nv && nopen != nB && !*err) *err = 4;
   if (*err) { delete S; return nullptr; }
   // constraints + boundary incidence lists (mirrors constraints_build)
   S->dmask.assign(nv, 0);
@@ -142,8 +149,9 @@ void* hh_star_build(long nv, const double* x, const double* y, long nT, const in
   std::vector<std::vector<int>> items(nv);
   for (long s = 0; s < nB; s++) {
     const BFace& b = S->bfaces[s];
-    for (int l = 0; l < 2; l++) S->dmask[b.v[face_v(b.f, l)]] |= S->surf_dir[b.phys];
-    for (int r = 0; r < 3; r++) items[b.v[r]].push_back((int)s * 4 + r);
+    S->dmask[b.a] |= S->surf_dir[b.phys]; S->dmask[b.b] |= S->surf_dir[b.phys];
+    if (b.v[0] < 0) continue;
+    for (int r = 0; r < 3; r++) if (b.v[r] < no) items[b.v[r]].push_back((int)s * 4 + r);
   }
   S->bv_ptr.push_back(0);
   for (long v = 0; v < nv; v++) if (!items[v].empty()) {
