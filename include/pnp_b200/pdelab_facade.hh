@@ -1,0 +1,185 @@
+// pdelab_facade.hh -- header-only C++ facade over the C ABI (pnp_b200.h) that keeps the PDELab / ISTL names the
+// dune-pnp drivers use, so that stationary_pnp / stationary_pnp_from_pb / instationary_pnp_md read the same after the
+// backend switch.  Reference call sites (relative to /root/reference/src):
+//   GridOperator<...>(gfsu,cu,gfsv,cv,lop), go.residual(u,r), go.jacobian(u,A)      stationary_pnp.hh:240-246
+//   ISTLBackend_NOVLP_BCGS_SSORk / _BCGS_NOPREC / _CG_NOPREC / _CG_Jacobi / _CG_AMG_SSOR   instationary_pnp_from_pb_md.hh:188-211
+//   Newton<GO,LS,U>(go,u,ls) + setters + apply()                                    stationary_pnp.hh:280-294
+//   StationaryLinearProblemSolver<GO,LS,U>(go,u,ls,red).apply()                      instationary_pnp_from_pb_md.hh:349-350
+//   interpolate(BCExtension, gfs, u)                                                 stationary_pnp_from_pb.hh:270
+// Errors are rethrown as the same-named exception types PDELab throws.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../pnp_b200.h"
+
+namespace Dune {
+namespace PNPB200 {
+
+struct Exception : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NewtonNotConverged : Exception { using Exception::Exception; };
+struct NewtonLinearSolverError : Exception { using Exception::Exception; };
+struct NewtonLineSearchError : Exception { using Exception::Exception; };
+struct NewtonDefectError : Exception { using Exception::Exception; };
+struct ISTLError : Exception { using Exception::Exception; };
+
+inline void check(pnp_ctx* c, pnp_status st) {
+  if (st == PNP_OK) return;
+  const std::string m = pnp_last_error(c);
+  switch (st) {
+    case PNP_E_NOT_CONVERGED: throw NewtonNotConverged(m);
+    case PNP_E_LINEAR_SOLVER: throw NewtonLinearSolverError(m);
+    case PNP_E_LINE_SEARCH: throw NewtonLineSearchError(m);
+    case PNP_E_NAN: throw NewtonDefectError(m);
+    case PNP_E_BREAKDOWN: throw ISTLError(m);
+    default: throw Exception(m);
+  }
+}
+
+// Grid + Sysparams: GmshReader/GridFactory (pnp_solver_main.cc:82-114) and Sysparams::readConfigFile
+class Grid {
+ public:
+  explicit Grid(int device = 0) { if (pnp_ctx_create(device, &c_) != PNP_OK) throw Exception("no CUDA device"); }
+  ~Grid() { pnp_ctx_destroy(c_); }
+  Grid(const Grid&) = delete;
+  Grid& operator=(const Grid&) = delete;
+  void readConfigFile(const std::string& cfg) { check(c_, pnp_params_read(c_, cfg.c_str())); }
+  void readGmsh(const std::string& msh) { check(c_, pnp_mesh_read_gmsh(c_, msh.c_str())); }
+  void globalRefine(int levels) { check(c_, pnp_mesh_refine(c_, levels)); }
+  void finalize(bool renumber = true) { check(c_, pnp_mesh_finalize(c_, renumber)); }
+  long size() const { long nv = 0; pnp_mesh_sizes(c_, &nv, nullptr, nullptr, nullptr); return nv; }
+  pnp_ctx* ctx() const { return c_; }
+ private:
+  pnp_ctx* c_ = nullptr;
+};
+
+// BackendVectorSelector<GFS,double>::Type
+class Vector {
+ public:
+  Vector(Grid& g, int fields, double value = 0.0) : g_(g), fields_(fields) {
+    check(g.ctx(), pnp_vec_create(g.ctx(), fields, &h_));
+    if (value != 0.0) check(g.ctx(), pnp_vec_set(g.ctx(), h_, value));
+  }
+  ~Vector() { pnp_vec_destroy(g_.ctx(), h_); }
+  Vector(const Vector&) = delete;
+  void set(const std::vector<double>& host) { check(g_.ctx(), pnp_vec_upload(g_.ctx(), h_, host.data())); }
+  std::vector<double> get() const { std::vector<double> v(fields_ * g_.size()); check(g_.ctx(), pnp_vec_download(g_.ctx(), h_, v.data())); return v; }
+  void axpy(double a, const Vector& x) { check(g_.ctx(), pnp_vec_axpy(g_.ctx(), h_, a, x.h_)); }
+  double two_norm() const { double n; check(g_.ctx(), pnp_vec_norm(g_.ctx(), h_, &n)); return n; }
+  int handle() const { return h_; }
+  int fields() const { return fields_; }
+ private:
+  Grid& g_; int fields_; int h_ = -1;
+};
+
+// local operator tags (files of the same name in the reference)
+struct PBOperator { static constexpr int op = PNP_OP_PB, fields = 1; };
+struct PoissonOperator { static constexpr int op = PNP_OP_POISSON, fields = 1; };
+struct DiffusionOperator { static constexpr int op = PNP_OP_DIFFUSION, fields = 1; };
+struct DiffusionTOperator { static constexpr int op = PNP_OP_MASS, fields = 1; };
+struct PnpOperator { static constexpr int op = PNP_OP_PNP, fields = 3; };
+
+template <class LOP> class GridOperator;
+
+// GridOperator::Traits::Jacobian / MatrixContainer
+template <class LOP> class Matrix {
+ public:
+  explicit Matrix(GridOperator<LOP>& go);
+  ~Matrix() { pnp_matrix_destroy(g_.ctx(), h_); }
+  int handle() const { return h_; }
+ private:
+  Grid& g_; int h_ = -1;
+};
+
+template <class LOP> class GridOperator {
+ public:
+  // bcComponent: the BCType<...,component> a scalar operator is built with (btype.hh:5)
+  GridOperator(Grid& g, int bcComponent = 0) : g_(g) { check(g.ctx(), pnp_operator_create(g.ctx(), LOP::op, bcComponent, &h_)); }
+  void setCoefficient(int which, const Vector& v) { check(g_.ctx(), pnp_operator_set_coefficient(g_.ctx(), h_, which, v.handle())); }
+  void setValency(double z) { check(g_.ctx(), pnp_operator_set_valency(g_.ctx(), h_, z)); }
+  void residual(const Vector& u, Vector& r) const { check(g_.ctx(), pnp_residual(g_.ctx(), h_, u.handle(), r.handle())); }
+  void jacobian(const Vector& u, Matrix<LOP>& A, int mode = PNP_JAC_FD_FAITHFUL, double eps = 1e-11) const {
+    check(g_.ctx(), pnp_jacobian(g_.ctx(), h_, u.handle(), A.handle(), mode, eps));
+  }
+  Grid& grid() const { return g_; }
+  int handle() const { return h_; }
+ private:
+  Grid& g_; int h_ = -1;
+};
+template <class LOP> Matrix<LOP>::Matrix(GridOperator<LOP>& go) : g_(go.grid()) { check(g_.ctx(), pnp_matrix_create(g_.ctx(), go.handle(), &h_)); }
+
+// ISTLBackend_NOVLP_*: apply(A,z,r,reduction), result()
+struct LinearSolverResult { bool converged = false; int iterations = 0; double reduction = 1, conv_rate = 1, elapsed = 0; };
+class LinearSolverBackend {
+ public:
+  LinearSolverBackend(Grid& g, int kind, int prec, unsigned maxiter, int steps, int verbose) : g_(g) {
+    check(g.ctx(), pnp_solver_create(g.ctx(), kind, prec, (int)maxiter, steps, verbose, &h_));
+  }
+  template <class M> void apply(M& A, Vector& z, Vector& r, double reduction) {
+    pnp_lin_result lr{};
+    check(g_.ctx(), pnp_solver_apply(g_.ctx(), h_, A.handle(), z.handle(), r.handle(), reduction, &lr));
+    res_ = {lr.converged != 0, lr.iterations, lr.reduction, lr.conv_rate, lr.seconds};
+  }
+  double norm(const Vector& v) const { return v.two_norm(); }
+  const LinearSolverResult& result() const { return res_; }
+  int handle() const { return h_; }
+ private:
+  Grid& g_; int h_ = -1; LinearSolverResult res_;
+};
+struct ISTLBackend_NOVLP_BCGS_NOPREC : LinearSolverBackend {
+  ISTLBackend_NOVLP_BCGS_NOPREC(Grid& g, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_BCGS, PNP_PREC_NONE, maxiter, 1, verbose) {}
+};
+struct ISTLBackend_NOVLP_CG_NOPREC : LinearSolverBackend {
+  ISTLBackend_NOVLP_CG_NOPREC(Grid& g, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_CG, PNP_PREC_NONE, maxiter, 1, verbose) {}
+};
+struct ISTLBackend_NOVLP_CG_Jacobi : LinearSolverBackend {
+  ISTLBackend_NOVLP_CG_Jacobi(Grid& g, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_CG, PNP_PREC_JACOBI, maxiter, 1, verbose) {}
+};
+struct ISTLBackend_NOVLP_BCGS_SSORk : LinearSolverBackend {
+  ISTLBackend_NOVLP_BCGS_SSORk(Grid& g, unsigned maxiter = 5000, int steps = 5, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_BCGS, PNP_PREC_SSOR, maxiter, steps, verbose) {}
+};
+struct ISTLBackend_NOVLP_CG_AMG_SSOR : LinearSolverBackend {
+  ISTLBackend_NOVLP_CG_AMG_SSOR(Grid& g, int smoothsteps = 2, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_CG, PNP_PREC_AMG, maxiter, smoothsteps, verbose) {}
+};
+struct ISTLBackend_NOVLP_BCGS_AMG : LinearSolverBackend {  // new: what bench.py runs for the non-symmetric PNP system
+  ISTLBackend_NOVLP_BCGS_AMG(Grid& g, int smoothsteps = 2, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_BCGS, PNP_PREC_AMG, maxiter, smoothsteps, verbose) {}
+};
+
+// Dune::PDELab::Newton
+template <class GO, class LS> class Newton {
+ public:
+  enum Strategy { noLineSearch, hackbuschReusken, hackbuschReuskenAcceptBest };
+  Newton(GO& go, Vector& u, LS& ls) : go_(go), u_(u), ls_(ls) { pnp_newton_opts_default(&o_); }
+  void setLineSearchStrategy(Strategy) {}  // the reference always selects hackbuschReuskenAcceptBest
+  void setReassembleThreshold(double v) { o_.reassemble_threshold = v; }
+  void setVerbosityLevel(int v) { o_.verbosity = v; }
+  void setReduction(double v) { o_.reduction = v; }
+  void setMinLinearReduction(double v) { o_.min_linear_reduction = v; }
+  void setMaxIterations(unsigned v) { o_.max_iterations = (int)v; }
+  void setLineSearchMaxIterations(unsigned v) { o_.line_search_max_iterations = (int)v; }
+  void setJacobianMode(int mode, double eps = 1e-11) { o_.jac_mode = mode; o_.fd_epsilon = eps; }
+  void apply() { check(go_.grid().ctx(), pnp_newton_apply(go_.grid().ctx(), go_.handle(), u_.handle(), ls_.handle(), &o_, &r_)); }
+  const pnp_newton_result& result() const { return r_; }
+ private:
+  GO& go_; Vector& u_; LS& ls_; pnp_newton_opts o_; pnp_newton_result r_{};
+};
+
+template <class GO, class LS> class StationaryLinearProblemSolver {
+ public:
+  StationaryLinearProblemSolver(GO& go, Vector& u, LS& ls, double reduction) : go_(go), u_(u), ls_(ls), red_(reduction) {}
+  void apply(int jac_mode = PNP_JAC_FD_FAITHFUL, double eps = 1e-11) {
+    pnp_lin_result lr{};
+    check(go_.grid().ctx(), pnp_slp_apply(go_.grid().ctx(), go_.handle(), u_.handle(), ls_.handle(), red_, jac_mode, eps, &lr));
+  }
+ private:
+  GO& go_; Vector& u_; LS& ls_; double red_;
+};
+
+// interpolate(BCExtension<...,component,PbDGF>, gfs, u)
+inline void interpolate_bcext(Grid& g, int component, const Vector* pb, Vector& out) {
+  check(g.ctx(), pnp_interpolate_bcext(g.ctx(), component, pb ? pb->handle() : -1, out.handle()));
+}
+
+}  // namespace PNPB200
+}  // namespace Dune
