@@ -145,7 +145,11 @@ def run_reference(args, rank):
 def coarse_stage(c, capi, coarse_level, jac_mode, prec_steps, verbose):
     """Reference flow on the coarse level: PB Newton -> interpolate(BCExtension) -> PNP Newton. Returns the 3-field vector."""
     def solver():
-        return c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0)
+        # plain aggregation AMG V(2,2): it survives the convection-dominated first Newton step of the reference flow
+        # (discontinuous initial guess at the outflow Dirichlet boundary)
+        s_ = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0)
+        c.solver_set_option(s_, "amg_geometric", 0)
+        return s_
     c.mesh_refine(coarse_level); c.mesh_finalize(True)
     hpb = c.operator(capi.OP_PB, 0)
     vpb = c.vec(1)
@@ -168,7 +172,19 @@ def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
     c.carry_set([vu])
     c.mesh_refine(levels - coarse_level); c.mesh_finalize(True)
     us = c.vec(3); c.carry_get(0, us)
-    return c.operator(capi.OP_PNP, 0), c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0), us
+    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps), us
+
+
+AMG_FINE = {"amg_geometric": 1}   # refinement levels as multigrid levels (P1 interpolation), aggregation below the coarsest mesh
+
+
+def fine_solver(c, capi, prec_steps):
+    """BiCGSTAB + multigrid for the timed step: V(nu,nu) damped Jacobi; the mesh levels created by pnp_mesh_refine are the
+    upper multigrid levels (P1 interpolation, Galerkin operators), aggregation AMG continues below the Gmsh mesh."""
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0)
+    for k, v in AMG_FINE.items():
+        c.solver_set_option(s, k, v)
+    return s
 
 
 def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose, rank, world, dist):
@@ -205,7 +221,7 @@ def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps,
     if verbose:
         print("# rank %d: %d owned + %d ghost vertices, %d neighbours" % (rank, plan.n_own, plan.nv - plan.n_own, len(plan.nbr)),
               file=sys.stderr, flush=True)
-    return c.operator(capi.OP_PNP, 0), c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0), us
+    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps), us
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -311,7 +327,9 @@ def run_gpu(args, rank, world, local_rank):
                    "levels": args.levels, "dofs": gdof, "matrix_slots": gslots,
                    "rank0_owned_vertices": n_own, "rank0_ghost_vertices": nv - n_own,
                    "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the level-%d mesh), halo exchange + scalar allreduce over NCCL, block-Jacobi AMG" % (world, args.coarse_level),
-                   "jacobian": args.jac, "preconditioner": "AMG V(%d,%d) damped Jacobi" % (args.prec_steps, args.prec_steps),
+                   "jacobian": args.jac, "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
+                       "refinement levels with P1 interpolation + Galerkin operators, aggregation AMG below the Gmsh mesh" if world == 1
+                       else "aggregation AMG per subdomain (block-Jacobi over ranks)"),
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
                    "l2_policy": "inputs larger than L2 (per GPU: matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
         "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,

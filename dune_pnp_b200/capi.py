@@ -58,16 +58,21 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise ImportError("libpnp_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(make -C dune_pnp_b200/csrc)")
-        # libpnp_b200.so needs libnccl.so.2.  PyTorch bundles a newer NCCL under the same soname; whichever copy is
-        # loaded first serves both, so load the bundled one first (otherwise a later `import torch` would find the
-        # older system copy already mapped and fail to resolve its newer symbols).
+        # libpnp_b200.so needs libnccl.so.2 and libcusolver.so.11 (+ cublas/cusparse).  PyTorch bundles its own copies
+        # under the same sonames; whichever copy is mapped first serves both, so map the bundled ones first (otherwise a
+        # later `import torch` would find older system copies already mapped and fail to resolve its newer symbols).
         try:
             import importlib.util
-            spec = importlib.util.find_spec("nvidia.nccl")
-            if spec is not None and spec.submodule_search_locations:
-                cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
-                if os.path.exists(cand):
-                    C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            for pkg, names in (("nvidia.nccl", ["libnccl.so.2"]), ("nvidia.nvjitlink", ["libnvJitLink.so.12"]),
+                               ("nvidia.cublas", ["libcublasLt.so.12", "libcublas.so.12"]),
+                               ("nvidia.cusparse", ["libcusparse.so.12"]), ("nvidia.cusolver", ["libcusolver.so.11"])):
+                spec = importlib.util.find_spec(pkg)
+                if spec is None or not spec.submodule_search_locations:
+                    continue
+                for nm in names:
+                    cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", nm)
+                    if os.path.exists(cand):
+                        C.CDLL(cand, mode=C.RTLD_GLOBAL)
         except Exception:
             pass
         L = C.CDLL(LIB_PATH)
@@ -317,6 +322,9 @@ class Context:
         h = C.c_int()
         self._ck(lib().pnp_solver_create(self._h, kind, prec, maxit, prec_steps, verbosity, C.byref(h)))
         return h.value
+
+    def solver_set_option(self, solver, name, value):
+        self._ck(lib().pnp_solver_set_option(self._h, solver, name.encode(), C.c_double(value)))
 
     def solve(self, solver, A, z, r, reduction):
         res = LinResult()

@@ -14,8 +14,13 @@
 // Symbolic phase (aggregates, coarse patterns, gather lists) once per mesh/operator type;
 // numeric phase (Galerkin sums, inverse diagonals) per Jacobian -- deterministic gathers, no atomics.
 #include <cub/cub.cuh>
+#include <cusolverDn.h>
+
+#include <cmath>
+#include <cstring>
 
 #include "pnp_common.cuh"
+#include "pnp_spmv.cuh"
 
 namespace pnp {
 
@@ -29,9 +34,15 @@ struct Level {
   const int* rp = nullptr; const unsigned* col = nullptr; const double* vals = nullptr;
   DBuf<int> rp_own; DBuf<unsigned> col_own; DBuf<double> vals_own;
   DBuf<double> dinv, x, x2, b, r;
+  double lmax = 2.0;      // Gershgorin bound of the spectrum of D^-1 A
   // transfer to the next coarser level
-  DBuf<int> agg, agg_ptr, agg_mem;   // vertex -> aggregate; members of each aggregate
-  DBuf<int> seg_ptr, seg_items;      // coarse slot -> fine slots summed into it
+  // Prolongation row of fine vertex i: one parent (weight 1: aggregate / coinciding coarse vertex) or two parents
+  // (weight 1/2 each: midpoint of a coarse edge, P1 interpolation of the refinement hierarchy).
+  DBuf<int> agg, par1;               // first parent; second parent or -1 (par1 empty: aggregation level)
+  DBuf<int> agg_ptr, agg_mem;        // coarse vertex -> fine vertices it is a parent of (restriction = P^T)
+  DBuf<int> seg_ptr, seg_items;      // coarse slot -> fine slots summed into it (Galerkin P^T A P)
+  DBuf<unsigned char> seg_w;         // weight code of each item: 0 -> 1, 1 -> 1/2, 2 -> 1/4 (empty: all 1)
+  double alpha = 1.0;                // scaling of the coarse correction coming up from the next level
 };
 
 } // namespace
@@ -42,7 +53,18 @@ struct Amg {
   long nv0 = -1, nslots0 = -1;
   double omega = 0.7, alpha = 1.6;
   int coarse_sweeps = 40;
+  int gamma = 1;          // 1: V-cycle, 2: W-cycle ...
+  int wlevels = 99;       // ... on the first `wlevels` levels only (V below): bounds the visits of the small levels
+  int smoother = 0;       // 0: damped Jacobi, 1: Chebyshev on [lmax/cheb_ratio, lmax] of D^-1 A
+  double cheb_ratio = 8.0;
   int comp0 = 0;
+  // coarsest level: dense LU (cuSOLVER getrf/getrs) when it has at most dense_max dofs, else `coarse_sweeps` sweeps
+  int dense_max = 4096, dense_n = 0;
+  cusolverDnHandle_t cus = nullptr;
+  DBuf<double> dense, dense_work;
+  DBuf<int> dense_piv, dense_info;
+  ~Amg() { if (cus) cusolverDnDestroy(cus); }
+  int n_geo = 0;          // number of geometric (P1) transfers at the top of the hierarchy
   std::vector<std::unique_ptr<Level>> L;
   DBuf<unsigned char> tmp;
   void* temp(size_t bytes) { if (bytes > tmp.n) tmp.alloc(bytes); return tmp.p; }
@@ -145,8 +167,8 @@ __global__ void k_iota(int* a, int n) {
 // At level 0 Dirichlet dofs are left out of the hierarchy (their rows/columns are already decoupled;
 // only the unit diagonal has to be skipped): dmask/rp0 non-null, F = 3 uses bits 0..2, F = 1 uses bit comp0.
 template <int NP>
-__global__ void k_galerkin(const int* __restrict__ seg_ptr, const int* __restrict__ seg_items, long nsc,
-                           const double* __restrict__ vf, long nsf, double* __restrict__ vc,
+__global__ void k_galerkin(const int* __restrict__ seg_ptr, const int* __restrict__ seg_items,
+                           const unsigned char* __restrict__ seg_w, long nsc, const double* __restrict__ vf, long nsf, double* __restrict__ vc,
                            const unsigned char* __restrict__ dmask, const unsigned* __restrict__ colf, const int* __restrict__ rpf,
                            int comp0) {
   for (long cs = blockIdx.x * (long)blockDim.x + threadIdx.x; cs < nsc; cs += (long)gridDim.x * blockDim.x) {
@@ -170,13 +192,17 @@ __global__ void k_galerkin(const int* __restrict__ seg_ptr, const int* __restric
           }
         }
       }
+      const double w = seg_w ? (seg_w[t] == 0 ? 1.0 : (seg_w[t] == 1 ? 0.5 : 0.25)) : 1.0;
 #pragma unroll
-      for (int p = 0; p < NP; p++) acc[p] += v[p];
+      for (int p = 0; p < NP; p++) acc[p] += w * v[p];
     }
 #pragma unroll
     for (int p = 0; p < NP; p++) vc[p * nsc + cs] = acc[p];
   }
 }
+// smoother matrix M^-1: scalar operators 1/a_ii; PNP: inverse of every vertex's 3x3 diagonal block (point-block Jacobi --
+// the phi/c couplings inside a vertex grow like h^2 relative to the stiffness terms, so on coarse levels a scalar
+// diagonal no longer dominates them)
 template <int NP>
 __global__ void k_dinv(const int* __restrict__ rp, const double* __restrict__ vals, long stride, int nv,
                        double* __restrict__ dinv) {
@@ -184,74 +210,83 @@ __global__ void k_dinv(const int* __restrict__ rp, const double* __restrict__ va
     const int s = rp[v];
     if (NP == 1) { const double d = vals[s]; dinv[v] = d != 0.0 ? 1.0 / d : 0.0; }
     else {
-      const double d0 = vals[s], d1 = vals[4 * stride + s], d2 = vals[6 * stride + s];
-      dinv[3l * v] = d0 != 0.0 ? 1.0 / d0 : 0.0;
-      dinv[3l * v + 1] = d1 != 0.0 ? 1.0 / d1 : 0.0;
-      dinv[3l * v + 2] = d2 != 0.0 ? 1.0 / d2 : 0.0;
-    }
-  }
-}
-
-// y = A x with an epilogue: EPI 0: y = A x; 1: y = b - A x; 2: y = x + omega*dinv*(b - A x)
-template <int NP, int EPI, int LANES>
-__global__ void __launch_bounds__(BLK)
-k_level_op(const int* __restrict__ rp, const unsigned* __restrict__ col, const double* __restrict__ vals, long stride,
-           const double* __restrict__ x, const double* __restrict__ b, const double* __restrict__ dinv, double omega,
-           double* __restrict__ y, int nv) {
-  constexpr int F = NP == 1 ? 1 : 3;
-  constexpr int RPW = 32 / LANES;
-  const int lane = threadIdx.x & (LANES - 1);
-  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-  const int ngrp = gridDim.x * blockDim.x / LANES;
-  for (int base = grp - (grp % RPW); base < nv; base += ngrp) {
-    const int row = base + (grp % RPW);
-    double acc[F];
-#pragma unroll
-    for (int k = 0; k < F; k++) acc[k] = 0.0;
-    if (row < nv) {
-      for (int s = rp[row] + lane; s < rp[row + 1]; s += LANES) {
-        const long c = col[s] & STAR_VMASK;
-        if (NP == 1) acc[0] += vals[s] * x[c];
-        else {
-          const double x0 = x[3 * c], x1 = x[3 * c + 1], x2 = x[3 * c + 2];
-          acc[0] += vals[s] * x0 + vals[stride + s] * x1 + vals[2 * stride + s] * x2;
-          acc[1] += vals[3 * stride + s] * x0 + vals[4 * stride + s] * x1;
-          acc[2] += vals[5 * stride + s] * x0 + vals[6 * stride + s] * x2;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < F; k++)
-#pragma unroll
-      for (int o = LANES / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (lane == 0 && row < nv) {
-#pragma unroll
-      for (int k = 0; k < F; k++) {
-        const long i = (long)F * row + k;
-        if (EPI == 0) y[i] = acc[k];
-        else if (EPI == 1) y[i] = b[i] - acc[k];
-        else y[i] = x[i] + omega * dinv[i] * (b[i] - acc[k]);
+      // B = [a b c; d e 0; f 0 g]
+      const double a = vals[s], b = vals[stride + s], c_ = vals[2 * stride + s], d = vals[3 * stride + s],
+                   e = vals[4 * stride + s], f = vals[5 * stride + s], g = vals[6 * stride + s];
+      const double det = a * e * g - b * d * g - c_ * e * f;
+      double* o = dinv + 9l * v;
+      const double scale = fabs(a * e * g) + fabs(b * d * g) + fabs(c_ * e * f);
+      if (fabs(det) > 1e-12 * scale && scale > 0.0) {
+        const double id = 1.0 / det;
+        o[0] = e * g * id;   o[1] = -b * g * id;           o[2] = -c_ * e * id;
+        o[3] = -d * g * id;  o[4] = (a * g - c_ * f) * id; o[5] = c_ * d * id;
+        o[6] = -e * f * id;  o[7] = b * f * id;            o[8] = (a * e - b * d) * id;
+      } else { // (near-)singular block, e.g. an all-Dirichlet coarse vertex: fall back to the scalar diagonal
+        for (int i = 0; i < 9; i++) o[i] = 0.0;
+        o[0] = a != 0.0 ? 1.0 / a : 0.0; o[4] = e != 0.0 ? 1.0 / e : 0.0; o[8] = g != 0.0 ? 1.0 / g : 0.0;
       }
     }
   }
 }
-// first sweep from a zero initial guess: x = omega * dinv * b
+// first sweep from a zero initial guess: x = omega * M^-1 b  (also the first Chebyshev direction d)
+template <int F>
 __global__ void k_jacobi0(const double* __restrict__ dinv, const double* __restrict__ b, double omega,
-                          double* __restrict__ x, long n) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    x[i] = omega * dinv[i] * b[i];
+                          double* __restrict__ x, int nv, double* __restrict__ dvec) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    if (F == 1) {
+      const double z = omega * dinv[v] * b[v];
+      x[v] = z; if (dvec) dvec[v] = z;
+    } else {
+      const double* B = dinv + 9l * v;
+      const double r0 = b[3l * v], r1 = b[3l * v + 1], r2 = b[3l * v + 2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double z = omega * (B[3 * k] * r0 + B[3 * k + 1] * r1 + B[3 * k + 2] * r2);
+        x[3l * v + k] = z; if (dvec) dvec[3l * v + k] = z;
+      }
+    }
+  }
+}
+// Gershgorin bound of D^-1 A: max over dof rows of sum_j |a_ij| / |a_ii|
+template <int NP>
+__global__ void k_gershgorin(const int* __restrict__ rp, const double* __restrict__ vals, long stride, int nv,
+                             unsigned long long* __restrict__ out) {
+  double best = 0.0;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    const int s0 = rp[v], s1 = rp[v + 1];
+    if (NP == 1) {
+      double sum = 0.0;
+      for (int s = s0; s < s1; s++) sum += fabs(vals[s]);
+      const double d = fabs(vals[s0]);
+      if (d > 0.0) best = fmax(best, sum / d);
+    } else {
+      double s0_ = 0.0, s1_ = 0.0, s2_ = 0.0;
+      for (int s = s0; s < s1; s++) {
+        s0_ += fabs(vals[s]) + fabs(vals[stride + s]) + fabs(vals[2 * stride + s]);
+        s1_ += fabs(vals[3 * stride + s]) + fabs(vals[4 * stride + s]);
+        s2_ += fabs(vals[5 * stride + s]) + fabs(vals[6 * stride + s]);
+      }
+      const double d0 = fabs(vals[s0]), d1 = fabs(vals[4 * stride + s0]), d2 = fabs(vals[6 * stride + s0]);
+      if (d0 > 0.0) best = fmax(best, s0_ / d0);
+      if (d1 > 0.0) best = fmax(best, s1_ / d1);
+      if (d2 > 0.0) best = fmax(best, s2_ / d2);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(best)); // positive doubles order like integers
 }
 template <int F>
-__global__ void k_restrict(const int* __restrict__ agg_ptr, const int* __restrict__ agg_mem, int nc,
-                           const double* __restrict__ r, double* __restrict__ bc) {
+__global__ void k_restrict(const int* __restrict__ agg_ptr, const int* __restrict__ agg_mem, const int* __restrict__ par1,
+                           int nc, const double* __restrict__ r, double* __restrict__ bc) {
   for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += gridDim.x * blockDim.x) {
     double acc[F];
 #pragma unroll
     for (int k = 0; k < F; k++) acc[k] = 0.0;
     for (int t = agg_ptr[I]; t < agg_ptr[I + 1]; t++) {
       const long v = agg_mem[t];
+      const double w = (par1 && par1[v] >= 0) ? 0.5 : 1.0;
 #pragma unroll
-      for (int k = 0; k < F; k++) acc[k] += r[F * v + k];
+      for (int k = 0; k < F; k++) acc[k] += w * r[F * v + k];
     }
 #pragma unroll
     for (int k = 0; k < F; k++) bc[(long)F * I + k] = acc[k];
@@ -259,14 +294,71 @@ __global__ void k_restrict(const int* __restrict__ agg_ptr, const int* __restric
 }
 // x += alpha * P x_c ; constrained dofs (level 0 only) receive no correction
 template <int F>
-__global__ void k_prolong(const int* __restrict__ agg, int nv, const double* __restrict__ xc, double alpha,
-                          double* __restrict__ x, const unsigned char* __restrict__ dmask, int comp0) {
+__global__ void k_prolong(const int* __restrict__ agg, const int* __restrict__ par1, int nv, const double* __restrict__ xc,
+                          double alpha, double* __restrict__ x, const unsigned char* __restrict__ dmask, int comp0) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     const long I = agg[v];
+    const long J = par1 ? par1[v] : -1;
     const unsigned m = dmask ? (F == 3 ? dmask[v] : (dmask[v] >> comp0) & 1u) : 0u;
 #pragma unroll
     for (int k = 0; k < F; k++)
-      if (!((m >> k) & 1u)) x[(long)F * v + k] += alpha * xc[F * I + k];
+      if (!((m >> k) & 1u))
+        x[(long)F * v + k] += alpha * (J >= 0 ? 0.5 * (xc[F * I + k] + xc[F * J + k]) : xc[F * I + k]);
+  }
+}
+// ---- geometric levels: P1 interpolation between two consecutive refinement levels ----
+// parents of every fine vertex, both in the internal numbering of their level
+__global__ void k_geo_parents(const int* __restrict__ int2ext_f, int nvf, int nvc, const uint64_t* __restrict__ edges,
+                              const int* __restrict__ ext2int_c, int* __restrict__ par0, int* __restrict__ par1) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvf; i += gridDim.x * blockDim.x) {
+    const int e = int2ext_f[i];
+    if (e < nvc) { par0[i] = ext2int_c[e]; par1[i] = -1; }
+    else {
+      const uint64_t k = edges[e - nvc];
+      par0[i] = ext2int_c[(int)(k >> 32)]; par1[i] = ext2int_c[(int)(k & 0xffffffffu)];
+    }
+  }
+}
+// (parent, child) pairs for the restriction lists: 2 per fine vertex, unused ones get key INT_MAX
+__global__ void k_geo_pairs(const int* __restrict__ par0, const int* __restrict__ par1, int nvf, int* __restrict__ key,
+                            int* __restrict__ val) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvf; i += gridDim.x * blockDim.x) {
+    key[2 * i] = par0[i]; val[2 * i] = i;
+    key[2 * i + 1] = par1[i] >= 0 ? par1[i] : 0x7fffffff; val[2 * i + 1] = i;
+  }
+}
+__device__ __forceinline__ int find_slot(const int* rp, const unsigned* col, int I, int J) {
+  for (int s = rp[I]; s < rp[I + 1]; s++) if ((int)(col[s] & STAR_VMASK) == J) return s;
+  return -1;
+}
+// Galerkin items: fine slot (i,j) feeds coarse slot (I,J) for every parent I of i and J of j with weight w_I*w_J.
+// 4 candidate items per fine slot at [4s, 4s+4): key = coarse slot (INT_MAX if unused), val = s | weight code << 29
+__global__ void k_geo_items(const int* __restrict__ rpf, const unsigned* __restrict__ colf, int nvf,
+                            const int* __restrict__ par0, const int* __restrict__ par1, const int* __restrict__ rpc,
+                            const unsigned* __restrict__ colc, int* __restrict__ key, unsigned* __restrict__ val,
+                            int* __restrict__ err) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvf; i += gridDim.x * blockDim.x) {
+    const int I[2] = {par0[i], par1[i]};
+    for (int s = rpf[i]; s < rpf[i + 1]; s++) {
+      const int j = (int)(colf[s] & STAR_VMASK);
+      const int J[2] = {par0[j], par1[j]};
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const long o = 4l * s + 2 * a + b;
+          if (I[a] < 0 || J[b] < 0) { key[o] = 0x7fffffff; val[o] = 0; continue; }
+          const int cs = find_slot(rpc, colc, I[a], J[b]);
+          if (cs < 0) { atomicExch(err, 1); key[o] = 0x7fffffff; val[o] = 0; continue; }
+          const unsigned wc = (I[1] >= 0 ? 1u : 0u) + (J[1] >= 0 ? 1u : 0u);
+          key[o] = cs; val[o] = (unsigned)s | (wc << 29);
+        }
+    }
+  }
+}
+__global__ void k_geo_unpack(const unsigned* __restrict__ val, long n, int* __restrict__ items, unsigned char* __restrict__ w) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    items[t] = (int)(val[t] & 0x1fffffffu); w[t] = (unsigned char)(val[t] >> 29);
   }
 }
 
@@ -274,16 +366,13 @@ __global__ void k_prolong(const int* __restrict__ agg, int nv, const double* __r
   do { kern<<<grid_for((n), BLK), BLK, 0, (c).stream>>>(__VA_ARGS__); PNP_CHECK_LAUNCH(); (c).launches++; } while (0)
 
 template <int EPI>
-void level_op(Ctx& c, const Amg& A, const Level& l, const double* x, const double* b, double* y) {
-  constexpr int LANES = 8;
-  const int grid = grid_for((long)l.nv * LANES, BLK, c.sm_count * 8);
+void level_op(Ctx& c, const Amg& A, const Level& l, const double* x, const double* b, double* y, double omega_or_c2 = -1.0,
+              double c1 = 0.0, double* dvec = nullptr) {
+  StarOpArgs a{l.rp, l.col, l.vals, l.nslots, l.nv, x, y};
+  a.b = b; a.dinv = l.dinv.p; a.block = A.NP == 7; a.omega = omega_or_c2 < 0 ? A.omega : omega_or_c2; a.c1 = c1; a.dvec = dvec;
   const bool fine = &l == A.L[0].get();
   if (fine) c.prof_mark();
-  if (A.NP == 1)
-    k_level_op<1, EPI, LANES><<<grid, BLK, 0, c.stream>>>(l.rp, l.col, l.vals, l.nslots, x, b, l.dinv.p, A.omega, y, l.nv);
-  else
-    k_level_op<7, EPI, LANES><<<grid, BLK, 0, c.stream>>>(l.rp, l.col, l.vals, l.nslots, x, b, l.dinv.p, A.omega, y, l.nv);
-  PNP_CHECK_LAUNCH(); c.launches++;
+  launch_star_op<EPI, 0>(c, A.NP, a);
   if (fine) c.prof_mark();
 }
 
@@ -315,6 +404,7 @@ bool coarsen(Ctx& c, Amg& A, int li) {
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   const int nc = last_id + last_flag;
   if (nc < 1 || nc > 0.8 * nv) return false;
+  f.alpha = A.alpha;
   f.agg.alloc(nv);
   KL(c, k_attach, nv, f.rp, f.col, f.vals, nv, st.p, root_id.p, f.agg.p);
   // members of each aggregate
@@ -366,10 +456,64 @@ bool coarsen(Ctx& c, Amg& A, int li) {
   return true;
 }
 
+// builds level li+1 from the refinement hierarchy: coarse star = that mesh level's star, P = P1 interpolation
+void coarsen_geometric(Ctx& c, Amg& A, int li, const HierLevel& h, const int* int2ext_f) {
+  Level& f = *A.L[li];
+  const int nvf = f.nv, nvc = (int)h.nv;
+  size_t bytes = 0;
+  f.agg.alloc(nvf); f.par1.alloc(nvf);
+  KL(c, k_geo_parents, nvf, int2ext_f, nvf, nvc, h.edges.p, h.ext2int.p, f.agg.p, f.par1.p);
+  { // restriction lists
+    DBuf<int> key(2 * (size_t)nvf), val(2 * (size_t)nvf), skey(2 * (size_t)nvf), sval(2 * (size_t)nvf);
+    KL(c, k_geo_pairs, nvf, f.agg.p, f.par1.p, nvf, key.p, val.p);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.p, skey.p, val.p, sval.p, 2 * nvf, 0, 32, c.stream);
+    PNP_CUDA(cub::DeviceRadixSort::SortPairs(A.temp(bytes), bytes, key.p, skey.p, val.p, sval.p, 2 * nvf, 0, 32, c.stream));
+    f.agg_ptr.alloc((size_t)nvc + 1);
+    KL(c, k_lower_bounds_i32, nvc + 1, skey.p, 2 * nvf, nvc, f.agg_ptr.p);
+    int nvalid = 0;
+    PNP_CUDA(cudaMemcpyAsync(&nvalid, f.agg_ptr.p + nvc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PNP_CUDA(cudaStreamSynchronize(c.stream));
+    f.agg_mem.alloc(nvalid);
+    PNP_CUDA(cudaMemcpyAsync(f.agg_mem.p, sval.p, (size_t)nvalid * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+    PNP_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  auto nl = std::make_unique<Level>();
+  nl->nv = nvc; nl->nslots = h.nslots; nl->rp = h.rp.p; nl->col = h.adj.p;
+  { // Galerkin gather lists
+    const long n4 = 4 * f.nslots;
+    PNP_REQUIRE(n4 < (1l << 31) && f.nslots < (1l << 29), PNP_E_MESH, "multigrid: too many matrix slots on one level");
+    DBuf<int> key(n4), skey(n4), err(1);
+    DBuf<unsigned> val(n4), sval(n4);
+    err.zero(c.stream);
+    KL(c, k_geo_items, nvf, f.rp, f.col, nvf, f.agg.p, f.par1.p, nl->rp, nl->col, key.p, val.p, err.p);
+    int herr = 0;
+    err.download(&herr, 1, c.stream);
+    PNP_REQUIRE(herr == 0, PNP_E_MESH, "multigrid: refinement levels are not nested");
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.p, skey.p, val.p, sval.p, (int)n4, 0, 32, c.stream);
+    PNP_CUDA(cub::DeviceRadixSort::SortPairs(A.temp(bytes), bytes, key.p, skey.p, val.p, sval.p, (int)n4, 0, 32, c.stream));
+    key.release(); val.release();
+    f.seg_ptr.alloc((size_t)nl->nslots + 1);
+    KL(c, k_lower_bounds_i32, nl->nslots + 1, skey.p, (int)n4, (int)nl->nslots, f.seg_ptr.p);
+    int nvalid = 0;
+    PNP_CUDA(cudaMemcpyAsync(&nvalid, f.seg_ptr.p + nl->nslots, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PNP_CUDA(cudaStreamSynchronize(c.stream));
+    f.seg_items.alloc(nvalid); f.seg_w.alloc(nvalid);
+    KL(c, k_geo_unpack, nvalid, sval.p, (long)nvalid, f.seg_items.p, f.seg_w.p);
+    PNP_CUDA(cudaStreamSynchronize(c.stream));
+    c.launches += 4;
+  }
+  f.alpha = 1.0; // P1 interpolation needs no over-correction
+  nl->vals_own.alloc((size_t)A.NP * nl->nslots);
+  nl->vals = nl->vals_own.p;
+  A.L.push_back(std::move(nl));
+}
+
 void alloc_work(Amg& A, Level& l) {
   const size_t n = (size_t)A.F * l.nv;
-  l.dinv.alloc(n); l.x.alloc(n); l.x2.alloc(n); l.b.alloc(n); l.r.alloc(n);
+  l.dinv.alloc(A.NP == 7 ? 9 * (size_t)l.nv : n); l.x.alloc(n); l.x2.alloc(n); l.b.alloc(n); l.r.alloc(n);
 }
+
+void dense_factor(Ctx& c, Amg& A);
 
 void numeric(Ctx& c, Amg& A, int comp0) {
   for (size_t li = 0; li < A.L.size(); li++) {
@@ -378,33 +522,133 @@ void numeric(Ctx& c, Amg& A, int comp0) {
       Level& n = *A.L[li + 1];
       const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
       if (A.NP == 1)
-        KL(c, k_galerkin<1>, n.nslots, l.seg_ptr.p, l.seg_items.p, n.nslots, l.vals, l.nslots, n.vals_own.p, dm, l.col, l.rp, comp0);
+        KL(c, k_galerkin<1>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, dm, l.col, l.rp, comp0);
       else
-        KL(c, k_galerkin<7>, n.nslots, l.seg_ptr.p, l.seg_items.p, n.nslots, l.vals, l.nslots, n.vals_own.p, dm, l.col, l.rp, comp0);
+        KL(c, k_galerkin<7>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, dm, l.col, l.rp, comp0);
     }
     if (A.NP == 1) KL(c, k_dinv<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
     else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
   }
+  A.dense_n = 0;
+  if ((long)A.F * A.L.back()->nv <= A.dense_max && A.L.size() > 1) dense_factor(c, A);
+  if (A.smoother == 1) {
+    DBuf<unsigned long long> d_l(A.L.size());
+    d_l.zero(c.stream);
+    for (size_t li = 0; li < A.L.size(); li++) {
+      Level& l = *A.L[li];
+      if (A.NP == 1) KL(c, k_gershgorin<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, d_l.p + li);
+      else KL(c, k_gershgorin<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, d_l.p + li);
+    }
+    std::vector<unsigned long long> h = d_l.to_host(c.stream);
+    for (size_t li = 0; li < A.L.size(); li++) {
+      double v; std::memcpy(&v, &h[li], sizeof v);
+      A.L[li]->lmax = (v > 0.0 && std::isfinite(v)) ? v : 2.0;
+    }
+  }
 }
 
-// one V-cycle on level li: solves A x = b approximately, x from a zero initial guess; result in l.x
-void vcycle(Ctx& c, Amg& A, int li, int nu, int comp0) {
-  Level& l = *A.L[li];
+// ---- dense coarsest-level solve ----
+template <int NP>
+__global__ void k_dense_fill(const int* __restrict__ rp, const unsigned* __restrict__ col, const double* __restrict__ vals,
+                             long stride, int nv, double* __restrict__ Ad, long n) {
+  constexpr int F = NP == 1 ? 1 : 3;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nv; r += gridDim.x * blockDim.x)
+    for (int s = rp[r]; s < rp[r + 1]; s++) {
+      const long cidx = col[s] & STAR_VMASK;
+      if (cidx >= nv) continue;
+      if (NP == 1) Ad[cidx * n + r] = vals[s];
+      else {
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+          for (int kj = 0; kj < 3; kj++) {
+            const int pl = pnp_plane(ki, kj);
+            if (pl >= 0) Ad[(F * cidx + kj) * n + F * r + ki] = vals[pl * stride + s];
+          }
+      }
+    }
+}
+__global__ void k_dense_fix_diag(double* __restrict__ Ad, long n) { // decoupled zero rows (all-Dirichlet coarse dofs)
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    if (Ad[i * n + i] == 0.0) Ad[i * n + i] = 1.0;
+}
+#define PNP_CUSOLVER(call)                                                                                          \
+  do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS)                                             \
+    throw ::pnp::Error(PNP_E_CUDA, std::string(#call) + " -> cusolver status " + std::to_string((int)s_)); } while (0)
+
+void dense_factor(Ctx& c, Amg& A) {
+  Level& l = *A.L.back();
   const long n = (long)A.F * l.nv;
+  A.dense_n = (int)n;
+  if (!A.cus) PNP_CUSOLVER(cusolverDnCreate(&A.cus));
+  PNP_CUSOLVER(cusolverDnSetStream(A.cus, c.stream));
+  if (A.dense.n != (size_t)(n * n)) { A.dense.alloc(n * n); A.dense_piv.alloc(n); A.dense_info.alloc(1); }
+  A.dense.zero(c.stream);
+  if (A.NP == 1) KL(c, k_dense_fill<1>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, A.dense.p, n);
+  else KL(c, k_dense_fill<7>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, A.dense.p, n);
+  KL(c, k_dense_fix_diag, n, A.dense.p, n);
+  int lwork = 0;
+  PNP_CUSOLVER(cusolverDnDgetrf_bufferSize(A.cus, (int)n, (int)n, A.dense.p, (int)n, &lwork));
+  if (A.dense_work.n < (size_t)lwork) A.dense_work.alloc(lwork);
+  PNP_CUSOLVER(cusolverDnDgetrf(A.cus, (int)n, (int)n, A.dense.p, (int)n, A.dense_work.p, A.dense_piv.p, A.dense_info.p));
+  int info = 0;
+  A.dense_info.download(&info, 1, c.stream);
+  PNP_REQUIRE(info == 0, PNP_E_BREAKDOWN, "multigrid: coarsest-level matrix is singular (LU info " + std::to_string(info) + ")");
+}
+void dense_solve(Ctx& c, Amg& A, Level& l) { // l.x = A^-1 l.b
+  const long n = A.dense_n;
+  PNP_CUDA(cudaMemcpyAsync(l.x.p, l.b.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  PNP_CUSOLVER(cusolverDnDgetrs(A.cus, CUBLAS_OP_N, (int)n, 1, A.dense.p, (int)n, A.dense_piv.p, l.x.p, (int)n, A.dense_info.p));
+  c.launches += 2;
+}
+
+void jacobi0(Ctx& c, Amg& A, Level& l, double omega, double* dvec) {
+  if (A.F == 1) KL(c, k_jacobi0<1>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
+  else KL(c, k_jacobi0<3>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
+}
+
+// `steps` smoothing steps on level l for A x = b; zero: x starts from 0.  Result in l.x.
+void smooth(Ctx& c, Amg& A, Level& l, int steps, bool zero) {
+  const long n = (long)A.F * l.nv;
+  if (steps <= 0) { if (zero) PNP_CUDA(cudaMemsetAsync(l.x.p, 0, n * sizeof(double), c.stream)); return; }
+  if (A.smoother == 0) {
+    int s = 0;
+    if (zero) { jacobi0(c, A, l, A.omega, nullptr); s = 1; }
+    for (; s < steps; s++) { level_op<2>(c, A, l, l.x.p, l.b.p, l.x2.p); std::swap(l.x.p, l.x2.p); }
+    return;
+  }
+  // Chebyshev polynomial smoother for D^-1 A on [lmax/ratio, 1.1*lmax]; l.r holds the direction d
+  const double lmx = 1.1 * l.lmax, lmn = l.lmax / A.cheb_ratio;
+  const double theta = 0.5 * (lmx + lmn), delta = 0.5 * (lmx - lmn), sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  int s = 0;
+  if (zero) { jacobi0(c, A, l, 1.0 / theta, l.r.p); s = 1; }
+  else { level_op<3>(c, A, l, l.x.p, l.b.p, l.x2.p, 1.0 / theta, 0.0, l.r.p); std::swap(l.x.p, l.x2.p); s = 1; }
+  for (; s < steps; s++) {
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    level_op<3>(c, A, l, l.x.p, l.b.p, l.x2.p, 2.0 * rho_new / delta, rho_new * rho, l.r.p);
+    std::swap(l.x.p, l.x2.p);
+    rho = rho_new;
+  }
+}
+
+// one multigrid cycle on level li for A x = b (gamma = 1: V, 2: W); zero: x starts from 0.  Result in l.x
+void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
+  Level& l = *A.L[li];
   const bool coarsest = li + 1 == (int)A.L.size();
-  const int pre = coarsest ? A.coarse_sweeps : nu;
-  KL(c, k_jacobi0, n, l.dinv.p, l.b.p, A.omega, l.x.p, n);
-  for (int s = 1; s < pre; s++) { level_op<2>(c, A, l, l.x.p, l.b.p, l.x2.p); std::swap(l.x.p, l.x2.p); }
+  if (coarsest && A.dense_n > 0) { dense_solve(c, A, l); return; }
+  smooth(c, A, l, coarsest ? A.coarse_sweeps : nu, zero);
   if (coarsest) return;
   Level& nx = *A.L[li + 1];
   level_op<1>(c, A, l, l.x.p, l.b.p, l.r.p);
-  if (A.F == 1) KL(c, k_restrict<1>, nx.nv, l.agg_ptr.p, l.agg_mem.p, nx.nv, l.r.p, nx.b.p);
-  else KL(c, k_restrict<3>, nx.nv, l.agg_ptr.p, l.agg_mem.p, nx.nv, l.r.p, nx.b.p);
-  vcycle(c, A, li + 1, nu, comp0);
+  if (A.F == 1) KL(c, k_restrict<1>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
+  else KL(c, k_restrict<3>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
+  const int visits = li < A.wlevels ? A.gamma : 1;
+  for (int g = 0; g < visits; g++) cycle(c, A, li + 1, nu, comp0, g == 0);
   const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
-  if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.nv, nx.x.p, A.alpha, l.x.p, dm, comp0);
-  else KL(c, k_prolong<3>, l.nv, l.agg.p, l.nv, nx.x.p, A.alpha, l.x.p, dm, comp0);
-  for (int s = 0; s < nu; s++) { level_op<2>(c, A, l, l.x.p, l.b.p, l.x2.p); std::swap(l.x.p, l.x2.p); }
+  if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
+  else KL(c, k_prolong<3>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
+  smooth(c, A, l, nu, false);
 }
 
 } // namespace
@@ -421,17 +665,37 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
     auto l0 = std::make_unique<Level>();
     l0->nv = (int)c.n_own; l0->nslots = c.nslots; l0->rp = c.rp.p; l0->col = c.adj.p; l0->vals = M.vals.p;
     A.L.push_back(std::move(l0));
-    // the hierarchy's strength of connection is read from the current matrix values, level by level
-    for (int li = 0; li < 24; li++) {
-      if (A.L[li]->nv <= 64) break;
+    A.alpha = S.opt("amg_alpha", 1.6);
+    // geometric levels: every coarser level of the refinement hierarchy (if the mesh was refined in this context)
+    const bool geometric = S.opt("amg_geometric", 1) != 0 && c.n_own == c.nv && !c.hier.empty();
+    A.n_geo = 0;
+    if (geometric) {
+      const int* i2e = c.int2ext.p;
+      for (int hi = (int)c.hier.size() - 1; hi >= 0; hi--) {
+        const int li = (int)A.L.size() - 1;
+        coarsen_geometric(c, A, li, c.hier[hi], i2e);
+        i2e = c.hier[hi].int2ext.p;
+        Level& f = *A.L[li]; Level& n = *A.L[li + 1];
+        const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
+        if (A.NP == 1)
+          KL(c, k_galerkin<1>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
+        else
+          KL(c, k_galerkin<7>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
+        A.n_geo++;
+      }
+    }
+    // algebraic levels below: aggregates from the strength of connection of the current matrix values, level by level
+    A.dense_max = (int)S.opt("amg_dense_max", 4096);
+    for (int li = (int)A.L.size() - 1; li < 24; li++) {
+      if (A.L[li]->nv <= 64 || (long)A.F * A.L[li]->nv <= A.dense_max) break;
       if (!coarsen(c, A, li)) break;
       // numeric values of the new level are needed before it can be coarsened further
       Level& f = *A.L[li]; Level& n = *A.L[li + 1];
       const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
       if (A.NP == 1)
-        KL(c, k_galerkin<1>, n.nslots, f.seg_ptr.p, f.seg_items.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
+        KL(c, k_galerkin<1>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
       else
-        KL(c, k_galerkin<7>, n.nslots, f.seg_ptr.p, f.seg_items.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
+        KL(c, k_galerkin<7>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
     }
     for (auto& l : A.L) alloc_work(A, *l);
     { // level 0 iterates are SpMV inputs whose ghost columns must read as zero
@@ -442,12 +706,15 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
     }
     A.symbolic = true;
     if (S.verbosity > 0) {
-      std::printf("AMG hierarchy:");
+      std::printf("multigrid hierarchy (%d geometric transfers):", A.n_geo);
       for (auto& l : A.L) std::printf(" %d", l->nv);
       std::printf("\n");
     }
   }
   A.L[0]->vals = M.vals.p;
+  A.omega = S.opt("amg_omega", 0.7); A.gamma = (int)S.opt("amg_gamma", 1); A.wlevels = (int)S.opt("amg_wlevels", 99);
+  A.coarse_sweeps = (int)S.opt("amg_coarse_sweeps", 40); A.smoother = (int)S.opt("amg_smoother", 0);
+  A.cheb_ratio = S.opt("amg_cheb_ratio", 8.0);
   numeric(c, A, comp0);
 }
 
@@ -457,7 +724,7 @@ void amg_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y) {
   Level& l0 = *A.L[0];
   const long n = (long)A.F * l0.nv;
   PNP_CUDA(cudaMemcpyAsync(l0.b.p, d, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-  vcycle(c, A, 0, S.prec_steps > 0 ? S.prec_steps : 1, A.comp0);
+  cycle(c, A, 0, S.prec_steps > 0 ? S.prec_steps : 1, A.comp0, true);
   PNP_CUDA(cudaMemcpyAsync(y, l0.x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 }
 

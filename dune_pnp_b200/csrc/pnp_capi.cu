@@ -358,6 +358,12 @@ pnp_status pnp_solver_create(pnp_ctx* ctx, int kind, int prec, int maxit, int pr
   *handle = (int)c.solvers.size() - 1;
   API_END
 }
+pnp_status pnp_solver_set_option(pnp_ctx* ctx, int s, const char* name, double value) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(name, PNP_E_ARG, "null option name");
+  c.solver(s).opts[name] = value;
+  API_END
+}
 pnp_status pnp_solver_apply(pnp_ctx* ctx, int s, int A, int z, int r, double reduction, pnp_lin_result* out) {
   API_BEGIN(ctx)
   LinResult lr = solver_apply(c, c.solver(s), c.mat(A), c.vec(z), c.vec(r), reduction);

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -97,11 +98,24 @@ struct Operator {
   int aux0 = -1, aux1 = -1; // vector handles of coefficient fields
 };
 
+// One coarser level of the refinement hierarchy, captured by mesh_refine(): that level's vertex star (own locality
+// numbering) and the edges whose midpoints became the next finer level's new vertices (reference numbering of this
+// level: vertex nv + k of the finer level is the midpoint of edge k).  Feeds the geometric levels of the multigrid
+// preconditioner (pnp_amg.cu).
+struct HierLevel {
+  long nv = 0, nslots = 0, nE = 0;
+  DBuf<int> rp, int2ext, ext2int;
+  DBuf<unsigned> adj;
+  DBuf<uint64_t> edges; // (min << 32 | max), sorted
+};
+
 struct Amg; // pnp_amg.cu
 
 struct Solver {
   int kind = PNP_SOLVER_BCGS, prec = PNP_PREC_NONE, maxit = 5000, prec_steps = 1, verbosity = 0;
   std::shared_ptr<Amg> amg;
+  std::map<std::string, double> opts; // pnp_solver_set_option
+  double opt(const char* name, double dflt) const { auto it = opts.find(name); return it == opts.end() ? dflt : it->second; }
   DBuf<double> w[6]; // Krylov work vectors, sized on first use
   DBuf<double> dinv; // Jacobi: inverse diagonal
   void ensure(size_t n) { for (auto& b : w) if (b.n != n) b.alloc(n); if (dinv.n != n) dinv.alloc(n); }
@@ -158,6 +172,7 @@ struct Ctx {
   std::vector<std::unique_ptr<Matrix>> mats;
   std::vector<std::unique_ptr<Operator>> ops;
   std::vector<std::unique_ptr<Solver>> solvers;
+  std::vector<HierLevel> hier;         // coarser refinement levels, coarsest first
   std::vector<Vec> carry;              // nodal fields in reference numbering, interpolated by mesh_refine()
   // a new / refined mesh invalidates every object sized by it
   void invalidate_mesh_objects() {

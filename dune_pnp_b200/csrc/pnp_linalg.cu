@@ -13,6 +13,7 @@
 #include <cmath>
 
 #include "pnp_common.cuh"
+#include "pnp_spmv.cuh"
 
 namespace pnp {
 
@@ -60,59 +61,6 @@ __global__ void k_reduce_final(const double* __restrict__ partial, int nblocks, 
     }
     __syncthreads();
   }
-}
-
-// ---- SpMV: LANES lanes cooperate on one vertex row (rows have ~7 slots) -------------------
-// NP = 1: scalar matrix; NP = 7: 3-field PNP block matrix in plane layout.
-// NDOT = 0: y = A x;  1: also sum y.w1;  2: also sum y.w1 and y.y
-template <int NP, int NDOT, int LANES>
-__global__ void __launch_bounds__(RED_BLOCK)
-k_spmv(const int* __restrict__ rp, const unsigned* __restrict__ adj, const double* __restrict__ vals, long stride,
-       const double* __restrict__ x, double* __restrict__ y, int nv, const double* __restrict__ w1,
-       double* __restrict__ partial) {
-  constexpr int F = NP == 1 ? 1 : 3;
-  constexpr int RPW = 32 / LANES; // rows per warp
-  const int lane = threadIdx.x & (LANES - 1);
-  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-  const int ngrp = gridDim.x * blockDim.x / LANES;
-  double dsum[NDOT > 0 ? NDOT : 1];
-#pragma unroll
-  for (int j = 0; j < (NDOT > 0 ? NDOT : 1); j++) dsum[j] = 0.0;
-  // warp-uniform trip count: every lane of a warp runs the same number of iterations
-  const int base0 = grp - (grp % RPW);
-  for (int base = base0; base < nv; base += ngrp) {
-    const int row = base + (grp % RPW);
-    double acc[F];
-#pragma unroll
-    for (int k = 0; k < F; k++) acc[k] = 0.0;
-    if (row < nv) {
-      const int b = rp[row], e = rp[row + 1];
-      for (int s = b + lane; s < e; s += LANES) {
-        const long c = adj[s] & STAR_VMASK;
-        if (NP == 1) {
-          acc[0] += vals[s] * x[c];
-        } else {
-          const double x0 = x[3 * c], x1 = x[3 * c + 1], x2 = x[3 * c + 2];
-          acc[0] += vals[s] * x0 + vals[stride + s] * x1 + vals[2 * stride + s] * x2;
-          acc[1] += vals[3 * stride + s] * x0 + vals[4 * stride + s] * x1;
-          acc[2] += vals[5 * stride + s] * x0 + vals[6 * stride + s] * x2;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < F; k++)
-#pragma unroll
-      for (int o = LANES / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (lane == 0 && row < nv) {
-#pragma unroll
-      for (int k = 0; k < F; k++) {
-        y[(long)F * row + k] = acc[k];
-        if (NDOT >= 1) dsum[0] += acc[k] * w1[(long)F * row + k];
-        if (NDOT >= 2) dsum[1] += acc[k] * acc[k];
-      }
-    }
-  }
-  if (NDOT > 0) block_partials<(NDOT > 0 ? NDOT : 1)>(dsum, partial);
 }
 
 // ---- fused BLAS-1 ----
@@ -209,18 +157,11 @@ void finish_reduce(Ctx& c, int nblocks, int nr, double* out) {
 void spmv_dots(Ctx& c, const Matrix& A, double* x, double* y, int ndot, const double* w1, double* dots) {
   ensure_red(c);
   halo_exchange(c, x, A.nplanes == 1 ? 1 : 3); // ghost columns of x (no-op on one GPU)
-  constexpr int LANES = 8;
-  const long nv = c.n_own;
-  const int grid = grid_for(nv * LANES, RED_BLOCK, c.sm_count * 8);
-  const long st = c.nslots;
+  StarOpArgs a{c.rp.p, c.adj.p, A.vals.p, c.nslots, (int)c.n_own, x, y};
+  a.w1 = w1; a.partial = c.red_partial.p;
   c.prof_mark();
-#define SPMV_CASE(NPv, ND)                                                                                      \
-  k_spmv<NPv, ND, LANES><<<grid, RED_BLOCK, 0, c.stream>>>(c.rp.p, c.adj.p, A.vals.p, st, x, y, (int)nv, w1, \
-                                                          c.red_partial.p)
-  if (A.nplanes == 1) { if (ndot == 0) SPMV_CASE(1, 0); else if (ndot == 1) SPMV_CASE(1, 1); else SPMV_CASE(1, 2); }
-  else { if (ndot == 0) SPMV_CASE(7, 0); else if (ndot == 1) SPMV_CASE(7, 1); else SPMV_CASE(7, 2); }
-#undef SPMV_CASE
-  PNP_CHECK_LAUNCH(); c.launches++;
+  const int grid = ndot == 0 ? launch_star_op<EPI_PLAIN, 0>(c, A.nplanes, a)
+                 : ndot == 1 ? launch_star_op<EPI_PLAIN, 1>(c, A.nplanes, a) : launch_star_op<EPI_PLAIN, 2>(c, A.nplanes, a);
   c.prof_mark();
   if (ndot > 0) finish_reduce(c, grid, ndot, dots);
 }

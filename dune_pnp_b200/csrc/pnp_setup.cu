@@ -162,6 +162,7 @@ void mesh_set(Ctx& c, long nv, const double* x, const double* y, long nT, const 
     PNP_REQUIRE(ba[i] >= 0 && ba[i] < nv && bb[i] >= 0 && bb[i] < nv, PNP_E_MESH, "boundary vertex out of range");
   PNP_REQUIRE(n_own > 0 && n_own <= nv, PNP_E_ARG, "owned vertex count out of range");
   c.nv = nv; c.nT = nT; c.nB = nB; c.n_own = n_own;
+  c.hier.clear();
   c.halo_nbr.clear(); c.halo_send_ptr.clear(); c.halo_recv_ptr.clear(); c.halo_send_ext.clear();
   c.invalidate_mesh_objects();
   c.carry.clear();
@@ -171,6 +172,8 @@ void mesh_set(Ctx& c, long nv, const double* x, const double* y, long nT, const 
   PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+static void star_build(Ctx& c, bool renumber);
+
 void mesh_refine(Ctx& c, int levels) {
   PNP_REQUIRE(c.nv > 0, PNP_E_ARG, "no mesh set");
   PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "device refinement works on an unpartitioned mesh (refine before partitioning)");
@@ -178,6 +181,12 @@ void mesh_refine(Ctx& c, int levels) {
   for (int l = 0; l < levels; l++) {
     const long nT = c.nT, nv = c.nv, nB = c.nB, nk = 3 * nT;
     PNP_REQUIRE(nk < (1l << 31), PNP_E_MESH, "mesh too large to refine");
+    // keep this level for the geometric multigrid hierarchy: its star moves out of the context
+    if (!c.finalized) star_build(c, true);
+    HierLevel hl;
+    hl.nv = nv; hl.nslots = c.nslots;
+    hl.rp = std::move(c.rp); hl.adj = std::move(c.adj); hl.int2ext = std::move(c.int2ext); hl.ext2int = std::move(c.ext2int);
+    c.finalized = false;
     DBuf<uint64_t> keys(nk), sorted(nk), ukeys(nk);
     DBuf<long> d_nE(1);
     LAUNCH(c, k_edge_keys, nk, c.ctri.p, nT, keys.p);
@@ -214,6 +223,8 @@ void mesh_refine(Ctx& c, int levels) {
     c.cx = std::move(nx); c.cy = std::move(ny); c.ctri = std::move(ntri);
     c.cba = std::move(na); c.cbb = std::move(nb); c.cbphys = std::move(np);
     c.nv = nv + nE; c.nT = 4 * nT; c.nB = 2 * nB; c.n_own = c.nv;
+    hl.nE = nE; hl.edges = std::move(ukeys);
+    c.hier.push_back(std::move(hl));
   }
   c.invalidate_mesh_objects();
 }
@@ -239,7 +250,8 @@ void carry_get(Ctx& c, int i, Vec& out) {
   PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-void mesh_finalize(Ctx& c, bool renumber) {
+// vertex star of the current mesh: fills c.int2ext/ext2int/xy/rp/adj/nslots
+static void star_build(Ctx& c, bool renumber) {
   PNP_REQUIRE(c.nv > 0, PNP_E_ARG, "no mesh set");
   PNP_REQUIRE(c.nv < STAR_MAX_VERTICES, PNP_E_MESH, "more than 2^27 vertices on one GPU");
   const long nv = c.nv, nT = c.nT, nB = c.nB, nrec = 3 * nT, no = c.n_own;
@@ -294,6 +306,13 @@ void mesh_finalize(Ctx& c, bool renumber) {
   err.download(&herr, 1, c.stream);
   PNP_REQUIRE(herr != 1, PNP_E_MESH, "degenerate triangle (zero area or repeated vertex)");
   PNP_REQUIRE(herr == 0, PNP_E_MESH, "vertex star is not a single fan (non-manifold mesh)");
+}
+
+void mesh_finalize(Ctx& c, bool renumber) {
+  star_build(c, renumber);
+  const long nv = c.nv, nB = c.nB, no = c.n_own;
+  DBuf<int> err(1); err.zero(c.stream);
+  int herr = 0;
 
   // boundary faces
   c.d_bfaces.alloc(nB);

@@ -150,6 +150,13 @@ typedef struct {
   int status;
 } pnp_lin_result;
 pnp_status pnp_solver_create(pnp_ctx*, int kind, int prec, int maxit, int prec_steps, int verbosity, int* solver);
+/* tuning knobs of the preconditioner, by name: "amg_smoother" (0 damped Jacobi, 1 Chebyshev), "amg_omega",
+ * "amg_alpha" (coarse-correction scaling, dune-istl default 1.6), "amg_gamma" (1 V-cycle, 2 W-cycle), "amg_wlevels" (W on the first n levels only),
+ * "amg_coarse_sweeps", "amg_dense_max" (coarsest level with at most this many dofs is solved by dense LU; 0: sweeps),
+ * "amg_cheb_ratio" (lambda_max / lambda_min of the Chebyshev interval), "amg_geometric" (default 1: when
+ * the mesh was refined with pnp_mesh_refine, the coarser refinement levels become multigrid levels with P1
+ * interpolation and Galerkin operators; aggregation continues below the coarsest mesh) */
+pnp_status pnp_solver_set_option(pnp_ctx*, int solver, const char* name, double value);
 /* z: initial guess in, solution out; r: right-hand side in, residual out (as ISTL does) */
 pnp_status pnp_solver_apply(pnp_ctx*, int solver, int mat_handle, int z, int r, double reduction, pnp_lin_result*);
 
