@@ -175,14 +175,17 @@ def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
     return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps), us
 
 
+# N > 1: per-subdomain aggregation AMG V-cycle (no geometric levels across ranks yet; a truncated W-cycle halves the
+# iteration count but is launch-bound on the small levels: 166 its / 15.4 s vs 300 its / 4.0 s at k = 6, N = 2)
+AMG_PARTITIONED = {"amg_geometric": 0}
 AMG_FINE = {"amg_geometric": 1}   # refinement levels as multigrid levels (P1 interpolation), aggregation below the coarsest mesh
 
 
-def fine_solver(c, capi, prec_steps):
+def fine_solver(c, capi, prec_steps, options=None):
     """BiCGSTAB + multigrid for the timed step: V(nu,nu) damped Jacobi; the mesh levels created by pnp_mesh_refine are the
     upper multigrid levels (P1 interpolation, Galerkin operators), aggregation AMG continues below the Gmsh mesh."""
     s = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0)
-    for k, v in AMG_FINE.items():
+    for k, v in (AMG_FINE if options is None else options).items():
         c.solver_set_option(s, k, v)
     return s
 
@@ -221,7 +224,7 @@ def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps,
     if verbose:
         print("# rank %d: %d owned + %d ghost vertices, %d neighbours" % (rank, plan.n_own, plan.nv - plan.n_own, len(plan.nbr)),
               file=sys.stderr, flush=True)
-    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps), us
+    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps, AMG_PARTITIONED), us
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -313,7 +316,14 @@ def run_gpu(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     # algorithmic bytes of one fine-level 3-field SpMV (DESIGN.md "SpMV"): 7 value planes + column index per
     # slot, row pointer + x read + y written per vertex
-    spmv_bytes = (7 * 8 + 4) * ns + (4 + 2 * 3 * 8) * n_own   # rank 0's share
+    # per epilogue kind: plain y = A x; residual also reads b (24 B/vertex); a smoother step reads b, its own x row
+    # and the 3x3 inverse diagonal block (24 + 24 + 72 B/vertex)
+    base = (7 * 8 + 4) * ns + (4 + 2 * 3 * 8) * n_own   # rank 0's share
+    kind_bytes = [base, base + 24 * n_own, base + 120 * n_own]
+    spmv_total_bytes = sum(b * n for b, n in zip(kind_bytes, n_spmv))
+    spmv_ms_by_kind, n_spmv_by_kind = spmv_ms, n_spmv
+    spmv_ms, n_spmv = sum(spmv_ms), sum(n_spmv)
+    spmv_bytes = spmv_total_bytes / max(n_spmv, 1)
     spmv_avg_s = spmv_ms / 1e3 / max(n_spmv, 1)
     achieved = spmv_bytes / spmv_avg_s / 1e9
     asm_s = float(np.mean([x.seconds_assembly for x in stats]))
@@ -335,11 +345,13 @@ def run_gpu(args, rank, world, local_rank):
         "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,
         "krylov_iterations": int(r.linear_iterations), "line_search_trials": int(r.line_search_trials),
         "defect_before": r.first_defect, "defect_after": r.defect,
-        "spmv_gbs": achieved, "spmv_launches_timed": n_spmv, "spmv_share_of_step": spmv_ms / 1e3 / max(sec_dev, 1e-30),
+        "spmv_gbs": achieved, "spmv_launches_timed": n_spmv,
+        "spmv_by_kind": {k: {"launches": n, "avg_ms": (m / n if n else None), "bytes": b} for k, n, m, b in
+                         zip(["plain", "residual", "smoother"], n_spmv_by_kind, spmv_ms_by_kind, kind_bytes)}, "spmv_share_of_step": spmv_ms / 1e3 / max(sec_dev, 1e-30),
         "setup_s": t_setup, "wall_s": wall,
-        "roofline": {"bound": "hbm", "kernel": "3-field SpMV on the vertex-star layout (k_spmv<7,*> / k_level_op<7,*>)",
+        "roofline": {"bound": "hbm", "kernel": "3-field SpMV on the vertex-star layout, fine level (k_star_op<7,EPI,NDOT>, all epilogues)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,  # launch-weighted mean over the epilogue kinds
                      "avg_launch_ms": spmv_avg_s * 1e3},
         "cpu_baseline": None if cpu is None else {
             "value": cpu["value"], "unit": UNIT, "cores": 1, "kind": "port",

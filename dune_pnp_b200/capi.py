@@ -118,9 +118,9 @@ class Context:
         self._ck(lib().pnp_profile_spmv(self._h, int(enable)))
 
     def profile_spmv_get(self):
-        n = C.c_long(); ms = C.c_double()
-        self._ck(lib().pnp_profile_spmv_get(self._h, C.byref(n), C.byref(ms)))
-        return n.value, ms.value
+        n = (C.c_long * 3)(); ms = (C.c_double * 3)()
+        self._ck(lib().pnp_profile_spmv_get(self._h, n, ms))
+        return list(n), list(ms)
 
     def profiler_range(self, start):
         self._ck(lib().pnp_profiler_range(self._h, int(start)))

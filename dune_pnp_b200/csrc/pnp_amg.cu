@@ -371,7 +371,7 @@ void level_op(Ctx& c, const Amg& A, const Level& l, const double* x, const doubl
   StarOpArgs a{l.rp, l.col, l.vals, l.nslots, l.nv, x, y};
   a.b = b; a.dinv = l.dinv.p; a.block = A.NP == 7; a.omega = omega_or_c2 < 0 ? A.omega : omega_or_c2; a.c1 = c1; a.dvec = dvec;
   const bool fine = &l == A.L[0].get();
-  if (fine) c.prof_mark();
+  if (fine) c.prof_mark(EPI == EPI_RESIDUAL ? 1 : 2);
   launch_star_op<EPI, 0>(c, A.NP, a);
   if (fine) c.prof_mark();
 }

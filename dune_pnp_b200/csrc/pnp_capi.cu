@@ -71,10 +71,13 @@ pnp_status pnp_profile_spmv(pnp_ctx* ctx, int enable) {
 pnp_status pnp_profile_spmv_get(pnp_ctx* ctx, long* launches, double* total_ms) {
   API_BEGIN(ctx)
   PNP_CUDA(cudaStreamSynchronize(c.stream));
-  double ms = 0;
-  for (size_t i = 0; i + 1 < c.prof_used; i += 2) { float t = 0; PNP_CUDA(cudaEventElapsedTime(&t, c.prof_ev[i], c.prof_ev[i + 1])); ms += t; }
-  if (launches) *launches = (long)(c.prof_used / 2);
-  if (total_ms) *total_ms = ms;
+  for (int k = 0; k < 3; k++) { if (launches) launches[k] = 0; if (total_ms) total_ms[k] = 0; }
+  for (size_t i = 0; i + 1 < c.prof_used; i += 2) {
+    float t = 0; PNP_CUDA(cudaEventElapsedTime(&t, c.prof_ev[i], c.prof_ev[i + 1]));
+    const int k = c.prof_kind[i / 2];
+    if (launches) launches[k]++;
+    if (total_ms) total_ms[k] += t;
+  }
   API_END
 }
 pnp_status pnp_profiler_range(pnp_ctx* ctx, int start) {

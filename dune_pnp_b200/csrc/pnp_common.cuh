@@ -160,11 +160,13 @@ struct Ctx {
   // optional CUDA-event profile of the fine-level SpMV launches (bench.py's roofline leg)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_kind;          // per event pair: 0 plain/dot SpMV, 1 residual epilogue, 2 smoother epilogue
   size_t prof_used = 0;
   cudaEvent_t tm0 = nullptr, tm1 = nullptr; // pnp_timer_start/stop
-  void prof_mark() {
+  void prof_mark(int kind = 0) {
     if (!prof) return;
     if (prof_used == prof_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); }
+    if (prof_used % 2 == 0) { if (prof_kind.size() <= prof_used / 2) prof_kind.resize(prof_used / 2 + 1); prof_kind[prof_used / 2] = kind; }
     cudaEventRecord(prof_ev[prof_used++], stream);
   }
   // handle tables
@@ -172,12 +174,17 @@ struct Ctx {
   std::vector<std::unique_ptr<Matrix>> mats;
   std::vector<std::unique_ptr<Operator>> ops;
   std::vector<std::unique_ptr<Solver>> solvers;
+  // Newton / SLP work space (r, z, previous iterate, Jacobian), kept between calls: allocating and freeing ~20 GB per
+  // Newton call costs more than the step itself
+  Vec ws_r, ws_z, ws_prev;
+  Matrix ws_A;
   std::vector<HierLevel> hier;         // coarser refinement levels, coarsest first
   std::vector<Vec> carry;              // nodal fields in reference numbering, interpolated by mesh_refine()
   // a new / refined mesh invalidates every object sized by it
   void invalidate_mesh_objects() {
     finalized = false; constraints_built = false;
     vecs.clear(); mats.clear(); ops.clear(); solvers.clear();
+    ws_r.d.release(); ws_z.d.release(); ws_prev.d.release(); ws_A.vals.release();
   }
   // scratch for reductions
   DBuf<double> red_partial, red_out;

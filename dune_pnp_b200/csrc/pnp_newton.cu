@@ -21,12 +21,13 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
   PNP_REQUIRE(u.fields == F, PNP_E_ARG, "vector field count does not match the operator");
   const long n = c.n_own * F, nall = c.nv * F;
   R = pnp_newton_result();
-  Vec r, z, prev_u;
+  Vec &r = c.ws_r, &z = c.ws_z, &prev_u = c.ws_prev;
+  Matrix& A = c.ws_A;
   r.fields = z.fields = prev_u.fields = F;
-  r.d.alloc(nall); z.d.alloc(nall); prev_u.d.alloc(nall);
+  if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); prev_u.d.alloc(nall); }
   r.d.zero(c.stream); z.d.zero(c.stream);
-  Matrix A; A.op = op.op; A.nplanes = op_planes(op.op);
-  A.vals.alloc((size_t)A.nplanes * c.nslots);
+  A.op = op.op; A.nplanes = op_planes(op.op);
+  if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
   const double t_start = now();
   auto sync = [&] { PNP_CUDA(cudaStreamSynchronize(c.stream)); };
   auto defect = [&]() {
@@ -129,10 +130,13 @@ LinResult slp_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, double reduct
   const int F = op_fields(op.op);
   PNP_REQUIRE(u.fields == F, PNP_E_ARG, "vector field count does not match the operator");
   const long n = c.n_own * F, nall = c.nv * F;
-  Vec r, z; r.fields = z.fields = F; r.d.alloc(nall); z.d.alloc(nall);
+  Vec &r = c.ws_r, &z = c.ws_z;
+  Matrix& A = c.ws_A;
+  r.fields = z.fields = F;
+  if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); c.ws_prev.d.alloc(nall); }
   r.d.zero(c.stream); z.d.zero(c.stream);
-  Matrix A; A.op = op.op; A.nplanes = op_planes(op.op);
-  A.vals.alloc((size_t)A.nplanes * c.nslots);
+  A.op = op.op; A.nplanes = op_planes(op.op);
+  if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
   assemble_jacobian(c, op, u, A, jac_mode, eps);
   assemble_residual(c, op, u, r);
   vec_zero(c, z.d.p, n);

@@ -57,6 +57,7 @@ long pnp_launch_count(pnp_ctx* ctx);
 /* measurement hooks (bench.py): CUDA events on the context's stream.  pnp_profile_spmv(ctx,1) brackets every
  * fine-level SpMV launch with an event pair; pnp_profile_spmv_get() returns their count and summed duration. */
 pnp_status pnp_profile_spmv(pnp_ctx*, int enable);
+/* launches[3], total_ms[3]: by epilogue kind -- 0: y = A x (+ fused dots), 1: y = b - A x, 2: smoother step */
 pnp_status pnp_profile_spmv_get(pnp_ctx*, long* launches, double* total_ms);
 /* cudaProfilerStart/Stop: lets `ncu --profile-from-start off` see only the timed region */
 pnp_status pnp_profiler_range(pnp_ctx*, int start);
