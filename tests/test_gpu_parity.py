@@ -308,3 +308,138 @@ def test_errors_are_reported():
     with pytest.raises(capi.PnpError) as e:
         c.mesh_finalize()
     assert e.value.status == 9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# solver stack beyond Jacobi: multigrid preconditioner, StationaryLinearProblemSolver, nested iteration
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op", [ora.OP_PB, ora.OP_PNP])
+@pytest.mark.parametrize("geometric", [0, 1])
+def test_multigrid_preconditioner(op, geometric):
+    """BiCGSTAB + multigrid on a twice-refined pore mesh: aggregation-only vs refinement levels as multigrid levels."""
+    capi = _capi()
+    c, m, p = make_ctx("pore", levels=2)
+    F = ora.nfields(op)
+    h = c.operator(op, 0)
+    u = c.vec(F); c.vec_set(u, 0.05)
+    A = c.matrix(h)
+    c.jacobian(h, u, A, capi.JAC_ANALYTIC, 0.0)
+    b = np.random.RandomState(0).uniform(-1, 1, F * m.nv)
+    b[c.constraints(h, F)] = 0.0
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 300, 2)
+    c.solver_set_option(s, "amg_geometric", geometric)
+    z, r = c.vec(F), c.vec(F, b)
+    res = c.solve(s, A, z, r, 1e-8)
+    assert res.converged
+    assert res.iterations <= (12 if geometric else 40)
+    rp, col = c.pattern(h, F)
+    val = c.matrix_values(h, A, len(col))
+    assert np.linalg.norm(b - ora.spmv(rp, col, val, c.download(z, F))) <= 2e-8 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("smoother,gamma", [(1, 1), (0, 2)])
+def test_multigrid_options(smoother, gamma):
+    capi = _capi()
+    c, m, p = make_ctx("pore_small", levels=2)
+    h = c.operator(capi.OP_PB, 0)
+    u = c.vec(1); A = c.matrix(h)
+    c.jacobian(h, u, A, capi.JAC_ANALYTIC, 0.0)
+    b = np.random.RandomState(1).uniform(-1, 1, m.nv); b[c.constraints(h, 1)] = 0.0
+    s = c.solver(capi.SOLVER_CG if smoother == 1 else capi.SOLVER_BCGS, capi.PREC_AMG, 200, 2)
+    for k, v in (("amg_geometric", 0), ("amg_smoother", smoother), ("amg_gamma", gamma), ("amg_alpha", 1.0 if gamma == 2 else 1.6),
+                 ("amg_dense_max", 0)):
+        c.solver_set_option(s, k, v)
+    z, r = c.vec(1), c.vec(1, b)
+    res = c.solve(s, A, z, r, 1e-8)
+    assert res.converged and res.iterations < 60
+
+
+@pytest.mark.parametrize("name", ["sphere", "pore_small"])
+def test_slp_poisson_matches_oracle(name):
+    """StationaryLinearProblemSolver on the Poisson operator (instationary_pnp_from_pb_md.hh:343-350): one step solves it."""
+    capi = _capi()
+    c, m, p = make_ctx(name)
+    rng = np.random.RandomState(3)
+    cp = 0.06 * np.exp(rng.uniform(-1, 1, m.nv)); cm = 0.06 * np.exp(rng.uniform(-1, 1, m.nv))
+    u0 = ora.interpolate(m, p, 0, np.zeros(m.nv))
+    h = _gpu_operator(c, capi.OP_POISSON, cp, cm, 1.0)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 5000)
+    vu = c.vec(1, u0)
+    res = c.slp(h, vu, s, 1e-10)
+    assert res.converged
+    u_o, res_o = ora.slp(m, p, ora.OP_POISSON, u0, 1e-10, prec=ora.PREC_SSOR, aux0=cp, aux1=cm)
+    assert res_o["converged"]
+    u = c.download(vu, 1)
+    assert np.linalg.norm(u - u_o) <= 1e-8 * np.linalg.norm(u_o)
+    d = ora.dirichlet(m, p, 1, 0)
+    assert np.array_equal(u[d], u0[d])  # Dirichlet values never change
+
+
+@pytest.mark.parametrize("valency", [1.0, -1.0])
+def test_slp_diffusion_matches_oracle(valency):
+    """One StationaryLinearProblemSolver step on the drift-diffusion operator (instationary_pnp_from_pb_md.hh:357-386)."""
+    capi = _capi()
+    c, m, p = make_ctx("pore_small")
+    phi = 0.05 * m.x + 0.01 * m.y
+    u0 = ora.interpolate(m, p, 1, np.zeros(m.nv)) * (1 + 0.1 * np.sin(m.x))
+    u0[ora.dirichlet(m, p, 1, 1)] = 0.06
+    h = c.operator(capi.OP_DIFFUSION, 1)
+    c.operator_set_coefficient(h, 0, c.vec(1, phi)); c.operator_set_valency(h, valency)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 5000)
+    vu = c.vec(1, u0)
+    res = c.slp(h, vu, s, 1e-10)
+    assert res.converged
+    u_o, res_o = ora.slp(m, p, ora.OP_DIFFUSION, u0, 1e-10, prec=ora.PREC_SSOR, aux0=phi, valency=valency, comp0=1)
+    assert np.linalg.norm(c.download(vu, 1) - u_o) <= 1e-8 * np.linalg.norm(u_o)
+
+
+def test_nested_iteration_carry_matches_interpolation():
+    capi = _capi()
+    import bench
+    c, m, p = make_ctx("pore_small")
+    u = np.random.RandomState(9).uniform(-1, 1, 3 * m.nv)
+    vu = c.vec(3, u)
+    c.carry_set([vu])
+    c.mesh_refine(2); c.mesh_finalize(True)
+    out = c.vec(3); c.carry_get(0, out)
+    want, mm = u, m
+    for _ in range(2):
+        want = bench.carry_numpy(mm, want, 3); mm = mm.refine(1)
+    assert np.array_equal(c.download(out, 3), want)
+
+
+def test_full_size_properties_level5():
+    """Size-independent checks on a 2.9 M-vertex mesh (k = 5): linearity of the Jacobian action, J(u) z ~ R(u+z) - R(u)
+    for the PNP operator, residual of the Dirichlet dofs is zero, SpMV of the mass matrix with ones integrates the area."""
+    capi = _capi()
+    a = util.load_mesh_arrays("pore")
+    c = capi.Context(0); c.mesh_set(**a); c.params_read(util.cfg_path("pore")); c.mesh_refine(5); c.mesh_finalize(True)
+    nv = c.mesh_sizes()["nv"]
+    assert nv == 2946529
+    # mass operator: sum(M 1) over non-Dirichlet rows + nothing else; use a component without Dirichlet rows? all have -> compare area bound
+    hm = c.operator(capi.OP_MASS, 0)
+    one, r = c.vec(1), c.vec(1); c.vec_set(one, 1.0)
+    c.residual(hm, one, r)   # residual of the mass operator = M u
+    area = 100.0 * 55.0      # bounding box; the pore/DNA cut-outs make the domain smaller
+    tot = c.dot(r, one)
+    assert 0.5 * area < tot < area
+    # PNP: directional derivative vs Jacobian action on smooth non-constant fields (Dirichlet rows excluded:
+    # the residual is constrained to zero there while (J z)_d = z_d)
+    g = c.mesh_get()
+    x, y = g["x"], g["y"]
+    uh = np.concatenate([0.3 * np.sin(0.05 * x) * np.cos(0.04 * y), 0.06 * np.exp(-0.01 * x), 0.06 * np.exp(0.01 * x + 0.003 * y)])
+    zh = 1e-5 * np.concatenate([np.cos(0.07 * x + 0.02 * y), 0.06 * np.sin(0.03 * x), 0.06 * np.cos(0.05 * y)])
+    h = c.operator(capi.OP_PNP, 0)
+    free = ~c.constraints(h, 3)
+    zh[~free] = 0.0  # Dirichlet columns are not part of the Jacobian
+    u, z, ru, ruz, Jz, A = c.vec(3, uh), c.vec(3, zh), c.vec(3), c.vec(3), c.vec(3), c.matrix(h)
+    c.residual(h, u, ru)
+    c.jacobian(h, u, A, capi.JAC_ANALYTIC, 0.0)
+    c.spmv(A, z, Jz)
+    c.axpy(u, 1.0, z)
+    c.residual(h, u, ruz)
+    lhs = (c.download(ruz, 3) - c.download(ru, 3))[free]
+    rhs = c.download(Jz, 3)[free]
+    # (R(u+z) - R(u) - J z) is second order in z: the only non-linear terms are the c * grad(phi) products
+    assert np.linalg.norm(lhs - rhs) <= 1e-4 * np.linalg.norm(rhs)
+    assert not c.download(ru, 3)[~free].any()
