@@ -190,41 +190,36 @@ def fine_solver(c, capi, prec_steps, options=None):
     return s
 
 
-def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose, rank, world, dist):
-    """N > 1: every rank solves the (small) coarse problem, keeps its part of the coarse mesh plus one ghost layer,
-    refines it on its GPU carrying the coarse solution, trims the ghost layer, and builds the halo plan."""
+def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose, rank, world, dist, cfg):
+    """N > 1: every rank solves the (small) coarse problem; the Gmsh mesh is partitioned, every rank refines its part level
+    by level (host plumbing, dune_pnp_b200/partition.py) and registers each level as a multigrid level of the library
+    (distributed geometric multigrid: halo exchange per level, re-discretised coarse operators, replicated dense solve
+    on the Gmsh mesh).  The start state is the coarse solution, injected at `coarse_level` and P1-interpolated upwards."""
     from dune_pnp_b200 import partition
+    a_base = c.mesh_get()                        # level 0 (the context still holds the Gmsh mesh)
     vu = coarse_stage(c, capi, coarse_level, jac_mode, prec_steps, verbose)
-    a0 = c.mesh_get()
-    u0 = c.download(vu, 3).reshape(3, -1)
-    tri = a0["tri"]
-    part = partition.rcb_partition(a0["x"][tri].mean(1), a0["y"][tri].mean(1), world)
-    lm = partition.extract_local(a0, part, rank, {"u": u0})
-    L = levels - coarse_level
-    c.mesh_set(lm.x, lm.y, lm.tri, lm.ba, lm.bb, lm.bphys)
-    c.carry_set_host(lm.fields["u"])
-    c.mesh_refine(L)
-    fine = c.mesh_get()
-    uf = c.carry_get_host(0, 3)
-    lmf = partition.LocalMesh(fine["x"], fine["y"], fine["tri"], np.repeat(lm.tag, 4 ** L), fine["ba"], fine["bb"],
-                              fine["bphys"], {"u": uf}).trim(rank)
+    ak = c.mesh_get()
+    uk = c.download(vu, 3).reshape(3, -1)
+    lookup_tab = {k: i for i, k in enumerate(partition._coord_keys(ak["x"], ak["y"]))}
+
+    def lookup(x, y):
+        idx = np.array([lookup_tab[k] for k in partition._coord_keys(x, y)], dtype=np.int64)
+        return {"u": uk[:, idx]}
 
     def all_gather(obj):
         out = [None] * world
         dist.all_gather_object(out, obj)
         return out
-    plan = partition.finalize(lmf, rank, world, all_gather)
+    plans = partition.build_hierarchy(a_base, world, rank, levels, all_gather=all_gather, fields_at=(coarse_level, lookup))
     uid = [capi.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    c.mesh_set_local(plan.n_own, plan.x, plan.y, plan.tri, plan.ba, plan.bb, plan.bphys)
-    c.comm_init(rank, world, uid[0])
-    c.halo_set(plan.nbr, plan.send_ptr, plan.send_idx, plan.recv_ptr)
-    c.mesh_finalize(True)
-    us = c.vec(3, plan.fields["u"].reshape(-1))
+    children = partition.setup_distributed(capi, c, plans, cfg, rank, world, uid[0])
+    fine = plans[-1]
+    us = c.vec(3, fine.fields["u"].reshape(-1))
     if verbose:
-        print("# rank %d: %d owned + %d ghost vertices, %d neighbours" % (rank, plan.n_own, plan.nv - plan.n_own, len(plan.nbr)),
-              file=sys.stderr, flush=True)
-    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps, AMG_PARTITIONED), us
+        print("# rank %d: %d owned + %d ghost vertices, %d neighbours, %d multigrid levels" % (
+            rank, fine.n_own, fine.nv - fine.n_own, len(fine.nbr), len(plans)), file=sys.stderr, flush=True)
+    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps), us, children
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -242,8 +237,8 @@ def run_gpu(args, rank, world, local_rank):
     if world == 1:
         h, s, us = build_state(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, args.verbose)
     else:
-        h, s, us = build_state_partitioned(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, args.verbose,
-                                           rank, world, dist)
+        h, s, us, _children = build_state_partitioned(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps,
+                                                      args.verbose, rank, world, dist, cfg)
     sizes = c.mesh_sizes()
     nv, ns = sizes["nv"], sizes["nslots"]       # local vertices (owned + ghost), local matrix slots
     n_own = c.mesh_owned()
@@ -336,10 +331,10 @@ def run_gpu(args, rank, world, local_rank):
                                "step (Jacobian assembly, BiCGSTAB + aggregation AMG, line search)" % args.levels,
                    "levels": args.levels, "dofs": gdof, "matrix_slots": gslots,
                    "rank0_owned_vertices": n_own, "rank0_ghost_vertices": nv - n_own,
-                   "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the level-%d mesh), halo exchange + scalar allreduce over NCCL, block-Jacobi AMG" % (world, args.coarse_level),
+                   "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the Gmsh mesh), NCCL halo exchange per multigrid level + scalar allreduce" % world,
                    "jacobian": args.jac, "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
                        "refinement levels with P1 interpolation + Galerkin operators, aggregation AMG below the Gmsh mesh" if world == 1
-                       else "aggregation AMG per subdomain (block-Jacobi over ranks)"),
+                       else "distributed refinement levels with P1 interpolation, re-discretised operators, replicated dense LU on the Gmsh mesh"),
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
                    "l2_policy": "inputs larger than L2 (per GPU: matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
         "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,

@@ -93,9 +93,14 @@ def _i(a):
 class Context:
     """One GPU, one mesh.  Mirrors the C ABI one to one; numpy arrays in the reference's numbering."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, parent=None):
         self._h = C.c_void_p()
-        st = lib().pnp_ctx_create(device, C.byref(self._h))
+        self._children = []
+        if parent is not None:
+            st = lib().pnp_ctx_create_child(parent._h, C.byref(self._h))
+            parent._children.append(self)
+        else:
+            st = lib().pnp_ctx_create(device, C.byref(self._h))
         if st != 0:
             raise PnpError(st, "cannot create a context on CUDA device %d (no CPU fallback exists)" % device)
 
@@ -192,6 +197,14 @@ class Context:
         nbr = np.ascontiguousarray(nbr, dtype=np.int32); send_ptr = np.ascontiguousarray(send_ptr, dtype=np.int32)
         send_idx = np.ascontiguousarray(send_idx, dtype=np.int32); recv_ptr = np.ascontiguousarray(recv_ptr, dtype=np.int32)
         self._ck(lib().pnp_halo_set(self._h, len(nbr), _i(nbr), _i(send_ptr), _i(send_idx), _i(recv_ptr)))
+
+    def mg_push_level(self, child, par0, par1):
+        par0 = np.ascontiguousarray(par0, dtype=np.int32); par1 = np.ascontiguousarray(par1, dtype=np.int32)
+        self._ck(lib().pnp_mg_push_level(self._h, child._h, _i(par0), _i(par1)))
+
+    def mg_set_coarse_global(self, gid, n_global):
+        gid = np.ascontiguousarray(gid, dtype=np.int32)
+        self._ck(lib().pnp_mg_set_coarse_global(self._h, _i(gid), C.c_long(n_global)))
 
     def halo_exchange(self, vec):
         self._ck(lib().pnp_halo_exchange(self._h, vec))

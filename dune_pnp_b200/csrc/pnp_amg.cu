@@ -43,6 +43,10 @@ struct Level {
   DBuf<int> seg_ptr, seg_items;      // coarse slot -> fine slots summed into it (Galerkin P^T A P)
   DBuf<unsigned char> seg_w;         // weight code of each item: 0 -> 1, 1 -> 1/2, 2 -> 1/4 (empty: all 1)
   double alpha = 1.0;                // scaling of the coarse correction coming up from the next level
+  // distributed geometric level: the context that owns this level's mesh part (halo plan, Dirichlet mask); coarse
+  // levels are re-discretised on it from the injected state u
+  Ctx* lc = nullptr;
+  Vec u; Matrix Amat;
 };
 
 } // namespace
@@ -64,6 +68,8 @@ struct Amg {
   DBuf<double> dense, dense_work;
   DBuf<int> dense_piv, dense_info;
   ~Amg() { if (cus) cusolverDnDestroy(cus); }
+  bool distributed = false; // levels are parts of a mesh hierarchy spread over the ranks (halo exchange per level)
+  DBuf<double> grhs;        // replicated coarsest level: global right-hand side / solution
   int n_geo = 0;          // number of geometric (P1) transfers at the top of the hierarchy
   std::vector<std::unique_ptr<Level>> L;
   DBuf<unsigned char> tmp;
@@ -320,12 +326,64 @@ __global__ void k_geo_parents(const int* __restrict__ int2ext_f, int nvf, int nv
   }
 }
 // (parent, child) pairs for the restriction lists: 2 per fine vertex, unused ones get key INT_MAX
-__global__ void k_geo_pairs(const int* __restrict__ par0, const int* __restrict__ par1, int nvf, int* __restrict__ key,
-                            int* __restrict__ val) {
+__global__ void k_geo_pairs(const int* __restrict__ par0, const int* __restrict__ par1, int nvf, int nrows_c,
+                            int* __restrict__ key, int* __restrict__ val) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvf; i += gridDim.x * blockDim.x) {
-    key[2 * i] = par0[i]; val[2 * i] = i;
-    key[2 * i + 1] = par1[i] >= 0 ? par1[i] : 0x7fffffff; val[2 * i + 1] = i;
+    key[2 * i] = (par0[i] >= 0 && par0[i] < nrows_c) ? par0[i] : 0x7fffffff; val[2 * i] = i;     // rows of owned coarse vertices only
+    key[2 * i + 1] = (par1[i] >= 0 && par1[i] < nrows_c) ? par1[i] : 0x7fffffff; val[2 * i + 1] = i;
   }
+}
+// injection of the state: a coarse vertex takes the value of the fine vertex it coincides with
+template <int F>
+__global__ void k_inject(const int* __restrict__ par0, const int* __restrict__ par1, int nvf, const double* __restrict__ uf,
+                         double* __restrict__ uc) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvf; i += gridDim.x * blockDim.x)
+    if (par1[i] < 0 && par0[i] >= 0) {
+#pragma unroll
+      for (int k = 0; k < F; k++) uc[(long)F * par0[i] + k] = uf[(long)F * i + k];
+    }
+}
+template <int F>
+__global__ void k_mask_dirichlet(double* __restrict__ b, const unsigned char* __restrict__ dmask, int nv, int comp0) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    const unsigned m = F == 3 ? dmask[v] : (dmask[v] >> comp0) & 1u;
+#pragma unroll
+    for (int k = 0; k < F; k++) if ((m >> k) & 1u) b[(long)F * v + k] = 0.0;
+  }
+}
+// replicated coarsest level: dense matrix / vectors in GLOBAL dof numbering
+template <int NP>
+__global__ void k_dense_fill_global(const int* __restrict__ rp, const unsigned* __restrict__ col, const double* __restrict__ vals,
+                                    long stride, int nrows, const int* __restrict__ gid, double* __restrict__ Ad, long n) {
+  constexpr int F = NP == 1 ? 1 : 3;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const long rg = gid[r];
+    for (int s = rp[r]; s < rp[r + 1]; s++) {
+      const long cg = gid[col[s] & STAR_VMASK];
+      if (NP == 1) Ad[cg * n + rg] = vals[s];
+      else {
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+          for (int kj = 0; kj < 3; kj++) {
+            const int pl = pnp_plane(ki, kj);
+            if (pl >= 0) Ad[(F * cg + kj) * n + F * rg + ki] = vals[pl * stride + s];
+          }
+      }
+    }
+  }
+}
+template <int F>
+__global__ void k_to_global(const double* __restrict__ loc, const int* __restrict__ gid, int nrows, double* __restrict__ glob) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nrows; v += gridDim.x * blockDim.x)
+#pragma unroll
+    for (int k = 0; k < F; k++) glob[(long)F * gid[v] + k] = loc[(long)F * v + k];
+}
+template <int F>
+__global__ void k_from_global(const double* __restrict__ glob, const int* __restrict__ gid, int nloc, double* __restrict__ loc) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nloc; v += gridDim.x * blockDim.x)
+#pragma unroll
+    for (int k = 0; k < F; k++) loc[(long)F * v + k] = glob[(long)F * gid[v] + k];
 }
 __device__ __forceinline__ int find_slot(const int* rp, const unsigned* col, int I, int J) {
   for (int s = rp[I]; s < rp[I + 1]; s++) if ((int)(col[s] & STAR_VMASK) == J) return s;
@@ -371,6 +429,7 @@ void level_op(Ctx& c, const Amg& A, const Level& l, const double* x, const doubl
   StarOpArgs a{l.rp, l.col, l.vals, l.nslots, l.nv, x, y};
   a.b = b; a.dinv = l.dinv.p; a.block = A.NP == 7; a.omega = omega_or_c2 < 0 ? A.omega : omega_or_c2; a.c1 = c1; a.dvec = dvec;
   const bool fine = &l == A.L[0].get();
+  if (A.distributed) halo_exchange(*l.lc, const_cast<double*>(x), A.F); // ghost columns of the iterate
   if (fine) c.prof_mark(EPI == EPI_RESIDUAL ? 1 : 2);
   launch_star_op<EPI, 0>(c, A.NP, a);
   if (fine) c.prof_mark();
@@ -465,7 +524,7 @@ void coarsen_geometric(Ctx& c, Amg& A, int li, const HierLevel& h, const int* in
   KL(c, k_geo_parents, nvf, int2ext_f, nvf, nvc, h.edges.p, h.ext2int.p, f.agg.p, f.par1.p);
   { // restriction lists
     DBuf<int> key(2 * (size_t)nvf), val(2 * (size_t)nvf), skey(2 * (size_t)nvf), sval(2 * (size_t)nvf);
-    KL(c, k_geo_pairs, nvf, f.agg.p, f.par1.p, nvf, key.p, val.p);
+    KL(c, k_geo_pairs, nvf, f.agg.p, f.par1.p, nvf, nvc, key.p, val.p);
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.p, skey.p, val.p, sval.p, 2 * nvf, 0, 32, c.stream);
     PNP_CUDA(cub::DeviceRadixSort::SortPairs(A.temp(bytes), bytes, key.p, skey.p, val.p, sval.p, 2 * nvf, 0, 32, c.stream));
     f.agg_ptr.alloc((size_t)nvc + 1);
@@ -508,14 +567,74 @@ void coarsen_geometric(Ctx& c, Amg& A, int li, const HierLevel& h, const int* in
   A.L.push_back(std::move(nl));
 }
 
-void alloc_work(Amg& A, Level& l) {
-  const size_t n = (size_t)A.F * l.nv;
-  l.dinv.alloc(A.NP == 7 ? 9 * (size_t)l.nv : n); l.x.alloc(n); l.x2.alloc(n); l.b.alloc(n); l.r.alloc(n);
+void alloc_work(Ctx& c, Amg& A, Level& l) {
+  const size_t n = (size_t)A.F * l.nv, nall = (A.distributed && l.lc) ? (size_t)A.F * l.lc->nv : n;
+  l.dinv.alloc(A.NP == 7 ? 9 * (size_t)l.nv : n); l.x.alloc(nall); l.x2.alloc(nall); l.b.alloc(nall); l.r.alloc(nall);
+  l.x.zero(c.stream); l.x2.zero(c.stream); l.b.zero(c.stream); l.r.zero(c.stream);
+}
+
+// distributed hierarchy: level li+1 lives on the child context `ref.lc`; transfers from the registered parent arrays
+void coarsen_distributed(Ctx& c, Amg& A, int li, MgLevelRef& ref) {
+  Level& f = *A.L[li];
+  Ctx& fc = *f.lc; Ctx& kc = *ref.lc;
+  const int nvf_all = (int)fc.nv, nvc = (int)kc.n_own;
+  size_t bytes = 0;
+  f.agg.alloc(nvf_all); f.par1.alloc(nvf_all);
+  PNP_CUDA(cudaMemcpyAsync(f.agg.p, ref.par0.p, nvf_all * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+  PNP_CUDA(cudaMemcpyAsync(f.par1.p, ref.par1.p, nvf_all * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+  {
+    DBuf<int> key(2 * (size_t)nvf_all), val(2 * (size_t)nvf_all), skey(2 * (size_t)nvf_all), sval(2 * (size_t)nvf_all);
+    KL(c, k_geo_pairs, nvf_all, f.agg.p, f.par1.p, nvf_all, nvc, key.p, val.p);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.p, skey.p, val.p, sval.p, 2 * nvf_all, 0, 32, c.stream);
+    PNP_CUDA(cub::DeviceRadixSort::SortPairs(A.temp(bytes), bytes, key.p, skey.p, val.p, sval.p, 2 * nvf_all, 0, 32, c.stream));
+    f.agg_ptr.alloc((size_t)nvc + 1);
+    KL(c, k_lower_bounds_i32, nvc + 1, skey.p, 2 * nvf_all, nvc, f.agg_ptr.p);
+    int nvalid = 0;
+    PNP_CUDA(cudaMemcpyAsync(&nvalid, f.agg_ptr.p + nvc, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PNP_CUDA(cudaStreamSynchronize(c.stream));
+    f.agg_mem.alloc(nvalid);
+    PNP_CUDA(cudaMemcpyAsync(f.agg_mem.p, sval.p, (size_t)nvalid * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+    PNP_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  f.alpha = 1.0;
+  auto nl = std::make_unique<Level>();
+  nl->lc = &kc; nl->nv = nvc; nl->nslots = kc.nslots; nl->rp = kc.rp.p; nl->col = kc.adj.p;
+  nl->u.fields = A.F; nl->u.d.alloc((size_t)A.F * kc.nv); nl->u.d.zero(c.stream);
+  nl->Amat.op = A.NP == 7 ? OP_PNP : OP_PB; nl->Amat.nplanes = A.NP;
+  nl->Amat.vals.alloc((size_t)A.NP * kc.nslots);
+  nl->vals = nl->Amat.vals.p;
+  A.L.push_back(std::move(nl));
 }
 
 void dense_factor(Ctx& c, Amg& A);
 
+void dense_factor_global(Ctx& c, Amg& A);
+
 void numeric(Ctx& c, Amg& A, int comp0) {
+  if (A.distributed) {
+    // re-discretise every coarser level at the injected state (what assemble_jacobian last linearised on the fine level)
+    PNP_REQUIRE(c.last_u, PNP_E_ARG, "distributed multigrid needs the state of the last Jacobian assembly");
+    const double* uf = c.last_u;
+    for (size_t li = 0; li + 1 < A.L.size(); li++) {
+      Level& l = *A.L[li]; Level& n = *A.L[li + 1];
+      const int nvf_all = (int)l.lc->nv;
+      if (A.F == 1) KL(c, k_inject<1>, nvf_all, l.agg.p, l.par1.p, nvf_all, uf, n.u.d.p);
+      else KL(c, k_inject<3>, nvf_all, l.agg.p, l.par1.p, nvf_all, uf, n.u.d.p);
+      Operator op = c.last_op; op.aux0 = op.aux1 = -1;
+      n.Amat.op = op.op;
+      n.lc->launches = 0;
+      assemble_jacobian(*n.lc, op, n.u, n.Amat, c.last_mode, c.last_eps); // (exchanges the ghost part of u first)
+      c.launches += n.lc->launches;
+      uf = n.u.d.p;
+    }
+    for (size_t li = 0; li < A.L.size(); li++) {
+      Level& l = *A.L[li];
+      if (A.NP == 1) KL(c, k_dinv<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
+      else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
+    }
+    dense_factor_global(c, A);
+    return;
+  }
   for (size_t li = 0; li < A.L.size(); li++) {
     Level& l = *A.L[li];
     if (li + 1 < A.L.size()) {
@@ -602,6 +721,41 @@ void dense_solve(Ctx& c, Amg& A, Level& l) { // l.x = A^-1 l.b
   c.launches += 2;
 }
 
+// coarsest level of the distributed hierarchy: every rank contributes its owned rows, the matrix is summed over the
+// ranks and factorised redundantly; each cycle sums the right-hand side the same way
+void dense_factor_global(Ctx& c, Amg& A) {
+  Level& l = *A.L.back();
+  const long n = (long)A.F * c.mg_nglobal;
+  A.dense_n = (int)n;
+  if (!A.cus) PNP_CUSOLVER(cusolverDnCreate(&A.cus));
+  PNP_CUSOLVER(cusolverDnSetStream(A.cus, c.stream));
+  if (A.dense.n != (size_t)(n * n)) { A.dense.alloc(n * n); A.dense_piv.alloc(n); A.dense_info.alloc(1); A.grhs.alloc(n); }
+  A.dense.zero(c.stream);
+  if (A.NP == 1) KL(c, k_dense_fill_global<1>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, c.mg_gid.p, A.dense.p, n);
+  else KL(c, k_dense_fill_global<7>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, c.mg_gid.p, A.dense.p, n);
+  allreduce_sum(c, A.dense.p, (size_t)(n * n));
+  KL(c, k_dense_fix_diag, n, A.dense.p, n);
+  int lwork = 0;
+  PNP_CUSOLVER(cusolverDnDgetrf_bufferSize(A.cus, (int)n, (int)n, A.dense.p, (int)n, &lwork));
+  if (A.dense_work.n < (size_t)lwork) A.dense_work.alloc(lwork);
+  PNP_CUSOLVER(cusolverDnDgetrf(A.cus, (int)n, (int)n, A.dense.p, (int)n, A.dense_work.p, A.dense_piv.p, A.dense_info.p));
+  int info = 0;
+  A.dense_info.download(&info, 1, c.stream);
+  PNP_REQUIRE(info == 0, PNP_E_BREAKDOWN, "multigrid: coarsest-level matrix is singular (LU info " + std::to_string(info) + ")");
+}
+void dense_solve_global(Ctx& c, Amg& A, Level& l) {
+  const long n = A.dense_n;
+  A.grhs.zero(c.stream);
+  if (A.F == 1) KL(c, k_to_global<1>, l.nv, l.b.p, c.mg_gid.p, l.nv, A.grhs.p);
+  else KL(c, k_to_global<3>, l.nv, l.b.p, c.mg_gid.p, l.nv, A.grhs.p);
+  allreduce_sum(c, A.grhs.p, (size_t)n);
+  PNP_CUSOLVER(cusolverDnDgetrs(A.cus, CUBLAS_OP_N, (int)n, 1, A.dense.p, (int)n, A.dense_piv.p, A.grhs.p, (int)n, A.dense_info.p));
+  const int nloc = (int)l.lc->nv; // owned and ghost vertices: no halo exchange needed afterwards
+  if (A.F == 1) KL(c, k_from_global<1>, nloc, A.grhs.p, c.mg_gid.p, nloc, l.x.p);
+  else KL(c, k_from_global<3>, nloc, A.grhs.p, c.mg_gid.p, nloc, l.x.p);
+  c.launches += 2;
+}
+
 void jacobi0(Ctx& c, Amg& A, Level& l, double omega, double* dvec) {
   if (A.F == 1) KL(c, k_jacobi0<1>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
   else KL(c, k_jacobi0<3>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
@@ -636,16 +790,22 @@ void smooth(Ctx& c, Amg& A, Level& l, int steps, bool zero) {
 void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   Level& l = *A.L[li];
   const bool coarsest = li + 1 == (int)A.L.size();
-  if (coarsest && A.dense_n > 0) { dense_solve(c, A, l); return; }
+  if (coarsest && A.dense_n > 0) { if (A.distributed) dense_solve_global(c, A, l); else dense_solve(c, A, l); return; }
   smooth(c, A, l, coarsest ? A.coarse_sweeps : nu, zero);
   if (coarsest) return;
   Level& nx = *A.L[li + 1];
   level_op<1>(c, A, l, l.x.p, l.b.p, l.r.p);
+  if (A.distributed) halo_exchange(*l.lc, l.r.p, A.F); // children of an owned coarse vertex may be ghosts here
   if (A.F == 1) KL(c, k_restrict<1>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
   else KL(c, k_restrict<3>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
+  if (A.distributed) { // re-discretised coarse levels carry their own Dirichlet rows: no residual into them
+    if (A.F == 1) KL(c, k_mask_dirichlet<1>, nx.nv, nx.b.p, nx.lc->dmask.p, nx.nv, comp0);
+    else KL(c, k_mask_dirichlet<3>, nx.nv, nx.b.p, nx.lc->dmask.p, nx.nv, comp0);
+  }
   const int visits = li < A.wlevels ? A.gamma : 1;
   for (int g = 0; g < visits; g++) cycle(c, A, li + 1, nu, comp0, g == 0);
-  const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
+  if (A.distributed && !(li + 2 == (int)A.L.size() && A.dense_n > 0)) halo_exchange(*nx.lc, nx.x.p, A.F); // parents may be ghosts
+  const unsigned char* dm = A.distributed ? l.lc->dmask.p : (li == 0 ? c.dmask.p : nullptr);
   if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
   else KL(c, k_prolong<3>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
   smooth(c, A, l, nu, false);
@@ -666,9 +826,16 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
     l0->nv = (int)c.n_own; l0->nslots = c.nslots; l0->rp = c.rp.p; l0->col = c.adj.p; l0->vals = M.vals.p;
     A.L.push_back(std::move(l0));
     A.alpha = S.opt("amg_alpha", 1.6);
+    A.L[0]->lc = &c;
+    A.distributed = S.opt("amg_geometric", 1) != 0 && !c.mg.empty() && c.mg_nglobal > 0 &&
+                    (M.op == OP_PB || M.op == OP_PNP || M.op == OP_MASS);
+    if (A.distributed) {
+      for (auto& ref : c.mg) coarsen_distributed(c, A, (int)A.L.size() - 1, ref);
+      A.n_geo = (int)c.mg.size();
+    }
     // geometric levels: every coarser level of the refinement hierarchy (if the mesh was refined in this context)
-    const bool geometric = S.opt("amg_geometric", 1) != 0 && c.n_own == c.nv && !c.hier.empty();
-    A.n_geo = 0;
+    const bool geometric = !A.distributed && S.opt("amg_geometric", 1) != 0 && c.n_own == c.nv && !c.hier.empty();
+    if (!A.distributed) A.n_geo = 0;
     if (geometric) {
       const int* i2e = c.int2ext.p;
       for (int hi = (int)c.hier.size() - 1; hi >= 0; hi--) {
@@ -686,7 +853,7 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
     }
     // algebraic levels below: aggregates from the strength of connection of the current matrix values, level by level
     A.dense_max = (int)S.opt("amg_dense_max", 4096);
-    for (int li = (int)A.L.size() - 1; li < 24; li++) {
+    for (int li = (int)A.L.size() - 1; li < 24 && !A.distributed; li++) {
       if (A.L[li]->nv <= 64 || (long)A.F * A.L[li]->nv <= A.dense_max) break;
       if (!coarsen(c, A, li)) break;
       // numeric values of the new level are needed before it can be coarsened further
@@ -697,8 +864,8 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
       else
         KL(c, k_galerkin<7>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
     }
-    for (auto& l : A.L) alloc_work(A, *l);
-    { // level 0 iterates are SpMV inputs whose ghost columns must read as zero
+    for (auto& l : A.L) alloc_work(c, A, *l);
+    if (!A.distributed) { // level 0 iterates are SpMV inputs whose ghost columns must read as zero
       Level& l0r = *A.L[0];
       const size_t nall = (size_t)A.F * c.nv;
       l0r.x.alloc(nall); l0r.x2.alloc(nall);

@@ -119,6 +119,7 @@ void assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, 
   const double *a0, *a1;
   coefficient_ptrs(c, op, &a0, &a1);
   A.comp0 = op.comp0;
+  c.last_u = u.d.p; c.last_op = op; c.last_mode = mode; c.last_eps = eps;
   halo_exchange(c, u.d.p, u.fields);
   switch (op.op) {
     case OP_PB: launch_jac<OP_PB>(c, op, u.d.p, a0, a1, A, mode, eps); break;

@@ -57,13 +57,55 @@ pnp_status pnp_ctx_create(int device, pnp_ctx** out) {
   *out = h;
   return PNP_OK;
 }
+pnp_status pnp_ctx_create_child(pnp_ctx* parent, pnp_ctx** out) {
+  if (!parent || !out) return PNP_E_ARG;
+  pnp_ctx* h = new pnp_ctx;
+  Ctx& p = parent->c;
+  h->c.device = p.device; h->c.stream = p.stream; h->c.owns_stream = false; h->c.sm_count = p.sm_count;
+  h->c.rank = p.rank; h->c.world = p.world; h->c.nccl = p.nccl;
+  h->c.params = p.params;
+  *out = h;
+  return PNP_OK;
+}
 void pnp_ctx_destroy(pnp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->c.device);
   if (ctx->c.h_red) cudaFreeHost(ctx->c.h_red);
-  cudaStream_t s = ctx->c.stream;
+  cudaStream_t s = ctx->c.owns_stream ? ctx->c.stream : nullptr;
   delete ctx;
   if (s) cudaStreamDestroy(s);
+}
+pnp_status pnp_mg_push_level(pnp_ctx* ctx, pnp_ctx* child, const int* par0, const int* par1) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(child && par0 && par1, PNP_E_ARG, "null arguments");
+  Ctx& f = c.mg.empty() ? c : *c.mg.back().lc;   // the next finer level
+  Ctx& k = child->c;
+  PNP_REQUIRE(f.finalized && k.finalized, PNP_E_ARG, "both levels must be finalized");
+  std::vector<int> fi2e = f.int2ext.to_host(c.stream), ke2i = k.ext2int.to_host(c.stream);
+  std::vector<int> p0(f.nv), p1(f.nv);
+  for (long i = 0; i < f.nv; i++) {
+    const int e = fi2e[i];
+    PNP_REQUIRE(par0[e] < k.nv && par1[e] < k.nv, PNP_E_ARG, "parent index out of range");
+    p0[i] = par0[e] >= 0 ? ke2i[par0[e]] : -1;
+    p1[i] = par1[e] >= 0 ? ke2i[par1[e]] : -1;
+  }
+  MgLevelRef r; r.lc = &k;
+  r.par0.alloc(f.nv); r.par1.alloc(f.nv);
+  r.par0.upload(p0.data(), f.nv, c.stream); r.par1.upload(p1.data(), f.nv, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.mg.push_back(std::move(r));
+  API_END
+}
+pnp_status pnp_mg_set_coarse_global(pnp_ctx* ctx, const int* gid, long n_global) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(!c.mg.empty() && gid && n_global > 0, PNP_E_ARG, "no multigrid level pushed");
+  Ctx& k = *c.mg.back().lc;
+  std::vector<int> i2e = k.int2ext.to_host(c.stream), g(k.nv);
+  for (long i = 0; i < k.nv; i++) { g[i] = gid[i2e[i]]; PNP_REQUIRE(g[i] >= 0 && g[i] < n_global, PNP_E_ARG, "global index out of range"); }
+  c.mg_gid.alloc(k.nv); c.mg_gid.upload(g.data(), k.nv, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.mg_nglobal = n_global;
+  API_END
 }
 pnp_status pnp_profile_spmv(pnp_ctx* ctx, int enable) {
   API_BEGIN(ctx) c.prof = enable != 0; c.prof_used = 0; API_END

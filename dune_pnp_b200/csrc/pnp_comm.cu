@@ -91,7 +91,7 @@ void halo_exchange(Ctx& c, double* x, int F) {
   PNP_NCCL(ncclGroupEnd());
 }
 
-void allreduce_sum(Ctx& c, double* dev, int n) {
+void allreduce_sum(Ctx& c, double* dev, size_t n) {
   if (c.world == 1) return;
   PNP_REQUIRE(c.nccl, PNP_E_ARG, "no communicator (pnp_comm_init)");
   PNP_NCCL(ncclAllReduce(dev, dev, n, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));

@@ -109,6 +109,15 @@ struct HierLevel {
   DBuf<uint64_t> edges; // (min << 32 | max), sorted
 };
 
+struct Ctx;
+// One coarser level of a DISTRIBUTED multigrid hierarchy: a child context holding this rank's part of the coarser mesh
+// (own star, Dirichlet mask, halo plan) and, for every local vertex of the next finer level (internal numbering), its
+// parents on this level (internal numbering, -1: none).
+struct MgLevelRef {
+  Ctx* lc = nullptr;
+  DBuf<int> par0, par1;
+};
+
 struct Amg; // pnp_amg.cu
 
 struct Solver {
@@ -178,6 +187,11 @@ struct Ctx {
   // Newton call costs more than the step itself
   Vec ws_r, ws_z, ws_prev;
   Matrix ws_A;
+  bool owns_stream = true;             // child contexts (coarser multigrid levels) share the parent's stream and communicator
+  std::vector<MgLevelRef> mg;          // distributed multigrid: coarser levels, finest-but-one first
+  DBuf<int> mg_gid; long mg_nglobal = 0; // coarsest level: internal vertex -> global vertex index (replicated dense solve)
+  // what the last assemble_jacobian() call linearised (coarse levels of the distributed multigrid re-discretise it)
+  const double* last_u = nullptr; Operator last_op; int last_mode = 0; double last_eps = 1e-11;
   std::vector<HierLevel> hier;         // coarser refinement levels, coarsest first
   std::vector<Vec> carry;              // nodal fields in reference numbering, interpolated by mesh_refine()
   // a new / refined mesh invalidates every object sized by it
@@ -217,7 +231,7 @@ void comm_unique_id(char* out128);
 void halo_set(Ctx&, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr);
 void halo_finalize(Ctx&);
 void halo_exchange(Ctx&, double* x, int fields);
-void allreduce_sum(Ctx&, double* dev, int n);
+void allreduce_sum(Ctx&, double* dev, size_t n);
 void carry_set(Ctx&, const int* handles, int n);
 void carry_get(Ctx&, int i, Vec& out);
 void vec_upload(Ctx&, Vec&, const double* host_lex);

@@ -46,10 +46,14 @@ class LocalMesh:
     """A rank's piece of the mesh in its own vertex numbering: x, y, tri, tag (owner rank of each triangle), boundary
     segments ba/bb/bphys, carried nodal fields (dict name -> (F, nv) arrays)."""
 
-    def __init__(self, x, y, tri, tag, ba, bb, bphys, fields=None):
+    def __init__(self, x, y, tri, tag, ba, bb, bphys, fields=None, par=None, gid=None):
         self.x, self.y, self.tri, self.tag = x, y, tri.astype(np.int32), tag.astype(np.int32)
         self.ba, self.bb, self.bphys = ba.astype(np.int32), bb.astype(np.int32), bphys.astype(np.int32)
         self.fields = dict(fields or {})
+        # par[v] = (p0, p1): parents of v in the numbering of the LocalMesh this one was refined from (p1 = -1 for a
+        # vertex that coincides with its parent); gid[v] = vertex index in the global mesh (coarsest level only)
+        self.par = par
+        self.gid = gid
 
     @property
     def nv(self):
@@ -67,7 +71,8 @@ class LocalMesh:
         keep_b = (pos < len(keys)) & (keys[np.minimum(pos, len(keys) - 1)] == bk) if len(keys) else np.zeros(len(bk), bool)
         fields = {k: v[:, used] for k, v in self.fields.items()}
         return LocalMesh(self.x[used], self.y[used], new_id[tri], self.tag[keep_tri], new_id[self.ba[keep_b]],
-                         new_id[self.bb[keep_b]], self.bphys[keep_b], fields)
+                         new_id[self.bb[keep_b]], self.bphys[keep_b], fields,
+                         None if self.par is None else self.par[used], None if self.gid is None else self.gid[used])
 
     def trim(self, me):
         """One ghost layer: my triangles + every triangle touching a vertex of one of my triangles."""
@@ -93,14 +98,17 @@ class LocalMesh:
         tri = np.stack([t[:, 0], ab, ac, ab, t[:, 1], bc, ac, bc, t[:, 2], ab, bc, ac], axis=1).reshape(-1, 3)
         m = mid(self.ba, self.bb)
         ba = np.stack([self.ba, m], axis=1).reshape(-1); bb = np.stack([m, self.bb], axis=1).reshape(-1)
-        return LocalMesh(x, y, tri, np.repeat(self.tag, 4), ba, bb, np.repeat(self.bphys, 2), fields)
+        par = np.full((len(x), 2), -1, dtype=np.int64)
+        par[:nv, 0] = np.arange(nv)
+        par[nv:, 0] = a; par[nv:, 1] = b
+        return LocalMesh(x, y, tri, np.repeat(self.tag, 4), ba, bb, np.repeat(self.bphys, 2), fields, par)
 
 
 def extract_local(a, part, me, fields=None):
     """Rank `me`'s local mesh (with one ghost layer) from the global arrays `a` and the triangle partition `part`."""
     f = {k: np.asarray(v, dtype=np.float64).reshape(-1, len(a["x"])) for k, v in (fields or {}).items()}
     lm = LocalMesh(np.asarray(a["x"], float), np.asarray(a["y"], float), np.asarray(a["tri"]), part, np.asarray(a["ba"]),
-                   np.asarray(a["bb"]), np.asarray(a["bphys"]), f)
+                   np.asarray(a["bb"]), np.asarray(a["bphys"]), f, None, np.arange(len(a["x"]), dtype=np.int64))
     return lm.trim(me)
 
 
@@ -182,6 +190,9 @@ def finalize(lm, me, world, all_gather=None):
     p.tag = lm.tag
     p.fields = {k: v[:, order] for k, v in lm.fields.items()}
     p.n_own, p.nv = len(own_ids), nv
+    p.old2new = new_id                                # LocalMesh numbering -> this plan's numbering
+    p.par = None if lm.par is None else lm.par[order]  # parents, still in the coarser LocalMesh's numbering
+    p.gid = None if lm.gid is None else lm.gid[order]
     p.nbr = np.array(nbr, dtype=np.int32); p.send_ptr = np.array(send_ptr, dtype=np.int32)
     p.send_idx = send_idx; p.recv_ptr = np.array(recv_ptr, dtype=np.int32)
     return p
@@ -196,3 +207,55 @@ def build_local(a, nparts, me, levels, fields=None, all_gather=None):
     for _ in range(levels):
         lm = lm.refine().trim(me)
     return finalize(lm, me, nparts, all_gather)
+
+
+def build_hierarchy(a, nparts, me, levels, all_gather=None, fields_at=None):
+    """Distributed multigrid hierarchy: partitions the global mesh `a` (level 0), and returns the list of per-level plans
+    [level 0 (coarsest), ..., level `levels` (finest)].  plan.par (levels >= 1) gives, for every local vertex, its parents
+    in the numbering of the next coarser plan (-1: none).  plan.gid (level 0) are global vertex indices.
+    fields_at = (level, lookup) injects nodal fields at that level: lookup(x, y) -> dict name -> (F, n) arrays; they
+    are P1-interpolated to the finer levels."""
+    tri = np.asarray(a["tri"])
+    cx = np.asarray(a["x"])[tri].mean(1); cy = np.asarray(a["y"])[tri].mean(1)
+    part = rcb_partition(cx, cy, nparts)
+    lm = extract_local(a, part, me)
+    plans = []
+    prev = None
+    n_global = len(a["x"])
+    for l in range(levels + 1):
+        if l > 0:
+            lm = lm.refine().trim(me)
+        if fields_at is not None and fields_at[0] == l:
+            lm.fields = {k: np.asarray(v, dtype=np.float64) for k, v in fields_at[1](lm.x, lm.y).items()}
+        p = finalize(lm, me, nparts, all_gather)
+        if l > 0:
+            par = p.par.copy()
+            ok = par >= 0
+            par[ok] = prev.old2new[par[ok]]
+            p.par = par
+        p.n_global = n_global
+        plans.append(p)
+        prev = p
+    return plans
+
+
+def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id):
+    """Creates the library-side hierarchy from build_hierarchy() plans: `root` gets the finest level, one child context
+    per coarser level; returns the list of child contexts (keep them alive as long as root)."""
+    fine = plans[-1]
+    root.params_read(cfg_path)
+    root.mesh_set_local(fine.n_own, fine.x, fine.y, fine.tri, fine.ba, fine.bb, fine.bphys)
+    root.comm_init(rank, world, unique_id)
+    root.halo_set(fine.nbr, fine.send_ptr, fine.send_idx, fine.recv_ptr)
+    root.mesh_finalize(True)
+    children = []
+    for l in range(len(plans) - 2, -1, -1):
+        p = plans[l]
+        ch = capi.Context(parent=root)
+        ch.mesh_set_local(p.n_own, p.x, p.y, p.tri, p.ba, p.bb, p.bphys)
+        ch.halo_set(p.nbr, p.send_ptr, p.send_idx, p.recv_ptr)
+        ch.mesh_finalize(True)
+        root.mg_push_level(ch, plans[l + 1].par[:, 0], plans[l + 1].par[:, 1])
+        children.append(ch)
+    root.mg_set_coarse_global(plans[0].gid, int(plans[0].n_global))
+    return children

@@ -82,6 +82,14 @@ pnp_status pnp_comm_unique_id(char* out128);                 /* ncclGetUniqueId 
 pnp_status pnp_comm_init(pnp_ctx*, int rank, int world, const char* unique_id128);
 pnp_status pnp_halo_set(pnp_ctx*, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr);
 pnp_status pnp_halo_exchange(pnp_ctx*, int vec_handle);       /* refresh the ghost part of a vector */
+/* distributed geometric multigrid: a child context (same stream and communicator) holds this rank's part of a coarser
+ * mesh level (pnp_mesh_set_local + pnp_halo_set + pnp_mesh_finalize on the child).  pnp_mg_push_level registers it as the
+ * next coarser level: par0/par1[v] = parents of local vertex v of the next finer level (caller's local numbering on both
+ * levels, -1: none; one parent: coinciding vertex, two: midpoint of a coarse edge).  Coarse operators are re-discretised
+ * on the child meshes; the coarsest level is gathered by its global vertex indices and solved redundantly by dense LU. */
+pnp_status pnp_ctx_create_child(pnp_ctx* parent, pnp_ctx** child);
+pnp_status pnp_mg_push_level(pnp_ctx*, pnp_ctx* child, const int* par0, const int* par1);
+pnp_status pnp_mg_set_coarse_global(pnp_ctx*, const int* global_vertex_index, long n_global);
 /* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
 pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
 /* nested iteration: pnp_carry_set() stores vectors in reference numbering; every later pnp_mesh_refine() level

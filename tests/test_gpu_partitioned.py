@@ -103,3 +103,27 @@ def test_partitioned_local_amg_solves_owned_block():
     res = c.solve(s, A, z, rhs, 1e-10)
     assert res.converged and res.iterations < 60
     assert np.all(c.download(z, 1)[plan.n_own:] == 0.0)  # ghost part untouched
+
+
+@pytest.mark.parametrize("op_name,F", [("OP_PB", 1), ("OP_PNP", 3)])
+def test_distributed_multigrid_on_one_rank(op_name, F):
+    """The distributed geometric multigrid (child contexts per level, re-discretised coarse operators, dense coarsest
+    solve by global index) with a single subdomain: everything but NCCL runs."""
+    from dune_pnp_b200 import capi, partition
+    a = util.load_mesh_arrays("pore")
+    plans = partition.build_hierarchy(a, 1, 0, 2)
+    root = capi.Context(0)
+    children = partition.setup_distributed(capi, root, plans, util.cfg_path("pore"), 0, 1, None)
+    assert len(children) == 2
+    op = getattr(capi, op_name)
+    h = root.operator(op, 0)
+    nv = root.mesh_sizes()["nv"]
+    u = root.vec(F); root.vec_set(u, 0.05)
+    A = root.matrix(h)
+    root.jacobian(h, u, A, capi.JAC_ANALYTIC, 0.0)
+    b = np.random.RandomState(0).uniform(-1, 1, F * nv)
+    b[root.constraints(h, F)] = 0.0
+    s = root.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 200, 2)
+    z, r = root.vec(F), root.vec(F, b)
+    res = root.solve(s, A, z, r, 1e-8)
+    assert res.converged and res.iterations <= 12

@@ -95,6 +95,25 @@ def _worker(rank, world, port, levels, q):
             g = loc2glob[:plan.n_own]
             err = np.abs(r_loc - r_glob.reshape(F, -1)[:, g])
             assert np.all(err <= 1e-12 * ab.reshape(F, -1)[:, g] + 1e-300), "owned residual rows differ from the global ones"
+        # (e) distributed multigrid hierarchy: parents of every local vertex exist on the next coarser local level
+        plans = partition.build_hierarchy(a, world, rank, levels, all_gather=all_gather)
+        assert plans[-1].n_own == plan.n_own and np.array_equal(plans[-1].x, plan.x)
+        assert np.array_equal(np.asarray(a["x"])[plans[0].gid], plans[0].x)
+        for l in range(1, len(plans)):
+            f, cz = plans[l], plans[l - 1]
+            p0, p1 = f.par[:, 0], f.par[:, 1]
+            assert p0.min() >= 0 and p0.max() < cz.nv and p1.max() < cz.nv
+            one = p1 < 0
+            assert np.array_equal(f.x[one], cz.x[p0[one]]) and np.array_equal(f.y[one], cz.y[p0[one]])
+            assert np.array_equal(f.x[~one], 0.5 * (cz.x[np.minimum(p0, p1)[~one]] + cz.x[np.maximum(p0, p1)[~one]]))
+            # same owner on every level: an owned coarse vertex is the parent of its (owned) coincident fine vertex ...
+            coinc = np.where(one)[0]
+            assert np.array_equal(coinc < f.n_own, p0[coinc] < cz.n_own)
+            # ... and all children of an owned coarse vertex are present: weights of P^T restricted to owned rows sum up
+            w = np.zeros(cz.nv); np.add.at(w, p0, np.where(one, 1.0, 0.5)); np.add.at(w, p1[~one], 0.5)
+            tw = torch.tensor([w[:cz.n_own].sum()], dtype=torch.float64); dist.all_reduce(tw)
+            nf = torch.tensor([float(f.n_own)], dtype=torch.float64); dist.all_reduce(nf)
+            assert abs(tw.item() - nf.item()) < 1e-9, "restriction weights do not add up to the number of fine vertices"
         q.put((rank, "ok", plan.n_own, plan.nv))
     except Exception as e:  # pragma: no cover
         import traceback
