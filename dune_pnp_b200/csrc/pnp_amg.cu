@@ -16,7 +16,9 @@
 #include <cub/cub.cuh>
 #include <cusolverDn.h>
 
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "pnp_common.cuh"
@@ -354,20 +356,23 @@ __global__ void k_mask_dirichlet(double* __restrict__ b, const unsigned char* __
 // replicated coarsest level: dense matrix / vectors in GLOBAL dof numbering
 template <int NP>
 __global__ void k_dense_fill_global(const int* __restrict__ rp, const unsigned* __restrict__ col, const double* __restrict__ vals,
-                                    long stride, int nrows, const int* __restrict__ gid, double* __restrict__ Ad, long n) {
+                                    long stride, int nrows, const int* __restrict__ gid, double* __restrict__ Ad, long n,
+                                    const unsigned char* __restrict__ dmask, int comp0) {
   constexpr int F = NP == 1 ? 1 : 3;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
     const long rg = gid[r];
     for (int s = rp[r]; s < rp[r + 1]; s++) {
       const long cg = gid[col[s] & STAR_VMASK];
-      if (NP == 1) Ad[cg * n + rg] = vals[s];
+      // (aggregated coarse system: several entries land on one dense entry; unit diagonals of constrained dofs stay out)
+      const unsigned dm = (dmask && s == rp[r]) ? dmask[r] : 0u;
+      if (NP == 1) { if (!((dm >> comp0) & 1u)) atomicAdd(&Ad[cg * n + rg], vals[s]); }
       else {
 #pragma unroll
         for (int ki = 0; ki < 3; ki++)
 #pragma unroll
           for (int kj = 0; kj < 3; kj++) {
             const int pl = pnp_plane(ki, kj);
-            if (pl >= 0) Ad[(F * cg + kj) * n + F * rg + ki] = vals[pl * stride + s];
+            if (pl >= 0 && !(ki == kj && ((dm >> ki) & 1u))) atomicAdd(&Ad[(F * cg + kj) * n + F * rg + ki], vals[pl * stride + s]);
           }
       }
     }
@@ -377,7 +382,17 @@ template <int F>
 __global__ void k_to_global(const double* __restrict__ loc, const int* __restrict__ gid, int nrows, double* __restrict__ glob) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nrows; v += gridDim.x * blockDim.x)
 #pragma unroll
-    for (int k = 0; k < F; k++) glob[(long)F * gid[v] + k] = loc[(long)F * v + k];
+    for (int k = 0; k < F; k++) atomicAdd(&glob[(long)F * gid[v] + k], loc[(long)F * v + k]);
+}
+// x += alpha * (aggregate value), constrained dofs excepted
+template <int F>
+__global__ void k_add_from_global(const double* __restrict__ glob, const int* __restrict__ gid, int nrows, double alpha,
+                                  double* __restrict__ x, const unsigned char* __restrict__ dmask, int comp0) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nrows; v += gridDim.x * blockDim.x) {
+    const unsigned m = F == 3 ? dmask[v] : (dmask[v] >> comp0) & 1u;
+#pragma unroll
+    for (int k = 0; k < F; k++) if (!((m >> k) & 1u)) x[(long)F * v + k] += alpha * glob[(long)F * gid[v] + k];
+  }
 }
 template <int F>
 __global__ void k_from_global(const double* __restrict__ glob, const int* __restrict__ gid, int nloc, double* __restrict__ loc) {
@@ -731,17 +746,36 @@ void dense_factor_global(Ctx& c, Amg& A) {
   PNP_CUSOLVER(cusolverDnSetStream(A.cus, c.stream));
   if (A.dense.n != (size_t)(n * n)) { A.dense.alloc(n * n); A.dense_piv.alloc(n); A.dense_info.alloc(1); A.grhs.alloc(n); }
   A.dense.zero(c.stream);
-  if (A.NP == 1) KL(c, k_dense_fill_global<1>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, c.mg_gid.p, A.dense.p, n);
-  else KL(c, k_dense_fill_global<7>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, c.mg_gid.p, A.dense.p, n);
+  const unsigned char* dm = c.mg_aggregated ? l.lc->dmask.p : nullptr;
+  if (A.NP == 1) KL(c, k_dense_fill_global<1>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, c.mg_gid.p, A.dense.p, n, dm, A.comp0);
+  else KL(c, k_dense_fill_global<7>, l.nv, l.rp, l.col, l.vals, l.nslots, l.nv, c.mg_gid.p, A.dense.p, n, dm, A.comp0);
   allreduce_sum(c, A.dense.p, (size_t)(n * n));
   KL(c, k_dense_fix_diag, n, A.dense.p, n);
   int lwork = 0;
   PNP_CUSOLVER(cusolverDnDgetrf_bufferSize(A.cus, (int)n, (int)n, A.dense.p, (int)n, &lwork));
   if (A.dense_work.n < (size_t)lwork) A.dense_work.alloc(lwork);
+  static const bool timing = std::getenv("PNP_AMG_TIMING") != nullptr;
+  if (timing) PNP_CUDA(cudaStreamSynchronize(c.stream));
+  const auto t0 = std::chrono::steady_clock::now();
   PNP_CUSOLVER(cusolverDnDgetrf(A.cus, (int)n, (int)n, A.dense.p, (int)n, A.dense_work.p, A.dense_piv.p, A.dense_info.p));
   int info = 0;
   A.dense_info.download(&info, 1, c.stream);
+  if (timing) std::printf("[amg] rank %d global dense LU n = %ld: %.1f ms\n", c.rank, n,
+                          1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   PNP_REQUIRE(info == 0, PNP_E_BREAKDOWN, "multigrid: coarsest-level matrix is singular (LU info " + std::to_string(info) + ")");
+}
+// aggregated variant: the coarsest distributed level was smoothed; its residual (l.r) is summed per aggregate over all
+// ranks, the dense aggregate system is solved redundantly and the correction is added back (piecewise constant)
+void dense_correct_aggregated(Ctx& c, Amg& A, Level& l) {
+  const long n = A.dense_n;
+  A.grhs.zero(c.stream);
+  if (A.F == 1) KL(c, k_to_global<1>, l.nv, l.r.p, c.mg_gid.p, l.nv, A.grhs.p);
+  else KL(c, k_to_global<3>, l.nv, l.r.p, c.mg_gid.p, l.nv, A.grhs.p);
+  allreduce_sum(c, A.grhs.p, (size_t)n);
+  PNP_CUSOLVER(cusolverDnDgetrs(A.cus, CUBLAS_OP_N, (int)n, 1, A.dense.p, (int)n, A.dense_piv.p, A.grhs.p, (int)n, A.dense_info.p));
+  if (A.F == 1) KL(c, k_add_from_global<1>, l.nv, A.grhs.p, c.mg_gid.p, l.nv, A.alpha, l.x.p, l.lc->dmask.p, A.comp0);
+  else KL(c, k_add_from_global<3>, l.nv, A.grhs.p, c.mg_gid.p, l.nv, A.alpha, l.x.p, l.lc->dmask.p, A.comp0);
+  c.launches += 2;
 }
 void dense_solve_global(Ctx& c, Amg& A, Level& l) {
   const long n = A.dense_n;
@@ -790,6 +824,13 @@ void smooth(Ctx& c, Amg& A, Level& l, int steps, bool zero) {
 void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   Level& l = *A.L[li];
   const bool coarsest = li + 1 == (int)A.L.size();
+  if (coarsest && A.dense_n > 0 && A.distributed && c.mg_aggregated) { // smoothed level on top of the replicated aggregate solve
+    smooth(c, A, l, nu, zero);
+    level_op<1>(c, A, l, l.x.p, l.b.p, l.r.p);
+    dense_correct_aggregated(c, A, l);
+    smooth(c, A, l, nu, false);
+    return;
+  }
   if (coarsest && A.dense_n > 0) { if (A.distributed) dense_solve_global(c, A, l); else dense_solve(c, A, l); return; }
   smooth(c, A, l, coarsest ? A.coarse_sweeps : nu, zero);
   if (coarsest) return;
@@ -804,7 +845,7 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   }
   const int visits = li < A.wlevels ? A.gamma : 1;
   for (int g = 0; g < visits; g++) cycle(c, A, li + 1, nu, comp0, g == 0);
-  if (A.distributed && !(li + 2 == (int)A.L.size() && A.dense_n > 0)) halo_exchange(*nx.lc, nx.x.p, A.F); // parents may be ghosts
+  if (A.distributed && !(li + 2 == (int)A.L.size() && A.dense_n > 0 && !c.mg_aggregated)) halo_exchange(*nx.lc, nx.x.p, A.F); // parents may be ghosts
   const unsigned char* dm = A.distributed ? l.lc->dmask.p : (li == 0 ? c.dmask.p : nullptr);
   if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
   else KL(c, k_prolong<3>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
@@ -879,10 +920,19 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
     }
   }
   A.L[0]->vals = M.vals.p;
+  static const bool timing = std::getenv("PNP_AMG_TIMING") != nullptr;
+  if (timing) PNP_CUDA(cudaStreamSynchronize(c.stream));
+  const auto t_num0 = std::chrono::steady_clock::now();
   A.omega = S.opt("amg_omega", 0.7); A.gamma = (int)S.opt("amg_gamma", 1); A.wlevels = (int)S.opt("amg_wlevels", 99);
   A.coarse_sweeps = (int)S.opt("amg_coarse_sweeps", 40); A.smoother = (int)S.opt("amg_smoother", 0);
   A.cheb_ratio = S.opt("amg_cheb_ratio", 8.0);
   numeric(c, A, comp0);
+  if (timing) {
+    PNP_CUDA(cudaStreamSynchronize(c.stream));
+    std::printf("[amg] rank %d numeric setup %.1f ms (levels %zu, dense n = %d, distributed %d)\n", c.rank,
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_num0).count(), A.L.size(), A.dense_n,
+                (int)A.distributed);
+  }
 }
 
 // y = M^{-1} d : `prec_steps` pre- and post-smoothing sweeps per level

@@ -96,8 +96,14 @@ pnp_status pnp_mg_push_level(pnp_ctx* ctx, pnp_ctx* child, const int* par0, cons
   c.mg.push_back(std::move(r));
   API_END
 }
+pnp_status pnp_mg_set_coarse_aggregates(pnp_ctx* ctx, const int* agg, long n_aggregates) {
+  const pnp_status st = pnp_mg_set_coarse_global(ctx, agg, n_aggregates);
+  if (st == PNP_OK) ctx->c.mg_aggregated = true;
+  return st;
+}
 pnp_status pnp_mg_set_coarse_global(pnp_ctx* ctx, const int* gid, long n_global) {
   API_BEGIN(ctx)
+  c.mg_aggregated = false;
   PNP_REQUIRE(!c.mg.empty() && gid && n_global > 0, PNP_E_ARG, "no multigrid level pushed");
   Ctx& k = *c.mg.back().lc;
   std::vector<int> i2e = k.int2ext.to_host(c.stream), g(k.nv);

@@ -189,7 +189,10 @@ struct Ctx {
   Matrix ws_A;
   bool owns_stream = true;             // child contexts (coarser multigrid levels) share the parent's stream and communicator
   std::vector<MgLevelRef> mg;          // distributed multigrid: coarser levels, finest-but-one first
-  DBuf<int> mg_gid; long mg_nglobal = 0; // coarsest level: internal vertex -> global vertex index (replicated dense solve)
+  // coarsest distributed level: internal vertex -> index in the replicated dense system.  mg_aggregated = false: that
+  // index is the global vertex (the level itself is solved densely); true: it is an aggregate of global vertices (the
+  // level is smoothed like the others and the Galerkin aggregate system below it is the dense one)
+  DBuf<int> mg_gid; long mg_nglobal = 0; bool mg_aggregated = false;
   // what the last assemble_jacobian() call linearised (coarse levels of the distributed multigrid re-discretise it)
   const double* last_u = nullptr; Operator last_op; int last_mode = 0; double last_eps = 1e-11;
   std::vector<HierLevel> hier;         // coarser refinement levels, coarsest first

@@ -239,9 +239,11 @@ def build_hierarchy(a, nparts, me, levels, all_gather=None, fields_at=None):
     return plans
 
 
-def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id):
+def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggregates=None):
     """Creates the library-side hierarchy from build_hierarchy() plans: `root` gets the finest level, one child context
-    per coarser level; returns the list of child contexts (keep them alive as long as root)."""
+    per coarser level; returns the list of child contexts (keep them alive as long as root).  aggregates = (agg, n_agg) from
+    aggregate_greedy() on the global coarsest mesh: the coarsest level is then smoothed and its aggregate system is the
+    replicated dense solve (cheap LU); None: the coarsest level itself is solved densely."""
     fine = plans[-1]
     root.params_read(cfg_path)
     root.mesh_set_local(fine.n_own, fine.x, fine.y, fine.tri, fine.ba, fine.bb, fine.bphys)
@@ -257,5 +259,43 @@ def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id):
         ch.mesh_finalize(True)
         root.mg_push_level(ch, plans[l + 1].par[:, 0], plans[l + 1].par[:, 1])
         children.append(ch)
-    root.mg_set_coarse_global(plans[0].gid, int(plans[0].n_global))
+    if aggregates is None:
+        root.mg_set_coarse_global(plans[0].gid, int(plans[0].n_global))
+    else:
+        agg, n_agg = aggregates
+        root.mg_set_coarse_aggregates(np.asarray(agg)[plans[0].gid], int(n_agg))
     return children
+
+
+def aggregate_greedy(nv, tri, leftovers_join=True):
+    """Deterministic greedy aggregation of the (global, coarsest) mesh graph: a vertex whose neighbourhood is still free
+    becomes the root of an aggregate with all its neighbours; leftovers join an adjacent aggregate."""
+    tri = np.asarray(tri, dtype=np.int64)
+    e = np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [0, 2]]])
+    e = np.unique(np.concatenate([e, e[:, ::-1]]), axis=0)
+    ptr = np.searchsorted(e[:, 0], np.arange(nv + 1))
+    nbr = e[:, 1]
+    agg = np.full(nv, -1, dtype=np.int64)
+    n_agg = 0
+    for v in range(nv):
+        nb = nbr[ptr[v]:ptr[v + 1]]
+        if agg[v] < 0 and np.all(agg[nb] < 0):
+            agg[v] = n_agg; agg[nb] = n_agg; n_agg += 1
+    if not leftovers_join:  # leftovers first form aggregates among themselves (keeps the aggregates small)
+        for v in range(nv):
+            if agg[v] < 0:
+                nb = nbr[ptr[v]:ptr[v + 1]]
+                free = nb[agg[nb] < 0]
+                if len(free) >= 2:
+                    agg[v] = n_agg; agg[free] = n_agg; n_agg += 1
+    size = np.bincount(agg[agg >= 0], minlength=n_agg)
+    for v in range(nv):
+        if agg[v] < 0:
+            nb = nbr[ptr[v]:ptr[v + 1]]
+            done = nb[agg[nb] >= 0]
+            if len(done):
+                best = done[np.argmin(size[agg[done]])]   # join the smallest adjacent aggregate
+                agg[v] = agg[best]; size[agg[v]] += 1
+            else:
+                agg[v] = n_agg; n_agg += 1; size = np.append(size, 1)
+    return agg.astype(np.int32), n_agg

@@ -90,6 +90,9 @@ pnp_status pnp_halo_exchange(pnp_ctx*, int vec_handle);       /* refresh the gho
 pnp_status pnp_ctx_create_child(pnp_ctx* parent, pnp_ctx** child);
 pnp_status pnp_mg_push_level(pnp_ctx*, pnp_ctx* child, const int* par0, const int* par1);
 pnp_status pnp_mg_set_coarse_global(pnp_ctx*, const int* global_vertex_index, long n_global);
+/* alternative: the coarsest pushed level stays a smoothed level and the dense system is its Galerkin aggregate:
+ * aggregate[v] = aggregate index of local vertex v (the same global aggregation on every rank) */
+pnp_status pnp_mg_set_coarse_aggregates(pnp_ctx*, const int* aggregate, long n_aggregates);
 /* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
 pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
 /* nested iteration: pnp_carry_set() stores vectors in reference numbering; every later pnp_mesh_refine() level
