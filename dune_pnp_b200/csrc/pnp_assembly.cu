@@ -7,10 +7,55 @@
 // the ring (4 B/slot), gathers coordinates and coefficients (L1/L2 hits after the locality
 // renumbering) and writes F residual entries or NPLANES*rowlen matrix values.
 //
-// Compiled with -fmad=false: the FD-faithful path must round like the CPU restatement.
+// This source is compiled TWICE (Makefile): with -DPNP_ASM_FAITHFUL -fmad=false it provides the FD-faithful Jacobian
+// kernels, which must round like the CPU restatement (no FMA contraction, the reference's operation order); without
+// the macro (FMA allowed) it provides the residual and exact-derivative Jacobian kernels plus the host-side dispatch.
 #include "pnp_common.cuh"
 
 namespace pnp {
+
+// implemented in the other compilation of this file
+void launch_jacobian_fd(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps);
+
+namespace {
+
+template <int OP, int MODE>
+__global__ void __launch_bounds__(128)
+k_jacobian(StarView M, PhysParams P, const double* __restrict__ u, const double* __restrict__ aux0,
+           const double* __restrict__ aux1, double eps, int comp0, double* __restrict__ vals, long stride) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < M.nv; v += gridDim.x * blockDim.x)
+    jacobian_row<OP, MODE>(M, P, u, aux0, aux1, eps, comp0, v, vals, stride);
+}
+
+template <int OP, int MODE>
+void launch_jac(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps) {
+  const StarView M = c.star();
+  const PhysParams P = c.phys(op.valency);
+  const int block = 128, grid = grid_for(c.n_own, block, c.sm_count * 16);
+  k_jacobian<OP, MODE><<<grid, block, 0, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, A.vals.p, c.nslots);
+  PNP_CHECK_LAUNCH(); c.launches++;
+}
+template <int MODE>
+void dispatch_jac(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps) {
+  switch (op.op) {
+    case OP_PB: launch_jac<OP_PB, MODE>(c, op, u, a0, a1, A, eps); break;
+    case OP_POISSON: launch_jac<OP_POISSON, MODE>(c, op, u, a0, a1, A, eps); break;
+    case OP_DIFFUSION: launch_jac<OP_DIFFUSION, MODE>(c, op, u, a0, a1, A, eps); break;
+    case OP_MASS: launch_jac<OP_MASS, MODE>(c, op, u, a0, a1, A, eps); break;
+    case OP_PNP: launch_jac<OP_PNP, MODE>(c, op, u, a0, a1, A, eps); break;
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
+  }
+}
+
+} // namespace
+
+#ifdef PNP_ASM_FAITHFUL
+
+void launch_jacobian_fd(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps) {
+  dispatch_jac<JAC_FD_FAITHFUL>(c, op, u, a0, a1, A, eps);
+}
+
+#else
 
 namespace {
 
@@ -21,19 +66,11 @@ k_residual(StarView M, PhysParams P, const double* __restrict__ u, const double*
   constexpr int F = OpTraits<OP>::F;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < M.nv; v += gridDim.x * blockDim.x) {
     double out[F];
-    residual_row<OP>(M, P, u, aux0, aux1, v, out);
+    residual_row<OP, false>(M, P, u, aux0, aux1, v, out);
     const unsigned db = dir_bits<OP>(M, v, comp0);
 #pragma unroll
     for (int k = 0; k < F; k++) r[(long)F * v + k] = ((db >> k) & 1u) ? 0.0 : out[k]; // constrain_residual
   }
-}
-
-template <int OP, int MODE>
-__global__ void __launch_bounds__(128)
-k_jacobian(StarView M, PhysParams P, const double* __restrict__ u, const double* __restrict__ aux0,
-           const double* __restrict__ aux1, double eps, int comp0, double* __restrict__ vals, long stride) {
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < M.nv; v += gridDim.x * blockDim.x)
-    jacobian_row<OP, MODE>(M, P, u, aux0, aux1, eps, comp0, v, vals, stride);
 }
 
 // alpha_boundary: one thread per vertex that occurs in a boundary face (boundary_vertex_sum, pnp_star.cuh)
@@ -54,7 +91,6 @@ __global__ void k_boundary(StarView M, PhysParams P, const BFace* __restrict__ f
 }
 
 } // namespace
-
 static void coefficient_ptrs(Ctx& c, const Operator& op, const double** a0, const double** a1) {
   *a0 = *a1 = nullptr;
   const int need = op.op == OP_POISSON ? 2 : (op.op == OP_DIFFUSION ? 1 : 0);
@@ -98,19 +134,6 @@ void assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
   }
 }
 
-template <int OP>
-static void launch_jac(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A,
-                       int mode, double eps) {
-  const StarView M = c.star();
-  const PhysParams P = c.phys(op.valency);
-  const int block = 128, grid = grid_for(c.n_own, block, c.sm_count * 16);
-  if (mode == JAC_FD_FAITHFUL)
-    k_jacobian<OP, JAC_FD_FAITHFUL><<<grid, block, 0, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, A.vals.p, c.nslots);
-  else
-    k_jacobian<OP, JAC_ANALYTIC><<<grid, block, 0, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, A.vals.p, c.nslots);
-  PNP_CHECK_LAUNCH(); c.launches++;
-}
-
 void assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, double eps) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built (mesh finalized + parameters set?)");
   PNP_REQUIRE(u.fields == op_fields(op.op), PNP_E_ARG, "vector field count does not match the operator");
@@ -121,14 +144,10 @@ void assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, 
   A.comp0 = op.comp0;
   c.last_u = u.d.p; c.last_op = op; c.last_mode = mode; c.last_eps = eps;
   halo_exchange(c, u.d.p, u.fields);
-  switch (op.op) {
-    case OP_PB: launch_jac<OP_PB>(c, op, u.d.p, a0, a1, A, mode, eps); break;
-    case OP_POISSON: launch_jac<OP_POISSON>(c, op, u.d.p, a0, a1, A, mode, eps); break;
-    case OP_DIFFUSION: launch_jac<OP_DIFFUSION>(c, op, u.d.p, a0, a1, A, mode, eps); break;
-    case OP_MASS: launch_jac<OP_MASS>(c, op, u.d.p, a0, a1, A, mode, eps); break;
-    case OP_PNP: launch_jac<OP_PNP>(c, op, u.d.p, a0, a1, A, mode, eps); break;
-    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
-  }
+  if (mode == JAC_FD_FAITHFUL) launch_jacobian_fd(c, op, u.d.p, a0, a1, A, eps);
+  else dispatch_jac<JAC_ANALYTIC>(c, op, u.d.p, a0, a1, A, eps);
 }
+
+#endif // PNP_ASM_FAITHFUL
 
 } // namespace pnp

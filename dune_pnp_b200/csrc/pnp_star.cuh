@@ -85,7 +85,7 @@ PNP_HD void residual_tri(unsigned flags, const VData<OP>& V, const VData<OP>& cu
 }
 
 // Volume part of residual row(s) of vertex v: out[k] = sum over incident elements (ring order).
-template <int OP>
+template <int OP, bool FAITHFUL = false>
 PNP_HD void residual_row(const StarView& M, const PhysParams& P, const double* u, const double* aux0,
                          const double* aux1, int v, double* out) {
   constexpr int F = OpTraits<OP>::F;
@@ -107,7 +107,11 @@ PNP_HD void residual_row(const StarView& M, const PhysParams& P, const double* u
       double rl[F];
 #pragma unroll
       for (int k = 0; k < F; k++) rl[k] = 0.0;
-      residual_tri<OP>(a_cur, V, cur, nxt, P, rl);
+      // FAITHFUL: the element's own vertex order (the reference's operation order, needed by the FD Jacobian);
+      // otherwise the triangle is taken as (v, this neighbour, next neighbour): same integrals (the quadrature rules
+      // are symmetric), no branch on the element-local index, results equal up to rounding
+      if (FAITHFUL) residual_tri<OP>(a_cur, V, cur, nxt, P, rl);
+      else tri_rows<OP, 0>(V, cur, nxt, P, rl);
 #pragma unroll
       for (int k = 0; k < F; k++) out[k] += rl[k];
     }
@@ -188,17 +192,23 @@ PNP_HD void jacobian_row(const StarView& M, const PhysParams& P, const double* u
         for (int j = 0; j < 3; j++)
 #pragma unroll
           for (int p = 0; p < NP; p++) blk[j][p] = 0.0;
-        const int li = (a_cur >> STAR_LI_SHIFT) & 3;
-        const bool cw = a_cur & STAR_CW;
-        const VData<OP>& N = cw ? nxt : cur;
-        const VData<OP>& Pp = cw ? cur : nxt;
-        // local column index of: v -> li, n -> (li+1)%3, p -> (li+2)%3
-        const double *bv, *bn, *bp;
-        if (li == 0) { tri_jac<OP, 0, MODE>(V, N, Pp, P, eps, blk); bv = blk[0]; bn = blk[1]; bp = blk[2]; }
-        else if (li == 1) { tri_jac<OP, 1, MODE>(Pp, V, N, P, eps, blk); bv = blk[1]; bn = blk[2]; bp = blk[0]; }
-        else { tri_jac<OP, 2, MODE>(N, Pp, V, P, eps, blk); bv = blk[2]; bn = blk[0]; bp = blk[1]; }
-        const double* bcur = cw ? bp : bn;
-        const double* bnxt = cw ? bn : bp;
+        const double *bv, *bcur, *bnxt;
+        if (MODE == JAC_ANALYTIC) { // vertex-centric order (v, this neighbour, next neighbour): no branch on li
+          tri_jac<OP, 0, MODE>(V, cur, nxt, P, eps, blk);
+          bv = blk[0]; bcur = blk[1]; bnxt = blk[2];
+        } else {
+          const int li = (a_cur >> STAR_LI_SHIFT) & 3;
+          const bool cw = a_cur & STAR_CW;
+          const VData<OP>& N = cw ? nxt : cur;
+          const VData<OP>& Pp = cw ? cur : nxt;
+          // local column index of: v -> li, n -> (li+1)%3, p -> (li+2)%3
+          const double *bn, *bp;
+          if (li == 0) { tri_jac<OP, 0, MODE>(V, N, Pp, P, eps, blk); bv = blk[0]; bn = blk[1]; bp = blk[2]; }
+          else if (li == 1) { tri_jac<OP, 1, MODE>(Pp, V, N, P, eps, blk); bv = blk[1]; bn = blk[2]; bp = blk[0]; }
+          else { tri_jac<OP, 2, MODE>(N, Pp, V, P, eps, blk); bv = blk[2]; bn = blk[0]; bp = blk[1]; }
+          bcur = cw ? bp : bn;
+          bnxt = cw ? bn : bp;
+        }
 #pragma unroll
         for (int p = 0; p < NP; p++) { diag[p] += bv[p]; val[p] += bcur[p]; carry[p] = bnxt[p]; }
         closed = last;

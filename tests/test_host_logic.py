@@ -58,7 +58,8 @@ def test_residual_rows_match_oracle(name, levels, op):
     r_o, ab = ora.residual(m, p, op, u, a0, a1, valency=-1.0, want_abs=True)
     r = S.residual(op, p.sys, u, a0, a1, valency=-1.0)
     assert np.all(np.abs(r - r_o) <= 1e-12 * ab)
-    assert np.all(np.abs(r - r_o) <= 8 * 2.3e-16 * ab)  # only the summation order over a vertex's elements differs
+    # rounding level: the product takes each triangle as (v, neighbour, next neighbour) and sums over the ring
+    assert np.all(np.abs(r - r_o) <= 64 * 2.3e-16 * ab)
 
 
 @pytest.mark.parametrize("mode", [0, 1])
