@@ -65,10 +65,9 @@ class LocalMesh:
         used = np.zeros(self.nv, dtype=bool)
         used[tri.ravel()] = True
         new_id = np.cumsum(used) - 1
-        keys = np.unique(_edge_keys(tri))
-        bk = (np.minimum(self.ba, self.bb).astype(np.int64) << 32) | np.maximum(self.ba, self.bb).astype(np.int64)
-        pos = np.searchsorted(keys, bk)
-        keep_b = (pos < len(keys)) & (keys[np.minimum(pos, len(keys) - 1)] == bk) if len(keys) else np.zeros(len(bk), bool)
+        # a boundary segment stays if both end vertices stay: if one of them is owned, the segment's triangle touches an
+        # owned vertex and was kept; segments between two far ghosts only contribute Dirichlet flags in the library
+        keep_b = used[self.ba] & used[self.bb]
         fields = {k: v[:, used] for k, v in self.fields.items()}
         return LocalMesh(self.x[used], self.y[used], new_id[tri], self.tag[keep_tri], new_id[self.ba[keep_b]],
                          new_id[self.bb[keep_b]], self.bphys[keep_b], fields,
