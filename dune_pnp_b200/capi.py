@@ -343,6 +343,14 @@ class Context:
     def solver_set_option(self, solver, name, value):
         self._ck(lib().pnp_solver_set_option(self._h, solver, name.encode(), C.c_double(value)))
 
+    def solver_get(self, solver, name):
+        out = C.c_double(0)
+        self._ck(lib().pnp_solver_get(self._h, solver, name.encode(), C.byref(out)))
+        return out.value
+
+    def precond_apply(self, solver, A, d, v):
+        self._ck(lib().pnp_precond_apply(self._h, solver, A, d, v))
+
     def solve(self, solver, A, z, r, reduction):
         res = LinResult()
         self._ck(lib().pnp_solver_apply(self._h, solver, A, z, r, C.c_double(reduction), C.byref(res)))

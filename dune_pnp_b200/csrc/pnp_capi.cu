@@ -415,6 +415,21 @@ pnp_status pnp_solver_set_option(pnp_ctx* ctx, int s, const char* name, double v
   c.solver(s).opts[name] = value;
   API_END
 }
+pnp_status pnp_solver_get(pnp_ctx* ctx, int s, const char* name, double* value) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(name && value, PNP_E_ARG, "null argument");
+  const std::string n(name);
+  if (n == "ssor_levels") *value = sweep_levels(c.solver(s), false);
+  else if (n == "ilu0_levels") *value = sweep_levels(c.solver(s), true);
+  else PNP_REQUIRE(false, PNP_E_ARG, "unknown solver fact");
+  API_END
+}
+pnp_status pnp_precond_apply(pnp_ctx* ctx, int s, int A, int d, int v) {
+  API_BEGIN(ctx)
+  precond_apply(c, c.solver(s), c.mat(A), c.vec(d), c.vec(v));
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
 pnp_status pnp_solver_apply(pnp_ctx* ctx, int s, int A, int z, int r, double reduction, pnp_lin_result* out) {
   API_BEGIN(ctx)
   LinResult lr = solver_apply(c, c.solver(s), c.mat(A), c.vec(z), c.vec(r), reduction);

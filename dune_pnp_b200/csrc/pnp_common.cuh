@@ -119,10 +119,12 @@ struct MgLevelRef {
 };
 
 struct Amg; // pnp_amg.cu
+struct SweepPrec; // pnp_precond.cu: level schedules of the SSOR / ILU0 sweeps, ILU0 factor
 
 struct Solver {
   int kind = PNP_SOLVER_BCGS, prec = PNP_PREC_NONE, maxit = 5000, prec_steps = 1, verbosity = 0;
   std::shared_ptr<Amg> amg;
+  std::shared_ptr<SweepPrec> sweep;
   std::map<std::string, double> opts; // pnp_solver_set_option
   double opt(const char* name, double dflt) const { auto it = opts.find(name); return it == opts.end() ? dflt : it->second; }
   DBuf<double> w[6]; // Krylov work vectors, sized on first use
@@ -258,5 +260,8 @@ void vec_copy(Ctx&, const double* x, double* y, long n);
 void vec_zero(Ctx&, double* x, long n);
 struct LinResult { bool converged = false; int iterations = 0; double reduction = 1, conv_rate = 1; int status = 0; double seconds = 0; };
 LinResult solver_apply(Ctx&, Solver&, const Matrix& A, Vec& z, Vec& r, double reduction);
+void precond_apply(Ctx&, Solver&, const Matrix& A, Vec& d, Vec& v); // v = M^-1 d (setup + one application)
+// pnp_precond.cu
+int sweep_levels(const Solver&, bool ilu);
 
 } // namespace pnp

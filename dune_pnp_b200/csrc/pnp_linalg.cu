@@ -194,6 +194,8 @@ void amg_setup(Ctx&, Solver&, const Matrix&);                        // pnp_amg.
 void amg_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y); // pnp_amg.cu
 void ssor_setup(Ctx&, Solver&, const Matrix&);                       // pnp_precond.cu
 void ssor_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y);
+void ilu0_setup(Ctx&, Solver&, const Matrix&);
+void ilu0_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y);
 
 namespace {
 void prec_setup(Ctx& c, Solver& S, const Matrix& A) {
@@ -207,8 +209,9 @@ void prec_setup(Ctx& c, Solver& S, const Matrix& A) {
       break;
     }
     case PNP_PREC_SSOR: ssor_setup(c, S, A); break;
+    case PNP_PREC_ILU0: ilu0_setup(c, S, A); break;
     case PNP_PREC_AMG: amg_setup(c, S, A); break;
-    default: PNP_REQUIRE(false, PNP_E_ARG, "preconditioner not implemented (ILU0 is planned, see DESIGN.md)");
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown preconditioner");
   }
 }
 // y = M^{-1} d  (ISTL: y = 0; prec.apply(y, d))
@@ -220,6 +223,7 @@ void prec_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double* y, 
       PNP_CHECK_LAUNCH(); c.launches++;
       break;
     case PNP_PREC_SSOR: ssor_apply(c, S, A, d, y); break;
+    case PNP_PREC_ILU0: ilu0_apply(c, S, A, d, y); break;
     case PNP_PREC_AMG: amg_apply(c, S, A, d, y); break;
     default: break;
   }
@@ -326,6 +330,15 @@ LinResult cg(Ctx& c, Solver& S, const Matrix& A, double* x, double* b, long n, d
   return finish(res, S.maxit, def, def0, false, 0);
 }
 } // namespace
+
+void precond_apply(Ctx& c, Solver& S, const Matrix& A, Vec& d, Vec& v) {
+  PNP_REQUIRE(d.fields == v.fields && d.fields == (A.nplanes == 1 ? 1 : 3) && d.d.p != v.d.p, PNP_E_ARG,
+              "vector field count does not match the matrix");
+  S.ensure((size_t)c.nv * d.fields);
+  ensure_red(c);
+  prec_setup(c, S, A);
+  prec_apply(c, S, A, d.d.p, v.d.p, c.n_own * d.fields);
+}
 
 LinResult solver_apply(Ctx& c, Solver& S, const Matrix& A, Vec& z, Vec& r, double reduction) {
   PNP_REQUIRE(z.fields == r.fields && z.fields == (A.nplanes == 1 ? 1 : 3), PNP_E_ARG,

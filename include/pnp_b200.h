@@ -169,6 +169,12 @@ pnp_status pnp_solver_create(pnp_ctx*, int kind, int prec, int maxit, int prec_s
  * the mesh was refined with pnp_mesh_refine, the coarser refinement levels become multigrid levels with P1
  * interpolation and Galerkin operators; aggregation continues below the coarsest mesh) */
 pnp_status pnp_solver_set_option(pnp_ctx*, int solver, const char* name, double value);
+/* read-back of solver facts, by name: "ssor_levels" / "ilu0_levels" (number of levels of the level-scheduled sweep that
+ * reproduces SeqSSOR / SeqILU0 in the reference's row order; 0 before the first use) */
+pnp_status pnp_solver_get(pnp_ctx*, int solver, const char* name, double* value);
+/* one application of the solver's preconditioner, v = M^-1 d, as ISTL's Preconditioner::pre/apply/post on the matrix
+ * (SeqSSOR / SeqILU0 / SeqJac / AMG / Richardson).  d and v are distinct vectors of the matrix' field count. */
+pnp_status pnp_precond_apply(pnp_ctx*, int solver, int mat_handle, int d, int v);
 /* z: initial guess in, solution out; r: right-hand side in, residual out (as ISTL does) */
 pnp_status pnp_solver_apply(pnp_ctx*, int solver, int mat_handle, int z, int r, double reduction, pnp_lin_result*);
 

@@ -15,7 +15,7 @@ _LIB = None
 
 OP_PB, OP_POISSON, OP_DIFFUSION, OP_MASS, OP_PNP = range(5)
 SOLVER_BCGS, SOLVER_CG = 0, 1
-PREC_NONE, PREC_JACOBI, PREC_SSOR = 0, 1, 2
+PREC_NONE, PREC_JACOBI, PREC_SSOR, PREC_ILU0 = 0, 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -177,6 +177,15 @@ def linsolve(rowptr, col, val, b, reduction, maxit, solver=SOLVER_BCGS, prec=PRE
                    status=int(res[4]), seconds=res[5])
 
 
+def prec_apply(rowptr, col, val, d, prec, steps=1):
+    """v = M^-1 d, one application of an ISTL preconditioner (PREC_*)."""
+    n = len(rowptr) - 1
+    v = np.zeros(n); d = _f64(d); val = _f64(val)
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32)
+    _chk(lib().ora_prec_apply(n, _i(rowptr), _i(col), _d(val), prec, steps, _d(d), _d(v)))
+    return v
+
+
 def spmv(rowptr, col, val, x):
     n = len(rowptr) - 1
     y = np.zeros(n); x = _f64(x); val = _f64(val)
@@ -217,3 +226,14 @@ def slp(mesh, params, op, u0, reduction, solver=SOLVER_BCGS, prec=PREC_SSOR, ste
     _chk(lib().ora_slp(mesh.h, params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
                        C.c_double(reduction), solver, prec, steps, maxit, jac_mode, C.c_double(eps), _d(res)))
     return u, dict(converged=bool(res[0]), iterations=int(res[1]), reduction=res[2])
+
+
+def onestep(mesh, params, xold, g, phi, valency, dt, reduction=1e-5, method=0, solver=SOLVER_BCGS, prec=PREC_SSOR, steps=1,
+            maxit=5000, jac_mode=0, eps=1e-11, comp0=1):
+    """OneStepMethod<Alexander2>::apply (method 0; 1: implicit Euler) for the Nernst-Planck transport of one species."""
+    xnew = np.zeros(mesh.nv); res = np.zeros(8)
+    _chk(lib().ora_onestep(mesh.h, params.h, comp0, method, C.c_double(dt), _d(_f64(xold)), _d(_f64(g)), _d(_f64(phi)),
+                           C.c_double(valency), _d(xnew), C.c_double(reduction), solver, prec, steps, maxit, jac_mode,
+                           C.c_double(eps), _d(res)))
+    nst = 1 if method == 1 else 2
+    return xnew, [dict(converged=bool(res[2 * k]), iterations=int(res[2 * k + 1])) for k in range(nst)]

@@ -157,6 +157,16 @@ int ora_linsolve(int n, const int* rowptr, const int* col, const double* val, do
   return 0;
   ORA_CATCH(-1)
 }
+// v = M^-1 d for one of the ISTL preconditioners (PREC_*), applied once
+int ora_prec_apply(int n, const int* rowptr, const int* col, const double* val, int prec, int steps, const double* d,
+                   double* v) {
+  ORA_TRY
+  CSR A; A.n = n; A.rowptr.assign(rowptr, rowptr + n + 1); A.col.assign(col, col + rowptr[n]);
+  A.val.assign(val, val + rowptr[n]);
+  prec_apply(A, prec, steps, v, d);
+  return 0;
+  ORA_CATCH(-1)
+}
 void ora_spmv(int n, const int* rowptr, const int* col, const double* val, const double* x, double* y) {
   for (int r = 0; r < n; r++) {
     double s = 0.0;
@@ -201,6 +211,24 @@ int ora_slp(void* mh, void* ph, int op, int comp0, double* u, const double* aux0
   OpCtx c = make_ctx(m, s, op, aux0, aux1, valency, intorder);
   LinResult lr = slp_apply(sp, c, u, reduction, solver, prec, steps, maxit, jac_mode, eps);
   result[0] = lr.converged; result[1] = lr.iterations; result[2] = lr.reduction; result[3] = lr.conv_rate; result[4] = lr.status;
+  return 0;
+  ORA_CATCH(-1)
+}
+
+// OneStepMethod<Alexander2 (method 0) | ImplicitEuler (1)>::apply for the scalar transport problem:
+// spatial operator DiffusionOperator(phi, valency), temporal operator DiffusionTOperator; result[2*stage + {0,1}] =
+// {converged, iterations} of the stage solves
+int ora_onestep(void* mh, void* ph, int comp0, int method, double dt, const double* xold, const double* g,
+                const double* phi, double valency, double* xnew, double reduction, int solver, int prec, int steps,
+                int maxit, int jac_mode, double eps, double* result) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  Space sp = make_space(*m, *s, 1, comp0);
+  OpCtx c0 = make_ctx(m, s, OP_DIFFUSION, phi, nullptr, valency, -1);
+  OpCtx c1 = make_ctx(m, s, OP_MASS, nullptr, nullptr, 1.0, -1);
+  TimeMethod tm = method == 1 ? implicit_euler() : alexander2();
+  OneStepResult R = onestep_apply(sp, c0, c1, tm, dt, xold, g, xnew, reduction, solver, prec, steps, maxit, jac_mode, eps);
+  for (size_t k = 0; k < R.stage.size(); k++) { result[2 * k] = R.stage[k].converged; result[2 * k + 1] = R.stage[k].iterations; }
   return 0;
   ORA_CATCH(-1)
 }

@@ -712,33 +712,76 @@ inline void interpolate_bcext(const Mesh& m, const Sysparams& s, int comp, const
 // ----------------------------------------------------------------------------
 // ISTL solvers (App. A.7)
 // ----------------------------------------------------------------------------
-enum Prec { PREC_NONE = 0, PREC_JACOBI = 1, PREC_SSOR = 2 };
+enum Prec { PREC_NONE = 0, PREC_JACOBI = 1, PREC_SSOR = 2, PREC_ILU0 = 3 };
 struct LinResult { bool converged = false; int iterations = 0; double reduction = 1, conv_rate = 1; int status = 0; };
 
-inline void prec_apply(const CSR& A, int prec, int steps, double* v, const double* d) {
-  int N = A.n;
-  std::fill(v, v + N, 0.0);
-  if (prec == PREC_NONE) { std::copy(d, d + N, v); return; } // Richardson: v = d
-  if (prec == PREC_JACOBI) { for (int i = 0; i < N; i++) v[i] = d[i] / A.val[A.find(i, i)]; return; }
-  for (int s = 0; s < steps; s++) { // SeqSSOR, w = 1
-    for (int i = 0; i < N; i++) {
-      double sum = d[i], dii = 0;
-      for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) { if (A.col[k] == i) dii = A.val[k]; sum -= A.val[k] * v[A.col[k]]; }
-      v[i] += sum / dii;
+// [UPSTREAM dune-istl 2.2 ilu.hh] bilu0_decomposition: in-place ILU(0) on the pattern of A, rows ascending; for every
+// lower entry (i,j), j ascending: a_ij *= a_jj^-1 (finished rows keep their diagonal INVERTED), then a_ik -= a_ij a_jk
+// for the k > j present in both rows; finally a_ii is inverted.  (ILU0 is not one of the reference's five backends; the
+// north star asks for it next to SSOR, so it is restated the way ISTL's SeqILU0 would run on the PDELab matrix.)
+inline void ilu0_decompose(CSR& A) {
+  for (int i = 0; i < A.n; i++) {
+    for (int kj = A.rowptr[i]; kj < A.rowptr[i + 1] && A.col[kj] < i; kj++) {
+      const int j = A.col[kj];
+      A.val[kj] *= A.val[A.find(j, j)];
+      int ki = kj + 1;
+      for (int kk = A.find(j, j) + 1; kk < A.rowptr[j + 1]; kk++) {
+        while (ki < A.rowptr[i + 1] && A.col[ki] < A.col[kk]) ki++;
+        if (ki < A.rowptr[i + 1] && A.col[ki] == A.col[kk]) A.val[ki] -= A.val[kj] * A.val[kk];
+      }
     }
-    for (int i = N - 1; i >= 0; i--) {
-      double sum = d[i], dii = 0;
-      for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) { if (A.col[k] == i) dii = A.val[k]; sum -= A.val[k] * v[A.col[k]]; }
-      v[i] += sum / dii;
-    }
+    const int d = A.find(i, i);
+    A.val[d] = 1.0 / A.val[d];
   }
 }
+// bilu_backsolve: L v = d (unit lower), then U v = v with the inverted diagonal
+inline void ilu0_backsolve(const CSR& LU, double* v, const double* d) {
+  for (int i = 0; i < LU.n; i++) {
+    double sum = d[i];
+    for (int k = LU.rowptr[i]; k < LU.rowptr[i + 1] && LU.col[k] < i; k++) sum -= LU.val[k] * v[LU.col[k]];
+    v[i] = sum;
+  }
+  for (int i = LU.n - 1; i >= 0; i--) {
+    double sum = v[i];
+    const int dg = LU.find(i, i);
+    for (int k = dg + 1; k < LU.rowptr[i + 1]; k++) sum -= LU.val[k] * v[LU.col[k]];
+    v[i] = sum * LU.val[dg];
+  }
+}
+
+struct Preconditioner {
+  const CSR& A; int prec, steps; CSR LU;
+  Preconditioner(const CSR& A_, int prec_, int steps_) : A(A_), prec(prec_), steps(steps_) {
+    if (prec == PREC_ILU0) { LU = A; ilu0_decompose(LU); }
+  }
+  // v = M^-1 d  (ISTL: v = 0; prec.apply(v, d))
+  void apply(double* v, const double* d) const {
+    int N = A.n;
+    std::fill(v, v + N, 0.0);
+    if (prec == PREC_NONE) { std::copy(d, d + N, v); return; } // Richardson: v = d
+    if (prec == PREC_JACOBI) { for (int i = 0; i < N; i++) v[i] = d[i] / A.val[A.find(i, i)]; return; }
+    if (prec == PREC_ILU0) { ilu0_backsolve(LU, v, d); return; }
+    for (int s = 0; s < steps; s++) { // SeqSSOR, w = 1
+      for (int i = 0; i < N; i++) {
+        double sum = d[i], dii = 0;
+        for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) { if (A.col[k] == i) dii = A.val[k]; sum -= A.val[k] * v[A.col[k]]; }
+        v[i] += sum / dii;
+      }
+      for (int i = N - 1; i >= 0; i--) {
+        double sum = d[i], dii = 0;
+        for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) { if (A.col[k] == i) dii = A.val[k]; sum -= A.val[k] * v[A.col[k]]; }
+        v[i] += sum / dii;
+      }
+    }
+  }
+};
+inline void prec_apply(const CSR& A, int prec, int steps, double* v, const double* d) { Preconditioner(A, prec, steps).apply(v, d); }
 inline double dot(int N, const double* a, const double* b) { double s = 0; for (int i = 0; i < N; i++) s += a[i] * b[i]; return s; }
 inline double nrm2(int N, const double* a) { return std::sqrt(dot(N, a, a)); }
 
 // BiCGSTABSolver::apply(x,b): b is overwritten with the residual
 inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, int maxit, int prec, int steps = 1) {
-  int N = A.n; LinResult res;
+  int N = A.n; LinResult res; const Preconditioner P(A, prec, steps);
   std::vector<double> r(N), rt(N), p(N, 0.0), v(N, 0.0), t(N), y(N), tmp(N);
   A.mv(x, tmp.data());
   for (int i = 0; i < N; i++) r[i] = b[i] - tmp[i];
@@ -760,7 +803,7 @@ inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, 
       beta = (rho_new / rho) * (alpha / omega);
       for (int i = 0; i < N; i++) { p[i] += -omega * v[i]; p[i] *= beta; p[i] += r[i]; }
     }
-    prec_apply(A, prec, steps, y.data(), p.data());
+    P.apply(y.data(), p.data());
     A.mv(y.data(), v.data());
     h = dot(N, rt.data(), v.data());
     if (std::fabs(h) < 1e-80) { res.status = 2; return finish(false); }
@@ -769,7 +812,7 @@ inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, 
     norm = nrm2(N, r.data());
     if (norm < reduction * norm0) return finish(true);
     it += 0.5;
-    prec_apply(A, prec, steps, y.data(), r.data());
+    P.apply(y.data(), r.data());
     A.mv(y.data(), t.data());
     omega = dot(N, t.data(), r.data()) / dot(N, t.data(), t.data());
     for (int i = 0; i < N; i++) { x[i] += omega * y[i]; r[i] += -omega * t[i]; }
@@ -783,7 +826,7 @@ inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, 
 
 // CGSolver::apply(x,b)
 inline LinResult cg(const CSR& A, double* x, double* b, double reduction, int maxit, int prec, int steps = 1) {
-  int N = A.n; LinResult res;
+  int N = A.n; LinResult res; const Preconditioner P(A, prec, steps);
   std::vector<double> p(N), q(N), tmp(N);
   A.mv(x, tmp.data());
   for (int i = 0; i < N; i++) b[i] -= tmp[i];
@@ -794,7 +837,7 @@ inline LinResult cg(const CSR& A, double* x, double* b, double reduction, int ma
     res.conv_rate = i > 0 ? std::pow(res.reduction, 1.0 / i) : 0; return res;
   };
   if (def0 < 1e-30) return finish(true);
-  prec_apply(A, prec, steps, p.data(), b);
+  P.apply(p.data(), b);
   double rholast = dot(N, p.data(), b);
   for (i = 1; i <= maxit; i++) {
     A.mv(p.data(), q.data());
@@ -803,7 +846,7 @@ inline LinResult cg(const CSR& A, double* x, double* b, double reduction, int ma
     for (int k = 0; k < N; k++) { x[k] += lambda * p[k]; b[k] -= lambda * q[k]; }
     def = nrm2(N, b);
     if (def < def0 * reduction || def < 1e-30) return finish(true);
-    prec_apply(A, prec, steps, q.data(), b);
+    P.apply(q.data(), b);
     double rho = dot(N, q.data(), b);
     double beta = rho / rholast;
     for (int k = 0; k < N; k++) p[k] = beta * p[k] + q[k];
@@ -908,6 +951,67 @@ inline LinResult slp_apply(const Space& sp, const OpCtx& c, double* u, double re
   LinResult lr = lin_solve(solver, A, z.data(), r.data(), reduction, maxit, prec, steps);
   for (int i = 0; i < N; i++) u[i] -= z[i];
   return lr;
+}
+
+// ----------------------------------------------------------------------------
+// OneStepMethod + OneStepGridOperator (App. A.9) [UPSTREAM dune-pdelab 1.1 instationary/onestep.hh,
+// gridoperator/onestep.hh, timesteppingparameterinterface]; call sites
+// instationary_pnp_from_pb_md.hh:368-391 (construction) and :421-425 (apply per time step).
+// ----------------------------------------------------------------------------
+struct TimeMethod { // TimeSteppingParameterInterface: s stages, d[0..s], a[r][0..s], b[r][0..s] (r = 0..s-1)
+  int s = 1; std::vector<double> d; std::vector<std::vector<double>> a, b;
+};
+inline TimeMethod alexander2() { // Alexander2Parameter
+  const double alpha = 1.0 - 0.5 * std::sqrt(2.0);
+  TimeMethod m; m.s = 2; m.d = {0.0, alpha, 1.0};
+  m.a = {{-1.0, 1.0, 0.0}, {-1.0, 0.0, 1.0}};
+  m.b = {{0.0, alpha, 0.0}, {0.0, 1.0 - alpha, alpha}};
+  return m;
+}
+inline TimeMethod implicit_euler() { // ImplicitEulerParameter
+  TimeMethod m; m.s = 1; m.d = {0.0, 1.0}; m.a = {{-1.0, 1.0}}; m.b = {{0.0, 1.0}};
+  return m;
+}
+struct OneStepResult { std::vector<LinResult> stage; };
+// xold -> xnew over one step of size dt.  c0: spatial operator (DiffusionOperator), c1: temporal operator
+// (DiffusionTOperator); g: Dirichlet values (interpolate(f, ...) at the constrained dofs; the reference's boundary
+// function cpB is time independent); the stage problems are solved by StationaryLinearProblemSolver (one linear solve).
+inline OneStepResult onestep_apply(const Space& sp, const OpCtx& c0, const OpCtx& c1, const TimeMethod& tm, double dt,
+                                   const double* xold, const double* g, double* xnew, double reduction, int solver,
+                                   int prec, int steps, int maxit, int jac_mode = 0, double eps = 1e-11) {
+  const int N = sp.N();
+  OneStepResult out;
+  std::vector<std::vector<double>> x(tm.s + 1, std::vector<double>(N));
+  std::copy(xold, xold + N, x[0].begin());
+  CSR A = make_pattern(sp), B = make_pattern(sp);
+  std::vector<double> cst(N), r0(N), r1(N), res(N), z(N);
+  for (int r = 1; r <= tm.s; r++) {
+    // preStage: constant part of the residual from the earlier stages
+    std::fill(cst.begin(), cst.end(), 0.0);
+    for (int i = 0; i < r; i++) {
+      const double ai = tm.a[r - 1][i], bi = tm.b[r - 1][i];
+      if (std::fabs(ai) > 1e-6) { residual(sp, c1, x[i].data(), r1.data()); for (int k = 0; k < N; k++) cst[k] += ai * r1[k]; }
+      if (std::fabs(bi) > 1e-6) { residual(sp, c0, x[i].data(), r0.data()); for (int k = 0; k < N; k++) cst[k] += bi * dt * r0[k]; }
+    }
+    // initial guess: previous stage; Dirichlet dofs from the boundary function, the rest copied (copy_nonconstrained_dofs)
+    std::vector<double>& xn = x[r];
+    xn = x[r - 1];
+    for (int k = 0; k < N; k++) if (sp.dirichlet[k]) xn[k] = g[k];
+    // StationaryLinearProblemSolver on the one-step operator
+    const double ar = tm.a[r - 1][r], br = tm.b[r - 1][r];
+    jacobian(sp, c1, xn.data(), A, jac_mode, eps);
+    jacobian(sp, c0, xn.data(), B, jac_mode, eps);
+    for (size_t k = 0; k < A.val.size(); k++) A.val[k] = ar * A.val[k] + br * dt * B.val[k];
+    for (int k = 0; k < N; k++) if (sp.dirichlet[k]) A.val[A.find(k, k)] = 1.0; // constrained rows are trivial
+    residual(sp, c1, xn.data(), r1.data());
+    residual(sp, c0, xn.data(), r0.data());
+    for (int k = 0; k < N; k++) res[k] = sp.dirichlet[k] ? 0.0 : cst[k] + ar * r1[k] + br * dt * r0[k];
+    std::fill(z.begin(), z.end(), 0.0);
+    out.stage.push_back(lin_solve(solver, A, z.data(), res.data(), reduction, maxit, prec, steps));
+    for (int k = 0; k < N; k++) xn[k] -= z[k];
+  }
+  std::copy(x[tm.s].begin(), x[tm.s].end(), xnew);
+  return out;
 }
 
 } // namespace pnpo

@@ -25,7 +25,7 @@ def lib():
     global _LIB
     if _LIB is None:
         csrc = os.path.join(_HERE, "..", "dune_pnp_b200", "csrc")
-        deps = [_SRC] + [os.path.join(csrc, f) for f in ("pnp_elem.cuh", "pnp_star.cuh", "pnp_setup_algos.cuh")]
+        deps = [_SRC] + [os.path.join(csrc, f) for f in ("pnp_elem.cuh", "pnp_star.cuh", "pnp_setup_algos.cuh", "pnp_sweep.cuh")]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
                                    _SRC, "-o", _SO])
@@ -157,4 +157,30 @@ class Star:
         vals = np.zeros((7 if F == 3 else 1) * self.nslots)
         lib().hh_jacobian(self.h, op, _d(self._phys(params_sys, valency)), _d(u), _d(a0), _d(a1), comp0, mode,
                           C.c_double(eps), _d(vals))
+        self.last_vals = vals  # internal planes, for the sweep emulation
         return self.export_csr(F, comp0, vals)
+
+    # ---- level-scheduled preconditioner sweeps (pnp_sweep.cuh) ----
+    def sweep_levels(self, F, full):
+        lev = np.zeros(F * self.n_own, dtype=np.int32)
+        n = lib().hh_sweep_levels(self.h, F, int(full), _i(lev))
+        return n, lev
+
+    def ssor_apply(self, F, vals, steps, d_lex):
+        """vals: NP planes in internal layout; d, result in reference numbering."""
+        d = self.to_internal(d_lex, F); x = np.zeros_like(d)
+        lib().hh_ssor_apply(self.h, F, _d(np.ascontiguousarray(vals, dtype=np.float64)), steps, _d(d), _d(x))
+        return self.to_external(x, F)
+
+    def ilu0_apply(self, F, vals, d_lex):
+        vals = np.asarray(vals, dtype=np.float64).reshape(-1, self.nslots)
+        if F == 3:  # 7 stored planes -> the 9 blocks of PDELab's pattern
+            lu = np.zeros((9, self.nslots))
+            for (f, g), pl in PNP_PLANE.items():
+                lu[3 * f + g] = vals[pl]
+        else:
+            lu = vals.copy()
+        lu = np.ascontiguousarray(lu)
+        d = self.to_internal(d_lex, F); x = np.zeros_like(d)
+        lib().hh_ilu0_apply(self.h, F, _d(lu), _d(d), _d(x))
+        return self.to_external(x, F)

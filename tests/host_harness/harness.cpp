@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../dune_pnp_b200/csrc/pnp_star.cuh"
+#include "../../dune_pnp_b200/csrc/pnp_sweep.cuh"
 
 using namespace pnp;
 
@@ -193,4 +194,62 @@ void hh_jacobian(void* h, int op, const double* phys, const double* u, const dou
   }
 }
 
+} // extern "C"
+
+// ---- level-scheduled sweeps (pnp_sweep.cuh): the kernels of pnp_precond.cu emulated level by level ----
+// Levels by fixpoint relaxation (as the device does); returns the number of levels.  lev: F*n_own ints.
+template <int F> static int sweep_levels_t(Star* S, bool full, int* lev) {
+  const SweepView V{S->rp.data(), S->adj.data(), S->int2ext.data(), (int)S->n_own};
+  std::fill(lev, lev + F * S->n_own, 0);
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (int v = (int)S->n_own - 1; v >= 0; v--) // deliberately against the sweep order: worst case for the relaxation
+      for (int f = 0; f < F; f++) {
+        const int l = sweep_level_relax<F>(V, lev, v, f, full);
+        if (l != lev[F * v + f]) { lev[F * v + f] = l; changed = true; }
+      }
+  }
+  return 1 + *std::max_element(lev, lev + F * S->n_own);
+}
+// dofs grouped by level; inside a level in DESCENDING internal index (any order must give the same result)
+static std::vector<std::vector<int>> level_sets(const int* lev, long n, int nlev) {
+  std::vector<std::vector<int>> L(nlev);
+  for (long i = n - 1; i >= 0; i--) L[lev[i]].push_back((int)i);
+  return L;
+}
+extern "C" {
+int hh_sweep_levels(void* h, int F, int full, int* lev) {
+  return F == 1 ? sweep_levels_t<1>((Star*)h, full, lev) : sweep_levels_t<3>((Star*)h, full, lev);
+}
+// x = SSOR^steps applied to d (x starts at 0), vals: NP planes (internal layout)
+void hh_ssor_apply(void* h, int F, const double* vals, int steps, const double* d, double* x) {
+  Star* S = (Star*)h;
+  const SweepView V{S->rp.data(), S->adj.data(), S->int2ext.data(), (int)S->n_own};
+  const long n = (long)F * S->n_own, stride = (long)S->adj.size();
+  std::vector<int> lev(n);
+  const int nlev = hh_sweep_levels(h, F, 0, lev.data());
+  const auto L = level_sets(lev.data(), n, nlev);
+  std::fill(x, x + n, 0.0);
+  for (int s = 0; s < steps; s++) {
+    for (int l = 0; l < nlev; l++)
+      for (int i : L[l]) { if (F == 1) gs_update<1>(V, vals, stride, d, x, i, 0); else gs_update<7>(V, vals, stride, d, x, i / 3, i % 3); }
+    for (int l = nlev - 1; l >= 0; l--)
+      for (int i : L[l]) { if (F == 1) gs_update<1>(V, vals, stride, d, x, i, 0); else gs_update<7>(V, vals, stride, d, x, i / 3, i % 3); }
+  }
+}
+// x = (LU)^-1 d with the ILU(0) factor of the matrix given as F*F planes (overwritten by the factor)
+void hh_ilu0_apply(void* h, int F, double* lu, const double* d, double* x) {
+  Star* S = (Star*)h;
+  const SweepView V{S->rp.data(), S->adj.data(), S->int2ext.data(), (int)S->n_own};
+  const long n = (long)F * S->n_own, stride = (long)S->adj.size();
+  std::vector<int> lev(n);
+  const int nlev = hh_sweep_levels(h, F, 1, lev.data());
+  const auto L = level_sets(lev.data(), n, nlev);
+  for (int l = 0; l < nlev; l++)
+    for (int i : L[l]) { if (F == 1) ilu0_row<1>(V, lu, stride, i, 0); else ilu0_row<3>(V, lu, stride, i / 3, i % 3); }
+  for (int l = 0; l < nlev; l++)
+    for (int i : L[l]) { if (F == 1) ilu0_forward<1>(V, lu, stride, d, x, i, 0); else ilu0_forward<3>(V, lu, stride, d, x, i / 3, i % 3); }
+  for (int l = nlev - 1; l >= 0; l--)
+    for (int i : L[l]) { if (F == 1) ilu0_backward<1>(V, lu, stride, x, i, 0); else ilu0_backward<3>(V, lu, stride, x, i / 3, i % 3); }
+}
 } // extern "C"

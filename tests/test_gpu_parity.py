@@ -450,3 +450,99 @@ def test_full_size_properties_level5():
     # (R(u+z) - R(u) - J z) is second order in z: the only non-linear terms are the c * grad(phi) products
     assert np.linalg.norm(lhs - rhs) <= 1e-4 * np.linalg.norm(rhs)
     assert not c.download(ru, 3)[~free].any()
+
+
+# ---- SSOR(k) / ILU0: the reference's sequential sweeps, level-scheduled on the device (pnp_precond.cu) ----
+def _assembled(name, levels, op, renumber=True):
+    capi = _capi()
+    c, m, p = make_ctx(name, renumber=renumber, levels=levels)
+    rng = np.random.RandomState(7)
+    F = ora.nfields(op)
+    u = rng.uniform(-0.5, 0.5, F * m.nv)
+    if op == ora.OP_PNP:
+        u[m.nv:] = rng.uniform(0.02, 0.1, 2 * m.nv)
+    a0 = rng.uniform(0, 1, m.nv); a1 = rng.uniform(0, 1, m.nv)
+    h = _gpu_operator(c, op, a0, a1, 1.0)
+    vu, A = c.vec(F, u), c.matrix(h)
+    c.jacobian(h, vu, A, 1, 0.0)
+    rp, col = c.pattern(h, F)
+    val = c.matrix_values(h, A, len(col))
+    return c, m, F, A, rp, col, val, rng
+
+
+SWEEP_CASES = [("one_wall", 1, ora.OP_PB), ("sphere", 0, ora.OP_POISSON), ("cylinder", 0, ora.OP_PNP),
+               ("pore_small", 1, ora.OP_PNP), ("pore", 2, ora.OP_DIFFUSION), ("pore", 1, ora.OP_PNP)]
+
+
+@pytest.mark.parametrize("prec,steps", [(2, 1), (2, 3), (3, 1)])
+@pytest.mark.parametrize("name,levels,op", SWEEP_CASES)
+def test_ssor_ilu0_application_equals_sequential_sweep(name, levels, op, prec, steps):
+    """v = M^-1 d of SeqSSOR(n) / SeqILU0 in the reference's row order (ISTLBackend_NOVLP_BCGS_SSORk,
+    instationary_pnp_from_pb_md.hh:188-191): the level-scheduled device sweep equals the sequential CPU sweep."""
+    capi = _capi()
+    c, m, F, A, rp, col, val, rng = _assembled(name, levels, op)
+    d = rng.uniform(-1, 1, F * m.nv)
+    s = c.solver(capi.SOLVER_BCGS, prec, 100, steps)
+    vd, vv = c.vec(F, d), c.vec(F)
+    c.precond_apply(s, A, vd, vv)
+    v = c.download(vv, F)
+    v_o = ora.prec_apply(rp, col, val, d, prec, steps)
+    assert np.linalg.norm(v - v_o) <= 1e-12 * np.linalg.norm(v_o)
+    nlev = c.solver_get(s, "ssor_levels" if prec == 2 else "ilu0_levels")
+    assert 1 <= nlev <= F * m.nv
+
+
+@pytest.mark.parametrize("renumber", [False, True])
+@pytest.mark.parametrize("kind,prec", [(0, 2), (1, 2), (0, 3), (1, 3)])
+def test_krylov_with_ssor_ilu0_matches_oracle_iteration_counts(kind, prec, renumber):
+    """BiCGSTAB / CG preconditioned by SSOR(1) / ILU0 on the Poisson matrix of the refined sphere mesh: the sweep order is
+    the reference's whatever the internal numbering, so iteration counts equal the CPU path's."""
+    capi = _capi()
+    c, m, F, A, rp, col, val, rng = _assembled("sphere", 2, ora.OP_POISSON, renumber)
+    b = rng.uniform(-1, 1, m.nv)
+    s = c.solver(kind, prec, 2000)
+    vz, vb = c.vec(1), c.vec(1, b)
+    res = c.solve(s, A, vz, vb, 1e-10)
+    z_o, res_o = ora.linsolve(rp, col, val, b, 1e-10, 2000, kind, prec)
+    assert res.converged and res_o["converged"]
+    # same sweep, but BiCGSTAB's scalars feel the summation order of the dot products / SpMV rows (internal numbering)
+    assert abs(res.iterations - res_o["iterations"]) <= (max(3, res_o["iterations"] // 10) if renumber else 1)
+    assert np.linalg.norm(c.download(vz, 1) - z_o) <= 1e-7 * np.linalg.norm(z_o)
+
+
+@pytest.mark.parametrize("name", ["one_wall", "sphere", "pore"])
+def test_newton_pb_default_backend_bcgs_ssor(name):
+    """The reference's default backend (LINEARSOLVER=1: BiCGSTAB + SSOR(1)) on the PB Newton solve: equal Newton AND
+    equal linear iteration counts per Newton step."""
+    capi = _capi()
+    c, m, p = make_ctx(name)
+    h = c.operator(capi.OP_PB, 0)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 5000, 1)
+    vu = c.vec(1)
+    st, res = c.newton(h, vu, s, c.newton_opts(jac_mode=0))
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, jac_mode=0); opts[12] = 5000
+    u_o, res_o = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+    assert res.converged and res_o["converged"] and res.iterations == res_o["iterations"]
+    assert abs(res.linear_iterations - res_o["total_linear_iterations"]) <= res.iterations
+    assert np.linalg.norm(c.download(vu, 1) - u_o) <= 10 * p.sys[7] * np.linalg.norm(u_o) + 1e-14
+
+
+def test_newton_pnp_with_ssor_and_ilu0():
+    """Monolithic PNP Newton on cylinder.msh from the interpolated PB state with SSOR(1) and ILU0 vs the oracle's SSOR."""
+    capi = _capi()
+    c, m, p = make_ctx("cylinder")
+    hpb = c.operator(capi.OP_PB, 0)
+    vpb = c.vec(1)
+    c.newton(hpb, vpb, c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 5000), c.newton_opts())
+    f = [c.vec(1) for _ in range(3)]
+    for k in range(3):
+        c.interpolate_bcext(k, vpb, f[k])
+    u0 = np.concatenate([c.download(f[k], 1) for k in range(3)])
+    h = c.operator(capi.OP_PNP, 0)
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR); opts[12] = 20000
+    u_o, res_o = ora.newton(m, p, ora.OP_PNP, u0, opts)
+    for prec in (capi.PREC_SSOR, capi.PREC_ILU0):
+        vu = c.vec(3, u0)
+        st, res = c.newton(h, vu, c.solver(capi.SOLVER_BCGS, prec, 20000, 1), c.newton_opts())
+        assert res.converged and res.iterations == res_o["iterations"]
+        assert np.linalg.norm(c.download(vu, 3) - u_o) <= 10 * p.sys[7] * np.linalg.norm(u_o)

@@ -119,3 +119,51 @@ def test_no_cpu_fallback_without_a_gpu():
     with pytest.raises(capi.PnpError) as e:
         capi.Context(0)
     assert e.value.status == 6  # PNP_E_CUDA
+
+
+# ---- sequential-order preconditioners, level-scheduled (pnp_sweep.cuh) vs the oracle's plain sequential sweeps ----
+def _jac_case(name, levels, op):
+    a, m, p = case(name, levels)
+    S = harness.Star(a, p.surf, True)
+    rng = np.random.RandomState(3)
+    F = ora.nfields(op)
+    u = rng.uniform(-0.5, 0.5, F * m.nv)
+    if op == ora.OP_PNP:
+        u[m.nv:] = rng.uniform(0.02, 0.1, 2 * m.nv)
+    a0 = rng.uniform(0, 1, m.nv); a1 = rng.uniform(0, 1, m.nv)
+    rp, col, val = S.jacobian(op, p.sys, u, a0, a1, valency=1.0, mode=1)
+    return S, F, rp, col, val, rng.uniform(-1, 1, F * m.nv)
+
+
+def test_sweep_levels_are_a_valid_schedule():
+    S, F, rp, col, val, d = _jac_case("cylinder", 0, ora.OP_PNP)
+    for full in (0, 1):
+        nlev, lev = S.sweep_levels(3, full)
+        lev_lex = np.zeros(3 * S.nv, dtype=np.int64)
+        lev_lex.reshape(3, S.nv)[:, S.int2ext] = lev.reshape(S.nv, 3).T
+        for i in range(3 * S.nv):
+            cols = col[rp[i]:rp[i + 1]]
+            vals_i = val[rp[i]:rp[i + 1]]
+            lower = cols[(cols < i) & ((vals_i != 0) | bool(full))]
+            # coupled predecessors sit on strictly lower levels, and the level is the smallest such number
+            assert np.all(lev_lex[lower] < lev_lex[i])
+        assert lev.min() == 0 and len(np.unique(lev)) == nlev
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+@pytest.mark.parametrize("name,levels,op", [("one_wall", 1, ora.OP_PB), ("sphere", 0, ora.OP_POISSON), ("cylinder", 0, ora.OP_PNP),
+                                            ("pore_small", 1, ora.OP_PNP), ("pore", 0, ora.OP_DIFFUSION)])
+def test_level_scheduled_ssor_equals_sequential_ssor(name, levels, op, steps):
+    S, F, rp, col, val, d = _jac_case(name, levels, op)
+    x = S.ssor_apply(F, S.last_vals, steps, d)
+    x_o = ora.prec_apply(rp, col, val, d, ora.PREC_SSOR, steps)
+    assert np.linalg.norm(x - x_o) <= 1e-13 * np.linalg.norm(x_o)
+
+
+@pytest.mark.parametrize("name,levels,op", [("one_wall", 1, ora.OP_PB), ("sphere", 0, ora.OP_POISSON), ("cylinder", 0, ora.OP_PNP),
+                                            ("pore_small", 1, ora.OP_PNP), ("pore", 0, ora.OP_DIFFUSION)])
+def test_level_scheduled_ilu0_equals_sequential_ilu0(name, levels, op):
+    S, F, rp, col, val, d = _jac_case(name, levels, op)
+    x = S.ilu0_apply(F, S.last_vals, d)
+    x_o = ora.prec_apply(rp, col, val, d, ora.PREC_ILU0)
+    assert np.linalg.norm(x - x_o) <= 1e-12 * np.linalg.norm(x_o)
