@@ -15,6 +15,7 @@ OP_PB, OP_POISSON, OP_DIFFUSION, OP_MASS, OP_PNP = range(5)
 JAC_FD_FAITHFUL, JAC_ANALYTIC = 0, 1
 SOLVER_BCGS, SOLVER_CG = 0, 1
 PREC_NONE, PREC_JACOBI, PREC_SSOR, PREC_ILU0, PREC_AMG = range(5)
+TIME_ALEXANDER2, TIME_IMPLICIT_EULER = 0, 1
 STATUS = {0: "PNP_OK", 1: "PNP_E_NOT_CONVERGED", 2: "PNP_E_LINEAR_SOLVER", 3: "PNP_E_LINE_SEARCH", 4: "PNP_E_NAN",
           5: "PNP_E_BREAKDOWN", 6: "PNP_E_CUDA", 7: "PNP_E_CONFIG", 8: "PNP_E_ARG", 9: "PNP_E_MESH"}
 
@@ -374,6 +375,14 @@ class Context:
         res = LinResult()
         self._ck(lib().pnp_slp_apply(self._h, op, u, solver, C.c_double(reduction), jac_mode, C.c_double(eps), C.byref(res)))
         return res
+
+    def onestep(self, op_space, op_time, solver, dt, x_old, dirichlet_values, x_new, reduction=1e-5, method=TIME_ALEXANDER2,
+                jac_mode=JAC_FD_FAITHFUL, eps=1e-11, time=0.0):
+        """OneStepMethod::apply; returns the stage solves' LinResults."""
+        res = (LinResult * 2)()
+        self._ck(lib().pnp_onestep_apply(self._h, method, op_space, op_time, solver, C.c_double(time), C.c_double(dt), x_old,
+                                         dirichlet_values, x_new, C.c_double(reduction), jac_mode, C.c_double(eps), res))
+        return list(res)[: (1 if method == TIME_IMPLICIT_EULER else 2)]
 
     def interpolate_bcext(self, component, pb_vec, out_vec):
         self._ck(lib().pnp_interpolate_bcext(self._h, component, -1 if pb_vec is None else pb_vec, out_vec))

@@ -8,6 +8,7 @@
 namespace pnp {
 int newton_apply(Ctx&, const Operator&, Vec&, Solver&, const pnp_newton_opts&, pnp_newton_result&);
 LinResult slp_apply(Ctx&, const Operator&, Vec&, Solver&, double, int, double);
+int onestep_apply(Ctx&, int, const Operator&, const Operator&, Solver&, double, Vec&, Vec&, Vec&, double, int, double, LinResult*);
 namespace {
 __global__ void k_fill(double* x, long n, double v) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] = v;
@@ -475,6 +476,19 @@ pnp_status pnp_slp_apply(pnp_ctx* ctx, int op, int u, int solver, double reducti
   API_BEGIN(ctx)
   LinResult lr = slp_apply(c, c.oper(op), c.vec(u), c.solver(solver), reduction, jac_mode, eps);
   to_lin(lr, out);
+  API_END
+}
+pnp_status pnp_onestep_apply(pnp_ctx* ctx, int method, int op_space, int op_time, int solver, double time, double dt,
+                             int x_old, int dirichlet_values, int x_new, double reduction, int jac_mode, double eps,
+                             pnp_lin_result* stage_results) {
+  API_BEGIN(ctx)
+  (void)time; // the reference's boundary functions and operators do not depend on time
+  LinResult lr[2];
+  const int st = onestep_apply(c, method, c.oper(op_space), c.oper(op_time), c.solver(solver), dt, c.vec(x_old),
+                               c.vec(dirichlet_values), c.vec(x_new), reduction, jac_mode, eps, lr);
+  if (stage_results) for (int k = 0; k < (method == PNP_TIME_IMPLICIT_EULER ? 1 : 2); k++) to_lin(lr[k], stage_results + k);
+  if (st == PNP_E_BREAKDOWN) { c.err = "BiCGSTAB breakdown in a stage solve"; return PNP_E_BREAKDOWN; }
+  if (st == PNP_E_NAN) { c.err = "non-finite residual norm in a stage solve"; return PNP_E_NAN; }
   API_END
 }
 pnp_status pnp_mesh_owned(pnp_ctx* ctx, long* n_own) { API_BEGIN(ctx) if (n_own) *n_own = c.n_own; API_END }

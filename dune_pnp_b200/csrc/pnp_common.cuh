@@ -189,6 +189,8 @@ struct Ctx {
   // Newton call costs more than the step itself
   Vec ws_r, ws_z, ws_prev;
   Matrix ws_A;
+  Vec ws_stage[6];                     // one-step method: stage vectors, constant residual part, operator residuals
+  Matrix ws_B;                         // one-step method: Jacobian of the temporal operator
   bool owns_stream = true;             // child contexts (coarser multigrid levels) share the parent's stream and communicator
   std::vector<MgLevelRef> mg;          // distributed multigrid: coarser levels, finest-but-one first
   // coarsest distributed level: internal vertex -> index in the replicated dense system.  mg_aggregated = false: that
@@ -203,7 +205,8 @@ struct Ctx {
   void invalidate_mesh_objects() {
     finalized = false; constraints_built = false;
     vecs.clear(); mats.clear(); ops.clear(); solvers.clear();
-    ws_r.d.release(); ws_z.d.release(); ws_prev.d.release(); ws_A.vals.release();
+    ws_r.d.release(); ws_z.d.release(); ws_prev.d.release(); ws_A.vals.release(); ws_B.vals.release();
+    for (auto& v : ws_stage) v.d.release();
   }
   // scratch for reductions
   DBuf<double> red_partial, red_out;

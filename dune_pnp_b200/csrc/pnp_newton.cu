@@ -146,4 +146,104 @@ LinResult slp_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, double reduct
   return lr;
 }
 
+// ---- OneStepMethod + OneStepGridOperator (/root/reference/src/instationary_pnp_from_pb_md.hh:368-391,
+// applied per time step at :421-425) ------------------------------------------------------------------------------
+namespace {
+struct TimeMethod { int s; double d[3], a[2][3], b[2][3]; };
+TimeMethod time_method(int method) {
+  if (method == PNP_TIME_IMPLICIT_EULER) return TimeMethod{1, {0.0, 1.0, 0.0}, {{-1.0, 1.0, 0.0}, {0, 0, 0}}, {{0.0, 1.0, 0.0}, {0, 0, 0}}};
+  PNP_REQUIRE(method == PNP_TIME_ALEXANDER2, PNP_E_ARG, "unknown time stepping method");
+  const double al = 1.0 - 0.5 * std::sqrt(2.0); // Alexander2Parameter
+  return TimeMethod{2, {0.0, al, 1.0}, {{-1.0, 1.0, 0.0}, {-1.0, 0.0, 1.0}}, {{0.0, al, 0.0}, {0.0, 1.0 - al, al}}};
+}
+// A = a*A + b*B over all slots
+__global__ void k_stage_matrix(double* __restrict__ A, const double* __restrict__ B, double a, double b, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) A[i] = a * A[i] + b * B[i];
+}
+// constrained rows of the combined matrix are trivial: unit diagonal (their off-diagonals are zero in both parts)
+__global__ void k_unit_dirichlet_diag(const int* __restrict__ rp, const unsigned char* __restrict__ dmask, int comp, int n_own,
+                                      double* __restrict__ A) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_own; v += gridDim.x * blockDim.x)
+    if ((dmask[v] >> comp) & 1u) A[rp[v]] = 1.0;
+}
+// Dirichlet dofs take the boundary function's values (interpolate + copy_nonconstrained_dofs)
+__global__ void k_set_dirichlet(const unsigned char* __restrict__ dmask, int comp, int n, const double* __restrict__ g,
+                                double* __restrict__ x) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+    if ((dmask[v] >> comp) & 1u) x[v] = g[v];
+}
+// y = (init ? 0 : y) + a*p + b*q
+__global__ void k_lincomb(double* __restrict__ y, int init, double a, const double* __restrict__ p, double b,
+                          const double* __restrict__ q, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    double v = init ? 0.0 : y[i];
+    if (p) v += a * p[i];
+    if (q) v += b * q[i];
+    y[i] = v;
+  }
+}
+} // namespace
+
+// xold -> xnew over one step dt.  op0: spatial operator (GO0), op1: temporal operator (GO1); g: Dirichlet values; each
+// stage is one StationaryLinearProblemSolver::apply on  a_rr*M + b_rr*dt*J0.  stage[r] receives the stage solves' results.
+int onestep_apply(Ctx& c, int method, const Operator& op0, const Operator& op1, Solver& S, double dt, Vec& xold, Vec& g,
+                  Vec& xnew, double reduction, int jac_mode, double eps, LinResult* stage) {
+  PNP_REQUIRE(op_fields(op0.op) == 1 && op_fields(op1.op) == 1, PNP_E_ARG, "one-step method: scalar operators expected");
+  PNP_REQUIRE(xold.fields == 1 && xnew.fields == 1 && g.fields == 1, PNP_E_ARG, "one-step method: 1-field vectors expected");
+  PNP_REQUIRE(op0.comp0 == op1.comp0, PNP_E_ARG, "spatial and temporal operator must share the constraints");
+  const TimeMethod tm = time_method(method);
+  const long n = c.n_own, nall = c.nv;
+  const int comp = op0.comp0;
+  for (auto& v : c.ws_stage) { v.fields = 1; if (v.d.n != (size_t)nall) { v.d.alloc(nall); v.d.zero(c.stream); } }
+  Vec &x1 = c.ws_stage[0], &x2 = c.ws_stage[1], &cst = c.ws_stage[2], &r0 = c.ws_stage[3], &r1 = c.ws_stage[4];
+  Vec &r = c.ws_r, &z = c.ws_z;
+  r.fields = z.fields = 1;
+  if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); c.ws_prev.d.alloc(nall); r.d.zero(c.stream); z.d.zero(c.stream); }
+  Matrix &A = c.ws_A, &B = c.ws_B;
+  A.op = op0.op; B.op = op1.op; A.nplanes = B.nplanes = 1;
+  if (A.vals.n != (size_t)c.nslots) A.vals.alloc(c.nslots);
+  if (B.vals.n != (size_t)c.nslots) B.vals.alloc(c.nslots);
+  Vec* x[3] = {&xold, &x1, &x2};
+  const int gv = grid_for(n, 256), gs = grid_for(c.nslots, 256);
+  for (int rs = 1; rs <= tm.s; rs++) {
+    // preStage: the part of the stage residual that the earlier stages fix
+    bool first = true;
+    for (int i = 0; i < rs; i++) {
+      const double ai = tm.a[rs - 1][i], bi = tm.b[rs - 1][i];
+      const bool do1 = std::fabs(ai) > 1e-6, do0 = std::fabs(bi) > 1e-6;
+      if (do1) assemble_residual(c, op1, *x[i], r1);
+      if (do0) assemble_residual(c, op0, *x[i], r0);
+      if (do0 || do1) {
+        k_lincomb<<<gv, 256, 0, c.stream>>>(cst.d.p, first, ai, do1 ? r1.d.p : nullptr, bi * dt, do0 ? r0.d.p : nullptr, n);
+        PNP_CHECK_LAUNCH(); c.launches++;
+        first = false;
+      }
+    }
+    if (first) vec_zero(c, cst.d.p, n);
+    Vec& xn = *x[rs];
+    vec_copy(c, x[rs - 1]->d.p, xn.d.p, n);
+    k_set_dirichlet<<<gv, 256, 0, c.stream>>>(c.dmask.p, comp, (int)n, g.d.p, xn.d.p);
+    PNP_CHECK_LAUNCH(); c.launches++;
+    const double ar = tm.a[rs - 1][rs], br = tm.b[rs - 1][rs];
+    assemble_jacobian(c, op1, xn, B, jac_mode, eps);
+    assemble_jacobian(c, op0, xn, A, jac_mode, eps);
+    k_stage_matrix<<<gs, 256, 0, c.stream>>>(A.vals.p, B.vals.p, br * dt, ar, c.nslots);
+    k_unit_dirichlet_diag<<<gv, 256, 0, c.stream>>>(c.rp.p, c.dmask.p, comp, (int)n, A.vals.p);
+    PNP_CHECK_LAUNCH(); c.launches += 2;
+    assemble_residual(c, op1, xn, r1);
+    assemble_residual(c, op0, xn, r0);
+    vec_copy(c, cst.d.p, r.d.p, n);
+    k_lincomb<<<gv, 256, 0, c.stream>>>(r.d.p, 0, ar, r1.d.p, br * dt, r0.d.p, n);
+    PNP_CHECK_LAUNCH(); c.launches++;
+    vec_zero(c, z.d.p, n);
+    const LinResult lr = solver_apply(c, S, A, z, r, reduction);
+    if (stage) stage[rs - 1] = lr;
+    if (lr.status) return lr.status;
+    vec_axpy(c, -1.0, z.d.p, xn.d.p, n);
+  }
+  vec_copy(c, x[tm.s]->d.p, xnew.d.p, n);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
 } // namespace pnp

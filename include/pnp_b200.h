@@ -209,6 +209,16 @@ pnp_status pnp_newton_apply(pnp_ctx*, int op_handle, int u, int solver, const pn
 pnp_status pnp_slp_apply(pnp_ctx*, int op_handle, int u, int solver, double reduction, int jac_mode, double fd_epsilon,
                          pnp_lin_result*);
 
+/* ---- time stepping: Dune::PDELab::OneStepMethod<Real,IGO,PDESOLVER,U,U>::apply(time, dt, xold, f, xnew) on a
+ * OneStepGridOperator<GO0,GO1> with a StationaryLinearProblemSolver per stage (instationary_pnp_from_pb_md.hh:368-391,
+ * applied at :421-425).  op_space = GO0's local operator (DiffusionOperator), op_time = GO1's (DiffusionTOperator);
+ * dirichlet_values = the boundary function f interpolated to the dofs (only constrained dofs are read; the reference's
+ * cpB/cmB are time independent); stage_results: one entry per stage (2 for Alexander2) or NULL. */
+enum { PNP_TIME_ALEXANDER2 = 0, PNP_TIME_IMPLICIT_EULER = 1 };
+pnp_status pnp_onestep_apply(pnp_ctx*, int method, int op_space, int op_time, int solver, double time, double dt, int x_old,
+                             int dirichlet_values, int x_new, double reduction, int jac_mode, double fd_epsilon,
+                             pnp_lin_result* stage_results);
+
 /* ---- initial guess / Dirichlet values: interpolate(BCExtension) (dirichlet_bc.hh:54-123) --- */
 /* component 0: phi, 1: c+, 2: c-; pb_vec < 0 means a zero PB field; out is a 1-field vector */
 pnp_status pnp_interpolate_bcext(pnp_ctx*, int component, int pb_vec, int out_vec);

@@ -6,6 +6,7 @@
 //   Newton<GO,LS,U>(go,u,ls) + setters + apply()                                    stationary_pnp.hh:280-294
 //   StationaryLinearProblemSolver<GO,LS,U>(go,u,ls,red).apply()                      instationary_pnp_from_pb_md.hh:349-350
 //   interpolate(BCExtension, gfs, u)                                                 stationary_pnp_from_pb.hh:270
+//   OneStepGridOperator<GO0,GO1>, OneStepMethod<...>(Alexander2Parameter, igo, pdesolver).apply(t,dt,x,f,xnew)   instationary_pnp_from_pb_md.hh:368-391,421-425
 // Errors are rethrown as the same-named exception types PDELab throws.
 #pragma once
 #include <stdexcept>
@@ -146,6 +147,10 @@ struct ISTLBackend_NOVLP_BCGS_AMG : LinearSolverBackend {  // new: what bench.py
   ISTLBackend_NOVLP_BCGS_AMG(Grid& g, int smoothsteps = 2, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_BCGS, PNP_PREC_AMG, maxiter, smoothsteps, verbose) {}
 };
 
+struct ISTLBackend_NOVLP_BCGS_ILU0 : LinearSolverBackend {  // new (north star): SeqILU0 in the reference's row order
+  ISTLBackend_NOVLP_BCGS_ILU0(Grid& g, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_BCGS, PNP_PREC_ILU0, maxiter, 1, verbose) {}
+};
+
 // Dune::PDELab::Newton
 template <class GO, class LS> class Newton {
  public:
@@ -174,6 +179,30 @@ template <class GO, class LS> class StationaryLinearProblemSolver {
   }
  private:
   GO& go_; Vector& u_; LS& ls_; double red_;
+};
+
+// Alexander2Parameter / ImplicitEulerParameter + OneStepGridOperator<GO0,GO1> + OneStepMethod<Real,IGO,PDESOLVER,U,U>
+// (instationary_pnp_from_pb_md.hh:368-391).  The stage solver is the StationaryLinearProblemSolver the reference builds
+// with (igo, ls, 1e-5); it is folded into the method here: OneStepMethod(method, igo, ls, reduction).
+struct Alexander2Parameter { static constexpr int method = PNP_TIME_ALEXANDER2; };
+struct ImplicitEulerParameter { static constexpr int method = PNP_TIME_IMPLICIT_EULER; };
+template <class GO0, class GO1> struct OneStepGridOperator {
+  OneStepGridOperator(GO0& go0_, GO1& go1_) : go0(go0_), go1(go1_) {}
+  GO0& go0; GO1& go1;
+};
+template <class Method, class IGO, class LS> class OneStepMethod {
+ public:
+  OneStepMethod(const Method&, IGO& igo, LS& ls, double reduction) : igo_(igo), ls_(ls), red_(reduction) {}
+  void setJacobianMode(int mode, double eps = 1e-11) { mode_ = mode; eps_ = eps; }
+  // apply(time, dt, xold, f, xnew): f = boundary function interpolated to the dofs (Dirichlet values)
+  void apply(double time, double dt, const Vector& xold, const Vector& f, Vector& xnew) {
+    pnp_ctx* c = igo_.go0.grid().ctx();
+    check(c, pnp_onestep_apply(c, Method::method, igo_.go0.handle(), igo_.go1.handle(), ls_.handle(), time, dt, xold.handle(),
+                               f.handle(), xnew.handle(), red_, mode_, eps_, stage_));
+  }
+  const pnp_lin_result* stageResults() const { return stage_; }
+ private:
+  IGO& igo_; LS& ls_; double red_; int mode_ = PNP_JAC_FD_FAITHFUL; double eps_ = 1e-11; pnp_lin_result stage_[2] = {};
 };
 
 // interpolate(BCExtension<...,component,PbDGF>, gfs, u)

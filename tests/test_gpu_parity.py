@@ -546,3 +546,92 @@ def test_newton_pnp_with_ssor_and_ilu0():
         st, res = c.newton(h, vu, c.solver(capi.SOLVER_BCGS, prec, 20000, 1), c.newton_opts())
         assert res.converged and res.iterations == res_o["iterations"]
         assert np.linalg.norm(c.download(vu, 3) - u_o) <= 10 * p.sys[7] * np.linalg.norm(u_o)
+
+
+# ---- f1: OneStepMethod<Alexander2> on OneStepGridOperator<DiffusionOperator, DiffusionTOperator> ----
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("name,levels,valency,mode", [("pore_small", 1, 1.0, 0), ("pore", 0, -1.0, 0), ("cylinder", 0, 1.0, 1)])
+def test_onestep_transport_matches_oracle(name, levels, valency, mode, method):
+    """One time step of the split scheme's ion transport (instationary_pnp_from_pb_md.hh:421-425): two SDIRK stages, each a
+    StationaryLinearProblemSolver on a*M + b*dt*J0 with the default BiCGSTAB + SSOR(1) backend, reduction 1e-5."""
+    capi = _capi()
+    c, m, p = make_ctx(name, levels=levels)
+    rng = np.random.RandomState(11)
+    phi = 0.5 * np.sin(3 * m.x) * np.cos(2 * m.y)
+    g = ora.interpolate(m, p, 1, phi)            # cpB: Dirichlet values / Boltzmann profile
+    x0 = g * (1 + 0.1 * rng.uniform(-1, 1, m.nv))
+    d = ora.dirichlet(m, p, 1, 1)
+    x0[d] = g[d]
+    dt = p.sys[11]
+    h0 = c.operator(capi.OP_DIFFUSION, 1); c.operator_set_coefficient(h0, 0, c.vec(1, phi)); c.operator_set_valency(h0, valency)
+    h1 = c.operator(capi.OP_MASS, 1)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 5000, 1)
+    vx0, vg, vx1 = c.vec(1, x0), c.vec(1, g), c.vec(1)
+    res = c.onestep(h0, h1, s, dt, vx0, vg, vx1, 1e-5, method, mode)
+    x1 = c.download(vx1, 1)
+    x1_o, res_o = ora.onestep(m, p, x0, g, phi, valency, dt, 1e-5, method, jac_mode=mode, comp0=1)
+    assert len(res) == len(res_o)
+    for a, b in zip(res, res_o):
+        assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= 1
+    assert np.linalg.norm(x1 - x1_o) <= 1e-4 * np.linalg.norm(x1_o - x0) + 1e-12 * np.linalg.norm(x1_o)
+    assert np.array_equal(x1[d], g[d])           # constrained dofs carry the boundary values exactly
+    assert np.array_equal(c.download(vx0, 1), x0)  # xold is not modified
+
+
+def test_onestep_exact_in_time_for_linear_decay():
+    """Stage algebra pin: with Phi = 0 and a spatially linear state the diffusion residual vanishes in the interior of a
+    patch, so M (x1 - x0) = 0 there: a steady state stays steady through both Alexander2 stages to solver accuracy."""
+    capi = _capi()
+    c, m, p = make_ctx("cylinder")
+    x0 = 0.3 + 0.1 * m.x - 0.05 * m.y
+    h0 = c.operator(capi.OP_DIFFUSION, 1); c.operator_set_coefficient(h0, 0, c.vec(1, np.zeros(m.nv))); c.operator_set_valency(h0, 1.0)
+    h1 = c.operator(capi.OP_MASS, 1)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_ILU0, 5000, 1)
+    vx0, vx1 = c.vec(1, x0), c.vec(1)
+    c.onestep(h0, h1, s, 0.1, vx0, vx0, vx1, 1e-12, 0, 1)
+    x1 = c.download(vx1, 1)
+    x1_o, _ = ora.onestep(m, p, x0, x0, np.zeros(m.nv), 1.0, 0.1, 1e-12, 0, prec=ora.PREC_ILU0, jac_mode=1, comp0=1)
+    assert np.linalg.norm(x1 - x1_o) <= 1e-9 * np.linalg.norm(x1_o)
+
+
+@pytest.mark.parametrize("name,levels", [("pore_small", 0), ("pore", 0)])
+def test_instationary_pnp_md_time_loop_matches_oracle(name, levels):
+    """The driver the reference binary runs at HEAD (instationary_pnp_from_pb_md.hh:112-455): PB Newton -> interpolate ->
+    operator-split loop (Alexander2 transport of c+ and c-, linear Poisson update), default backend BiCGSTAB + SSOR(1),
+    FD Jacobians.  Three time steps; fields agree with the oracle's loop to the accuracy of the inexact stage solves."""
+    capi = _capi()
+    c, m, p = make_ctx(name, levels=levels)
+    tau, nsteps, upd = p.sys[11], 3, max(1, int(p.sys[14]))
+    ls = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 20000, 1)
+    hpb = c.operator(capi.OP_PB, 0)
+    vpb = c.vec(1)
+    st, rpb = c.newton(hpb, vpb, ls, c.newton_opts(jac_mode=0))
+    uphi, ucp, ucm, cpB, cmB, new = (c.vec(1) for _ in range(6))
+    c.interpolate_bcext(0, vpb, uphi)
+    c.interpolate_bcext(1, vpb, ucp); c.interpolate_bcext(1, vpb, cpB)
+    c.interpolate_bcext(2, vpb, ucm); c.interpolate_bcext(2, vpb, cmB)
+    hphi = c.operator(capi.OP_POISSON, 0)
+    c.operator_set_coefficient(hphi, 0, ucp); c.operator_set_coefficient(hphi, 1, ucm)
+    h0p, h0m = c.operator(capi.OP_DIFFUSION, 1), c.operator(capi.OP_DIFFUSION, 1)
+    c.operator_set_coefficient(h0p, 0, uphi); c.operator_set_valency(h0p, 1.0)
+    c.operator_set_coefficient(h0m, 0, uphi); c.operator_set_valency(h0m, -1.0)
+    h1 = c.operator(capi.OP_MASS, 1)
+    # oracle side
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, jac_mode=0); opts[12] = 20000
+    pb_o, rpb_o = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+    assert rpb.iterations == rpb_o["iterations"]
+    phi_o, cp_o, cm_o = (ora.interpolate(m, p, k, pb_o) for k in range(3))
+    cpB_o, cmB_o = cp_o.copy(), cm_o.copy()
+    for i in range(nsteps):
+        rs = c.onestep(h0p, h1, ls, tau, ucp, cpB, new, 1e-5); c.vec_copy(ucp, new)
+        rs += c.onestep(h0m, h1, ls, tau, ucm, cmB, new, 1e-5); c.vec_copy(ucm, new)
+        cp_o, ro = ora.onestep(m, p, cp_o, cpB_o, phi_o, 1.0, tau, 1e-5, maxit=20000, comp0=1)
+        cm_o, ro2 = ora.onestep(m, p, cm_o, cmB_o, phi_o, -1.0, tau, 1e-5, maxit=20000, comp0=1)
+        for a, b in zip(rs, ro + ro2):
+            assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= 1 + b["iterations"] // 10
+        if i % upd == 0:
+            r = c.slp(hphi, uphi, ls, 1e-10)
+            phi_o, r_o = ora.slp(m, p, ora.OP_POISSON, phi_o, 1e-10, prec=ora.PREC_SSOR, maxit=20000, aux0=cp_o, aux1=cm_o)
+            assert r.converged and r_o["converged"]
+    for v, w, tol in ((uphi, phi_o, 1e-7), (ucp, cp_o, 1e-4), (ucm, cm_o, 1e-4)):
+        assert np.linalg.norm(c.download(v, 1) - w) <= tol * np.linalg.norm(w)

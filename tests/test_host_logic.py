@@ -167,3 +167,11 @@ def test_level_scheduled_ilu0_equals_sequential_ilu0(name, levels, op):
     x = S.ilu0_apply(F, S.last_vals, d)
     x_o = ora.prec_apply(rp, col, val, d, ora.PREC_ILU0)
     assert np.linalg.norm(x - x_o) <= 1e-12 * np.linalg.norm(x_o)
+
+
+@pytest.mark.parametrize("example", ["stationary_pnp_from_pb", "instationary_pnp_md"])
+def test_facade_examples_compile(example):
+    """The PDELab-named C++ facade and the two driver rewrites compile against the C ABI header (no CUDA needed)."""
+    import subprocess
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", example + ".cc")])

@@ -180,3 +180,37 @@ def test_golden_solutions_regression(name):
     u, r = ora.newton(m, p, ora.OP_PNP, u0, opts)
     assert r0["iterations"] == int(g["pb_newton_iterations"]) and r["iterations"] == int(g["pnp_newton_iterations"])
     assert np.array_equal(pb, g["pb"]) and np.array_equal(u0, g["u0"]) and np.array_equal(u, g["u"])
+
+
+@pytest.mark.parametrize("method,order", [(0, 2), (1, 1)])
+def test_onestep_method_convergence_order_against_matrix_exponential(method, order):
+    """Pins the restated OneStepMethod stage algebra: for the linear transport problem
+    M x' = -K x the Alexander2 scheme converges with order 2 and implicit Euler with order 1 towards
+    expm(-T M^-1 K) x0 (dense reference, cylinder.msh)."""
+    import scipy.linalg
+    import scipy.sparse as sp
+    m = ora.Mesh.from_arrays(**util.load_mesh_arrays("cylinder"))
+    p = ora.Params.read(util.cfg_path("cylinder"))
+    nv = m.nv
+    phi = 0.5 * np.sin(3 * m.x) * np.cos(2 * m.y)
+    d = ora.dirichlet(m, p, 1, 1)
+    rng = np.random.RandomState(5)
+    x0 = rng.uniform(0.5, 1.5, nv); x0[d] = 0.0
+    g = np.zeros(nv)
+    rp, col, kv = ora.jacobian(m, p, ora.OP_DIFFUSION, x0, phi, valency=1.0, comp0=1, mode=1)
+    _, _, mv = ora.jacobian(m, p, ora.OP_MASS, x0, comp0=1, mode=1)
+    K = sp.csr_matrix((kv, col, rp), shape=(nv, nv)).toarray()
+    M = sp.csr_matrix((mv, col, rp), shape=(nv, nv)).toarray()
+    f = ~d
+    T = 0.4
+    exact = scipy.linalg.expm(-T * np.linalg.solve(M[np.ix_(f, f)], K[np.ix_(f, f)])) @ x0[f]
+    errs = []
+    for n in (4, 8, 16):
+        x = x0.copy()
+        for _ in range(n):
+            x, res = ora.onestep(m, p, x, g, phi, 1.0, T / n, 1e-13, method, prec=ora.PREC_ILU0, jac_mode=1, comp0=1)
+            assert all(r["converged"] for r in res)
+        assert np.all(x[d] == 0.0)
+        errs.append(np.linalg.norm(x[f] - exact))
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert abs(rates[-1] - order) < 0.25, (errs, rates)
