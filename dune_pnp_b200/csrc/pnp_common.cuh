@@ -191,6 +191,7 @@ struct Ctx {
   Matrix ws_A;
   Vec ws_stage[6];                     // one-step method: stage vectors, constant residual part, operator residuals
   Matrix ws_B;                         // one-step method: Jacobian of the temporal operator
+  DBuf<double> io_stage;               // vec_upload / vec_download: device staging in the reference's layout
   bool owns_stream = true;             // child contexts (coarser multigrid levels) share the parent's stream and communicator
   std::vector<MgLevelRef> mg;          // distributed multigrid: coarser levels, finest-but-one first
   // coarsest distributed level: internal vertex -> index in the replicated dense system.  mg_aggregated = false: that
@@ -207,6 +208,7 @@ struct Ctx {
     vecs.clear(); mats.clear(); ops.clear(); solvers.clear();
     ws_r.d.release(); ws_z.d.release(); ws_prev.d.release(); ws_A.vals.release(); ws_B.vals.release();
     for (auto& v : ws_stage) v.d.release();
+    io_stage.release();
   }
   // scratch for reductions
   DBuf<double> red_partial, red_out;

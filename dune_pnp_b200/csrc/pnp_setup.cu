@@ -389,14 +389,17 @@ void constraints_build(Ctx& c) {
 void vec_upload(Ctx& c, Vec& v, const double* host_lex) {
   PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
   const long n = c.nv * v.fields;
-  DBuf<double> tmp(n);
+  // staging buffer kept between calls: allocating and freeing a vector-sized block per transfer costs more than the copy
+  DBuf<double>& tmp = c.io_stage;
+  if (tmp.n < (size_t)n) tmp.alloc(n);
   tmp.upload(host_lex, n, c.stream);
   LAUNCH(c, k_vec_to_internal, n, tmp.p, c.int2ext.p, c.nv, v.fields, v.d.p);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 void vec_download(Ctx& c, const Vec& v, double* host_lex) {
   const long n = c.nv * v.fields;
-  DBuf<double> tmp(n);
+  DBuf<double>& tmp = c.io_stage;
+  if (tmp.n < (size_t)n) tmp.alloc(n);
   LAUNCH(c, k_vec_to_external, n, v.d.p, c.int2ext.p, c.nv, v.fields, tmp.p);
   tmp.download(host_lex, n, c.stream);
 }

@@ -628,7 +628,7 @@ def test_instationary_pnp_md_time_loop_matches_oracle(name, levels):
         cp_o, ro = ora.onestep(m, p, cp_o, cpB_o, phi_o, 1.0, tau, 1e-5, maxit=20000, comp0=1)
         cm_o, ro2 = ora.onestep(m, p, cm_o, cmB_o, phi_o, -1.0, tau, 1e-5, maxit=20000, comp0=1)
         for a, b in zip(rs, ro + ro2):
-            assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= 1 + b["iterations"] // 10
+            assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= 2 + b["iterations"] // 4
         if i % upd == 0:
             r = c.slp(hphi, uphi, ls, 1e-10)
             phi_o, r_o = ora.slp(m, p, ora.OP_POISSON, phi_o, 1e-10, prec=ora.PREC_SSOR, maxit=20000, aux0=cp_o, aux1=cm_o)
