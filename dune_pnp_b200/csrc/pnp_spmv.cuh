@@ -59,7 +59,7 @@ __device__ __forceinline__ void accumulate(const StarOpArgs& a, const SlotData<N
 }
 
 template <int NP, int EPI, int NDOT>
-__global__ void __launch_bounds__(SPMV_BLOCK) k_star_op(const StarOpArgs a) {
+__global__ void __launch_bounds__(SPMV_BLOCK, 4) k_star_op(const StarOpArgs a) {
   constexpr int F = NP == 1 ? 1 : 3;
   constexpr int L = SPMV_LANES, RPW = 32 / L; // 4 rows per group step
   const int lane = threadIdx.x & 31, sub = lane & (L - 1), grp = lane / L;
@@ -88,6 +88,27 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_star_op(const StarOpArgs a) {
         ok[h] = b[h] + sub < e[h];
         load_slot<NP>(a, b[h] + sub, ok[h], d[h]);
       }
+      // Epilogue operands are fetched NOW, together with the slot loads, by the lane that will finish component `sub`
+      // of the row (lanes 0..F-1 of the 8-lane group): their addresses only depend on the row, and loading them after
+      // the reduction would add one more dependent memory round trip to every step of this latency-bound loop.
+      double eb[2], ex[2], ew[2], ed[2], eB[2][3];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        eb[h] = ex[h] = ew[h] = ed[h] = 0.0; eB[h][0] = eB[h][1] = eB[h][2] = 0.0;
+        if (sub < F && row[h] < a.nv) {
+          const long idx = (long)F * row[h] + sub;
+          if (EPI != EPI_PLAIN) eb[h] = a.b[idx];
+          if (EPI == EPI_PLAIN && NDOT >= 1) ew[h] = a.w1[idx];
+          if (EPI == EPI_JACOBI || EPI == EPI_CHEBYSHEV) {
+            ex[h] = a.x[idx];
+            if (F == 3 && a.block) {
+              const double* B = a.dinv + 9l * row[h] + 3 * sub;
+              eB[h][0] = B[0]; eB[h][1] = B[1]; eB[h][2] = B[2];
+            } else eB[h][0] = a.dinv[idx];
+            if (EPI == EPI_CHEBYSHEV && a.c1 != 0.0) ed[h] = a.dvec[idx];
+          }
+        }
+      }
       double acc[2][F];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
@@ -114,37 +135,32 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_star_op(const StarOpArgs a) {
         for (int k = 0; k < F; k++)
 #pragma unroll
           for (int o = L / 2; o > 0; o >>= 1) acc[h][k] += __shfl_xor_sync(0xffffffffu, acc[h][k], o);
-        if (sub == 0 && row[h] < a.nv) {
-          const long i0 = (long)F * row[h];
-          if (EPI == EPI_PLAIN || EPI == EPI_RESIDUAL) {
-#pragma unroll
-            for (int k = 0; k < F; k++) {
-              const double ax = acc[h][k];
-              if (EPI == EPI_PLAIN) {
-                a.y[i0 + k] = ax;
-                if (NDOT >= 1) dsum[0] += ax * a.w1[i0 + k];
-                if (NDOT >= 2) dsum[1] += ax * ax;
-              } else a.y[i0 + k] = a.b[i0 + k] - ax;
-            }
-          } else {
-            double r[F], z[F];
-#pragma unroll
-            for (int k = 0; k < F; k++) r[k] = a.b[i0 + k] - acc[h][k];
-            if (F == 3 && a.block) {
-              const double* B = a.dinv + 9l * row[h];
-#pragma unroll
-              for (int ki = 0; ki < F; ki++) z[ki] = B[3 * ki] * r[0] + B[3 * ki + 1] * r[1 % F] + B[3 * ki + 2] * r[2 % F];
-            } else {
-#pragma unroll
-              for (int k = 0; k < F; k++) z[k] = a.dinv[i0 + k] * r[k];
-            }
-#pragma unroll
-            for (int k = 0; k < F; k++) {
-              if (EPI == EPI_JACOBI) a.y[i0 + k] = a.x[i0 + k] + a.omega * z[k];
-              else { // Chebyshev: d = c1*d + c2*M^-1 (b - A x) ; y = x + d
-                const double dn = (a.c1 != 0.0 ? a.c1 * a.dvec[i0 + k] : 0.0) + a.omega * z[k];
-                a.dvec[i0 + k] = dn; a.y[i0 + k] = a.x[i0 + k] + dn;
-              }
+        // every lane of the group now holds the row sums; lane `sub` < F finishes component `sub`
+        const double ax = F == 1 ? acc[h][0] : (sub == 0 ? acc[h][0] : (sub == 1 ? acc[h][1 % F] : acc[h][2 % F]));
+        const bool mine = sub < F && row[h] < a.nv;
+        const long idx = (long)F * row[h] + sub;
+        if (EPI == EPI_PLAIN) {
+          if (mine) {
+            a.y[idx] = ax;
+            if (NDOT >= 1) dsum[0] += ax * ew[h];
+            if (NDOT >= 2) dsum[NDOT >= 2 ? 1 : 0] += ax * ax;
+          }
+        } else if (EPI == EPI_RESIDUAL) {
+          if (mine) a.y[idx] = eb[h] - ax;
+        } else {
+          const double rr = eb[h] - ax; // component `sub` of b - A x (lanes sub < F)
+          double z;
+          if (F == 3) {
+            const int g8 = lane & ~(L - 1);
+            const double r0v = __shfl_sync(0xffffffffu, rr, g8), r1v = __shfl_sync(0xffffffffu, rr, g8 + 1),
+                         r2v = __shfl_sync(0xffffffffu, rr, g8 + 2);
+            z = a.block ? eB[h][0] * r0v + eB[h][1] * r1v + eB[h][2] * r2v : eB[h][0] * rr;
+          } else z = eB[h][0] * rr;
+          if (mine) {
+            if (EPI == EPI_JACOBI) a.y[idx] = ex[h] + a.omega * z;
+            else { // Chebyshev: d = c1*d + c2*M^-1 (b - A x) ; y = x + d
+              const double dn = (a.c1 != 0.0 ? a.c1 * ed[h] : 0.0) + a.omega * z;
+              a.dvec[idx] = dn; a.y[idx] = ex[h] + dn;
             }
           }
         }

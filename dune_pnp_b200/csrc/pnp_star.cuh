@@ -157,11 +157,13 @@ template <int OP> PNP_HD unsigned dir_bits(const StarView& M, int w, int comp0) 
   return OP == OP_PNP ? (m & 7u) : ((m >> comp0) & 1u);
 }
 
-// Assembles the block row of vertex v into vals[plane*stride + slot].
+// Assembles the block row of vertex v into vals[plane*stride + slot - sbase] (sbase != 0: `vals` is a staging tile
+// that starts at global slot sbase).
 template <int OP, int MODE>
 PNP_HD void jacobian_row(const StarView& M, const PhysParams& P, const double* u, const double* aux0,
-                         const double* aux1, double eps, int comp0, int v, double* vals, long stride) {
+                         const double* aux1, double eps, int comp0, int v, double* vals, long stride, int sbase = 0) {
   constexpr int NP = OpTraits<OP>::NPLANES;
+  vals -= sbase; // only entries [sbase, ...) of a plane are touched
   const int sd = M.rp[v], s0 = sd + 1, s1 = M.rp[v + 1];
   const unsigned rb = dir_bits<OP>(M, v, comp0);
   double diag[NP], carry[NP];
