@@ -597,11 +597,12 @@ def test_onestep_exact_in_time_for_linear_decay():
 
 # pore.cfg's tau = 1 exceeds the dielectric relaxation time 1/(4 PI l_b 2 c0): the split scheme (lagged potential) diverges
 # there within three steps -- in the oracle as well -- so the pore cases step with 0.05; one_wall.cfg's 0.1 is stable
+@pytest.mark.parametrize("red", [1e-5, 1e-12])
 @pytest.mark.parametrize("name,levels,tau", [("one_wall", 2, 0.1), ("pore_small", 0, 0.05), ("pore", 0, 0.05)])
-def test_instationary_pnp_md_time_loop_matches_oracle(name, levels, tau):
+def test_instationary_pnp_md_time_loop_matches_oracle(name, levels, tau, red):
     """The driver the reference binary runs at HEAD (instationary_pnp_from_pb_md.hh:112-455): PB Newton -> interpolate ->
     operator-split loop (Alexander2 transport of c+ and c-, linear Poisson update), default backend BiCGSTAB + SSOR(1),
-    FD Jacobians.  Three time steps: equal stage iteration counts, fields agree with the oracle's loop."""
+    FD Jacobians.  Three time steps: stage iteration counts and fields agree with the oracle's loop."""
     capi = _capi()
     c, m, p = make_ctx(name, levels=levels)
     nsteps, upd = 3, max(1, int(p.sys[14]))
@@ -625,21 +626,20 @@ def test_instationary_pnp_md_time_loop_matches_oracle(name, levels, tau):
     assert rpb.iterations == rpb_o["iterations"]
     phi_o, cp_o, cm_o = (ora.interpolate(m, p, k, pb_o) for k in range(3))
     cpB_o, cmB_o = cp_o.copy(), cm_o.copy()
-    same_path = True
     for i in range(nsteps):
-        rs = c.onestep(h0p, h1, ls, tau, ucp, cpB, new, 1e-5); c.vec_copy(ucp, new)
-        rs += c.onestep(h0m, h1, ls, tau, ucm, cmB, new, 1e-5); c.vec_copy(ucm, new)
-        cp_o, ro = ora.onestep(m, p, cp_o, cpB_o, phi_o, 1.0, tau, 1e-5, maxit=20000, comp0=1)
-        cm_o, ro2 = ora.onestep(m, p, cm_o, cmB_o, phi_o, -1.0, tau, 1e-5, maxit=20000, comp0=1)
+        rs = c.onestep(h0p, h1, ls, tau, ucp, cpB, new, red); c.vec_copy(ucp, new)
+        rs += c.onestep(h0m, h1, ls, tau, ucm, cmB, new, red); c.vec_copy(ucm, new)
+        cp_o, ro = ora.onestep(m, p, cp_o, cpB_o, phi_o, 1.0, tau, red, maxit=20000, comp0=1)
+        cm_o, ro2 = ora.onestep(m, p, cm_o, cmB_o, phi_o, -1.0, tau, red, maxit=20000, comp0=1)
         for a, b in zip(rs, ro + ro2):
             assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= 1
-            same_path = same_path and a.iterations == b["iterations"]
         if i % upd == 0:
             r = c.slp(hphi, uphi, ls, 1e-10)
             phi_o, r_o = ora.slp(m, p, ora.OP_POISSON, phi_o, 1e-10, prec=ora.PREC_SSOR, maxit=20000, aux0=cp_o, aux1=cm_o)
             assert r.converged and r_o["converged"]
-    # a stage solve stopping one half-iteration apart (the 1e-5 reduction test decided by rounding) moves the fields by the
-    # accuracy of the inexact solves; on the same Krylov path the FD Jacobians' noise (1e-5 relative) and rounding remain
-    tol = 5e-5 if same_path else 5e-4
+    # red = 1e-5 is the reference's stage reduction (instationary_pnp_from_pb_md.hh:383-386): the solves stop after ~3
+    # iterations, a half-iteration apart at times (the reduction test decided by rounding; `iterations` is rounded up), so
+    # the fields agree to the accuracy of those inexact solves.  With red = 1e-12 only rounding separates the two sides.
+    tol = 5e-4 if red > 1e-6 else 1e-7
     for v, w in ((uphi, phi_o), (ucp, cp_o), (ucm, cm_o)):
         assert np.linalg.norm(c.download(v, 1) - w) <= tol * np.linalg.norm(w)
