@@ -178,6 +178,7 @@ def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
 # N > 1: per-subdomain aggregation AMG V-cycle (no geometric levels across ranks yet; a truncated W-cycle halves the
 # iteration count but is launch-bound on the small levels: 166 its / 15.4 s vs 300 its / 4.0 s at k = 6, N = 2)
 AMG_PARTITIONED = {"amg_geometric": 0}
+EXTRA_SOLVER_OPTS = {}            # --solver-opt NAME=VALUE
 AMG_FINE = {"amg_geometric": 1}   # refinement levels as multigrid levels (P1 interpolation), aggregation below the coarsest mesh
 
 
@@ -185,7 +186,7 @@ def fine_solver(c, capi, prec_steps, options=None):
     """BiCGSTAB + multigrid for the timed step: V(nu,nu) damped Jacobi; the mesh levels created by pnp_mesh_refine are the
     upper multigrid levels (P1 interpolation, Galerkin operators), aggregation AMG continues below the Gmsh mesh."""
     s = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, prec_steps, 0)
-    for k, v in (AMG_FINE if options is None else options).items():
+    for k, v in list((AMG_FINE if options is None else options).items()) + list(EXTRA_SOLVER_OPTS.items()):
         c.solver_set_option(s, k, v)
     return s
 
@@ -334,7 +335,7 @@ def run_gpu(args, rank, world, local_rank):
                    "levels": args.levels, "dofs": gdof, "matrix_slots": gslots,
                    "rank0_owned_vertices": n_own, "rank0_ghost_vertices": nv - n_own,
                    "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the Gmsh mesh), NCCL halo exchange per multigrid level + scalar allreduce" % world,
-                   "jacobian": args.jac, "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
+                   "jacobian": args.jac, "solver_options": dict(EXTRA_SOLVER_OPTS), "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
                        "refinement levels with P1 interpolation + Galerkin operators, aggregation AMG below the Gmsh mesh" if world == 1
                        else "distributed refinement levels with P1 interpolation, re-discretised operators, replicated dense LU on the Gmsh mesh"),
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
@@ -375,8 +376,13 @@ def main():
     ap.add_argument("--jac", choices=["analytic", "fd"], default="analytic")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--solver-opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="pnp_solver_set_option for the timed step's multigrid (experiments), e.g. amg_smoother=1")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    for kv in args.solver_opt:
+        k, v = kv.split("=")
+        EXTRA_SOLVER_OPTS[k] = float(v)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

@@ -940,8 +940,21 @@ void amg_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y) {
   Amg& A = *S.amg;
   Level& l0 = *A.L[0];
   const long n = (long)A.F * l0.nv;
+  const int nu = S.prec_steps > 0 ? S.prec_steps : 1;
+  if (c.n_own == c.nv) {
+    // one GPU: the finest level works on the caller's vectors -- d is its right-hand side and y one of its two iterate
+    // buffers.  A cycle swaps the iterate buffers 2*nu - 1 times, so starting with y as the spare one the result lands in
+    // y: no vector copies around the cycle (2 x 2.3 GB of traffic per application at k = 7).
+    double *keep_b = l0.b.p, *keep_x = l0.x.p, *keep_x2 = l0.x2.p;
+    l0.b.p = const_cast<double*>(d); l0.x2.p = y;
+    cycle(c, A, 0, nu, A.comp0, true);
+    double* result = l0.x.p;
+    l0.b.p = keep_b; l0.x.p = keep_x; l0.x2.p = keep_x2;
+    if (result != y) PNP_CUDA(cudaMemcpyAsync(y, result, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    return;
+  }
   PNP_CUDA(cudaMemcpyAsync(l0.b.p, d, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-  cycle(c, A, 0, S.prec_steps > 0 ? S.prec_steps : 1, A.comp0, true);
+  cycle(c, A, 0, nu, A.comp0, true);
   PNP_CUDA(cudaMemcpyAsync(y, l0.x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 }
 

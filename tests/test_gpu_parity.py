@@ -624,7 +624,10 @@ def test_instationary_pnp_md_time_loop_matches_oracle(name, levels, tau, red):
     opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, jac_mode=0); opts[12] = 20000
     pb_o, rpb_o = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
     assert rpb.iterations == rpb_o["iterations"]
-    phi_o, cp_o, cm_o = (ora.interpolate(m, p, k, pb_o) for k in range(3))
+    pb_g = c.download(vpb, 1)
+    assert np.linalg.norm(pb_g - pb_o) <= 10 * p.sys[7] * np.linalg.norm(pb_o) + 1e-14
+    # the time loop itself is compared from the SAME initial state (the two PB solutions differ by the Newton tolerance)
+    phi_o, cp_o, cm_o = (ora.interpolate(m, p, k, pb_g) for k in range(3))
     cpB_o, cmB_o = cp_o.copy(), cm_o.copy()
     for i in range(nsteps):
         rs = c.onestep(h0p, h1, ls, tau, ucp, cpB, new, red); c.vec_copy(ucp, new)
@@ -632,7 +635,7 @@ def test_instationary_pnp_md_time_loop_matches_oracle(name, levels, tau, red):
         cp_o, ro = ora.onestep(m, p, cp_o, cpB_o, phi_o, 1.0, tau, red, maxit=20000, comp0=1)
         cm_o, ro2 = ora.onestep(m, p, cm_o, cmB_o, phi_o, -1.0, tau, red, maxit=20000, comp0=1)
         for a, b in zip(rs, ro + ro2):
-            assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= 1
+            assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= (1 if red > 1e-6 else 2)
         if i % upd == 0:
             r = c.slp(hphi, uphi, ls, 1e-10)
             phi_o, r_o = ora.slp(m, p, ora.OP_POISSON, phi_o, 1e-10, prec=ora.PREC_SSOR, maxit=20000, aux0=cp_o, aux1=cm_o)
