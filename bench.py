@@ -179,6 +179,7 @@ def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
 # iteration count but is launch-bound on the small levels: 166 its / 15.4 s vs 300 its / 4.0 s at k = 6, N = 2)
 AMG_PARTITIONED = {"amg_geometric": 0}
 EXTRA_SOLVER_OPTS = {}            # --solver-opt NAME=VALUE
+DENSE_COARSE = False              # --dense-coarse
 AMG_FINE = {"amg_geometric": 1}   # refinement levels as multigrid levels (P1 interpolation), aggregation below the coarsest mesh
 
 
@@ -214,9 +215,10 @@ def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps,
     plans = partition.build_hierarchy(a_base, world, rank, levels, all_gather=all_gather, fields_at=(coarse_level, lookup))
     uid = [capi.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    # coarsest level = the Gmsh mesh, solved exactly by a replicated dense LU (9 144 dofs, ~57 ms per Newton step); the
-    # cheaper aggregate variant (partition.aggregate_greedy) needs 8-9 Krylov iterations instead of 5
-    children = partition.setup_distributed(capi, c, plans, cfg, rank, world, uid[0], aggregates=None)
+    # coarsest distributed level = the Gmsh mesh; it is gathered to a replica of the whole Gmsh mesh on every rank, below
+    # which the one-GPU hierarchy continues (aggregation levels, small dense LU): the cycle equals the N = 1 cycle.
+    # (--dense-coarse: replicated dense LU of the 9 144-dof Gmsh system instead, ~57 ms per Newton step on every rank)
+    children = partition.setup_distributed(capi, c, plans, cfg, rank, world, uid[0], replica_mesh=None if DENSE_COARSE else a_base)
     fine = plans[-1]
     us = c.vec(3, fine.fields["u"].reshape(-1))
     if verbose:
@@ -337,7 +339,7 @@ def run_gpu(args, rank, world, local_rank):
                    "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the Gmsh mesh), NCCL halo exchange per multigrid level + scalar allreduce" % world,
                    "jacobian": args.jac, "solver_options": dict(EXTRA_SOLVER_OPTS), "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
                        "refinement levels with P1 interpolation + Galerkin operators, aggregation AMG below the Gmsh mesh" if world == 1
-                       else "distributed refinement levels with P1 interpolation, re-discretised operators, replicated dense LU on the Gmsh mesh"),
+                       else "distributed refinement levels with P1 interpolation, re-discretised operators, " + ("replicated dense LU on the Gmsh mesh" if DENSE_COARSE else "replicated aggregation AMG below the Gmsh mesh")),
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
                    "l2_policy": "inputs larger than L2 (per GPU: matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
         "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,
@@ -379,7 +381,10 @@ def main():
     ap.add_argument("--solver-opt", action="append", default=[], metavar="NAME=VALUE",
                     help="pnp_solver_set_option for the timed step's multigrid (experiments), e.g. amg_smoother=1")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--dense-coarse", action="store_true", help="N > 1: replicated dense LU on the Gmsh mesh instead of the replica hierarchy")
     args = ap.parse_args()
+    global DENSE_COARSE
+    DENSE_COARSE = args.dense_coarse
     for kv in args.solver_opt:
         k, v = kv.split("=")
         EXTRA_SOLVER_OPTS[k] = float(v)

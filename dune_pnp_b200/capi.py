@@ -207,6 +207,10 @@ class Context:
         gid = np.ascontiguousarray(gid, dtype=np.int32)
         self._ck(lib().pnp_mg_set_coarse_global(self._h, _i(gid), C.c_long(n_global)))
 
+    def mg_set_coarse_replica(self, replica, gid, n_global):
+        gid = np.ascontiguousarray(gid, dtype=np.int32)
+        self._ck(lib().pnp_mg_set_coarse_replica(self._h, replica._h, _i(gid), C.c_long(n_global)))
+
     def mg_set_coarse_aggregates(self, agg, n_agg):
         agg = np.ascontiguousarray(agg, dtype=np.int32)
         self._ck(lib().pnp_mg_set_coarse_aggregates(self._h, _i(agg), C.c_long(n_agg)))

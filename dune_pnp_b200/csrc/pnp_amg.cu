@@ -72,6 +72,9 @@ struct Amg {
   ~Amg() { if (cus) cusolverDnDestroy(cus); }
   bool distributed = false; // levels are parts of a mesh hierarchy spread over the ranks (halo exchange per level)
   DBuf<double> grhs;        // replicated coarsest level: global right-hand side / solution
+  // replica variant (Ctx::mg_replica): the coarsest distributed level is gathered to a context that holds the whole
+  // coarsest mesh; that context runs its own (single-GPU) hierarchy below: aggregation levels + small dense LU
+  std::unique_ptr<Solver> rep_solver; Matrix rep_A; Vec rep_u; DBuf<double> rep_x;
   int n_geo = 0;          // number of geometric (P1) transfers at the top of the hierarchy
   std::vector<std::unique_ptr<Level>> L;
   DBuf<unsigned char> tmp;
@@ -624,6 +627,7 @@ void coarsen_distributed(Ctx& c, Amg& A, int li, MgLevelRef& ref) {
 void dense_factor(Ctx& c, Amg& A);
 
 void dense_factor_global(Ctx& c, Amg& A);
+void replica_setup(Ctx& c, Amg& A);
 
 void numeric(Ctx& c, Amg& A, int comp0) {
   if (A.distributed) {
@@ -647,7 +651,7 @@ void numeric(Ctx& c, Amg& A, int comp0) {
       if (A.NP == 1) KL(c, k_dinv<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
       else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
     }
-    dense_factor_global(c, A);
+    if (c.mg_replica) replica_setup(c, A); else dense_factor_global(c, A);
     return;
   }
   for (size_t li = 0; li < A.L.size(); li++) {
@@ -790,6 +794,53 @@ void dense_solve_global(Ctx& c, Amg& A, Level& l) {
   c.launches += 2;
 }
 
+} // namespace
+void amg_setup(Ctx& c, Solver& S, const Matrix& M);
+void amg_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y);
+namespace {
+// replica variant of the coarsest distributed level.  Numeric setup: the injected state of that level is summed to the
+// replica (every vertex is owned by exactly one rank), the replica re-discretises its operator and sets up its own
+// hierarchy.  Solve: gather the right-hand side, one cycle of the replica's multigrid, scatter to owned + ghost vertices.
+void replica_setup(Ctx& c, Amg& A) {
+  Ctx& rc = *c.mg_replica;
+  Level& l = *A.L.back();
+  const long n = (long)A.F * c.mg_nglobal;
+  A.dense_n = (int)n; // marks the coarsest level as "solved below"
+  if (A.grhs.n != (size_t)n) { A.grhs.alloc(n); A.rep_x.alloc(n); A.rep_u.d.alloc(n); }
+  A.rep_u.fields = A.F;
+  A.rep_u.d.zero(c.stream);
+  if (A.F == 1) KL(c, k_to_global<1>, l.nv, l.u.d.p, c.mg_gid.p, l.nv, A.rep_u.d.p);
+  else KL(c, k_to_global<3>, l.nv, l.u.d.p, c.mg_gid.p, l.nv, A.rep_u.d.p);
+  allreduce_sum(c, A.rep_u.d.p, (size_t)n);
+  Operator op = c.last_op; op.aux0 = op.aux1 = -1;
+  A.rep_A.op = op.op; A.rep_A.nplanes = A.NP;
+  if (A.rep_A.vals.n != (size_t)A.NP * rc.nslots) A.rep_A.vals.alloc((size_t)A.NP * rc.nslots);
+  rc.launches = 0;
+  assemble_jacobian(rc, op, A.rep_u, A.rep_A, c.last_mode, c.last_eps);
+  if (!A.rep_solver) { A.rep_solver = std::make_unique<Solver>(); A.rep_solver->prec = PNP_PREC_AMG; }
+  auto& ro = A.rep_solver->opts;
+  ro["amg_geometric"] = 0; ro["amg_omega"] = A.omega; ro["amg_alpha"] = A.alpha; ro["amg_gamma"] = A.gamma;
+  ro["amg_dense_max"] = A.dense_max; ro["amg_coarse_sweeps"] = A.coarse_sweeps; ro["amg_smoother"] = A.smoother;
+  ro["amg_cheb_ratio"] = A.cheb_ratio;
+  amg_setup(rc, *A.rep_solver, A.rep_A);
+  c.launches += rc.launches;
+}
+void replica_solve(Ctx& c, Amg& A, Level& l, int nu) {
+  Ctx& rc = *c.mg_replica;
+  const long n = (long)A.F * c.mg_nglobal;
+  A.grhs.zero(c.stream);
+  if (A.F == 1) KL(c, k_to_global<1>, l.nv, l.b.p, c.mg_gid.p, l.nv, A.grhs.p);
+  else KL(c, k_to_global<3>, l.nv, l.b.p, c.mg_gid.p, l.nv, A.grhs.p);
+  allreduce_sum(c, A.grhs.p, (size_t)n);
+  A.rep_solver->prec_steps = nu;
+  rc.launches = 0;
+  amg_apply(rc, *A.rep_solver, A.rep_A, A.grhs.p, A.rep_x.p);
+  const int nloc = (int)l.lc->nv; // owned and ghost vertices: no halo exchange needed afterwards
+  if (A.F == 1) KL(c, k_from_global<1>, nloc, A.rep_x.p, c.mg_gid.p, nloc, l.x.p);
+  else KL(c, k_from_global<3>, nloc, A.rep_x.p, c.mg_gid.p, nloc, l.x.p);
+  c.launches += rc.launches + 2;
+}
+
 void jacobi0(Ctx& c, Amg& A, Level& l, double omega, double* dvec) {
   if (A.F == 1) KL(c, k_jacobi0<1>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
   else KL(c, k_jacobi0<3>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
@@ -831,7 +882,12 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
     smooth(c, A, l, nu, false);
     return;
   }
-  if (coarsest && A.dense_n > 0) { if (A.distributed) dense_solve_global(c, A, l); else dense_solve(c, A, l); return; }
+  if (coarsest && A.dense_n > 0) {
+    if (A.distributed && c.mg_replica) replica_solve(c, A, l, nu);
+    else if (A.distributed) dense_solve_global(c, A, l);
+    else dense_solve(c, A, l);
+    return;
+  }
   smooth(c, A, l, coarsest ? A.coarse_sweeps : nu, zero);
   if (coarsest) return;
   Level& nx = *A.L[li + 1];

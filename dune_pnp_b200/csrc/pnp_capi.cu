@@ -104,7 +104,7 @@ pnp_status pnp_mg_set_coarse_aggregates(pnp_ctx* ctx, const int* agg, long n_agg
 }
 pnp_status pnp_mg_set_coarse_global(pnp_ctx* ctx, const int* gid, long n_global) {
   API_BEGIN(ctx)
-  c.mg_aggregated = false;
+  c.mg_aggregated = false; c.mg_replica = nullptr;
   PNP_REQUIRE(!c.mg.empty() && gid && n_global > 0, PNP_E_ARG, "no multigrid level pushed");
   Ctx& k = *c.mg.back().lc;
   std::vector<int> i2e = k.int2ext.to_host(c.stream), g(k.nv);
@@ -112,6 +112,24 @@ pnp_status pnp_mg_set_coarse_global(pnp_ctx* ctx, const int* gid, long n_global)
   c.mg_gid.alloc(k.nv); c.mg_gid.upload(g.data(), k.nv, c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   c.mg_nglobal = n_global;
+  API_END
+}
+pnp_status pnp_mg_set_coarse_replica(pnp_ctx* ctx, pnp_ctx* replica, const int* gid, long n_global) {
+  API_BEGIN(ctx)
+  c.mg_aggregated = false; c.mg_replica = nullptr;
+  PNP_REQUIRE(!c.mg.empty() && gid && n_global > 0 && replica, PNP_E_ARG, "no multigrid level pushed / null arguments");
+  Ctx& k = *c.mg.back().lc;
+  Ctx& r = replica->c;
+  PNP_REQUIRE(r.finalized && r.n_own == r.nv && r.nv == n_global, PNP_E_ARG, "the replica must hold the whole coarsest mesh, finalized");
+  std::vector<int> i2e = k.int2ext.to_host(c.stream), re2i = r.ext2int.to_host(c.stream), g(k.nv);
+  for (long i = 0; i < k.nv; i++) {
+    const int gi = gid[i2e[i]];
+    PNP_REQUIRE(gi >= 0 && gi < n_global, PNP_E_ARG, "global index out of range");
+    g[i] = re2i[gi]; // straight into the replica's internal numbering: gathered vectors are the replica's vectors
+  }
+  c.mg_gid.alloc(k.nv); c.mg_gid.upload(g.data(), k.nv, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.mg_nglobal = n_global; c.mg_replica = &r;
   API_END
 }
 pnp_status pnp_profile_spmv(pnp_ctx* ctx, int enable) {

@@ -198,6 +198,7 @@ struct Ctx {
   // index is the global vertex (the level itself is solved densely); true: it is an aggregate of global vertices (the
   // level is smoothed like the others and the Galerkin aggregate system below it is the dense one)
   DBuf<int> mg_gid; long mg_nglobal = 0; bool mg_aggregated = false;
+  Ctx* mg_replica = nullptr;           // whole coarsest mesh on every rank: single-GPU multigrid below it (mg_gid maps into ITS internal numbering)
   // what the last assemble_jacobian() call linearised (coarse levels of the distributed multigrid re-discretise it)
   const double* last_u = nullptr; Operator last_op; int last_mode = 0; double last_eps = 1e-11;
   std::vector<HierLevel> hier;         // coarser refinement levels, coarsest first

@@ -238,11 +238,12 @@ def build_hierarchy(a, nparts, me, levels, all_gather=None, fields_at=None):
     return plans
 
 
-def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggregates=None):
+def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggregates=None, replica_mesh=None):
     """Creates the library-side hierarchy from build_hierarchy() plans: `root` gets the finest level, one child context
     per coarser level; returns the list of child contexts (keep them alive as long as root).  aggregates = (agg, n_agg) from
     aggregate_greedy() on the global coarsest mesh: the coarsest level is then smoothed and its aggregate system is the
-    replicated dense solve (cheap LU); None: the coarsest level itself is solved densely."""
+    replicated dense solve (cheap LU); None: the coarsest level itself is solved densely.  replica_mesh = arrays of the
+    whole coarsest mesh: the coarsest level is gathered to a replica context that runs the one-GPU multigrid below it."""
     fine = plans[-1]
     root.params_read(cfg_path)
     root.mesh_set_local(fine.n_own, fine.x, fine.y, fine.tri, fine.ba, fine.bb, fine.bphys)
@@ -258,7 +259,14 @@ def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggre
         ch.mesh_finalize(True)
         root.mg_push_level(ch, plans[l + 1].par[:, 0], plans[l + 1].par[:, 1])
         children.append(ch)
-    if aggregates is None:
+    if replica_mesh is not None:
+        # every rank also holds the WHOLE coarsest mesh: the one-GPU multigrid continues below it (redundantly)
+        rep = capi.Context(parent=root)
+        rep.mesh_set(**replica_mesh)
+        rep.mesh_finalize(True)
+        root.mg_set_coarse_replica(rep, plans[0].gid, int(plans[0].n_global))
+        children.append(rep)
+    elif aggregates is None:
         root.mg_set_coarse_global(plans[0].gid, int(plans[0].n_global))
     else:
         agg, n_agg = aggregates

@@ -93,6 +93,12 @@ pnp_status pnp_mg_set_coarse_global(pnp_ctx*, const int* global_vertex_index, lo
 /* alternative: the coarsest pushed level stays a smoothed level and the dense system is its Galerkin aggregate:
  * aggregate[v] = aggregate index of local vertex v (the same global aggregation on every rank) */
 pnp_status pnp_mg_set_coarse_aggregates(pnp_ctx*, const int* aggregate, long n_aggregates);
+/* third variant: `replica` is a child context that holds the WHOLE coarsest mesh on every rank (pnp_mesh_set +
+ * pnp_mesh_finalize on the child; global_vertex_index[v] = replica vertex of local vertex v of the coarsest pushed
+ * level).  The coarsest distributed level is then gathered to the replica (allreduce of F values per vertex) and the
+ * replica runs the single-GPU multigrid below it (aggregation levels, small dense LU) redundantly on every rank: the
+ * cycle equals the one-GPU cycle, and no rank factorises a matrix of the size of the coarsest mesh. */
+pnp_status pnp_mg_set_coarse_replica(pnp_ctx*, pnp_ctx* replica, const int* global_vertex_index, long n_global);
 /* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
 pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
 /* nested iteration: pnp_carry_set() stores vectors in reference numbering; every later pnp_mesh_refine() level

@@ -129,3 +129,37 @@ def test_distributed_multigrid_on_one_rank(op_name, F, aggregated):
     z, r = root.vec(F), root.vec(F, b)
     res = root.solve(s, A, z, r, 1e-8)
     assert res.converged and res.iterations <= (16 if aggregated else 8)
+
+
+@pytest.mark.parametrize("op_name,F", [("OP_PB", 1), ("OP_PNP", 3)])
+def test_distributed_multigrid_replica_coarse_level(op_name, F):
+    """Replica variant of the coarsest level: the distributed Gmsh level is gathered to a context holding the whole Gmsh
+    mesh, below which the one-GPU hierarchy (aggregation levels + small dense LU) runs.  One subdomain (no NCCL):
+    converges like the exact dense coarse solve, and the solution solves the assembled system."""
+    from dune_pnp_b200 import capi, partition
+    a = util.load_mesh_arrays("pore")
+    plans = partition.build_hierarchy(a, 1, 0, 2)
+    its = {}
+    for variant in ("dense", "replica"):
+        root = capi.Context(0)
+        children = partition.setup_distributed(capi, root, plans, util.cfg_path("pore"), 0, 1, None,
+                                               replica_mesh=a if variant == "replica" else None)
+        assert len(children) == (3 if variant == "replica" else 2)
+        op = getattr(capi, op_name)
+        h = root.operator(op, 0)
+        nv = root.mesh_sizes()["nv"]
+        u = root.vec(F); root.vec_set(u, 0.05)
+        A = root.matrix(h)
+        root.jacobian(h, u, A, capi.JAC_ANALYTIC, 0.0)
+        b = np.random.RandomState(0).uniform(-1, 1, F * nv)
+        b[root.constraints(h, F)] = 0.0
+        s = root.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 200, 2)
+        z, r, y = root.vec(F), root.vec(F, b), root.vec(F)
+        res = root.solve(s, A, z, r, 1e-8)
+        assert res.converged
+        its[variant] = res.iterations
+        root.spmv(A, z, y)
+        assert np.linalg.norm(root.download(y, F) - b) <= 2e-8 * np.linalg.norm(b)
+        del children
+        root.close()
+    assert its["replica"] <= its["dense"] + 4
