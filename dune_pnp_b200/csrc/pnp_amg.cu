@@ -64,6 +64,7 @@ struct Amg {
   int smoother = 0;       // 0: damped Jacobi, 1: Chebyshev on [lmax/cheb_ratio, lmax] of D^-1 A
   double cheb_ratio = 8.0;
   int comp0 = 0;
+  int pre_steps = -1, post_steps = -1; // smoothing steps before / after the coarse correction (-1: the solver's prec_steps)
   // coarsest level: dense LU (cuSOLVER getrf/getrs) when it has at most dense_max dofs, else `coarse_sweeps` sweeps
   int dense_max = 4096, dense_n = 0;
   cusolverDnHandle_t cus = nullptr;
@@ -821,7 +822,7 @@ void replica_setup(Ctx& c, Amg& A) {
   auto& ro = A.rep_solver->opts;
   ro["amg_geometric"] = 0; ro["amg_omega"] = A.omega; ro["amg_alpha"] = A.alpha; ro["amg_gamma"] = A.gamma;
   ro["amg_dense_max"] = A.dense_max; ro["amg_coarse_sweeps"] = A.coarse_sweeps; ro["amg_smoother"] = A.smoother;
-  ro["amg_cheb_ratio"] = A.cheb_ratio;
+  ro["amg_cheb_ratio"] = A.cheb_ratio; ro["amg_pre_steps"] = A.pre_steps; ro["amg_post_steps"] = A.post_steps;
   amg_setup(rc, *A.rep_solver, A.rep_A);
   c.launches += rc.launches;
 }
@@ -888,7 +889,8 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
     else dense_solve(c, A, l);
     return;
   }
-  smooth(c, A, l, coarsest ? A.coarse_sweeps : nu, zero);
+  const int nu_pre = A.pre_steps >= 0 ? A.pre_steps : nu, nu_post = A.post_steps >= 0 ? A.post_steps : nu;
+  smooth(c, A, l, coarsest ? A.coarse_sweeps : nu_pre, zero);
   if (coarsest) return;
   Level& nx = *A.L[li + 1];
   level_op<1>(c, A, l, l.x.p, l.b.p, l.r.p);
@@ -905,7 +907,7 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   const unsigned char* dm = A.distributed ? l.lc->dmask.p : (li == 0 ? c.dmask.p : nullptr);
   if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
   else KL(c, k_prolong<3>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
-  smooth(c, A, l, nu, false);
+  smooth(c, A, l, nu_post, false);
 }
 
 } // namespace
@@ -982,6 +984,7 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
   A.omega = S.opt("amg_omega", 0.7); A.gamma = (int)S.opt("amg_gamma", 1); A.wlevels = (int)S.opt("amg_wlevels", 99);
   A.coarse_sweeps = (int)S.opt("amg_coarse_sweeps", 40); A.smoother = (int)S.opt("amg_smoother", 0);
   A.cheb_ratio = S.opt("amg_cheb_ratio", 8.0);
+  A.pre_steps = (int)S.opt("amg_pre_steps", -1); A.post_steps = (int)S.opt("amg_post_steps", -1);
   numeric(c, A, comp0);
   if (timing) {
     PNP_CUDA(cudaStreamSynchronize(c.stream));
@@ -999,10 +1002,14 @@ void amg_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y) {
   const int nu = S.prec_steps > 0 ? S.prec_steps : 1;
   if (c.n_own == c.nv) {
     // one GPU: the finest level works on the caller's vectors -- d is its right-hand side and y one of its two iterate
-    // buffers.  A cycle swaps the iterate buffers 2*nu - 1 times, so starting with y as the spare one the result lands in
-    // y: no vector copies around the cycle (2 x 2.3 GB of traffic per application at k = 7).
+    // buffers.  A cycle swaps the iterate buffers (pre - 1) + post times (the first pre-smoothing step starts from zero
+    // and writes in place); y starts as the spare buffer if that count is odd, as the iterate if it is even, so the
+    // result lands in y: no vector copies around the cycle (2 x 2.3 GB of traffic per application at k = 7).
     double *keep_b = l0.b.p, *keep_x = l0.x.p, *keep_x2 = l0.x2.p;
-    l0.b.p = const_cast<double*>(d); l0.x2.p = y;
+    const int pre = A.pre_steps >= 0 ? A.pre_steps : nu, post = A.post_steps >= 0 ? A.post_steps : nu;
+    const int swaps = (pre > 0 ? pre - 1 : 0) + post;
+    l0.b.p = const_cast<double*>(d);
+    if (swaps & 1) l0.x2.p = y; else l0.x.p = y;
     cycle(c, A, 0, nu, A.comp0, true);
     double* result = l0.x.p;
     l0.b.p = keep_b; l0.x.p = keep_x; l0.x2.p = keep_x2;

@@ -171,7 +171,8 @@ pnp_status pnp_solver_create(pnp_ctx*, int kind, int prec, int maxit, int prec_s
 /* tuning knobs of the preconditioner, by name: "amg_smoother" (0 damped Jacobi, 1 Chebyshev), "amg_omega",
  * "amg_alpha" (coarse-correction scaling, dune-istl default 1.6), "amg_gamma" (1 V-cycle, 2 W-cycle), "amg_wlevels" (W on the first n levels only),
  * "amg_coarse_sweeps", "amg_dense_max" (coarsest level with at most this many dofs is solved by dense LU; 0: sweeps),
- * "amg_cheb_ratio" (lambda_max / lambda_min of the Chebyshev interval), "amg_geometric" (default 1: when
+ * "amg_cheb_ratio" (lambda_max / lambda_min of the Chebyshev interval), "amg_pre_steps" / "amg_post_steps" (smoothing
+ * steps before / after the coarse correction; default: the solver's prec_steps for both), "amg_geometric" (default 1: when
  * the mesh was refined with pnp_mesh_refine, the coarser refinement levels become multigrid levels with P1
  * interpolation and Galerkin operators; aggregation continues below the coarsest mesh) */
 pnp_status pnp_solver_set_option(pnp_ctx*, int solver, const char* name, double value);

@@ -1,6 +1,6 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -4
+# experiments on the timed step's multigrid: one bench line per variant (development aid; bench.py is the bench)
 i=0
-for v in "" "--prec-steps 1" "--prec-steps 3" "--solver-opt amg_smoother=1" "--solver-opt amg_smoother=1 --prec-steps 3" "--solver-opt amg_omega=0.8" "--prec-steps 1 --solver-opt amg_omega=0.8" "--solver-opt amg_gamma=2 --solver-opt amg_wlevels=1 --prec-steps 1"; do
+for v in "$@"; do
   i=$((i+1))
   python bench.py --no-cpu --steps 2 --warmup 3 $v > gpurun_out/var_$i.json 2> gpurun_out/var_$i.err
   python - "$v" gpurun_out/var_$i.json <<'PY'
