@@ -649,3 +649,64 @@ def test_instationary_pnp_md_time_loop_matches_oracle(name, levels, tau, red, mo
     tol = 5e-4 if mode == 0 else 1e-7
     for v, w in ((uphi, phi_o), (ucp, cp_o), (ucm, cm_o)):
         assert np.linalg.norm(c.download(v, 1) - w) <= tol * np.linalg.norm(w)
+
+
+# ---- the reference's drivers on the C++ facade (include/pnp_b200/drivers.hh, examples/) ----
+def _build_example(name, tmp_path):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / name)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", name + ".cc"), "-L", os.path.join(root, "dune_pnp_b200"), "-lpnp_b200",
+                           "-Wl,-rpath," + os.path.join(root, "dune_pnp_b200"), "-o", exe])
+    return exe
+
+
+def test_driver_instationary_pnp_md_runs_like_the_reference_binary(tmp_path):
+    """dune_pnp <cfg>: PnpSolverMain::run reads the config, the Gmsh file it names, and runs instationary_pnp_md
+    (pnp_solver_main.cc:70-116).  Five time steps of one_wall; the printed norms equal the same loop driven through the C ABI."""
+    import subprocess
+    capi = _capi()
+    a = util.load_mesh_arrays("one_wall")
+    util.write_gmsh(str(tmp_path / "one_wall.msh"), a)
+    cfg = open(util.cfg_path("one_wall")).read()
+    (tmp_path / "one_wall.cfg").write_text(cfg)
+    exe = _build_example("instationary_pnp_md", tmp_path)
+    out = subprocess.run([exe, "one_wall.cfg", "1", "5"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l.split() for l in out.stdout.splitlines() if l.startswith("step")]
+    assert len(lines) == 5
+    # the same loop through the Python mirror of the C ABI
+    c, m, p = make_ctx("one_wall", levels=1)
+    ls = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, int(p.sys[5]), 1)
+    vpb = c.vec(1)
+    c.newton(c.operator(capi.OP_PB, 0), vpb, ls, c.newton_opts(jac_mode=0))
+    uphi, ucp, ucm, cpB, cmB, new = (c.vec(1) for _ in range(6))
+    c.interpolate_bcext(0, vpb, uphi)
+    c.interpolate_bcext(1, vpb, ucp); c.interpolate_bcext(1, vpb, cpB)
+    c.interpolate_bcext(2, vpb, ucm); c.interpolate_bcext(2, vpb, cmB)
+    hphi = c.operator(capi.OP_POISSON, 0)
+    c.operator_set_coefficient(hphi, 0, ucp); c.operator_set_coefficient(hphi, 1, ucm)
+    h0p, h0m = c.operator(capi.OP_DIFFUSION, 1), c.operator(capi.OP_DIFFUSION, 1)
+    c.operator_set_coefficient(h0p, 0, uphi); c.operator_set_valency(h0p, 1.0)
+    c.operator_set_coefficient(h0m, 0, uphi); c.operator_set_valency(h0m, -1.0)
+    h1 = c.operator(capi.OP_MASS, 1)
+    for i in range(5):
+        c.onestep(h0p, h1, ls, p.sys[11], ucp, cpB, new, 1e-5); c.vec_copy(ucp, new)
+        c.onestep(h0m, h1, ls, p.sys[11], ucm, cmB, new, 1e-5); c.vec_copy(ucm, new)
+        c.slp(hphi, uphi, ls, 1e-10)
+        got = [float(lines[i][k]) for k in (6, 8, 10)]
+        want = [c.norm(uphi), c.norm(ucp), c.norm(ucm)]
+        assert np.allclose(got, want, rtol=1e-9), (i, got, want)
+
+
+@pytest.mark.parametrize("example,args", [("stationary_pnp_from_pb", ["1"]), ("stationary_pnp", [])])
+def test_driver_stationary_examples_converge(example, args, tmp_path):
+    import subprocess
+    a = util.load_mesh_arrays("cylinder")
+    util.write_gmsh(str(tmp_path / "cylinder.msh"), a)
+    exe = _build_example(example, tmp_path)
+    out = subprocess.run([exe, util.cfg_path("cylinder"), str(tmp_path / "cylinder.msh")] + args, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and "PNP Newton" in out.stdout, out.stdout + out.stderr

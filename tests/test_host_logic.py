@@ -169,7 +169,7 @@ def test_level_scheduled_ilu0_equals_sequential_ilu0(name, levels, op):
     assert np.linalg.norm(x - x_o) <= 1e-12 * np.linalg.norm(x_o)
 
 
-@pytest.mark.parametrize("example", ["stationary_pnp_from_pb", "instationary_pnp_md"])
+@pytest.mark.parametrize("example", ["stationary_pnp", "stationary_pnp_from_pb", "instationary_pnp_md"])
 def test_facade_examples_compile(example):
     """The PDELab-named C++ facade and the two driver rewrites compile against the C ABI header (no CUDA needed)."""
     import subprocess
