@@ -388,5 +388,14 @@ class Context:
                                          dirichlet_values, x_new, C.c_double(reduction), jac_mode, C.c_double(eps), res))
         return list(res)[: (1 if method == TIME_IMPLICIT_EULER else 2)]
 
+    def ion_flux(self, phi, cp, cm):
+        ns = int(self.params_get()[0][0])
+        ip = np.zeros(ns); im = np.zeros(ns)
+        self._ck(lib().pnp_ion_flux(self._h, phi, cp, cm, _d(ip), _d(im)))
+        return ip, im
+
+    def write_cell_data(self, vec, filename):
+        self._ck(lib().pnp_write_cell_data(self._h, vec, filename.encode()))
+
     def interpolate_bcext(self, component, pb_vec, out_vec):
         self._ck(lib().pnp_interpolate_bcext(self._h, component, -1 if pb_vec is None else pb_vec, out_vec))

@@ -509,6 +509,18 @@ pnp_status pnp_onestep_apply(pnp_ctx* ctx, int method, int op_space, int op_time
   if (st == PNP_E_NAN) { c.err = "non-finite residual norm in a stage solve"; return PNP_E_NAN; }
   API_END
 }
+pnp_status pnp_ion_flux(pnp_ctx* ctx, int phi, int cp, int cm, double* ip, double* im) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(ip && im, PNP_E_ARG, "null output");
+  ion_flux(c, c.vec(phi), c.vec(cp), c.vec(cm), ip, im);
+  API_END
+}
+pnp_status pnp_write_cell_data(pnp_ctx* ctx, int v, const char* filename) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(filename, PNP_E_ARG, "null file name");
+  write_cell_data(c, c.vec(v), filename);
+  API_END
+}
 pnp_status pnp_mesh_owned(pnp_ctx* ctx, long* n_own) { API_BEGIN(ctx) if (n_own) *n_own = c.n_own; API_END }
 pnp_status pnp_interpolate_bcext(pnp_ctx* ctx, int component, int pb_vec, int out_vec) {
   API_BEGIN(ctx)

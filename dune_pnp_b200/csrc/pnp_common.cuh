@@ -269,5 +269,8 @@ LinResult solver_apply(Ctx&, Solver&, const Matrix& A, Vec& z, Vec& r, double re
 void precond_apply(Ctx&, Solver&, const Matrix& A, Vec& d, Vec& v); // v = M^-1 d (setup + one application)
 // pnp_precond.cu
 int sweep_levels(const Solver&, bool ilu);
+// pnp_output.cu
+void ion_flux(Ctx&, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, double* im);
+void write_cell_data(Ctx&, const Vec& u, const std::string& filename);
 
 } // namespace pnp

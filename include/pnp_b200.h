@@ -226,6 +226,14 @@ pnp_status pnp_onestep_apply(pnp_ctx*, int method, int op_space, int op_time, in
                              int dirichlet_values, int x_new, double reduction, int jac_mode, double fd_epsilon,
                              pnp_lin_result* stage_results);
 
+/* ---- diagnostics of the time loop (instationary_pnp_from_pb_md.hh:430-452) --------------------------------- */
+/* calcIonFlux (ionFlux.hh:8-96): ip[s], im[s] = currents of the two species through surface s, s < n_surfaces; the
+ * reference appends "time ip[0] im[0] ip[1] im[1] ..." to current.dat.  With several ranks the sums run over all ranks. */
+pnp_status pnp_ion_flux(pnp_ctx*, int phi, int cp, int cm, double* ip, double* im);
+/* DataWriter::writeData (datawriter.hh:45-94): one text line per element, "x y<TAB>value<TAB>gradx grady", scientific
+ * with precision 5, in grid element order */
+pnp_status pnp_write_cell_data(pnp_ctx*, int vec_handle, const char* filename);
+
 /* ---- initial guess / Dirichlet values: interpolate(BCExtension) (dirichlet_bc.hh:54-123) --- */
 /* component 0: phi, 1: c+, 2: c-; pb_vec < 0 means a zero PB field; out is a 1-field vector */
 pnp_status pnp_interpolate_bcext(pnp_ctx*, int component, int pb_vec, int out_vec);

@@ -70,6 +70,7 @@ class Vector {
   double two_norm() const { double n; check(g_.ctx(), pnp_vec_norm(g_.ctx(), h_, &n)); return n; }
   int handle() const { return h_; }
   int fields() const { return fields_; }
+  Grid& grid() const { return g_; }
  private:
   Grid& g_; int fields_; int h_ = -1;
 };
@@ -204,6 +205,18 @@ template <class Method, class IGO, class LS> class OneStepMethod {
  private:
   IGO& igo_; LS& ls_; double red_; int mode_ = PNP_JAC_FD_FAITHFUL; double eps_ = 1e-11; pnp_lin_result stage_[2] = {};
 };
+
+// DataWriter<GV>::writeData(gfs, u, filename) (datawriter.hh:45-94) and calcIonFlux(...) (ionFlux.hh:8-96)
+inline void writeData(const Vector& u, const std::string& filename) {
+  pnp_ctx* c = u.grid().ctx();
+  check(c, pnp_write_cell_data(c, u.handle(), filename.c_str()));
+}
+inline void calcIonFlux(const Vector& uphi, const Vector& ucp, const Vector& ucm, std::vector<double>& ip, std::vector<double>& im) {
+  pnp_ctx* c = uphi.grid().ctx();
+  double sys[16]; check(c, pnp_params_get(c, sys, nullptr, nullptr, 0));
+  ip.assign((size_t)sys[0], 0.0); im.assign((size_t)sys[0], 0.0);
+  check(c, pnp_ion_flux(c, uphi.handle(), ucp.handle(), ucm.handle(), ip.data(), im.data()));
+}
 
 // interpolate(BCExtension<...,component,PbDGF>, gfs, u)
 inline void interpolate_bcext(Grid& g, int component, const Vector* pb, Vector& out) {

@@ -237,3 +237,15 @@ def onestep(mesh, params, xold, g, phi, valency, dt, reduction=1e-5, method=0, s
                            C.c_double(eps), _d(res)))
     nst = 1 if method == 1 else 2
     return xnew, [dict(converged=bool(res[2 * k]), iterations=int(res[2 * k + 1])) for k in range(nst)]
+
+
+def ion_flux(mesh, params, phi, cp, cm):
+    """calcIonFlux: (ip, im) per surface."""
+    ns = int(params.sys[0])
+    ip = np.zeros(ns); im = np.zeros(ns)
+    _chk(lib().ora_ion_flux(mesh.h, params.h, _d(_f64(phi)), _d(_f64(cp)), _d(_f64(cm)), _d(ip), _d(im)))
+    return ip, im
+
+
+def write_cell_data(mesh, u, filename):
+    _chk(lib().ora_write_cell_data(mesh.h, _d(_f64(u)), filename.encode()))

@@ -233,4 +233,11 @@ int ora_onestep(void* mh, void* ph, int comp0, int method, double dt, const doub
   ORA_CATCH(-1)
 }
 
+int ora_ion_flux(void* mh, void* ph, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
+  ORA_TRY ion_flux(*(Mesh*)mh, ((Params*)ph)->s, phi, cp, cm, ip, im); return 0; ORA_CATCH(-1)
+}
+int ora_write_cell_data(void* mh, const double* u, const char* filename) {
+  ORA_TRY write_cell_data(*(Mesh*)mh, u, filename); return 0; ORA_CATCH(-1)
+}
+
 } // extern "C"

@@ -1014,4 +1014,67 @@ inline OneStepResult onestep_apply(const Space& sp, const OpCtx& c0, const OpCtx
   return out;
 }
 
+// ----------------------------------------------------------------------------
+// Diagnostics of the time loop
+// ----------------------------------------------------------------------------
+// calcIonFlux (ionFlux.hh:8-96): element loop, intersections in iteration order, boundary intersections only (:74);
+// everything is evaluated at the intersection centre mapped into the element (:51-53).  ip, im: n_surfaces entries
+// (component 0 of the reference's FieldVectors).
+inline void ion_flux(const Mesh& m, const Sysparams& s, const double* phi, const double* cp, const double* cm,
+                     double* ip, double* im) {
+  for (int i = 0; i < s.n_surfaces; i++) { ip[i] = 0; im[i] = 0; } // :40-43
+  for (int e = 0; e < m.nT; e++) {
+    const ElemGeo g = elem_geo(m, e);
+    const int* tv = &m.tri[3 * e];
+    for (int gi = 0; gi < 3; gi++) {
+      const int f = FACE_ITER[gi];
+      const int seg = m.fseg[3 * e + f];
+      if (seg < 0) continue;
+      const int la = FACE_V[f][0], lb = FACE_V[f][1], lc = 3 - la - lb;
+      const double ax = m.x[tv[la]], ay = m.y[tv[la]], bx = m.x[tv[lb]], by = m.y[tv[lb]];
+      const double ex = 0.5 * (ax + bx), ey = 0.5 * (ay + by);            // ii->geometry().center()
+      // local = it->geometry().local(evalPos): barycentric weights (1/2, 1/2, 0) on the face's vertices
+      double w[3] = {0, 0, 0}; w[la] = 0.5; w[lb] = 0.5;
+      double vcp = 0, vcm = 0, gphi[2] = {0, 0}, gcp[2] = {0, 0}, gcm[2] = {0, 0};
+      for (int k = 0; k < 3; k++) {
+        vcp += cp[tv[k]] * w[k]; vcm += cm[tv[k]] * w[k];
+        for (int d = 0; d < 2; d++) {
+          gphi[d] += phi[tv[k]] * g.gphi[k][d]; gcp[d] += cp[tv[k]] * g.gphi[k][d]; gcm[d] += cm[tv[k]] * g.gphi[k][d];
+        }
+      }
+      const double len = std::sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
+      double factor = len;                                                // ii->geometry().volume()
+      if (s.cylindrical) factor *= 2 * s.PI * ey;                         // :63-64
+      for (int d = 0; d < 2; d++) { gcp[d] *= -factor; gcm[d] *= -factor; gphi[d] *= factor; gphi[d] *= vcp; } // :65-69
+      double nx = (by - ay) / len, ny = -(bx - ax) / len;                 // unitOuterNormal
+      if (nx * (m.x[tv[lc]] - ex) + ny * (m.y[tv[lc]] - ey) > 0) { nx = -nx; ny = -ny; }
+      const int pg = m.bphys[seg];                                        // :72
+      ip[pg] += (gcp[0] + gphi[0]) * nx + (gcp[1] + gphi[1]) * ny;        // :73
+      const double ratio = vcm / vcp;
+      for (int d = 0; d < 2; d++) gphi[d] *= ratio;                       // :78
+      im[pg] += (gcm[0] - gphi[0]) * nx + (gcm[1] - gphi[1]) * ny;        // :79
+    }
+  }
+}
+
+// DataWriter::writeData (datawriter.hh:45-94): element loop; centre, value at the centre, gradient; the stream keeps
+// precision 5 / std::scientific; FieldVector prints its components separated by blanks; the groups are tab separated.
+inline void write_cell_data(const Mesh& m, const double* u, const std::string& filename) {
+  std::ofstream out(filename.c_str(), std::ios::out);
+  out.precision(5);
+  for (int e = 0; e < m.nT; e++) {
+    const ElemGeo g = elem_geo(m, e);
+    const int* tv = &m.tri[3 * e];
+    const double cx = (g.x0 + g.x1 + g.x2) / 3.0, cy = (g.y0 + g.y1 + g.y2) / 3.0;
+    double val = 0, gr[2] = {0, 0};
+    for (int k = 0; k < 3; k++) {
+      val += u[tv[k]] / 3.0;
+      for (int d = 0; d < 2; d++) gr[d] += u[tv[k]] * g.gphi[k][d];
+    }
+    out << std::left << std::scientific << cx << " " << cy << "\t";
+    out << std::left << val << "\t";
+    out << std::left << gr[0] << " " << gr[1] << std::endl;
+  }
+}
+
 } // namespace pnpo

@@ -673,10 +673,14 @@ def test_driver_instationary_pnp_md_runs_like_the_reference_binary(tmp_path):
     cfg = open(util.cfg_path("one_wall")).read()
     (tmp_path / "one_wall.cfg").write_text(cfg)
     exe = _build_example("instationary_pnp_md", tmp_path)
-    out = subprocess.run([exe, "one_wall.cfg", "1", "5"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, "one_wall.cfg", "1", "5", "files"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = [l.split() for l in out.stdout.splitlines() if l.startswith("step")]
     assert len(lines) == 5
+    # the files the reference's loop writes (instationary_pnp_from_pb_md.hh:430-452)
+    cur = (tmp_path / "current.dat").read_text().splitlines()
+    assert len(cur) == 5 and all(len(l.split()) == 1 + 4 * 4 for l in cur)  # time + (ip, 0, im, 0) per surface
+    assert len((tmp_path / "phi005.dat").read_text().splitlines()) == 4 * len(a["tri"])
     # the same loop through the Python mirror of the C ABI
     c, m, p = make_ctx("one_wall", levels=1)
     ls = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, int(p.sys[5]), 1)
@@ -710,3 +714,33 @@ def test_driver_stationary_examples_converge(example, args, tmp_path):
     out = subprocess.run([exe, util.cfg_path("cylinder"), str(tmp_path / "cylinder.msh")] + args, capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0 and "PNP Newton" in out.stdout, out.stdout + out.stderr
+
+
+# ---- f3 / f4: the time loop's diagnostics ----
+@pytest.mark.parametrize("name,levels", [("one_wall", 1), ("cylinder", 0), ("pore", 1)])
+def test_ion_flux_matches_oracle(name, levels):
+    """calcIonFlux (ionFlux.hh:8-96): per-surface currents of both species, face by face on the device."""
+    c, m, p = make_ctx(name, levels=levels)
+    rng = np.random.RandomState(5)
+    phi = 0.4 * np.sin(0.2 * m.x) + 0.1 * m.y
+    cp = 0.06 * np.exp(-phi) * (1 + 0.05 * rng.uniform(-1, 1, m.nv)); cm = 0.06 * np.exp(phi) * (1 + 0.05 * rng.uniform(-1, 1, m.nv))
+    ip, im = c.ion_flux(c.vec(1, phi), c.vec(1, cp), c.vec(1, cm))
+    ip_o, im_o = ora.ion_flux(m, p, phi, cp, cm)
+    ip_a, im_a = ora.ion_flux(m, p, np.abs(phi), np.abs(cp), np.abs(cm))
+    scale = np.abs(ip_o).max() + np.abs(im_o).max() + np.abs(ip_a).max() + np.abs(im_a).max()
+    assert np.all(np.abs(ip - ip_o) <= 1e-11 * scale) and np.all(np.abs(im - im_o) <= 1e-11 * scale)
+    assert np.any(ip_o != 0)
+
+
+def test_write_cell_data_matches_oracle(tmp_path):
+    """DataWriter::writeData (datawriter.hh:45-94): same text file as the oracle's writer (numbers printed with 6 digits)."""
+    c, m, p = make_ctx("cylinder", levels=1)
+    u = np.cos(0.3 * m.x) * np.sin(0.2 * m.y) + 0.01 * m.x
+    c.write_cell_data(c.vec(1, u), str(tmp_path / "gpu.dat"))
+    ora.write_cell_data(m, u, str(tmp_path / "ora.dat"))
+    a = open(tmp_path / "gpu.dat").read().splitlines(); b = open(tmp_path / "ora.dat").read().splitlines()
+    assert len(a) == len(b) == m.nT
+    assert all(la.count("\t") == 2 and len(la.split()) == 5 for la in a)
+    A = np.array([[float(t) for t in l.split()] for l in a]); B = np.array([[float(t) for t in l.split()] for l in b])
+    assert np.allclose(A, B, rtol=2e-5, atol=1e-12)
+    assert sum(la == lb for la, lb in zip(a, b)) >= 0.99 * len(a)  # identical text up to last-digit rounding ties

@@ -214,3 +214,44 @@ def test_onestep_method_convergence_order_against_matrix_exponential(method, ord
         errs.append(np.linalg.norm(x[f] - exact))
     rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
     assert abs(rates[-1] - order) < 0.25, (errs, rates)
+
+
+def test_ion_flux_pins():
+    """calcIonFlux restatement (ionFlux.hh:8-96): (1) constant concentrations and a linear potential on a planar mesh: the
+    surface currents sum to zero over the closed boundary (divergence theorem, exact for P1); (2) ip of c+ = exp(+phi)-like
+    equilibrium vanishes to discretisation accuracy and im is insensitive to c+."""
+    m = ora.Mesh.from_arrays(**util.load_mesh_arrays("cylinder"))
+    p = ora.Params.read(util.cfg_path("cylinder"))
+    assert p.sys[1] == 0  # planar
+    phi = 0.3 * m.x - 0.2 * m.y
+    c = np.full(m.nv, 0.06)
+    ip, im = ora.ion_flux(m, p, phi, c, c)
+    scale = 0.06 * np.hypot(0.3, 0.2) * (m.x.max() - m.x.min() + m.y.max() - m.y.min())
+    assert abs(ip.sum()) <= 1e-12 * scale and abs(im.sum()) <= 1e-12 * scale
+    assert np.allclose(ip, -im, rtol=0, atol=1e-13 * scale)  # ip = c grad(phi).n, im = -c grad(phi).n
+    # linearity in the potential at fixed concentrations
+    ip2, im2 = ora.ion_flux(m, p, 2 * phi, c, c)
+    assert np.allclose(ip2, 2 * ip, rtol=1e-12, atol=1e-15) and np.allclose(im2, 2 * im, rtol=1e-12, atol=1e-15)
+    # pure diffusion: phi = 0 -> ip = -grad(c+).n summed, independent of c-
+    cp = 0.06 * (1 + 0.1 * m.x)
+    ip3, _ = ora.ion_flux(m, p, 0 * phi, cp, c)
+    ip4, _ = ora.ion_flux(m, p, 0 * phi, cp, 3 * c)
+    assert np.array_equal(ip3, ip4) and abs(ip3.sum()) <= 1e-12 * scale  # grad(c+) constant: closed-surface sum vanishes
+
+
+def test_write_cell_data_format(tmp_path):
+    """DataWriter::writeData (datawriter.hh:45-94): one line per element, 'x y<TAB>value<TAB>gx gy', %.5e."""
+    m = ora.Mesh.from_arrays(**util.load_mesh_arrays("one_wall"))
+    u = 0.5 * m.x - 0.25 * m.y + 1.0
+    fn = str(tmp_path / "phi.dat")
+    ora.write_cell_data(m, u, fn)
+    lines = open(fn).read().splitlines()
+    assert len(lines) == m.nT
+    import re
+    num = r"-?\d\.\d{5}e[+-]\d{2}"
+    pat = re.compile("^%s %s\t%s\t%s %s$" % (num, num, num, num, num))
+    assert all(pat.match(l) for l in lines)
+    first = [float(t) for t in lines[0].replace("\t", " ").split()]
+    tri0 = m.tri[0]
+    assert np.allclose(first[:2], [m.x[tri0].mean(), m.y[tri0].mean()], rtol=1e-5)
+    assert np.allclose(first[2], u[tri0].mean(), rtol=1e-5) and np.allclose(first[3:], [0.5, -0.25], rtol=1e-5)
