@@ -305,6 +305,15 @@ def run_gpu(args, rank, world, local_rank):
         step(True)
     barrier()
     wall_e2e = time.perf_counter() - t0
+    # ---- the two flavours of jacobian_volume, one launch each on the step's state (outside the timed step): the step uses
+    # the exact derivative; the reference's NumericalJacobianVolume replay (FD-faithful) is reported beside it ----
+    A2 = c.matrix(h)
+    jac_ms = {}
+    for name_, mode_ in (("analytic", capi.JAC_ANALYTIC), ("fd_faithful", capi.JAC_FD_FAITHFUL)):
+        c.jacobian(h, us, A2, mode_, 1e-11)
+        barrier()
+        c.timer_start(); c.jacobian(h, us, A2, mode_, 1e-11); jac_ms[name_] = c.timer_stop()
+    c.matrix_destroy(A2)
     tmax = torch.tensor([ms_dev / 1e3, wall, wall_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -343,6 +352,7 @@ def run_gpu(args, rank, world, local_rank):
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
                    "l2_policy": "inputs larger than L2 (per GPU: matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
         "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,
+        "jacobian_ms": jac_ms, "newton_step_s_with_fd_jacobian": sec_step + (jac_ms["fd_faithful"] - jac_ms["analytic"]) / 1e3,
         "krylov_iterations": int(r.linear_iterations), "line_search_trials": int(r.line_search_trials),
         "defect_before": r.first_defect, "defect_after": r.defect,
         "spmv_gbs": achieved, "spmv_launches_timed": n_spmv,

@@ -187,26 +187,46 @@ __global__ void k_galerkin(const int* __restrict__ seg_ptr, const int* __restric
     double acc[NP];
 #pragma unroll
     for (int p = 0; p < NP; p++) acc[p] = 0.0;
-    for (int t = seg_ptr[cs]; t < seg_ptr[cs + 1]; t++) {
-      const int s = seg_items[t];
-      double v[NP];
+    // items are taken four at a time: the four slot indices first, then all 4*NP value loads, so that the scattered
+    // gathers of one thread overlap (a coarse slot of a refinement level has ~12 items; one at a time the loop is a
+    // chain of dependent index -> value round trips).  The summation order is the item order, as before.
+    constexpr int U = 4;
+    const int t1 = seg_ptr[cs + 1];
+    for (int t0 = seg_ptr[cs]; t0 < t1; t0 += U) {
+      int s[U]; double w[U]; double v[U][NP];
 #pragma unroll
-      for (int p = 0; p < NP; p++) v[p] = vf[p * nsf + s];
+      for (int q = 0; q < U; q++) {
+        const bool ok = t0 + q < t1;
+        s[q] = ok ? seg_items[t0 + q] : -1;
+        const unsigned char wc = (ok && seg_w) ? seg_w[t0 + q] : 0;
+        w[q] = ok ? (wc == 0 ? 1.0 : (wc == 1 ? 0.5 : 0.25)) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < U; q++)
+#pragma unroll
+        for (int p = 0; p < NP; p++) v[q][p] = s[q] >= 0 ? vf[p * nsf + s[q]] : 0.0;
       if (dmask) { // level 0: skip the unit diagonal of constrained dofs (slot s is a diagonal slot iff s == rp[col[s]])
-        const unsigned w = colf[s] & STAR_VMASK;
-        const unsigned m = dmask[w];
-        if (m && rpf[w] == s) {
-          if (NP == 1) { if ((m >> comp0) & 1u) v[0] = 0.0; }
-          else {
-            if (m & 1u) v[0] = 0.0;
-            if (m & 2u) v[NP == 7 ? 4 : 0] = 0.0;
-            if (m & 4u) v[NP == 7 ? 6 : 0] = 0.0;
+#pragma unroll
+        for (int q = 0; q < U; q++) {
+          if (s[q] < 0) continue;
+          const unsigned wv = colf[s[q]] & STAR_VMASK;
+          const unsigned m = dmask[wv];
+          if (m && rpf[wv] == s[q]) {
+            if (NP == 1) { if ((m >> comp0) & 1u) v[q][0] = 0.0; }
+            else {
+              if (m & 1u) v[q][0] = 0.0;
+              if (m & 2u) v[q][NP == 7 ? 4 : 0] = 0.0;
+              if (m & 4u) v[q][NP == 7 ? 6 : 0] = 0.0;
+            }
           }
         }
       }
-      const double w = seg_w ? (seg_w[t] == 0 ? 1.0 : (seg_w[t] == 1 ? 0.5 : 0.25)) : 1.0;
 #pragma unroll
-      for (int p = 0; p < NP; p++) acc[p] += w * v[p];
+      for (int q = 0; q < U; q++)
+        if (s[q] >= 0) {
+#pragma unroll
+          for (int p = 0; p < NP; p++) acc[p] += w[q] * v[q][p];
+        }
     }
 #pragma unroll
     for (int p = 0; p < NP; p++) vc[p * nsc + cs] = acc[p];
