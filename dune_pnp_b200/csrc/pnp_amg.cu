@@ -49,6 +49,13 @@ struct Level {
   // levels are re-discretised on it from the injected state u
   Ctx* lc = nullptr;
   Vec u; Matrix Amat;
+  // Dirichlet mask of the level's OWN vertices: level 0, distributed levels and re-discretised geometric levels keep
+  // their constrained dofs (identity rows); null for Galerkin / aggregation levels, which carry none of their own
+  const unsigned char* dm = nullptr;
+  // geometric level of a one-GPU hierarchy whose operator is re-discretised on its own star (coordinates and mask
+  // gathered from the finest level, state u injected) instead of the Galerkin product
+  bool redisc = false;
+  DBuf<XY> xy_own; DBuf<unsigned char> dmask_own;
 };
 
 } // namespace
@@ -72,6 +79,7 @@ struct Amg {
   DBuf<int> dense_piv, dense_info;
   ~Amg() { if (cus) cusolverDnDestroy(cus); }
   bool distributed = false; // levels are parts of a mesh hierarchy spread over the ranks (halo exchange per level)
+  bool redisc = false;      // one GPU: the geometric levels are re-discretised (as the distributed levels are), not Galerkin products
   DBuf<double> grhs;        // replicated coarsest level: global right-hand side / solution
   // replica variant (Ctx::mg_replica): the coarsest distributed level is gathered to a context that holds the whole
   // coarsest mesh; that context runs its own (single-GPU) hierarchy below: aggregation levels + small dense LU
@@ -338,6 +346,15 @@ __global__ void k_prolong(const int* __restrict__ agg, const int* __restrict__ p
         x[(long)F * v + k] += alpha * (J >= 0 ? 0.5 * (xc[F * I + k] + xc[F * J + k]) : xc[F * I + k]);
   }
 }
+// coordinates and Dirichlet mask of a coarser refinement level: a coarse vertex IS a finest-level vertex (same reference index)
+__global__ void k_level_geometry(const int* __restrict__ int2ext_c, const int* __restrict__ ext2int_f, const XY* __restrict__ xy_f,
+                                 const unsigned char* __restrict__ dmask_f, int nvc, XY* __restrict__ xy_c,
+                                 unsigned char* __restrict__ dmask_c) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvc; i += gridDim.x * blockDim.x) {
+    const int j = ext2int_f[int2ext_c[i]];
+    xy_c[i] = xy_f[j]; dmask_c[i] = dmask_f[j];
+  }
+}
 // ---- geometric levels: P1 interpolation between two consecutive refinement levels ----
 // parents of every fine vertex, both in the internal numbering of their level
 __global__ void k_geo_parents(const int* __restrict__ int2ext_f, int nvf, int nvc, const uint64_t* __restrict__ edges,
@@ -555,7 +572,7 @@ bool coarsen(Ctx& c, Amg& A, int li) {
 }
 
 // builds level li+1 from the refinement hierarchy: coarse star = that mesh level's star, P = P1 interpolation
-void coarsen_geometric(Ctx& c, Amg& A, int li, const HierLevel& h, const int* int2ext_f) {
+void coarsen_geometric(Ctx& c, Amg& A, int li, const HierLevel& h, const int* int2ext_f, bool redisc) {
   Level& f = *A.L[li];
   const int nvf = f.nv, nvc = (int)h.nv;
   size_t bytes = 0;
@@ -577,7 +594,13 @@ void coarsen_geometric(Ctx& c, Amg& A, int li, const HierLevel& h, const int* in
   }
   auto nl = std::make_unique<Level>();
   nl->nv = nvc; nl->nslots = h.nslots; nl->rp = h.rp.p; nl->col = h.adj.p;
-  { // Galerkin gather lists
+  nl->redisc = redisc;
+  if (redisc) {
+    nl->xy_own.alloc(nvc); nl->dmask_own.alloc(nvc);
+    KL(c, k_level_geometry, nvc, h.int2ext.p, c.ext2int.p, c.xy.p, c.dmask.p, nvc, nl->xy_own.p, nl->dmask_own.p);
+    nl->dm = nl->dmask_own.p;
+    nl->u.fields = A.F; nl->u.d.alloc((size_t)A.F * nvc);
+  } else { // Galerkin gather lists
     const long n4 = 4 * f.nslots;
     PNP_REQUIRE(n4 < (1l << 31) && f.nslots < (1l << 29), PNP_E_MESH, "multigrid: too many matrix slots on one level");
     DBuf<int> key(n4), skey(n4), err(1);
@@ -638,6 +661,7 @@ void coarsen_distributed(Ctx& c, Amg& A, int li, MgLevelRef& ref) {
   f.alpha = 1.0;
   auto nl = std::make_unique<Level>();
   nl->lc = &kc; nl->nv = nvc; nl->nslots = kc.nslots; nl->rp = kc.rp.p; nl->col = kc.adj.p;
+  nl->dm = kc.dmask.p;
   nl->u.fields = A.F; nl->u.d.alloc((size_t)A.F * kc.nv); nl->u.d.zero(c.stream);
   nl->Amat.op = A.NP == 7 ? OP_PNP : OP_PB; nl->Amat.nplanes = A.NP;
   nl->Amat.vals.alloc((size_t)A.NP * kc.nslots);
@@ -649,6 +673,27 @@ void dense_factor(Ctx& c, Amg& A);
 
 void dense_factor_global(Ctx& c, Amg& A);
 void replica_setup(Ctx& c, Amg& A);
+
+// matrix values of level li+1 from level li (one-GPU hierarchy): re-discretisation at the injected state for a `redisc`
+// geometric level, else the Galerkin product P^T A P by deterministic gathers.  uf = state on level li (only followed
+// through re-discretised levels); returns the state on level li+1.
+const double* level_values(Ctx& c, Amg& A, int li, const double* uf, int comp0) {
+  Level& l = *A.L[li]; Level& n = *A.L[li + 1];
+  if (n.redisc) {
+    if (A.F == 1) KL(c, k_inject<1>, l.nv, l.agg.p, l.par1.p, l.nv, uf, n.u.d.p);
+    else KL(c, k_inject<3>, l.nv, l.agg.p, l.par1.p, l.nv, uf, n.u.d.p);
+    Operator op = c.last_op; op.aux0 = op.aux1 = -1;
+    assemble_jacobian_on(c, StarView{n.rp, n.col, n.xy_own.p, n.dmask_own.p, n.nv}, n.nslots, op, n.u.d.p, n.vals_own.p,
+                         c.last_mode, c.last_eps);
+    return n.u.d.p;
+  }
+  // constrained dofs of the finer level are left out of the product (only their unit diagonal has to be skipped)
+  if (A.NP == 1)
+    KL(c, k_galerkin<1>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, l.dm, l.col, l.rp, comp0);
+  else
+    KL(c, k_galerkin<7>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, l.dm, l.col, l.rp, comp0);
+  return nullptr;
+}
 
 void numeric(Ctx& c, Amg& A, int comp0) {
   if (A.distributed) {
@@ -675,16 +720,10 @@ void numeric(Ctx& c, Amg& A, int comp0) {
     if (c.mg_replica) replica_setup(c, A); else dense_factor_global(c, A);
     return;
   }
+  const double* uf = c.last_u;
   for (size_t li = 0; li < A.L.size(); li++) {
     Level& l = *A.L[li];
-    if (li + 1 < A.L.size()) {
-      Level& n = *A.L[li + 1];
-      const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
-      if (A.NP == 1)
-        KL(c, k_galerkin<1>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, dm, l.col, l.rp, comp0);
-      else
-        KL(c, k_galerkin<7>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, dm, l.col, l.rp, comp0);
-    }
+    if (li + 1 < A.L.size()) uf = level_values(c, A, (int)li, uf, comp0);
     if (A.NP == 1) KL(c, k_dinv<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
     else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
   }
@@ -917,14 +956,14 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   if (A.distributed) halo_exchange(*l.lc, l.r.p, A.F); // children of an owned coarse vertex may be ghosts here
   if (A.F == 1) KL(c, k_restrict<1>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
   else KL(c, k_restrict<3>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
-  if (A.distributed) { // re-discretised coarse levels carry their own Dirichlet rows: no residual into them
-    if (A.F == 1) KL(c, k_mask_dirichlet<1>, nx.nv, nx.b.p, nx.lc->dmask.p, nx.nv, comp0);
-    else KL(c, k_mask_dirichlet<3>, nx.nv, nx.b.p, nx.lc->dmask.p, nx.nv, comp0);
+  if (nx.dm) { // re-discretised coarse levels carry their own Dirichlet rows: no residual into them
+    if (A.F == 1) KL(c, k_mask_dirichlet<1>, nx.nv, nx.b.p, nx.dm, nx.nv, comp0);
+    else KL(c, k_mask_dirichlet<3>, nx.nv, nx.b.p, nx.dm, nx.nv, comp0);
   }
   const int visits = li < A.wlevels ? A.gamma : 1;
   for (int g = 0; g < visits; g++) cycle(c, A, li + 1, nu, comp0, g == 0);
   if (A.distributed && !(li + 2 == (int)A.L.size() && A.dense_n > 0 && !c.mg_aggregated)) halo_exchange(*nx.lc, nx.x.p, A.F); // parents may be ghosts
-  const unsigned char* dm = A.distributed ? l.lc->dmask.p : (li == 0 ? c.dmask.p : nullptr);
+  const unsigned char* dm = l.dm; // constrained dofs of this level receive no correction
   if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
   else KL(c, k_prolong<3>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
   smooth(c, A, l, nu_post, false);
@@ -937,7 +976,12 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
   Amg& A = *S.amg;
   const int comp0 = M.comp0;
   A.comp0 = comp0;
-  if (!A.symbolic || A.NP != M.nplanes || A.nv0 != c.n_own || A.nslots0 != c.nslots) {
+  // one GPU with refinement levels: re-discretise the coarse operators (cheaper than the Galerkin gathers by an order of
+  // magnitude, and what the distributed hierarchy does) when M is the plain Jacobian of the last assembly
+  const bool want_redisc = S.opt("amg_geometric", 1) != 0 && S.opt("amg_rediscretise", 1) != 0 && c.n_own == c.nv &&
+                           !c.hier.empty() && c.mg.empty() && c.last_u && c.last_vals == M.vals.p &&
+                           (M.op == OP_PB || M.op == OP_PNP || M.op == OP_MASS);
+  if (!A.symbolic || A.NP != M.nplanes || A.nv0 != c.n_own || A.nslots0 != c.nslots || A.redisc != want_redisc) {
     A.L.clear();
     A.NP = M.nplanes; A.F = M.nplanes == 1 ? 1 : 3;
     A.nv0 = c.n_own; A.nslots0 = c.nslots;
@@ -946,6 +990,8 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
     A.L.push_back(std::move(l0));
     A.alpha = S.opt("amg_alpha", 1.6);
     A.L[0]->lc = &c;
+    A.L[0]->dm = c.dmask.p;
+    A.redisc = want_redisc;
     A.distributed = S.opt("amg_geometric", 1) != 0 && !c.mg.empty() && c.mg_nglobal > 0 &&
                     (M.op == OP_PB || M.op == OP_PNP || M.op == OP_MASS);
     if (A.distributed) {
@@ -957,16 +1003,12 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
     if (!A.distributed) A.n_geo = 0;
     if (geometric) {
       const int* i2e = c.int2ext.p;
+      const double* uf = c.last_u;
       for (int hi = (int)c.hier.size() - 1; hi >= 0; hi--) {
         const int li = (int)A.L.size() - 1;
-        coarsen_geometric(c, A, li, c.hier[hi], i2e);
+        coarsen_geometric(c, A, li, c.hier[hi], i2e, A.redisc);
         i2e = c.hier[hi].int2ext.p;
-        Level& f = *A.L[li]; Level& n = *A.L[li + 1];
-        const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
-        if (A.NP == 1)
-          KL(c, k_galerkin<1>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
-        else
-          KL(c, k_galerkin<7>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
+        uf = level_values(c, A, li, uf, comp0); // the aggregation below needs the numeric values
         A.n_geo++;
       }
     }
@@ -976,12 +1018,7 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
       if (A.L[li]->nv <= 64 || (long)A.F * A.L[li]->nv <= A.dense_max) break;
       if (!coarsen(c, A, li)) break;
       // numeric values of the new level are needed before it can be coarsened further
-      Level& f = *A.L[li]; Level& n = *A.L[li + 1];
-      const unsigned char* dm = li == 0 ? c.dmask.p : nullptr;
-      if (A.NP == 1)
-        KL(c, k_galerkin<1>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
-      else
-        KL(c, k_galerkin<7>, n.nslots, f.seg_ptr.p, f.seg_items.p, f.seg_w.p, n.nslots, f.vals, f.nslots, n.vals_own.p, dm, f.col, f.rp, comp0);
+      level_values(c, A, li, nullptr, comp0);
     }
     for (auto& l : A.L) alloc_work(c, A, *l);
     if (!A.distributed) { // level 0 iterates are SpMV inputs whose ghost columns must read as zero

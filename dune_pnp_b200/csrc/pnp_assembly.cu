@@ -15,7 +15,8 @@
 namespace pnp {
 
 // implemented in the other compilation of this file
-void launch_jacobian_fd(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps);
+void launch_jacobian_fd(Ctx& c, const StarView& M, const Operator& op, const double* u, const double* a0, const double* a1,
+                        double* vals, long stride, double eps);
 
 namespace {
 
@@ -51,9 +52,10 @@ k_jacobian(StarView M, PhysParams P, const double* __restrict__ u, const double*
   }
 }
 
+// M: the star to assemble on -- the context's own (finest) one, or a coarser refinement level's (multigrid)
 template <int OP, int MODE>
-void launch_jac(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps) {
-  const StarView M = c.star();
+void launch_jac(Ctx& c, const StarView& M, const Operator& op, const double* u, const double* a0, const double* a1,
+                double* vals, long stride, double eps) {
   const PhysParams P = c.phys(op.valency);
   const int smem = OpTraits<OP>::NPLANES * JAC_CAP * (int)sizeof(double);
   static bool configured = false; // per instantiation
@@ -61,18 +63,19 @@ void launch_jac(Ctx& c, const Operator& op, const double* u, const double* a0, c
     PNP_CUDA(cudaFuncSetAttribute(k_jacobian<OP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = grid_for(c.n_own, JAC_CHUNK, c.sm_count * 16);
-  k_jacobian<OP, MODE><<<grid, JAC_CHUNK, smem, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, A.vals.p, c.nslots);
+  const int grid = grid_for(M.nv, JAC_CHUNK, c.sm_count * 16);
+  k_jacobian<OP, MODE><<<grid, JAC_CHUNK, smem, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, vals, stride);
   PNP_CHECK_LAUNCH(); c.launches++;
 }
 template <int MODE>
-void dispatch_jac(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps) {
+void dispatch_jac(Ctx& c, const StarView& M, const Operator& op, const double* u, const double* a0, const double* a1,
+                  double* vals, long stride, double eps) {
   switch (op.op) {
-    case OP_PB: launch_jac<OP_PB, MODE>(c, op, u, a0, a1, A, eps); break;
-    case OP_POISSON: launch_jac<OP_POISSON, MODE>(c, op, u, a0, a1, A, eps); break;
-    case OP_DIFFUSION: launch_jac<OP_DIFFUSION, MODE>(c, op, u, a0, a1, A, eps); break;
-    case OP_MASS: launch_jac<OP_MASS, MODE>(c, op, u, a0, a1, A, eps); break;
-    case OP_PNP: launch_jac<OP_PNP, MODE>(c, op, u, a0, a1, A, eps); break;
+    case OP_PB: launch_jac<OP_PB, MODE>(c, M, op, u, a0, a1, vals, stride, eps); break;
+    case OP_POISSON: launch_jac<OP_POISSON, MODE>(c, M, op, u, a0, a1, vals, stride, eps); break;
+    case OP_DIFFUSION: launch_jac<OP_DIFFUSION, MODE>(c, M, op, u, a0, a1, vals, stride, eps); break;
+    case OP_MASS: launch_jac<OP_MASS, MODE>(c, M, op, u, a0, a1, vals, stride, eps); break;
+    case OP_PNP: launch_jac<OP_PNP, MODE>(c, M, op, u, a0, a1, vals, stride, eps); break;
     default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
   }
 }
@@ -81,8 +84,9 @@ void dispatch_jac(Ctx& c, const Operator& op, const double* u, const double* a0,
 
 #ifdef PNP_ASM_FAITHFUL
 
-void launch_jacobian_fd(Ctx& c, const Operator& op, const double* u, const double* a0, const double* a1, Matrix& A, double eps) {
-  dispatch_jac<JAC_FD_FAITHFUL>(c, op, u, a0, a1, A, eps);
+void launch_jacobian_fd(Ctx& c, const StarView& M, const Operator& op, const double* u, const double* a0, const double* a1,
+                        double* vals, long stride, double eps) {
+  dispatch_jac<JAC_FD_FAITHFUL>(c, M, op, u, a0, a1, vals, stride, eps);
 }
 
 #else
@@ -172,10 +176,20 @@ void assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, 
   const double *a0, *a1;
   coefficient_ptrs(c, op, &a0, &a1);
   A.comp0 = op.comp0;
-  c.last_u = u.d.p; c.last_op = op; c.last_mode = mode; c.last_eps = eps;
+  c.last_u = u.d.p; c.last_op = op; c.last_mode = mode; c.last_eps = eps; c.last_vals = A.vals.p;
   halo_exchange(c, u.d.p, u.fields);
-  if (mode == JAC_FD_FAITHFUL) launch_jacobian_fd(c, op, u.d.p, a0, a1, A, eps);
-  else dispatch_jac<JAC_ANALYTIC>(c, op, u.d.p, a0, a1, A, eps);
+  if (mode == JAC_FD_FAITHFUL) launch_jacobian_fd(c, c.star(), op, u.d.p, a0, a1, A.vals.p, c.nslots, eps);
+  else dispatch_jac<JAC_ANALYTIC>(c, c.star(), op, u.d.p, a0, a1, A.vals.p, c.nslots, eps);
+}
+
+// The same operator on another star of the same mesh hierarchy (a coarser refinement level held by the multigrid):
+// u in that level's numbering, vals = NPLANES planes of `stride` slots.  Operators with coefficient fields are not
+// supported here (their coefficients live on the finest level only).
+void assemble_jacobian_on(Ctx& c, const StarView& M, long stride, const Operator& op, const double* u, double* vals, int mode,
+                          double eps) {
+  PNP_REQUIRE(op.op == OP_PB || op.op == OP_PNP || op.op == OP_MASS, PNP_E_ARG, "no coefficient fields on coarse levels");
+  if (mode == JAC_FD_FAITHFUL) launch_jacobian_fd(c, M, op, u, nullptr, nullptr, vals, stride, eps);
+  else dispatch_jac<JAC_ANALYTIC>(c, M, op, u, nullptr, nullptr, vals, stride, eps);
 }
 
 #endif // PNP_ASM_FAITHFUL

@@ -201,6 +201,7 @@ struct Ctx {
   Ctx* mg_replica = nullptr;           // whole coarsest mesh on every rank: single-GPU multigrid below it (mg_gid maps into ITS internal numbering)
   // what the last assemble_jacobian() call linearised (coarse levels of the distributed multigrid re-discretise it)
   const double* last_u = nullptr; Operator last_op; int last_mode = 0; double last_eps = 1e-11;
+  const double* last_vals = nullptr;   // ... and the matrix values it wrote (reset when they are combined into something else)
   std::vector<HierLevel> hier;         // coarser refinement levels, coarsest first
   std::vector<Vec> carry;              // nodal fields in reference numbering, interpolated by mesh_refine()
   // a new / refined mesh invalidates every object sized by it
@@ -257,6 +258,7 @@ void interpolate_bcext(Ctx&, int comp, const Vec* pb, Vec& out);
 // pnp_assembly.cu
 void assemble_residual(Ctx&, const Operator&, Vec& u, Vec& r);   // refreshes the ghost part of u
 void assemble_jacobian(Ctx&, const Operator&, Vec& u, Matrix& A, int mode, double eps);
+void assemble_jacobian_on(Ctx&, const StarView& M, long stride, const Operator&, const double* u, double* vals, int mode, double eps);
 // pnp_linalg.cu
 void spmv(Ctx&, const Matrix& A, double* x, double* y); // refreshes the ghost part of x
 double vec_norm(Ctx&, const double* x, long n);

@@ -230,6 +230,7 @@ int onestep_apply(Ctx& c, int method, const Operator& op0, const Operator& op1, 
     k_stage_matrix<<<gs, 256, 0, c.stream>>>(A.vals.p, B.vals.p, br * dt, ar, c.nslots);
     k_unit_dirichlet_diag<<<gv, 256, 0, c.stream>>>(c.rp.p, c.dmask.p, comp, (int)n, A.vals.p);
     PNP_CHECK_LAUNCH(); c.launches += 2;
+    c.last_vals = nullptr; // A is a combination now: a multigrid must not re-discretise `op0` for it
     assemble_residual(c, op1, xn, r1);
     assemble_residual(c, op0, xn, r0);
     vec_copy(c, cst.d.p, r.d.p, n);

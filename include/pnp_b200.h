@@ -174,7 +174,9 @@ pnp_status pnp_solver_create(pnp_ctx*, int kind, int prec, int maxit, int prec_s
  * "amg_cheb_ratio" (lambda_max / lambda_min of the Chebyshev interval), "amg_pre_steps" / "amg_post_steps" (smoothing
  * steps before / after the coarse correction; default: the solver's prec_steps for both), "amg_geometric" (default 1: when
  * the mesh was refined with pnp_mesh_refine, the coarser refinement levels become multigrid levels with P1
- * interpolation and Galerkin operators; aggregation continues below the coarsest mesh) */
+ * interpolation; aggregation continues below the coarsest mesh), "amg_rediscretise" (default 1: the operators of those
+ * levels are re-discretised on the level meshes at the injected state when the matrix is the Jacobian of the last
+ * pnp_jacobian / Newton assembly of a PB, PNP or mass operator; 0 or any other matrix: Galerkin products) */
 pnp_status pnp_solver_set_option(pnp_ctx*, int solver, const char* name, double value);
 /* read-back of solver facts, by name: "ssor_levels" / "ilu0_levels" (number of levels of the level-scheduled sweep that
  * reproduces SeqSSOR / SeqILU0 in the reference's row order; 0 before the first use) */
