@@ -180,6 +180,7 @@ def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
 AMG_PARTITIONED = {"amg_geometric": 0}
 EXTRA_SOLVER_OPTS = {}            # --solver-opt NAME=VALUE
 DENSE_COARSE = False              # --dense-coarse
+REPLICA_LEVEL = 3                 # --replica-level: N > 1, refinement level at which the hierarchy stops being distributed
 AMG_FINE = {"amg_geometric": 1}   # refinement levels as multigrid levels (P1 interpolation), aggregation below the coarsest mesh
 
 
@@ -215,10 +216,12 @@ def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps,
     plans = partition.build_hierarchy(a_base, world, rank, levels, all_gather=all_gather, fields_at=(coarse_level, lookup))
     uid = [capi.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    # coarsest distributed level = the Gmsh mesh; it is gathered to a replica of the whole Gmsh mesh on every rank, below
-    # which the one-GPU hierarchy continues (aggregation levels, small dense LU): the cycle equals the N = 1 cycle.
+    # the hierarchy is distributed down to refinement level REPLICA_LEVEL; that level is gathered to a replica of the whole
+    # level mesh on every rank, below which the one-GPU hierarchy continues (refinement levels, aggregation levels, small
+    # dense LU): the cycle equals the N = 1 cycle and the small levels need no halo exchanges.
     # (--dense-coarse: replicated dense LU of the 9 144-dof Gmsh system instead, ~57 ms per Newton step on every rank)
-    children = partition.setup_distributed(capi, c, plans, cfg, rank, world, uid[0], replica_mesh=None if DENSE_COARSE else a_base)
+    children = partition.setup_distributed(capi, c, plans, cfg, rank, world, uid[0], replica_mesh=None if DENSE_COARSE else a_base,
+                                           replica_level=0 if DENSE_COARSE else max(0, min(REPLICA_LEVEL, levels - 1)))
     fine = plans[-1]
     us = c.vec(3, fine.fields["u"].reshape(-1))
     if verbose:
@@ -348,7 +351,7 @@ def run_gpu(args, rank, world, local_rank):
                    "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the Gmsh mesh), NCCL halo exchange per multigrid level + scalar allreduce" % world,
                    "jacobian": args.jac, "solver_options": dict(EXTRA_SOLVER_OPTS), "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
                        "refinement levels with P1 interpolation + Galerkin operators, aggregation AMG below the Gmsh mesh" if world == 1
-                       else "distributed refinement levels with P1 interpolation, re-discretised operators, " + ("replicated dense LU on the Gmsh mesh" if DENSE_COARSE else "replicated aggregation AMG below the Gmsh mesh")),
+                       else "distributed refinement levels with P1 interpolation, re-discretised operators, " + ("replicated dense LU on the Gmsh mesh" if DENSE_COARSE else "levels <= %d replicated on every rank (one-GPU hierarchy: refinement levels, aggregation AMG below the Gmsh mesh)" % REPLICA_LEVEL)),
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
                    "l2_policy": "inputs larger than L2 (per GPU: matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
         "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,
@@ -396,10 +399,11 @@ def main():
     ap.add_argument("--solver-opt", action="append", default=[], metavar="NAME=VALUE",
                     help="pnp_solver_set_option for the timed step's multigrid (experiments), e.g. amg_smoother=1")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--replica-level", type=int, default=3, help="N > 1: levels below this one run replicated on every rank (no halo exchanges there)")
     ap.add_argument("--dense-coarse", action="store_true", help="N > 1: replicated dense LU on the Gmsh mesh instead of the replica hierarchy")
     args = ap.parse_args()
-    global DENSE_COARSE
-    DENSE_COARSE = args.dense_coarse
+    global DENSE_COARSE, REPLICA_LEVEL
+    DENSE_COARSE = args.dense_coarse; REPLICA_LEVEL = args.replica_level
     for kv in args.solver_opt:
         k, v = kv.split("=")
         EXTRA_SOLVER_OPTS[k] = float(v)

@@ -238,12 +238,15 @@ def build_hierarchy(a, nparts, me, levels, all_gather=None, fields_at=None):
     return plans
 
 
-def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggregates=None, replica_mesh=None):
+def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggregates=None, replica_mesh=None,
+                      replica_level=0):
     """Creates the library-side hierarchy from build_hierarchy() plans: `root` gets the finest level, one child context
     per coarser level; returns the list of child contexts (keep them alive as long as root).  aggregates = (agg, n_agg) from
     aggregate_greedy() on the global coarsest mesh: the coarsest level is then smoothed and its aggregate system is the
     replicated dense solve (cheap LU); None: the coarsest level itself is solved densely.  replica_mesh = arrays of the
-    whole coarsest mesh: the coarsest level is gathered to a replica context that runs the one-GPU multigrid below it."""
+    whole coarsest mesh: the coarsest level is gathered to a replica context that runs the one-GPU multigrid below it.
+    replica_level = k > 0: the distributed hierarchy stops at level k; the replica refines the whole coarsest mesh k times
+    on its device and continues below with its own geometric levels (no halo exchanges on the small levels)."""
     fine = plans[-1]
     root.params_read(cfg_path)
     root.mesh_set_local(fine.n_own, fine.x, fine.y, fine.tri, fine.ba, fine.bb, fine.bphys)
@@ -251,7 +254,9 @@ def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggre
     root.halo_set(fine.nbr, fine.send_ptr, fine.send_idx, fine.recv_ptr)
     root.mesh_finalize(True)
     children = []
-    for l in range(len(plans) - 2, -1, -1):
+    lowest = replica_level if replica_mesh is not None else 0
+    assert 0 <= lowest <= len(plans) - 2
+    for l in range(len(plans) - 2, lowest - 1, -1):
         p = plans[l]
         ch = capi.Context(parent=root)
         ch.mesh_set_local(p.n_own, p.x, p.y, p.tri, p.ba, p.bb, p.bphys)
@@ -263,8 +268,16 @@ def setup_distributed(capi, root, plans, cfg_path, rank, world, unique_id, aggre
         # every rank also holds the WHOLE coarsest mesh: the one-GPU multigrid continues below it (redundantly)
         rep = capi.Context(parent=root)
         rep.mesh_set(**replica_mesh)
+        if lowest == 0:
+            gid, n_global = plans[0].gid, int(plans[0].n_global)
+        else:  # vertices of the refined replica are matched by their (bitwise equal) coordinates
+            rep.mesh_refine(lowest)
+            g = rep.mesh_get()
+            tab = {k: i for i, k in enumerate(_coord_keys(g["x"], g["y"]))}
+            gid = np.array([tab[k] for k in _coord_keys(plans[lowest].x, plans[lowest].y)], dtype=np.int32)
+            n_global = len(g["x"])
         rep.mesh_finalize(True)
-        root.mg_set_coarse_replica(rep, plans[0].gid, int(plans[0].n_global))
+        root.mg_set_coarse_replica(rep, gid, n_global)
         children.append(rep)
     elif aggregates is None:
         root.mg_set_coarse_global(plans[0].gid, int(plans[0].n_global))

@@ -134,17 +134,19 @@ def test_distributed_multigrid_on_one_rank(op_name, F, aggregated):
 @pytest.mark.parametrize("op_name,F", [("OP_PB", 1), ("OP_PNP", 3)])
 def test_distributed_multigrid_replica_coarse_level(op_name, F):
     """Replica variant of the coarsest level: the distributed Gmsh level is gathered to a context holding the whole Gmsh
-    mesh, below which the one-GPU hierarchy (aggregation levels + small dense LU) runs.  One subdomain (no NCCL):
+    mesh, below which the one-GPU hierarchy (aggregation levels + small dense LU) runs; "replica1": the hierarchy stops
+    being distributed at refinement level 1 and the replica refines the Gmsh mesh itself.  One subdomain (no NCCL):
     converges like the exact dense coarse solve, and the solution solves the assembled system."""
     from dune_pnp_b200 import capi, partition
     a = util.load_mesh_arrays("pore")
     plans = partition.build_hierarchy(a, 1, 0, 2)
     its = {}
-    for variant in ("dense", "replica"):
+    for variant in ("dense", "replica", "replica1"):
         root = capi.Context(0)
         children = partition.setup_distributed(capi, root, plans, util.cfg_path("pore"), 0, 1, None,
-                                               replica_mesh=a if variant == "replica" else None)
-        assert len(children) == (3 if variant == "replica" else 2)
+                                               replica_mesh=None if variant == "dense" else a,
+                                               replica_level=1 if variant == "replica1" else 0)
+        assert len(children) == {"dense": 2, "replica": 3, "replica1": 2}[variant]
         op = getattr(capi, op_name)
         h = root.operator(op, 0)
         nv = root.mesh_sizes()["nv"]
@@ -162,4 +164,4 @@ def test_distributed_multigrid_replica_coarse_level(op_name, F):
         assert np.linalg.norm(root.download(y, F) - b) <= 2e-8 * np.linalg.norm(b)
         del children
         root.close()
-    assert its["replica"] <= its["dense"] + 4
+    assert its["replica"] <= its["dense"] + 4 and its["replica1"] <= its["dense"] + 4
