@@ -879,7 +879,7 @@ void replica_setup(Ctx& c, Amg& A) {
   assemble_jacobian(rc, op, A.rep_u, A.rep_A, c.last_mode, c.last_eps);
   if (!A.rep_solver) { A.rep_solver = std::make_unique<Solver>(); A.rep_solver->prec = PNP_PREC_AMG; }
   auto& ro = A.rep_solver->opts;
-  ro["amg_geometric"] = 0; ro["amg_omega"] = A.omega; ro["amg_alpha"] = A.alpha; ro["amg_gamma"] = A.gamma;
+  ro["amg_geometric"] = 1; /* refinement levels the replica made itself, if any */ ro["amg_omega"] = A.omega; ro["amg_alpha"] = A.alpha; ro["amg_gamma"] = A.gamma;
   ro["amg_dense_max"] = A.dense_max; ro["amg_coarse_sweeps"] = A.coarse_sweeps; ro["amg_smoother"] = A.smoother;
   ro["amg_cheb_ratio"] = A.cheb_ratio; ro["amg_pre_steps"] = A.pre_steps; ro["amg_post_steps"] = A.post_steps;
   amg_setup(rc, *A.rep_solver, A.rep_A);
