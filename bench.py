@@ -345,12 +345,12 @@ def run_gpu(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "test/pore_pnp (pore.msh + pore.cfg) uniformly refined %d times: one monolithic PNP Newton "
-                               "step (Jacobian assembly, BiCGSTAB + aggregation AMG, line search)" % args.levels,
+                               "step (Jacobian assembly, BiCGSTAB + multigrid, line search)" % args.levels,
                    "levels": args.levels, "dofs": gdof, "matrix_slots": gslots,
                    "rank0_owned_vertices": n_own, "rank0_ghost_vertices": nv - n_own,
                    "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the Gmsh mesh), NCCL halo exchange per multigrid level + scalar allreduce" % world,
                    "jacobian": args.jac, "solver_options": dict(EXTRA_SOLVER_OPTS), "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
-                       "refinement levels with P1 interpolation + Galerkin operators, aggregation AMG below the Gmsh mesh" if world == 1
+                       "refinement levels with P1 interpolation + re-discretised operators, aggregation AMG below the Gmsh mesh" if world == 1
                        else "distributed refinement levels with P1 interpolation, re-discretised operators, " + ("replicated dense LU on the Gmsh mesh" if DENSE_COARSE else "levels <= %d replicated on every rank (one-GPU hierarchy: refinement levels, aggregation AMG below the Gmsh mesh)" % REPLICA_LEVEL)),
                    "start_state": "PNP solution of level %d, P1-interpolated" % args.coarse_level,
                    "l2_policy": "inputs larger than L2 (per GPU: matrix %.1f GB, vectors %.2f GB each)" % (7 * 8 * ns / 1e9, 8 * ndof / 1e9)},
