@@ -58,11 +58,8 @@ void launch_jac(Ctx& c, const StarView& M, const Operator& op, const double* u, 
                 double* vals, long stride, double eps) {
   const PhysParams P = c.phys(op.valency);
   const int smem = OpTraits<OP>::NPLANES * JAC_CAP * (int)sizeof(double);
-  static bool configured = false; // per instantiation
-  if (!configured) {
-    PNP_CUDA(cudaFuncSetAttribute(k_jacobian<OP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  // (set on every launch: the attribute is per device and a process may drive several contexts)
+  PNP_CUDA(cudaFuncSetAttribute(k_jacobian<OP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = grid_for(M.nv, JAC_CHUNK, c.sm_count * 16);
   k_jacobian<OP, MODE><<<grid, JAC_CHUNK, smem, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, vals, stride);
   PNP_CHECK_LAUNCH(); c.launches++;

@@ -782,3 +782,49 @@ def test_multigrid_rediscretised_vs_galerkin_coarse_operators(op):
     res = c.solve(s, A, z, r, 1e-9)
     assert res.converged and res.iterations == its[0]
     assert np.linalg.norm(c.download(z, F) - sols[0]) <= 1e-6 * np.linalg.norm(sols[0])
+
+
+def test_errors_of_the_solver_and_time_stepping_entry_points():
+    """Argument errors come back as PNP_E_ARG (8) with a message, never as a crash; solver failures as their own codes."""
+    capi = _capi()
+    c, m, p = make_ctx("one_wall")
+    h0, h1 = c.operator(capi.OP_DIFFUSION, 1), c.operator(capi.OP_MASS, 2)   # different constraint components
+    c.operator_set_coefficient(h0, 0, c.vec(1))
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 50, 1)
+    x, g, y, u3 = c.vec(1), c.vec(1), c.vec(1), c.vec(3)
+    with pytest.raises(capi.PnpError) as e:
+        c.onestep(h0, h1, s, 0.1, x, g, y)
+    assert e.value.status == 8 and "constraints" in str(e.value)
+    h1 = c.operator(capi.OP_MASS, 1)
+    with pytest.raises(capi.PnpError) as e:
+        c.onestep(h0, h1, s, 0.1, u3, g, y)          # 3-field vector into the scalar transport step
+    assert e.value.status == 8
+    with pytest.raises(capi.PnpError) as e:
+        c.onestep(h0, h1, s, 0.1, x, g, y, method=7)  # unknown time stepping method
+    assert e.value.status == 8
+    hpb = c.operator(capi.OP_PB, 0)
+    A = c.matrix(hpb)
+    c.jacobian(hpb, x, A, capi.JAC_ANALYTIC, 0.0)
+    with pytest.raises(capi.PnpError) as e:
+        c.precond_apply(s, A, x, x)                   # d and v must be distinct
+    assert e.value.status == 8
+    with pytest.raises(capi.PnpError) as e:
+        c.precond_apply(s, A, u3, c.vec(3))           # field count does not match the matrix
+    assert e.value.status == 8
+    with pytest.raises(capi.PnpError) as e:
+        c.solver_get(s, "no_such_fact")
+    assert e.value.status == 8
+    with pytest.raises(capi.PnpError) as e:
+        c.ion_flux(u3, x, y)
+    assert e.value.status == 8
+    with pytest.raises(capi.PnpError) as e:
+        c.write_cell_data(x, "/nonexistent_dir/phi.dat")
+    assert e.value.status == 7
+    with pytest.raises(capi.PnpError) as e:
+        c.solver(capi.SOLVER_BCGS, 9, 50, 1)          # unknown preconditioner
+    assert e.value.status == 8
+    # a linear solve that cannot reach the reduction within maxit reports converged = 0, not an error (ISTL behaviour)
+    b = np.random.RandomState(0).uniform(-1, 1, m.nv); b[c.constraints(hpb, 1)] = 0
+    s1 = c.solver(capi.SOLVER_CG, capi.PREC_NONE, 2)
+    res = c.solve(s1, A, c.vec(1), c.vec(1, b), 1e-14)
+    assert not res.converged and res.iterations == 2
