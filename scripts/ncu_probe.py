@@ -1,6 +1,8 @@
 """Profiling target: the hot kernels once each on the refined pore mesh (default k = 7: 141 M dofs), for
 `ncu --set full -k regex:'k_star_op|k_residual|k_jacobian'`: PNP residual, analytic Jacobian, FD-faithful Jacobian,
-two fine-level SpMVs (k_star_op<7,0,0>).  Prints CUDA-event times of the same launches when run without ncu."""
+two fine-level SpMVs (k_star_op<7,0,0>) and, with a second argument "amg", one multigrid V(2,2) application whose first
+k_star_op launches are the fine-level smoother step (k_star_op<7,2,0>) and residual (k_star_op<7,1,0>).
+Prints CUDA-event times of the same launches when run without ncu."""
 import os
 import sys
 
@@ -39,3 +41,7 @@ timed("jacobian fd-faithful", lambda: c.jacobian(h, u, A, 0, 1e-11), jac_b)
 c.jacobian(h, u, A, 1, 0.0)
 timed("spmv 3-field", lambda: c.spmv(A, x, y), spmv_b)
 timed("spmv 3-field", lambda: c.spmv(A, x, y), spmv_b)
+if len(sys.argv) > 2 and sys.argv[2] == "amg":
+    s_amg = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 100, 2)
+    c.precond_apply(s_amg, A, x, y)   # setup (symbolic + numeric) and one cycle
+    timed("multigrid V(2,2) cycle", lambda: c.precond_apply(s_amg, A, x, y), 4 * 27.9e9)
