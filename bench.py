@@ -365,10 +365,10 @@ def run_gpu(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "3-field SpMV on the vertex-star layout, fine level (k_star_op<7,EPI,NDOT>, all epilogues)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this size (plain
-                     # epilogue: 21.62 GB read + 1.13 GB written against 22.22 GB algorithmic); other sizes: not captured
-                     "traffic": 22.75e9 if (world == 1 and args.levels == 7) else None,
+                     # epilogue: 21.56 GB read + 1.13 GB written against 22.22 GB algorithmic); other sizes: not captured
+                     "traffic": 22.69e9 if (world == 1 and args.levels == 7) else None,
                      "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k_star_op<7,0,0> at k = 7 "
-                                       "(profiles/hot_kernels_full_r01c_summary.txt); algorithmic bytes of that epilogue: 22.22e9",
+                                       "(profiles/hot_kernels_full_r01d_summary.txt); algorithmic bytes of that epilogue: 22.22e9",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,  # launch-weighted mean over the epilogue kinds
                      "avg_launch_ms": spmv_avg_s * 1e3},
         "cpu_baseline": None if cpu is None else {
