@@ -698,7 +698,7 @@ const double* level_values(Ctx& c, Amg& A, int li, const double* uf, int comp0) 
 void numeric(Ctx& c, Amg& A, int comp0) {
   if (A.distributed) {
     // re-discretise every coarser level at the injected state (what assemble_jacobian last linearised on the fine level)
-    PNP_REQUIRE(c.last_u, PNP_E_ARG, "distributed multigrid needs the state of the last Jacobian assembly");
+    PNP_REQUIRE(c.last_u, PNP_E_ARG, "distributed multigrid needs the state of the last Jacobian assembly (the vector must stay alive)");
     const double* uf = c.last_u;
     for (size_t li = 0; li + 1 < A.L.size(); li++) {
       Level& l = *A.L[li]; Level& n = *A.L[li + 1];

@@ -335,7 +335,13 @@ pnp_status pnp_vec_create(pnp_ctx* ctx, int fields, int* handle) {
   *handle = (int)c.vecs.size() - 1;
   API_END
 }
-pnp_status pnp_vec_destroy(pnp_ctx* ctx, int h) { API_BEGIN(ctx) c.vec(h); c.vecs[h].reset(); API_END }
+pnp_status pnp_vec_destroy(pnp_ctx* ctx, int h) {
+  API_BEGIN(ctx)
+  // a multigrid set up later must not re-discretise at a state that no longer exists
+  if (c.vec(h).d.p == c.last_u) { c.last_u = nullptr; c.last_vals = nullptr; }
+  c.vecs[h].reset();
+  API_END
+}
 pnp_status pnp_vec_upload(pnp_ctx* ctx, int h, const double* host) { API_BEGIN(ctx) vec_upload(c, c.vec(h), host); API_END }
 pnp_status pnp_vec_download(pnp_ctx* ctx, int h, double* host) { API_BEGIN(ctx) vec_download(c, c.vec(h), host); API_END }
 pnp_status pnp_vec_set(pnp_ctx* ctx, int h, double value) {
@@ -392,7 +398,12 @@ pnp_status pnp_matrix_create(pnp_ctx* ctx, int op_handle, int* handle) {
   *handle = (int)c.mats.size() - 1;
   API_END
 }
-pnp_status pnp_matrix_destroy(pnp_ctx* ctx, int h) { API_BEGIN(ctx) c.mat(h); c.mats[h].reset(); API_END }
+pnp_status pnp_matrix_destroy(pnp_ctx* ctx, int h) {
+  API_BEGIN(ctx)
+  if (c.mat(h).vals.p == c.last_vals) c.last_vals = nullptr;
+  c.mats[h].reset();
+  API_END
+}
 pnp_status pnp_residual(pnp_ctx* ctx, int op, int u, int r) {
   API_BEGIN(ctx)
   assemble_residual(c, c.oper(op), c.vec(u), c.vec(r));

@@ -208,6 +208,7 @@ struct Ctx {
   void invalidate_mesh_objects() {
     finalized = false; constraints_built = false;
     vecs.clear(); mats.clear(); ops.clear(); solvers.clear();
+    last_u = nullptr; last_vals = nullptr;
     ws_r.d.release(); ws_z.d.release(); ws_prev.d.release(); ws_A.vals.release(); ws_B.vals.release();
     for (auto& v : ws_stage) v.d.release();
     io_stage.release();
