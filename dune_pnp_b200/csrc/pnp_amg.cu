@@ -699,6 +699,8 @@ void numeric(Ctx& c, Amg& A, int comp0) {
   if (A.distributed) {
     // re-discretise every coarser level at the injected state (what assemble_jacobian last linearised on the fine level)
     PNP_REQUIRE(c.last_u, PNP_E_ARG, "distributed multigrid needs the state of the last Jacobian assembly (the vector must stay alive)");
+    PNP_REQUIRE(c.last_vals == A.L[0]->vals, PNP_E_ARG,
+                "distributed multigrid re-discretises its coarse levels: the matrix must be the Jacobian of the last assembly");
     const double* uf = c.last_u;
     for (size_t li = 0; li + 1 < A.L.size(); li++) {
       Level& l = *A.L[li]; Level& n = *A.L[li + 1];
