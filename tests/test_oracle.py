@@ -255,3 +255,25 @@ def test_write_cell_data_format(tmp_path):
     tri0 = m.tri[0]
     assert np.allclose(first[:2], [m.x[tri0].mean(), m.y[tri0].mean()], rtol=1e-5)
     assert np.allclose(first[2], u[tri0].mean(), rtol=1e-5) and np.allclose(first[3:], [0.5, -0.25], rtol=1e-5)
+
+
+def test_one_wall_pb_against_the_references_gouy_chapman_curve():
+    """The one analytic anchor the reference ships: test/one_wall_dh/one_wall.gp:4-12 plots the solution against the
+    Gouy-Chapman profile g(x) = 2 ln((1 + tanh(phi0/4) e^{-kappa x}) / (1 - tanh(phi0/4) e^{-kappa x})) and its
+    Debye-Hueckel limit F/kappa e^{-kappa x} (columns 1 and -3 of the DataWriter file).  The constants in the .gp file are
+    stale; with the cfg's own l_b, c0, flux and the code's PI: kappa^2 = 8 PI l_b c0 and the Grahame relation
+    phi0 = 2 asinh(j / (2 kappa)).  The domain is finite (phi = 0 at x = 5, kappa L = 6.1), which moves the curve by
+    ~4 phi0 e^{-kappa L} = 0.2 % of phi0."""
+    m, p = case("one_wall", 3)
+    PI, l_b, c0 = p.sys[4], p.sys[2], p.sys[3]
+    j = p.surf[0][1]                                  # coulombFlux of surface 0
+    kappa = np.sqrt(8 * PI * l_b * c0)
+    phi0 = 2 * np.arcsinh(j / (2 * kappa))
+    g = lambda x: 2 * np.log((1 + np.tanh(0.25 * phi0) * np.exp(-kappa * x)) / (1 - np.tanh(0.25 * phi0) * np.exp(-kappa * x)))
+    opts = ora.newton_opts(p, prec=ora.PREC_SSOR); opts[0], opts[2], opts[12] = 1e-10, 1e-8, 5000
+    u, res = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+    assert res["converged"]
+    assert abs(np.abs(u).max() - phi0) <= 5e-3 * phi0
+    assert np.max(np.abs(np.abs(u) - g(m.x))) <= 5e-3 * phi0
+    # Debye-Hueckel limit of the same file: j / kappa e^{-kappa x}, valid to O(phi0^2) relative
+    assert np.max(np.abs(np.abs(u) - j / kappa * np.exp(-kappa * m.x))) <= (phi0 ** 2 / 8 + 5e-3) * phi0
