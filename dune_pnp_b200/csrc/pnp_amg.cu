@@ -1067,11 +1067,14 @@ void amg_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y) {
     double *keep_b = l0.b.p, *keep_x = l0.x.p, *keep_x2 = l0.x2.p;
     const int pre = A.pre_steps >= 0 ? A.pre_steps : nu, post = A.post_steps >= 0 ? A.post_steps : nu;
     const int swaps = (pre > 0 ? pre - 1 : 0) + post;
+    struct Restore { // the level's buffers own their memory: put the pointers back whatever happens in the cycle
+      Level& l; double *b, *x, *x2;
+      ~Restore() { l.b.p = b; l.x.p = x; l.x2.p = x2; }
+    } restore{l0, keep_b, keep_x, keep_x2};
     l0.b.p = const_cast<double*>(d);
     if (swaps & 1) l0.x2.p = y; else l0.x.p = y;
     cycle(c, A, 0, nu, A.comp0, true);
     double* result = l0.x.p;
-    l0.b.p = keep_b; l0.x.p = keep_x; l0.x2.p = keep_x2;
     if (result != y) PNP_CUDA(cudaMemcpyAsync(y, result, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
     return;
   }
