@@ -277,3 +277,26 @@ def test_one_wall_pb_against_the_references_gouy_chapman_curve():
     assert np.max(np.abs(np.abs(u) - g(m.x))) <= 5e-3 * phi0
     # Debye-Hueckel limit of the same file: j / kappa e^{-kappa x}, valid to O(phi0^2) relative
     assert np.max(np.abs(np.abs(u) - j / kappa * np.exp(-kappa * m.x))) <= (phi0 ** 2 / 8 + 5e-3) * phi0
+
+
+def test_pb_solution_is_an_equilibrium_of_the_pnp_operator():
+    """Cross-pin of two of the reference's operators (pb_operator.hh:116-118 against pnp_operator.hh:169-191): with
+    c+- = c0 exp(+-u) the phi-row of PnpOperator is the PB residual (4 PI l_b (c+ - c-) = 8 PI l_b c0 sinh u, same
+    boundary flux term) and the two Nernst-Planck rows vanish identically in the continuum, so the discrete PB solution
+    makes the PNP residual O(h^2) small.  The sign is the PNP operator's own (phi -> -phi relative to BCExtension,
+    which hands c+ = c0 exp(-pb) to the PNP Newton as the initial guess, dirichlet_bc.hh:106-107): with that sign the
+    residual is four orders of magnitude larger and does not converge."""
+    norms, wrong = [], []
+    for lev in (1, 2, 3):
+        m, p = case("one_wall", lev)
+        opts = ora.newton_opts(p, prec=ora.PREC_SSOR); opts[0], opts[2], opts[12] = 1e-12, 1e-10, 20000
+        u, res = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+        assert res["converged"]
+        c0 = p.sys[3]
+        r = ora.residual(m, p, ora.OP_PNP, np.concatenate([u, c0 * np.exp(u), c0 * np.exp(-u)])).reshape(3, -1)
+        rw = ora.residual(m, p, ora.OP_PNP, np.concatenate([u, c0 * np.exp(-u), c0 * np.exp(u)])).reshape(3, -1)
+        norms.append(np.linalg.norm(r, axis=1)); wrong.append(np.linalg.norm(rw, axis=1))
+    norms, wrong = np.array(norms), np.array(wrong)
+    # nodal residuals of an O(h^2)-consistent state shrink like h^3 (phi-row) resp. at least h^2 per refinement
+    assert np.all(norms[:-1, 0] / norms[1:, 0] > 6.0) and np.all(norms[:-1, 1:] / norms[1:, 1:] > 3.0)
+    assert np.all(wrong[-1] > 1e3 * norms[-1]) and np.all(wrong[:-1] / wrong[1:] < 2.5)
