@@ -300,3 +300,27 @@ def test_pb_solution_is_an_equilibrium_of_the_pnp_operator():
     # nodal residuals of an O(h^2)-consistent state shrink like h^3 (phi-row) resp. at least h^2 per refinement
     assert np.all(norms[:-1, 0] / norms[1:, 0] > 6.0) and np.all(norms[:-1, 1:] / norms[1:, 1:] > 3.0)
     assert np.all(wrong[-1] > 1e3 * norms[-1]) and np.all(wrong[:-1] / wrong[1:] < 2.5)
+
+
+def test_pb_solution_is_a_steady_state_of_the_split_scheme():
+    """Cross-pin of the operators of the reference's HEAD driver (instationary_pnp_md): with the concentrations that
+    BCExtension derives from the PB field (c+ = c0 exp(-pb), c- = c0 exp(+pb), dirichlet_bc.hh:106-115) the Poisson
+    residual (poisson_operator.hh:121-123) is the PB residual and both drift-diffusion residuals
+    (diffusion_operator.hh:100,110, valency +-1) vanish in the continuum: discretely O(h^2)."""
+    norms = []
+    for lev in (1, 2, 3):
+        m, p = case("one_wall", lev)
+        opts = ora.newton_opts(p, prec=ora.PREC_SSOR); opts[0], opts[2], opts[12] = 1e-12, 1e-10, 20000
+        pb, res = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+        cp, cm = ora.interpolate(m, p, 1, pb), ora.interpolate(m, p, 2, pb)
+        assert np.allclose(cp, p.sys[3] * np.exp(-pb)) and np.allclose(cm, p.sys[3] * np.exp(pb))  # no Dirichlet c on one_wall
+        rphi = ora.residual(m, p, ora.OP_POISSON, pb, cp, cm)
+        rp = ora.residual(m, p, ora.OP_DIFFUSION, cp, pb, valency=1.0, comp0=1)
+        rm = ora.residual(m, p, ora.OP_DIFFUSION, cm, pb, valency=-1.0, comp0=1)
+        # scale: the same residuals with the opposite valency (a state that is NOT steady)
+        sp = ora.residual(m, p, ora.OP_DIFFUSION, cp, pb, valency=-1.0, comp0=1)
+        norms.append([np.linalg.norm(rphi), np.linalg.norm(rp), np.linalg.norm(rm), np.linalg.norm(sp)])
+    norms = np.array(norms)
+    assert np.all(norms[:-1, 0] / norms[1:, 0] > 6.0)          # Poisson row: h^3 in nodal terms
+    assert np.all(norms[:-1, 1:3] / norms[1:, 1:3] > 3.0)      # transport rows: at least h^2
+    assert np.all(norms[-1, 1:3] < 1e-3 * norms[-1, 3])
