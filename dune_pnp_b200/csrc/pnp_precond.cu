@@ -8,8 +8,10 @@
 // so Krylov iteration counts match the CPU path.  With several ranks the sweeps act on the local diagonal block
 // (ghost columns skipped), like the NOVLP backends.
 //
-// Cost: the number of levels is the longest chain of coupled dofs in the reference's numbering (tens on the Gmsh meshes,
-// O(sqrt(N)) on refined ones), so these are the parity preconditioners; the multigrid of pnp_amg.cu is the fast one.
+// Cost: the number of levels is the longest chain of coupled dofs in the reference's numbering: 18-100 on the Gmsh meshes,
+// 10-35 on refined ones (old vertices are numbered before the edge midpoints, which keeps the chains short), so a sweep
+// is one matrix pass in a few dozen launches at any size.  They are the parity preconditioners because their Krylov
+// iteration counts grow like 1/h; the multigrid of pnp_amg.cu is the fast one.
 // HBM traffic per sweep = one pass over the matrix planes (8*NP*nslots) + adjacency (4*nslots per field) + vectors.
 #include <cub/cub.cuh>
 
