@@ -32,7 +32,7 @@ class NewtonOpts(C.Structure):
     _fields_ = [("reduction", C.c_double), ("abs_limit", C.c_double), ("min_linear_reduction", C.c_double),
                 ("reassemble_threshold", C.c_double), ("max_iterations", C.c_int),
                 ("line_search_max_iterations", C.c_int), ("damping", C.c_double), ("jac_mode", C.c_int),
-                ("fd_epsilon", C.c_double), ("verbosity", C.c_int)]
+                ("fd_epsilon", C.c_double), ("verbosity", C.c_int), ("line_search_strategy", C.c_int)]
 
 
 class NewtonResult(C.Structure):

@@ -64,6 +64,8 @@ struct Amg {
   int NP = 1, F = 1;
   bool symbolic = false;
   long nv0 = -1, nslots0 = -1;
+  long mg_epoch = -1;       // Ctx::mg_epoch the hierarchy was built for
+  double sym_key = 0.0;     // the options that shape the hierarchy (a change rebuilds it)
   double omega = 0.7, alpha = 1.6;
   int coarse_sweeps = 40;
   int gamma = 1;          // 1: V-cycle, 2: W-cycle ...
@@ -695,6 +697,23 @@ const double* level_values(Ctx& c, Amg& A, int li, const double* uf, int comp0) 
   return nullptr;
 }
 
+// Gershgorin bounds of D^-1 A on every level (Chebyshev smoother); distributed: the maximum over the ranks
+void gershgorin_bounds(Ctx& c, Amg& A) {
+  DBuf<unsigned long long> d_l(A.L.size());
+  d_l.zero(c.stream);
+  for (size_t li = 0; li < A.L.size(); li++) {
+    Level& l = *A.L[li];
+    if (A.NP == 1) KL(c, k_gershgorin<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, d_l.p + li);
+    else KL(c, k_gershgorin<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, d_l.p + li);
+  }
+  if (A.distributed) allreduce_max_u64(c, d_l.p, A.L.size());
+  std::vector<unsigned long long> h = d_l.to_host(c.stream);
+  for (size_t li = 0; li < A.L.size(); li++) {
+    double v; std::memcpy(&v, &h[li], sizeof v);
+    A.L[li]->lmax = (v > 0.0 && std::isfinite(v)) ? v : 2.0;
+  }
+}
+
 void numeric(Ctx& c, Amg& A, int comp0) {
   if (A.distributed) {
     // re-discretise every coarser level at the injected state (what assemble_jacobian last linearised on the fine level)
@@ -720,6 +739,7 @@ void numeric(Ctx& c, Amg& A, int comp0) {
       else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
     }
     if (c.mg_replica) replica_setup(c, A); else dense_factor_global(c, A);
+    if (A.smoother == 1) gershgorin_bounds(c, A);
     return;
   }
   const double* uf = c.last_u;
@@ -730,21 +750,8 @@ void numeric(Ctx& c, Amg& A, int comp0) {
     else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
   }
   A.dense_n = 0;
-  if ((long)A.F * A.L.back()->nv <= A.dense_max && A.L.size() > 1) dense_factor(c, A);
-  if (A.smoother == 1) {
-    DBuf<unsigned long long> d_l(A.L.size());
-    d_l.zero(c.stream);
-    for (size_t li = 0; li < A.L.size(); li++) {
-      Level& l = *A.L[li];
-      if (A.NP == 1) KL(c, k_gershgorin<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, d_l.p + li);
-      else KL(c, k_gershgorin<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, d_l.p + li);
-    }
-    std::vector<unsigned long long> h = d_l.to_host(c.stream);
-    for (size_t li = 0; li < A.L.size(); li++) {
-      double v; std::memcpy(&v, &h[li], sizeof v);
-      A.L[li]->lmax = (v > 0.0 && std::isfinite(v)) ? v : 2.0;
-    }
-  }
+  if ((long)A.F * A.L.back()->nv <= A.dense_max) dense_factor(c, A); // (a one-level hierarchy is a direct solve)
+  if (A.smoother == 1) gershgorin_bounds(c, A);
 }
 
 // ---- dense coarsest-level solve ----
@@ -983,10 +990,12 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
   const bool want_redisc = S.opt("amg_geometric", 1) != 0 && S.opt("amg_rediscretise", 1) != 0 && c.n_own == c.nv &&
                            !c.hier.empty() && c.mg.empty() && c.last_u && c.last_vals == M.vals.p &&
                            (M.op == OP_PB || M.op == OP_PNP || M.op == OP_MASS);
-  if (!A.symbolic || A.NP != M.nplanes || A.nv0 != c.n_own || A.nslots0 != c.nslots || A.redisc != want_redisc) {
+  const double sym_key = S.opt("amg_geometric", 1) + 3.0 * S.opt("amg_dense_max", 4096) + 1e7 * S.opt("amg_alpha", 1.6);
+  if (!A.symbolic || A.NP != M.nplanes || A.nv0 != c.n_own || A.nslots0 != c.nslots || A.redisc != want_redisc ||
+      A.mg_epoch != c.mg_epoch || A.sym_key != sym_key) {
     A.L.clear();
     A.NP = M.nplanes; A.F = M.nplanes == 1 ? 1 : 3;
-    A.nv0 = c.n_own; A.nslots0 = c.nslots;
+    A.nv0 = c.n_own; A.nslots0 = c.nslots; A.mg_epoch = c.mg_epoch; A.sym_key = sym_key;
     auto l0 = std::make_unique<Level>();
     l0->nv = (int)c.n_own; l0->nslots = c.nslots; l0->rp = c.rp.p; l0->col = c.adj.p; l0->vals = M.vals.p;
     A.L.push_back(std::move(l0));

@@ -135,6 +135,11 @@ static void coefficient_ptrs(Ctx& c, const Operator& op, const double** a0, cons
     PNP_REQUIRE(c.vec(op.aux1).fields == 1, PNP_E_ARG, "coefficient must be a 1-field vector");
     *a1 = c.vec(op.aux1).d.p;
   }
+  // partitioned mesh: the coefficient fields are read at ghost vertices too, and solver results only cover owned dofs
+  if (c.n_own < c.nv) {
+    if (*a0) halo_exchange(c, const_cast<double*>(*a0), 1);
+    if (*a1) halo_exchange(c, const_cast<double*>(*a1), 1);
+  }
 }
 
 void assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {

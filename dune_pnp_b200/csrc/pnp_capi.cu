@@ -65,14 +65,32 @@ pnp_status pnp_ctx_create_child(pnp_ctx* parent, pnp_ctx** out) {
   h->c.device = p.device; h->c.stream = p.stream; h->c.owns_stream = false; h->c.sm_count = p.sm_count;
   h->c.rank = p.rank; h->c.world = p.world; h->c.nccl = p.nccl;
   h->c.params = p.params;
+  h->c.parent = &p; p.children.push_back(&h->c);
   *out = h;
   return PNP_OK;
 }
+// Lifetime of child contexts: a child may be destroyed before its parent (the parent then forgets every multigrid level
+// from that child downwards, and a multigrid built on them is rebuilt at its next use); a parent destroyed first
+// orphans its children (they lose the borrowed stream and communicator and must only be destroyed afterwards).
 void pnp_ctx_destroy(pnp_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->c.device);
-  if (ctx->c.h_red) cudaFreeHost(ctx->c.h_red);
-  cudaStream_t s = ctx->c.owns_stream ? ctx->c.stream : nullptr;
+  Ctx& c = ctx->c;
+  cudaSetDevice(c.device);
+  if (c.parent) {
+    Ctx& p = *c.parent;
+    for (size_t i = 0; i < p.children.size(); i++) if (p.children[i] == &c) { p.children.erase(p.children.begin() + i); break; }
+    for (size_t i = 0; i < p.mg.size(); i++) if (p.mg[i].lc == &c) { p.mg.resize(i); p.mg_gid.release(); p.mg_nglobal = 0; p.mg_replica = nullptr; break; }
+    if (p.mg_replica == &c) { p.mg_replica = nullptr; p.mg_gid.release(); p.mg_nglobal = 0; }
+    p.mg_epoch++;
+  }
+  for (Ctx* k : c.children) { k->parent = nullptr; k->stream = nullptr; k->nccl = nullptr; }
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  if (c.h_red) cudaFreeHost(c.h_red);
+  for (cudaEvent_t e : c.prof_ev) cudaEventDestroy(e);
+  if (c.tm0) cudaEventDestroy(c.tm0);
+  if (c.tm1) cudaEventDestroy(c.tm1);
+  if (c.owns_comm) comm_destroy(c);
+  cudaStream_t s = c.owns_stream ? c.stream : nullptr;
   delete ctx;
   if (s) cudaStreamDestroy(s);
 }
@@ -95,6 +113,7 @@ pnp_status pnp_mg_push_level(pnp_ctx* ctx, pnp_ctx* child, const int* par0, cons
   r.par0.upload(p0.data(), f.nv, c.stream); r.par1.upload(p1.data(), f.nv, c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   c.mg.push_back(std::move(r));
+  c.mg_epoch++;
   API_END
 }
 pnp_status pnp_mg_set_coarse_aggregates(pnp_ctx* ctx, const int* agg, long n_aggregates) {
@@ -111,7 +130,7 @@ pnp_status pnp_mg_set_coarse_global(pnp_ctx* ctx, const int* gid, long n_global)
   for (long i = 0; i < k.nv; i++) { g[i] = gid[i2e[i]]; PNP_REQUIRE(g[i] >= 0 && g[i] < n_global, PNP_E_ARG, "global index out of range"); }
   c.mg_gid.alloc(k.nv); c.mg_gid.upload(g.data(), k.nv, c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
-  c.mg_nglobal = n_global;
+  c.mg_nglobal = n_global; c.mg_epoch++;
   API_END
 }
 pnp_status pnp_mg_set_coarse_replica(pnp_ctx* ctx, pnp_ctx* replica, const int* gid, long n_global) {
@@ -129,7 +148,7 @@ pnp_status pnp_mg_set_coarse_replica(pnp_ctx* ctx, pnp_ctx* replica, const int* 
   }
   c.mg_gid.alloc(k.nv); c.mg_gid.upload(g.data(), k.nv, c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
-  c.mg_nglobal = n_global; c.mg_replica = &r;
+  c.mg_nglobal = n_global; c.mg_replica = &r; c.mg_epoch++;
   API_END
 }
 pnp_status pnp_profile_spmv(pnp_ctx* ctx, int enable) {
@@ -475,6 +494,7 @@ void pnp_newton_opts_default(pnp_newton_opts* o) {
   o->reduction = 1e-8; o->abs_limit = 1e-12; o->min_linear_reduction = 1e-3; o->reassemble_threshold = 0.0;
   o->max_iterations = 40; o->line_search_max_iterations = 10; o->damping = 0.5;
   o->jac_mode = PNP_JAC_FD_FAITHFUL; o->fd_epsilon = 1e-11; o->verbosity = 0;
+  o->line_search_strategy = PNP_LS_HACKBUSCH_REUSKEN_ACCEPT_BEST;
 }
 pnp_status pnp_newton_opts_from_params(pnp_ctx* ctx, pnp_newton_opts* o) {
   API_BEGIN(ctx)
@@ -505,6 +525,8 @@ pnp_status pnp_slp_apply(pnp_ctx* ctx, int op, int u, int solver, double reducti
   API_BEGIN(ctx)
   LinResult lr = slp_apply(c, c.oper(op), c.vec(u), c.solver(solver), reduction, jac_mode, eps);
   to_lin(lr, out);
+  if (lr.status == PNP_E_BREAKDOWN) { c.err = "BiCGSTAB breakdown (rho, omega or h vanished)"; return PNP_E_BREAKDOWN; }
+  if (lr.status == PNP_E_NAN) { c.err = "non-finite residual norm in the linear solver"; return PNP_E_NAN; }
   API_END
 }
 pnp_status pnp_onestep_apply(pnp_ctx* ctx, int method, int op_space, int op_time, int solver, double time, double dt,

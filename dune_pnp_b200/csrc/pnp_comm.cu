@@ -48,7 +48,11 @@ void comm_init(Ctx& c, int rank, int world, const char* unique_id128) {
   std::memcpy(&id, unique_id128, 128);
   ncclComm_t comm;
   PNP_NCCL(ncclCommInitRank(&comm, world, id, rank));
-  c.nccl = comm;
+  c.nccl = comm; c.owns_comm = true;
+}
+void comm_destroy(Ctx& c) {
+  if (c.nccl && c.owns_comm) ncclCommDestroy((ncclComm_t)c.nccl);
+  c.nccl = nullptr; c.owns_comm = false;
 }
 
 void halo_set(Ctx& c, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr) {
@@ -95,6 +99,12 @@ void allreduce_sum(Ctx& c, double* dev, size_t n) {
   if (c.world == 1) return;
   PNP_REQUIRE(c.nccl, PNP_E_ARG, "no communicator (pnp_comm_init)");
   PNP_NCCL(ncclAllReduce(dev, dev, n, ncclDouble, ncclSum, (ncclComm_t)c.nccl, c.stream));
+}
+
+void allreduce_max_u64(Ctx& c, unsigned long long* dev, size_t n) {
+  if (c.world == 1) return;
+  PNP_REQUIRE(c.nccl, PNP_E_ARG, "no communicator (pnp_comm_init)");
+  PNP_NCCL(ncclAllReduce(dev, dev, n, ncclUint64, ncclMax, (ncclComm_t)c.nccl, c.stream));
 }
 
 } // namespace pnp

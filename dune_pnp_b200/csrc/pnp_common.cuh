@@ -199,6 +199,10 @@ struct Ctx {
   // level is smoothed like the others and the Galerkin aggregate system below it is the dense one)
   DBuf<int> mg_gid; long mg_nglobal = 0; bool mg_aggregated = false;
   Ctx* mg_replica = nullptr;           // whole coarsest mesh on every rank: single-GPU multigrid below it (mg_gid maps into ITS internal numbering)
+  long mg_epoch = 0;                   // bumped by every pnp_mg_* call: a multigrid built for an older hierarchy is rebuilt
+  Ctx* parent = nullptr;               // child contexts: the context whose stream / communicator they borrow
+  std::vector<Ctx*> children;          // ... and the children a context has handed out (their lifetime is bounded by the parent's)
+  bool owns_comm = false;
   // what the last assemble_jacobian() call linearised (coarse levels of the distributed multigrid re-discretise it)
   const double* last_u = nullptr; Operator last_op; int last_mode = 0; double last_eps = 1e-11;
   const double* last_vals = nullptr;   // ... and the matrix values it wrote (reset when they are combined into something else)
@@ -241,10 +245,12 @@ void constraints_build(Ctx&);
 // pnp_comm.cu
 void comm_init(Ctx&, int rank, int world, const char* unique_id128);
 void comm_unique_id(char* out128);
+void comm_destroy(Ctx&);
 void halo_set(Ctx&, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr);
 void halo_finalize(Ctx&);
 void halo_exchange(Ctx&, double* x, int fields);
 void allreduce_sum(Ctx&, double* dev, size_t n);
+void allreduce_max_u64(Ctx&, unsigned long long* dev, size_t n);
 void carry_set(Ctx&, const int* handles, int n);
 void carry_get(Ctx&, int i, Vec& out);
 void vec_upload(Ctx&, Vec&, const double* host_lex);

@@ -45,6 +45,10 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
   R.defect = defect();
   R.first_defect = R.defect;
   double prev_defect = R.defect;
+  // PDELab's Newton sets reassemble_threshold = 0 after a line-search failure on a matrix that was not reassembled
+  // (newton.hh, NewtonLineSearchError handler): the next pass is forced to assemble, whatever the threshold says
+  double reassemble_threshold = o.reassemble_threshold;
+  int ls_retries = 0;
   record(R.defect, 0);
   if (!std::isfinite(R.defect)) { R.seconds_total = now() - t_start; return PNP_E_NAN; }
   if (o.verbosity >= 2) std::printf("  Initial defect: %12.4e\n", R.defect);
@@ -54,7 +58,7 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
     if (R.iterations >= o.max_iterations) { status = PNP_E_NOT_CONVERGED; break; }
     // prepare_step
     bool reassembled = false;
-    if (R.defect / prev_defect > o.reassemble_threshold || R.jacobian_assemblies == 0) {
+    if (R.defect / prev_defect > reassemble_threshold || R.jacobian_assemblies == 0) {
       const double t0 = now();
       assemble_jacobian(c, op, u, A, o.jac_mode, o.fd_epsilon);
       sync();
@@ -80,7 +84,7 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
       status = lr.status == PNP_E_BREAKDOWN ? PNP_E_BREAKDOWN : PNP_E_LINEAR_SOLVER;
       break;
     }
-    // line_search, strategy hackbuschReuskenAcceptBest
+    // line_search: hackbuschReuskenAcceptBest (the reference drivers' choice), hackbuschReusken or noLineSearch
     double lambda = 1.0, best_lambda = 0.0, best_defect = R.defect;
     vec_copy(c, u.d.p, prev_u.d.p, n);
     int i = 0;
@@ -89,11 +93,12 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
       vec_axpy(c, -lambda, z.d.p, u.d.p, n);
       R.defect = defect();
       R.line_search_trials++;
+      if (o.line_search_strategy == PNP_LS_NONE) break; // noLineSearch: the full step is taken whatever the defect does
       const bool finite = std::isfinite(R.defect);
       if (finite && R.defect <= (1.0 - lambda / 4) * prev_defect) break;
       if (finite && R.defect < best_defect) { best_defect = R.defect; best_lambda = lambda; }
       if (++i >= o.line_search_max_iterations) {
-        if (best_lambda == 0.0) {
+        if (best_lambda == 0.0 || o.line_search_strategy == PNP_LS_HACKBUSCH_REUSKEN) {
           vec_copy(c, prev_u.d.p, u.d.p, n);
           R.defect = defect();
           ls_failed = true;
@@ -110,9 +115,12 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
       vec_copy(c, prev_u.d.p, u.d.p, n);
     }
     if (ls_failed) {
-      if (reassembled) { status = PNP_E_LINE_SEARCH; break; }
-      continue; // retry with a freshly assembled matrix
+      // a retry is only worth it with a freshly assembled matrix, and only once per step (bounded loop)
+      if (reassembled || ++ls_retries > o.max_iterations) { status = PNP_E_LINE_SEARCH; break; }
+      reassemble_threshold = 0.0; // defect / prev_defect is exactly 1 now: forces the assembly
+      continue;
     }
+    reassemble_threshold = o.reassemble_threshold;
     R.reduction = R.defect / R.first_defect;
     R.iterations++;
     record(R.defect, lr.iterations);
@@ -141,7 +149,8 @@ LinResult slp_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, double reduct
   assemble_residual(c, op, u, r);
   vec_zero(c, z.d.p, n);
   LinResult lr = solver_apply(c, S, A, z, r, reduction);
-  vec_axpy(c, -1.0, z.d.p, u.d.p, n);
+  // an ISTL breakdown throws before the update in the reference: u stays untouched
+  if (lr.status != PNP_E_BREAKDOWN && lr.status != PNP_E_NAN) vec_axpy(c, -1.0, z.d.p, u.d.p, n);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   return lr;
 }

@@ -164,6 +164,8 @@ void mesh_set(Ctx& c, long nv, const double* x, const double* y, long nT, const 
   c.nv = nv; c.nT = nT; c.nB = nB; c.n_own = n_own;
   c.hier.clear();
   c.halo_nbr.clear(); c.halo_send_ptr.clear(); c.halo_recv_ptr.clear(); c.halo_send_ext.clear();
+  // a new mesh drops the registered multigrid levels too (they describe the old one)
+  c.mg.clear(); c.mg_gid.release(); c.mg_nglobal = 0; c.mg_aggregated = false; c.mg_replica = nullptr;
   c.invalidate_mesh_objects();
   c.carry.clear();
   c.cx.alloc(nv); c.cy.alloc(nv); c.ctri.alloc(3 * nT); c.cba.alloc(nB); c.cbb.alloc(nB); c.cbphys.alloc(nB);

@@ -188,6 +188,8 @@ pnp_status pnp_precond_apply(pnp_ctx*, int solver, int mat_handle, int d, int v)
 pnp_status pnp_solver_apply(pnp_ctx*, int solver, int mat_handle, int z, int r, double reduction, pnp_lin_result*);
 
 /* ---- Newton: Dune::PDELab::Newton (stationary_pnp.hh:280-294) ------------------------------ */
+/* Newton::setLineSearchStrategy (stationary_pnp.hh:283): PDELab 1.1's three strategies */
+enum { PNP_LS_HACKBUSCH_REUSKEN_ACCEPT_BEST = 0, PNP_LS_NONE = 1, PNP_LS_HACKBUSCH_REUSKEN = 2 };
 typedef struct {
   double reduction;             /* setReduction */
   double abs_limit;             /* PDELab default 1e-12 */
@@ -199,6 +201,7 @@ typedef struct {
   int jac_mode;                 /* PNP_JAC_* */
   double fd_epsilon;            /* NumericalJacobianVolume epsilon: 1e-11 (PDELab <= 1.1) */
   int verbosity;
+  int line_search_strategy;     /* setLineSearchStrategy: PNP_LS_* (the reference drivers pass hackbuschReuskenAcceptBest) */
 } pnp_newton_opts;
 typedef struct {
   int converged;

@@ -156,8 +156,13 @@ struct ISTLBackend_NOVLP_BCGS_ILU0 : LinearSolverBackend {  // new (north star):
 template <class GO, class LS> class Newton {
  public:
   enum Strategy { noLineSearch, hackbuschReusken, hackbuschReuskenAcceptBest };
-  Newton(GO& go, Vector& u, LS& ls) : go_(go), u_(u), ls_(ls) { pnp_newton_opts_default(&o_); }
-  void setLineSearchStrategy(Strategy) {}  // the reference always selects hackbuschReuskenAcceptBest
+  Newton(GO& go, Vector& u, LS& ls) : go_(go), u_(u), ls_(ls) {
+    pnp_newton_opts_default(&o_);
+    o_.line_search_strategy = PNP_LS_HACKBUSCH_REUSKEN; // PDELab's default until setLineSearchStrategy is called
+  }
+  void setLineSearchStrategy(Strategy s) {
+    o_.line_search_strategy = s == noLineSearch ? PNP_LS_NONE : (s == hackbuschReusken ? PNP_LS_HACKBUSCH_REUSKEN : PNP_LS_HACKBUSCH_REUSKEN_ACCEPT_BEST);
+  }
   void setReassembleThreshold(double v) { o_.reassemble_threshold = v; }
   void setVerbosityLevel(int v) { o_.verbosity = v; }
   void setReduction(double v) { o_.reduction = v; }

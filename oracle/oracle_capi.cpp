@@ -175,7 +175,7 @@ void ora_spmv(int n, const int* rowptr, const int* col, const double* val, const
   }
 }
 // opts[16] = {reduction, abs_limit, min_linear_reduction, reassemble_threshold, maxit, ls_maxit, damping,
-//             jac_mode, fd_eps, solver, prec, prec_steps, lin_maxit, verbosity}
+//             jac_mode, fd_eps, solver, prec, prec_steps, lin_maxit, verbosity, line_search_strategy}
 // result[16] = {status, converged, iterations, first_defect, defect, reduction, total_linear_iterations,
 //               total_ls_trials, jacobian_assemblies, residual_assemblies, seconds}
 // hist (optional, cap entries): defect history; lin_hist: linear iterations per step
@@ -189,7 +189,7 @@ int ora_newton(void* mh, void* ph, int op, int comp0, double* u, const double* a
   o.reduction = opts[0]; o.abs_limit = opts[1]; o.min_linear_reduction = opts[2]; o.reassemble_threshold = opts[3];
   o.maxit = (int)opts[4]; o.ls_maxit = (int)opts[5]; o.damping = opts[6]; o.jac_mode = (int)opts[7]; o.fd_eps = opts[8];
   o.solver = (int)opts[9]; o.prec = (int)opts[10]; o.prec_steps = (int)opts[11]; o.lin_maxit = (int)opts[12];
-  o.verbosity = (int)opts[13];
+  o.verbosity = (int)opts[13]; o.line_search = (int)opts[14];
   auto t0 = std::chrono::steady_clock::now();
   NewtonResult R = newton(sp, c, u, o);
   double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

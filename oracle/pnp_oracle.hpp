@@ -871,6 +871,7 @@ struct NewtonOpts {
   int jac_mode = 0; double fd_eps = 1e-11;
   int solver = SOLVER_BCGS, prec = PREC_NONE, prec_steps = 1, lin_maxit = 5000;
   int verbosity = 0;
+  int line_search = 0; // 0 hackbuschReuskenAcceptBest (what the reference drivers select), 1 noLineSearch, 2 hackbuschReusken
 };
 struct NewtonResult {
   int status = 0; // 0 ok, 1 not converged, 2 linear solver, 3 line search, 4 nan
@@ -888,13 +889,15 @@ inline NewtonResult newton(const Space& sp, const OpCtx& c, double* u, const New
   R.defect = defect(); R.first_defect = R.defect; double prev_defect = R.defect;
   R.defect_history.push_back(R.defect);
   if (!std::isfinite(R.defect)) { R.status = 4; return R; }
+  // newton.hh: a NewtonLineSearchError on a matrix that was not reassembled sets reassemble_threshold = 0 and retries
+  double reassemble_threshold = o.reassemble_threshold; int ls_retries = 0;
   while (true) {
     R.converged = R.defect < o.abs_limit || R.defect < R.first_defect * o.reduction;
     if (R.converged) break;
     if (R.iterations >= o.maxit) { R.status = 1; break; }
     // prepare_step
     bool reassembled = false;
-    if (R.defect / prev_defect > o.reassemble_threshold || R.jacobian_assemblies == 0) {
+    if (R.defect / prev_defect > reassemble_threshold || R.jacobian_assemblies == 0) {
       jacobian(sp, c, u, A, o.jac_mode, o.fd_eps); R.jacobian_assemblies++; reassembled = true;
     }
     double stop_defect = std::max(R.first_defect * o.reduction, o.abs_limit);
@@ -916,11 +919,12 @@ inline NewtonResult newton(const Space& sp, const OpCtx& c, double* u, const New
     while (true) {
       for (int k = 0; k < N; k++) u[k] += -lambda * z[k];
       R.defect = defect(); R.total_ls_trials++;
+      if (o.line_search == 1) break; // noLineSearch: full step, whatever the defect does
       bool finite = std::isfinite(R.defect);
       if (finite && R.defect <= (1.0 - lambda / 4) * prev_defect) break;
       if (finite && R.defect < best_defect) { best_defect = R.defect; best_lambda = lambda; }
       if (++i >= o.ls_maxit) {
-        if (best_lambda == 0.0) { std::copy(prev_u.begin(), prev_u.end(), u); R.defect = defect(); ls_fail = true; break; }
+        if (best_lambda == 0.0 || o.line_search == 2) { std::copy(prev_u.begin(), prev_u.end(), u); R.defect = defect(); ls_fail = true; break; }
         if (best_lambda != lambda) {
           std::copy(prev_u.begin(), prev_u.end(), u);
           for (int k = 0; k < N; k++) u[k] += -best_lambda * z[k];
@@ -931,7 +935,11 @@ inline NewtonResult newton(const Space& sp, const OpCtx& c, double* u, const New
       lambda *= o.damping;
       std::copy(prev_u.begin(), prev_u.end(), u);
     }
-    if (ls_fail) { if (reassembled) { R.status = 3; break; } else continue; }
+    if (ls_fail) {
+      if (reassembled || ++ls_retries > o.maxit) { R.status = 3; break; }
+      reassemble_threshold = 0.0; continue;
+    }
+    reassemble_threshold = o.reassemble_threshold;
     R.reduction = R.defect / R.first_defect;
     R.iterations++;
     R.defect_history.push_back(R.defect);

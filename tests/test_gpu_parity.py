@@ -120,7 +120,9 @@ def test_residual_parity(name, levels, op):
     r = c.download(vr, F)
     r_o, ab = ora.residual(m, p, op, u, a0, a1, valency=-1.0, want_abs=True)
     assert rel_err(r, r_o, ab) <= TOL
-    assert np.array_equal(r == 0, r_o == 0) or True
+    # constrained residual entries are exact zeros on both sides (constrain_residual)
+    d = ora.dirichlet(m, p, F, 0)
+    assert not r[d].any() and not r_o[d].any()
 
 
 @pytest.mark.parametrize("mode", [0, 1])
