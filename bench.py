@@ -227,7 +227,56 @@ def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps,
     if verbose:
         print("# rank %d: %d owned + %d ghost vertices, %d neighbours, %d multigrid levels" % (
             rank, fine.n_own, fine.nv - fine.n_own, len(fine.nbr), len(plans)), file=sys.stderr, flush=True)
-    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps), us, children
+    return c.operator(capi.OP_PNP, 0), fine_solver(c, capi, prec_steps), us, (children, fine)
+
+
+def parity_vs_n1(args, c, capi, u_vec, fine, rank, world, dist, torch, cfg, a, jac_mode):
+    """Relative L2 distance between the N-rank step result and the 1-rank result of the same step (rank 0 runs the whole
+    problem once more on its own GPU, outside every timed region).  Vertices are matched by their bitwise coordinates:
+    both sides are sorted lexicographically by (x, y) bit patterns on the device."""
+    def sort_xy(xb, yb):
+        i1 = torch.argsort(yb, stable=True)
+        i2 = torch.argsort(xb[i1], stable=True)
+        return i1[i2]
+    n_own = fine.n_own
+    dev = torch.device("cuda")
+    xb = torch.from_numpy(np.ascontiguousarray(fine.x[:n_own]).view(np.int64)).to(dev)
+    yb = torch.from_numpy(np.ascontiguousarray(fine.y[:n_own]).view(np.int64)).to(dev)
+    uo = torch.from_numpy(c.download(u_vec, 3).reshape(3, -1)[:, :n_own].copy()).to(dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_own], dtype=torch.int64, device=dev))
+    counts = [int(t.item()) for t in counts]
+    if rank != 0:
+        dist.send(xb, 0); dist.send(yb, 0); dist.send(uo.contiguous(), 0)
+        out = torch.zeros(1, dtype=torch.float64, device=dev)
+        dist.broadcast(out, 0)
+        return float(out.item())
+    X, Y, U = [xb], [yb], [uo]
+    for r in range(1, world):
+        tx = torch.empty(counts[r], dtype=torch.int64, device=dev); ty = torch.empty_like(tx)
+        tu = torch.empty((3, counts[r]), dtype=torch.float64, device=dev)
+        dist.recv(tx, r); dist.recv(ty, r); dist.recv(tu, r)
+        X.append(tx); Y.append(ty); U.append(tu)
+    X, Y, U = torch.cat(X), torch.cat(Y), torch.cat(U, dim=1)
+    o = sort_xy(X, Y)
+    Xs, Ys, U = X[o], Y[o], U[:, o]
+    del X, Y, o
+    # the 1-rank run of the same step
+    c1 = capi.Context(torch.cuda.current_device())
+    c1.mesh_set(**a); c1.params_read(cfg)
+    h1, s1, us1 = build_state(c1, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, False)
+    u1 = c1.vec(3); c1.vec_copy(u1, us1)
+    st, r1 = c1.newton(h1, u1, s1, c1.newton_opts(jac_mode=jac_mode, max_iterations=1), check=False)
+    g = c1.mesh_get()
+    ref = torch.from_numpy(c1.download(u1, 3).reshape(3, -1)).to(dev)
+    c1.close()
+    x1 = torch.from_numpy(g["x"].view(np.int64)).to(dev); y1 = torch.from_numpy(g["y"].view(np.int64)).to(dev)
+    o1 = sort_xy(x1, y1)
+    assert len(o1) == U.shape[1] and bool(torch.equal(x1[o1], Xs)) and bool(torch.equal(y1[o1], Ys)), "owned vertices of all ranks must tile the global mesh"
+    ref = ref[:, o1]
+    val = float((torch.linalg.norm(U - ref) / torch.linalg.norm(ref)).item())
+    dist.broadcast(torch.tensor([val], dtype=torch.float64, device=dev), 0)
+    return val
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -245,8 +294,8 @@ def run_gpu(args, rank, world, local_rank):
     if world == 1:
         h, s, us = build_state(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps, args.verbose)
     else:
-        h, s, us, _children = build_state_partitioned(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps,
-                                                      args.verbose, rank, world, dist, cfg)
+        h, s, us, (_children, fine_plan) = build_state_partitioned(c, capi, args.levels, args.coarse_level, jac_mode, args.prec_steps,
+                                                                   args.verbose, rank, world, dist, cfg)
     sizes = c.mesh_sizes()
     nv, ns = sizes["nv"], sizes["nslots"]       # local vertices (owned + ghost), local matrix slots
     n_own = c.mesh_owned()
@@ -317,6 +366,11 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         c.timer_start(); c.jacobian(h, us, A2, mode_, 1e-11); jac_ms[name_] = c.timer_stop()
     c.matrix_destroy(A2)
+    # ---- N > 1: the step's result against the 1-rank result of the same step ----
+    parity = None
+    if world > 1 and not args.no_check:
+        step(False)
+        parity = parity_vs_n1(args, c, capi, u, fine_plan, rank, world, dist, torch, cfg, a, jac_mode)
     tmax = torch.tensor([ms_dev / 1e3, wall, wall_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -357,7 +411,7 @@ def run_gpu(args, rank, world, local_rank):
         "newton_step_s": sec_step, "assembled_dofs_per_s": gdof / asm_s if asm_s > 0 else None,
         "jacobian_ms": jac_ms, "newton_step_s_with_fd_jacobian": sec_step + (jac_ms["fd_faithful"] - jac_ms["analytic"]) / 1e3,
         "krylov_iterations": int(r.linear_iterations), "line_search_trials": int(r.line_search_trials),
-        "defect_before": r.first_defect, "defect_after": r.defect,
+        "defect_before": r.first_defect, "defect_after": r.defect, "parity_vs_n1": parity,
         "spmv_gbs": achieved, "spmv_launches_timed": n_spmv,
         "spmv_by_kind": {k: {"launches": n, "avg_ms": (m / n if n else None), "bytes": b} for k, n, m, b in
                          zip(["plain", "residual", "smoother"], n_spmv_by_kind, spmv_ms_by_kind, kind_bytes)}, "spmv_share_of_step": spmv_ms / 1e3 / max(sec_dev, 1e-30),
@@ -396,6 +450,7 @@ def main():
     ap.add_argument("--jac", choices=["analytic", "fd"], default="analytic")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip parity_vs_n1 (rank 0 re-runs the step on one GPU and compares)")
     ap.add_argument("--solver-opt", action="append", default=[], metavar="NAME=VALUE",
                     help="pnp_solver_set_option for the timed step's multigrid (experiments), e.g. amg_smoother=1")
     ap.add_argument("--verbose", action="store_true")

@@ -36,6 +36,7 @@ def lib():
         for f in ("ora_mesh_create", "ora_mesh_read_gmsh", "ora_mesh_refine", "ora_params_read", "ora_params_create"):
             getattr(L, f).restype = C.c_void_p
         L.ora_pattern.restype = C.c_long
+        L.ora_pattern_sets.restype = C.c_long
         _LIB = L
     return _LIB
 
@@ -131,12 +132,14 @@ def dirichlet(mesh, params, fields, comp0=0):
     return out.astype(bool)
 
 
-def pattern(mesh, params, fields, comp0=0):
+def pattern(mesh, params, fields, comp0=0, literal=False):
+    """literal=True: the std::set-per-row restatement of PDELab's pattern rule (slow; cross-check of the fast builder)."""
+    fn = lib().ora_pattern_sets if literal else lib().ora_pattern
     N = fields * mesh.nv
     rowptr = np.zeros(N + 1, dtype=np.int32)
-    nnz = _chk(lib().ora_pattern(mesh.h, params.h, fields, comp0, _i(rowptr), None))
+    nnz = _chk(fn(mesh.h, params.h, fields, comp0, _i(rowptr), None))
     col = np.zeros(nnz, dtype=np.int32)
-    _chk(lib().ora_pattern(mesh.h, params.h, fields, comp0, _i(rowptr), _i(col)))
+    _chk(fn(mesh.h, params.h, fields, comp0, _i(rowptr), _i(col)))
     return rowptr, col
 
 

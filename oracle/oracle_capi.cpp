@@ -115,6 +115,16 @@ long ora_pattern(void* mh, void* ph, int fields, int comp0, int* rowptr, int* co
   return (long)A.col.size();
   ORA_CATCH(-1)
 }
+// the literal (std::set per row) restatement of the pattern rule: cross-check of make_pattern() in the tests
+long ora_pattern_sets(void* mh, void* ph, int fields, int comp0, int* rowptr, int* col) {
+  ORA_TRY
+  Space sp = make_space(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
+  CSR A = make_pattern_sets(sp);
+  if (rowptr) std::copy(A.rowptr.begin(), A.rowptr.end(), rowptr);
+  if (col) std::copy(A.col.begin(), A.col.end(), col);
+  return (long)A.col.size();
+  ORA_CATCH(-1)
+}
 int ora_residual(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1,
                  double valency, int intorder, double* r, double* absr) {
   ORA_TRY

@@ -584,7 +584,7 @@ inline Space make_space(const Mesh& m, const Sysparams& s, int fields, int comp0
 
 // FullVolumePattern + ISTLBCRSMatrixBackend<1,1>, PDELab-1.1 add_entry: links whose row or
 // column is constrained are dropped, constrained rows keep their diagonal (A.4).
-inline CSR make_pattern(const Space& sp) {
+inline CSR make_pattern_sets(const Space& sp) { // literal restatement (std::set per row); make_pattern() is its fast equal
   const Mesh& m = *sp.m;
   int N = sp.N(), nf = sp.fields;
   std::vector<std::set<int>> rows(N);
@@ -602,6 +602,48 @@ inline CSR make_pattern(const Space& sp) {
   for (int r = 0; r < N; r++) A.rowptr[r + 1] = A.rowptr[r] + (int)rows[r].size();
   A.col.reserve(A.rowptr[N]);
   for (int r = 0; r < N; r++) A.col.insert(A.col.end(), rows[r].begin(), rows[r].end());
+  A.val.assign(A.col.size(), 0.0);
+  return A;
+}
+
+inline CSR make_pattern(const Space& sp) {
+  const Mesh& m = *sp.m;
+  const int N = sp.N(), nf = sp.fields, nv = m.nv;
+  // vertex -> sorted vertices it shares an element with (itself included): the scalar P1 pattern.  The dof pattern
+  // follows from it because all fields of a vertex couple to all fields of its neighbours (FullVolumePattern) and the
+  // lexicographic mapper orders columns by (field, vertex).
+  std::vector<int> cnt(nv + 1, 0);
+  for (int e = 0; e < m.nT; e++) for (int i = 0; i < 3; i++) cnt[m.tri[3 * e + i] + 1] += 3;
+  for (int v = 0; v < nv; v++) cnt[v + 1] += cnt[v];
+  std::vector<int> raw(cnt[nv]), fill(cnt.begin(), cnt.end() - 1);
+  for (int e = 0; e < m.nT; e++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) raw[fill[m.tri[3 * e + i]]++] = m.tri[3 * e + j];
+  std::vector<int> nptr(nv + 1, 0), nbr; nbr.reserve(raw.size() / 2);
+  for (int v = 0; v < nv; v++) {
+    auto b = raw.begin() + cnt[v], e = raw.begin() + cnt[v + 1];
+    std::sort(b, e);
+    e = std::unique(b, e);
+    nbr.insert(nbr.end(), b, e);
+    nptr[v + 1] = (int)nbr.size();
+  }
+  CSR A; A.n = N; A.rowptr.assign(N + 1, 0);
+  for (int ki = 0; ki < nf; ki++) for (int v = 0; v < nv; v++) {
+    const int gi = sp.gdof(ki, v);
+    int len = 0;
+    if (sp.dirichlet[gi]) len = 1; // constrained rows keep their diagonal only
+    else for (int kj = 0; kj < nf; kj++) for (int t = nptr[v]; t < nptr[v + 1]; t++) len += !sp.dirichlet[sp.gdof(kj, nbr[t])];
+    A.rowptr[gi + 1] = len;
+  }
+  for (int r = 0; r < N; r++) A.rowptr[r + 1] += A.rowptr[r];
+  A.col.resize(A.rowptr[N]);
+  for (int ki = 0; ki < nf; ki++) for (int v = 0; v < nv; v++) {
+    const int gi = sp.gdof(ki, v);
+    int o = A.rowptr[gi];
+    if (sp.dirichlet[gi]) { A.col[o] = gi; continue; }
+    for (int kj = 0; kj < nf; kj++) for (int t = nptr[v]; t < nptr[v + 1]; t++) {
+      const int gj = sp.gdof(kj, nbr[t]);
+      if (!sp.dirichlet[gj]) A.col[o++] = gj;
+    }
+  }
   A.val.assign(A.col.size(), 0.0);
   return A;
 }

@@ -70,6 +70,20 @@ def test_gmsh_reader(name, tmp_path):
         assert np.array_equal(g[k], a[k]), k
 
 
+@pytest.mark.parametrize("name", util.MESHES)
+def test_gmsh_reader_on_the_reference_files(name):
+    """The reference's own mesh files, committed verbatim (tests/golden/msh/: Gmsh 2.1 for one_wall and pore, 2.2 for the
+    others; GmshReader call at pnp_solver_main.cc:82-91): the product reader yields exactly the fixture arrays."""
+    import os
+    capi = _capi()
+    c = capi.Context(0)
+    c.mesh_read_gmsh(os.path.join(util.GOLDEN, "msh", name + ".msh"))
+    g = c.mesh_get()
+    a = util.load_mesh_arrays(name)
+    for k in a:
+        assert np.array_equal(g[k], a[k]), k
+
+
 @pytest.mark.parametrize("name,levels", [("one_wall", 3), ("pore_small", 2), ("pore", 1)])
 def test_device_refinement_matches_oracle(name, levels):
     c, m, p = make_ctx(name, levels=levels)

@@ -37,6 +37,26 @@ def test_gmsh_reader_semantics(tmp_path):
         assert np.array_equal(getattr(m, k), a[k]), k
 
 
+@pytest.mark.parametrize("name", util.MESHES)
+def test_gmsh_reader_on_the_reference_files(name):
+    """tests/golden/msh/*.msh are the reference's own files (Gmsh 2.1 and 2.2 ASCII, copied verbatim by
+    scripts/make_fixtures.py): reading them gives the committed fixture arrays."""
+    m = ora.Mesh.read_gmsh(os.path.join(util.GOLDEN, "msh", name + ".msh"))
+    a = util.load_mesh_arrays(name)
+    for k in a:
+        assert np.array_equal(getattr(m, k), a[k]), k
+
+
+@pytest.mark.parametrize("name", util.MESHES)
+def test_fast_pattern_equals_the_literal_restatement(name):
+    """make_pattern() (vertex adjacency, O(nnz)) against the std::set-per-row restatement of PDELab's pattern rule."""
+    m, p = case(name, 1)
+    for F, comp0 in ((1, 0), (1, 1), (1, 2), (3, 0)):
+        rp, col = ora.pattern(m, p, F, comp0)
+        rp2, col2 = ora.pattern(m, p, F, comp0, literal=True)
+        assert np.array_equal(rp, rp2) and np.array_equal(col, col2)
+
+
 def test_config_reader(tmp_path):
     p = ora.Params.read(util.cfg_path("pore"))
     assert p.sys[0] == 7 and p.sys[1] == 1 and p.sys[4] == 3.1415 and p.sys[7] == 1e-9 and p.sys[8] == 1e-8
