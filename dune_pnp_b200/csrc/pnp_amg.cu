@@ -22,7 +22,7 @@
 #include <cstring>
 
 #include "pnp_common.cuh"
-#include "pnp_spmv.cuh"
+#include "pnp_spmv_tma.cuh"
 
 namespace pnp {
 
@@ -489,7 +489,7 @@ void level_op(Ctx& c, const Amg& A, const Level& l, const double* x, const doubl
   const bool fine = &l == A.L[0].get();
   if (A.distributed) halo_exchange(*l.lc, const_cast<double*>(x), A.F); // ghost columns of the iterate
   if (fine) c.prof_mark(EPI == EPI_RESIDUAL ? 1 : 2);
-  launch_star_op<EPI, 0>(c, A.NP, a);
+  launch_star_op_auto<EPI, 0>(c, A.NP, a);
   if (fine) c.prof_mark();
 }
 

@@ -44,10 +44,12 @@ template <class T> struct DBuf {
   DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
   ~DBuf() { release(); }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  // 64 bytes of slack behind every array: the bulk copies of the streaming kernels (pnp_spmv_tma.cuh) round their
+  // extent up to 16 bytes and may read a few bytes past the last element
   void alloc(size_t n_) {
     release();
     n = n_;
-    if (n) PNP_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    if (n) PNP_CUDA(cudaMalloc(&p, n * sizeof(T) + 64));
   }
   void zero(cudaStream_t s) { if (n) PNP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const T* h, size_t cnt, cudaStream_t s) {

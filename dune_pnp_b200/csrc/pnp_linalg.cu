@@ -13,7 +13,7 @@
 #include <cmath>
 
 #include "pnp_common.cuh"
-#include "pnp_spmv.cuh"
+#include "pnp_spmv_tma.cuh"
 
 namespace pnp {
 
@@ -160,8 +160,8 @@ void spmv_dots(Ctx& c, const Matrix& A, double* x, double* y, int ndot, const do
   StarOpArgs a{c.rp.p, c.adj.p, A.vals.p, c.nslots, (int)c.n_own, x, y};
   a.w1 = w1; a.partial = c.red_partial.p;
   c.prof_mark();
-  const int grid = ndot == 0 ? launch_star_op<EPI_PLAIN, 0>(c, A.nplanes, a)
-                 : ndot == 1 ? launch_star_op<EPI_PLAIN, 1>(c, A.nplanes, a) : launch_star_op<EPI_PLAIN, 2>(c, A.nplanes, a);
+  const int grid = ndot == 0 ? launch_star_op_auto<EPI_PLAIN, 0>(c, A.nplanes, a)
+                 : ndot == 1 ? launch_star_op_auto<EPI_PLAIN, 1>(c, A.nplanes, a) : launch_star_op_auto<EPI_PLAIN, 2>(c, A.nplanes, a);
   c.prof_mark();
   if (ndot > 0) finish_reduce(c, grid, ndot, dots);
 }

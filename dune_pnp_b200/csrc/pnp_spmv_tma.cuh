@@ -1,0 +1,377 @@
+// pnp_spmv_tma.cuh -- the streaming form of the star SpMV (k_star_op, pnp_spmv.cuh) for levels large enough to fill the
+// GPU: one persistent CTA per SM; a producer warp streams the value planes, the column indices, the row pointers and the
+// epilogue operands of 128-row tiles into shared memory with 1-D bulk copies (cp.async.bulk, the TMA engine) through a
+// ring of mbarrier-guarded stages, while eight consumer warps do the products out of shared memory.  The bytes in flight
+// no longer sit in registers behind the scoreboard (the plain-load kernel ran at 49 % warps active, 62-64 registers and
+// ~14 long-scoreboard stall cycles per issue, profiles/hot_kernels_full_r01d_summary.txt); only the x gathers -- L1/L2
+// hits after the locality renumbering -- remain ordinary loads, and all of a warp's gathers for a tile step are issued
+// before the first product.
+//
+// A tile's slots are ONE contiguous range [rp[r0], rp[r0+128]) of every plane, so each plane is one bulk copy; source
+// addresses are rounded down and sizes up to the 16-byte granularity bulk copies need (arrays carry 64 bytes of slack,
+// DBuf::alloc).  Tiles with more than TMA_CAP slots (average valence > 6.5 over 128 rows: unrefined Gmsh meshes only)
+// read their slots with plain loads.
+//
+// The damped point-block Jacobi epilogue inverts every vertex's 3x3 diagonal block from the diagonal slot that is in
+// shared memory anyway, instead of reading a stored inverse (72 B/vertex, 12 % of the smoother's traffic).
+#pragma once
+#include "pnp_spmv.cuh"
+
+namespace pnp {
+
+constexpr int TMA_TR = 128;                      // rows per tile
+constexpr int TMA_NW = 8;                        // consumer warps
+constexpr int TMA_THREADS = (TMA_NW + 1) * 32;   // + 1 producer warp
+constexpr int TMA_CAP = 960;                     // staged slots per tile and plane
+constexpr int TMA_MAX_STAGES = 3;
+
+template <int NP> struct TmaLayout {
+  static constexpr int F = NP == 1 ? 1 : 3;
+  static constexpr int PLANE = (TMA_CAP + 2) * 8;                    // bytes of one value plane of a stage
+  static constexpr int COLS = NP * PLANE;                            // (CAP + 4) column indices
+  static constexpr int RP = COLS + (TMA_CAP + 4) * 4;                // (TR + 4) row pointers
+  static constexpr int B = RP + (TMA_TR + 4) * 4;                    // F*TR (+2) doubles: right-hand side / dot operand
+  static constexpr int XO = B + (F * TMA_TR + 2) * 8;                // F*TR (+2) doubles: the rows' own x (smoother)
+  static constexpr int STAGE = XO + (F * TMA_TR + 2) * 8;
+  static constexpr int YBUF = TMA_TR * F * 8;                        // output staging, per consumer warp a slice
+  static constexpr int HEAD = 128;                                   // mbarriers
+  static_assert(PLANE % 16 == 0 && COLS % 16 == 0 && RP % 16 == 0 && B % 16 == 0 && XO % 16 == 0 && STAGE % 16 == 0, "bulk copy alignment");
+  static constexpr int smem_bytes(int stages) { return HEAD + stages * STAGE + YBUF; }
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// inverse of the diagonal block B = [a b c; d e 0; f 0 g] (planes 0..6 of the diagonal slot), row `k`; the same rule as
+// k_dinv (pnp_amg.cu): a (near-)singular block falls back to the scalar diagonal
+__device__ __forceinline__ void block_inverse_row(const double* dv, int k, double* o) {
+  const double a = dv[0], b = dv[1], c_ = dv[2], d = dv[3], e = dv[4], f = dv[5], g = dv[6];
+  const double det = a * e * g - b * d * g - c_ * e * f;
+  const double scale = fabs(a * e * g) + fabs(b * d * g) + fabs(c_ * e * f);
+  if (fabs(det) > 1e-12 * scale && scale > 0.0) {
+    const double id = 1.0 / det;
+    if (k == 0) { o[0] = e * g * id; o[1] = -b * g * id; o[2] = -c_ * e * id; }
+    else if (k == 1) { o[0] = -d * g * id; o[1] = (a * g - c_ * f) * id; o[2] = c_ * d * id; }
+    else { o[0] = -e * f * id; o[1] = b * f * id; o[2] = (a * e - b * d) * id; }
+  } else {
+    const double dd = k == 0 ? a : (k == 1 ? e : g);
+    const double inv = dd != 0.0 ? 1.0 / dd : 0.0;
+    o[0] = k == 0 ? inv : 0.0; o[1] = k == 1 ? inv : 0.0; o[2] = k == 2 ? inv : 0.0;
+  }
+}
+
+template <int NP, int EPI, int NDOT>
+__global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs a, const int nstages) {
+  using L = TmaLayout<NP>;
+  constexpr int F = L::F;
+  constexpr int RW = TMA_TR / TMA_NW;   // rows per consumer warp and tile
+  constexpr int STEPS = RW / 4;         // 8 lanes share a row: 4 rows per step
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + TMA_MAX_STAGES;
+  unsigned char* stages = smem + L::HEAD;
+  double* ybuf = reinterpret_cast<double*>(stages + (size_t)nstages * L::STAGE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (a.nv + TMA_TR - 1) / TMA_TR;
+  const int sp = (int)(a.stride & 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  double dsum[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+  for (int j = 0; j < (NDOT > 0 ? NDOT : 1); j++) dsum[j] = 0.0;
+
+  if (warp == TMA_NW) {
+    // ---------------- producer: lane 0 feeds the ring; the other lanes of the warp walk the loop with it (the kernel's
+    // closing __syncthreads wants converged warps) ----------------
+    int t = blockIdx.x;
+    int lo_n = 0, hi_n = 0;
+    if (lane == 0 && t < ntiles) { lo_n = a.rp[t * TMA_TR]; hi_n = a.rp[min(t * TMA_TR + TMA_TR, a.nv)]; }
+    for (int it = 0; t < ntiles; t += gridDim.x, it++) {
+      if (lane == 0) {
+        const int lo = lo_n, hi = hi_n;
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) { lo_n = a.rp[tn * TMA_TR]; hi_n = a.rp[min(tn * TMA_TR + TMA_TR, a.nv)]; } // in flight during the wait
+        const int stage = it % nstages;
+        const unsigned parity = (unsigned)((it / nstages) & 1);
+        mbar_wait(&empty[stage], parity ^ 1u);
+        unsigned char* st = stages + (size_t)stage * L::STAGE;
+        const int r0 = t * TMA_TR, rows = min(TMA_TR, a.nv - r0);
+        const bool staged = hi - lo <= TMA_CAP;
+        // byte counts first (one expect_tx), then the copies
+        unsigned nb_plane[NP];
+        unsigned total = 0;
+        const int lo_c = lo & ~3;
+        const unsigned nb_cols = (unsigned)(((hi - lo_c) + 3) & ~3) * 4u;
+        if (staged) {
+#pragma unroll
+          for (int p = 0; p < NP; p++) {
+            const int o = (lo + p * sp) & 1;
+            nb_plane[p] = (unsigned)(((hi - lo + o) + 1) & ~1) * 8u;
+            total += nb_plane[p];
+          }
+          total += nb_cols;
+        }
+        const unsigned nb_rp = (unsigned)((rows + 1 + 3) & ~3) * 4u;
+        const unsigned nb_vec = (unsigned)((F * rows + 1) & ~1) * 8u;
+        total += nb_rp;
+        constexpr bool need_b = EPI != EPI_PLAIN || NDOT >= 1;
+        constexpr bool need_xo = EPI == EPI_JACOBI;
+        if (need_b) total += nb_vec;
+        if (need_xo) total += nb_vec;
+        mbar_expect_tx(&full[stage], total);
+        if (staged) {
+#pragma unroll
+          for (int p = 0; p < NP; p++) {
+            const int o = (lo + p * sp) & 1;
+            bulk_g2s(st + p * L::PLANE, a.vals + (size_t)p * a.stride + (lo - o), nb_plane[p], &full[stage]);
+          }
+          bulk_g2s(st + L::COLS, a.col + lo_c, nb_cols, &full[stage]);
+        }
+        bulk_g2s(st + L::RP, a.rp + r0, nb_rp, &full[stage]);
+        if (need_b) bulk_g2s(st + L::B, (EPI == EPI_PLAIN ? a.w1 : a.b) + (size_t)F * r0, nb_vec, &full[stage]);
+        if (need_xo) bulk_g2s(st + L::XO, a.x + (size_t)F * r0, nb_vec, &full[stage]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- consumers ----------------
+    const int sub = lane & 7, grp = lane >> 3;
+    double* yw = ybuf + warp * RW * F;
+    int t = blockIdx.x;
+    for (int it = 0; t < ntiles; t += gridDim.x, it++) {
+      const int stage = it % nstages;
+      const unsigned parity = (unsigned)((it / nstages) & 1);
+      mbar_wait(&full[stage], parity);
+      const unsigned char* st = stages + (size_t)stage * L::STAGE;
+      const double* sv = reinterpret_cast<const double*>(st);
+      const unsigned* sc = reinterpret_cast<const unsigned*>(st + L::COLS);
+      const int* srp = reinterpret_cast<const int*>(st + L::RP);
+      const double* sb = reinterpret_cast<const double*>(st + L::B);
+      const double* sxo = reinterpret_cast<const double*>(st + L::XO);
+      const int r0 = t * TMA_TR, rows = min(TMA_TR, a.nv - r0);
+      const int lo = srp[0], hi = srp[rows];
+      const bool staged = hi - lo <= TMA_CAP; // block-uniform
+      const int cbase = lo & ~3;
+      int vb[NP]; // plane p, slot s -> sv[vb[p] + s]
+#pragma unroll
+      for (int p = 0; p < NP; p++) vb[p] = p * (TMA_CAP + 2) - lo + ((lo + p * sp) & 1);
+      int bb[STEPS], ee[STEPS];
+      double acc[STEPS][F];
+#pragma unroll
+      for (int q = 0; q < STEPS; q++) {
+        const int rl = RW * warp + 4 * q + grp;
+        const bool valid = rl < rows;
+        bb[q] = valid ? srp[rl] : hi;
+        ee[q] = valid ? srp[rl + 1] : hi;
+#pragma unroll
+        for (int k = 0; k < F; k++) acc[q][k] = 0.0;
+      }
+      if (staged) {
+        // first eight slots of every row: all column indices, then all x gathers, then the products
+        unsigned cc[STEPS];
+        bool ok[STEPS];
+        double xv[STEPS][F];
+#pragma unroll
+        for (int q = 0; q < STEPS; q++) {
+          const int s = bb[q] + sub;
+          ok[q] = s < ee[q];
+          cc[q] = ok[q] ? (sc[s - cbase] & STAR_VMASK) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < STEPS; q++) {
+#pragma unroll
+          for (int k = 0; k < F; k++) xv[q][k] = ok[q] ? a.x[(size_t)F * cc[q] + k] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < STEPS; q++) {
+          if (ok[q]) {
+            const int s = bb[q] + sub;
+            if (NP == 1) acc[q][0] += sv[vb[0] + s] * xv[q][0];
+            else {
+              const double x0 = xv[q][0], x1 = xv[q][1 % F], x2 = xv[q][2 % F];
+              acc[q][0] += sv[vb[0] + s] * x0 + sv[vb[1 % NP] + s] * x1 + sv[vb[2 % NP] + s] * x2;
+              acc[q][1 % F] += sv[vb[3 % NP] + s] * x0 + sv[vb[4 % NP] + s] * x1;
+              acc[q][2 % F] += sv[vb[5 % NP] + s] * x0 + sv[vb[6 % NP] + s] * x2;
+            }
+          }
+        }
+        // rows with more than eight slots (valence > 7)
+#pragma unroll
+        for (int q = 0; q < STEPS; q++) {
+          for (int s = bb[q] + 8 + sub; s < ee[q]; s += 8) {
+            const size_t c = sc[s - cbase] & STAR_VMASK;
+            if (NP == 1) acc[q][0] += sv[vb[0] + s] * a.x[c];
+            else {
+              const double x0 = a.x[3 * c], x1 = a.x[3 * c + 1], x2 = a.x[3 * c + 2];
+              acc[q][0] += sv[vb[0] + s] * x0 + sv[vb[1 % NP] + s] * x1 + sv[vb[2 % NP] + s] * x2;
+              acc[q][1 % F] += sv[vb[3 % NP] + s] * x0 + sv[vb[4 % NP] + s] * x1;
+              acc[q][2 % F] += sv[vb[5 % NP] + s] * x0 + sv[vb[6 % NP] + s] * x2;
+            }
+          }
+        }
+      } else {
+        // over-full tile: slots straight from global memory
+#pragma unroll
+        for (int q = 0; q < STEPS; q++) {
+          for (int s = bb[q] + sub; s < ee[q]; s += 8) {
+            const size_t c = a.col[s] & STAR_VMASK;
+            if (NP == 1) acc[q][0] += a.vals[s] * a.x[c];
+            else {
+              const double x0 = a.x[3 * c], x1 = a.x[3 * c + 1], x2 = a.x[3 * c + 2];
+              const double* v = a.vals + s;
+              acc[q][0] += v[0] * x0 + v[(1 % NP) * a.stride] * x1 + v[(2 % NP) * a.stride] * x2;
+              acc[q][1 % F] += v[(3 % NP) * a.stride] * x0 + v[(4 % NP) * a.stride] * x1;
+              acc[q][2 % F] += v[(5 % NP) * a.stride] * x0 + v[(6 % NP) * a.stride] * x2;
+            }
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < STEPS; q++) {
+#pragma unroll
+        for (int k = 0; k < F; k++)
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) acc[q][k] += __shfl_xor_sync(0xffffffffu, acc[q][k], o);
+        const int rl = RW * warp + 4 * q + grp;
+        const bool mine = sub < F && rl < rows;
+        const double ax = F == 1 ? acc[q][0] : (sub == 0 ? acc[q][0] : (sub == 1 ? acc[q][1 % F] : acc[q][2 % F]));
+        const int il = F * rl + sub; // tile-local dof
+        double yv = 0.0;
+        if (EPI == EPI_PLAIN) {
+          yv = ax;
+          if (mine) {
+            if (NDOT >= 1) dsum[0] += ax * sb[il];
+            if (NDOT >= 2) dsum[NDOT >= 2 ? 1 : 0] += ax * ax;
+          }
+        } else if (EPI == EPI_RESIDUAL) {
+          yv = mine ? sb[il] - ax : 0.0;
+        } else { // damped (point-block) Jacobi step: y = x + omega * D^-1 (b - A x)
+          const double rr = mine ? sb[il] - ax : 0.0;
+          double z;
+          if (F == 3) {
+            const int g8 = lane & ~7;
+            const double r0v = __shfl_sync(0xffffffffu, rr, g8), r1v = __shfl_sync(0xffffffffu, rr, g8 + 1),
+                         r2v = __shfl_sync(0xffffffffu, rr, g8 + 2);
+            z = 0.0;
+            if (mine) {
+              double dv[NP];
+#pragma unroll
+              for (int p = 0; p < NP; p++) dv[p] = staged ? sv[vb[p] + bb[q]] : a.vals[(size_t)p * a.stride + bb[q]];
+              double o[3];
+              block_inverse_row(dv, sub, o);
+              z = o[0] * r0v + o[1] * r1v + o[2] * r2v;
+            }
+          } else {
+            z = 0.0;
+            if (mine) {
+              const double d = staged ? sv[vb[0] + bb[q]] : a.vals[bb[q]];
+              z = (d != 0.0 ? 1.0 / d : 0.0) * rr;
+            }
+          }
+          yv = mine ? sxo[il] + a.omega * z : 0.0;
+        }
+        if (sub < F) yw[F * (4 * q + grp) + sub] = yv;
+      }
+      __syncwarp();
+      // this warp's RW*F results are contiguous in y
+      {
+        const size_t g0 = (size_t)F * (r0 + RW * warp);
+        const size_t gend = (size_t)F * a.nv;
+        for (int i = lane; i < RW * F; i += 32)
+          if (g0 + i < gend) a.y[g0 + i] = yw[i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+  }
+  if (NDOT > 0) {
+    __shared__ double sm[NDOT > 0 ? NDOT : 1][TMA_NW + 1];
+#pragma unroll
+    for (int j = 0; j < (NDOT > 0 ? NDOT : 1); j++) {
+      double s = dsum[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) sm[j][warp] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int j = 0; j < (NDOT > 0 ? NDOT : 1); j++) {
+        double s = lane < TMA_NW ? sm[j][lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) a.partial[(long)blockIdx.x * NDOT + j] = s;
+      }
+    }
+  }
+}
+
+// The streaming kernel serves levels with at least two tiles per SM whose arrays sit on 16-byte boundaries; everything
+// else (small levels, the Chebyshev epilogue) stays with the plain-load kernel.
+inline bool star_op_tma_ok(const Ctx& c, const StarOpArgs& a, int epi) {
+  static const bool off = std::getenv("PNP_NO_TMA") != nullptr;
+  // PNP_TMA_MIN_ROWS: test hook, lets the small parity meshes run through the streaming kernel as well
+  static const long min_rows_env = [] { const char* e = std::getenv("PNP_TMA_MIN_ROWS"); return e ? std::atol(e) : -1l; }();
+  if (off || epi == EPI_CHEBYSHEV) return false;
+  if ((long)a.nv < (min_rows_env >= 0 ? min_rows_env : 2l * TMA_TR * c.sm_count)) return false;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return al(a.rp) && al(a.col) && al(a.vals) && al(a.x) && (!a.b || al(a.b)) && (!a.w1 || al(a.w1));
+}
+
+inline int star_op_tma_stages() {
+  static const int n = [] { const char* e = std::getenv("PNP_TMA_STAGES"); int v = e ? std::atoi(e) : 3; return v < 2 ? 2 : (v > TMA_MAX_STAGES ? TMA_MAX_STAGES : v); }();
+  return n;
+}
+
+template <int NP, int EPI, int NDOT>
+inline int launch_star_op_tma_inst(Ctx& c, const StarOpArgs& a) {
+  using L = TmaLayout<NP>;
+  const int nstages = star_op_tma_stages();
+  const int smem = L::smem_bytes(nstages);
+  static unsigned long long configured = 0; // per device bit: the attribute is per device and function
+  if (!(configured >> (c.device & 63) & 1ull)) {
+    PNP_CUDA(cudaFuncSetAttribute(k_star_op_tma<NP, EPI, NDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::smem_bytes(TMA_MAX_STAGES)));
+    configured |= 1ull << (c.device & 63);
+  }
+  const int ntiles = (a.nv + TMA_TR - 1) / TMA_TR;
+  const int grid = ntiles < c.sm_count ? ntiles : c.sm_count;
+  k_star_op_tma<NP, EPI, NDOT><<<grid, TMA_THREADS, smem, c.stream>>>(a, nstages);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  return grid;
+}
+
+// launches the streaming or the plain-load kernel; returns the grid size (number of partial-sum blocks)
+template <int EPI, int NDOT>
+inline int launch_star_op_auto(Ctx& c, int nplanes, const StarOpArgs& a) {
+  if (EPI != EPI_CHEBYSHEV && star_op_tma_ok(c, a, EPI)) {
+    constexpr int E = EPI == EPI_CHEBYSHEV ? EPI_PLAIN : EPI; // (never instantiated for Chebyshev)
+    return nplanes == 1 ? launch_star_op_tma_inst<1, E, NDOT>(c, a) : launch_star_op_tma_inst<7, E, NDOT>(c, a);
+  }
+  return launch_star_op<EPI, NDOT>(c, nplanes, a);
+}
+
+} // namespace pnp

@@ -164,3 +164,18 @@ def test_residual_jacobian_spmv_parity_level5():
     c.spmv(A, vx, vy)
     y_o = ora.spmv(rp, col, val, x)
     assert rel_err(c.download(vy, 1), y_o, ora.spmv(rp, col, np.abs(val), np.abs(x))) <= TOL
+
+
+def test_streaming_spmv_kernel_on_the_small_meshes():
+    """k_star_op_tma (bulk-copy pipeline, pnp_spmv_tma.cuh) normally serves levels with >= 2 tiles per SM; with
+    PNP_TMA_MIN_ROWS=1 every SpMV / multigrid level operation of the small-mesh parity tests goes through it: partial last
+    tiles, tiles of unrefined Gmsh meshes with more slots than the stage holds (plain-load fallback), both plane counts."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PNP_TMA_MIN_ROWS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = "spmv_parity or linear_solvers_on_poisson or multigrid_preconditioner or multigrid_options or newton_pnp_from_pb_matches_oracle"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
+                          "-k", sel], env=env, cwd=root, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout
