@@ -397,5 +397,19 @@ class Context:
     def write_cell_data(self, vec, filename):
         self._ck(lib().pnp_write_cell_data(self._h, vec, filename.encode()))
 
+    def write_vtk(self, name, vecs, names, ascii=False):
+        arr = (C.c_int * len(vecs))(*vecs)
+        nm = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        self._ck(lib().pnp_write_vtk(self._h, name.encode(), len(vecs), arr, nm, int(ascii)))
+
+    def matrix_set_csr(self, op, A, rowptr, col, val):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        self._ck(lib().pnp_matrix_set_csr(self._h, op, A, _i(rowptr), _i(col), _d(val)))
+
+    def mesh_renumber(self, new_index):
+        new_index = np.ascontiguousarray(new_index, dtype=np.int32)
+        self._ck(lib().pnp_mesh_renumber(self._h, _i(new_index)))
+
     def interpolate_bcext(self, component, pb_vec, out_vec):
         self._ck(lib().pnp_interpolate_bcext(self._h, component, -1 if pb_vec is None else pb_vec, out_vec))

@@ -554,6 +554,18 @@ pnp_status pnp_write_cell_data(pnp_ctx* ctx, int v, const char* filename) {
   write_cell_data(c, c.vec(v), filename);
   API_END
 }
+pnp_status pnp_write_vtk(pnp_ctx* ctx, const char* name, int n, const int* vec_handles, const char* const* names, int ascii) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(name && n >= 0 && (n == 0 || (vec_handles && names)), PNP_E_ARG, "null arguments");
+  std::vector<const Vec*> f(n);
+  for (int i = 0; i < n; i++) f[i] = &c.vec(vec_handles[i]);
+  write_vtk(c, name, n, f.data(), names, ascii);
+  API_END
+}
+pnp_status pnp_matrix_set_csr(pnp_ctx* ctx, int op_handle, int mat_handle, const int* rowptr, const int* col, const double* val) {
+  API_BEGIN(ctx) matrix_import(c, op_handle, c.mat(mat_handle), rowptr, col, val); API_END
+}
+pnp_status pnp_mesh_renumber(pnp_ctx* ctx, const int* new_index) { API_BEGIN(ctx) mesh_renumber(c, new_index); API_END }
 pnp_status pnp_mesh_owned(pnp_ctx* ctx, long* n_own) { API_BEGIN(ctx) if (n_own) *n_own = c.n_own; API_END }
 pnp_status pnp_interpolate_bcext(pnp_ctx* ctx, int component, int pb_vec, int out_vec) {
   API_BEGIN(ctx)

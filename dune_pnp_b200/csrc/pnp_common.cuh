@@ -259,6 +259,8 @@ void vec_upload(Ctx&, Vec&, const double* host_lex);
 void vec_download(Ctx&, const Vec&, double* host_lex);
 long pattern_export(Ctx&, int op_handle, int* rowptr, int* col);
 void matrix_export(Ctx&, int op_handle, const Matrix&, double* val);
+void matrix_import(Ctx&, int op_handle, Matrix&, const int* rowptr, const int* col, const double* val);
+void mesh_renumber(Ctx&, const int* new_index);
 // pnp_host.cpp-like logic in pnp_hostside.cu
 void read_gmsh_file(const std::string& path, std::vector<double>& x, std::vector<double>& y, std::vector<int>& tri,
                     std::vector<int>& ba, std::vector<int>& bb, std::vector<int>& bphys);
@@ -283,5 +285,6 @@ int sweep_levels(const Solver&, bool ilu);
 // pnp_output.cu
 void ion_flux(Ctx&, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, double* im);
 void write_cell_data(Ctx&, const Vec& u, const std::string& filename);
+void write_vtk(Ctx&, const std::string& name, int nfields, const Vec* const* fields, const char* const* names, int ascii);
 
 } // namespace pnp

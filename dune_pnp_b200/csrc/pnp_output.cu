@@ -1,11 +1,14 @@
 // pnp_output.cu -- the two diagnostics the reference's time loop produces from the fields:
 //   calcIonFlux          /root/reference/src/ionFlux.hh:8-96        per-surface ion currents -> current.dat
 //   DataWriter::writeData /root/reference/src/datawriter.hh:45-94   cell-centre "x y  value  gradx grady" text files
+//   Dune::VTKWriter<GV>(gv, conforming) + addVertexData + write(name, binaryappended)
+//                        /root/reference/src/instationary_pnp_from_pb_md.hh:337-340,440; stationary_pnp_from_pb.hh:190-192
 // The ion current is a reduction over the O(sqrt N) boundary faces: one thread per face on the device, the per-surface
 // sums on the host in face order (deterministic).  writeData is host I/O by nature: the field is downloaded once and the
 // element loop runs on the host.
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 
 #include "pnp_common.cuh"
 
@@ -101,6 +104,89 @@ void write_cell_data(Ctx& c, const Vec& u, const std::string& filename) {
     std::fprintf(f, "%.5e %.5e\t%.5e\t%.5e %.5e\n", cx, cy, val, gx, gy);
   }
   std::fclose(f);
+}
+
+// Dune::VTKWriter (dune-grid 2.2, conforming): one .vtu piece with vertex data (Float32, as DUNE writes it), points,
+// cells (triangles: connectivity, offsets, types = 5).  binaryappended: every array is "<uint32 byte count><raw bytes>"
+// behind the '_' of <AppendedData encoding="raw">, the DataArray offsets count from there; ascii: the same arrays in
+// place.  Several ranks: rank r writes the piece "s<world>:p<rank>:<name>.vtu" (its owned + ghost vertices and all its
+// elements) and rank 0 the "s<world>:<name>.pvtu" index, as DUNE's parallel writer names them.
+void write_vtk(Ctx& c, const std::string& name, int nfields, const Vec* const* fields, const char* const* names, int ascii) {
+  PNP_REQUIRE(c.finalized && nfields >= 0, PNP_E_ARG, "VTK writer: finalized mesh expected");
+  for (int i = 0; i < nfields; i++)
+    PNP_REQUIRE(fields[i] && fields[i]->fields == 1 && names[i], PNP_E_ARG, "VTK writer: 1-field vectors with names expected");
+  const long nv = c.nv, nT = c.nT;
+  std::vector<std::vector<float>> data(nfields, std::vector<float>((size_t)nv));
+  std::vector<double> lex((size_t)nv);
+  for (int i = 0; i < nfields; i++) {
+    vec_download(c, *fields[i], lex.data());
+    for (long v = 0; v < nv; v++) data[i][v] = (float)lex[v];
+  }
+  const std::vector<double> x = c.cx.to_host(c.stream), y = c.cy.to_host(c.stream);
+  const std::vector<int> tri = c.ctri.to_host(c.stream);
+  std::vector<float> pts(3 * (size_t)nv);
+  for (long v = 0; v < nv; v++) { pts[3 * v] = (float)x[v]; pts[3 * v + 1] = (float)y[v]; pts[3 * v + 2] = 0.0f; }
+  std::vector<int> offs((size_t)nT);
+  for (long e = 0; e < nT; e++) offs[e] = (int)(3 * (e + 1));
+  std::vector<unsigned char> types((size_t)nT, 5); // VTK_TRIANGLE
+  char piece[512];
+  if (c.world > 1) std::snprintf(piece, sizeof piece, "s%04d:p%04d:%s.vtu", c.world, c.rank, name.c_str());
+  else std::snprintf(piece, sizeof piece, "%s.vtu", name.c_str());
+  // a directory part of `name` stays in front of the DUNE prefix
+  std::string dir, base = name;
+  const size_t slash = name.find_last_of('/');
+  if (slash != std::string::npos) { dir = name.substr(0, slash + 1); base = name.substr(slash + 1); }
+  if (c.world > 1) std::snprintf(piece, sizeof piece, "%ss%04d:p%04d:%s.vtu", dir.c_str(), c.world, c.rank, base.c_str());
+  std::FILE* f = std::fopen(piece, "wb");
+  PNP_REQUIRE(f, PNP_E_CONFIG, std::string("cannot open ") + piece);
+  unsigned long offset = 0;
+  std::vector<std::pair<const void*, unsigned>> blobs; // appended arrays in file order
+  auto array = [&](const char* type, const char* nm, int ncomp, const void* ptr, size_t count, size_t elsize, auto print) {
+    std::fprintf(f, "<DataArray type=\"%s\" Name=\"%s\" NumberOfComponents=\"%d\" ", type, nm, ncomp);
+    if (ascii) {
+      std::fprintf(f, "format=\"ascii\">\n");
+      for (size_t i = 0; i < count; i++) { print(i); std::fputc((i + 1) % 12 == 0 || i + 1 == count ? '\n' : ' ', f); }
+      std::fprintf(f, "</DataArray>\n");
+    } else {
+      std::fprintf(f, "format=\"appended\" offset=\"%lu\" />\n", offset);
+      blobs.push_back({ptr, (unsigned)(count * elsize)});
+      offset += 4 + count * elsize;
+    }
+  };
+  std::fprintf(f, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n");
+  std::fprintf(f, "<UnstructuredGrid>\n<Piece NumberOfCells=\"%ld\" NumberOfPoints=\"%ld\">\n", nT, nv);
+  if (nfields > 0) std::fprintf(f, "<PointData Scalars=\"%s\">\n", names[0]);
+  for (int i = 0; i < nfields; i++)
+    array("Float32", names[i], 1, data[i].data(), (size_t)nv, 4, [&](size_t k) { std::fprintf(f, "%g", (double)data[i][k]); });
+  if (nfields > 0) std::fprintf(f, "</PointData>\n");
+  std::fprintf(f, "<Points>\n");
+  array("Float32", "Coordinates", 3, pts.data(), 3 * (size_t)nv, 4, [&](size_t k) { std::fprintf(f, "%g", (double)pts[k]); });
+  std::fprintf(f, "</Points>\n<Cells>\n");
+  array("Int32", "connectivity", 1, tri.data(), 3 * (size_t)nT, 4, [&](size_t k) { std::fprintf(f, "%d", tri[k]); });
+  array("Int32", "offsets", 1, offs.data(), (size_t)nT, 4, [&](size_t k) { std::fprintf(f, "%d", offs[k]); });
+  array("UInt8", "types", 1, types.data(), (size_t)nT, 1, [&](size_t k) { std::fprintf(f, "%d", (int)types[k]); });
+  std::fprintf(f, "</Cells>\n</Piece>\n</UnstructuredGrid>\n");
+  if (!ascii) {
+    std::fprintf(f, "<AppendedData encoding=\"raw\">\n_");
+    for (auto& b : blobs) { std::fwrite(&b.second, 4, 1, f); std::fwrite(b.first, 1, b.second, f); }
+    std::fprintf(f, "\n</AppendedData>\n");
+  }
+  std::fprintf(f, "</VTKFile>\n");
+  std::fclose(f);
+  if (c.world > 1 && c.rank == 0) {
+    char idx[512];
+    std::snprintf(idx, sizeof idx, "%ss%04d:%s.pvtu", dir.c_str(), c.world, base.c_str());
+    std::FILE* g = std::fopen(idx, "w");
+    PNP_REQUIRE(g, PNP_E_CONFIG, std::string("cannot open ") + idx);
+    std::fprintf(g, "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<PUnstructuredGrid GhostLevel=\"0\">\n");
+    if (nfields > 0) std::fprintf(g, "<PPointData Scalars=\"%s\">\n", names[0]);
+    for (int i = 0; i < nfields; i++) std::fprintf(g, "<PDataArray type=\"Float32\" Name=\"%s\" NumberOfComponents=\"1\"/>\n", names[i]);
+    if (nfields > 0) std::fprintf(g, "</PPointData>\n");
+    std::fprintf(g, "<PPoints>\n<PDataArray type=\"Float32\" Name=\"Coordinates\" NumberOfComponents=\"3\"/>\n</PPoints>\n");
+    for (int r = 0; r < c.world; r++) std::fprintf(g, "<Piece Source=\"s%04d:p%04d:%s.vtu\"/>\n", c.world, r, base.c_str());
+    std::fprintf(g, "</PUnstructuredGrid>\n</VTKFile>\n");
+    std::fclose(g);
+  }
 }
 
 } // namespace pnp

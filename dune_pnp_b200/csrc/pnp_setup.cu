@@ -470,4 +470,60 @@ void matrix_export(Ctx& c, int op_handle, const Matrix& A, double* val) {
   });
 }
 
+// Import of an externally assembled matrix in the container layout of pattern_export() (what `A.base()` of an
+// ISTLBCRSMatrixBackend<1,1> matrix holds, stationary_pnp.hh:247): the ISTL-backend-level drop-in --
+// ls.apply(A, z, r, red) on a matrix PDELab assembled (instationary_pnp_from_pb_md.hh:188-211).  The pattern must be the
+// operator's pattern; entries of the (c+, c-) / (c-, c+) blocks, which the 7-plane layout does not store, must be zero.
+void matrix_import(Ctx& c, int op_handle, Matrix& A, const int* rowptr, const int* col, const double* val) {
+  PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built");
+  PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "matrix import works on an unpartitioned mesh");
+  PNP_REQUIRE(rowptr && col && val, PNP_E_ARG, "null CSR arrays");
+  const Operator& op = c.oper(op_handle);
+  PNP_REQUIRE(A.op == op.op, PNP_E_ARG, "matrix belongs to another operator type");
+  HostStar h = fetch_star(c);
+  const long ns = c.nslots, nv = c.nv;
+  std::vector<double> v((size_t)A.nplanes * ns, 0.0);
+  std::vector<int> rp_check((size_t)op_fields(op.op) * nv + 1);
+  bool bad_col = false, bad_zero = false;
+  const long nnz = walk_pattern(c, op, h, rp_check.data(), [&](long k, int ki, int kj, int slot, bool) {
+    if (col[k] != (int)(kj * nv + h.int2ext[h.adj[slot] & STAR_VMASK])) bad_col = true;
+    const int pl = op.op == OP_PNP ? pnp_plane(ki, kj) : 0;
+    if (pl < 0) { if (val[k] != 0.0) bad_zero = true; }
+    else v[(size_t)pl * ns + slot] = val[k];
+  });
+  for (size_t i = 0; i < rp_check.size(); i++) if (rowptr[i] != rp_check[i]) bad_col = true;
+  (void)nnz;
+  PNP_REQUIRE(!bad_col, PNP_E_ARG, "CSR pattern differs from the operator's pattern (pnp_pattern_get)");
+  PNP_REQUIRE(!bad_zero, PNP_E_ARG, "non-zero entry in a (c+, c-) coupling block: not a PNP Jacobian");
+  A.vals.upload(v.data(), v.size(), c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  A.comp0 = op.comp0;
+  if (c.last_vals == A.vals.p) c.last_vals = nullptr; // not "the last assembled Jacobian" any more: multigrid uses Galerkin products
+}
+
+// dof_perm hook: the numbering seen at the boundary is the numbering of the mesh arrays.  A caller whose grid
+// numbers vertices differently from the Gmsh file (UGGrid's leaf index after loadBalance(), pnp_solver_main.cc:106-114)
+// renumbers the mesh it read with pnp_mesh_read_gmsh: new_index[v] = the caller's index of vertex v.  Element and
+// boundary-segment order are kept.
+void mesh_renumber(Ctx& c, const int* new_index) {
+  PNP_REQUIRE(c.nv > 0 && new_index, PNP_E_ARG, "no mesh set");
+  PNP_REQUIRE(c.n_own == c.nv && c.hier.empty() && c.carry.empty(), PNP_E_ARG, "renumber the mesh right after it was set (before refinement / partitioning)");
+  const long nv = c.nv;
+  std::vector<char> seen((size_t)nv, 0);
+  for (long v = 0; v < nv; v++) {
+    PNP_REQUIRE(new_index[v] >= 0 && new_index[v] < nv && !seen[new_index[v]], PNP_E_ARG, "vertex permutation is not a bijection");
+    seen[new_index[v]] = 1;
+  }
+  std::vector<double> x = c.cx.to_host(c.stream), y = c.cy.to_host(c.stream), nx((size_t)nv), ny((size_t)nv);
+  std::vector<int> tri = c.ctri.to_host(c.stream), ba = c.cba.to_host(c.stream), bb = c.cbb.to_host(c.stream);
+  for (long v = 0; v < nv; v++) { nx[new_index[v]] = x[v]; ny[new_index[v]] = y[v]; }
+  for (auto& t : tri) t = new_index[t];
+  for (auto& t : ba) t = new_index[t];
+  for (auto& t : bb) t = new_index[t];
+  c.cx.upload(nx.data(), nv, c.stream); c.cy.upload(ny.data(), nv, c.stream); c.ctri.upload(tri.data(), tri.size(), c.stream);
+  c.cba.upload(ba.data(), ba.size(), c.stream); c.cbb.upload(bb.data(), bb.size(), c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.invalidate_mesh_objects();
+}
+
 } // namespace pnp

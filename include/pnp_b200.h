@@ -110,6 +110,11 @@ pnp_status pnp_carry_get(pnp_ctx*, int index, int vec_handle);
 /* same, for a field given / returned in reference numbering on the host ([fields][nv]); needs no finalized mesh */
 pnp_status pnp_carry_set_host(pnp_ctx*, int fields, const double* host);
 pnp_status pnp_carry_get_host(pnp_ctx*, int index, double* host);
+/* dof_perm hook: new_index[v] = the caller's index of vertex v (a bijection).  The numbering at this boundary is the
+ * numbering of the mesh arrays; a caller whose grid numbers the vertices differently from the Gmsh file (UGGrid's leaf
+ * index after loadBalance(), pnp_solver_main.cc:106-114) renumbers a mesh read with pnp_mesh_read_gmsh before finalizing
+ * it, and from then on vectors, patterns, matrices, constraints and sweep orders follow the caller's numbering. */
+pnp_status pnp_mesh_renumber(pnp_ctx*, const int* new_index);
 /* builds the vertex-star structure; renumber != 0 reorders vertices internally for locality */
 pnp_status pnp_mesh_finalize(pnp_ctx*, int renumber);
 pnp_status pnp_mesh_sizes(pnp_ctx*, long* nv, long* nT, long* nB, long* nslots);
@@ -157,6 +162,11 @@ pnp_status pnp_jacobian(pnp_ctx*, int op_handle, int u, int mat_handle, int mode
 /* values in the order of pnp_pattern_get() */
 pnp_status pnp_matrix_values_get(pnp_ctx*, int op_handle, int mat_handle, double* val);
 pnp_status pnp_spmv(pnp_ctx*, int mat_handle, int x, int y);
+/* the ISTL-backend-level drop-in: values of an EXTERNALLY assembled matrix in the container layout of pnp_pattern_get()
+ * -- what A.base() of the ISTLBCRSMatrixBackend<1,1> matrix holds when the driver calls ls.apply(A, z, r, red)
+ * (instationary_pnp_from_pb_md.hh:188-211; stationary_pnp.hh:247).  rowptr / col must equal the operator's pattern; a
+ * multigrid preconditioner treats such a matrix with Galerkin coarse operators. */
+pnp_status pnp_matrix_set_csr(pnp_ctx*, int op_handle, int mat_handle, const int* rowptr, const int* col, const double* val);
 
 /* ---- linear solvers: ISTLBackend_NOVLP_*::apply / result (instationary_pnp_from_pb_md.hh:188-211) */
 typedef struct {
@@ -238,6 +248,12 @@ pnp_status pnp_ion_flux(pnp_ctx*, int phi, int cp, int cm, double* ip, double* i
 /* DataWriter::writeData (datawriter.hh:45-94): one text line per element, "x y<TAB>value<TAB>gradx grady", scientific
  * with precision 5, in grid element order */
 pnp_status pnp_write_cell_data(pnp_ctx*, int vec_handle, const char* filename);
+
+/* Dune::VTKWriter<GV>(gv, VTKOptions::conforming) + addVertexData(VTKGridFunctionAdapter(dgf, name)) + write(name,
+ * VTKOptions::binaryappended) (instationary_pnp_from_pb_md.hh:337-340, :440; stationary_pnp_from_pb.hh:190-192, :386-390):
+ * "<name>.vtu" with the n 1-field vectors as Float32 vertex data; ascii != 0: VTKOptions::ascii.  Several ranks: every
+ * rank writes its piece "s<world>:p<rank>:<name>.vtu", rank 0 the "s<world>:<name>.pvtu" index. */
+pnp_status pnp_write_vtk(pnp_ctx*, const char* name, int n, const int* vec_handles, const char* const* names, int ascii);
 
 /* ---- initial guess / Dirichlet values: interpolate(BCExtension) (dirichlet_bc.hh:54-123) --- */
 /* component 0: phi, 1: c+, 2: c-; pb_vec < 0 means a zero PB field; out is a 1-field vector */

@@ -252,3 +252,11 @@ def ion_flux(mesh, params, phi, cp, cm):
 
 def write_cell_data(mesh, u, filename):
     _chk(lib().ora_write_cell_data(mesh.h, _d(_f64(u)), filename.encode()))
+
+
+def write_vtk(mesh, name, fields, names, ascii=False):
+    """Dune::VTKWriter vertex data: writes <name>.vtu."""
+    arrs = [_f64(f) for f in fields]
+    ptrs = (_dp * len(arrs))(*[_d(a) for a in arrs])
+    nm = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    _chk(lib().ora_write_vtk(mesh.h, name.encode(), len(arrs), ptrs, nm, int(ascii)))

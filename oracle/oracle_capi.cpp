@@ -250,4 +250,14 @@ int ora_write_cell_data(void* mh, const double* u, const char* filename) {
   ORA_TRY write_cell_data(*(Mesh*)mh, u, filename); return 0; ORA_CATCH(-1)
 }
 
+int ora_write_vtk(void* mh, const char* name, int n, const double* const* fields, const char* const* names, int ascii) {
+  ORA_TRY
+  std::vector<const double*> f(fields, fields + n);
+  std::vector<std::string> nm;
+  for (int i = 0; i < n; i++) nm.push_back(names[i]);
+  write_vtk(*(Mesh*)mh, name, f, nm, ascii != 0);
+  return 0;
+  ORA_CATCH(-1)
+}
+
 } // extern "C"

@@ -1127,4 +1127,62 @@ inline void write_cell_data(const Mesh& m, const double* u, const std::string& f
   }
 }
 
+
+// Dune::VTKWriter<GV>(gv, conforming).addVertexData(...).write(name, ascii | binaryappended)
+// (instationary_pnp_from_pb_md.hh:337-340,440; stationary_pnp_from_pb.hh:190-192): one .vtu piece -- Float32 vertex data
+// and points, Int32 connectivity / offsets, UInt8 cell types (5 = triangle); appended arrays are <uint32 bytes><raw>.
+inline void write_vtk(const Mesh& m, const std::string& name, const std::vector<const double*>& fields,
+                      const std::vector<std::string>& names, bool ascii) {
+  std::ofstream f(name + ".vtu", std::ios::binary);
+  if (!f) throw std::runtime_error("cannot open " + name + ".vtu");
+  struct Blob { std::string bytes; };
+  std::vector<Blob> blobs;
+  unsigned long offset = 0;
+  auto header = [&](const char* type, const std::string& nm, int ncomp) {
+    f << "<DataArray type=\"" << type << "\" Name=\"" << nm << "\" NumberOfComponents=\"" << ncomp << "\" ";
+  };
+  auto put = [&](const char* type, const std::string& nm, int ncomp, const std::vector<double>& vals, int kind) {
+    // kind 0: Float32, 1: Int32, 2: UInt8
+    header(type, nm, ncomp);
+    if (ascii) {
+      f << "format=\"ascii\">\n";
+      for (size_t i = 0; i < vals.size(); i++) {
+        char buf[64];
+        if (kind == 0) std::snprintf(buf, sizeof buf, "%g", (double)(float)vals[i]);
+        else std::snprintf(buf, sizeof buf, "%d", (int)vals[i]);
+        f << buf << (((i + 1) % 12 == 0 || i + 1 == vals.size()) ? '\n' : ' ');
+      }
+      f << "</DataArray>\n";
+    } else {
+      f << "format=\"appended\" offset=\"" << offset << "\" />\n";
+      Blob b;
+      for (double v : vals) {
+        if (kind == 0) { float x = (float)v; b.bytes.append((const char*)&x, 4); }
+        else if (kind == 1) { int x = (int)v; b.bytes.append((const char*)&x, 4); }
+        else { unsigned char x = (unsigned char)v; b.bytes.append((const char*)&x, 1); }
+      }
+      offset += 4 + b.bytes.size();
+      blobs.push_back(std::move(b));
+    }
+  };
+  f << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n";
+  f << "<UnstructuredGrid>\n<Piece NumberOfCells=\"" << m.nT << "\" NumberOfPoints=\"" << m.nv << "\">\n";
+  if (!fields.empty()) f << "<PointData Scalars=\"" << names[0] << "\">\n";
+  for (size_t i = 0; i < fields.size(); i++) put("Float32", names[i], 1, std::vector<double>(fields[i], fields[i] + m.nv), 0);
+  if (!fields.empty()) f << "</PointData>\n";
+  std::vector<double> pts(3 * (size_t)m.nv), conn(3 * (size_t)m.nT), offs(m.nT), types(m.nT, 5.0);
+  for (int v = 0; v < m.nv; v++) { pts[3 * v] = m.x[v]; pts[3 * v + 1] = m.y[v]; pts[3 * v + 2] = 0.0; }
+  for (int e = 0; e < m.nT; e++) { for (int i = 0; i < 3; i++) conn[3 * e + i] = m.tri[3 * e + i]; offs[e] = 3 * (e + 1); }
+  f << "<Points>\n"; put("Float32", "Coordinates", 3, pts, 0);
+  f << "</Points>\n<Cells>\n";
+  put("Int32", "connectivity", 1, conn, 1); put("Int32", "offsets", 1, offs, 1); put("UInt8", "types", 1, types, 2);
+  f << "</Cells>\n</Piece>\n</UnstructuredGrid>\n";
+  if (!ascii) {
+    f << "<AppendedData encoding=\"raw\">\n_";
+    for (auto& b : blobs) { unsigned n = (unsigned)b.bytes.size(); f.write((const char*)&n, 4); f.write(b.bytes.data(), b.bytes.size()); }
+    f << "\n</AppendedData>\n";
+  }
+  f << "</VTKFile>\n";
+}
+
 } // namespace pnpo
