@@ -91,6 +91,13 @@ def _i(a):
     return None if a is None else a.ctypes.data_as(_ip)
 
 
+def tune(name, value):
+    """Process-wide kernel tuning knob (pnp_tune)."""
+    st = lib().pnp_tune(name.encode(), C.c_double(value))
+    if st != 0:
+        raise PnpError(st, "unknown tuning knob " + name)
+
+
 class Context:
     """One GPU, one mesh.  Mirrors the C ABI one to one; numpy arrays in the reference's numbering."""
 

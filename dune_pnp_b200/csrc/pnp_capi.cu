@@ -187,6 +187,16 @@ pnp_status pnp_timer_stop(pnp_ctx* ctx, double* ms) {
   *ms = t;
   API_END
 }
+pnp_status pnp_tune(const char* name, double value) {
+  if (!name) return PNP_E_ARG;
+  const std::string n(name);
+  Tune& t = tune();
+  if (n == "tma") t.tma = value != 0;
+  else if (n == "tma_stages") t.tma_stages = (int)value;
+  else if (n == "tma_min_rows") t.tma_min_rows = (long)value;
+  else return PNP_E_ARG;
+  return PNP_OK;
+}
 const char* pnp_last_error(pnp_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
 long pnp_launch_count(pnp_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 

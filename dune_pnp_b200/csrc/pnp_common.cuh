@@ -62,6 +62,14 @@ template <class T> struct DBuf {
   std::vector<T> to_host(cudaStream_t s) const { std::vector<T> h(n); download(h.data(), n, s); return h; }
 };
 
+// process-wide tuning knobs (pnp_tune): experiments and tests switch kernel variants without rebuilding
+struct Tune {
+  int tma = 1;            // streaming (bulk-copy) SpMV for large levels; 0: plain-load kernel everywhere
+  int tma_stages = 3;     // ring depth of the streaming SpMV (2..3)
+  long tma_min_rows = -1; // smallest level the streaming SpMV serves (-1: two tiles per SM)
+};
+inline Tune& tune() { static Tune t; return t; }
+
 inline int grid_for(long n, int block, int max_blocks = 148 * 32) {
   long g = (n + block - 1) / block;
   if (g < 1) g = 1;

@@ -1,11 +1,16 @@
 // pnp_spmv_tma.cuh -- the streaming form of the star SpMV (k_star_op, pnp_spmv.cuh) for levels large enough to fill the
 // GPU: one persistent CTA per SM; a producer warp streams the value planes, the column indices, the row pointers and the
 // epilogue operands of 128-row tiles into shared memory with 1-D bulk copies (cp.async.bulk, the TMA engine) through a
-// ring of mbarrier-guarded stages, while eight consumer warps do the products out of shared memory.  The bytes in flight
+// ring of mbarrier-guarded stages, while the consumer warps do the products out of shared memory.  The bytes in flight
 // no longer sit in registers behind the scoreboard (the plain-load kernel ran at 49 % warps active, 62-64 registers and
-// ~14 long-scoreboard stall cycles per issue, profiles/hot_kernels_full_r01d_summary.txt); only the x gathers -- L1/L2
-// hits after the locality renumbering -- remain ordinary loads, and all of a warp's gathers for a tile step are issued
-// before the first product.
+// ~14 long-scoreboard stall cycles per issue, profiles/hot_kernels_full_r01d_summary.txt).
+//
+// Shared memory has no coalescing rule, so a consumer LANE owns a whole ROW (LPR = 1; LPR lanes split a row's slots
+// otherwise): no shuffle reduction, no idle lanes on 7-slot rows, one epilogue per row -- the first streaming version
+// kept the plain-load kernel's 8-lanes-per-row mapping and was issue-bound at 9 warps per SM (1.83 G warp instructions,
+// 30 % issue utilisation, 5.4 ms against the plain-load kernel's 4.0 ms; profiles/spmv_tma_r02_summary.txt).  The x
+// gathers of columns inside the window [r0 - 128, r0 + 256) -- 90 % of them with the locality numbering -- are
+// shared-memory reads from a staged copy of that part of x; the rest are ordinary loads.
 //
 // A tile's slots are ONE contiguous range [rp[r0], rp[r0+128]) of every plane, so each plane is one bulk copy; source
 // addresses are rounded down and sizes up to the 16-byte granularity bulk copies need (arrays carry 64 bytes of slack,
@@ -20,10 +25,12 @@
 namespace pnp {
 
 constexpr int TMA_TR = 128;                      // rows per tile
-constexpr int TMA_NW = 8;                        // consumer warps
+constexpr int TMA_LPR = 1;                       // lanes per row
+constexpr int TMA_NW = TMA_TR * TMA_LPR / 32;    // consumer warps
 constexpr int TMA_THREADS = (TMA_NW + 1) * 32;   // + 1 producer warp
 constexpr int TMA_CAP = 960;                     // staged slots per tile and plane
 constexpr int TMA_MAX_STAGES = 3;
+constexpr int TMA_W = 128;                       // rows of x staged on either side of the tile (the gather window)
 
 template <int NP> struct TmaLayout {
   static constexpr int F = NP == 1 ? 1 : 3;
@@ -31,11 +38,14 @@ template <int NP> struct TmaLayout {
   static constexpr int COLS = NP * PLANE;                            // (CAP + 4) column indices
   static constexpr int RP = COLS + (TMA_CAP + 4) * 4;                // (TR + 4) row pointers
   static constexpr int B = RP + (TMA_TR + 4) * 4;                    // F*TR (+2) doubles: right-hand side / dot operand
-  static constexpr int XO = B + (F * TMA_TR + 2) * 8;                // F*TR (+2) doubles: the rows' own x (smoother)
-  static constexpr int STAGE = XO + (F * TMA_TR + 2) * 8;
+  // x of the rows [r0 - W, r0 + TR + W): with the locality numbering 90 % of a tile's columns lie in this window
+  // (measured on the refined pore mesh), so their gathers are shared-memory reads; the smoother takes the rows' own x
+  // from it as well
+  static constexpr int XW = B + (F * TMA_TR + 2) * 8;
+  static constexpr int STAGE = XW + (F * (TMA_TR + 2 * TMA_W) + 2) * 8;
   static constexpr int YBUF = TMA_TR * F * 8;                        // output staging, per consumer warp a slice
   static constexpr int HEAD = 128;                                   // mbarriers
-  static_assert(PLANE % 16 == 0 && COLS % 16 == 0 && RP % 16 == 0 && B % 16 == 0 && XO % 16 == 0 && STAGE % 16 == 0, "bulk copy alignment");
+  static_assert(PLANE % 16 == 0 && COLS % 16 == 0 && RP % 16 == 0 && B % 16 == 0 && XW % 16 == 0 && STAGE % 16 == 0, "bulk copy alignment");
   static constexpr int smem_bytes(int stages) { return HEAD + stages * STAGE + YBUF; }
 };
 
@@ -80,12 +90,37 @@ __device__ __forceinline__ void block_inverse_row(const double* dv, int k, doubl
   }
 }
 
+// one slot of a row: y_row += A(row, col) x(col); STAGED: values / column index / x window from the stage
+template <int NP, bool STAGED>
+__device__ __forceinline__ void slot_product(const StarOpArgs& a, bool ok, int s, const double* sv, const int* vb, const unsigned* sc,
+                                             int cbase, const double* sx, int wlo, unsigned wn, double* acc, double* dg) {
+  constexpr int F = NP == 1 ? 1 : 3;
+  const unsigned c = !ok ? 0u : ((STAGED ? sc[s - cbase] : a.col[s]) & STAR_VMASK);
+  const unsigned cw = c - (unsigned)wlo; // (wraps for columns below the window)
+  const bool in = cw < wn;
+  double x[F], v[NP];
+#pragma unroll
+  for (int k = 0; k < F; k++) x[k] = !ok ? 0.0 : (in ? sx[F * cw + k] : a.x[(size_t)F * c + k]);
+#pragma unroll
+  for (int p = 0; p < NP; p++) v[p] = !ok ? 0.0 : (STAGED ? sv[vb[p] + s] : a.vals[(size_t)p * a.stride + s]);
+  if (dg) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) dg[p] = v[p];
+  }
+  if (NP == 1) acc[0] += v[0] * x[0];
+  else {
+    acc[0] += v[0] * x[0] + v[1 % NP] * x[1 % F] + v[2 % NP] * x[2 % F];
+    acc[1 % F] += v[3 % NP] * x[0] + v[4 % NP] * x[1 % F];
+    acc[2 % F] += v[5 % NP] * x[0] + v[6 % NP] * x[2 % F];
+  }
+}
+
 template <int NP, int EPI, int NDOT>
 __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs a, const int nstages) {
   using L = TmaLayout<NP>;
   constexpr int F = L::F;
-  constexpr int RW = TMA_TR / TMA_NW;   // rows per consumer warp and tile
-  constexpr int STEPS = RW / 4;         // 8 lanes share a row: 4 rows per step
+  constexpr int LPR = TMA_LPR;
+  constexpr int RW = 32 / LPR;          // rows per consumer warp and tile
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + TMA_MAX_STAGES;
@@ -138,9 +173,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
         const unsigned nb_vec = (unsigned)((F * rows + 1) & ~1) * 8u;
         total += nb_rp;
         constexpr bool need_b = EPI != EPI_PLAIN || NDOT >= 1;
-        constexpr bool need_xo = EPI == EPI_JACOBI;
         if (need_b) total += nb_vec;
-        if (need_xo) total += nb_vec;
+        const int wlo = max(r0 - TMA_W, 0), whi = min(r0 + TMA_TR + TMA_W, a.nv);
+        const unsigned nb_win = (unsigned)((F * (whi - wlo) + 1) & ~1) * 8u;
+        total += nb_win;
         mbar_expect_tx(&full[stage], total);
         if (staged) {
 #pragma unroll
@@ -152,13 +188,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
         }
         bulk_g2s(st + L::RP, a.rp + r0, nb_rp, &full[stage]);
         if (need_b) bulk_g2s(st + L::B, (EPI == EPI_PLAIN ? a.w1 : a.b) + (size_t)F * r0, nb_vec, &full[stage]);
-        if (need_xo) bulk_g2s(st + L::XO, a.x + (size_t)F * r0, nb_vec, &full[stage]);
+        bulk_g2s(st + L::XW, a.x + (size_t)F * wlo, nb_win, &full[stage]);
       }
       __syncwarp();
     }
   } else {
-    // ---------------- consumers ----------------
-    const int sub = lane & 7, grp = lane >> 3;
+    // ---------------- consumers: lane <-> row (LPR lanes per row) ----------------
+    const int sub = lane % LPR;
     double* yw = ybuf + warp * RW * F;
     int t = blockIdx.x;
     for (int it = 0; t < ntiles; t += gridDim.x, it++) {
@@ -170,137 +206,89 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
       const unsigned* sc = reinterpret_cast<const unsigned*>(st + L::COLS);
       const int* srp = reinterpret_cast<const int*>(st + L::RP);
       const double* sb = reinterpret_cast<const double*>(st + L::B);
-      const double* sxo = reinterpret_cast<const double*>(st + L::XO);
+      const double* sx = reinterpret_cast<const double*>(st + L::XW);
       const int r0 = t * TMA_TR, rows = min(TMA_TR, a.nv - r0);
+      const int wlo = max(r0 - TMA_W, 0);
+      const unsigned wn = (unsigned)(min(r0 + TMA_TR + TMA_W, a.nv) - wlo); // window rows
+      const double* sxo = sx + (size_t)F * (r0 - wlo);                        // the tile's own rows inside the window
       const int lo = srp[0], hi = srp[rows];
       const bool staged = hi - lo <= TMA_CAP; // block-uniform
       const int cbase = lo & ~3;
       int vb[NP]; // plane p, slot s -> sv[vb[p] + s]
 #pragma unroll
       for (int p = 0; p < NP; p++) vb[p] = p * (TMA_CAP + 2) - lo + ((lo + p * sp) & 1);
-      int bb[STEPS], ee[STEPS];
-      double acc[STEPS][F];
+      const int rl = RW * warp + lane / LPR; // row of this lane inside the tile
+      const bool valid = rl < rows;
+      const int b0 = valid ? srp[rl] : hi, e0 = valid ? srp[rl + 1] : hi;
+      double acc[F], dg[NP];
 #pragma unroll
-      for (int q = 0; q < STEPS; q++) {
-        const int rl = RW * warp + 4 * q + grp;
-        const bool valid = rl < rows;
-        bb[q] = valid ? srp[rl] : hi;
-        ee[q] = valid ? srp[rl + 1] : hi;
+      for (int k = 0; k < F; k++) acc[k] = 0.0;
 #pragma unroll
-        for (int k = 0; k < F; k++) acc[q][k] = 0.0;
-      }
+      for (int p = 0; p < NP; p++) dg[p] = 0.0;
+      const int len = e0 - b0;
+      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      // slot `sub` first: for sub == 0 it is the diagonal, whose values the smoother epilogue inverts
       if (staged) {
-        // first eight slots of every row: all column indices, then all x gathers, then the products
-        unsigned cc[STEPS];
-        bool ok[STEPS];
-        double xv[STEPS][F];
+        slot_product<NP, true>(a, sub < len, b0 + sub, sv, vb, sc, cbase, sx, wlo, wn, acc, EPI == EPI_JACOBI ? dg : nullptr);
+        for (int j0 = sub + LPR; j0 < maxlen; j0 += 3 * LPR) {
 #pragma unroll
-        for (int q = 0; q < STEPS; q++) {
-          const int s = bb[q] + sub;
-          ok[q] = s < ee[q];
-          cc[q] = ok[q] ? (sc[s - cbase] & STAR_VMASK) : 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < STEPS; q++) {
-#pragma unroll
-          for (int k = 0; k < F; k++) xv[q][k] = ok[q] ? a.x[(size_t)F * cc[q] + k] : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < STEPS; q++) {
-          if (ok[q]) {
-            const int s = bb[q] + sub;
-            if (NP == 1) acc[q][0] += sv[vb[0] + s] * xv[q][0];
-            else {
-              const double x0 = xv[q][0], x1 = xv[q][1 % F], x2 = xv[q][2 % F];
-              acc[q][0] += sv[vb[0] + s] * x0 + sv[vb[1 % NP] + s] * x1 + sv[vb[2 % NP] + s] * x2;
-              acc[q][1 % F] += sv[vb[3 % NP] + s] * x0 + sv[vb[4 % NP] + s] * x1;
-              acc[q][2 % F] += sv[vb[5 % NP] + s] * x0 + sv[vb[6 % NP] + s] * x2;
-            }
+          for (int u = 0; u < 3; u++) {
+            const int j = j0 + u * LPR;
+            slot_product<NP, true>(a, j < len, b0 + j, sv, vb, sc, cbase, sx, wlo, wn, acc, nullptr);
           }
         }
-        // rows with more than eight slots (valence > 7)
-#pragma unroll
-        for (int q = 0; q < STEPS; q++) {
-          for (int s = bb[q] + 8 + sub; s < ee[q]; s += 8) {
-            const size_t c = sc[s - cbase] & STAR_VMASK;
-            if (NP == 1) acc[q][0] += sv[vb[0] + s] * a.x[c];
-            else {
-              const double x0 = a.x[3 * c], x1 = a.x[3 * c + 1], x2 = a.x[3 * c + 2];
-              acc[q][0] += sv[vb[0] + s] * x0 + sv[vb[1 % NP] + s] * x1 + sv[vb[2 % NP] + s] * x2;
-              acc[q][1 % F] += sv[vb[3 % NP] + s] * x0 + sv[vb[4 % NP] + s] * x1;
-              acc[q][2 % F] += sv[vb[5 % NP] + s] * x0 + sv[vb[6 % NP] + s] * x2;
-            }
-          }
-        }
-      } else {
-        // over-full tile: slots straight from global memory
-#pragma unroll
-        for (int q = 0; q < STEPS; q++) {
-          for (int s = bb[q] + sub; s < ee[q]; s += 8) {
-            const size_t c = a.col[s] & STAR_VMASK;
-            if (NP == 1) acc[q][0] += a.vals[s] * a.x[c];
-            else {
-              const double x0 = a.x[3 * c], x1 = a.x[3 * c + 1], x2 = a.x[3 * c + 2];
-              const double* v = a.vals + s;
-              acc[q][0] += v[0] * x0 + v[(1 % NP) * a.stride] * x1 + v[(2 % NP) * a.stride] * x2;
-              acc[q][1 % F] += v[(3 % NP) * a.stride] * x0 + v[(4 % NP) * a.stride] * x1;
-              acc[q][2 % F] += v[(5 % NP) * a.stride] * x0 + v[(6 % NP) * a.stride] * x2;
-            }
-          }
-        }
+      } else { // over-full tile: slots straight from global memory
+        slot_product<NP, false>(a, sub < len, b0 + sub, sv, vb, sc, cbase, sx, wlo, wn, acc, EPI == EPI_JACOBI ? dg : nullptr);
+        for (int j = sub + LPR; j < maxlen; j += LPR)
+          slot_product<NP, false>(a, j < len, b0 + j, sv, vb, sc, cbase, sx, wlo, wn, acc, nullptr);
       }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < STEPS; q++) {
+      if (LPR > 1) {
 #pragma unroll
         for (int k = 0; k < F; k++)
 #pragma unroll
-          for (int o = 4; o > 0; o >>= 1) acc[q][k] += __shfl_xor_sync(0xffffffffu, acc[q][k], o);
-        const int rl = RW * warp + 4 * q + grp;
-        const bool mine = sub < F && rl < rows;
-        const double ax = F == 1 ? acc[q][0] : (sub == 0 ? acc[q][0] : (sub == 1 ? acc[q][1 % F] : acc[q][2 % F]));
-        const int il = F * rl + sub; // tile-local dof
-        double yv = 0.0;
+          for (int o = LPR / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      }
+      const bool mine = valid && sub == 0;
+      double yv[F];
+#pragma unroll
+      for (int k = 0; k < F; k++) yv[k] = 0.0;
+      if (mine) {
         if (EPI == EPI_PLAIN) {
-          yv = ax;
-          if (mine) {
-            if (NDOT >= 1) dsum[0] += ax * sb[il];
-            if (NDOT >= 2) dsum[NDOT >= 2 ? 1 : 0] += ax * ax;
+#pragma unroll
+          for (int k = 0; k < F; k++) {
+            yv[k] = acc[k];
+            if (NDOT >= 1) dsum[0] += acc[k] * sb[F * rl + k];
+            if (NDOT >= 2) dsum[NDOT >= 2 ? 1 : 0] += acc[k] * acc[k];
           }
         } else if (EPI == EPI_RESIDUAL) {
-          yv = mine ? sb[il] - ax : 0.0;
-        } else { // damped (point-block) Jacobi step: y = x + omega * D^-1 (b - A x)
-          const double rr = mine ? sb[il] - ax : 0.0;
-          double z;
-          if (F == 3) {
-            const int g8 = lane & ~7;
-            const double r0v = __shfl_sync(0xffffffffu, rr, g8), r1v = __shfl_sync(0xffffffffu, rr, g8 + 1),
-                         r2v = __shfl_sync(0xffffffffu, rr, g8 + 2);
-            z = 0.0;
-            if (mine) {
-              double dv[NP];
 #pragma unroll
-              for (int p = 0; p < NP; p++) dv[p] = staged ? sv[vb[p] + bb[q]] : a.vals[(size_t)p * a.stride + bb[q]];
+          for (int k = 0; k < F; k++) yv[k] = sb[F * rl + k] - acc[k];
+        } else { // damped (point-block) Jacobi step: y = x + omega * D^-1 (b - A x)
+          double r[F], z[F];
+#pragma unroll
+          for (int k = 0; k < F; k++) r[k] = sb[F * rl + k] - acc[k];
+          if (F == 3) {
+#pragma unroll
+            for (int k = 0; k < F; k++) {
               double o[3];
-              block_inverse_row(dv, sub, o);
-              z = o[0] * r0v + o[1] * r1v + o[2] * r2v;
+              block_inverse_row(dg, k, o);
+              z[k] = o[0] * r[0] + o[1] * r[1 % F] + o[2] * r[2 % F];
             }
-          } else {
-            z = 0.0;
-            if (mine) {
-              const double d = staged ? sv[vb[0] + bb[q]] : a.vals[bb[q]];
-              z = (d != 0.0 ? 1.0 / d : 0.0) * rr;
-            }
-          }
-          yv = mine ? sxo[il] + a.omega * z : 0.0;
+          } else z[0] = (dg[0] != 0.0 ? 1.0 / dg[0] : 0.0) * r[0];
+#pragma unroll
+          for (int k = 0; k < F; k++) yv[k] = sxo[F * rl + k] + a.omega * z[k];
         }
-        if (sub < F) yw[F * (4 * q + grp) + sub] = yv;
+      }
+      if (sub == 0) {
+#pragma unroll
+        for (int k = 0; k < F; k++) yw[F * (lane / LPR) + k] = yv[k];
       }
       __syncwarp();
       // this warp's RW*F results are contiguous in y
       {
         const size_t g0 = (size_t)F * (r0 + RW * warp);
         const size_t gend = (size_t)F * a.nv;
+#pragma unroll
         for (int i = lane; i < RW * F; i += 32)
           if (g0 + i < gend) a.y[g0 + i] = yw[i];
       }
@@ -333,18 +321,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
 // The streaming kernel serves levels with at least two tiles per SM whose arrays sit on 16-byte boundaries; everything
 // else (small levels, the Chebyshev epilogue) stays with the plain-load kernel.
 inline bool star_op_tma_ok(const Ctx& c, const StarOpArgs& a, int epi) {
-  static const bool off = std::getenv("PNP_NO_TMA") != nullptr;
-  // PNP_TMA_MIN_ROWS: test hook, lets the small parity meshes run through the streaming kernel as well
-  static const long min_rows_env = [] { const char* e = std::getenv("PNP_TMA_MIN_ROWS"); return e ? std::atol(e) : -1l; }();
-  if (off || epi == EPI_CHEBYSHEV) return false;
-  if ((long)a.nv < (min_rows_env >= 0 ? min_rows_env : 2l * TMA_TR * c.sm_count)) return false;
+  const Tune& t = tune();
+  if (!t.tma || epi == EPI_CHEBYSHEV) return false;
+  if ((long)a.nv < (t.tma_min_rows >= 0 ? t.tma_min_rows : 2l * TMA_TR * c.sm_count)) return false;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   return al(a.rp) && al(a.col) && al(a.vals) && al(a.x) && (!a.b || al(a.b)) && (!a.w1 || al(a.w1));
 }
 
 inline int star_op_tma_stages() {
-  static const int n = [] { const char* e = std::getenv("PNP_TMA_STAGES"); int v = e ? std::atoi(e) : 3; return v < 2 ? 2 : (v > TMA_MAX_STAGES ? TMA_MAX_STAGES : v); }();
-  return n;
+  const int v = tune().tma_stages;
+  return v < 2 ? 2 : (v > TMA_MAX_STAGES ? TMA_MAX_STAGES : v);
 }
 
 template <int NP, int EPI, int NDOT>

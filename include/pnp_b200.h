@@ -51,6 +51,10 @@ enum { PNP_PREC_NONE = 0, PNP_PREC_JACOBI = 1, PNP_PREC_SSOR = 2, PNP_PREC_ILU0 
 pnp_status pnp_ctx_create(int device, pnp_ctx** out);
 void pnp_ctx_destroy(pnp_ctx* ctx);
 const char* pnp_last_error(pnp_ctx* ctx);
+/* process-wide kernel tuning knobs (experiments, tests): "tma" (1: large levels run the bulk-copy streaming SpMV, 0: the
+ * plain-load kernel everywhere), "tma_stages" (2..3), "tma_min_rows" (smallest level served by the streaming kernel, -1:
+ * two tiles per SM) */
+pnp_status pnp_tune(const char* name, double value);
 /* number of CUDA kernels this context has launched so far */
 long pnp_launch_count(pnp_ctx* ctx);
 

@@ -49,20 +49,24 @@ def _pnp_from_pb_oracle(m, p, tight):
     return pb, rpb, u0, u, r
 
 
+@pytest.mark.parametrize("tight", [False, True])
 @pytest.mark.parametrize("levels", [0, 1])
-def test_stationary_pnp_from_pb_on_pore_matches_oracle(levels):
-    """pore.cfg asks for reduction 1e-9 / linear reduction 1e-8 (test/pore_pnp/pore.cfg:7-12): that IS the tight run."""
+def test_stationary_pnp_from_pb_on_pore_matches_oracle(levels, tight):
+    """tight=False: pore.cfg's own Newton settings (reduction 1e-9 / linear reduction 1e-8, test/pore_pnp/pore.cfg:7-12):
+    equal Newton iteration counts; two runs that both stop at that reduction agree to about 10x the reduction in the
+    defect, i.e. ~1e-8 .. 1e-7 in the fields (measured 1.6e-8).  tight=True (1e-11 / 1e-9): CONVERGED fields, within 1e-8."""
     c, m, p = make_ctx("pore", levels=levels)
-    pb, rpb, u0, u, res = _pnp_from_pb_gpu(c, tight=False)
-    pb_o, rpb_o, u0_o, u_o, res_o = _pnp_from_pb_oracle(m, p, tight=False)
+    pb, rpb, u0, u, res = _pnp_from_pb_gpu(c, tight=tight)
+    pb_o, rpb_o, u0_o, u_o, res_o = _pnp_from_pb_oracle(m, p, tight=tight)
     assert rpb.converged and rpb_o["converged"] and rpb.iterations == rpb_o["iterations"]
     assert np.linalg.norm(pb - pb_o) <= 1e-8 * np.linalg.norm(pb_o)
     assert np.linalg.norm(u0 - u0_o) <= 1e-8 * np.linalg.norm(u0_o)
     assert res.converged and res_o["converged"]
     assert res.iterations == res_o["iterations"]
     nv = m.nv
+    tol = 1e-8 if tight else 1e-7
     for k in range(3):
-        assert np.linalg.norm(u[k * nv:(k + 1) * nv] - u_o[k * nv:(k + 1) * nv]) <= 1e-8 * np.linalg.norm(u_o[k * nv:(k + 1) * nv])
+        assert np.linalg.norm(u[k * nv:(k + 1) * nv] - u_o[k * nv:(k + 1) * nv]) <= tol * np.linalg.norm(u_o[k * nv:(k + 1) * nv])
     # defect histories of the two Newton runs agree as far as the linear solves' accuracy lets them
     assert abs(res.first_defect - res_o["first_defect"]) <= 1e-7 * res_o["first_defect"]
 
@@ -166,16 +170,48 @@ def test_residual_jacobian_spmv_parity_level5():
     assert rel_err(c.download(vy, 1), y_o, ora.spmv(rp, col, np.abs(val), np.abs(x))) <= TOL
 
 
-def test_streaming_spmv_kernel_on_the_small_meshes():
-    """k_star_op_tma (bulk-copy pipeline, pnp_spmv_tma.cuh) normally serves levels with >= 2 tiles per SM; with
-    PNP_TMA_MIN_ROWS=1 every SpMV / multigrid level operation of the small-mesh parity tests goes through it: partial last
-    tiles, tiles of unrefined Gmsh meshes with more slots than the stage holds (plain-load fallback), both plane counts."""
-    import subprocess
-    import sys
-    env = dict(os.environ, PNP_TMA_MIN_ROWS="1")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sel = "spmv_parity or linear_solvers_on_poisson or multigrid_preconditioner or multigrid_options or newton_pnp_from_pb_matches_oracle"
-    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
-                          "-k", sel], env=env, cwd=root, capture_output=True, text=True, timeout=1200)
-    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
-    assert " passed" in out.stdout
+@pytest.fixture
+def streaming_everywhere():
+    capi = _capi()
+    capi.tune("tma_min_rows", 1)
+    yield
+    capi.tune("tma_min_rows", -1)
+
+
+def test_streaming_spmv_kernel_on_the_small_meshes(streaming_everywhere):
+    """k_star_op_tma (bulk-copy pipeline, pnp_spmv_tma.cuh) normally serves levels with >= 2 tiles per SM; with the tuning
+    knob tma_min_rows = 1 every SpMV / multigrid level operation of these small-mesh parity tests goes through it: partial
+    last tiles, tiles of unrefined Gmsh meshes with more slots than a stage holds (plain-load fallback), gather windows
+    clipped at both ends, both plane counts."""
+    import test_gpu_parity as t
+    for name, levels in (("sphere", 0), ("pore", 0), ("pore_small", 2), ("cylinder", 1)):
+        for op in (ora.OP_PB, ora.OP_PNP):
+            t.test_spmv_parity(name, levels, op)
+    for kind, prec in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        t.test_linear_solvers_on_poisson(kind, prec)
+    for op in (ora.OP_PB, ora.OP_PNP):
+        for geometric in (0, 1):
+            t.test_multigrid_preconditioner(op, geometric)
+    t.test_multigrid_options(0, 2)
+    t.test_newton_pnp_from_pb_matches_oracle("pore_small", False)
+
+
+def test_streaming_and_plain_spmv_agree_level4(streaming_everywhere):
+    """The two SpMV kernels on the same 738 k-vertex matrix: all three epilogues of the multigrid cycle, compared through
+    one V(2,2) application (identical arithmetic per row up to the summation order inside a row)."""
+    capi = _capi()
+    c, m, p = make_ctx("pore", levels=4)
+    h = c.operator(capi.OP_PNP, 0)
+    u = c.vec(3, _smooth_state(m, ora.OP_PNP))
+    A = c.matrix(h)
+    c.jacobian(h, u, A, capi.JAC_ANALYTIC, 0.0)
+    d = np.random.RandomState(2).uniform(-1, 1, 3 * m.nv); d[c.constraints(h, 3)] = 0.0
+    vd, out = c.vec(3, d), {}
+    for tma in (1, 0):
+        capi.tune("tma", tma)
+        s = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 50, 2)
+        v = c.vec(3)
+        c.precond_apply(s, A, vd, v)
+        out[tma] = c.download(v, 3)
+    capi.tune("tma", 1)
+    assert np.linalg.norm(out[1] - out[0]) <= 1e-11 * np.linalg.norm(out[0])
