@@ -141,14 +141,23 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
   if (warp == TMA_NW) {
     // ---------------- producer: lane 0 feeds the ring; the other lanes of the warp walk the loop with it (the kernel's
     // closing __syncthreads wants converged warps) ----------------
+    // The slot range of a tile comes from two row pointers in global memory.  A load issued while the bulk copies saturate
+    // DRAM takes microseconds, and with one tile of look-ahead it paced the whole pipeline (2.2 us per tile whatever the
+    // consumers did: the first two streaming versions ran at 4.1 TB/s for that reason alone).  So every lane fetches the
+    // boundaries of one of the next 32 tiles, a full batch ahead of their use, and lane 0 picks them up by shuffle.
+    auto load_batch = [&](int batch, int& lo, int& hi) {
+      const long tt = blockIdx.x + (long)(batch * 32 + lane) * gridDim.x;
+      lo = 0; hi = 0;
+      if (tt < ntiles) { lo = a.rp[tt * TMA_TR]; hi = a.rp[min((int)tt * TMA_TR + TMA_TR, a.nv)]; }
+    };
+    int cur_lo, cur_hi, nxt_lo, nxt_hi;
+    load_batch(0, cur_lo, cur_hi);
+    load_batch(1, nxt_lo, nxt_hi);
     int t = blockIdx.x;
-    int lo_n = 0, hi_n = 0;
-    if (lane == 0 && t < ntiles) { lo_n = a.rp[t * TMA_TR]; hi_n = a.rp[min(t * TMA_TR + TMA_TR, a.nv)]; }
     for (int it = 0; t < ntiles; t += gridDim.x, it++) {
+      if (it > 0 && (it & 31) == 0) { cur_lo = nxt_lo; cur_hi = nxt_hi; load_batch(it / 32 + 1, nxt_lo, nxt_hi); }
+      const int lo = __shfl_sync(0xffffffffu, cur_lo, it & 31), hi = __shfl_sync(0xffffffffu, cur_hi, it & 31);
       if (lane == 0) {
-        const int lo = lo_n, hi = hi_n;
-        const int tn = t + gridDim.x;
-        if (tn < ntiles) { lo_n = a.rp[tn * TMA_TR]; hi_n = a.rp[min(tn * TMA_TR + TMA_TR, a.nv)]; } // in flight during the wait
         const int stage = it % nstages;
         const unsigned parity = (unsigned)((it / nstages) & 1);
         mbar_wait(&empty[stage], parity ^ 1u);

@@ -57,6 +57,34 @@ def test_fast_pattern_equals_the_literal_restatement(name):
         assert np.array_equal(rp, rp2) and np.array_equal(col, col2)
 
 
+def test_pore_without_dna_mesh_is_reproducible_and_faithful_to_the_geo():
+    """BASELINE config C4: the reference ships only pore_without_dna.geo; scripts/make_pore_without_dna_mesh.py
+    triangulates it deterministically.  The committed fixture is what the script produces, the physical line tags are the
+    .geo's (:69-74) and the domain is the .geo's polygon (box 100 x 55 minus the membrane with its two rounded corners)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("mkmesh", os.path.join(root, "scripts", "make_pore_without_dna_mesh.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    g = mk.generate()
+    a = util.load_mesh_arrays("pore_without_dna")
+    for k in a:
+        assert np.array_equal(g[k], a[k]), k
+    x, y, tri = a["x"], a["y"], a["tri"]
+    p0, p1, p2 = (np.stack([x[tri[:, i]], y[tri[:, i]]], axis=1) for i in range(3))
+    det = (p1[:, 0] - p0[:, 0]) * (p2[:, 1] - p0[:, 1]) - (p2[:, 0] - p0[:, 0]) * (p1[:, 1] - p0[:, 1])
+    assert np.all(det > 0)
+    membrane = 20.0 * 45.0 - 2 * (1.0 - np.pi / 4)  # 20 x (55 - 10) block, two corners rounded with radius 1
+    # each quarter circle is two chords: 4 circular segments of area (pi/4 - sin(pi/4)) / 2 are missing from the membrane
+    assert abs(0.5 * det.sum() - (100.0 * 55.0 - membrane) - 2 * (np.pi / 4 - np.sin(np.pi / 4))) < 1e-9
+    # tags: axis r = 0 -> 1, inflow z = -50 -> 2, outflow z = +50 -> 3, top left -> 4, top right -> 5, membrane -> 0
+    mx, my = 0.5 * (x[a["ba"]] + x[a["bb"]]), 0.5 * (y[a["ba"]] + y[a["bb"]])
+    ph = a["bphys"]
+    assert np.all(ph[my == 0] == 1) and np.all(ph[mx == -50] == 2) and np.all(ph[mx == 50] == 3)
+    assert np.all(ph[(my == 55) & (mx < 0)] == 4) and np.all(ph[(my == 55) & (mx > 0)] == 5)
+    assert np.all((np.abs(mx[ph == 0]) <= 10 + 1e-9) & (my[ph == 0] >= 10 - 1e-9))
+    assert sorted(set(ph.tolist())) == [0, 1, 2, 3, 4, 5]
+
+
 def test_config_reader(tmp_path):
     p = ora.Params.read(util.cfg_path("pore"))
     assert p.sys[0] == 7 and p.sys[1] == 1 and p.sys[4] == 3.1415 and p.sys[7] == 1e-9 and p.sys[8] == 1e-8

@@ -4,9 +4,10 @@ import os
 import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MESHES = ["one_wall", "sphere", "cylinder", "pore_small", "pore"]
+MESHES = ["one_wall", "sphere", "cylinder", "pore_small", "pore", "pore_without_dna"]
 # mesh fixture -> config that goes with it
-CASES = {"one_wall": "one_wall", "sphere": "sphere", "cylinder": "cylinder", "pore_small": "pore", "pore": "pore"}
+CASES = {"one_wall": "one_wall", "sphere": "sphere", "cylinder": "cylinder", "pore_small": "pore", "pore": "pore",
+         "pore_without_dna": "pore_without_dna"}  # (generated mesh: scripts/make_pore_without_dna_mesh.py)
 
 
 def load_mesh_arrays(name):
