@@ -27,7 +27,10 @@ namespace pnp {
 constexpr int TMA_TR = 128;                      // rows per tile
 constexpr int TMA_LPR = 1;                       // lanes per row
 constexpr int TMA_NW = TMA_TR * TMA_LPR / 32;    // consumer warps
-constexpr int TMA_THREADS = (TMA_NW + 1) * 32;   // + 1 producer warp
+// producer warps: one per copy stream of a tile -- NP value planes, column indices, row pointers, x window, and the
+// right-hand side / dot operand where the epilogue reads one
+constexpr int tma_producers(int np, int epi, int ndot) { return np + 3 + ((epi != EPI_PLAIN || ndot >= 1) ? 1 : 0); }
+constexpr int tma_threads(int np, int epi, int ndot) { return (TMA_NW + tma_producers(np, epi, ndot)) * 32; }
 constexpr int TMA_CAP = 960;                     // staged slots per tile and plane
 constexpr int TMA_MAX_STAGES = 3;
 constexpr int TMA_W = 128;                       // rows of x staged on either side of the tile (the gather window)
@@ -116,7 +119,7 @@ __device__ __forceinline__ void slot_product(const StarOpArgs& a, bool ok, int s
 }
 
 template <int NP, int EPI, int NDOT>
-__global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs a, const int nstages) {
+__global__ void __launch_bounds__(tma_threads(NP, EPI, NDOT), 1) k_star_op_tma(const StarOpArgs a, const int nstages) {
   using L = TmaLayout<NP>;
   constexpr int F = L::F;
   constexpr int LPR = TMA_LPR;
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
   const int ntiles = (a.nv + TMA_TR - 1) / TMA_TR;
   const int sp = (int)(a.stride & 1);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nstages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_NW); }
+    for (int s = 0; s < nstages; s++) { mbar_init(&full[s], tma_producers(NP, EPI, NDOT)); mbar_init(&empty[s], TMA_NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -138,13 +141,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
 #pragma unroll
   for (int j = 0; j < (NDOT > 0 ? NDOT : 1); j++) dsum[j] = 0.0;
 
-  if (warp == TMA_NW) {
-    // ---------------- producer: lane 0 feeds the ring; the other lanes of the warp walk the loop with it (the kernel's
-    // closing __syncthreads wants converged warps) ----------------
-    // The slot range of a tile comes from two row pointers in global memory.  A load issued while the bulk copies saturate
-    // DRAM takes microseconds, and with one tile of look-ahead it paced the whole pipeline (2.2 us per tile whatever the
-    // consumers did: the first two streaming versions ran at 4.1 TB/s for that reason alone).  So every lane fetches the
-    // boundaries of one of the next 32 tiles, a full batch ahead of their use, and lane 0 picks them up by shuffle.
+  if (warp >= TMA_NW) {
+    // ---------------- producers: ONE WARP PER COPY STREAM (value plane p, column indices, row pointers, gather window,
+    // right-hand side).  Issuing a bulk copy costs a chain of R2UR / ELECT / UBLKCP instructions in a single thread; one
+    // thread issuing all eleven copies of a tile needed ~4 300 cycles per tile and paced the whole kernel at 4.1 TB/s
+    // whatever the consumers did (profiles/spmv_tma_r02_summary.txt).  Lane 0 of every producer warp issues its copy; the
+    // other lanes walk the loop with it (the kernel's closing __syncthreads wants converged warps).
+    // The slot range of a tile comes from two row pointers in global memory; a load issued while the bulk copies
+    // saturate DRAM takes microseconds, so every lane fetches the boundaries of one of the next 32 tiles, a full batch
+    // ahead of their use, and lane 0 picks them up by shuffle.
+    const int role = warp - TMA_NW; // 0..NP-1: plane, NP: columns, NP+1: row pointers, NP+2: x window, NP+3: b / w1
     auto load_batch = [&](int batch, int& lo, int& hi) {
       const long tt = blockIdx.x + (long)(batch * 32 + lane) * gridDim.x;
       lo = 0; hi = 0;
@@ -164,40 +170,32 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
         unsigned char* st = stages + (size_t)stage * L::STAGE;
         const int r0 = t * TMA_TR, rows = min(TMA_TR, a.nv - r0);
         const bool staged = hi - lo <= TMA_CAP;
-        // byte counts first (one expect_tx), then the copies
-        unsigned nb_plane[NP];
-        unsigned total = 0;
-        const int lo_c = lo & ~3;
-        const unsigned nb_cols = (unsigned)(((hi - lo_c) + 3) & ~3) * 4u;
-        if (staged) {
-#pragma unroll
-          for (int p = 0; p < NP; p++) {
-            const int o = (lo + p * sp) & 1;
-            nb_plane[p] = (unsigned)(((hi - lo + o) + 1) & ~1) * 8u;
-            total += nb_plane[p];
+        const void* src = nullptr; void* dst = nullptr; unsigned nb = 0;
+        if (role < NP) {
+          if (staged) {
+            const int o = (lo + role * sp) & 1;
+            nb = (unsigned)(((hi - lo + o) + 1) & ~1) * 8u;
+            src = a.vals + (size_t)role * a.stride + (lo - o); dst = st + role * L::PLANE;
           }
-          total += nb_cols;
-        }
-        const unsigned nb_rp = (unsigned)((rows + 1 + 3) & ~3) * 4u;
-        const unsigned nb_vec = (unsigned)((F * rows + 1) & ~1) * 8u;
-        total += nb_rp;
-        constexpr bool need_b = EPI != EPI_PLAIN || NDOT >= 1;
-        if (need_b) total += nb_vec;
-        const int wlo = max(r0 - TMA_W, 0), whi = min(r0 + TMA_TR + TMA_W, a.nv);
-        const unsigned nb_win = (unsigned)((F * (whi - wlo) + 1) & ~1) * 8u;
-        total += nb_win;
-        mbar_expect_tx(&full[stage], total);
-        if (staged) {
-#pragma unroll
-          for (int p = 0; p < NP; p++) {
-            const int o = (lo + p * sp) & 1;
-            bulk_g2s(st + p * L::PLANE, a.vals + (size_t)p * a.stride + (lo - o), nb_plane[p], &full[stage]);
+        } else if (role == NP) {
+          if (staged) {
+            const int lo_c = lo & ~3;
+            nb = (unsigned)(((hi - lo_c) + 3) & ~3) * 4u;
+            src = a.col + lo_c; dst = st + L::COLS;
           }
-          bulk_g2s(st + L::COLS, a.col + lo_c, nb_cols, &full[stage]);
+        } else if (role == NP + 1) {
+          nb = (unsigned)((rows + 1 + 3) & ~3) * 4u;
+          src = a.rp + r0; dst = st + L::RP;
+        } else if (role == NP + 2) {
+          const int wlo = max(r0 - TMA_W, 0), whi = min(r0 + TMA_TR + TMA_W, a.nv);
+          nb = (unsigned)((F * (whi - wlo) + 1) & ~1) * 8u;
+          src = a.x + (size_t)F * wlo; dst = st + L::XW;
+        } else {
+          nb = (unsigned)((F * rows + 1) & ~1) * 8u;
+          src = (EPI == EPI_PLAIN ? a.w1 : a.b) + (size_t)F * r0; dst = st + L::B;
         }
-        bulk_g2s(st + L::RP, a.rp + r0, nb_rp, &full[stage]);
-        if (need_b) bulk_g2s(st + L::B, (EPI == EPI_PLAIN ? a.w1 : a.b) + (size_t)F * r0, nb_vec, &full[stage]);
-        bulk_g2s(st + L::XW, a.x + (size_t)F * wlo, nb_win, &full[stage]);
+        if (nb) { mbar_expect_tx(&full[stage], nb); bulk_g2s(dst, src, nb, &full[stage]); }
+        else mbar_arrive(&full[stage]);
       }
       __syncwarp();
     }
@@ -306,13 +304,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_star_op_tma(const StarOpArgs
     }
   }
   if (NDOT > 0) {
-    __shared__ double sm[NDOT > 0 ? NDOT : 1][TMA_NW + 1];
+    __shared__ double sm[NDOT > 0 ? NDOT : 1][TMA_NW];
 #pragma unroll
     for (int j = 0; j < (NDOT > 0 ? NDOT : 1); j++) {
       double s = dsum[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) sm[j][warp] = s;
+      if (lane == 0 && warp < TMA_NW) sm[j][warp] = s;
     }
     __syncthreads();
     if (warp == 0) {
@@ -354,7 +352,7 @@ inline int launch_star_op_tma_inst(Ctx& c, const StarOpArgs& a) {
   }
   const int ntiles = (a.nv + TMA_TR - 1) / TMA_TR;
   const int grid = ntiles < c.sm_count ? ntiles : c.sm_count;
-  k_star_op_tma<NP, EPI, NDOT><<<grid, TMA_THREADS, smem, c.stream>>>(a, nstages);
+  k_star_op_tma<NP, EPI, NDOT><<<grid, tma_threads(NP, EPI, NDOT), smem, c.stream>>>(a, nstages);
   PNP_CHECK_LAUNCH(); c.launches++;
   return grid;
 }

@@ -166,28 +166,29 @@ struct Mesh {
   void finalize() {
     nv = (int)x.size(); nT = (int)tri.size() / 3; nB = (int)ba.size();
     nbr.assign(3 * nT, -1); fseg.assign(3 * nT, -1);
-    std::map<std::pair<int, int>, std::pair<int, int>> first; // edge -> (elem, face)
+    // (edge key, 3*e + f) sorted by key: the two faces of an interior edge are neighbours in the list
+    auto key = [](int a, int b) { return ((uint64_t)std::min(a, b) << 32) | (uint64_t)std::max(a, b); };
+    std::vector<std::pair<uint64_t, int>> faces; faces.reserve(3 * (size_t)nT);
     for (int e = 0; e < nT; e++)
-      for (int f = 0; f < 3; f++) {
-        int a = tri[3 * e + FACE_V[f][0]], b = tri[3 * e + FACE_V[f][1]];
-        auto key = std::make_pair(std::min(a, b), std::max(a, b));
-        auto it = first.find(key);
-        if (it == first.end()) first[key] = {e, f};
-        else {
-          nbr[3 * e + f] = it->second.first;
-          nbr[3 * it->second.first + it->second.second] = e;
-        }
+      for (int f = 0; f < 3; f++) faces.push_back({key(tri[3 * e + FACE_V[f][0]], tri[3 * e + FACE_V[f][1]]), 3 * e + f});
+    std::sort(faces.begin(), faces.end());
+    std::vector<std::pair<uint64_t, int>> segs; segs.reserve(nB);
+    for (int s = 0; s < nB; s++) segs.push_back({key(ba[s], bb[s]), s});
+    std::sort(segs.begin(), segs.end()); // (a segment listed twice: the later one wins, as with the map this replaces)
+    for (size_t i = 0; i < faces.size();) {
+      size_t j = i + 1;
+      while (j < faces.size() && faces[j].first == faces[i].first) j++;
+      if (j - i > 2) throw std::runtime_error("edge shared by more than two elements");
+      if (j - i == 2) {
+        nbr[faces[i].second] = faces[i + 1].second / 3;
+        nbr[faces[i + 1].second] = faces[i].second / 3;
+      } else {
+        auto it = std::upper_bound(segs.begin(), segs.end(), std::make_pair(faces[i].first, 0x7fffffff));
+        if (it == segs.begin() || (it - 1)->first != faces[i].first) throw std::runtime_error("boundary face without boundary segment");
+        fseg[faces[i].second] = (it - 1)->second;
       }
-    std::map<std::pair<int, int>, int> seg;
-    for (int s = 0; s < nB; s++) seg[{std::min(ba[s], bb[s]), std::max(ba[s], bb[s])}] = s;
-    for (int e = 0; e < nT; e++)
-      for (int f = 0; f < 3; f++)
-        if (nbr[3 * e + f] < 0) {
-          int a = tri[3 * e + FACE_V[f][0]], b = tri[3 * e + FACE_V[f][1]];
-          auto it = seg.find({std::min(a, b), std::max(a, b)});
-          if (it == seg.end()) throw std::runtime_error("boundary face without boundary segment");
-          fseg[3 * e + f] = it->second;
-        }
+      i = j;
+    }
   }
 };
 
