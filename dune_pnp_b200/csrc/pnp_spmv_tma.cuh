@@ -234,16 +234,55 @@ __global__ void __launch_bounds__(tma_threads(NP, EPI, NDOT), 1) k_star_op_tma(c
       for (int p = 0; p < NP; p++) dg[p] = 0.0;
       const int len = e0 - b0;
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
-      // slot `sub` first: for sub == 0 it is the diagonal, whose values the smoother epilogue inverts
       if (staged) {
-        slot_product<NP, true>(a, sub < len, b0 + sub, sv, vb, sc, cbase, sx, wlo, wn, acc, EPI == EPI_JACOBI ? dg : nullptr);
-        for (int j0 = sub + LPR; j0 < maxlen; j0 += 3 * LPR) {
+        // The first MAXS slots of the lane in three unrolled phases -- column indices, then ALL x gathers, then the
+        // products -- so that the gathers of columns outside the staged window (10 % of the slots, ordinary loads that
+        // go to L2 or DRAM while the bulk copies saturate it) are in flight together: taken slot by slot, each of them
+        // stalled the warp for a full memory round trip and the consumers, not the feed, paced the kernel
+        // (profiles/spmv_tma_r02_summary.txt).  Slot `sub` comes first: for sub == 0 it is the diagonal, whose values
+        // the smoother epilogue inverts.
+        constexpr int MAXS = (8 + LPR - 1) / LPR;
+        unsigned cj[MAXS];
+        bool okj[MAXS];
+        double xj[MAXS][F];
 #pragma unroll
-          for (int u = 0; u < 3; u++) {
-            const int j = j0 + u * LPR;
-            slot_product<NP, true>(a, j < len, b0 + j, sv, vb, sc, cbase, sx, wlo, wn, acc, nullptr);
+        for (int u = 0; u < MAXS; u++) {
+          const int j = sub + u * LPR;
+          okj[u] = j < len;
+          cj[u] = okj[u] ? (sc[b0 + j - cbase] & STAR_VMASK) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < MAXS; u++) {
+          const unsigned cw = cj[u] - (unsigned)wlo; // (wraps for columns below the window)
+          const bool in = cw < wn;
+          const bool ldg = okj[u] && !in, lds = okj[u] && in;
+#pragma unroll
+          for (int k = 0; k < F; k++) {
+            double xg = 0.0, xs = 0.0;
+            if (ldg) xg = a.x[(size_t)F * cj[u] + k];
+            if (lds) xs = sx[F * cw + k];
+            xj[u][k] = in ? xs : xg;
           }
         }
+#pragma unroll
+        for (int u = 0; u < MAXS; u++) {
+          const int s = b0 + sub + u * LPR;
+          double v[NP];
+#pragma unroll
+          for (int p = 0; p < NP; p++) v[p] = okj[u] ? sv[vb[p] + s] : 0.0;
+          if (EPI == EPI_JACOBI && u == 0) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) dg[p] = v[p];
+          }
+          if (NP == 1) acc[0] += v[0] * xj[u][0];
+          else {
+            acc[0] += v[0] * xj[u][0] + v[1 % NP] * xj[u][1 % F] + v[2 % NP] * xj[u][2 % F];
+            acc[1 % F] += v[3 % NP] * xj[u][0] + v[4 % NP] * xj[u][1 % F];
+            acc[2 % F] += v[5 % NP] * xj[u][0] + v[6 % NP] * xj[u][2 % F];
+          }
+        }
+        for (int j = sub + MAXS * LPR; j < maxlen; j += LPR) // rows with more slots (valence > 7)
+          slot_product<NP, true>(a, j < len, b0 + j, sv, vb, sc, cbase, sx, wlo, wn, acc, nullptr);
       } else { // over-full tile: slots straight from global memory
         slot_product<NP, false>(a, sub < len, b0 + sub, sv, vb, sc, cbase, sx, wlo, wn, acc, EPI == EPI_JACOBI ? dg : nullptr);
         for (int j = sub + LPR; j < maxlen; j += LPR)

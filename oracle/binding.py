@@ -37,6 +37,9 @@ def lib():
             getattr(L, f).restype = C.c_void_p
         L.ora_pattern.restype = C.c_long
         L.ora_pattern_sets.restype = C.c_long
+        L.ora_bench_create.restype = C.c_void_p
+        L.ora_bench_nnz.restype = C.c_long
+        L.ora_set_threads(1)
         _LIB = L
     return _LIB
 
@@ -260,3 +263,37 @@ def write_vtk(mesh, name, fields, names, ascii=False):
     ptrs = (_dp * len(arrs))(*[_d(a) for a in arrs])
     nm = (C.c_char_p * len(names))(*[n.encode() for n in names])
     _chk(lib().ora_write_vtk(mesh.h, name.encode(), len(arrs), ptrs, nm, int(ascii)))
+
+
+def max_threads():
+    return int(lib().ora_max_threads())
+
+
+def assembly_par(mesh, params, op, u, threads, mode=0):
+    """Multi-core (OpenMP, two-phase) residual and Jacobian; must equal residual() / jacobian() bit for bit."""
+    u = _f64(u)
+    rowptr, col = pattern(mesh, params, nfields(op))
+    r = np.zeros_like(u); val = np.zeros(len(col))
+    _chk(lib().ora_assembly_par(mesh.h, params.h, op, _d(u), threads, mode, _d(r), _d(val)))
+    return r, val
+
+
+class Bench:
+    """Phases of one PNP Newton step on `threads` host cores (CPU baseline of bench.py)."""
+
+    def __init__(self, mesh, params, op=OP_PNP):
+        self.mesh, self.params = mesh, params
+        self.h = C.c_void_p(_chk(lib().ora_bench_create(mesh.h, params.h, op)))
+        self.nnz = lib().ora_bench_nnz(self.h)
+
+    def step(self, u, threads=1, jac_mode=0, krylov_iters=5, spmv_reps=3):
+        out = np.zeros(8)
+        _chk(lib().ora_bench_step(self.h, _d(_f64(u)), threads, jac_mode, krylov_iters, spmv_reps, _d(out)))
+        return dict(jacobian_s=out[0], residual_s=out[1], krylov_s=out[2], spmv_s=out[3], total_s=out[4], defect=out[5],
+                    reduction=out[6], krylov_iterations=int(out[7]))
+
+    def __del__(self):
+        try:
+            lib().ora_bench_free(self.h)
+        except Exception:
+            pass

@@ -260,4 +260,87 @@ int ora_write_vtk(void* mh, const char* name, int n, const double* const* fields
   ORA_CATCH(-1)
 }
 
+// ---- CPU baseline of bench.py: the phases of one PNP Newton step, timed on `threads` cores ----
+struct BenchState {
+  const Mesh* m; const Sysparams* s; Space sp; OpCtx c; CSR A; Incidence I; std::vector<double> scratch, r, z, y;
+};
+void ora_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n < 1 ? 1 : n);
+#else
+  (void)n;
+#endif
+}
+int ora_max_threads() {
+#ifdef _OPENMP
+  return omp_get_num_procs();
+#else
+  return 1;
+#endif
+}
+void* ora_bench_create(void* mh, void* ph, int op) {
+  ORA_TRY
+  auto* b = new BenchState;
+  b->m = (Mesh*)mh; b->s = &((Params*)ph)->s;
+  b->sp = make_space(*b->m, *b->s, op_fields(op), 0);
+  b->c = make_ctx(b->m, b->s, op, nullptr, nullptr, 1.0, -1);
+  b->A = make_pattern(b->sp);
+  b->I = vertex_elements(*b->m);
+  b->r.assign(b->sp.N(), 0.0); b->z.assign(b->sp.N(), 0.0); b->y.assign(b->sp.N(), 0.0);
+  return b;
+  ORA_CATCH(nullptr)
+}
+void ora_bench_free(void* h) { delete (BenchState*)h; }
+long ora_bench_nnz(void* h) { return (long)((BenchState*)h)->A.col.size(); }
+// One bounded sample of a Newton step at state u: 1 Jacobian assembly (jac_mode 0: the reference's FD jacobian_volume),
+// 2 residual assemblies, `krylov_iters` iterations of BiCGSTAB + SSOR(1) (the reference's default backend) on A z = r,
+// and `spmv_reps` extra SpMVs timed on their own.  out[8] = {t_jacobian, t_residual (one), t_krylov (all iterations),
+// t_spmv (one, median), t_total (jacobian + 2 residuals + krylov), defect, reduction reached by the bounded solve, 0}
+int ora_bench_step(void* h, const double* u, int threads, int jac_mode, int krylov_iters, int spmv_reps, double* out) {
+  ORA_TRY
+  BenchState& b = *(BenchState*)h;
+  ora_set_threads(threads);
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point e) { return std::chrono::duration<double>(e - a).count(); };
+  const int N = b.sp.N();
+  auto t0 = now();
+  jacobian_par(b.sp, b.c, b.I, u, b.A, jac_mode, 1e-11, b.scratch);
+  auto t1 = now();
+  residual_par(b.sp, b.c, b.I, u, b.r.data(), b.scratch);
+  auto t2 = now();
+  residual_par(b.sp, b.c, b.I, u, b.y.data(), b.scratch); // the line search's trial residual
+  auto t3 = now();
+  const double defect = nrm2(N, b.r.data());
+  std::fill(b.z.begin(), b.z.end(), 0.0);
+  std::vector<double> rhs = b.r;
+  auto t4 = now();
+  LinResult lr = bicgstab(b.A, b.z.data(), rhs.data(), 1e-30, krylov_iters, PREC_SSOR, 1);
+  auto t5 = now();
+  std::vector<double> ts;
+  for (int k = 0; k < spmv_reps; k++) { auto a0 = now(); b.A.mv(b.z.data(), b.y.data()); ts.push_back(sec(a0, now())); }
+  std::sort(ts.begin(), ts.end());
+  out[0] = sec(t0, t1); out[1] = 0.5 * sec(t1, t3); out[2] = sec(t4, t5); out[3] = ts.empty() ? 0.0 : ts[ts.size() / 2];
+  out[4] = sec(t0, t3) + sec(t4, t5); out[5] = defect; out[6] = lr.reduction; out[7] = lr.iterations;
+  ora_set_threads(1);
+  return 0;
+  ORA_CATCH(-1)
+}
+// bit-identity check of the multi-core assembly against the sequential one (tests)
+int ora_assembly_par(void* mh, void* ph, int op, const double* u, int threads, int mode, double* r, double* val) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  Space sp = make_space(*m, *s, op_fields(op), 0);
+  OpCtx c = make_ctx(m, s, op, nullptr, nullptr, 1.0, -1);
+  CSR A = make_pattern(sp);
+  Incidence I = vertex_elements(*m);
+  std::vector<double> scratch;
+  ora_set_threads(threads);
+  residual_par(sp, c, I, u, r, scratch);
+  jacobian_par(sp, c, I, u, A, mode, 1e-11, scratch);
+  ora_set_threads(1);
+  std::copy(A.val.begin(), A.val.end(), val);
+  return 0;
+  ORA_CATCH(-1)
+}
+
 } // extern "C"

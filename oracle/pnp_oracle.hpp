@@ -21,6 +21,9 @@
 // path is compiled with -fmad=false so element results can be compared bitwise).
 #pragma once
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -547,6 +550,7 @@ struct CSR {
     return (it != e && *it == c) ? (int)(it - col.begin()) : -1;
   }
   void mv(const double* xx, double* yy) const {
+#pragma omp parallel for schedule(static)
     for (int r = 0; r < n; r++) {
       double sum = 0.0;
       for (int k = rowptr[r]; k < rowptr[r + 1]; k++) sum += val[k] * xx[col[k]];
@@ -704,6 +708,72 @@ inline void jacobian(const Space& sp, const OpCtx& c, const double* u, CSR& A, i
 }
 
 // ----------------------------------------------------------------------------
+// Multi-core variants of the grid operator for the CPU baseline ("(ii) all host cores via
+// OpenMP").  Two phases, no atomics: (1) element loop in parallel into per-element blocks, (2) row loop in parallel,
+// every dof summing its elements' contributions in ascending element order -- the order of the sequential scatter, so
+// the results equal residual() / jacobian() bit for bit whatever the thread count (tests/test_oracle.py).
+// ----------------------------------------------------------------------------
+struct Incidence { std::vector<int> ptr, elem; }; // vertex -> (element, local index) pairs, elements ascending: elem = 4*e + i
+inline Incidence vertex_elements(const Mesh& m) {
+  Incidence I; I.ptr.assign(m.nv + 1, 0);
+  for (int e = 0; e < m.nT; e++) for (int i = 0; i < 3; i++) I.ptr[m.tri[3 * e + i] + 1]++;
+  for (int v = 0; v < m.nv; v++) I.ptr[v + 1] += I.ptr[v];
+  I.elem.resize(I.ptr[m.nv]);
+  std::vector<int> fill(I.ptr.begin(), I.ptr.end() - 1);
+  for (int e = 0; e < m.nT; e++) for (int i = 0; i < 3; i++) I.elem[fill[m.tri[3 * e + i]]++] = 4 * e + i;
+  return I;
+}
+inline void residual_par(const Space& sp, const OpCtx& c, const Incidence& I, const double* u, double* r, std::vector<double>& scratch) {
+  const Mesh& m = *sp.m;
+  const int nf = sp.fields, n = 3 * nf;
+  scratch.resize((size_t)n * m.nT);
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < m.nT; e++) {
+    double xl[9], *rl = &scratch[(size_t)n * e];
+    for (int k = 0; k < nf; k++) for (int i = 0; i < 3; i++) xl[3 * k + i] = u[sp.gdof(k, m.tri[3 * e + i])];
+    for (int q = 0; q < n; q++) rl[q] = 0.0;
+    alpha_volume(c, e, xl, rl);
+    for (int fi = 0; fi < 3; fi++) { const int f = FACE_ITER[fi]; if (m.fseg[3 * e + f] >= 0) alpha_boundary(c, e, f, rl); }
+  }
+#pragma omp parallel for schedule(static)
+  for (int v = 0; v < m.nv; v++)
+    for (int k = 0; k < nf; k++) {
+      const int g = sp.gdof(k, v);
+      double sum = 0.0;
+      for (int t = I.ptr[v]; t < I.ptr[v + 1]; t++) sum += scratch[(size_t)n * (I.elem[t] >> 2) + 3 * k + (I.elem[t] & 3)];
+      r[g] = sp.dirichlet[g] ? 0.0 : sum;
+    }
+}
+inline void jacobian_par(const Space& sp, const OpCtx& c, const Incidence& I, const double* u, CSR& A, int mode, double eps,
+                         std::vector<double>& scratch) {
+  const Mesh& m = *sp.m;
+  const int nf = sp.fields, n = 3 * nf;
+  scratch.resize((size_t)n * n * m.nT);
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < m.nT; e++) {
+    double xl[9], *Ae = &scratch[(size_t)n * n * e];
+    for (int k = 0; k < nf; k++) for (int i = 0; i < 3; i++) xl[3 * k + i] = u[sp.gdof(k, m.tri[3 * e + i])];
+    for (int q = 0; q < n * n; q++) Ae[q] = 0.0;
+    if (mode == 0) jacobian_volume_fd(c, e, xl, Ae, eps); else jacobian_volume_exact(c, e, xl, Ae);
+  }
+#pragma omp parallel for schedule(static)
+  for (int v = 0; v < m.nv; v++)
+    for (int ki = 0; ki < nf; ki++) {
+      const int gi = sp.gdof(ki, v);
+      for (int k = A.rowptr[gi]; k < A.rowptr[gi + 1]; k++) A.val[k] = 0.0;
+      if (sp.dirichlet[gi]) { A.val[A.find(gi, gi)] = 1.0; continue; }
+      for (int t = I.ptr[v]; t < I.ptr[v + 1]; t++) {
+        const int e = I.elem[t] >> 2, i = I.elem[t] & 3;
+        const double* Ae = &scratch[(size_t)n * n * e];
+        for (int kj = 0; kj < nf; kj++) for (int j = 0; j < 3; j++) {
+          const int gj = sp.gdof(kj, m.tri[3 * e + j]);
+          if (!sp.dirichlet[gj]) A.val[A.find(gi, gj)] += Ae[(3 * ki + i) * n + 3 * kj + j];
+        }
+      }
+    }
+}
+
+// ----------------------------------------------------------------------------
 // BCExtension + interpolate (dirichlet_bc.hh:21-123; App. A.6 "interpolate")
 // ----------------------------------------------------------------------------
 inline bool global_on_intersection(const Mesh& m, double px, double py, int e, int f) { // :21-33
@@ -819,7 +889,13 @@ struct Preconditioner {
   }
 };
 inline void prec_apply(const CSR& A, int prec, int steps, double* v, const double* d) { Preconditioner(A, prec, steps).apply(v, d); }
-inline double dot(int N, const double* a, const double* b) { double s = 0; for (int i = 0; i < N; i++) s += a[i] * b[i]; return s; }
+// (one thread -- the default, and what every parity test runs with -- gives the plain sequential sum)
+inline double dot(int N, const double* a, const double* b) {
+  double s = 0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
+  for (int i = 0; i < N; i++) s += a[i] * b[i];
+  return s;
+}
 inline double nrm2(int N, const double* a) { return std::sqrt(dot(N, a, a)); }
 
 // BiCGSTABSolver::apply(x,b): b is overwritten with the residual
@@ -827,6 +903,7 @@ inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, 
   int N = A.n; LinResult res; const Preconditioner P(A, prec, steps);
   std::vector<double> r(N), rt(N), p(N, 0.0), v(N, 0.0), t(N), y(N), tmp(N);
   A.mv(x, tmp.data());
+#pragma omp parallel for schedule(static)
   for (int i = 0; i < N; i++) r[i] = b[i] - tmp[i];
   rt = r;
   double rho = 1, alpha = 1, omega = 1, rho_new, beta, h;
@@ -844,6 +921,7 @@ inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, 
     if (it < 1) p = r;
     else {
       beta = (rho_new / rho) * (alpha / omega);
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < N; i++) { p[i] += -omega * v[i]; p[i] *= beta; p[i] += r[i]; }
     }
     P.apply(y.data(), p.data());
@@ -851,6 +929,7 @@ inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, 
     h = dot(N, rt.data(), v.data());
     if (std::fabs(h) < 1e-80) { res.status = 2; return finish(false); }
     alpha = rho_new / h;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < N; i++) { x[i] += alpha * y[i]; r[i] += -alpha * v[i]; }
     norm = nrm2(N, r.data());
     if (norm < reduction * norm0) return finish(true);
@@ -858,6 +937,7 @@ inline LinResult bicgstab(const CSR& A, double* x, double* b, double reduction, 
     P.apply(y.data(), r.data());
     A.mv(y.data(), t.data());
     omega = dot(N, t.data(), r.data()) / dot(N, t.data(), t.data());
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < N; i++) { x[i] += omega * y[i]; r[i] += -omega * t[i]; }
     rho = rho_new;
     norm = nrm2(N, r.data());

@@ -23,23 +23,26 @@ __device__ __forceinline__ void bulk(void* d, const void* s, unsigned n, uint64_
 }
 
 // (a) TMA: thread 0 of warp `nw` produces, nw consumer warps release
-__global__ void k_tma(const char* src, size_t total, int stage_bytes, int nstages, int ncopies, int nw, unsigned long long* sink) {
+__global__ void k_tma(const char* src, size_t total, int stage_bytes, int nstages, int ncopies, int nw, unsigned long long* sink, size_t stream_stride = 0, int src_off = 0, int shrink = 0) {
   extern __shared__ __align__(128) unsigned char sm[];
   uint64_t* full = (uint64_t*)sm; uint64_t* empty = full + 8;
   unsigned char* buf = sm + 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { for (int s = 0; s < nstages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], nw); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  const long ntiles = total / stage_bytes;
+  const long ntiles = (stream_stride ? stream_stride * ncopies : total) / stage_bytes;
   if (warp == nw) {
     if (lane == 0) {
       int it = 0;
       for (long t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
         const int st = it % nstages; const unsigned par = (it / nstages) & 1;
         mbar_wait(&empty[st], par ^ 1u);
-        mbar_expect(&full[st], stage_bytes);
         const int cb = stage_bytes / ncopies;
-        for (int k = 0; k < ncopies; k++) bulk(buf + (size_t)st * stage_bytes + (size_t)k * cb, src + (size_t)t * stage_bytes + (size_t)k * cb, cb, &full[st]);
+        mbar_expect(&full[st], (cb - shrink) * ncopies);
+        for (int k = 0; k < ncopies; k++) {
+          const char* sk = stream_stride ? src + (size_t)k * stream_stride + (size_t)t * cb : src + (size_t)t * stage_bytes + (size_t)k * cb;
+          bulk(buf + (size_t)st * stage_bytes + (size_t)k * cb, sk + src_off, cb - shrink, &full[st]);
+        }
       }
     }
   } else {
@@ -111,19 +114,28 @@ int main() {
   CK(cudaFuncSetAttribute(k_ldgsts, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   char nm[200];
   run("ldg.128, 148*8 blocks x 256", [&] { k_ldg<<<sms * 8, 256>>>((const uint4*)src, total / 16, sink); });
-  for (int ctas = 1; ctas <= 4; ctas *= 2)
-    for (int sb : {16384, 32768, 65536})
-      for (int ns : {2, 3, 4, 6})
+  for (int ctas = 1; ctas <= 1; ctas *= 2)
+    for (int sb : {65536})
+      for (int ns : {2, 3})
         for (int nc : {1, 8}) {
           const int smem = 128 + sb * ns;
           if (smem * ctas > 220 * 1024) continue;
           snprintf(nm, sizeof nm, "tma  ctas/SM %d stage %3d KB x %d stages, %d copies/stage", ctas, sb / 1024, ns, nc);
           run(nm, [&] { k_tma<<<sms * ctas, 5 * 32, smem>>>(src, total, sb, ns, nc, 4, sink); });
         }
-  for (int ctas = 1; ctas <= 2; ctas *= 2)
-    for (int sb : {32768, 65536})
-      for (int ns : {2, 3})
-        for (int np : {1, 2, 4}) {
+  // the SpMV's pattern: 8 streams far apart, misaligned starts, odd sizes
+  for (int ns : {2, 3})
+    for (int mode = 0; mode < 4; mode++) {
+      const int sb = 65536, nc = 8;
+      const size_t stride = (mode & 1) ? (total / 8) : 0;
+      const int off = (mode & 2) ? 16 : 0, shr = (mode & 2) ? 48 : 0;
+      snprintf(nm, sizeof nm, "tma 64 KB x %d stages, 8 copies: %s, %s", ns, stride ? "8 streams 2 GiB apart" : "contiguous", off ? "misaligned +16 B, size -48 B" : "aligned");
+      run(nm, [&] { k_tma<<<sms, 5 * 32, 128 + sb * ns>>>(src, total, sb, ns, nc, 4, sink, stride, off, shr); });
+    }
+  for (int ctas = 1; ctas <= 1; ctas *= 2)
+    for (int sb : {65536})
+      for (int ns : {2})
+        for (int np : {2}) {
           const int smem = 128 + sb * ns;
           if (smem * ctas > 220 * 1024) continue;
           snprintf(nm, sizeof nm, "ldgsts ctas/SM %d stage %3d KB x %d stages, %d producer warps", ctas, sb / 1024, ns, np);
