@@ -382,10 +382,10 @@ def run_gpu(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     # algorithmic bytes of one fine-level 3-field SpMV (DESIGN.md "SpMV"): 7 value planes + column index per
     # slot, row pointer + x read + y written per vertex
-    # per epilogue kind: plain y = A x; residual also reads b (24 B/vertex); a smoother step reads b, its own x row
-    # and the 3x3 inverse diagonal block (24 + 24 + 72 B/vertex)
+    # per epilogue kind: plain y = A x; residual also reads b (24 B/vertex); a smoother step reads b and its own x row
+    # (24 + 24 B/vertex; the 3x3 inverse diagonal block is computed in the kernel from the diagonal slot, not read)
     base = (7 * 8 + 4) * ns + (4 + 2 * 3 * 8) * n_own   # rank 0's share
-    kind_bytes = [base, base + 24 * n_own, base + 120 * n_own]
+    kind_bytes = [base, base + 24 * n_own, base + 48 * n_own]
     spmv_total_bytes = sum(b * n for b, n in zip(kind_bytes, n_spmv))
     spmv_ms_by_kind, n_spmv_by_kind = spmv_ms, n_spmv
     spmv_ms, n_spmv = sum(spmv_ms), sum(n_spmv)

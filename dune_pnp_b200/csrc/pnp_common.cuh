@@ -65,7 +65,8 @@ template <class T> struct DBuf {
 // process-wide tuning knobs (pnp_tune): experiments and tests switch kernel variants without rebuilding
 struct Tune {
   int tma = 1;            // streaming (bulk-copy) SpMV for large levels; 0: plain-load kernel everywhere
-  int tma_stages = 3;     // ring depth of the streaming SpMV (2..3)
+  int tma_stages = 2;     // ring depth of the streaming SpMV (2..3); two stages leave more of the SM's memory to L1
+  int tma_lpr = 2;        // lanes per row in the streaming SpMV (1 or 2): 2 -> eight consumer warps per SM
   long tma_min_rows = -1; // smallest level the streaming SpMV serves (-1: two tiles per SM)
 };
 inline Tune& tune() { static Tune t; return t; }

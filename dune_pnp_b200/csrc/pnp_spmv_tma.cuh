@@ -25,12 +25,11 @@
 namespace pnp {
 
 constexpr int TMA_TR = 128;                      // rows per tile
-constexpr int TMA_LPR = 1;                       // lanes per row
-constexpr int TMA_NW = TMA_TR * TMA_LPR / 32;    // consumer warps
+constexpr int tma_nw(int lpr) { return TMA_TR * lpr / 32; } // consumer warps for `lpr` lanes per row
 // producer warps: one per copy stream of a tile -- NP value planes, column indices, row pointers, x window, and the
 // right-hand side / dot operand where the epilogue reads one
 constexpr int tma_producers(int np, int epi, int ndot) { return np + 3 + ((epi != EPI_PLAIN || ndot >= 1) ? 1 : 0); }
-constexpr int tma_threads(int np, int epi, int ndot) { return (TMA_NW + tma_producers(np, epi, ndot)) * 32; }
+constexpr int tma_threads(int np, int epi, int ndot, int lpr) { return (tma_nw(lpr) + tma_producers(np, epi, ndot)) * 32; }
 constexpr int TMA_CAP = 960;                     // staged slots per tile and plane
 constexpr int TMA_MAX_STAGES = 3;
 constexpr int TMA_W = 128;                       // rows of x staged on either side of the tile (the gather window)
@@ -118,11 +117,11 @@ __device__ __forceinline__ void slot_product(const StarOpArgs& a, bool ok, int s
   }
 }
 
-template <int NP, int EPI, int NDOT>
-__global__ void __launch_bounds__(tma_threads(NP, EPI, NDOT), 1) k_star_op_tma(const StarOpArgs a, const int nstages) {
+template <int NP, int EPI, int NDOT, int LPR>
+__global__ void __launch_bounds__(tma_threads(NP, EPI, NDOT, LPR), 1) k_star_op_tma(const StarOpArgs a, const int nstages) {
   using L = TmaLayout<NP>;
   constexpr int F = L::F;
-  constexpr int LPR = TMA_LPR;
+  constexpr int TMA_NW = tma_nw(LPR);
   constexpr int RW = 32 / LPR;          // rows per consumer warp and tile
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -379,21 +378,25 @@ inline int star_op_tma_stages() {
   return v < 2 ? 2 : (v > TMA_MAX_STAGES ? TMA_MAX_STAGES : v);
 }
 
-template <int NP, int EPI, int NDOT>
-inline int launch_star_op_tma_inst(Ctx& c, const StarOpArgs& a) {
+template <int NP, int EPI, int NDOT, int LPR>
+inline int launch_star_op_tma_lpr(Ctx& c, const StarOpArgs& a) {
   using L = TmaLayout<NP>;
   const int nstages = star_op_tma_stages();
   const int smem = L::smem_bytes(nstages);
   static unsigned long long configured = 0; // per device bit: the attribute is per device and function
   if (!(configured >> (c.device & 63) & 1ull)) {
-    PNP_CUDA(cudaFuncSetAttribute(k_star_op_tma<NP, EPI, NDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::smem_bytes(TMA_MAX_STAGES)));
+    PNP_CUDA(cudaFuncSetAttribute(k_star_op_tma<NP, EPI, NDOT, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::smem_bytes(TMA_MAX_STAGES)));
     configured |= 1ull << (c.device & 63);
   }
   const int ntiles = (a.nv + TMA_TR - 1) / TMA_TR;
   const int grid = ntiles < c.sm_count ? ntiles : c.sm_count;
-  k_star_op_tma<NP, EPI, NDOT><<<grid, tma_threads(NP, EPI, NDOT), smem, c.stream>>>(a, nstages);
+  k_star_op_tma<NP, EPI, NDOT, LPR><<<grid, tma_threads(NP, EPI, NDOT, LPR), smem, c.stream>>>(a, nstages);
   PNP_CHECK_LAUNCH(); c.launches++;
   return grid;
+}
+template <int NP, int EPI, int NDOT>
+inline int launch_star_op_tma_inst(Ctx& c, const StarOpArgs& a) {
+  return tune().tma_lpr == 2 ? launch_star_op_tma_lpr<NP, EPI, NDOT, 2>(c, a) : launch_star_op_tma_lpr<NP, EPI, NDOT, 1>(c, a);
 }
 
 // launches the streaming or the plain-load kernel; returns the grid size (number of partial-sum blocks)
