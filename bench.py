@@ -95,12 +95,15 @@ def carry_numpy(m_coarse, u_lex, F):
     return np.concatenate([u, 0.5 * (u[:, a] + u[:, b])], axis=1).reshape(-1)
 
 
-def cpu_newton_step(level=0, reps=1):
-    """One oracle Newton step of the reference flow on the pore mesh: the SECOND Newton iteration (start state =
-    state after the first iteration, stored in tests/golden/pore_solution.npz by scripts/make_golden_solutions.py),
-    optionally P1-interpolated `level` times.  Solver as the reference's default build: BiCGSTAB + SSOR(1)
-    (LINEARSOLVER=1, instationary_pnp_from_pb_md.hh:188-191), FD Jacobian (eps 1e-11), cfg Newton settings.
-    Level 0 (9 144 dofs) is the bounded sample: at level 1 the same step already needs ~20 000 Krylov iterations."""
+_CPU_STATE = {}
+
+
+def cpu_setup(level):
+    """Oracle objects for the CPU arm at refinement level `level` of the pore mesh (cached): mesh, pattern, incidence lists
+    and the start state -- the state after the first PNP Newton iteration on the unrefined mesh
+    (tests/golden/pore_solution.npz, scripts/make_golden_solutions.py), P1-interpolated `level` times."""
+    if level in _CPU_STATE:
+        return _CPU_STATE[level]
     from oracle import binding as ora
     import util
     a, cfg = load_case()
@@ -110,31 +113,58 @@ def cpu_newton_step(level=0, reps=1):
     for _ in range(level):
         u = carry_numpy(m, u, 3)
         m = m.refine(1)
-    opts1 = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, maxit=1)
-    ts, info = [], None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        _, info = ora.newton(m, p, ora.OP_PNP, u, opts1)
-        ts.append(time.perf_counter() - t0)
-    t = float(np.median(ts))
-    return dict(dofs=3 * m.nv, seconds=t, value=3 * m.nv / t, lin_its=info["total_linear_iterations"],
-                ls_trials=info["total_ls_trials"], level=level)
+    _CPU_STATE[level] = (ora.Bench(m, p, ora.OP_PNP), m, u)
+    return _CPU_STATE[level]
+
+
+def cpu_newton_step(level=5, threads=1, krylov_iters=5):
+    """One BOUNDED sample of the reference's Newton step on the host (the oracle; DUNE itself cannot be built here): the
+    reference's own jacobian_volume (NumericalJacobianVolume, eps 1e-11), two residual assemblies (defect + one line-search
+    trial) and `krylov_iters` iterations of its default backend BiCGSTAB + SSOR(1) (instationary_pnp_from_pb_md.hh:188-191).
+    The Krylov budget is what the GPU step needs with its multigrid (5); BiCGSTAB + SSOR(1) needs 1 440 iterations for
+    this step on the unrefined mesh and more on every finer one, so the sample is a LOWER bound of the reference's step
+    time.  threads > 1: element / row loops and vector operations on that many cores (OpenMP), SSOR sweeps sequential."""
+    b, m, u = cpu_setup(level)
+    r = b.step(u, threads=threads, jac_mode=0, krylov_iters=krylov_iters)
+    dofs = 3 * m.nv
+    nnz = b.nnz
+    return dict(dofs=dofs, level=level, threads=threads, seconds=r["total_s"], value=dofs / r["total_s"],
+                phases_s={"jacobian_fd": r["jacobian_s"], "residual": r["residual_s"], "krylov_iteration": r["krylov_s"] / max(r["krylov_iterations"], 1),
+                          "spmv": r["spmv_s"]},
+                spmv_gbs=(12.0 * nnz + 20.0 * dofs) / r["spmv_s"] / 1e9, assembled_dofs_per_s=dofs / (r["jacobian_s"] + r["residual_s"]),
+                krylov_iterations=r["krylov_iterations"])
+
+
+def cpu_sample_text(r):
+    return ("oracle (CPU restatement of the reference path), pore mesh refined %d times (%d dofs), %d thread(s): FD Jacobian %.2f s + "
+            "2 residuals x %.2f s + %d BiCGSTAB/SSOR(1) iterations x %.2f s (budget = the GPU step's iteration count; the "
+            "reference's solver needs >= 1 440: lower bound of its step time); SpMV %.1f GB/s" % (
+                r["level"], r["dofs"], r["threads"], r["phases_s"]["jacobian_fd"], r["phases_s"]["residual"], r["krylov_iterations"],
+                r["phases_s"]["krylov_iteration"], r["spmv_gbs"]))
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    res = [cpu_newton_step(args.cpu_level, reps=1) for _ in range(args.warmup + args.steps)][args.warmup:]
+    from oracle import binding as ora
+    threads = args.cpu_threads if args.cpu_threads > 0 else ora.max_threads()
+    # the sample is sized so that W + K steps end within a few minutes: ~20 s per step at level 5 on 8 cores, ~5 s at level 4
+    # (DOF/s barely depends on the level: every phase is linear in the mesh size)
+    level = args.cpu_level if args.cpu_level >= 0 else (5 if args.warmup + args.steps <= 8 else 4)
+    cpu_setup(level)
+    res = [cpu_newton_step(level, threads) for _ in range(args.warmup + args.steps)][args.warmup:]
     t = float(np.mean([r["seconds"] for r in res]))
     r = res[-1]
-    sample = "pore mesh refined %d times (%d dofs), one Newton step: FD Jacobian + BiCGSTAB/SSOR(1) (%d its) + line search" % (
-        r["level"], r["dofs"], r["lin_its"])
+    one = cpu_newton_step(level, 1)   # the single-core figures beside it
     line = {"impl": "reference", "metric": METRIC, "value": r["dofs"] / t, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "pore_pnp Newton step (CPU sample at refinement level %d)" % r["level"],
-                       "levels": r["level"], "dofs": r["dofs"]},
-            "cpu_baseline": {"value": r["dofs"] / t, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "config": {"workload": "test/pore_pnp (pore.msh + pore.cfg) uniformly refined %d times: bounded sample of one monolithic PNP "
+                                   "Newton step on the host cores" % r["level"], "levels": r["level"], "dofs": r["dofs"]},
+            "cpu_baseline": {"value": r["dofs"] / t, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(r),
+                             "phases_s": r["phases_s"], "assembled_dofs_per_s": r["assembled_dofs_per_s"], "spmv_gbs": r["spmv_gbs"],
+                             "single_core": {"value": one["value"], "phases_s": one["phases_s"], "assembled_dofs_per_s": one["assembled_dofs_per_s"],
+                                             "spmv_gbs": one["spmv_gbs"]}},
             "e2e": {"value": r["dofs"] / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -336,6 +366,7 @@ def run_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     c.profile_spmv(True)
     l0 = c.launch_count()
+    c.profile_bytes(reset=True)
     barrier()
     c.profiler_range(True)
     c.timer_start()
@@ -346,6 +377,7 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     wall = time.perf_counter() - t0
     launches = c.launch_count() - l0
+    step_bytes = c.profile_bytes()   # algorithmic bytes of every launch of the timed region, by kernel class (this rank)
     n_spmv, spmv_ms = c.profile_spmv_get()
     c.profile_spmv(False)
     clocks = sampler.stop() if sampler else None
@@ -374,6 +406,9 @@ def run_gpu(args, rank, world, local_rank):
     tmax = torch.tensor([ms_dev / 1e3, wall, wall_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sb = torch.tensor([step_bytes[k] for k in sorted(step_bytes)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sb)
+        step_bytes = dict(zip(sorted(step_bytes), [float(v) for v in sb.tolist()]))
     sec_dev, wall, wall_e2e = [float(v) for v in tmax.tolist()]
     sec_step = max(sec_dev, 0.0) / args.steps
     if rank != 0:
@@ -393,7 +428,13 @@ def run_gpu(args, rank, world, local_rank):
     spmv_avg_s = spmv_ms / 1e3 / max(n_spmv, 1)
     achieved = spmv_bytes / spmv_avg_s / 1e9
     asm_s = float(np.mean([x.seconds_assembly for x in stats]))
-    cpu = cpu_newton_step(args.cpu_level) if not args.no_cpu else None
+    cpu = None
+    if not args.no_cpu:  # bounded CPU sample on all host cores (and the single-core phases beside it)
+        from oracle import binding as ora
+        nthr = args.cpu_threads if args.cpu_threads > 0 else ora.max_threads()
+        lvl = args.cpu_level if args.cpu_level >= 0 else 5
+        cpu = cpu_newton_step(lvl, nthr, krylov_iters=max(1, int(r.linear_iterations)))
+        cpu1 = cpu_newton_step(lvl, 1, krylov_iters=1) if nthr > 1 else cpu
     line = {
         "metric": METRIC, "value": gdof / sec_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True,
@@ -424,11 +465,18 @@ def run_gpu(args, rank, world, local_rank):
                      "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k_star_op<7,0,0> at k = 7 "
                                        "(profiles/hot_kernels_full_r01d_summary.txt); algorithmic bytes of that epilogue: 22.22e9",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,  # launch-weighted mean over the epilogue kinds
-                     "avg_launch_ms": spmv_avg_s * 1e3},
+                     "avg_launch_ms": spmv_avg_s * 1e3,
+                     # the WHOLE step: algorithmic bytes of every kernel launched in the timed region (all ranks), by class,
+                     # over the step time -- against the measured copy bandwidth and the nominal 8 TB/s of the north star
+                     "step": {"bytes_per_step": sum(step_bytes.values()) / args.steps,
+                              "by_class_gb": {k: v / args.steps / 1e9 for k, v in step_bytes.items()},
+                              "achieved": sum(step_bytes.values()) / args.steps / sec_step / 1e9 / world, "unit": "GB/s per GPU",
+                              "frac": sum(step_bytes.values()) / args.steps / sec_step / 1e9 / world / peak,
+                              "frac_of_8000": sum(step_bytes.values()) / args.steps / sec_step / 1e9 / world / 8000.0}},
         "cpu_baseline": None if cpu is None else {
-            "value": cpu["value"], "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "oracle (CPU restatement), pore mesh refined %d times (%d dofs), one Newton step: FD Jacobian + "
-                      "BiCGSTAB/SSOR(1) (%d its) + line search, %.1f s" % (cpu["level"], cpu["dofs"], cpu["lin_its"], cpu["seconds"])},
+            "value": cpu["value"], "unit": UNIT, "cores": cpu["threads"], "kind": "port", "sample": cpu_sample_text(cpu),
+            "phases_s": cpu["phases_s"], "assembled_dofs_per_s": cpu["assembled_dofs_per_s"], "spmv_gbs": cpu["spmv_gbs"],
+            "single_core_phases_s": cpu1["phases_s"]},
         "e2e": {"value": gdof / (wall_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 8 * ndof * world,
                 "d2h_bytes_per_step": 8 * ndof * world},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -445,7 +493,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--levels", type=int, default=7, help="uniform refinements of pore.msh (7 -> 141 M dofs)")
     ap.add_argument("--coarse-level", type=int, default=3)
-    ap.add_argument("--cpu-level", type=int, default=0)
+    ap.add_argument("--cpu-level", type=int, default=-1, help="refinement level of the CPU arm (default: 5 -> 8.84 M dofs, BASELINE.md "
+                    "section 4; --impl reference with more than 8 steps in all: 4, so that the run ends within a few minutes)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0: all cores)")
     ap.add_argument("--prec-steps", type=int, default=2)
     ap.add_argument("--jac", choices=["analytic", "fd"], default="analytic")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")

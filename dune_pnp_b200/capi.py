@@ -135,6 +135,11 @@ class Context:
         self._ck(lib().pnp_profile_spmv_get(self._h, n, ms))
         return list(n), list(ms)
 
+    def profile_bytes(self, reset=False):
+        out = (C.c_double * 6)()
+        self._ck(lib().pnp_profile_bytes(self._h, int(reset), out))
+        return dict(zip(("spmv_fine", "spmv_coarse", "assembly", "blas1", "transfer", "dense"), list(out)))
+
     def profiler_range(self, start):
         self._ck(lib().pnp_profiler_range(self._h, int(start)))
 

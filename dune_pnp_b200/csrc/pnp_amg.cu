@@ -489,7 +489,7 @@ void level_op(Ctx& c, const Amg& A, const Level& l, const double* x, const doubl
   const bool fine = &l == A.L[0].get();
   if (A.distributed) halo_exchange(*l.lc, const_cast<double*>(x), A.F); // ghost columns of the iterate
   if (fine) c.prof_mark(EPI == EPI_RESIDUAL ? 1 : 2);
-  launch_star_op_auto<EPI, 0>(c, A.NP, a);
+  launch_star_op_auto<EPI, 0>(c, A.NP, a, fine);
   if (fine) c.prof_mark();
 }
 
@@ -684,6 +684,7 @@ const double* level_values(Ctx& c, Amg& A, int li, const double* uf, int comp0) 
   if (n.redisc) {
     if (A.F == 1) KL(c, k_inject<1>, l.nv, l.agg.p, l.par1.p, l.nv, uf, n.u.d.p);
     else KL(c, k_inject<3>, l.nv, l.agg.p, l.par1.p, l.nv, uf, n.u.d.p);
+    c.acct(Ctx::ACC_TRANSFER, 8.0 * l.nv + 16.0 * A.F * n.nv);
     Operator op = c.last_op; op.aux0 = op.aux1 = -1;
     assemble_jacobian_on(c, StarView{n.rp, n.col, n.xy_own.p, n.dmask_own.p, n.nv}, n.nslots, op, n.u.d.p, n.vals_own.p,
                          c.last_mode, c.last_eps);
@@ -694,6 +695,7 @@ const double* level_values(Ctx& c, Amg& A, int li, const double* uf, int comp0) 
     KL(c, k_galerkin<1>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, l.dm, l.col, l.rp, comp0);
   else
     KL(c, k_galerkin<7>, n.nslots, l.seg_ptr.p, l.seg_items.p, l.seg_w.p, n.nslots, l.vals, l.nslots, n.vals_own.p, l.dm, l.col, l.rp, comp0);
+  c.acct(Ctx::ACC_ASSEMBLY, 8.0 * A.NP * ((double)l.nslots + (double)n.nslots) + 5.0 * (double)l.seg_items.n + 4.0 * (double)n.nslots);
   return nullptr;
 }
 
@@ -726,17 +728,19 @@ void numeric(Ctx& c, Amg& A, int comp0) {
       const int nvf_all = (int)l.lc->nv;
       if (A.F == 1) KL(c, k_inject<1>, nvf_all, l.agg.p, l.par1.p, nvf_all, uf, n.u.d.p);
       else KL(c, k_inject<3>, nvf_all, l.agg.p, l.par1.p, nvf_all, uf, n.u.d.p);
+      c.acct(Ctx::ACC_TRANSFER, 8.0 * nvf_all + 16.0 * A.F * n.nv);
       Operator op = c.last_op; op.aux0 = op.aux1 = -1;
       n.Amat.op = op.op;
       n.lc->launches = 0;
       assemble_jacobian(*n.lc, op, n.u, n.Amat, c.last_mode, c.last_eps); // (exchanges the ghost part of u first)
-      c.launches += n.lc->launches;
+      c.absorb(*n.lc);
       uf = n.u.d.p;
     }
     for (size_t li = 0; li < A.L.size(); li++) {
       Level& l = *A.L[li];
       if (A.NP == 1) KL(c, k_dinv<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
       else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
+      c.acct(Ctx::ACC_ASSEMBLY, (4.0 + 8.0 * A.NP + (A.NP == 7 ? 72.0 : 8.0)) * l.nv);
     }
     if (c.mg_replica) replica_setup(c, A); else dense_factor_global(c, A);
     if (A.smoother == 1) gershgorin_bounds(c, A);
@@ -748,6 +752,7 @@ void numeric(Ctx& c, Amg& A, int comp0) {
     if (li + 1 < A.L.size()) uf = level_values(c, A, (int)li, uf, comp0);
     if (A.NP == 1) KL(c, k_dinv<1>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
     else KL(c, k_dinv<7>, l.nv, l.rp, l.vals, l.nslots, l.nv, l.dinv.p);
+    c.acct(Ctx::ACC_ASSEMBLY, (4.0 + 8.0 * A.NP + (A.NP == 7 ? 72.0 : 8.0)) * l.nv);
   }
   A.dense_n = 0;
   if ((long)A.F * A.L.back()->nv <= A.dense_max) dense_factor(c, A); // (a one-level hierarchy is a direct solve)
@@ -798,6 +803,7 @@ void dense_factor(Ctx& c, Amg& A) {
   PNP_CUSOLVER(cusolverDnDgetrf_bufferSize(A.cus, (int)n, (int)n, A.dense.p, (int)n, &lwork));
   if (A.dense_work.n < (size_t)lwork) A.dense_work.alloc(lwork);
   PNP_CUSOLVER(cusolverDnDgetrf(A.cus, (int)n, (int)n, A.dense.p, (int)n, A.dense_work.p, A.dense_piv.p, A.dense_info.p));
+  c.acct(Ctx::ACC_DENSE, 24.0 * (double)n * (double)n); // zero fill + factor in place (read and write)
   int info = 0;
   A.dense_info.download(&info, 1, c.stream);
   PNP_REQUIRE(info == 0, PNP_E_BREAKDOWN, "multigrid: coarsest-level matrix is singular (LU info " + std::to_string(info) + ")");
@@ -806,7 +812,7 @@ void dense_solve(Ctx& c, Amg& A, Level& l) { // l.x = A^-1 l.b
   const long n = A.dense_n;
   PNP_CUDA(cudaMemcpyAsync(l.x.p, l.b.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
   PNP_CUSOLVER(cusolverDnDgetrs(A.cus, CUBLAS_OP_N, (int)n, 1, A.dense.p, (int)n, A.dense_piv.p, l.x.p, (int)n, A.dense_info.p));
-  c.launches += 2;
+  c.launches += 2; c.acct(Ctx::ACC_DENSE, 8.0 * (double)n * (double)n);
 }
 
 // coarsest level of the distributed hierarchy: every rank contributes its owned rows, the matrix is summed over the
@@ -892,7 +898,7 @@ void replica_setup(Ctx& c, Amg& A) {
   ro["amg_dense_max"] = A.dense_max; ro["amg_coarse_sweeps"] = A.coarse_sweeps; ro["amg_smoother"] = A.smoother;
   ro["amg_cheb_ratio"] = A.cheb_ratio; ro["amg_pre_steps"] = A.pre_steps; ro["amg_post_steps"] = A.post_steps;
   amg_setup(rc, *A.rep_solver, A.rep_A);
-  c.launches += rc.launches;
+  c.absorb(rc);
 }
 void replica_solve(Ctx& c, Amg& A, Level& l, int nu) {
   Ctx& rc = *c.mg_replica;
@@ -907,12 +913,13 @@ void replica_solve(Ctx& c, Amg& A, Level& l, int nu) {
   const int nloc = (int)l.lc->nv; // owned and ghost vertices: no halo exchange needed afterwards
   if (A.F == 1) KL(c, k_from_global<1>, nloc, A.rep_x.p, c.mg_gid.p, nloc, l.x.p);
   else KL(c, k_from_global<3>, nloc, A.rep_x.p, c.mg_gid.p, nloc, l.x.p);
-  c.launches += rc.launches + 2;
+  c.absorb(rc); c.launches += 2;
 }
 
 void jacobi0(Ctx& c, Amg& A, Level& l, double omega, double* dvec) {
   if (A.F == 1) KL(c, k_jacobi0<1>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
   else KL(c, k_jacobi0<3>, l.nv, l.dinv.p, l.b.p, omega, l.x.p, l.nv, dvec);
+  c.acct(Ctx::ACC_TRANSFER, ((A.NP == 7 ? 72.0 : 8.0) + 16.0 * A.F + (dvec ? 8.0 * A.F : 0.0)) * l.nv);
 }
 
 // `steps` smoothing steps on level l for A x = b; zero: x starts from 0.  Result in l.x.
@@ -965,9 +972,11 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   if (A.distributed) halo_exchange(*l.lc, l.r.p, A.F); // children of an owned coarse vertex may be ghosts here
   if (A.F == 1) KL(c, k_restrict<1>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
   else KL(c, k_restrict<3>, nx.nv, l.agg_ptr.p, l.agg_mem.p, l.par1.p, nx.nv, l.r.p, nx.b.p);
+  c.acct(Ctx::ACC_TRANSFER, (8.0 * A.F + 4.0) * l.nv + 4.0 * (double)l.agg_mem.n + (8.0 * A.F + 4.0) * nx.nv);
   if (nx.dm) { // re-discretised coarse levels carry their own Dirichlet rows: no residual into them
     if (A.F == 1) KL(c, k_mask_dirichlet<1>, nx.nv, nx.b.p, nx.dm, nx.nv, comp0);
     else KL(c, k_mask_dirichlet<3>, nx.nv, nx.b.p, nx.dm, nx.nv, comp0);
+    c.acct(Ctx::ACC_TRANSFER, 1.0 * nx.nv);
   }
   const int visits = li < A.wlevels ? A.gamma : 1;
   for (int g = 0; g < visits; g++) cycle(c, A, li + 1, nu, comp0, g == 0);
@@ -975,6 +984,7 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   const unsigned char* dm = l.dm; // constrained dofs of this level receive no correction
   if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
   else KL(c, k_prolong<3>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
+  c.acct(Ctx::ACC_TRANSFER, (16.0 * A.F + 9.0) * l.nv + 8.0 * A.F * nx.nv);
   smooth(c, A, l, nu_post, false);
 }
 
@@ -1084,7 +1094,7 @@ void amg_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y) {
     if (swaps & 1) l0.x2.p = y; else l0.x.p = y;
     cycle(c, A, 0, nu, A.comp0, true);
     double* result = l0.x.p;
-    if (result != y) PNP_CUDA(cudaMemcpyAsync(y, result, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    if (result != y) { PNP_CUDA(cudaMemcpyAsync(y, result, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream)); c.acct(Ctx::ACC_BLAS1, 16.0 * n); }
     return;
   }
   PNP_CUDA(cudaMemcpyAsync(l0.b.p, d, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));

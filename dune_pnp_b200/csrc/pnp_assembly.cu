@@ -63,6 +63,8 @@ void launch_jac(Ctx& c, const StarView& M, const Operator& op, const double* u, 
   const int grid = grid_for(M.nv, JAC_CHUNK, c.sm_count * 16);
   k_jacobian<OP, MODE><<<grid, JAC_CHUNK, smem, c.stream>>>(M, P, u, a0, a1, eps, op.comp0, vals, stride);
   PNP_CHECK_LAUNCH(); c.launches++;
+  // ring (4 B/slot), row pointer + coordinates + Dirichlet mask + state (+ coefficient fields) per vertex, NP planes written
+  c.acct(Ctx::ACC_ASSEMBLY, (4.0 + 8.0 * OpTraits<OP>::NPLANES) * (double)stride + (21.0 + 8.0 * OpTraits<OP>::F + 8.0 * OpTraits<OP>::NAUX) * (double)M.nv);
 }
 template <int MODE>
 void dispatch_jac(Ctx& c, const StarView& M, const Operator& op, const double* u, const double* a0, const double* a1,
@@ -161,6 +163,7 @@ void assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
     default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
   }
   PNP_CHECK_LAUNCH(); c.launches++;
+  c.acct(Ctx::ACC_ASSEMBLY, 4.0 * (double)c.nslots + (21.0 + 16.0 * F + 8.0 * (op.op == OP_POISSON ? 2 : (op.op == OP_DIFFUSION ? 1 : 0))) * (double)c.n_own);
   // doAlphaBoundary is false for the diffusion and mass operators (diffusion_operator.hh:34)
   if ((op.op == OP_PB || op.op == OP_POISSON || op.op == OP_PNP) && c.n_bv > 0) {
     // Poisson is constructed with the PB BCType (component 0): instationary_pnp_from_pb_md.hh:343-344

@@ -166,6 +166,11 @@ pnp_status pnp_profile_spmv_get(pnp_ctx* ctx, long* launches, double* total_ms) 
   }
   API_END
 }
+pnp_status pnp_profile_bytes(pnp_ctx* ctx, int reset, double* out6) {
+  API_BEGIN(ctx)
+  for (int k = 0; k < Ctx::ACC_N; k++) { if (out6) out6[k] = c.alg_bytes[k]; if (reset) c.alg_bytes[k] = 0; }
+  API_END
+}
 pnp_status pnp_profiler_range(pnp_ctx* ctx, int start) {
   API_BEGIN(ctx)
   PNP_CUDA(cudaStreamSynchronize(c.stream));

@@ -179,6 +179,16 @@ struct Ctx {
   HostParams params;
   bool constraints_built = false;
   long launches = 0;                   // kernels launched (bench.py reports gpu_launches)
+  // ALGORITHMIC bytes moved since the last reset, by kernel class (bench.py's roofline.step): compulsory traffic of every
+  // launch -- each array a kernel must read or write counted once (DESIGN.md section 3 lists the per-kernel figures)
+  enum { ACC_SPMV_FINE = 0, ACC_SPMV_COARSE = 1, ACC_ASSEMBLY = 2, ACC_BLAS1 = 3, ACC_TRANSFER = 4, ACC_DENSE = 5, ACC_N = 6 };
+  double alg_bytes[ACC_N] = {0, 0, 0, 0, 0, 0};
+  void acct(int cls, double bytes) { alg_bytes[cls] += bytes; }
+  // a level context's (child's) launches and bytes are the parent's
+  void absorb(Ctx& child) {
+    launches += child.launches; child.launches = 0;
+    for (int k = 0; k < ACC_N; k++) { alg_bytes[k] += child.alg_bytes[k]; child.alg_bytes[k] = 0; }
+  }
   // optional CUDA-event profile of the fine-level SpMV launches (bench.py's roofline leg)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;

@@ -174,7 +174,7 @@ double vec_dot(Ctx& c, const double* x, const double* y, long n) {
   ensure_red(c);
   const int g = red_grid(c, n);
   k_dot<<<g, RED_BLOCK, 0, c.stream>>>(x, y, n, c.red_partial.p);
-  PNP_CHECK_LAUNCH(); c.launches++;
+  PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, (x == y ? 8.0 : 16.0) * n);
   double d;
   finish_reduce(c, g, 1, &d);
   return d;
@@ -182,12 +182,13 @@ double vec_dot(Ctx& c, const double* x, const double* y, long n) {
 double vec_norm(Ctx& c, const double* x, long n) { return std::sqrt(vec_dot(c, x, x, n)); }
 void vec_axpy(Ctx& c, double a, const double* x, double* y, long n) {
   k_axpy<<<grid_for(n, 256), 256, 0, c.stream>>>(a, x, y, n);
-  PNP_CHECK_LAUNCH(); c.launches++;
+  PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 24.0 * n);
 }
 void vec_copy(Ctx& c, const double* x, double* y, long n) {
   PNP_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  c.acct(Ctx::ACC_BLAS1, 16.0 * n);
 }
-void vec_zero(Ctx& c, double* x, long n) { PNP_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), c.stream)); }
+void vec_zero(Ctx& c, double* x, long n) { PNP_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), c.stream)); c.acct(Ctx::ACC_BLAS1, 8.0 * n); }
 
 // ---- preconditioner dispatch ----------------------------------------------------------------
 void amg_setup(Ctx&, Solver&, const Matrix&);                        // pnp_amg.cu
@@ -220,7 +221,7 @@ void prec_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double* y, 
     case PNP_PREC_NONE: vec_copy(c, d, y, n); break; // Richardson: y = d
     case PNP_PREC_JACOBI:
       k_diag_apply<0><<<grid_for(n, RED_BLOCK), RED_BLOCK, 0, c.stream>>>(S.dinv.p, d, y, n, nullptr);
-      PNP_CHECK_LAUNCH(); c.launches++;
+      PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 24.0 * n);
       break;
     case PNP_PREC_SSOR: ssor_apply(c, S, A, d, y); break;
     case PNP_PREC_ILU0: ilu0_apply(c, S, A, d, y); break;
@@ -246,7 +247,7 @@ LinResult bicgstab(Ctx& c, Solver& S, const Matrix& A, double* x, double* r, lon
   // r = b - A x
   spmv(c, A, x, t);
   k_sub_norm<<<g, RED_BLOCK, 0, c.stream>>>(r, t, r, n, c.red_partial.p);
-  PNP_CHECK_LAUNCH(); c.launches++;
+  PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 24.0 * n);
   finish_reduce(c, g, 1, red);
   vec_copy(c, r, rt, n);
   vec_zero(c, p, n); vec_zero(c, v, n);
@@ -263,7 +264,7 @@ LinResult bicgstab(Ctx& c, Solver& S, const Matrix& A, double* x, double* r, lon
     else {
       beta = (rho_new / rho) * (alpha / omega);
       k_update_p<<<grid_for(n, 256), 256, 0, c.stream>>>(beta, omega, r, v, p, n);
-      PNP_CHECK_LAUNCH(); c.launches++;
+      PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 32.0 * n);
     }
     prec_apply(c, S, A, p, y, n);
     spmv_dots(c, A, y, v, 1, rt, red); // v = A y ; h = (rt, v)
@@ -271,7 +272,7 @@ LinResult bicgstab(Ctx& c, Solver& S, const Matrix& A, double* x, double* r, lon
     if (std::fabs(h) < 1e-80 || !std::isfinite(h)) return finish(res, it, norm, norm0, false, PNP_E_BREAKDOWN);
     alpha = rho_new / h;
     k_update_xr<<<g, RED_BLOCK, 0, c.stream>>>(alpha, y, v, x, r, rt, n, c.red_partial.p);
-    PNP_CHECK_LAUNCH(); c.launches++;
+    PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 56.0 * n);
     finish_reduce(c, g, 2, red);
     norm = std::sqrt(red[0]);
     if (S.verbosity > 1) std::printf("  BiCGSTAB %5.1f  %.6e\n", it, norm);
@@ -281,7 +282,7 @@ LinResult bicgstab(Ctx& c, Solver& S, const Matrix& A, double* x, double* r, lon
     spmv_dots(c, A, y, t, 2, r, red); // t = A y ; (t, r), (t, t)
     omega = red[0] / red[1];
     k_update_xr<<<g, RED_BLOCK, 0, c.stream>>>(omega, y, t, x, r, rt, n, c.red_partial.p);
-    PNP_CHECK_LAUNCH(); c.launches++;
+    PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 56.0 * n);
     finish_reduce(c, g, 2, red);
     rho = rho_new;
     norm = std::sqrt(red[0]);
@@ -301,7 +302,7 @@ LinResult cg(Ctx& c, Solver& S, const Matrix& A, double* x, double* b, long n, d
   const int g = red_grid(c, n);
   spmv(c, A, x, q);
   k_sub_norm<<<g, RED_BLOCK, 0, c.stream>>>(b, q, b, n, c.red_partial.p);
-  PNP_CHECK_LAUNCH(); c.launches++;
+  PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 24.0 * n);
   finish_reduce(c, g, 1, red);
   const double def0 = std::sqrt(red[0]);
   double def = def0;
@@ -314,7 +315,7 @@ LinResult cg(Ctx& c, Solver& S, const Matrix& A, double* x, double* b, long n, d
     spmv_dots(c, A, p, q, 1, p, red); // q = A p ; alpha = (p, q)
     const double lambda = rholast / red[0];
     k_update_xr<<<g, RED_BLOCK, 0, c.stream>>>(lambda, p, q, x, b, p, n, c.red_partial.p);
-    PNP_CHECK_LAUNCH(); c.launches++;
+    PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 56.0 * n);
     finish_reduce(c, g, 2, red);
     def = std::sqrt(red[0]);
     if (S.verbosity > 1) std::printf("  CG %5d  %.6e\n", i, def);
@@ -324,7 +325,7 @@ LinResult cg(Ctx& c, Solver& S, const Matrix& A, double* x, double* b, long n, d
     const double rho = vec_dot(c, q, b, n);
     const double beta = rho / rholast;
     k_xpby<<<grid_for(n, 256), 256, 0, c.stream>>>(beta, q, p, n);
-    PNP_CHECK_LAUNCH(); c.launches++;
+    PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 24.0 * n);
     rholast = rho;
   }
   return finish(res, S.maxit, def, def0, false, 0);

@@ -400,8 +400,20 @@ inline int launch_star_op_tma_inst(Ctx& c, const StarOpArgs& a) {
 }
 
 // launches the streaming or the plain-load kernel; returns the grid size (number of partial-sum blocks)
+// compulsory traffic of one star-op launch: NP value planes + column index per slot; row pointer, x read once and y
+// written per row; the epilogue's extra vectors (b; the dot operand; the Chebyshev direction read and written)
 template <int EPI, int NDOT>
-inline int launch_star_op_auto(Ctx& c, int nplanes, const StarOpArgs& a) {
+inline double star_op_bytes(int nplanes, const StarOpArgs& a) {
+  const double F = nplanes == 1 ? 1 : 3, nv = a.nv, ns = a.rp ? (double)a.stride : 0.0;
+  double b = (8.0 * nplanes + 4.0) * ns + (4.0 + 16.0 * F) * nv;
+  if (EPI != EPI_PLAIN) b += 8.0 * F * nv;
+  if (EPI == EPI_PLAIN && NDOT >= 1) b += 8.0 * F * nv;
+  if (EPI == EPI_CHEBYSHEV) b += 16.0 * F * nv;
+  return b;
+}
+template <int EPI, int NDOT>
+inline int launch_star_op_auto(Ctx& c, int nplanes, const StarOpArgs& a, bool fine = true) {
+  c.acct(fine ? Ctx::ACC_SPMV_FINE : Ctx::ACC_SPMV_COARSE, star_op_bytes<EPI, NDOT>(nplanes, a));
   if (EPI != EPI_CHEBYSHEV && star_op_tma_ok(c, a, EPI)) {
     constexpr int E = EPI == EPI_CHEBYSHEV ? EPI_PLAIN : EPI; // (never instantiated for Chebyshev)
     return nplanes == 1 ? launch_star_op_tma_inst<1, E, NDOT>(c, a) : launch_star_op_tma_inst<7, E, NDOT>(c, a);

@@ -63,6 +63,10 @@ long pnp_launch_count(pnp_ctx* ctx);
 pnp_status pnp_profile_spmv(pnp_ctx*, int enable);
 /* launches[3], total_ms[3]: by epilogue kind -- 0: y = A x (+ fused dots), 1: y = b - A x, 2: smoother step */
 pnp_status pnp_profile_spmv_get(pnp_ctx*, long* launches, double* total_ms);
+/* ALGORITHMIC bytes (compulsory traffic: every array a kernel must read or write, once) of all launches since the last
+ * reset, by kernel class: out6 = {fine-level SpMV, coarser-level SpMV, assembly (residual, Jacobian, coarse operators),
+ * vector updates / reductions / copies, grid transfers (restriction, prolongation, first smoothing step), dense coarse solve} */
+pnp_status pnp_profile_bytes(pnp_ctx*, int reset, double* out6);
 /* cudaProfilerStart/Stop: lets `ncu --profile-from-start off` see only the timed region */
 pnp_status pnp_profiler_range(pnp_ctx*, int start);
 pnp_status pnp_timer_start(pnp_ctx*);

@@ -183,15 +183,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-level", "2", "--cpu-threads", "2"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "newton_step_dofs_per_s" and line["unit"] == "DOF/s"
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
               "config", "cpu_baseline", "e2e"):
         assert k in line
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1 and line["value"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 2 and line["value"] > 0
+    # per-phase timers of the multi-core run and the single-core run beside it
+    for ph in ("jacobian_fd", "residual", "krylov_iteration", "spmv"):
+        assert cb["phases_s"][ph] > 0 and cb["single_core"]["phases_s"][ph] > 0
+    assert line["config"]["levels"] == 2 and line["config"]["dofs"] == 139959
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["dtype"] == "f64"
     # ranks other than 0 stay silent under torchrun
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")

@@ -85,6 +85,19 @@ def test_pore_without_dna_mesh_is_reproducible_and_faithful_to_the_geo():
     assert sorted(set(ph.tolist())) == [0, 1, 2, 3, 4, 5]
 
 
+@pytest.mark.parametrize("op", [ora.OP_PB, ora.OP_PNP])
+def test_multicore_assembly_is_bit_identical_to_the_sequential_one(op):
+    """The OpenMP variants of the CPU baseline (two phases, every dof sums its elements in ascending element order):
+    same bits as residual() / jacobian() for 1, 3 and 8 threads."""
+    m, p = case("pore", 1)
+    u = np.random.RandomState(4).uniform(0.01, 1.0, ora.nfields(op) * m.nv)
+    r0 = ora.residual(m, p, op, u)
+    _, _, v0 = ora.jacobian(m, p, op, u, mode=0)
+    for threads in (1, 3, 8):
+        r, v = ora.assembly_par(m, p, op, u, threads, 0)
+        assert np.array_equal(r, r0) and np.array_equal(v, v0)
+
+
 def test_config_reader(tmp_path):
     p = ora.Params.read(util.cfg_path("pore"))
     assert p.sys[0] == 7 and p.sys[1] == 1 and p.sys[4] == 3.1415 and p.sys[7] == 1e-9 and p.sys[8] == 1e-8
