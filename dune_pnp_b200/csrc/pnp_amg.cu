@@ -79,7 +79,6 @@ struct Amg {
   cusolverDnHandle_t cus = nullptr;
   DBuf<double> dense, dense_work;
   DBuf<int> dense_piv, dense_info;
-  ~Amg() { if (cus) cusolverDnDestroy(cus); }
   bool distributed = false; // levels are parts of a mesh hierarchy spread over the ranks (halo exchange per level)
   bool redisc = false;      // one GPU: the geometric levels are re-discretised (as the distributed levels are), not Galerkin products
   DBuf<double> grhs;        // replicated coarsest level: global right-hand side / solution
@@ -90,6 +89,17 @@ struct Amg {
   std::vector<std::unique_ptr<Level>> L;
   DBuf<unsigned char> tmp;
   void* temp(size_t bytes) { if (bytes > tmp.n) tmp.alloc(bytes); return tmp.p; }
+  // CUDA graph of the coarse correction (everything below the finest level of one cycle: ~80 small launches that are
+  // launch-latency bound, the more so the more GPUs share the mesh).  Captured at the second application, replayed after;
+  // the iterate pointers the smoothers swap are put back to their state at capture before every replay.
+  cudaGraphExec_t cg_exec = nullptr;
+  bool cg_failed = false;
+  int cg_calls = 0;
+  double cg_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<std::pair<double*, double*>> cg_before, cg_after;
+  long cg_launches = 0; double cg_bytes[Ctx::ACC_N] = {0, 0, 0, 0, 0, 0};
+  void cg_reset() { if (cg_exec) cudaGraphExecDestroy(cg_exec); cg_exec = nullptr; cg_calls = 0; }
+  ~Amg() { if (cg_exec) cudaGraphExecDestroy(cg_exec); if (cus) cusolverDnDestroy(cus); }
 };
 
 namespace {
@@ -947,6 +957,61 @@ void smooth(Ctx& c, Amg& A, Level& l, int steps, bool zero) {
   }
 }
 
+void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero);
+
+// The part of one cycle below the finest level (right-hand side in L[1]->b, result in L[1]->x), replayed from a CUDA graph
+void coarse_correction(Ctx& c, Amg& A, int nu, int comp0) {
+  auto direct = [&] {
+    const int visits = 0 < A.wlevels ? A.gamma : 1;
+    for (int g = 0; g < visits; g++) cycle(c, A, 1, nu, comp0, g == 0);
+  };
+  auto snapshot = [&](std::vector<std::pair<double*, double*>>& v) {
+    v.clear();
+    for (size_t li = 1; li < A.L.size(); li++) v.push_back({A.L[li]->x.p, A.L[li]->x2.p});
+  };
+  auto restore = [&](const std::vector<std::pair<double*, double*>>& v) {
+    for (size_t li = 1; li < A.L.size(); li++) { A.L[li]->x.p = v[li - 1].first; A.L[li]->x2.p = v[li - 1].second; }
+  };
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PNP_CUDA(cudaStreamIsCapturing(c.stream, &cap));
+  // (Chebyshev coefficients change with every numeric set-up; a replica's cycle runs inside its parent's capture)
+  if (!tune().graph || A.cg_failed || A.smoother != 0 || cap != cudaStreamCaptureStatusNone) { direct(); return; }
+  const double key[8] = {(double)nu, A.omega, (double)A.gamma, (double)A.wlevels, (double)A.pre_steps, (double)A.post_steps,
+                         (double)A.coarse_sweeps, (double)comp0 + 16.0 * A.dense_n};
+  if (A.cg_exec && std::memcmp(key, A.cg_key, sizeof key) != 0) A.cg_reset();
+  if (!A.cg_exec) {
+    if (A.cg_calls++ < 1) { direct(); return; } // first application: plain launches (libraries set up their work space)
+    std::memcpy(A.cg_key, key, sizeof key);
+    snapshot(A.cg_before);
+    const long l0 = c.launches;
+    double b0[Ctx::ACC_N];
+    for (int k = 0; k < Ctx::ACC_N; k++) b0[k] = c.alg_bytes[k];
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      try { direct(); } catch (const Error&) { ok = false; }
+      if (cudaStreamEndCapture(c.stream, &graph) != cudaSuccess || !graph) ok = false;
+    }
+    if (ok && cudaGraphInstantiate(&A.cg_exec, graph, 0) != cudaSuccess) { ok = false; A.cg_exec = nullptr; }
+    if (graph) cudaGraphDestroy(graph);
+    A.cg_launches = c.launches - l0; c.launches = l0;               // (nothing has run yet)
+    for (int k = 0; k < Ctx::ACC_N; k++) { A.cg_bytes[k] = c.alg_bytes[k] - b0[k]; c.alg_bytes[k] = b0[k]; }
+    snapshot(A.cg_after);
+    if (!ok) { // capture not possible here (a library call that cannot be captured): plain launches from now on
+      cudaGetLastError();
+      A.cg_failed = true; A.cg_exec = nullptr;
+      restore(A.cg_before);
+      direct();
+      return;
+    }
+  }
+  restore(A.cg_before);
+  PNP_CUDA(cudaGraphLaunch(A.cg_exec, c.stream));
+  restore(A.cg_after);
+  c.launches += A.cg_launches;
+  for (int k = 0; k < Ctx::ACC_N; k++) c.alg_bytes[k] += A.cg_bytes[k];
+}
+
 // one multigrid cycle on level li for A x = b (gamma = 1: V, 2: W); zero: x starts from 0.  Result in l.x
 void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
   Level& l = *A.L[li];
@@ -978,8 +1043,11 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
     else KL(c, k_mask_dirichlet<3>, nx.nv, nx.b.p, nx.dm, nx.nv, comp0);
     c.acct(Ctx::ACC_TRANSFER, 1.0 * nx.nv);
   }
-  const int visits = li < A.wlevels ? A.gamma : 1;
-  for (int g = 0; g < visits; g++) cycle(c, A, li + 1, nu, comp0, g == 0);
+  if (li == 0) coarse_correction(c, A, nu, comp0);
+  else {
+    const int visits = li < A.wlevels ? A.gamma : 1;
+    for (int g = 0; g < visits; g++) cycle(c, A, li + 1, nu, comp0, g == 0);
+  }
   if (A.distributed && !(li + 2 == (int)A.L.size() && A.dense_n > 0 && !c.mg_aggregated)) halo_exchange(*nx.lc, nx.x.p, A.F); // parents may be ghosts
   const unsigned char* dm = l.dm; // constrained dofs of this level receive no correction
   if (A.F == 1) KL(c, k_prolong<1>, l.nv, l.agg.p, l.par1.p, l.nv, nx.x.p, l.alpha, l.x.p, dm, comp0);
@@ -1003,7 +1071,7 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
   const double sym_key = S.opt("amg_geometric", 1) + 3.0 * S.opt("amg_dense_max", 4096) + 1e7 * S.opt("amg_alpha", 1.6);
   if (!A.symbolic || A.NP != M.nplanes || A.nv0 != c.n_own || A.nslots0 != c.nslots || A.redisc != want_redisc ||
       A.mg_epoch != c.mg_epoch || A.sym_key != sym_key) {
-    A.L.clear();
+    A.L.clear(); A.cg_reset(); A.cg_failed = false;
     A.NP = M.nplanes; A.F = M.nplanes == 1 ? 1 : 3;
     A.nv0 = c.n_own; A.nslots0 = c.nslots; A.mg_epoch = c.mg_epoch; A.sym_key = sym_key;
     auto l0 = std::make_unique<Level>();

@@ -68,6 +68,7 @@ struct Tune {
   int tma_stages = 2;     // ring depth of the streaming SpMV (2..3); two stages leave more of the SM's memory to L1
   int tma_lpr = 2;        // lanes per row in the streaming SpMV (1 or 2): 2 -> eight consumer warps per SM
   long tma_min_rows = -1; // smallest level the streaming SpMV serves (-1: two tiles per SM)
+  int graph = 1;          // the multigrid's coarse correction is replayed from a CUDA graph
 };
 inline Tune& tune() { static Tune t; return t; }
 

@@ -53,7 +53,8 @@ void pnp_ctx_destroy(pnp_ctx* ctx);
 const char* pnp_last_error(pnp_ctx* ctx);
 /* process-wide kernel tuning knobs (experiments, tests): "tma" (1: large levels run the bulk-copy streaming SpMV, 0: the
  * plain-load kernel everywhere), "tma_stages" (2..3), "tma_min_rows" (smallest level served by the streaming kernel, -1:
- * two tiles per SM) */
+ * two tiles per SM), "tma_lpr" (lanes per row, 1 or 2), "graph" (1: the multigrid's coarse correction is replayed from a
+ * CUDA graph) */
 pnp_status pnp_tune(const char* name, double value);
 /* number of CUDA kernels this context has launched so far */
 long pnp_launch_count(pnp_ctx* ctx);
