@@ -479,7 +479,7 @@ def run_gpu(args, rank, world, local_rank):
             "single_core_phases_s": cpu1["phases_s"]},
         "e2e": {"value": gdof / (wall_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 8 * ndof * world,
                 "d2h_bytes_per_step": 8 * ndof * world},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "coarse_correction_cuda_graph": int(c.solver_get(s, "amg_graph")),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

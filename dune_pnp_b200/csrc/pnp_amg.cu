@@ -1058,6 +1058,9 @@ void cycle(Ctx& c, Amg& A, int li, int nu, int comp0, bool zero) {
 
 } // namespace
 
+// 1: the coarse correction is replayed from a CUDA graph, -1: capture failed (plain launches), 0: not captured (yet)
+int amg_graph_state(const Solver& S) { return !S.amg ? 0 : (S.amg->cg_exec ? 1 : (S.amg->cg_failed ? -1 : 0)); }
+
 void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
   if (!S.amg) S.amg = std::make_shared<Amg>();
   Amg& A = *S.amg;

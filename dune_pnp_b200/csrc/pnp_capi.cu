@@ -7,6 +7,7 @@
 
 namespace pnp {
 int newton_apply(Ctx&, const Operator&, Vec&, Solver&, const pnp_newton_opts&, pnp_newton_result&);
+int amg_graph_state(const Solver&); // pnp_amg.cu
 LinResult slp_apply(Ctx&, const Operator&, Vec&, Solver&, double, int, double);
 int onestep_apply(Ctx&, int, const Operator&, const Operator&, Solver&, double, Vec&, Vec&, Vec&, double, int, double, LinResult*);
 namespace {
@@ -487,6 +488,7 @@ pnp_status pnp_solver_get(pnp_ctx* ctx, int s, const char* name, double* value) 
   const std::string n(name);
   if (n == "ssor_levels") *value = sweep_levels(c.solver(s), false);
   else if (n == "ilu0_levels") *value = sweep_levels(c.solver(s), true);
+  else if (n == "amg_graph") *value = amg_graph_state(c.solver(s));
   else PNP_REQUIRE(false, PNP_E_ARG, "unknown solver fact");
   API_END
 }

@@ -198,7 +198,8 @@ pnp_status pnp_solver_create(pnp_ctx*, int kind, int prec, int maxit, int prec_s
  * pnp_jacobian / Newton assembly of a PB, PNP or mass operator; 0 or any other matrix: Galerkin products) */
 pnp_status pnp_solver_set_option(pnp_ctx*, int solver, const char* name, double value);
 /* read-back of solver facts, by name: "ssor_levels" / "ilu0_levels" (number of levels of the level-scheduled sweep that
- * reproduces SeqSSOR / SeqILU0 in the reference's row order; 0 before the first use) */
+ * reproduces SeqSSOR / SeqILU0 in the reference's row order; 0 before the first use), "amg_graph" (1: the multigrid's coarse
+ * correction runs from a CUDA graph, -1: capture was not possible, 0: not captured yet) */
 pnp_status pnp_solver_get(pnp_ctx*, int solver, const char* name, double* value);
 /* one application of the solver's preconditioner, v = M^-1 d, as ISTL's Preconditioner::pre/apply/post on the matrix
  * (SeqSSOR / SeqILU0 / SeqJac / AMG / Richardson).  d and v are distinct vectors of the matrix' field count. */

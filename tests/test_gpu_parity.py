@@ -356,6 +356,7 @@ def test_multigrid_preconditioner(op, geometric):
     res = c.solve(s, A, z, r, 1e-8)
     assert res.converged
     assert res.iterations <= (12 if geometric else 40)
+    assert c.solver_get(s, "amg_graph") == 1   # the coarse correction was captured and replayed from a CUDA graph
     rp, col = c.pattern(h, F)
     val = c.matrix_values(h, A, len(col))
     assert np.linalg.norm(b - ora.spmv(rp, col, val, c.download(z, F))) <= 2e-8 * np.linalg.norm(b)
