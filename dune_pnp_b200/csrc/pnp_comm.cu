@@ -50,8 +50,13 @@ void comm_init(Ctx& c, int rank, int world, const char* unique_id128) {
   PNP_NCCL(ncclCommInitRank(&comm, world, id, rank));
   c.nccl = comm; c.owns_comm = true;
 }
+// Tear-down of the communicator a context created.  ncclCommDestroy is collective in effect (it waits for the peers'
+// side of the communicator), and contexts are destroyed whenever their owner lets go of them -- a Python finaliser at
+// interpreter exit, in any order across ranks -- where that wait never ends (measured: both ranks of a finished 2-GPU
+// run sat in it until the launcher was killed).  The stream has been synchronised, nothing is in flight:
+// ncclCommAbort frees the local resources without waiting for anyone.
 void comm_destroy(Ctx& c) {
-  if (c.nccl && c.owns_comm) ncclCommDestroy((ncclComm_t)c.nccl);
+  if (c.nccl && c.owns_comm) ncclCommAbort((ncclComm_t)c.nccl);
   c.nccl = nullptr; c.owns_comm = false;
 }
 
