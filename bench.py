@@ -482,8 +482,6 @@ def run_gpu(args, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks, "coarse_correction_cuda_graph": int(c.solver_get(s, "amg_graph")),
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -518,6 +516,16 @@ def main():
         run_reference(args, rank)
     else:
         run_gpu(args, rank, world, local_rank)
+        if world > 1:
+            # every rank leaves together and at once: the line is out; finalisers of NCCL-backed objects (torch's process
+            # group, the library's communicator, CUDA graphs holding NCCL nodes) have no defined order at interpreter exit
+            import torch.distributed as dist
+            try:
+                dist.barrier()
+            except Exception:
+                pass
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
 
 
 if __name__ == "__main__":

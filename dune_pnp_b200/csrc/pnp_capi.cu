@@ -84,8 +84,12 @@ void pnp_ctx_destroy(pnp_ctx* ctx) {
     if (p.mg_replica == &c) { p.mg_replica = nullptr; p.mg_gid.release(); p.mg_nglobal = 0; }
     p.mg_epoch++;
   }
-  for (Ctx* k : c.children) { k->parent = nullptr; k->stream = nullptr; k->nccl = nullptr; }
   if (c.stream) cudaStreamSynchronize(c.stream);
+  // CUDA graphs that captured NCCL operations must be gone before their communicator is torn down (the tear-down waits
+  // for them otherwise: a finished multi-GPU run never exited): drop every solver -- this context's and its children's,
+  // whose multigrid objects may hold such graphs -- first
+  c.solvers.clear();
+  for (Ctx* k : c.children) { k->solvers.clear(); k->parent = nullptr; k->stream = nullptr; k->nccl = nullptr; }
   if (c.h_red) cudaFreeHost(c.h_red);
   for (cudaEvent_t e : c.prof_ev) cudaEventDestroy(e);
   if (c.tm0) cudaEventDestroy(c.tm0);

@@ -128,12 +128,25 @@ def main():
     uo = owned(vu, 3)
     for k in range(3):
         e = torch.tensor([np.sum((uo[k] - u_g.reshape(3, -1)[k, own]) ** 2)], device="cuda"); dist.all_reduce(e)
-        assert np.sqrt(e.item()) <= 1e-8 * np.linalg.norm(u_g.reshape(3, -1)[k]), "Newton field %d" % k
+        # (two runs that both stop at pore.cfg's reduction 1e-9 agree to ~10x that in the defect: 1e-7 in the fields)
+        assert np.sqrt(e.item()) <= 1e-7 * np.linalg.norm(u_g.reshape(3, -1)[k]), "Newton field %d" % k
     print("NCCL_WORKER_OK rank %d: %d owned + %d ghost vertices, Newton %d its, linear %s" % (
         rank, n_own, nv - n_own, rg.iterations, list(rg.linear_iterations_history[:rg.n_history])), flush=True)
-    del children
+    dist.barrier()
+    sys.stdout.flush()
+    # orderly tear-down: solvers (CUDA graphs with NCCL nodes) and contexts before the communicators
+    for ch in children:
+        ch.close()
+    root.close()
     dist.destroy_process_group()
+    os._exit(0)
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # a failing rank must not leave its peers waiting in a collective: die at once, loudly
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)

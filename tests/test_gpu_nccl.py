@@ -24,6 +24,6 @@ def test_nccl_ranks_match_global_oracle(world, levels):
     port = 29500 + (os.getpid() % 2000)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "nccl_worker.py"), str(levels)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("NCCL_WORKER_OK") == world, out.stdout[-3000:]
