@@ -848,3 +848,153 @@ def test_errors_of_the_solver_and_time_stepping_entry_points():
     s1 = c.solver(capi.SOLVER_CG, capi.PREC_NONE, 2)
     res = c.solve(s1, A, c.vec(1), c.vec(1, b), 1e-14)
     assert not res.converged and res.iterations == 2
+
+
+# ---- boundary completions: VTK vertex data, externally assembled matrices, caller-side vertex numbering ----
+def _parse_vtu_appended(path):
+    """Arrays of a binaryappended .vtu: {name: numpy array} (the header gives type and offset, the blob <uint32 n><raw>)."""
+    import re
+    raw = open(path, "rb").read()
+    head, tail = raw.split(b'<AppendedData encoding="raw">\n_', 1)
+    out = {}
+    for m in re.finditer(rb'<DataArray type="(\w+)" Name="(\w+)" NumberOfComponents="(\d+)" format="appended" offset="(\d+)"', head):
+        ty, name, off = m.group(1).decode(), m.group(2).decode(), int(m.group(4))
+        n = int(np.frombuffer(tail[off:off + 4], dtype=np.uint32)[0])
+        dt = {"Float32": np.float32, "Int32": np.int32, "UInt8": np.uint8}[ty]
+        out[name] = np.frombuffer(tail[off + 4:off + 4 + n], dtype=dt)
+    return out
+
+
+def test_write_vtk_matches_oracle(tmp_path):
+    """Dune::VTKWriter vertex data (instationary_pnp_from_pb_md.hh:337-340, :440): same file as the oracle's writer, text
+    for text in ascii mode and byte for byte in binaryappended mode; the appended arrays decode to the fields (Float32)."""
+    c, m, p = make_ctx("cylinder", levels=1)
+    phi = np.cos(0.3 * m.x) * np.sin(0.2 * m.y); cp = 0.06 * np.exp(-phi); cm = 0.06 * np.exp(phi)
+    vecs = [c.vec(1, phi), c.vec(1, cp), c.vec(1, cm)]
+    names = ["phi", "cp", "cm"]
+    for ascii_ in (True, False):
+        g, o = str(tmp_path / ("gpu%d" % ascii_)), str(tmp_path / ("ora%d" % ascii_))
+        c.write_vtk(g, vecs, names, ascii=ascii_)
+        ora.write_vtk(m, o, [phi, cp, cm], names, ascii=ascii_)
+        assert open(g + ".vtu", "rb").read() == open(o + ".vtu", "rb").read()
+    arr = _parse_vtu_appended(str(tmp_path / "gpu0.vtu"))
+    assert np.array_equal(arr["phi"], phi.astype(np.float32)) and np.array_equal(arr["cm"], cm.astype(np.float32))
+    assert np.array_equal(arr["connectivity"].reshape(-1, 3), m.tri) and np.all(arr["types"] == 5)
+    assert np.array_equal(arr["Coordinates"].reshape(-1, 3)[:, 0], m.x.astype(np.float32))
+    assert np.array_equal(arr["offsets"], 3 * (np.arange(m.nT) + 1))
+
+
+@pytest.mark.parametrize("op,prec", [(ora.OP_PB, 2), (ora.OP_PNP, 3), (ora.OP_PNP, 4)])
+def test_solve_on_an_externally_assembled_matrix(op, prec):
+    """The ISTL-backend-level drop-in: ls.apply(A, z, r, red) on a matrix the CALLER assembled
+    (instationary_pnp_from_pb_md.hh:188-211; here the oracle's FD Jacobian in ISTLBCRSMatrixBackend<1,1> layout), imported
+    with pnp_matrix_set_csr and solved with SSOR(1) / ILU0 / multigrid-preconditioned BiCGSTAB."""
+    capi = _capi()
+    c, m, p = make_ctx("pore", levels=1)
+    F = ora.nfields(op)
+    rng = np.random.RandomState(8)
+    u = rng.uniform(-0.5, 0.5, F * m.nv)
+    if op == ora.OP_PNP:
+        u[m.nv:] = rng.uniform(0.02, 0.1, 2 * m.nv)
+    rp, col, val = ora.jacobian(m, p, op, u, mode=0)
+    h = c.operator(op, 0)
+    A = c.matrix(h)
+    c.matrix_set_csr(h, A, rp, col, val)
+    assert np.array_equal(c.matrix_values(h, A, len(col)), val)   # what went in comes out, entry for entry
+    x = rng.uniform(-1, 1, F * m.nv)
+    vx, vy = c.vec(F, x), c.vec(F)
+    c.spmv(A, vx, vy)
+    y_o = ora.spmv(rp, col, val, x)
+    assert rel_err(c.download(vy, F), y_o, ora.spmv(rp, col, np.abs(val), np.abs(x))) <= TOL
+    b = rng.uniform(-1, 1, F * m.nv); b[ora.dirichlet(m, p, F, 0)] = 0.0
+    s = c.solver(capi.SOLVER_BCGS, prec, 20000, 2 if prec == 4 else 1)
+    vz, vb = c.vec(F), c.vec(F, b)
+    res = c.solve(s, A, vz, vb, 1e-10)
+    assert res.converged
+    z = c.download(vz, F)
+    assert np.linalg.norm(b - ora.spmv(rp, col, val, z)) <= 2e-10 * np.linalg.norm(b)
+    if prec != 4:  # the reference's sequential preconditioners: same iteration counts as the CPU path
+        z_o, res_o = ora.linsolve(rp, col, val, b, 1e-10, 20000, ora.SOLVER_BCGS, prec)
+        assert abs(res.iterations - res_o["iterations"]) <= max(3, res_o["iterations"] // 10)
+    # a pattern that is not the operator's, or a value in a (c+, c-) block, is refused
+    with pytest.raises(capi.PnpError) as e:
+        c.matrix_set_csr(h, A, rp, np.roll(col, 1), val)
+    assert e.value.status == 8
+    if op == ora.OP_PNP:
+        bad = val.copy()
+        r0 = m.nv + int(np.where(~ora.dirichlet(m, p, 3, 0)[m.nv:2 * m.nv])[0][0])   # a free c+ row
+        k = rp[r0] + int(np.where(col[rp[r0]:rp[r0 + 1]] >= 2 * m.nv)[0][0])        # its first c- column
+        bad[k] = 1.0
+        with pytest.raises(capi.PnpError) as e:
+            c.matrix_set_csr(h, A, rp, col, bad)
+        assert e.value.status == 8 and "coupling" in str(e.value)
+
+
+def test_mesh_renumber_hook():
+    """dof_perm: after pnp_mesh_renumber the boundary speaks the caller's vertex numbering -- residual, pattern
+    and SSOR sweep order are those of the oracle on the permuted mesh."""
+    capi = _capi()
+    a = util.load_mesh_arrays("pore_small")
+    perm = np.random.RandomState(12).permutation(len(a["x"])).astype(np.int32)   # new index of vertex v
+    c = capi.Context(0)
+    c.mesh_read_gmsh(__import__("os").path.join(util.GOLDEN, "msh", "pore_small.msh"))
+    c.params_read(util.cfg_path("pore_small"))
+    c.mesh_renumber(perm)
+    c.mesh_finalize(True)
+    b = dict(a)
+    inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+    b["x"], b["y"] = a["x"][inv], a["y"][inv]
+    b["tri"], b["ba"], b["bb"] = perm[a["tri"]], perm[a["ba"]], perm[a["bb"]]
+    g = c.mesh_get()
+    for k in b:
+        assert np.array_equal(g[k], b[k]), k
+    m = ora.Mesh.from_arrays(**b); p = ora.Params.read(util.cfg_path("pore_small"))
+    u = np.random.RandomState(1).uniform(-1, 1, 3 * m.nv)
+    h = c.operator(capi.OP_PNP, 0)
+    vu, vr = c.vec(3, u), c.vec(3)
+    c.residual(h, vu, vr)
+    r_o, ab = ora.residual(m, p, ora.OP_PNP, u, want_abs=True)
+    assert rel_err(c.download(vr, 3), r_o, ab) <= TOL
+    rp, col = c.pattern(h, 3)
+    rp_o, col_o = ora.pattern(m, p, 3, 0)
+    assert np.array_equal(rp, rp_o) and np.array_equal(col, col_o)
+    A = c.matrix(h); c.jacobian(h, vu, A, capi.JAC_ANALYTIC, 0.0)
+    val = c.matrix_values(h, A, len(col))
+    d = np.random.RandomState(2).uniform(-1, 1, 3 * m.nv)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 100, 1)
+    vd, vv = c.vec(3, d), c.vec(3)
+    c.precond_apply(s, A, vd, vv)
+    v_o = ora.prec_apply(rp, col, val, d, ora.PREC_SSOR, 1)
+    assert np.linalg.norm(c.download(vv, 3) - v_o) <= 1e-12 * np.linalg.norm(v_o)
+    with pytest.raises(capi.PnpError) as e:
+        c.mesh_renumber(np.zeros(len(perm), dtype=np.int32))
+    assert e.value.status == 8
+
+
+@pytest.mark.parametrize("strategy,benign", [(0, False), (2, False), (1, True), (0, True)])
+def test_newton_line_search_strategies(strategy, benign):
+    """Newton::setLineSearchStrategy: hackbuschReuskenAcceptBest (0, what the drivers select), noLineSearch (1, the commented
+    alternative at stationary_pnp_from_pb.hh:174), hackbuschReusken (2).  PNP on pore_small from a rough state on which the
+    damped strategies run out of line-search iterations (4 allowed): accept-best carries on with the best trial and fails a
+    step later, plain Hackbusch-Reusken gives up at once -- status, Newton steps and trial counts equal the oracle's.  The
+    benign start converges with full steps under every strategy."""
+    capi = _capi()
+    c, m, p = make_ctx("pore_small")
+    u0 = np.concatenate([ora.interpolate(m, p, k, np.zeros(m.nv)) for k in range(3)])
+    u0[:m.nv] *= 3.0 if benign else 1.0
+    u0[m.nv:] *= 1 + 0.9 * np.sin(7 * np.tile(m.x, 2))
+    h = c.operator(capi.OP_PNP, 0)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_ILU0, 20000, 1)
+    vu = c.vec(3, u0)
+    st, res = c.newton(h, vu, s, c.newton_opts(jac_mode=1, line_search_strategy=strategy, line_search_max_iterations=4,
+                                               max_iterations=25), check=False)
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_ILU0, jac_mode=1)
+    opts[12] = 20000; opts[14] = strategy; opts[5] = 4; opts[4] = 25
+    u_o, res_o = ora.newton(m, p, ora.OP_PNP, u0, opts)
+    assert st == res_o["status"] and bool(res.converged) == res_o["converged"]
+    assert res.iterations == res_o["iterations"] and res.line_search_trials == res_o["total_ls_trials"]
+    if benign:
+        assert res.converged and res.line_search_trials == res.iterations
+        assert np.linalg.norm(c.download(vu, 3) - u_o) <= 10 * p.sys[7] * np.linalg.norm(u_o)
+    else:
+        assert st == 3 and res.line_search_trials > res.iterations   # PNP_E_LINE_SEARCH
