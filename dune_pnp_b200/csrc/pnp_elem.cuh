@@ -70,6 +70,56 @@ template <> PNP_HD void quad_point<7>(int q, double& xi0, double& xi1, double& w
   else { w = wd; xi0 = q == 4 ? c : d; xi1 = q == 5 ? c : d; }
 }
 
+// sinh for the Poisson-Boltzmann source term (pb_operator.hh:117), built from +, -, *, / and floor only, so that the device
+// (compiled -fmad=false) and the CPU oracle (-ffp-contract=off), which carries the same sequence of operations, get the same
+// BITS: NumericalJacobianVolume divides differences of the residual by delta ~ 1e-11, and a last-bit difference between
+// two libm's sinh would show up ten thousand times larger in the FD Jacobian.  |error| <= 4 ulp for |x| < 700.
+PNP_HD double pnp_pow2(int k) { // 2^k, -1022 <= k <= 1023
+  const unsigned long long bits = (unsigned long long)(k + 1023) << 52;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)bits);
+#else
+  double d; __builtin_memcpy(&d, &bits, sizeof d); return d;
+#endif
+}
+PNP_HD double pnp_sinh(double x) {
+  const double a = x < 0.0 ? -x : x;
+  double r;
+  if (a < 0.35) { // odd Taylor series, Horner in x^2 (next term x^17/17! < 1e-22)
+    const double t = a * a;
+    double p = 1.0 / 1307674368000.0;        // 1/15!
+    p = p * t + 1.0 / 6227020800.0;          // 1/13!
+    p = p * t + 1.0 / 39916800.0;            // 1/11!
+    p = p * t + 1.0 / 362880.0;              // 1/9!
+    p = p * t + 1.0 / 5040.0;                // 1/7!
+    p = p * t + 1.0 / 120.0;                 // 1/5!
+    p = p * t + 1.0 / 6.0;                   // 1/3!
+    r = a + a * (t * p);
+  } else {        // (e^a - e^-a) / 2 with e^a = 2^k e^s, |s| <= ln2 / 2
+    const double kf = floor(a * 1.44269504088896338700e+00 + 0.5);
+    const double s = (a - kf * 6.93147180369123816490e-01) - kf * 1.90821492927058770002e-10;
+    double p = 1.0 / 87178291200.0;          // 1/14!
+    p = p * s + 1.0 / 6227020800.0;
+    p = p * s + 1.0 / 479001600.0;
+    p = p * s + 1.0 / 39916800.0;
+    p = p * s + 1.0 / 3628800.0;
+    p = p * s + 1.0 / 362880.0;
+    p = p * s + 1.0 / 40320.0;
+    p = p * s + 1.0 / 5040.0;
+    p = p * s + 1.0 / 720.0;
+    p = p * s + 1.0 / 120.0;
+    p = p * s + 1.0 / 24.0;
+    p = p * s + 1.0 / 6.0;
+    p = p * s + 0.5;
+    p = p * s + 1.0;
+    p = p * s + 1.0;
+    const int k = (int)kf;
+    const double e = p * pnp_pow2(k / 2) * pnp_pow2(k - k / 2);
+    r = 0.5 * e - 0.5 / e;
+  }
+  return x < 0.0 ? -r : r;
+}
+
 // Affine geometry of one triangle with vertices in ELEMENT-LOCAL order.
 struct Geo {
   double y0, y1, y2;   // for geometry().global()[1]
@@ -134,7 +184,7 @@ PNP_HD void rows_faithful(const Geo& G, const PhysParams& P, const double (*xl)[
 #pragma unroll
       for (int i = 0; i < 3; i++) { gu[0] += xl[0][i] * G.g[i][0]; gu[1] += xl[0][i] * G.g[i][1]; }
       double src;
-      if (OP == OP_PB) src = 8 * PI * P.l_b * P.c0 * sinh(u);
+      if (OP == OP_PB) src = 8 * PI * P.l_b * P.c0 * pnp_sinh(u);
       else {
         double cp = 0.0, cm = 0.0;
 #pragma unroll

@@ -297,3 +297,10 @@ class Bench:
             lib().ora_bench_free(self.h)
         except Exception:
             pass
+
+
+def sinh_shared(x):
+    """The oracle's own sinh (pb_operator.hh:117 stand-in shared bit for bit with the device kernels)."""
+    x = _f64(x); y = np.zeros_like(x)
+    lib().ora_sinh_shared(len(x), _d(x), _d(y))
+    return y

@@ -343,4 +343,6 @@ int ora_assembly_par(void* mh, void* ph, int op, const double* u, int threads, i
   ORA_CATCH(-1)
 }
 
+void ora_sinh_shared(int n, const double* x, double* y) { for (int i = 0; i < n; i++) y[i] = sinh_shared(x[i]); }
+
 } // extern "C"

@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <map>
 #include <set>
@@ -368,6 +369,50 @@ inline ElemGeo elem_geo(const Mesh& m, int e) {
 
 // alpha_volume for element e with local coefficients xl (child-major for PNP:
 // [phi0 phi1 phi2 | cp0 cp1 cp2 | cm0 cm1 cm2]); ACCUMULATES into rl.
+// sinh of pb_operator.hh:117.  The reference calls std::sinh; this restatement carries its own sinh made of +, -, *, /
+// and floor only (|error| <= 4 ulp), because the device kernels must evaluate the SAME bits: NumericalJacobianVolume
+// divides residual differences by delta ~ 1e-11, so a last-bit difference between two libm's would appear 1e4 times larger
+// in the FD Jacobian and hide real discrepancies.  The CUDA side repeats this operation sequence
+// (dune_pnp_b200/csrc/pnp_elem.cuh: pnp_sinh); tests/test_host_logic.py checks the two bit for bit and against libm.
+inline double pow2_int(int k) { const uint64_t bits = (uint64_t)(k + 1023) << 52; double d; std::memcpy(&d, &bits, sizeof d); return d; }
+inline double sinh_shared(double x) {
+  const double a = x < 0.0 ? -x : x;
+  double r;
+  if (a < 0.35) {
+    const double t = a * a;
+    double p = 1.0 / 1307674368000.0;
+    p = p * t + 1.0 / 6227020800.0;
+    p = p * t + 1.0 / 39916800.0;
+    p = p * t + 1.0 / 362880.0;
+    p = p * t + 1.0 / 5040.0;
+    p = p * t + 1.0 / 120.0;
+    p = p * t + 1.0 / 6.0;
+    r = a + a * (t * p);
+  } else {
+    const double kf = std::floor(a * 1.44269504088896338700e+00 + 0.5);
+    const double s = (a - kf * 6.93147180369123816490e-01) - kf * 1.90821492927058770002e-10;
+    double p = 1.0 / 87178291200.0;
+    p = p * s + 1.0 / 6227020800.0;
+    p = p * s + 1.0 / 479001600.0;
+    p = p * s + 1.0 / 39916800.0;
+    p = p * s + 1.0 / 3628800.0;
+    p = p * s + 1.0 / 362880.0;
+    p = p * s + 1.0 / 40320.0;
+    p = p * s + 1.0 / 5040.0;
+    p = p * s + 1.0 / 720.0;
+    p = p * s + 1.0 / 120.0;
+    p = p * s + 1.0 / 24.0;
+    p = p * s + 1.0 / 6.0;
+    p = p * s + 0.5;
+    p = p * s + 1.0;
+    p = p * s + 1.0;
+    const int k = (int)kf;
+    const double e = p * pow2_int(k / 2) * pow2_int(k - k / 2);
+    r = 0.5 * e - 0.5 / e;
+  }
+  return x < 0.0 ? -r : r;
+}
+
 inline void alpha_volume(const OpCtx& c, int e, const double* xl, double* rl) {
   const Mesh& m = *c.m; const Sysparams& s = *c.s;
   const ElemGeo g = elem_geo(m, e);
@@ -405,7 +450,7 @@ inline void alpha_volume(const OpCtx& c, int e, const double* xl, double* rl) {
         for (int i = 0; i < 3; i++) u += xl[i] * phi[i];
         for (int i = 0; i < 3; i++) { gu[0] += xl[i] * g.gphi[i][0]; gu[1] += xl[i] * g.gphi[i][1]; }
         double src;
-        if (c.op == OP_PB) src = 8 * PI * s.l_b * s.c0 * std::sinh(u); // pb_operator.hh:117
+        if (c.op == OP_PB) src = 8 * PI * s.l_b * s.c0 * sinh_shared(u); // pb_operator.hh:117 (std::sinh there)
         else { // DiscreteGridFunction::evaluate = sum u_i phi_i  (poisson_operator.hh:97-100)
           double cp = 0.0, cm = 0.0;
           for (int i = 0; i < 3; i++) cp += c.cp[tv[i]] * phi[i];

@@ -253,3 +253,6 @@ void hh_ilu0_apply(void* h, int F, double* lu, const double* d, double* x) {
     for (int i : L[l]) { if (F == 1) ilu0_backward<1>(V, lu, stride, x, i, 0); else ilu0_backward<3>(V, lu, stride, x, i / 3, i % 3); }
 }
 } // extern "C"
+
+// the device's pnp_sinh compiled for the host (-ffp-contract=off): must equal the oracle's sinh_shared bit for bit
+extern "C" void hh_sinh(int n, const double* x, double* y) { for (int i = 0; i < n; i++) y[i] = pnp::pnp_sinh(x[i]); }

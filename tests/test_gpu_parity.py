@@ -152,16 +152,11 @@ def test_jacobian_parity(name, levels, op, mode):
     c.jacobian(h, vu, A, mode, 1e-11)
     rp, col, val_o, ab = ora.jacobian(m, p, op, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11, want_abs=True)
     val = c.matrix_values(h, A, len(col))
-    if op == capi.OP_PB:
-        # sinh/cosh come from CUDA's libm on the device and glibc on the host (ulp-level differences); the forward
-        # difference divides them by delta ~ 1e-11, so FD-mode parity is bounded by eps_mach * |r_e| / delta instead
-        r_o, rab = ora.residual(m, p, op, u, want_abs=True)
-        bound = (TOL if mode == 0 else TOL_EXACT) * ab + (4 * 2.3e-16 * rab.max() / 1e-11 if mode == 0 else 0.0)
-        assert np.all(np.abs(val - val_o) <= bound + 1e-300)
-    else:
-        assert rel_err(val, val_o, ab) <= (TOL if mode == 0 else TOL_EXACT)
-        if mode == 0:  # two-term sums (off-diagonal entries) must reproduce the oracle bit for bit
-            assert np.mean(val == val_o) > 0.9
+    # (PB included: the source term's sinh is one operation sequence shared bit for bit by the device and the oracle,
+    # SURVEY H1 -- with two different libm's the FD quotient amplified their last-bit differences by 1/delta)
+    assert rel_err(val, val_o, ab) <= (TOL if mode == 0 else TOL_EXACT)
+    if mode == 0:  # two-term sums (off-diagonal entries) must reproduce the oracle bit for bit
+        assert np.mean(val == val_o) > 0.9
 
 
 @pytest.mark.parametrize("name", ["cylinder", "pore"])

@@ -203,3 +203,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_shared_sinh_is_bit_identical_on_both_sides_and_accurate():
+    """the PB source term's sinh is one sequence of +, -, *, /, floor on the device (pnp_elem.cuh: pnp_sinh,
+    compiled here for the host without FMA contraction) and in the oracle (sinh_shared): same bits, within 4 ulp of libm."""
+    import ctypes as C
+    rng = np.random.RandomState(0)
+    x = np.concatenate([rng.uniform(-0.5, 0.5, 20000), rng.uniform(-30, 30, 20000), rng.uniform(-600, 600, 2000),
+                        [0.0, -0.0, 0.35, -0.35, 0.34999999999999, 1e-300, 1e-9, 709.0 * 0.98]])
+    y_dev = np.zeros_like(x)
+    harness.lib().hh_sinh(len(x), x.ctypes.data_as(C.POINTER(C.c_double)), y_dev.ctypes.data_as(C.POINTER(C.c_double)))
+    y_ora = ora.sinh_shared(x)
+    assert np.array_equal(y_dev.view(np.int64), y_ora.view(np.int64))
+    ref = np.sinh(x)
+    ulp = np.abs(y_ora - ref) / np.maximum(np.spacing(np.abs(ref)), 5e-324)
+    assert ulp.max() <= 4.0
+    assert np.array_equal(np.signbit(y_ora), np.signbit(x))
