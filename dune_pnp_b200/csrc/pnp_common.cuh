@@ -69,6 +69,7 @@ struct Tune {
   int tma_lpr = 2;        // lanes per row in the streaming SpMV (1 or 2): 2 -> eight consumer warps per SM
   long tma_min_rows = -1; // smallest level the streaming SpMV serves (-1: two tiles per SM)
   int graph = 1;          // the multigrid's coarse correction is replayed from a CUDA graph
+  int fd_warp = 1;        // FD-faithful Jacobian: warp-cooperative kernel (0: one thread per vertex)
 };
 inline Tune& tune() { static Tune t; return t; }
 

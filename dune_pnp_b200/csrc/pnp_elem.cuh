@@ -149,16 +149,20 @@ PNP_HD double dot2(const double* a, const double* b) { // FieldVector::operator*
 // aux[a][i] = coefficient field a (Poisson: c+, c-; diffusion: Phi) at local vertex i.
 // ACCUMULATES the contribution of this element to test function I of every field into out[k].
 // ---------------------------------------------------------------------------------------------
-template <int OP, int I>
-PNP_HD void rows_faithful(const Geo& G, const PhysParams& P, const double (*xl)[3], const double (*aux)[3],
-                          double* out) {
+// (I may be a run-time value: it only selects one basis value and one gradient; rows_faithful<OP, I> below fixes it at
+// compile time.  Same operations in the same order either way.)
+template <int OP>
+PNP_HD void rows_faithful_at(const Geo& G, const PhysParams& P, const double (*xl)[3], const double (*aux)[3], const int I,
+                             double* out) {
   constexpr int NQ = OpTraits<OP>::NQ;
   const double PI = P.PI;
+  const double gI[2] = {I == 0 ? G.g[0][0] : (I == 1 ? G.g[1][0] : G.g[2][0]), I == 0 ? G.g[0][1] : (I == 1 ? G.g[1][1] : G.g[2][1])};
 #pragma unroll
   for (int q = 0; q < NQ; q++) {
     double xi0, xi1, w;
     quad_point<NQ>(q, xi0, xi1, w);
     const double phi[3] = {1.0 - xi0 - xi1, xi0, xi1};
+    const double phiI = I == 0 ? phi[0] : (I == 1 ? phi[1] : phi[2]);
     const double gy = G.y0 + (G.y1 - G.y0) * xi0 + (G.y2 - G.y0) * xi1;
     double factor = w * G.detabs;
     if (OP == OP_PNP) {
@@ -173,9 +177,9 @@ PNP_HD void rows_faithful(const Geo& G, const PhysParams& P, const double (*xl)[
 #pragma unroll
         for (int i = 0; i < 3; i++) { gu[k][0] += xl[k][i] * G.g[i][0]; gu[k][1] += xl[k][i] * G.g[i][1]; }
       }
-      out[0] += (dot2(gu[0], G.g[I]) + 4 * PI * P.l_b * (u[1] - u[2]) * phi[I]) * factor;
-      out[1] += (dot2(gu[1], G.g[I]) - u[1] * dot2(gu[0], G.g[I])) * factor;
-      out[2] += (dot2(gu[2], G.g[I]) + u[2] * dot2(gu[0], G.g[I])) * factor;
+      out[0] += (dot2(gu[0], gI) + 4 * PI * P.l_b * (u[1] - u[2]) * phiI) * factor;
+      out[1] += (dot2(gu[1], gI) - u[1] * dot2(gu[0], gI)) * factor;
+      out[2] += (dot2(gu[2], gI) + u[2] * dot2(gu[0], gI)) * factor;
     } else if (OP == OP_PB || OP == OP_POISSON) {
       if (P.cylindrical) factor *= gy * 2 * PI;
       double u = 0.0, gu[2] = {0.0, 0.0};
@@ -193,7 +197,7 @@ PNP_HD void rows_faithful(const Geo& G, const PhysParams& P, const double (*xl)[
         for (int i = 0; i < 3; i++) cm += aux[1][i] * phi[i];
         src = 1 * P.l_b * 4 * PI * (cm - cp);
       }
-      out[0] += (dot2(gu, G.g[I]) + src * phi[I]) * factor;
+      out[0] += (dot2(gu, gI) + src * phiI) * factor;
     } else if (OP == OP_DIFFUSION) {
       double u = 0.0, gu[2] = {0.0, 0.0}, gP[2] = {0.0, 0.0};
 #pragma unroll
@@ -203,14 +207,18 @@ PNP_HD void rows_faithful(const Geo& G, const PhysParams& P, const double (*xl)[
 #pragma unroll
       for (int i = 0; i < 3; i++) { gP[0] += aux[0][i] * G.g[i][0]; gP[1] += aux[0][i] * G.g[i][1]; }
       const double a = 0;
-      out[0] += (dot2(gu, G.g[I]) + u * P.valency * dot2(gP, G.g[I]) + a * u * phi[I]) * factor;
+      out[0] += (dot2(gu, gI) + u * P.valency * dot2(gP, gI) + a * u * phiI) * factor;
     } else { // OP_MASS
       double u = 0.0;
 #pragma unroll
       for (int i = 0; i < 3; i++) u += xl[0][i] * phi[i];
-      out[0] += u * phi[I] * factor;
+      out[0] += u * phiI * factor;
     }
   }
+}
+template <int OP, int I>
+PNP_HD void rows_faithful(const Geo& G, const PhysParams& P, const double (*xl)[3], const double (*aux)[3], double* out) {
+  rows_faithful_at<OP>(G, P, xl, aux, I, out);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -993,3 +993,24 @@ def test_newton_line_search_strategies(strategy, benign):
         assert np.linalg.norm(c.download(vu, 3) - u_o) <= 10 * p.sys[7] * np.linalg.norm(u_o)
     else:
         assert st == 3 and res.line_search_trials > res.iterations   # PNP_E_LINE_SEARCH
+
+
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("name,levels", [("pore", 0), ("pore_small", 2), ("one_wall", 1)])
+def test_fd_jacobian_kernels_agree_bitwise(name, levels, op):
+    """The warp-cooperative NumericalJacobianVolume kernel (a lane per perturbed evaluation) against the one-thread-per-vertex
+    form it replaces: the same operations in the same order for every entry -> identical bits."""
+    capi = _capi()
+    c, m, p = make_ctx(name, levels=levels)
+    F = ora.nfields(op)
+    u, a0, a1 = _random_state(m, op, seed=13)
+    h = _gpu_operator(c, op, a0, a1, -1.0)
+    vu, A = c.vec(F, u), c.matrix(h)
+    rp, col = c.pattern(h, F)
+    out = {}
+    for warp in (1, 0):
+        capi.tune("fd_warp", warp)
+        c.jacobian(h, vu, A, capi.JAC_FD_FAITHFUL, 1e-11)
+        out[warp] = c.matrix_values(h, A, len(col))
+    capi.tune("fd_warp", 1)
+    assert np.array_equal(out[1], out[0])
