@@ -210,6 +210,7 @@ def build_state(c, capi, levels, coarse_level, jac_mode, prec_steps, verbose):
 AMG_PARTITIONED = {"amg_geometric": 0}
 EXTRA_SOLVER_OPTS = {}            # --solver-opt NAME=VALUE
 DENSE_COARSE = False              # --dense-coarse
+PYTHON_PARTITIONER = False        # --python-partitioner
 REPLICA_LEVEL = 3                 # --replica-level: N > 1, refinement level at which the hierarchy stops being distributed
 AMG_FINE = {"amg_geometric": 1}   # refinement levels as multigrid levels (P1 interpolation), aggregation below the coarsest mesh
 
@@ -243,7 +244,9 @@ def build_state_partitioned(c, capi, levels, coarse_level, jac_mode, prec_steps,
         out = [None] * world
         dist.all_gather_object(out, obj)
         return out
-    plans = partition.build_hierarchy(a_base, world, rank, levels, all_gather=all_gather, fields_at=(coarse_level, lookup))
+    # the library's native partitioner (csrc/pnp_partition.cu); --python-partitioner: its numpy cross-check (same plans)
+    build = partition.build_hierarchy if PYTHON_PARTITIONER else partition.build_hierarchy_native
+    plans = build(a_base, world, rank, levels, all_gather=all_gather, fields_at=(coarse_level, lookup))
     uid = [capi.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     # the hierarchy is distributed down to refinement level REPLICA_LEVEL; that level is gathered to a replica of the whole
@@ -443,7 +446,7 @@ def run_gpu(args, rank, world, local_rank):
                                "step (Jacobian assembly, BiCGSTAB + multigrid, line search)" % args.levels,
                    "levels": args.levels, "dofs": gdof, "matrix_slots": gslots,
                    "rank0_owned_vertices": n_own, "rank0_ghost_vertices": nv - n_own,
-                   "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the Gmsh mesh), NCCL halo exchange per multigrid level + scalar allreduce" % world,
+                   "parallelism": "1 GPU" if world == 1 else "%d subdomains (RCB of the Gmsh mesh, %s partitioner), NCCL halo exchange per multigrid level + scalar allreduce" % (world, "numpy" if PYTHON_PARTITIONER else "native"),
                    "jacobian": args.jac, "solver_options": dict(EXTRA_SOLVER_OPTS), "preconditioner": "multigrid V(%d,%d), damped Jacobi: %s" % (args.prec_steps, args.prec_steps,
                        "refinement levels with P1 interpolation + re-discretised operators, aggregation AMG below the Gmsh mesh" if world == 1
                        else "distributed refinement levels with P1 interpolation, re-discretised operators, " + ("replicated dense LU on the Gmsh mesh" if DENSE_COARSE else "levels <= %d replicated on every rank (one-GPU hierarchy: refinement levels, aggregation AMG below the Gmsh mesh)" % REPLICA_LEVEL)),
@@ -503,10 +506,11 @@ def main():
                     help="pnp_solver_set_option for the timed step's multigrid (experiments), e.g. amg_smoother=1")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--replica-level", type=int, default=3, help="N > 1: levels below this one run replicated on every rank (no halo exchanges there)")
+    ap.add_argument("--python-partitioner", action="store_true", help="N > 1: numpy partitioner (dune_pnp_b200/partition.py) instead of the native one")
     ap.add_argument("--dense-coarse", action="store_true", help="N > 1: replicated dense LU on the Gmsh mesh instead of the replica hierarchy")
     args = ap.parse_args()
-    global DENSE_COARSE, REPLICA_LEVEL
-    DENSE_COARSE = args.dense_coarse; REPLICA_LEVEL = args.replica_level
+    global DENSE_COARSE, REPLICA_LEVEL, PYTHON_PARTITIONER
+    DENSE_COARSE = args.dense_coarse; REPLICA_LEVEL = args.replica_level; PYTHON_PARTITIONER = args.python_partitioner
     for kv in args.solver_opt:
         k, v = kv.split("=")
         EXTRA_SOLVER_OPTS[k] = float(v)

@@ -340,3 +340,83 @@ def aggregate_greedy(nv, tri, leftovers_join=True):
             else:
                 agg[v] = n_agg; n_agg += 1; size = np.append(size, 1)
     return agg.astype(np.int32), n_agg
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same decomposition by the library's native partitioner (csrc/pnp_partition.cu, C ABI pnp_part_*): the plans it
+# returns equal build_hierarchy()'s array by array (tests/test_partition_native.py); only the two small all-gathers stay here.
+# ---------------------------------------------------------------------------------------------------------------
+def build_hierarchy_native(a, nparts, me, levels, all_gather=None, fields_at=None):
+    import ctypes as C
+    from . import capi
+    L = capi.lib()
+    L.pnp_part_last_error.restype = C.c_char_p
+    dp, ip, lp, up = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_ulonglong)
+
+    def ck(st):
+        if st != 0:
+            raise capi.PnpError(st, L.pnp_part_last_error(h).decode())
+    x = np.ascontiguousarray(a["x"], dtype=np.float64); y = np.ascontiguousarray(a["y"], dtype=np.float64)
+    tri = np.ascontiguousarray(a["tri"], dtype=np.int32); ba = np.ascontiguousarray(a["ba"], dtype=np.int32)
+    bb = np.ascontiguousarray(a["bb"], dtype=np.int32); ph = np.ascontiguousarray(a["bphys"], dtype=np.int32)
+    h = C.c_void_p()
+    st = L.pnp_part_create(C.c_long(len(x)), x.ctypes.data_as(dp), y.ctypes.data_as(dp), C.c_long(len(tri)), tri.ctypes.data_as(ip),
+                           C.c_long(len(ba)), ba.ctypes.data_as(ip), bb.ctypes.data_as(ip), ph.ctypes.data_as(ip), nparts, me, levels,
+                           C.byref(h))
+    if st != 0:
+        raise capi.PnpError(st, "pnp_part_create failed")
+    plans = []
+    try:
+        for l in range(levels + 1):
+            n = C.c_long()
+            ck(L.pnp_part_ghost_keys(h, l, C.byref(n), None))
+            keys = np.zeros(2 * n.value, dtype=np.uint64)
+            ck(L.pnp_part_ghost_keys(h, l, C.byref(n), keys.ctypes.data_as(up)))
+            if nparts > 1:
+                allk = all_gather(keys)
+                gptr = np.zeros(nparts + 1, dtype=np.int64); gptr[1:] = np.cumsum([len(k) // 2 for k in allk])
+                cat = np.ascontiguousarray(np.concatenate(allk), dtype=np.uint64)
+                cptr = np.zeros(nparts + 1, dtype=np.int64)
+                ck(L.pnp_part_claim(h, l, gptr.ctypes.data_as(lp), cat.ctypes.data_as(up), cptr.ctypes.data_as(lp), None))
+                cpos = np.zeros(max(1, cptr[-1]), dtype=np.int64)
+                ck(L.pnp_part_claim(h, l, gptr.ctypes.data_as(lp), cat.ctypes.data_as(up), cptr.ctypes.data_as(lp), cpos.ctypes.data_as(lp)))
+                claims_all = all_gather((cptr, cpos))            # every rank's claims about every rank's ghosts
+                mine = [claims_all[r][1][claims_all[r][0][me]:claims_all[r][0][me + 1]] for r in range(nparts)]
+                mptr = np.zeros(nparts + 1, dtype=np.int64); mptr[1:] = np.cumsum([len(m_) for m_ in mine])
+                mpos = np.ascontiguousarray(np.concatenate(mine) if mptr[-1] else np.zeros(1), dtype=np.int64)
+                ck(L.pnp_part_finalize(h, l, mptr.ctypes.data_as(lp), mpos.ctypes.data_as(lp)))
+            else:
+                ck(L.pnp_part_finalize(h, l, None, None))
+            sz = (C.c_long * 8)()
+            ck(L.pnp_part_sizes(h, l, sz))
+            nv, n_own, nT, nB, n_nbr, n_send, n_global, has_gid = list(sz)
+            p = Plan()
+            p.x, p.y = np.zeros(nv), np.zeros(nv)
+            p.tri = np.zeros((nT, 3), dtype=np.int32)
+            p.ba, p.bb, p.bphys = (np.zeros(nB, dtype=np.int32) for _ in range(3))
+            p.nbr = np.zeros(n_nbr, dtype=np.int32); p.send_ptr = np.zeros(n_nbr + 1, dtype=np.int32)
+            p.send_idx = np.zeros(n_send, dtype=np.int32); p.recv_ptr = np.zeros(n_nbr + 1, dtype=np.int32)
+            par0, par1 = np.zeros(nv, dtype=np.int32), np.zeros(nv, dtype=np.int32)
+            gid = np.zeros(nv if has_gid else 1, dtype=np.int32)
+            ck(L.pnp_part_get(h, l, p.x.ctypes.data_as(dp), p.y.ctypes.data_as(dp), p.tri.ctypes.data_as(ip), p.ba.ctypes.data_as(ip),
+                              p.bb.ctypes.data_as(ip), p.bphys.ctypes.data_as(ip), p.nbr.ctypes.data_as(ip), p.send_ptr.ctypes.data_as(ip),
+                              p.send_idx.ctypes.data_as(ip), p.recv_ptr.ctypes.data_as(ip), par0.ctypes.data_as(ip), par1.ctypes.data_as(ip),
+                              gid.ctypes.data_as(ip) if has_gid else None))
+            p.n_own, p.nv, p.n_global = n_own, nv, n_global
+            p.par = None if l == 0 else np.stack([par0, par1], axis=1).astype(np.int64)
+            p.gid = gid.astype(np.int64) if has_gid else None
+            # nodal fields: injected at one level, P1-interpolated to the finer ones
+            p.fields = {}
+            if fields_at is not None:
+                if fields_at[0] == l:
+                    p.fields = {k: np.asarray(v, dtype=np.float64) for k, v in fields_at[1](p.x, p.y).items()}
+                elif fields_at[0] < l:
+                    two = par1 >= 0
+                    for k, v in plans[-1].fields.items():
+                        f = v[:, par0].copy()
+                        f[:, two] = 0.5 * (v[:, par0[two]] + v[:, par1[two]])
+                        p.fields[k] = f
+            plans.append(p)
+    finally:
+        L.pnp_part_destroy(h)
+    return plans

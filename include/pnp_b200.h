@@ -108,6 +108,30 @@ pnp_status pnp_mg_set_coarse_aggregates(pnp_ctx*, const int* aggregate, long n_a
  * replica runs the single-GPU multigrid below it (aggregation levels, small dense LU) redundantly on every rank: the
  * cycle equals the one-GPU cycle, and no rank factorises a matrix of the size of the coarsest mesh. */
 pnp_status pnp_mg_set_coarse_replica(pnp_ctx*, pnp_ctx* replica, const int* global_vertex_index, long n_global);
+/* ---- native domain decomposition: grid->loadBalance() (pnp_solver_main.cc:93-108) --------------------------------------
+ * Host code, no GPU needed.  Every rank calls pnp_part_create with the SAME coarse mesh: recursive coordinate bisection of
+ * the triangle centroids into `world` parts, this rank's part with one ghost layer, `levels` uniform refinements of that
+ * local mesh (trimmed back to one layer after each).  Per level, coarsest first, the halo plan needs two small all-gathers
+ * whose transport is the caller's (MPI in a DUNE build, torch.distributed in the Python launchers, pnp_comm_allgatherv):
+ *   pnp_part_ghost_keys  -> (x bits, y bits) of this rank's ghost vertices            [all-gather: every rank's keys]
+ *   pnp_part_claim       -> for every rank q the positions of q's ghosts owned here    [all-gather: every rank's claims]
+ *   pnp_part_finalize    <- the positions of MY ghosts each rank r claimed (mine_ptr[r] .. mine_ptr[r+1])
+ * after which pnp_part_sizes / pnp_part_get return the level in the form pnp_mesh_set_local / pnp_halo_set /
+ * pnp_mg_push_level take: owned vertices first, ghosts grouped by owner rank in the order the owner sends them; par0/par1 =
+ * parents in the next coarser level's numbering; gid (coarsest level) = global vertex index.
+ * sizes[8] = {nv, n_own, nT, nB, n_nbr, n_send, n_global, has_gid}. */
+typedef struct pnp_part pnp_part;
+pnp_status pnp_part_create(long nv, const double* x, const double* y, long nT, const int* tri, long nB, const int* ba,
+                           const int* bb, const int* bphys, int world, int rank, int levels, pnp_part** out);
+void pnp_part_destroy(pnp_part*);
+const char* pnp_part_last_error(pnp_part*);
+pnp_status pnp_part_ghost_keys(pnp_part*, int level, long* n, unsigned long long* keys /* 2*n, may be NULL */);
+pnp_status pnp_part_claim(pnp_part*, int level, const long* ghost_ptr /* world+1 */, const unsigned long long* ghost_keys_all,
+                          long* claim_ptr /* world+1 */, long* claim_pos /* may be NULL */);
+pnp_status pnp_part_finalize(pnp_part*, int level, const long* mine_ptr /* world+1 */, const long* mine_pos);
+pnp_status pnp_part_sizes(pnp_part*, int level, long* sizes);
+pnp_status pnp_part_get(pnp_part*, int level, double* x, double* y, int* tri, int* ba, int* bb, int* bphys, int* nbr,
+                        int* send_ptr, int* send_idx, int* recv_ptr, int* par0, int* par1, int* gid);
 /* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
 pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
 /* nested iteration: pnp_carry_set() stores vectors in reference numbering; every later pnp_mesh_refine() level

@@ -297,9 +297,12 @@ def test_newton_pnp_from_pb_matches_oracle(name, tight):
         s = c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 20000, 2)
     else:
         s = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 20000, 1)
-    kw = dict(reduction=1e-11, min_linear_reduction=1e-9) if tight else {}
+    # tight: exact-derivative Jacobian on both sides -- the forward differences (eps = 1e-11) put noise of relative size
+    # ~1e-5 into the matrix, Newton then gains only ~5 digits per step near the solution, and whether the defect crosses
+    # 1e-11 * d0 in step 5 or 6 is decided by that noise (it flipped when the PB stage's sinh changed in the last bit)
+    kw = dict(reduction=1e-11, min_linear_reduction=1e-9, jac_mode=capi.JAC_ANALYTIC) if tight else {}
     st, res = c.newton(h, vu, s, c.newton_opts(**kw))
-    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR); opts[12] = 20000
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, jac_mode=1 if tight else 0); opts[12] = 20000
     if tight:
         opts[0], opts[2] = 1e-11, 1e-9
     u_o, res_o = ora.newton(m, p, ora.OP_PNP, u0_o, opts)
