@@ -32,7 +32,6 @@ void to_lin(const LinResult& lr, pnp_lin_result* out) {
 
 using namespace pnp;
 
-struct pnp_ctx { Ctx c; };
 
 #define API_BEGIN(ctx)                                  \
   if (!(ctx)) return PNP_E_ARG;                         \
@@ -89,6 +88,11 @@ void pnp_ctx_destroy(pnp_ctx* ctx) {
   // for them otherwise: a finished multi-GPU run never exited): drop every solver -- this context's and its children's,
   // whose multigrid objects may hold such graphs -- first
   c.solvers.clear();
+  { // levels pnp_partition_build created belong to this context
+    std::vector<void*> owned;
+    owned.swap(c.owned_children);
+    for (void* h : owned) pnp_ctx_destroy((pnp_ctx*)h);
+  }
   for (Ctx* k : c.children) { k->solvers.clear(); k->parent = nullptr; k->stream = nullptr; k->nccl = nullptr; }
   if (c.h_red) cudaFreeHost(c.h_red);
   for (cudaEvent_t e : c.prof_ev) cudaEventDestroy(e);
@@ -226,6 +230,24 @@ pnp_status pnp_comm_unique_id(char* out128) {
 }
 pnp_status pnp_comm_init(pnp_ctx* ctx, int rank, int world, const char* unique_id128) {
   API_BEGIN(ctx) comm_init(c, rank, world, unique_id128); API_END
+}
+pnp_status pnp_comm_init_file(pnp_ctx* ctx, int rank, int world, const char* path) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(world == 1 || path, PNP_E_ARG, "null rendezvous path");
+  comm_bootstrap_file(c, rank, world, path ? path : "");
+  API_END
+}
+pnp_status pnp_comm_allgatherv(pnp_ctx* ctx, const void* send, long nbytes, void* recv, long cap, long* counts) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(nbytes >= 0 && counts && (nbytes == 0 || send), PNP_E_ARG, "bad all-gather arguments");
+  std::vector<long> cnt;
+  std::vector<unsigned char> all = comm_allgatherv(c, send, nbytes, cnt);
+  for (int r = 0; r < c.world; r++) counts[r] = cnt[r];
+  if (recv) {
+    PNP_REQUIRE((long)all.size() <= cap, PNP_E_ARG, "receive buffer too small");
+    std::memcpy(recv, all.data(), all.size());
+  }
+  API_END
 }
 pnp_status pnp_halo_set(pnp_ctx* ctx, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr) {
   API_BEGIN(ctx) halo_set(c, n_nbr, nbr, send_ptr, send_idx, recv_ptr); API_END

@@ -11,6 +11,7 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <ctime>
 
 #include "pnp_common.cuh"
 
@@ -58,6 +59,55 @@ void comm_init(Ctx& c, int rank, int world, const char* unique_id128) {
 void comm_destroy(Ctx& c) {
   if (c.nccl && c.owns_comm) ncclCommAbort((ncclComm_t)c.nccl);
   c.nccl = nullptr; c.owns_comm = false;
+}
+
+// NCCL needs its unique id on every rank before the communicator exists.  A DUNE build would broadcast it over MPI; the
+// Python launchers use torch.distributed; a plain C++ driver started by any process launcher uses a file all ranks see:
+// rank 0 writes the id (write + rename: never seen half written), the others wait for it.
+void comm_bootstrap_file(Ctx& c, int rank, int world, const std::string& path) {
+  if (world == 1) { comm_init(c, 0, 1, nullptr); return; }
+  char id[128];
+  if (rank == 0) {
+    comm_unique_id(id);
+    const std::string tmp = path + ".tmp";
+    std::FILE* f = std::fopen(tmp.c_str(), "wb");
+    PNP_REQUIRE(f, PNP_E_CONFIG, "cannot write " + tmp);
+    std::fwrite(id, 1, 128, f); std::fclose(f);
+    PNP_REQUIRE(std::rename(tmp.c_str(), path.c_str()) == 0, PNP_E_CONFIG, "cannot rename " + tmp);
+  } else {
+    std::FILE* f = nullptr;
+    for (int tries = 0; tries < 6000 && !f; tries++) { // up to 10 minutes
+      f = std::fopen(path.c_str(), "rb");
+      if (!f) { struct timespec ts = {0, 100000000}; nanosleep(&ts, nullptr); }
+    }
+    PNP_REQUIRE(f, PNP_E_CONFIG, "rendezvous file " + path + " never appeared");
+    const size_t n = std::fread(id, 1, 128, f); std::fclose(f);
+    PNP_REQUIRE(n == 128, PNP_E_CONFIG, "rendezvous file " + path + " is truncated");
+  }
+  comm_init(c, rank, world, id);
+}
+
+// all-gather of byte blocks of different lengths (set-up plumbing: partition plans): counts[r] = length of rank r's block,
+// returned: the blocks in rank order
+std::vector<unsigned char> comm_allgatherv(Ctx& c, const void* send, long nbytes, std::vector<long>& counts) {
+  counts.assign(c.world, 0);
+  if (c.world == 1) { counts[0] = nbytes; return std::vector<unsigned char>((const unsigned char*)send, (const unsigned char*)send + nbytes); }
+  PNP_REQUIRE(c.nccl, PNP_E_ARG, "no communicator (pnp_comm_init)");
+  ncclComm_t comm = (ncclComm_t)c.nccl;
+  DBuf<long> d_cnt(c.world), d_mine(1);
+  d_mine.upload(&nbytes, 1, c.stream);
+  PNP_NCCL(ncclAllGather(d_mine.p, d_cnt.p, 1, ncclInt64, comm, c.stream));
+  d_cnt.download(counts.data(), c.world, c.stream);
+  long mx = 0;
+  for (long v : counts) mx = std::max(mx, v);
+  mx = (mx + 15) & ~15l;
+  if (mx == 0) return {};
+  DBuf<unsigned char> d_send(mx), d_recv((size_t)mx * c.world);
+  if (nbytes) d_send.upload((const unsigned char*)send, nbytes, c.stream);
+  PNP_NCCL(ncclAllGather(d_send.p, d_recv.p, mx, ncclChar, comm, c.stream));
+  std::vector<unsigned char> padded = d_recv.to_host(c.stream), out;
+  for (int r = 0; r < c.world; r++) out.insert(out.end(), padded.begin() + (size_t)r * mx, padded.begin() + (size_t)r * mx + counts[r]);
+  return out;
 }
 
 void halo_set(Ctx& c, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr) {

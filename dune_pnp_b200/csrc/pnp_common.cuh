@@ -225,6 +225,7 @@ struct Ctx {
   long mg_epoch = 0;                   // bumped by every pnp_mg_* call: a multigrid built for an older hierarchy is rebuilt
   Ctx* parent = nullptr;               // child contexts: the context whose stream / communicator they borrow
   std::vector<Ctx*> children;          // ... and the children a context has handed out (their lifetime is bounded by the parent's)
+  std::vector<void*> owned_children;   // pnp_ctx handles pnp_partition_build created: destroyed with this context
   bool owns_comm = false;
   // what the last assemble_jacobian() call linearised (coarse levels of the distributed multigrid re-discretise it)
   const double* last_u = nullptr; Operator last_op; int last_mode = 0; double last_eps = 1e-11;
@@ -269,6 +270,8 @@ void constraints_build(Ctx&);
 void comm_init(Ctx&, int rank, int world, const char* unique_id128);
 void comm_unique_id(char* out128);
 void comm_destroy(Ctx&);
+void comm_bootstrap_file(Ctx&, int rank, int world, const std::string& path);
+std::vector<unsigned char> comm_allgatherv(Ctx&, const void* send, long nbytes, std::vector<long>& counts);
 void halo_set(Ctx&, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr);
 void halo_finalize(Ctx&);
 void halo_exchange(Ctx&, double* x, int fields);
@@ -309,3 +312,6 @@ void write_cell_data(Ctx&, const Vec& u, const std::string& filename);
 void write_vtk(Ctx&, const std::string& name, int nfields, const Vec* const* fields, const char* const* names, int ascii);
 
 } // namespace pnp
+
+// the opaque handle of the C ABI
+struct pnp_ctx { pnp::Ctx c; };

@@ -373,4 +373,140 @@ pnp_status pnp_part_get(pnp_part* P, int level, double* x, double* y, int* tri, 
   PART_CATCH(P)
 }
 
+// The whole decomposition in one call, for drivers without a Python launcher (PnpSolverMain::run with N ranks,
+// pnp_solver_main.cc:93-108).  `root` holds the GLOBAL coarse mesh (pnp_mesh_set / pnp_mesh_read_gmsh), the parameters and
+// an initialised communicator (pnp_comm_init / pnp_comm_init_file) on every rank.  Afterwards root holds this rank's part
+// of the mesh refined `levels` times (finalized, halo plan set), the coarser levels are registered as multigrid levels down
+// to `replica_level`, below which a replica of the whole mesh continues on every rank (pnp_mg_set_coarse_replica).  The
+// level contexts belong to root and go with it.
+// Nodal fields (nfields > 0) given on the unpartitioned mesh of refinement level `field_level` -- values [nfields][nf] at
+// the vertices (fx, fy)[nf], e.g. a coarse solution for nested iteration -- are injected there by bitwise coordinate match
+// and P1-interpolated to the finest level; *start_vec receives a new vector of root holding them.
+pnp_status pnp_partition_build(pnp_ctx* root, int levels, int replica_level, int field_level, int nfields, long nf,
+                               const double* fx, const double* fy, const double* fields, int* start_vec) {
+  if (!root) return PNP_E_ARG;
+  Ctx& c = root->c;
+  pnp_part* P = nullptr;
+  try {
+    PNP_CUDA(cudaSetDevice(c.device));
+    PNP_REQUIRE(c.nv > 0 && c.n_own == c.nv && c.hier.empty(), PNP_E_ARG, "root must hold the unrefined global mesh");
+    PNP_REQUIRE(c.params.set, PNP_E_ARG, "parameters not set");
+    PNP_REQUIRE(levels >= 1 && replica_level >= 0 && replica_level <= levels - 1, PNP_E_ARG, "bad level arguments");
+    PNP_REQUIRE(nfields == 0 || (nfields == 1 || nfields == 3), PNP_E_ARG, "1 or 3 fields");
+    PNP_REQUIRE(nfields == 0 || (field_level >= 0 && field_level <= levels && fx && fy && fields && start_vec), PNP_E_ARG, "bad field arguments");
+    const int world = c.world, me = c.rank;
+    const long gnv = c.nv, gnT = c.nT, gnB = c.nB;
+    std::vector<double> gx = c.cx.to_host(c.stream), gy = c.cy.to_host(c.stream);
+    std::vector<int> gtri = c.ctri.to_host(c.stream), gba = c.cba.to_host(c.stream), gbb = c.cbb.to_host(c.stream), gph = c.cbphys.to_host(c.stream);
+    pnp_status st = pnp_part_create(gnv, gx.data(), gy.data(), gnT, gtri.data(), gnB, gba.data(), gbb.data(), gph.data(), world, me, levels, &P);
+    PNP_REQUIRE(st == PNP_OK, st, "partitioning failed");
+    auto pck = [&](pnp_status s_) { if (s_ != PNP_OK) throw Error(s_, P->err); };
+    for (int l = 0; l <= levels; l++) {
+      long ng = 0;
+      pck(pnp_part_ghost_keys(P, l, &ng, nullptr));
+      std::vector<unsigned long long> keys(2 * (size_t)ng + 1);
+      pck(pnp_part_ghost_keys(P, l, &ng, keys.data()));
+      if (world > 1) {
+        std::vector<long> cnt;
+        std::vector<unsigned char> allk = comm_allgatherv(c, keys.data(), 16 * ng, cnt);
+        std::vector<long> gptr(world + 1, 0);
+        for (int r = 0; r < world; r++) gptr[r + 1] = gptr[r] + cnt[r] / 16;
+        std::vector<long> cptr(world + 1, 0);
+        pck(pnp_part_claim(P, l, gptr.data(), (const unsigned long long*)allk.data(), cptr.data(), nullptr));
+        std::vector<long> blob(world + 1 + cptr[world]); // claim_ptr followed by claim_pos
+        pck(pnp_part_claim(P, l, gptr.data(), (const unsigned long long*)allk.data(), blob.data(), blob.data() + world + 1));
+        std::vector<unsigned char> allc = comm_allgatherv(c, blob.data(), (long)(blob.size() * sizeof(long)), cnt);
+        std::vector<long> mptr(world + 1, 0), mpos;
+        size_t off = 0;
+        for (int r = 0; r < world; r++) {
+          const long* b = (const long*)(allc.data() + off);
+          mpos.insert(mpos.end(), b + world + 1 + b[me], b + world + 1 + b[me + 1]);
+          mptr[r + 1] = (long)mpos.size();
+          off += cnt[r];
+        }
+        mpos.push_back(0);
+        pck(pnp_part_finalize(P, l, mptr.data(), mpos.data()));
+      } else pck(pnp_part_finalize(P, l, nullptr, nullptr));
+    }
+    // nodal fields: injection at field_level, P1 interpolation upwards
+    std::vector<double> f_fine;
+    if (nfields > 0) {
+      std::unordered_map<Key2, long, Key2Hash> at;
+      at.reserve((size_t)nf * 2);
+      for (long i = 0; i < nf; i++) at[Key2{dbits(fx[i]), dbits(fy[i])}] = i;
+      const PartLevel& L0 = P->L[field_level];
+      long nvl = (long)L0.x.size();
+      std::vector<double> f((size_t)nfields * nvl);
+      for (long v = 0; v < nvl; v++) {
+        auto it = at.find(Key2{dbits(L0.x[v]), dbits(L0.y[v])});
+        PNP_REQUIRE(it != at.end(), PNP_E_ARG, "a vertex of the field level has no counterpart in the given field");
+        for (int k = 0; k < nfields; k++) f[(size_t)k * nvl + v] = fields[(size_t)k * nf + it->second];
+      }
+      for (int l = field_level + 1; l <= levels; l++) {
+        const PartLevel& L = P->L[l];
+        const long nvf = (long)L.x.size();
+        std::vector<double> g((size_t)nfields * nvf);
+        for (long v = 0; v < nvf; v++)
+          for (int k = 0; k < nfields; k++) {
+            const double a0 = f[(size_t)k * nvl + L.par0[v]];
+            g[(size_t)k * nvf + v] = L.par1[v] < 0 ? a0 : 0.5 * (a0 + f[(size_t)k * nvl + L.par1[v]]);
+          }
+        f.swap(g); nvl = nvf;
+      }
+      f_fine.swap(f);
+    }
+    // library-side hierarchy: root <- finest level; one child context per coarser distributed level; the replica
+    auto set_level = [&](pnp_ctx* h, const PartLevel& L) {
+      Ctx& k = h->c;
+      mesh_set(k, (long)L.x.size(), L.x.data(), L.y.data(), (long)L.tri.size() / 3, L.tri.data(), (long)L.ba.size(), L.ba.data(),
+               L.bb.data(), L.lm.bphys.data(), L.n_own);
+      halo_set(k, (int)L.nbr.size(), L.nbr.data(), L.send_ptr.data(), L.send_idx.data(), L.recv_ptr.data());
+      mesh_finalize(k, true); // (builds the constraints as well: the parameters are set)
+    };
+    set_level(root, P->L[levels]);
+    auto cck = [&](pnp_status s_, pnp_ctx* h) { if (s_ != PNP_OK) throw Error(s_, h->c.err); };
+    for (int l = levels - 1; l >= replica_level; l--) {
+      pnp_ctx* ch = nullptr;
+      cck(pnp_ctx_create_child(root, &ch), root);
+      c.owned_children.push_back(ch);
+      set_level(ch, P->L[l]);
+      cck(pnp_mg_push_level(root, ch, P->L[l + 1].par0.data(), P->L[l + 1].par1.data()), root);
+    }
+    {
+      pnp_ctx* rep = nullptr;
+      cck(pnp_ctx_create_child(root, &rep), root);
+      c.owned_children.push_back(rep);
+      Ctx& rc = rep->c;
+      mesh_set(rc, gnv, gx.data(), gy.data(), gnT, gtri.data(), gnB, gba.data(), gbb.data(), gph.data(), gnv);
+      std::vector<int> gid;
+      long n_global = gnv;
+      const PartLevel& LR = P->L[replica_level];
+      if (replica_level == 0) gid = LR.gid;
+      else { // vertices of the refined replica are matched by their (bitwise equal) coordinates
+        mesh_refine(rc, replica_level);
+        std::vector<double> rx = rc.cx.to_host(c.stream), ry = rc.cy.to_host(c.stream);
+        std::unordered_map<Key2, long, Key2Hash> at;
+        at.reserve(rx.size() * 2);
+        for (size_t i = 0; i < rx.size(); i++) at[Key2{dbits(rx[i]), dbits(ry[i])}] = (long)i;
+        gid.resize(LR.x.size());
+        for (size_t v = 0; v < LR.x.size(); v++) {
+          auto it = at.find(Key2{dbits(LR.x[v]), dbits(LR.y[v])});
+          PNP_REQUIRE(it != at.end(), PNP_E_MESH, "replica level does not contain a vertex of the distributed level");
+          gid[v] = (int)it->second;
+        }
+        n_global = (long)rx.size();
+      }
+      mesh_finalize(rc, true);
+      cck(pnp_mg_set_coarse_replica(root, rep, gid.data(), n_global), root);
+    }
+    if (nfields > 0) {
+      cck(pnp_vec_create(root, nfields, start_vec), root);
+      vec_upload(c, c.vec(*start_vec), f_fine.data());
+    }
+    pnp_part_destroy(P);
+    return PNP_OK;
+  } catch (const pnp::Error& e) { c.err = e.what(); if (P) pnp_part_destroy(P); return e.code; }
+  catch (const std::exception& e) { c.err = e.what(); if (P) pnp_part_destroy(P); return PNP_E_ARG; }
+}
+
 } // extern "C"

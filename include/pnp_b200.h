@@ -89,6 +89,12 @@ pnp_status pnp_mesh_set_local(pnp_ctx*, long nv, long n_own, const double* x, co
 pnp_status pnp_mesh_owned(pnp_ctx*, long* n_own);
 pnp_status pnp_comm_unique_id(char* out128);                 /* ncclGetUniqueId on rank 0, broadcast by the launcher */
 pnp_status pnp_comm_init(pnp_ctx*, int rank, int world, const char* unique_id128);
+/* the same with the id passed through a file every rank can see (a C++ driver started by any process launcher, no MPI):
+ * rank 0 writes it, the others wait for it */
+pnp_status pnp_comm_init_file(pnp_ctx*, int rank, int world, const char* path);
+/* all-gather of byte blocks of different lengths over the context's communicator (set-up plumbing: the two exchanges of
+ * pnp_part_*): counts[world]; recv == NULL: sizes only */
+pnp_status pnp_comm_allgatherv(pnp_ctx*, const void* send, long nbytes, void* recv, long cap, long* counts);
 pnp_status pnp_halo_set(pnp_ctx*, int n_nbr, const int* nbr, const int* send_ptr, const int* send_idx, const int* recv_ptr);
 pnp_status pnp_halo_exchange(pnp_ctx*, int vec_handle);       /* refresh the ghost part of a vector */
 /* distributed geometric multigrid: a child context (same stream and communicator) holds this rank's part of a coarser
@@ -132,6 +138,14 @@ pnp_status pnp_part_finalize(pnp_part*, int level, const long* mine_ptr /* world
 pnp_status pnp_part_sizes(pnp_part*, int level, long* sizes);
 pnp_status pnp_part_get(pnp_part*, int level, double* x, double* y, int* tri, int* ba, int* bb, int* bphys, int* nbr,
                         int* send_ptr, int* send_idx, int* recv_ptr, int* par0, int* par1, int* gid);
+/* The whole decomposition in one call (a driver without a Python launcher: PnpSolverMain::run with N ranks).  `root` holds
+ * the GLOBAL coarse mesh, the parameters and an initialised communicator on every rank; afterwards it holds this rank's part
+ * of the mesh refined `levels` times, the coarser levels are its multigrid levels down to `replica_level`, and a replica of the
+ * whole mesh continues below on every rank.  The level contexts belong to root.  Optional nodal fields given on the
+ * unpartitioned mesh of refinement level `field_level` (values [nfields][nf] at vertices (fx, fy)[nf], e.g. a coarse solution)
+ * are injected there by coordinate match and P1-interpolated to the finest level into a new vector *start_vec. */
+pnp_status pnp_partition_build(pnp_ctx* root, int levels, int replica_level, int field_level, int nfields, long nf,
+                               const double* fx, const double* fy, const double* fields, int* start_vec);
 /* uniform red refinement on the device (synthetic large meshes; rule in DESIGN.md) */
 pnp_status pnp_mesh_refine(pnp_ctx*, int levels);
 /* nested iteration: pnp_carry_set() stores vectors in reference numbering; every later pnp_mesh_refine() level

@@ -50,6 +50,27 @@ class Grid {
   void globalRefine(int levels) { check(c_, pnp_mesh_refine(c_, levels)); }
   void finalize(bool renumber = true) { check(c_, pnp_mesh_finalize(c_, renumber)); }
   long size() const { long nv = 0; pnp_mesh_sizes(c_, &nv, nullptr, nullptr, nullptr); return nv; }
+  long ownedSize() const { long n = 0; pnp_mesh_owned(c_, &n); return n; }
+  // MPIHelper + grid->loadBalance() (pnp_solver_main.cc:93-108): one process per GPU.  The NCCL id travels through a file
+  // all ranks see (no MPI needed); loadBalance partitions the Gmsh mesh this grid holds, refines this rank's part `levels`
+  // times and registers the coarser levels as multigrid levels (replicated below `replicaLevel`).
+  void initCommunication(int rank, int world, const std::string& rendezvousFile) {
+    check(c_, pnp_comm_init_file(c_, rank, world, rendezvousFile.c_str()));
+  }
+  // returns the handle of a start vector when a field was given (its values on the unpartitioned level `fieldLevel` mesh)
+  int loadBalance(int levels, int replicaLevel, int fieldLevel = 0, int nfields = 0, const std::vector<double>* fx = nullptr,
+                  const std::vector<double>* fy = nullptr, const std::vector<double>* fields = nullptr) {
+    int start = -1;
+    check(c_, pnp_partition_build(c_, levels, replicaLevel, fieldLevel, nfields, fx ? (long)fx->size() : 0, fx ? fx->data() : nullptr,
+                                  fy ? fy->data() : nullptr, fields ? fields->data() : nullptr, &start));
+    return start;
+  }
+  std::vector<double> coordinates(int which) const { // 0: x, 1: y (reference numbering)
+    std::vector<double> v(size());
+    check(c_, which == 0 ? pnp_mesh_get(c_, v.data(), nullptr, nullptr, nullptr, nullptr, nullptr)
+                         : pnp_mesh_get(c_, nullptr, v.data(), nullptr, nullptr, nullptr, nullptr));
+    return v;
+  }
   pnp_ctx* ctx() const { return c_; }
  private:
   pnp_ctx* c_ = nullptr;
@@ -62,6 +83,7 @@ class Vector {
     check(g.ctx(), pnp_vec_create(g.ctx(), fields, &h_));
     if (value != 0.0) check(g.ctx(), pnp_vec_set(g.ctx(), h_, value));
   }
+  Vector(Grid& g, int fields, int existingHandle, bool) : g_(g), fields_(fields), h_(existingHandle) {} // adopts a library-made vector
   ~Vector() { pnp_vec_destroy(g_.ctx(), h_); }
   Vector(const Vector&) = delete;
   void set(const std::vector<double>& host) { check(g_.ctx(), pnp_vec_upload(g_.ctx(), h_, host.data())); }
