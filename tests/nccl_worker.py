@@ -119,7 +119,9 @@ def main():
     # 4b. monolithic PNP Newton from the oracle's interpolate(BCExtension) state, CONVERGED (reduction 1e-11, linear
     # reduction 1e-9: with pore.cfg's own 1e-9 / 1e-8 the last Newton step is decided by how far the two linear solvers
     # overshoot their tolerance -- the multigrid run stopped after 3 steps where the ILU0 run took 4)
-    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_ILU0); opts[12] = 20000
+    # exact-derivative Jacobian on both sides: the forward differences' noise (~1e-5 relative in the entries) decides
+    # whether a tight run needs one Newton step more or less (measured here: 4 against 5)
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_ILU0, jac_mode=1); opts[12] = 20000
     opts[0], opts[2] = 1e-11, 1e-9
     pb_g, _ = ora.newton(gm, p, ora.OP_PB, np.zeros(gm.nv), opts)
     u0_g = np.concatenate([ora.interpolate(gm, p, k, pb_g) for k in range(3)])
