@@ -420,10 +420,10 @@ def run_gpu(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     # algorithmic bytes of one fine-level 3-field SpMV (DESIGN.md "SpMV"): 7 value planes + column index per
     # slot, row pointer + x read + y written per vertex
-    # per epilogue kind: plain y = A x; residual also reads b (24 B/vertex); a smoother step reads b and its own x row
-    # (24 + 24 B/vertex; the 3x3 inverse diagonal block is computed in the kernel from the diagonal slot, not read)
+    # per epilogue kind: plain y = A x; residual and smoother step also read b (24 B/vertex).  The smoother's own x row is part
+    # of the x read, and its 3x3 inverse diagonal block is computed in the kernel from the diagonal slot, not read.
     base = (7 * 8 + 4) * ns + (4 + 2 * 3 * 8) * n_own   # rank 0's share
-    kind_bytes = [base, base + 24 * n_own, base + 48 * n_own]
+    kind_bytes = [base, base + 24 * n_own, base + 24 * n_own]
     spmv_total_bytes = sum(b * n for b, n in zip(kind_bytes, n_spmv))
     spmv_ms_by_kind, n_spmv_by_kind = spmv_ms, n_spmv
     spmv_ms, n_spmv = sum(spmv_ms), sum(n_spmv)
@@ -460,13 +460,15 @@ def run_gpu(args, rank, world, local_rank):
         "spmv_by_kind": {k: {"launches": n, "avg_ms": (m / n if n else None), "bytes": b} for k, n, m, b in
                          zip(["plain", "residual", "smoother"], n_spmv_by_kind, spmv_ms_by_kind, kind_bytes)}, "spmv_share_of_step": spmv_ms / 1e3 / max(sec_dev, 1e-30),
         "setup_s": t_setup, "wall_s": wall,
-        "roofline": {"bound": "hbm", "kernel": "3-field SpMV on the vertex-star layout, fine level (k_star_op<7,EPI,NDOT>, all epilogues)",
+        "roofline": {"bound": "hbm", "kernel": "3-field SpMV on the vertex-star layout, fine level (k_star_op_tma<7,EPI,NDOT,2>: bulk-copy "
+                               "pipeline, all epilogues -- plain / dots, residual, smoother step)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this size (plain
-                     # epilogue: 21.56 GB read + 1.13 GB written against 22.22 GB algorithmic); other sizes: not captured
-                     "traffic": 22.69e9 if (world == 1 and args.levels == 7) else None,
-                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k_star_op<7,0,0> at k = 7 "
-                                       "(profiles/hot_kernels_full_r01d_summary.txt); algorithmic bytes of that epilogue: 22.22e9",
+                     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this size (smoother
+                     # epilogue, 59 % of the launches: 22.37 GB read + 1.13 GB written against 23.34 GB algorithmic; residual
+                     # epilogue 22.41 + 1.13 GB); other sizes: not captured
+                     "traffic": 23.50e9 if (world == 1 and args.levels == 7) else None,
+                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k_star_op_tma<7,2,0,2> at k = 7 "
+                                       "(profiles/hot_kernels_full_r02_summary.txt); algorithmic bytes of that epilogue: 23.34e9",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,  # launch-weighted mean over the epilogue kinds
                      "avg_launch_ms": spmv_avg_s * 1e3,
                      # the WHOLE step: algorithmic bytes of every kernel launched in the timed region (all ranks), by class,
