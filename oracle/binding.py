@@ -38,6 +38,7 @@ def lib():
         L.ora_pattern.restype = C.c_long
         L.ora_pattern_sets.restype = C.c_long
         L.ora_bench_create.restype = C.c_void_p
+        L.ora2_pattern.restype = C.c_long
         L.ora_bench_nnz.restype = C.c_long
         L.ora_set_threads(1)
         _LIB = L
@@ -304,3 +305,71 @@ def sinh_shared(x):
     x = _f64(x); y = np.zeros_like(x)
     lib().ora_sinh_shared(len(x), _d(x), _d(y))
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# quadratic elements (PDEGREE = 2, pnp_oracle_p2.hpp): dofs = edges [0, nE) then vertices [nE, nE + nv); fields lexicographic
+# ---------------------------------------------------------------------------------------------------------------
+class P2:
+    def __init__(self, mesh, params):
+        self.mesh, self.params = mesh, params
+        sz = (C.c_long * 2)()
+        _chk(lib().ora2_sizes(mesh.h, params.h, sz))
+        self.nE, self.nd = int(sz[0]), int(sz[1])
+        self.eva = np.zeros(self.nE, dtype=np.int32); self.evb = np.zeros(self.nE, dtype=np.int32)
+        self.tedge = np.zeros((mesh.nT, 3), dtype=np.int32)
+        self.x = np.zeros(self.nd); self.y = np.zeros(self.nd)
+        _chk(lib().ora2_space(mesh.h, params.h, _i(self.eva), _i(self.evb), _i(self.tedge), _d(self.x), _d(self.y)))
+
+    def dirichlet(self, fields, comp0=0):
+        out = np.zeros(fields * self.nd, dtype=np.int8)
+        _chk(lib().ora2_dirichlet(self.mesh.h, self.params.h, fields, comp0, out.ctypes.data_as(C.c_char_p)))
+        return out.astype(bool)
+
+    def pattern(self, fields, comp0=0):
+        rowptr = np.zeros(fields * self.nd + 1, dtype=np.int32)
+        nnz = _chk(lib().ora2_pattern(self.mesh.h, self.params.h, fields, comp0, _i(rowptr), None))
+        col = np.zeros(nnz, dtype=np.int32)
+        _chk(lib().ora2_pattern(self.mesh.h, self.params.h, fields, comp0, _i(rowptr), _i(col)))
+        return rowptr, col
+
+    def residual(self, op, u, aux0=None, aux1=None, valency=1.0, intorder=-1, comp0=0, want_abs=False):
+        u = _f64(u); aux0 = _f64(aux0); aux1 = _f64(aux1)
+        r = np.zeros_like(u); ab = np.zeros_like(u) if want_abs else None
+        _chk(lib().ora2_residual(self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
+                                 _d(r), _d(ab)))
+        return (r, ab) if want_abs else r
+
+    def jacobian(self, op, u, aux0=None, aux1=None, valency=1.0, intorder=-1, comp0=0, mode=0, eps=1e-11, want_abs=False):
+        u = _f64(u); aux0 = _f64(aux0); aux1 = _f64(aux1)
+        rowptr, col = self.pattern(nfields(op), comp0)
+        val = np.zeros(len(col)); ab = np.zeros(len(col)) if want_abs else None
+        _chk(lib().ora2_jacobian(self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
+                                 mode, C.c_double(eps), _d(val), _d(ab)))
+        return (rowptr, col, val, ab) if want_abs else (rowptr, col, val)
+
+    def interpolate(self, comp, pb=None):
+        pb = _f64(pb)
+        u = np.zeros(self.nd)
+        _chk(lib().ora2_interpolate(self.mesh.h, self.params.h, comp, _d(pb), _d(u)))
+        return u
+
+    def newton(self, op, u0, opts, aux0=None, aux1=None, valency=1.0, intorder=-1, comp0=0, cap=128):
+        u = _f64(u0).copy(); aux0 = _f64(aux0); aux1 = _f64(aux1)
+        res = np.zeros(16); hist = np.zeros(cap); lin = np.zeros(cap, dtype=np.int32)
+        _chk(lib().ora2_newton(self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
+                               _d(_f64(opts)), _d(res), _d(hist), _i(lin), cap))
+        keys = ["status", "converged", "iterations", "first_defect", "defect", "reduction", "total_linear_iterations",
+                "total_ls_trials", "jacobian_assemblies", "residual_assemblies", "seconds"]
+        out = dict(zip(keys, res[:11]))
+        for k in ("status", "iterations", "total_linear_iterations", "total_ls_trials", "jacobian_assemblies", "residual_assemblies"):
+            out[k] = int(out[k])
+        out["converged"] = bool(out["converged"])
+        out["defect_history"] = hist[hist >= 0].copy(); out["lin_iter_history"] = lin[lin >= 0].copy()
+        return u, out
+
+
+def p2_basis(x, y):
+    phi = np.zeros(6); g = np.zeros(12)
+    lib().ora2_basis(C.c_double(x), C.c_double(y), _d(phi), _d(g))
+    return phi, g.reshape(6, 2)

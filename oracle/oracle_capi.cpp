@@ -1,6 +1,7 @@
 // oracle_capi.cpp -- C entry points of the CPU ORACLE for ctypes (test infrastructure only;
 // see the header of pnp_oracle.hpp).  Nothing under dune_pnp_b200/ may link or load this.
 #include "pnp_oracle.hpp"
+#include "pnp_oracle_p2.hpp"
 #include <chrono>
 #include <cstring>
 
@@ -344,5 +345,109 @@ int ora_assembly_par(void* mh, void* ph, int op, const double* u, int threads, i
 }
 
 void ora_sinh_shared(int n, const double* x, double* y) { for (int i = 0; i < n; i++) y[i] = sinh_shared(x[i]); }
+
+// ---- quadratic elements (PDEGREE = 2): pnp_oracle_p2.hpp ----
+static OpCtx make_ctx2(const Mesh* m, const Sysparams* s, int op, const double* a0, const double* a1, double valency, int intorder) {
+  return make_ctx(m, s, op, a0, a1, valency, intorder); // (coefficient vectors are P2 vectors of length nE + nv here)
+}
+// sizes[2] = {nE, scalar dofs}
+int ora2_sizes(void* mh, void* ph, long* sizes) {
+  ORA_TRY
+  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
+  sizes[0] = sp.nE; sizes[1] = sp.nd;
+  return 0;
+  ORA_CATCH(-1)
+}
+// edges (end vertices), element -> local edge index, coordinates of the scalar dofs
+int ora2_space(void* mh, void* ph, int* eva, int* evb, int* tedge, double* dx, double* dy) {
+  ORA_TRY
+  const Mesh& m = *(Mesh*)mh;
+  p2::Space2 sp = p2::make_space2(m, ((Params*)ph)->s, 1, 0);
+  if (eva) std::copy(sp.eva.begin(), sp.eva.end(), eva);
+  if (evb) std::copy(sp.evb.begin(), sp.evb.end(), evb);
+  if (tedge) std::copy(sp.tedge.begin(), sp.tedge.end(), tedge);
+  if (dx && dy) {
+    for (int k = 0; k < sp.nE; k++) { dx[k] = 0.5 * (m.x[sp.eva[k]] + m.x[sp.evb[k]]); dy[k] = 0.5 * (m.y[sp.eva[k]] + m.y[sp.evb[k]]); }
+    for (int v = 0; v < m.nv; v++) { dx[sp.nE + v] = m.x[v]; dy[sp.nE + v] = m.y[v]; }
+  }
+  return 0;
+  ORA_CATCH(-1)
+}
+int ora2_dirichlet(void* mh, void* ph, int fields, int comp0, char* out) {
+  ORA_TRY
+  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
+  std::copy(sp.dirichlet.begin(), sp.dirichlet.end(), out);
+  return 0;
+  ORA_CATCH(-1)
+}
+long ora2_pattern(void* mh, void* ph, int fields, int comp0, int* rowptr, int* col) {
+  ORA_TRY
+  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
+  CSR A = p2::make_pattern2(sp);
+  if (rowptr) std::copy(A.rowptr.begin(), A.rowptr.end(), rowptr);
+  if (col) std::copy(A.col.begin(), A.col.end(), col);
+  return (long)A.col.size();
+  ORA_CATCH(-1)
+}
+int ora2_residual(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
+                  int intorder, double* r, double* absr) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  p2::Space2 sp = p2::make_space2(*m, *s, op_fields(op), comp0);
+  OpCtx c = make_ctx2(m, s, op, aux0, aux1, valency, intorder);
+  p2::residual2(sp, c, u, r, absr);
+  return 0;
+  ORA_CATCH(-1)
+}
+int ora2_jacobian(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
+                  int intorder, int mode, double eps, double* val, double* absval) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  p2::Space2 sp = p2::make_space2(*m, *s, op_fields(op), comp0);
+  OpCtx c = make_ctx2(m, s, op, aux0, aux1, valency, intorder);
+  CSR A = p2::make_pattern2(sp);
+  std::vector<double> ab;
+  p2::jacobian2(sp, c, u, A, mode, eps, absval ? &ab : nullptr);
+  std::copy(A.val.begin(), A.val.end(), val);
+  if (absval) std::copy(ab.begin(), ab.end(), absval);
+  return 0;
+  ORA_CATCH(-1)
+}
+int ora2_interpolate(void* mh, void* ph, int comp, const double* pb, double* u) {
+  ORA_TRY
+  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, comp);
+  p2::interpolate_bcext2(sp, comp, pb, u);
+  return 0;
+  ORA_CATCH(-1)
+}
+int ora2_newton(void* mh, void* ph, int op, int comp0, double* u, const double* aux0, const double* aux1, double valency,
+                int intorder, const double* opts, double* result, double* hist, int* lin_hist, int cap) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  p2::Space2 sp = p2::make_space2(*m, *s, op_fields(op), comp0);
+  OpCtx c = make_ctx2(m, s, op, aux0, aux1, valency, intorder);
+  NewtonOpts o;
+  o.reduction = opts[0]; o.abs_limit = opts[1]; o.min_linear_reduction = opts[2]; o.reassemble_threshold = opts[3];
+  o.maxit = (int)opts[4]; o.ls_maxit = (int)opts[5]; o.damping = opts[6]; o.jac_mode = (int)opts[7]; o.fd_eps = opts[8];
+  o.solver = (int)opts[9]; o.prec = (int)opts[10]; o.prec_steps = (int)opts[11]; o.lin_maxit = (int)opts[12];
+  o.verbosity = (int)opts[13]; o.line_search = (int)opts[14];
+  auto t0 = std::chrono::steady_clock::now();
+  NewtonResult R = newton_core(sp.N(), p2::make_pattern2(sp), [&](const double* uu, double* r) { p2::residual2(sp, c, uu, r); },
+                               [&](const double* uu, CSR& A) { p2::jacobian2(sp, c, uu, A, o.jac_mode, o.fd_eps); }, u, o);
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  double v[11] = {(double)R.status, (double)R.converged, (double)R.iterations, R.first_defect, R.defect, R.reduction,
+                  (double)R.total_linear_iterations, (double)R.total_ls_trials, (double)R.jacobian_assemblies,
+                  (double)R.residual_assemblies, sec};
+  std::copy(v, v + 11, result);
+  if (hist) for (int i = 0; i < cap; i++) hist[i] = i < (int)R.defect_history.size() ? R.defect_history[i] : -1.0;
+  if (lin_hist) for (int i = 0; i < cap; i++) lin_hist[i] = i < (int)R.lin_iter_history.size() ? R.lin_iter_history[i] : -1;
+  return 0;
+  ORA_CATCH(-1)
+}
+void ora2_basis(double x, double y, double* phi, double* grad) {
+  p2::basis(x, y, phi);
+  double g[6][2]; p2::basis_grad(x, y, g);
+  for (int i = 0; i < 6; i++) { grad[2 * i] = g[i][0]; grad[2 * i + 1] = g[i][1]; }
+}
 
 } // extern "C"

@@ -1049,11 +1049,12 @@ struct NewtonResult {
   std::vector<double> defect_history; std::vector<int> lin_iter_history;
 };
 
-inline NewtonResult newton(const Space& sp, const OpCtx& c, double* u, const NewtonOpts& o) {
-  int N = sp.N(); NewtonResult R;
+// the Newton loop itself, for any space: residual_fn(u, r), jacobian_fn(u, A) on the pattern A
+template <class ResidualFn, class JacobianFn>
+inline NewtonResult newton_core(int N, CSR A, ResidualFn residual_fn, JacobianFn jacobian_fn, double* u, const NewtonOpts& o) {
+  NewtonResult R;
   std::vector<double> r(N), z(N), prev_u(N);
-  CSR A = make_pattern(sp);
-  auto defect = [&]() { residual(sp, c, u, r.data()); R.residual_assemblies++; return nrm2(N, r.data()); };
+  auto defect = [&]() { residual_fn(u, r.data()); R.residual_assemblies++; return nrm2(N, r.data()); };
   R.defect = defect(); R.first_defect = R.defect; double prev_defect = R.defect;
   R.defect_history.push_back(R.defect);
   if (!std::isfinite(R.defect)) { R.status = 4; return R; }
@@ -1066,7 +1067,7 @@ inline NewtonResult newton(const Space& sp, const OpCtx& c, double* u, const New
     // prepare_step
     bool reassembled = false;
     if (R.defect / prev_defect > reassemble_threshold || R.jacobian_assemblies == 0) {
-      jacobian(sp, c, u, A, o.jac_mode, o.fd_eps); R.jacobian_assemblies++; reassembled = true;
+      jacobian_fn(u, A); R.jacobian_assemblies++; reassembled = true;
     }
     double stop_defect = std::max(R.first_defect * o.reduction, o.abs_limit);
     double linear_reduction;
@@ -1114,6 +1115,10 @@ inline NewtonResult newton(const Space& sp, const OpCtx& c, double* u, const New
     (void)reassembled;
   }
   return R;
+}
+inline NewtonResult newton(const Space& sp, const OpCtx& c, double* u, const NewtonOpts& o) {
+  return newton_core(sp.N(), make_pattern(sp), [&](const double* uu, double* r) { residual(sp, c, uu, r); },
+                     [&](const double* uu, CSR& A) { jacobian(sp, c, uu, A, o.jac_mode, o.fd_eps); }, u, o);
 }
 
 // StationaryLinearProblemSolver::apply (App. A.9): one Newton step without line search

@@ -1,0 +1,138 @@
+"""CPU tests of the oracle's quadratic-element path (oracle/pnp_oracle_p2.hpp; the reference's -DPDEGREE=2 build,
+src/Makefile.am:57-110).  Parity unpinned like the P1 oracle; pins: Lagrange / partition-of-unity properties of the
+restated Pk2DLocalBasis, patch test (a quadratic harmonic function is reproduced exactly), FD vs exact derivative, Euler's
+formula for the dof count, the constraint rule (end vertices AND the edge dof of a Dirichlet face), and the convergence order
+(P2 gains a factor ~8 per refinement in the vertex values where P1 gains ~4)."""
+import numpy as np
+import pytest
+
+import util
+from oracle import binding as ora
+
+
+def case(name, levels=0):
+    m = ora.Mesh.from_arrays(**util.load_mesh_arrays(name)).refine(levels)
+    p = ora.Params.read(util.cfg_path(name))
+    return m, p, ora.P2(m, p)
+
+
+def test_basis_is_the_quadratic_lagrange_basis():
+    nodes = [(0, 0), (.5, 0), (1, 0), (0, .5), (.5, .5), (0, 1)]   # vertex0, edge0, vertex1, edge1, edge2, vertex2
+    for k, (x, y) in enumerate(nodes):
+        phi, _ = ora.p2_basis(x, y)
+        assert np.allclose(phi, np.eye(6)[k], atol=1e-15)
+    rng = np.random.RandomState(0)
+    for x, y in rng.uniform(0, 0.5, (20, 2)):
+        phi, g = ora.p2_basis(x, y)
+        assert abs(phi.sum() - 1) < 1e-14 and np.allclose(g.sum(0), 0, atol=1e-13)
+        h = 1e-6
+        px, _ = ora.p2_basis(x + h, y); mx, _ = ora.p2_basis(x - h, y)
+        py, _ = ora.p2_basis(x, y + h); my, _ = ora.p2_basis(x, y - h)
+        assert np.allclose((px - mx) / (2 * h), g[:, 0], atol=1e-8) and np.allclose((py - my) / (2 * h), g[:, 1], atol=1e-8)
+        # quadratics are reproduced: sum_i q(node_i) phi_i = q
+        q = lambda a, b: 1 + 2 * a - b + 3 * a * a - a * b + 0.5 * b * b  # noqa: E731
+        assert abs(sum(q(*n) * phi[i] for i, n in enumerate(nodes)) - q(x, y)) < 1e-13
+
+
+@pytest.mark.parametrize("name", util.MESHES)
+def test_dof_numbering_pattern_and_constraints(name):
+    m, p, P = case(name)
+    assert m.nv - P.nE + m.nT == 1                      # Euler (simply connected 2-D meshes)
+    assert P.nd == P.nE + m.nv
+    # edges are numbered by (min vertex, max vertex)
+    keys = (P.eva.astype(np.int64) << 32) | P.evb
+    assert np.all(np.diff(keys) > 0) and np.all(P.eva < P.evb)
+    for F, comp0 in ((1, 0), (1, 1), (3, 0)):
+        d = P.dirichlet(F, comp0)
+        d1 = ora.dirichlet(m, p, F, comp0)             # P1 constraints: the vertex part must agree
+        for k in range(F):
+            assert np.array_equal(d[k * P.nd + P.nE:(k + 1) * P.nd], d1[k * m.nv:(k + 1) * m.nv])
+            # an edge dof is constrained iff it is a boundary face whose surface is Dirichlet for the component
+            de = d[k * P.nd:k * P.nd + P.nE]
+            comp = k if F == 3 else comp0
+            want = np.zeros(P.nE, dtype=bool)
+            bkey = (np.minimum(m.ba, m.bb).astype(np.int64) << 32) | np.maximum(m.ba, m.bb)
+            pos = np.searchsorted(keys, bkey)
+            want[pos] = p.surf[m.bphys, 3 * comp] == 0
+            assert np.array_equal(de, want)
+        rp, col = P.pattern(F, comp0)
+        assert rp[-1] == len(col) and np.all(np.diff(rp) >= 1)
+        for r in (0, len(rp) // 2, len(rp) - 2):        # columns ascending, diagonal present
+            c = col[rp[r]:rp[r + 1]]
+            assert np.all(np.diff(c) > 0) and r in c
+        assert np.all(np.diff(rp)[d] == 1)              # constrained rows: diagonal only
+
+
+def test_patch_test_quadratic_harmonic_function():
+    """Laplace (Poisson operator with c+ = c-) on cylinder.msh: u = x^2 - y^2 lies in the P2 space and is harmonic, so the
+    residual vanishes at every dof whose support does not touch the boundary (there the Neumann flux term is missing)."""
+    m, p, P = case("cylinder")
+    u = P.x ** 2 - P.y ** 2
+    z = np.zeros(P.nd)
+    r, ab = P.residual(ora.OP_POISSON, u, z, z, want_abs=True)
+    bv = np.zeros(m.nv, bool); bv[m.ba] = True; bv[m.bb] = True
+    interior = np.ones(P.nd, bool)
+    interior[P.nE:][bv] = False
+    interior[:P.nE][bv[P.eva] | bv[P.evb]] = False
+    assert interior.sum() > 100 and np.max(np.abs(r[interior]) / ab[interior]) < 1e-10
+    # P1 would not: the same function interpolated linearly leaves an O(h^2) residual -- so the test has teeth
+    r1, ab1 = ora.residual(m, p, ora.OP_POISSON, m.x ** 2 - m.y ** 2, np.zeros(m.nv), np.zeros(m.nv), want_abs=True)
+    assert np.max(np.abs(r1[~bv]) / ab1[~bv]) > 1e-4
+
+
+@pytest.mark.parametrize("op", [ora.OP_PB, ora.OP_POISSON, ora.OP_DIFFUSION, ora.OP_MASS, ora.OP_PNP])
+def test_fd_jacobian_agrees_with_exact_derivative(op):
+    m, p, P = case("pore_small")
+    rng = np.random.RandomState(1)
+    F = ora.nfields(op)
+    u = 0.3 * rng.uniform(-1, 1, F * P.nd)
+    if op == ora.OP_PNP:
+        u[P.nd:] = 0.06 * (1 + 0.1 * rng.uniform(-1, 1, 2 * P.nd))
+    a0, a1 = rng.uniform(0, 1, P.nd), rng.uniform(0, 1, P.nd)
+    rp, col, v0 = P.jacobian(op, u, a0, a1, valency=-1.0, mode=0, eps=1e-7)
+    _, _, v1 = P.jacobian(op, u, a0, a1, valency=-1.0, mode=1)
+    assert np.max(np.abs(v0 - v1)) <= 1e-6 * np.max(np.abs(v1))
+    # J z ~ R(u + z) - R(u) on the free dofs
+    z = 1e-6 * rng.uniform(-1, 1, F * P.nd)
+    d = P.dirichlet(F, 0)
+    z[d] = 0
+    import scipy.sparse as sp
+    J = sp.csr_matrix((v1, col, rp))
+    lhs = P.residual(op, u + z, a0, a1, valency=-1.0) - P.residual(op, u, a0, a1, valency=-1.0)
+    assert np.linalg.norm((lhs - J @ z)[~d]) <= 1e-4 * np.linalg.norm((J @ z)[~d])
+
+
+def test_convergence_order_beats_linear_elements():
+    """PB Newton solve on one_wall.msh at three refinement levels: the vertex values of consecutive levels approach each other
+    by a factor ~8 per level with P2 (third order) and ~4 with P1."""
+    sols1, sols2 = [], []
+    for lev in (0, 1, 2):
+        m, p, P = case("one_wall", lev)
+        opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, jac_mode=1); opts[12] = 20000
+        opts[0], opts[2] = 1e-12, 1e-10
+        u2, r2 = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
+        u1, r1 = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+        assert r1["converged"] and r2["converged"]
+        sols1.append(u1); sols2.append(u2[P.nE:])
+    nv0 = len(sols1[0])
+    e1 = [np.linalg.norm(sols1[k][:nv0] - sols1[k + 1][:nv0]) for k in (0, 1)]   # refinement keeps the old vertices first
+    e2 = [np.linalg.norm(sols2[k][:nv0] - sols2[k + 1][:nv0]) for k in (0, 1)]
+    assert 2.5 < e1[0] / e1[1] < 6.0
+    assert e2[0] / e2[1] > 6.0 and e2[0] < 0.2 * e1[0]
+
+
+def test_interpolate_bcext_p2():
+    m, p, P = case("pore")
+    pb = np.sin(0.1 * P.x) * np.cos(0.07 * P.y)
+    for comp in range(3):
+        u = P.interpolate(comp, pb)
+        d = P.dirichlet(1, comp)
+        # vertex part equals the P1 interpolation of the vertex values (same rule, same element order)
+        u1 = ora.interpolate(m, p, comp, pb[P.nE:])
+        assert np.array_equal(u[P.nE:], u1)
+        free = ~d
+        want = pb if comp == 0 else 0.06 * np.exp(-pb if comp == 1 else pb)
+        # away from the boundary band the PB-derived guess
+        bv = np.zeros(m.nv, bool); bv[m.ba] = True; bv[m.bb] = True
+        inner = free.copy(); inner[P.nE:][bv] = False; inner[:P.nE][bv[P.eva] | bv[P.evb]] = False
+        assert np.allclose(u[inner], want[inner], rtol=1e-15)
