@@ -273,12 +273,12 @@ class Context:
         self._ck(lib().pnp_operator_set_valency(self._h, op, C.c_double(valency)))
 
     def constraints(self, op, fields):
-        out = np.zeros(fields * self.mesh_sizes()["nv"], dtype=np.int8)
+        out = np.zeros(fields * self.ndof(), dtype=np.int8)
         self._ck(lib().pnp_constraints_get(self._h, op, out.ctypes.data_as(C.c_char_p)))
         return out.astype(bool)
 
     def pattern(self, op, fields):
-        nv = self.mesh_sizes()["nv"]
+        nv = self.ndof()
         nnz = C.c_long(); rowptr = np.zeros(fields * nv + 1, dtype=np.int32)
         self._ck(lib().pnp_pattern_get(self._h, op, C.byref(nnz), _i(rowptr), None))
         col = np.zeros(nnz.value, dtype=np.int32)
@@ -300,7 +300,7 @@ class Context:
         self._ck(lib().pnp_vec_upload(self._h, v, _d(host)))
 
     def download(self, v, fields):
-        out = np.zeros(fields * self.mesh_sizes()["nv"])
+        out = np.zeros(fields * self.ndof())
         self._ck(lib().pnp_vec_download(self._h, v, _d(out)))
         return out
 
@@ -422,6 +422,25 @@ class Context:
     def mesh_renumber(self, new_index):
         new_index = np.ascontiguousarray(new_index, dtype=np.int32)
         self._ck(lib().pnp_mesh_renumber(self._h, _i(new_index)))
+
+    # ---- quadratic elements (-DPDEGREE=2) ----
+    def space_set_degree(self, degree):
+        self._ck(lib().pnp_space_set_degree(self._h, int(degree)))
+
+    def space_sizes(self):
+        deg = C.c_int(); nE = C.c_long(); nd = C.c_long()
+        self._ck(lib().pnp_space_sizes(self._h, C.byref(deg), C.byref(nE), C.byref(nd)))
+        return dict(degree=deg.value, n_edges=nE.value, ndof=nd.value)
+
+    def ndof(self):
+        """Scalar dofs per field: vertices (degree 1) or edges + vertices (degree 2)."""
+        return self.space_sizes()["ndof"]
+
+    def space_edges(self):
+        nE = self.space_sizes()["n_edges"]
+        va = np.zeros(nE, dtype=np.int32); vb = np.zeros(nE, dtype=np.int32)
+        self._ck(lib().pnp_space_edges(self._h, _i(va), _i(vb)))
+        return va, vb
 
     def interpolate_bcext(self, component, pb_vec, out_vec):
         self._ck(lib().pnp_interpolate_bcext(self._h, component, -1 if pb_vec is None else pb_vec, out_vec))

@@ -101,7 +101,9 @@ struct Matrix {
   int op = 0;
   int nplanes = 1;
   int comp0 = 0;  // BC component of the operator that assembled it (scalar operators)
-  DBuf<double> vals; // nplanes * nslots
+  DBuf<double> vals; // nplanes * nslots (star layout) or csr_nnz (quadratic elements)
+  // quadratic elements (pnp_p2.cu): scalar CSR in the reference's dof numbering; the pattern belongs to the space
+  const int* csr_rp = nullptr; const int* csr_col = nullptr; long csr_nnz = 0, csr_n = 0;
 };
 
 struct Operator {
@@ -132,6 +134,7 @@ struct MgLevelRef {
 };
 
 struct Amg; // pnp_amg.cu
+struct P2Space; // pnp_p2.cu
 struct SweepPrec; // pnp_precond.cu: level schedules of the SSOR / ILU0 sweeps, ILU0 factor
 
 struct Solver {
@@ -155,6 +158,12 @@ struct Ctx {
   // Rows exist for the first n_own vertices; on one GPU n_own == nv.  With a partitioned mesh the vertices
   // [n_own, nv) are ghosts: columns of owned rows whose values arrive by halo exchange (pnp_comm.cu).
   long n_own = 0;
+  // polynomial degree of the finite element space (PDEGREE of the reference's build): 1 = vertex-star layout, 2 = the
+  // edge + vertex dofs of pnp_p2.cu (p2_nd of them per field; vectors field-lexicographic, matrices CSR)
+  int degree = 1; long p2_nd = 0;
+  std::shared_ptr<P2Space> p2;
+  long rows() const { return degree == 2 ? p2_nd : n_own; } // dofs per field this rank owns
+  long cols() const { return degree == 2 ? p2_nd : nv; }    // ... and holds (owned + ghosts)
   int rank = 0, world = 1;
   void* nccl = nullptr;                 // ncclComm_t
   std::vector<int> halo_nbr, halo_send_ptr, halo_recv_ptr; // per neighbour rank: ranges into send list / ghost block
@@ -234,7 +243,7 @@ struct Ctx {
   std::vector<Vec> carry;              // nodal fields in reference numbering, interpolated by mesh_refine()
   // a new / refined mesh invalidates every object sized by it
   void invalidate_mesh_objects() {
-    finalized = false; constraints_built = false;
+    finalized = false; constraints_built = false; p2.reset(); p2_nd = 0;
     vecs.clear(); mats.clear(); ops.clear(); solvers.clear();
     last_u = nullptr; last_vals = nullptr;
     ws_r.d.release(); ws_z.d.release(); ws_prev.d.release(); ws_A.vals.release(); ws_B.vals.release();
@@ -306,6 +315,21 @@ LinResult solver_apply(Ctx&, Solver&, const Matrix& A, Vec& z, Vec& r, double re
 void precond_apply(Ctx&, Solver&, const Matrix& A, Vec& d, Vec& v); // v = M^-1 d (setup + one application)
 // pnp_precond.cu
 int sweep_levels(const Solver&, bool ilu);
+// pnp_p2.cu (quadratic elements)
+void p2_build(Ctx&);
+void p2_constraints(Ctx&);
+void p2_matrix_init(Ctx&, Matrix&, const Operator&);
+void p2_assemble_residual(Ctx&, const Operator&, Vec& u, Vec& r);
+void p2_assemble_jacobian(Ctx&, const Operator&, Vec& u, Matrix& A, int mode, double eps);
+void csr_spmv(Ctx&, const Matrix& A, const double* x, double* y);
+void csr_diag_inverse(Ctx&, const Matrix& A, double* dinv);
+const unsigned char* p2_dirichlet_flags(Ctx&); // per scalar dof: bit c = Dirichlet for BC component c (device)
+void p2_sizes(Ctx&, long* nE, long* nd);
+void p2_edges(Ctx&, int* eva, int* evb);
+void p2_constraints_get(Ctx&, const Operator&, char* out);
+long p2_pattern_export(Ctx&, const Operator&, int* rowptr, int* col);
+void p2_matrix_import(Ctx&, const Operator&, Matrix&, const int* rowptr, const int* col, const double* val);
+void p2_interpolate_bcext(Ctx&, int comp, const Vec* pb, Vec& out);
 // pnp_output.cu
 void ion_flux(Ctx&, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, double* im);
 void write_cell_data(Ctx&, const Vec& u, const std::string& filename);

@@ -1,0 +1,215 @@
+// pnp_elem_p2.cuh -- element-level fp64 math of the five local operators with QUADRATIC elements (the reference's
+// -DPDEGREE=2 build: /root/reference/src/Makefile.am:57-110; Pk2DLocalFiniteElementMap<GV,D,R,2>,
+// instationary_pnp_from_pb_md.hh:26-28,125).  The operator bodies are the reference's alpha_volume / alpha_boundary
+// (pnp_operator.hh:98-194, pb_operator.hh:74-120, poisson_operator.hh:74-126, diffusion_operator.hh:64-111,
+// diffusion_toperator.hh:58-72) evaluated for lfsu.size() = 6; __host__ __device__ like pnp_elem.cuh, compiled without FMA
+// contraction so that the FD Jacobian rounds like the CPU restatement.
+//
+// Local dof order (Pk2DLocalBasis<D,R,2>): Lagrange nodes (0,0),(1/2,0),(1,0),(0,1/2),(1/2,1/2),(0,1) =
+// vertex0, edge0=(v0,v1), vertex1, edge1=(v0,v2), edge2=(v1,v2), vertex2.
+#pragma once
+#include "pnp_elem.cuh"
+
+namespace pnp {
+namespace p2 {
+
+constexpr int NL = 6;
+
+PNP_HD bool node_is_edge(int i) { return i == 1 || i == 3 || i == 4; }
+PNP_HD int node_sub(int i) { return i == 0 ? 0 : (i == 1 ? 0 : (i == 2 ? 1 : (i == 3 ? 1 : 2))); } // local vertex / local edge
+PNP_HD double node_x(int i) { return i == 2 ? 1.0 : ((i == 1 || i == 4) ? 0.5 : 0.0); }
+PNP_HD double node_y(int i) { return i == 5 ? 1.0 : ((i == 3 || i == 4) ? 0.5 : 0.0); }
+
+// Pk2DLocalBasis<D,R,2>::evaluateFunction: node (i,j) -> prod_{a<i}(2x-a)/(i-a) prod_{b<j}(2y-b)/(j-b) prod_{g>i+j}(g-2x-2y)/(g-i-j)
+PNP_HD void basis(double x, double y, double* phi) {
+  const double s = 2 * x + 2 * y;
+  phi[0] = ((1 - s) / 1) * ((2 - s) / 2);
+  phi[1] = (2 * x) * ((2 - s) / 1);
+  phi[2] = (2 * x) * ((2 * x - 1) / 2);
+  phi[3] = (2 * y) * ((2 - s) / 1);
+  phi[4] = (2 * x) * (2 * y);
+  phi[5] = (2 * y) * ((2 * y - 1) / 2);
+}
+PNP_HD void basis_grad(double x, double y, double (*g)[2]) {
+  const double s = 2 * x + 2 * y;
+  g[0][0] = (2 * s - 3); g[0][1] = (2 * s - 3);
+  g[1][0] = 2 * (2 - s) - 4 * x; g[1][1] = -4 * x;
+  g[2][0] = 4 * x - 1; g[2][1] = 0.0;
+  g[3][0] = -4 * y; g[3][1] = 2 * (2 - s) - 4 * y;
+  g[4][0] = 4 * y; g[4][1] = 4 * x;
+  g[5][0] = 0.0; g[5][1] = 4 * y - 1;
+}
+
+// affine geometry: J^{-T}, |det J|, the vertices' y for the cylindrical factor
+struct Geo2 { double jit[2][2], detabs, y0, y1, y2; };
+PNP_HD Geo2 make_geo2(double x0, double y0, double x1, double y1, double x2, double y2) {
+  Geo2 G;
+  const double j00 = x1 - x0, j01 = x2 - x0, j10 = y1 - y0, j11 = y2 - y0;
+  const double det = j00 * j11 - j01 * j10;
+  const double di = 1.0 / det;
+  G.jit[0][0] = j11 * di;  G.jit[0][1] = -j10 * di;
+  G.jit[1][0] = -j01 * di; G.jit[1][1] = j00 * di;
+  G.detabs = fabs(det);
+  G.y0 = y0; G.y1 = y1; G.y2 = y2;
+  return G;
+}
+struct BasisAt { double phi[NL], g[NL][2]; };
+PNP_HD BasisAt basis_at(const Geo2& G, double x, double y) {
+  BasisAt B;
+  basis(x, y, B.phi);
+  double gh[NL][2];
+  basis_grad(x, y, gh);
+#pragma unroll
+  for (int i = 0; i < NL; i++)
+#pragma unroll
+    for (int r = 0; r < 2; r++) { // FieldMatrix::mv
+      double v = 0.0;
+      v += G.jit[r][0] * gh[i][0];
+      v += G.jit[r][1] * gh[i][1];
+      B.g[i][r] = v;
+    }
+  return B;
+}
+
+// alpha_volume: xl[NL*k + i] = local coefficient of field k at node i; caux[a][i] = local coefficients of the operator's
+// coefficient fields (Poisson: c+, c-; diffusion: Phi), P2 functions as well.  ACCUMULATES into rl[NL*k + i].
+template <int OP>
+PNP_HD void alpha_volume(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* rl) {
+  constexpr int NQ = OpTraits<OP>::NQ;
+  const double PI = P.PI;
+  for (int q = 0; q < NQ; q++) {
+    double xi0, xi1, w;
+    quad_point<NQ>(q, xi0, xi1, w);
+    const BasisAt B = basis_at(G, xi0, xi1);
+    const double gy = G.y0 + (G.y1 - G.y0) * xi0 + (G.y2 - G.y0) * xi1;
+    double factor = w * G.detabs;
+    if (OP == OP_PNP) {
+      if (P.cylindrical) factor *= gy * 2 * PI;
+      double u[3], gu[3][2];
+      for (int k = 0; k < 3; k++) {
+        u[k] = 0.0; gu[k][0] = 0.0; gu[k][1] = 0.0;
+        for (int i = 0; i < NL; i++) u[k] += xl[NL * k + i] * B.phi[i];
+        for (int i = 0; i < NL; i++) { gu[k][0] += xl[NL * k + i] * B.g[i][0]; gu[k][1] += xl[NL * k + i] * B.g[i][1]; }
+      }
+      for (int i = 0; i < NL; i++) rl[i] += (dot2(gu[0], B.g[i]) + 4 * PI * P.l_b * (u[1] - u[2]) * B.phi[i]) * factor;
+      for (int i = 0; i < NL; i++) rl[NL + i] += (dot2(gu[1], B.g[i]) - u[1] * dot2(gu[0], B.g[i])) * factor;
+      for (int i = 0; i < NL; i++) rl[2 * NL + i] += (dot2(gu[2], B.g[i]) + u[2] * dot2(gu[0], B.g[i])) * factor;
+    } else if (OP == OP_PB || OP == OP_POISSON) {
+      if (P.cylindrical) factor *= gy * 2 * PI;
+      double u = 0.0, gu[2] = {0.0, 0.0};
+      for (int i = 0; i < NL; i++) u += xl[i] * B.phi[i];
+      for (int i = 0; i < NL; i++) { gu[0] += xl[i] * B.g[i][0]; gu[1] += xl[i] * B.g[i][1]; }
+      double src;
+      if (OP == OP_PB) src = 8 * PI * P.l_b * P.c0 * pnp_sinh(u);
+      else {
+        double cp = 0.0, cm = 0.0;
+        for (int i = 0; i < NL; i++) cp += caux[0][i] * B.phi[i];
+        for (int i = 0; i < NL; i++) cm += caux[1][i] * B.phi[i];
+        src = 1 * P.l_b * 4 * PI * (cm - cp);
+      }
+      for (int i = 0; i < NL; i++) rl[i] += (dot2(gu, B.g[i]) + src * B.phi[i]) * factor;
+    } else if (OP == OP_DIFFUSION) {
+      double u = 0.0, gu[2] = {0.0, 0.0}, gP[2] = {0.0, 0.0};
+      for (int i = 0; i < NL; i++) u += xl[i] * B.phi[i];
+      for (int i = 0; i < NL; i++) { gu[0] += xl[i] * B.g[i][0]; gu[1] += xl[i] * B.g[i][1]; }
+      for (int i = 0; i < NL; i++) { gP[0] += caux[0][i] * B.g[i][0]; gP[1] += caux[0][i] * B.g[i][1]; }
+      const double a = 0;
+      for (int i = 0; i < NL; i++) rl[i] += (dot2(gu, B.g[i]) + u * P.valency * dot2(gP, B.g[i]) + a * u * B.phi[i]) * factor;
+    } else { // OP_MASS
+      double u = 0.0;
+      for (int i = 0; i < NL; i++) u += xl[i] * B.phi[i];
+      for (int i = 0; i < NL; i++) rl[i] += u * B.phi[i] * factor;
+    }
+  }
+}
+
+// alpha_boundary of DUNE face f with end points (ax,ay)->(bx,by) in element order; j[k] = flux of field k, skip[k]: the face
+// is Dirichlet for field k's component.  ACCUMULATES into rl.
+PNP_HD void alpha_boundary(int f, double ax, double ay, double bx, double by, int nfields, const double* j, const bool* skip,
+                           const PhysParams& P, double* rl) {
+  const double len = sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
+  const double tq[2] = {0.21132486540518711775, 0.78867513459481288225};
+  for (int q = 0; q < 2; q++) {
+    const double t = tq[q];
+    double l0, l1;
+    if (f == 0) { l0 = t; l1 = 0.0; } else if (f == 1) { l0 = 0.0; l1 = t; } else { l0 = 1.0 - t; l1 = t; }
+    double phi[NL];
+    basis(l0, l1, phi);
+    const double gy = ay + t * (by - ay);
+    double factor = 0.5 * len;
+    if (P.cylindrical) factor *= gy * 2 * P.PI;
+    for (int k = 0; k < nfields; k++) {
+      if (skip[k]) continue;
+      for (int i = 0; i < NL; i++) rl[NL * k + i] += j[k] * phi[i] * factor;
+    }
+  }
+}
+
+// NumericalJacobianVolume: Ae[i*n + j], n = NL * F, ACCUMULATED
+template <int OP>
+PNP_HD void jacobian_fd(const Geo2& G, const PhysParams& P, double* xl, const double (*caux)[NL], double eps, double* Ae) {
+  constexpr int n = NL * OpTraits<OP>::F;
+  double down[n], up[n];
+  for (int i = 0; i < n; i++) down[i] = 0.0;
+  alpha_volume<OP>(G, P, xl, caux, down);
+  for (int j = 0; j < n; j++) {
+    for (int i = 0; i < n; i++) up[i] = 0.0;
+    const double keep = xl[j];
+    const double delta = eps * (1.0 + fabs(keep));
+    xl[j] = keep + delta;
+    alpha_volume<OP>(G, P, xl, caux, up);
+    for (int i = 0; i < n; i++) Ae[i * n + j] += (up[i] - down[i]) / delta;
+    xl[j] = keep;
+  }
+}
+
+// exact derivative (not in the reference)
+template <int OP>
+PNP_HD void jacobian_exact(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* Ae) {
+  constexpr int NQ = OpTraits<OP>::NQ;
+  constexpr int n = NL * OpTraits<OP>::F;
+  for (int q = 0; q < NQ; q++) {
+    double xi0, xi1, w;
+    quad_point<NQ>(q, xi0, xi1, w);
+    const BasisAt B = basis_at(G, xi0, xi1);
+    const double gy = G.y0 + (G.y1 - G.y0) * xi0 + (G.y2 - G.y0) * xi1;
+    double factor = w * G.detabs;
+    if ((OP == OP_PNP || OP == OP_PB || OP == OP_POISSON) && P.cylindrical) factor *= gy * 2 * P.PI;
+    if (OP == OP_PNP) {
+      double u[3] = {0, 0, 0}, gP[2] = {0, 0};
+      for (int k = 0; k < 3; k++) for (int i = 0; i < NL; i++) u[k] += xl[NL * k + i] * B.phi[i];
+      for (int i = 0; i < NL; i++) { gP[0] += xl[i] * B.g[i][0]; gP[1] += xl[i] * B.g[i][1]; }
+      const double kap = 4 * P.PI * P.l_b;
+      for (int i = 0; i < NL; i++) {
+        const double dPi = gP[0] * B.g[i][0] + gP[1] * B.g[i][1];
+        for (int j = 0; j < NL; j++) {
+          const double K = B.g[j][0] * B.g[i][0] + B.g[j][1] * B.g[i][1];
+          Ae[i * n + j] += K * factor;
+          Ae[i * n + NL + j] += kap * B.phi[j] * B.phi[i] * factor;
+          Ae[i * n + 2 * NL + j] -= kap * B.phi[j] * B.phi[i] * factor;
+          Ae[(NL + i) * n + j] -= u[1] * K * factor;
+          Ae[(NL + i) * n + NL + j] += (K - B.phi[j] * dPi) * factor;
+          Ae[(2 * NL + i) * n + j] += u[2] * K * factor;
+          Ae[(2 * NL + i) * n + 2 * NL + j] += (K + B.phi[j] * dPi) * factor;
+        }
+      }
+    } else {
+      double u = 0, gP[2] = {0, 0};
+      for (int i = 0; i < NL; i++) u += xl[i] * B.phi[i];
+      if (OP == OP_DIFFUSION) for (int i = 0; i < NL; i++) { gP[0] += caux[0][i] * B.g[i][0]; gP[1] += caux[0][i] * B.g[i][1]; }
+      const double ch = OP == OP_PB ? 8 * P.PI * P.l_b * P.c0 * cosh(u) : 0.0;
+      for (int i = 0; i < NL; i++) for (int j = 0; j < NL; j++) {
+        const double K = B.g[j][0] * B.g[i][0] + B.g[j][1] * B.g[i][1];
+        double v;
+        if (OP == OP_PB) v = K + ch * B.phi[j] * B.phi[i];
+        else if (OP == OP_POISSON) v = K;
+        else if (OP == OP_DIFFUSION) v = K + B.phi[j] * P.valency * (gP[0] * B.g[i][0] + gP[1] * B.g[i][1]);
+        else v = B.phi[j] * B.phi[i];
+        Ae[i * n + j] += v * factor;
+      }
+    }
+  }
+}
+
+} // namespace p2
+} // namespace pnp

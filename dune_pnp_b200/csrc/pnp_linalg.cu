@@ -156,6 +156,12 @@ void finish_reduce(Ctx& c, int nblocks, int nr, double* out) {
 // y = A x with optional fused dots; returns them in dots[0..ndot)
 void spmv_dots(Ctx& c, const Matrix& A, double* x, double* y, int ndot, const double* w1, double* dots) {
   ensure_red(c);
+  if (A.csr_rp) { // quadratic elements: CSR rows, the dots as separate reductions
+    csr_spmv(c, A, x, y);
+    if (ndot >= 1) dots[0] = vec_dot(c, y, w1, A.csr_n);
+    if (ndot == 2) dots[1] = vec_dot(c, y, y, A.csr_n);
+    return;
+  }
   halo_exchange(c, x, A.nplanes == 1 ? 1 : 3); // ghost columns of x (no-op on one GPU)
   StarOpArgs a{c.rp.p, c.adj.p, A.vals.p, c.nslots, (int)c.n_own, x, y};
   a.w1 = w1; a.partial = c.red_partial.p;
@@ -200,6 +206,12 @@ void ilu0_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y);
 
 namespace {
 void prec_setup(Ctx& c, Solver& S, const Matrix& A) {
+  if (A.csr_rp) {
+    PNP_REQUIRE(S.prec == PNP_PREC_NONE || S.prec == PNP_PREC_JACOBI, PNP_E_ARG,
+                "quadratic elements: the preconditioners are none (Richardson) and Jacobi");
+    if (S.prec == PNP_PREC_JACOBI) csr_diag_inverse(c, A, S.dinv.p);
+    return;
+  }
   switch (S.prec) {
     case PNP_PREC_NONE: break;
     case PNP_PREC_JACOBI: {
@@ -335,17 +347,17 @@ LinResult cg(Ctx& c, Solver& S, const Matrix& A, double* x, double* b, long n, d
 void precond_apply(Ctx& c, Solver& S, const Matrix& A, Vec& d, Vec& v) {
   PNP_REQUIRE(d.fields == v.fields && d.fields == (A.nplanes == 1 ? 1 : 3) && d.d.p != v.d.p, PNP_E_ARG,
               "vector field count does not match the matrix");
-  S.ensure((size_t)c.nv * d.fields);
+  S.ensure((size_t)c.cols() * d.fields);
   ensure_red(c);
   prec_setup(c, S, A);
-  prec_apply(c, S, A, d.d.p, v.d.p, c.n_own * d.fields);
+  prec_apply(c, S, A, d.d.p, v.d.p, c.rows() * d.fields);
 }
 
 LinResult solver_apply(Ctx& c, Solver& S, const Matrix& A, Vec& z, Vec& r, double reduction) {
   PNP_REQUIRE(z.fields == r.fields && z.fields == (A.nplanes == 1 ? 1 : 3), PNP_E_ARG,
               "vector field count does not match the matrix");
-  const long n = c.n_own * z.fields; // owned dofs: what dots, norms and updates run over
-  S.ensure((size_t)c.nv * z.fields);  // work vectors carry a ghost part for the SpMV input
+  const long n = c.rows() * z.fields; // owned dofs: what dots, norms and updates run over
+  S.ensure((size_t)c.cols() * z.fields);  // work vectors carry a ghost part for the SpMV input
   ensure_red(c);
   auto t0 = std::chrono::steady_clock::now();
   prec_setup(c, S, A);

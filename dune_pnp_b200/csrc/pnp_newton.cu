@@ -19,7 +19,7 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton_opts& o, pnp_newton_result& R) {
   const int F = op_fields(op.op);
   PNP_REQUIRE(u.fields == F, PNP_E_ARG, "vector field count does not match the operator");
-  const long n = c.n_own * F, nall = c.nv * F;
+  const long n = c.rows() * F, nall = c.cols() * F;
   R = pnp_newton_result();
   Vec &r = c.ws_r, &z = c.ws_z, &prev_u = c.ws_prev;
   Matrix& A = c.ws_A;
@@ -27,7 +27,8 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
   if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); prev_u.d.alloc(nall); }
   r.d.zero(c.stream); z.d.zero(c.stream);
   A.op = op.op; A.nplanes = op_planes(op.op);
-  if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
+  if (c.degree == 2) p2_matrix_init(c, A, op);
+  else if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
   const double t_start = now();
   auto sync = [&] { PNP_CUDA(cudaStreamSynchronize(c.stream)); };
   auto defect = [&]() {
@@ -137,14 +138,15 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
 LinResult slp_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, double reduction, int jac_mode, double eps) {
   const int F = op_fields(op.op);
   PNP_REQUIRE(u.fields == F, PNP_E_ARG, "vector field count does not match the operator");
-  const long n = c.n_own * F, nall = c.nv * F;
+  const long n = c.rows() * F, nall = c.cols() * F;
   Vec &r = c.ws_r, &z = c.ws_z;
   Matrix& A = c.ws_A;
   r.fields = z.fields = F;
   if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); c.ws_prev.d.alloc(nall); }
   r.d.zero(c.stream); z.d.zero(c.stream);
   A.op = op.op; A.nplanes = op_planes(op.op);
-  if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
+  if (c.degree == 2) p2_matrix_init(c, A, op);
+  else if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
   assemble_jacobian(c, op, u, A, jac_mode, eps);
   assemble_residual(c, op, u, r);
   vec_zero(c, z.d.p, n);
@@ -201,8 +203,9 @@ int onestep_apply(Ctx& c, int method, const Operator& op0, const Operator& op1, 
   PNP_REQUIRE(xold.fields == 1 && xnew.fields == 1 && g.fields == 1, PNP_E_ARG, "one-step method: 1-field vectors expected");
   PNP_REQUIRE(op0.comp0 == op1.comp0, PNP_E_ARG, "spatial and temporal operator must share the constraints");
   const TimeMethod tm = time_method(method);
-  const long n = c.n_own, nall = c.nv;
+  const long n = c.rows(), nall = c.cols();
   const int comp = op0.comp0;
+  const bool p2 = c.degree == 2;
   for (auto& v : c.ws_stage) { v.fields = 1; if (v.d.n != (size_t)nall) { v.d.alloc(nall); v.d.zero(c.stream); } }
   Vec &x1 = c.ws_stage[0], &x2 = c.ws_stage[1], &cst = c.ws_stage[2], &r0 = c.ws_stage[3], &r1 = c.ws_stage[4];
   Vec &r = c.ws_r, &z = c.ws_z;
@@ -210,10 +213,14 @@ int onestep_apply(Ctx& c, int method, const Operator& op0, const Operator& op1, 
   if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); c.ws_prev.d.alloc(nall); r.d.zero(c.stream); z.d.zero(c.stream); }
   Matrix &A = c.ws_A, &B = c.ws_B;
   A.op = op0.op; B.op = op1.op; A.nplanes = B.nplanes = 1;
-  if (A.vals.n != (size_t)c.nslots) A.vals.alloc(c.nslots);
-  if (B.vals.n != (size_t)c.nslots) B.vals.alloc(c.nslots);
+  if (p2) { p2_matrix_init(c, A, op0); p2_matrix_init(c, B, op1); }
+  else {
+    if (A.vals.n != (size_t)c.nslots) A.vals.alloc(c.nslots);
+    if (B.vals.n != (size_t)c.nslots) B.vals.alloc(c.nslots);
+  }
+  const long nvals = p2 ? A.csr_nnz : c.nslots;
   Vec* x[3] = {&xold, &x1, &x2};
-  const int gv = grid_for(n, 256), gs = grid_for(c.nslots, 256);
+  const int gv = grid_for(n, 256), gs = grid_for(nvals, 256);
   for (int rs = 1; rs <= tm.s; rs++) {
     // preStage: the part of the stage residual that the earlier stages fix
     bool first = true;
@@ -231,13 +238,14 @@ int onestep_apply(Ctx& c, int method, const Operator& op0, const Operator& op1, 
     if (first) vec_zero(c, cst.d.p, n);
     Vec& xn = *x[rs];
     vec_copy(c, x[rs - 1]->d.p, xn.d.p, n);
-    k_set_dirichlet<<<gv, 256, 0, c.stream>>>(c.dmask.p, comp, (int)n, g.d.p, xn.d.p);
+    k_set_dirichlet<<<gv, 256, 0, c.stream>>>(p2 ? p2_dirichlet_flags(c) : c.dmask.p, comp, (int)n, g.d.p, xn.d.p);
     PNP_CHECK_LAUNCH(); c.launches++;
     const double ar = tm.a[rs - 1][rs], br = tm.b[rs - 1][rs];
     assemble_jacobian(c, op1, xn, B, jac_mode, eps);
     assemble_jacobian(c, op0, xn, A, jac_mode, eps);
-    k_stage_matrix<<<gs, 256, 0, c.stream>>>(A.vals.p, B.vals.p, br * dt, ar, c.nslots);
-    k_unit_dirichlet_diag<<<gv, 256, 0, c.stream>>>(c.rp.p, c.dmask.p, comp, (int)n, A.vals.p);
+    k_stage_matrix<<<gs, 256, 0, c.stream>>>(A.vals.p, B.vals.p, br * dt, ar, nvals);
+    // (a constrained CSR row holds its diagonal alone, a constrained star row starts with it)
+    k_unit_dirichlet_diag<<<gv, 256, 0, c.stream>>>(p2 ? A.csr_rp : c.rp.p, p2 ? p2_dirichlet_flags(c) : c.dmask.p, comp, (int)n, A.vals.p);
     PNP_CHECK_LAUNCH(); c.launches += 2;
     c.last_vals = nullptr; // A is a combination now: a multigrid must not re-discretise `op0` for it
     assemble_residual(c, op1, xn, r1);

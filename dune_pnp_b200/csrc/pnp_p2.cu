@@ -1,0 +1,450 @@
+// pnp_p2.cu -- quadratic elements (the reference's -DPDEGREE=2 build, /root/reference/src/Makefile.am:57-110;
+// instationary_pnp_from_pb_md.hh:26-28,125): the grid function space with edge dofs, its constraints and BCRS pattern,
+// residual and Jacobian assembly of the five local operators with 6 local dofs per field, a general CSR SpMV.
+//
+// The P1 path lives on the vertex-star layout, which is both mesh and pattern for linear elements only; the P2 couplings
+// (all 6 dofs of an element with each other) do not fit it, so this path uses the reference's own container layout on the
+// device: dofs numbered edges first [0, nE), then vertices [nE, nE + nv), fields lexicographic, matrices in
+// scalar CSR with ascending columns (ISTLBCRSMatrixBackend<1,1>) -- what pnp_pattern_get returns IS the device layout.
+// Assembly in two phases, deterministic and in the reference's summation order: (1) one thread per element computes the
+// element vector / matrix (alpha_volume + alpha_boundary; NumericalJacobianVolume or the exact derivative) into a scratch
+// block, (2) one thread per dof row sums its elements' contributions in ascending element order (the order of PDELab's
+// element loop) into the residual entry / the row's CSR slots.  No atomics; constrained rows are trivial, constrained
+// residual entries zero.  Compiled -fmad=false (Makefile): the FD Jacobian rounds like the CPU restatement.
+// Set-up (edge numbering, incidence lists, patterns, Dirichlet flags) runs on the host from the canonical mesh arrays:
+// quadratic elements are a functionality row here, the throughput path is the P1 star layout.
+#include <algorithm>
+
+#include "pnp_common.cuh"
+#include "pnp_elem_p2.cuh"
+
+namespace pnp {
+
+using p2::NL;
+
+struct P2Pattern {
+  long nnz = 0;
+  std::vector<int> h_rp, h_col;
+  DBuf<int> rp, col;
+};
+
+struct P2Space {
+  long nE = 0, nd = 0, nT = 0, nv = 0;
+  std::vector<int> h_eva, h_evb, h_e2d, h_fphys, h_nbr; // edges; element -> 6 scalar dofs; element face -> surface (-1 interior); face neighbours
+  std::vector<int> h_edge_phys;                           // per edge: surface of a boundary edge, -1 inside
+  std::vector<unsigned char> h_dir;                       // per scalar dof: bit c = Dirichlet for BC component c
+  DBuf<int> e2d, fphys, inc_ptr, inc;                     // incidence: scalar dof -> (element * 8 + local node), elements ascending
+  DBuf<unsigned char> dir;
+  std::map<int, std::unique_ptr<P2Pattern>> patterns;     // key = 4 * F + comp0
+  DBuf<double> scratch;
+};
+
+namespace {
+
+const int FACE_V2[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+
+template <int OP>
+__device__ __forceinline__ void p2_gather_element(int e, const int* tri, const double* cx, const double* cy, const int* e2d, long nd,
+                                                  const double* u, const double* aux0, const double* aux1, p2::Geo2& G, double* xl,
+                                                  double (*caux)[NL]) {
+  constexpr int F = OpTraits<OP>::F;
+  const int a = tri[3 * e], b = tri[3 * e + 1], c = tri[3 * e + 2];
+  G = p2::make_geo2(cx[a], cy[a], cx[b], cy[b], cx[c], cy[c]);
+  for (int i = 0; i < NL; i++) {
+    const int d = e2d[NL * e + i];
+    for (int k = 0; k < F; k++) xl[NL * k + i] = u[(long)k * nd + d];
+    caux[0][i] = OpTraits<OP>::NAUX >= 1 ? aux0[d] : 0.0;
+    caux[1][i] = OpTraits<OP>::NAUX >= 2 ? aux1[d] : 0.0;
+  }
+}
+
+// phase 1, residual: element vector (alpha_volume + alpha_boundary in intersection order 0, 2, 1) -> scratch[e * n ..]
+template <int OP>
+__global__ void k_p2_elem_residual(int nT, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
+                                   const int* __restrict__ e2d, const int* __restrict__ fphys, const double* __restrict__ surf_flux,
+                                   const unsigned char* __restrict__ surf_dir, PhysParams P, long nd, int comp0,
+                                   const double* __restrict__ u, const double* __restrict__ aux0, const double* __restrict__ aux1,
+                                   double* __restrict__ out) {
+  constexpr int F = OpTraits<OP>::F, n = NL * F;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nT; e += gridDim.x * blockDim.x) {
+    p2::Geo2 G; double xl[n], caux[2][NL], rl[n];
+    p2_gather_element<OP>(e, tri, cx, cy, e2d, nd, u, aux0, aux1, G, xl, caux);
+    for (int i = 0; i < n; i++) rl[i] = 0.0;
+    p2::alpha_volume<OP>(G, P, xl, caux, rl);
+    if (OP == OP_PB || OP == OP_POISSON || OP == OP_PNP) {
+      const int order[3] = {0, 2, 1};
+      for (int fi = 0; fi < 3; fi++) {
+        const int f = order[fi], ph = fphys[3 * e + f];
+        if (ph < 0) continue;
+        const int va = tri[3 * e + (f == 2 ? 1 : 0)], vb = tri[3 * e + (f == 0 ? 1 : 2)];
+        double j[3]; bool skip[3];
+        for (int k = 0; k < F; k++) {
+          const int comp = F == 3 ? k : comp0;
+          j[k] = surf_flux[3 * ph + comp]; skip[k] = (surf_dir[ph] >> comp) & 1;
+        }
+        p2::alpha_boundary(f, cx[va], cy[va], cx[vb], cy[vb], F, j, skip, P, rl);
+      }
+    }
+    for (int i = 0; i < n; i++) out[(long)e * n + i] = rl[i];
+  }
+}
+// phase 2, residual: r[(k, d)] = sum over d's elements, ascending; constrained entries zero
+__global__ void k_p2_gather_residual(long nd, int F, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                     const unsigned char* __restrict__ dir, const double* __restrict__ scratch, double* __restrict__ r) {
+  const int n = NL * F;
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < (long)F * nd; g += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(g / nd); const long d = g - (long)k * nd;
+    double sum = 0.0;
+    for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; t++) sum += scratch[(long)(inc[t] >> 3) * n + NL * k + (inc[t] & 7)];
+    r[g] = ((dir[d] >> (F == 3 ? k : comp0)) & 1u) ? 0.0 : sum;
+  }
+}
+// phase 1, Jacobian: element matrix -> scratch[e * n * n ..]
+template <int OP, int MODE>
+__global__ void k_p2_elem_jacobian(int nT, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
+                                   const int* __restrict__ e2d, PhysParams P, long nd, double eps, const double* __restrict__ u,
+                                   const double* __restrict__ aux0, const double* __restrict__ aux1, double* __restrict__ out) {
+  constexpr int F = OpTraits<OP>::F, n = NL * F;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nT; e += gridDim.x * blockDim.x) {
+    p2::Geo2 G; double xl[n], caux[2][NL];
+    p2_gather_element<OP>(e, tri, cx, cy, e2d, nd, u, aux0, aux1, G, xl, caux);
+    double* Ae = out + (long)e * n * n; // accumulated in place (one writer)
+    for (int i = 0; i < n * n; i++) Ae[i] = 0.0;
+    if (MODE == 0) p2::jacobian_fd<OP>(G, P, xl, caux, eps, Ae);
+    else p2::jacobian_exact<OP>(G, P, xl, caux, Ae);
+  }
+}
+// phase 2, Jacobian: row (ki, d) of the CSR matrix
+__global__ void k_p2_gather_jacobian(long nd, int F, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                     const int* __restrict__ e2d, const unsigned char* __restrict__ dir, const int* __restrict__ rp,
+                                     const int* __restrict__ col, const double* __restrict__ scratch, double* __restrict__ vals) {
+  const int n = NL * F;
+  for (long gi = blockIdx.x * (long)blockDim.x + threadIdx.x; gi < (long)F * nd; gi += (long)gridDim.x * blockDim.x) {
+    const int ki = (int)(gi / nd); const long d = gi - (long)ki * nd;
+    const int r0 = rp[gi], r1 = rp[gi + 1];
+    for (int s = r0; s < r1; s++) vals[s] = 0.0;
+    if ((dir[d] >> (F == 3 ? ki : comp0)) & 1u) { vals[r0] = 1.0; continue; } // trivial row (its only entry is the diagonal)
+    for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; t++) {
+      const int e = inc[t] >> 3, i = inc[t] & 7;
+      const double* Ae = scratch + (long)e * n * n + (long)(NL * ki + i) * n;
+      for (int kj = 0; kj < F; kj++)
+        for (int j = 0; j < NL; j++) {
+          const long dj = e2d[NL * e + j];
+          if ((dir[dj] >> (F == 3 ? kj : comp0)) & 1u) continue;
+          const int gj = (int)((long)kj * nd + dj);
+          int lo = r0, hi = r1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < gj) lo = mid + 1; else hi = mid; }
+          vals[lo] += Ae[NL * kj + j];
+        }
+    }
+  }
+}
+__global__ void k_csr_spmv(long N, const int* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ vals,
+                           const double* __restrict__ x, double* __restrict__ y) {
+  for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < N; r += (long)gridDim.x * blockDim.x) {
+    double sum = 0.0;
+    for (int s = rp[r]; s < rp[r + 1]; s++) sum += vals[s] * x[col[s]];
+    y[r] = sum;
+  }
+}
+__global__ void k_csr_diag_inverse(long N, const int* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ vals,
+                                   double* __restrict__ dinv) {
+  for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < N; r += (long)gridDim.x * blockDim.x) {
+    double d = 0.0;
+    for (int s = rp[r]; s < rp[r + 1]; s++) if (col[s] == r) d = vals[s];
+    dinv[r] = d != 0.0 ? 1.0 / d : 0.0;
+  }
+}
+
+template <int OP> void launch_elem_residual(Ctx& c, P2Space& S, int comp0, const PhysParams& P, const double* u, const double* a0,
+                                            const double* a1) {
+  const int g = grid_for(S.nT, 128);
+  k_p2_elem_residual<OP><<<g, 128, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, S.fphys.p, c.d_surf.p, c.d_surf_dir.p, P,
+                                                  S.nd, comp0, u, a0, a1, S.scratch.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+}
+template <int OP> void launch_elem_jacobian(Ctx& c, P2Space& S, const PhysParams& P, int mode, double eps, const double* u,
+                                            const double* a0, const double* a1) {
+  const int g = grid_for(S.nT, 64);
+  if (mode == 0) k_p2_elem_jacobian<OP, 0><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
+  else k_p2_elem_jacobian<OP, 1><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+}
+
+void coefficient_ptrs_p2(Ctx& c, const Operator& op, const double** a0, const double** a1) {
+  *a0 = *a1 = nullptr;
+  const int need = op.op == OP_POISSON ? 2 : (op.op == OP_DIFFUSION ? 1 : 0);
+  if (need >= 1) { PNP_REQUIRE(op.aux0 >= 0 && c.vec(op.aux0).fields == 1, PNP_E_ARG, "operator coefficient 0 not set"); *a0 = c.vec(op.aux0).d.p; }
+  if (need >= 2) { PNP_REQUIRE(op.aux1 >= 0 && c.vec(op.aux1).fields == 1, PNP_E_ARG, "operator coefficient 1 not set"); *a1 = c.vec(op.aux1).d.p; }
+}
+
+} // namespace
+
+// ---- space: edges, element dof map, incidence lists, boundary faces, Dirichlet flags (host, from the canonical mesh) ----
+void p2_build(Ctx& c) {
+  PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "quadratic elements work on an unpartitioned mesh");
+  auto S = std::make_shared<P2Space>();
+  const long nv = c.nv, nT = c.nT, nB = c.nB;
+  S->nT = nT; S->nv = nv;
+  const std::vector<int> tri = c.ctri.to_host(c.stream), ba = c.cba.to_host(c.stream), bb = c.cbb.to_host(c.stream),
+                         bph = c.cbphys.to_host(c.stream);
+  auto key = [](int a, int b) { return ((uint64_t)std::min(a, b) << 32) | (uint64_t)std::max(a, b); };
+  std::vector<uint64_t> keys(3 * (size_t)nT);
+  for (long e = 0; e < nT; e++) for (int f = 0; f < 3; f++) keys[3 * e + f] = key(tri[3 * e + FACE_V2[f][0]], tri[3 * e + FACE_V2[f][1]]);
+  std::vector<uint64_t> uk(keys);
+  std::sort(uk.begin(), uk.end()); uk.erase(std::unique(uk.begin(), uk.end()), uk.end());
+  S->nE = (long)uk.size(); S->nd = S->nE + nv;
+  PNP_REQUIRE(3 * S->nd < (1l << 31), PNP_E_MESH, "too many dofs for 32-bit column indices");
+  S->h_eva.resize(S->nE); S->h_evb.resize(S->nE);
+  for (long k = 0; k < S->nE; k++) { S->h_eva[k] = (int)(uk[k] >> 32); S->h_evb[k] = (int)(uk[k] & 0xffffffffu); }
+  std::vector<int> tedge(3 * (size_t)nT);
+  for (size_t i = 0; i < keys.size(); i++) tedge[i] = (int)(std::lower_bound(uk.begin(), uk.end(), keys[i]) - uk.begin());
+  S->h_e2d.resize(NL * (size_t)nT);
+  for (long e = 0; e < nT; e++)
+    for (int i = 0; i < NL; i++)
+      S->h_e2d[NL * e + i] = p2::node_is_edge(i) ? tedge[3 * e + p2::node_sub(i)] : (int)(S->nE + tri[3 * e + p2::node_sub(i)]);
+  // boundary faces: the element face whose edge is a boundary segment carries that segment's surface; neighbours across faces
+  std::vector<int> edge_phys(S->nE, -1), edge_elem0(S->nE, -1), edge_elem1(S->nE, -1);
+  for (long s = 0; s < nB; s++) {
+    auto it = std::lower_bound(uk.begin(), uk.end(), key(ba[s], bb[s]));
+    PNP_REQUIRE(it != uk.end() && *it == key(ba[s], bb[s]), PNP_E_MESH, "a boundary segment is not an edge of the mesh");
+    edge_phys[it - uk.begin()] = bph[s]; // (a segment listed twice: the later one wins)
+  }
+  for (long e = 0; e < nT; e++) for (int f = 0; f < 3; f++) { int& a = edge_elem0[tedge[3 * e + f]]; if (a < 0) a = (int)e; else edge_elem1[tedge[3 * e + f]] = (int)e; }
+  S->h_fphys.assign(3 * (size_t)nT, -1); S->h_nbr.assign(3 * (size_t)nT, -1);
+  for (long e = 0; e < nT; e++)
+    for (int f = 0; f < 3; f++) {
+      const int k = tedge[3 * e + f];
+      if (edge_elem1[k] < 0) { PNP_REQUIRE(edge_phys[k] >= 0, PNP_E_MESH, "boundary face without boundary segment"); S->h_fphys[3 * e + f] = edge_phys[k]; }
+      else S->h_nbr[3 * e + f] = edge_elem0[k] == e ? edge_elem1[k] : edge_elem0[k];
+    }
+  // incidence lists, elements ascending
+  std::vector<int> ptr(S->nd + 1, 0), inc(NL * (size_t)nT);
+  for (size_t i = 0; i < S->h_e2d.size(); i++) ptr[S->h_e2d[i] + 1]++;
+  for (long d = 0; d < S->nd; d++) ptr[d + 1] += ptr[d];
+  { std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) inc[fill[S->h_e2d[NL * e + i]]++] = (int)(e * 8 + i); }
+  S->h_edge_phys.assign(S->nE, -1);
+  for (long k = 0; k < S->nE; k++) if (edge_elem1[k] < 0) S->h_edge_phys[k] = edge_phys[k];
+  S->e2d.alloc(S->h_e2d.size()); S->e2d.upload(S->h_e2d.data(), S->h_e2d.size(), c.stream);
+  S->fphys.alloc(S->h_fphys.size()); S->fphys.upload(S->h_fphys.data(), S->h_fphys.size(), c.stream);
+  S->inc_ptr.alloc(ptr.size()); S->inc_ptr.upload(ptr.data(), ptr.size(), c.stream);
+  S->inc.alloc(inc.size()); S->inc.upload(inc.data(), inc.size(), c.stream);
+  S->h_dir.assign(S->nd, 0);
+  S->dir.alloc(S->nd); S->dir.zero(c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.p2 = S; c.p2_nd = S->nd;
+}
+
+// Dirichlet flags (ConformingDirichletConstraints): a Dirichlet face constrains its end vertices and its edge dof
+void p2_constraints(Ctx& c) {
+  PNP_REQUIRE(c.p2 && c.params.set, PNP_E_ARG, "quadratic space / parameters not set");
+  P2Space& S = *c.p2;
+  S.h_dir.assign(S.nd, 0);
+  for (long k = 0; k < S.nE; k++) {
+    const int ph = S.h_edge_phys[k];
+    if (ph < 0) continue;
+    PNP_REQUIRE(ph < c.params.n_surfaces, PNP_E_CONFIG, "physical tag without [surface_i] section");
+    unsigned char m = 0;
+    for (int comp = 0; comp < 3; comp++) if (c.params.surfaces[ph].btype[comp] == 0) m |= (unsigned char)(1u << comp);
+    S.h_dir[k] |= m; S.h_dir[S.nE + S.h_eva[k]] |= m; S.h_dir[S.nE + S.h_evb[k]] |= m;
+  }
+  S.dir.upload(S.h_dir.data(), S.nd, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  S.patterns.clear(); // (matrices created before a parameter change hold stale pattern pointers: like the P1 path, re-create them)
+}
+
+static P2Space& space(Ctx& c) {
+  PNP_REQUIRE(c.degree == 2 && c.p2, PNP_E_ARG, "no quadratic space (pnp_space_set_degree(ctx, 2) before pnp_mesh_finalize)");
+  return *c.p2;
+}
+
+// FullVolumePattern + ISTLBCRSMatrixBackend<1,1>: rows and columns ascending, constrained links dropped
+P2Pattern& p2_pattern(Ctx& c, int F, int comp0) {
+  P2Space& S = space(c);
+  auto& slot = S.patterns[4 * F + comp0];
+  if (slot) return *slot;
+  slot = std::make_unique<P2Pattern>();
+  P2Pattern& Pn = *slot;
+  const long nd = S.nd, nT = S.nT, N = F * nd;
+  auto dirichlet = [&](int k, long d) { return (S.h_dir[d] >> (F == 3 ? k : comp0)) & 1; };
+  std::vector<int> cnt(nd + 1, 0);
+  for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) cnt[S.h_e2d[NL * e + i] + 1] += NL;
+  for (long d = 0; d < nd; d++) cnt[d + 1] += cnt[d];
+  std::vector<int> raw(cnt[nd]), fill(cnt.begin(), cnt.end() - 1), nptr(nd + 1, 0), nbr;
+  for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) for (int j = 0; j < NL; j++) raw[fill[S.h_e2d[NL * e + i]]++] = S.h_e2d[NL * e + j];
+  for (long d = 0; d < nd; d++) {
+    auto b = raw.begin() + cnt[d], e = raw.begin() + cnt[d + 1];
+    std::sort(b, e); e = std::unique(b, e);
+    nbr.insert(nbr.end(), b, e); nptr[d + 1] = (int)nbr.size();
+  }
+  Pn.h_rp.assign(N + 1, 0);
+  for (int ki = 0; ki < F; ki++) for (long d = 0; d < nd; d++) {
+    int len = 0;
+    if (dirichlet(ki, d)) len = 1;
+    else for (int kj = 0; kj < F; kj++) for (int t = nptr[d]; t < nptr[d + 1]; t++) len += !dirichlet(kj, nbr[t]);
+    Pn.h_rp[ki * nd + d + 1] = len;
+  }
+  for (long r = 0; r < N; r++) Pn.h_rp[r + 1] += Pn.h_rp[r];
+  Pn.nnz = Pn.h_rp[N];
+  Pn.h_col.resize(Pn.nnz);
+  for (int ki = 0; ki < F; ki++) for (long d = 0; d < nd; d++) {
+    int o = Pn.h_rp[ki * nd + d];
+    if (dirichlet(ki, d)) { Pn.h_col[o] = (int)(ki * nd + d); continue; }
+    for (int kj = 0; kj < F; kj++) for (int t = nptr[d]; t < nptr[d + 1]; t++) if (!dirichlet(kj, nbr[t])) Pn.h_col[o++] = (int)(kj * nd + nbr[t]);
+  }
+  Pn.rp.alloc(Pn.h_rp.size()); Pn.rp.upload(Pn.h_rp.data(), Pn.h_rp.size(), c.stream);
+  Pn.col.alloc(Pn.h_col.size()); Pn.col.upload(Pn.h_col.data(), Pn.h_col.size(), c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  return Pn;
+}
+
+void p2_matrix_init(Ctx& c, Matrix& A, const Operator& op) {
+  const int F = op_fields(op.op);
+  P2Pattern& Pn = p2_pattern(c, F, F == 3 ? 0 : op.comp0);
+  A.op = op.op; A.nplanes = op_planes(op.op); A.comp0 = op.comp0;
+  A.csr_rp = Pn.rp.p; A.csr_col = Pn.col.p; A.csr_nnz = Pn.nnz; A.csr_n = F * space(c).nd;
+  if (A.vals.n != (size_t)Pn.nnz) { A.vals.alloc(Pn.nnz); A.vals.zero(c.stream); }
+}
+
+void p2_assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
+  P2Space& S = space(c);
+  PNP_REQUIRE(c.params.set, PNP_E_ARG, "parameters not set");
+  const int F = op_fields(op.op), n = NL * F;
+  PNP_REQUIRE(u.fields == F && r.fields == F, PNP_E_ARG, "vector field count does not match the operator");
+  const double *a0, *a1;
+  coefficient_ptrs_p2(c, op, &a0, &a1);
+  if (S.scratch.n < (size_t)n * S.nT) S.scratch.alloc((size_t)n * S.nT);
+  const PhysParams P = c.phys(op.valency);
+  switch (op.op) {
+    case OP_PB: launch_elem_residual<OP_PB>(c, S, op.comp0, P, u.d.p, a0, a1); break;
+    case OP_POISSON: launch_elem_residual<OP_POISSON>(c, S, op.comp0, P, u.d.p, a0, a1); break;
+    case OP_DIFFUSION: launch_elem_residual<OP_DIFFUSION>(c, S, op.comp0, P, u.d.p, a0, a1); break;
+    case OP_MASS: launch_elem_residual<OP_MASS>(c, S, op.comp0, P, u.d.p, a0, a1); break;
+    case OP_PNP: launch_elem_residual<OP_PNP>(c, S, op.comp0, P, u.d.p, a0, a1); break;
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
+  }
+  k_p2_gather_residual<<<grid_for(F * S.nd, 256), 256, 0, c.stream>>>(S.nd, F, op.comp0, S.inc_ptr.p, S.inc.p, S.dir.p, S.scratch.p, r.d.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  c.acct(Ctx::ACC_ASSEMBLY, (double)S.nT * (12 + 24 + 16.0 * n) + (double)F * S.nd * 16.0);
+}
+
+void p2_assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, double eps) {
+  P2Space& S = space(c);
+  PNP_REQUIRE(c.params.set, PNP_E_ARG, "parameters not set");
+  const int F = op_fields(op.op), n = NL * F;
+  PNP_REQUIRE(u.fields == F && A.op == op.op, PNP_E_ARG, "vector / matrix do not match the operator");
+  PNP_REQUIRE(mode == 0 || mode == 1, PNP_E_ARG, "unknown jacobian mode");
+  p2_matrix_init(c, A, op);
+  const double *a0, *a1;
+  coefficient_ptrs_p2(c, op, &a0, &a1);
+  if (S.scratch.n < (size_t)n * n * S.nT) S.scratch.alloc((size_t)n * n * S.nT);
+  const PhysParams P = c.phys(op.valency);
+  switch (op.op) {
+    case OP_PB: launch_elem_jacobian<OP_PB>(c, S, P, mode, eps, u.d.p, a0, a1); break;
+    case OP_POISSON: launch_elem_jacobian<OP_POISSON>(c, S, P, mode, eps, u.d.p, a0, a1); break;
+    case OP_DIFFUSION: launch_elem_jacobian<OP_DIFFUSION>(c, S, P, mode, eps, u.d.p, a0, a1); break;
+    case OP_MASS: launch_elem_jacobian<OP_MASS>(c, S, P, mode, eps, u.d.p, a0, a1); break;
+    case OP_PNP: launch_elem_jacobian<OP_PNP>(c, S, P, mode, eps, u.d.p, a0, a1); break;
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
+  }
+  k_p2_gather_jacobian<<<grid_for(F * S.nd, 128), 128, 0, c.stream>>>(S.nd, F, op.comp0, S.inc_ptr.p, S.inc.p, S.e2d.p, S.dir.p, A.csr_rp,
+                                                                      A.csr_col, S.scratch.p, A.vals.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  c.last_u = nullptr; c.last_vals = nullptr; // (no multigrid re-discretisation for quadratic elements)
+  c.acct(Ctx::ACC_ASSEMBLY, (double)S.nT * 16.0 * n * n + 12.0 * (double)A.csr_nnz);
+}
+
+void csr_spmv(Ctx& c, const Matrix& A, const double* x, double* y) {
+  k_csr_spmv<<<grid_for(A.csr_n, 256), 256, 0, c.stream>>>(A.csr_n, A.csr_rp, A.csr_col, A.vals.p, x, y);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  c.acct(Ctx::ACC_SPMV_FINE, 12.0 * (double)A.csr_nnz + 20.0 * (double)A.csr_n);
+}
+void csr_diag_inverse(Ctx& c, const Matrix& A, double* dinv) {
+  k_csr_diag_inverse<<<grid_for(A.csr_n, 256), 256, 0, c.stream>>>(A.csr_n, A.csr_rp, A.csr_col, A.vals.p, dinv);
+  PNP_CHECK_LAUNCH(); c.launches++;
+}
+
+const unsigned char* p2_dirichlet_flags(Ctx& c) { return space(c).dir.p; }
+
+// ---- the boundary's views of the space ----
+void p2_sizes(Ctx& c, long* nE, long* nd) { P2Space& S = space(c); if (nE) *nE = S.nE; if (nd) *nd = S.nd; }
+void p2_edges(Ctx& c, int* eva, int* evb) {
+  P2Space& S = space(c);
+  if (eva) std::copy(S.h_eva.begin(), S.h_eva.end(), eva);
+  if (evb) std::copy(S.h_evb.begin(), S.h_evb.end(), evb);
+}
+void p2_constraints_get(Ctx& c, const Operator& op, char* out) {
+  P2Space& S = space(c);
+  const int F = op_fields(op.op);
+  for (int k = 0; k < F; k++) for (long d = 0; d < S.nd; d++) out[k * S.nd + d] = (char)((S.h_dir[d] >> (F == 3 ? k : op.comp0)) & 1);
+}
+long p2_pattern_export(Ctx& c, const Operator& op, int* rowptr, int* col) {
+  const int F = op_fields(op.op);
+  P2Pattern& Pn = p2_pattern(c, F, F == 3 ? 0 : op.comp0);
+  if (rowptr) std::copy(Pn.h_rp.begin(), Pn.h_rp.end(), rowptr);
+  if (col) std::copy(Pn.h_col.begin(), Pn.h_col.end(), col);
+  return Pn.nnz;
+}
+void p2_matrix_import(Ctx& c, const Operator& op, Matrix& A, const int* rowptr, const int* col, const double* val) {
+  p2_matrix_init(c, A, op);
+  const int F = op_fields(op.op);
+  P2Pattern& Pn = p2_pattern(c, F, F == 3 ? 0 : op.comp0);
+  PNP_REQUIRE(std::equal(Pn.h_rp.begin(), Pn.h_rp.end(), rowptr) && std::equal(Pn.h_col.begin(), Pn.h_col.end(), col), PNP_E_ARG,
+              "CSR pattern differs from the operator's pattern (pnp_pattern_get)");
+  A.vals.upload(val, Pn.nnz, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// interpolate(BCExtension) for quadratic elements (dirichlet_bc.hh:54-123; interpolate: element loop, node by node, later
+// elements overwrite earlier ones); host code like the boundary band of the P1 version: an O(N) set-up step
+void p2_interpolate_bcext(Ctx& c, int comp, const Vec* pb, Vec& out) {
+  P2Space& S = space(c);
+  PNP_REQUIRE(comp >= 0 && comp < 3 && out.fields == 1 && (!pb || pb->fields == 1), PNP_E_ARG, "interpolate works on 1-field vectors");
+  const std::vector<double> x = c.cx.to_host(c.stream), y = c.cy.to_host(c.stream);
+  const std::vector<int> tri = c.ctri.to_host(c.stream);
+  std::vector<double> pbh;
+  if (pb) pbh = pb->d.to_host(c.stream);
+  std::vector<double> u(S.nd, 0.0);
+  const HostParams& s = c.params;
+  auto on_line = [&](double px, double py, int e, int f) { // globalOnIntersection, :21-33
+    const int a = tri[3 * e + FACE_V2[f][0]], b = tri[3 * e + FACE_V2[f][1]];
+    double vx = x[b] - x[a], vy = y[b] - y[a];
+    const double nrm = std::sqrt(vx * vx + vy * vy);
+    vx /= nrm; vy /= nrm;
+    const double dx = px - x[a], dy = py - y[a];
+    const double t = dx * vx + dy * vy;
+    const double ex = vx * t - dx, ey = vy * t - dy;
+    return std::sqrt(ex * ex + ey * ey) < 1e-9;
+  };
+  auto sticky = [&](int g) { return s.surfaces.at(g).btype[2] == 0; }; // bctype() falls through to minusDiffusionBtype (:40-51)
+  const int order[3] = {0, 2, 1};
+  for (long e = 0; e < S.nT; e++) {
+    const int a = tri[3 * e], b = tri[3 * e + 1], cv = tri[3 * e + 2];
+    for (int i = 0; i < NL; i++) {
+      const double px = x[a] + (x[b] - x[a]) * p2::node_x(i) + (x[cv] - x[a]) * p2::node_y(i);
+      const double py = y[a] + (y[b] - y[a]) * p2::node_x(i) + (y[cv] - y[a]) * p2::node_y(i);
+      int pg = -1;
+      for (int fi = 0; fi < 3; fi++) {
+        const int f = order[fi];
+        if (S.h_fphys[3 * e + f] >= 0) {
+          if (on_line(px, py, (int)e, f)) if (pg == -1 || !sticky(pg)) pg = S.h_fphys[3 * e + f];
+        } else {
+          const int o = S.h_nbr[3 * e + f];
+          for (int gi = 0; gi < 3; gi++) {
+            const int f2 = order[gi];
+            if (S.h_fphys[3 * o + f2] >= 0 && on_line(px, py, o, f2)) if (pg == -1 || !sticky(pg)) pg = S.h_fphys[3 * o + f2];
+          }
+        }
+      }
+      const int d = S.h_e2d[NL * e + i];
+      if (pg > -1 && s.surfaces.at(pg).btype[comp] == 0) { u[d] = s.surfaces[pg].dval[comp]; continue; }
+      const double yv = pb ? pbh[d] : 0.0;
+      u[d] = comp == 0 ? yv : (comp == 1 ? s.c0 * std::exp(-yv) : s.c0 * std::exp(+yv));
+    }
+  }
+  out.d.upload(u.data(), S.nd, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+} // namespace pnp

@@ -306,6 +306,20 @@ pnp_status pnp_write_vtk(pnp_ctx*, const char* name, int n, const int* vec_handl
 /* ---- initial guess / Dirichlet values: interpolate(BCExtension) (dirichlet_bc.hh:54-123) --- */
 /* component 0: phi, 1: c+, 2: c-; pb_vec < 0 means a zero PB field; out is a 1-field vector */
 pnp_status pnp_interpolate_bcext(pnp_ctx*, int component, int pb_vec, int out_vec);
+
+/* ---- quadratic elements: the reference's -DPDEGREE=2 programs (src/Makefile.am:57-110; Pk2DLocalFiniteElementMap<..., 
+ * PDEGREE>, instationary_pnp_from_pb_md.hh:26-28,125; stationary_pnp.hh:190-193) ----
+ * pnp_space_set_degree(ctx, 2) before pnp_mesh_finalize() selects the P2 space: per field one dof per edge, then one per
+ * vertex -- dof k < n_edges sits on edge k (edges ordered by (min vertex, max vertex), pnp_space_edges), dof n_edges + v
+ * on vertex v; fields lexicographic.  Vectors (pnp_vec_upload/download), constraints, patterns (pnp_pattern_get: scalar
+ * BCRS, ascending columns) and matrix values use that numbering; it is also the device layout (CSR matrices, no
+ * renumbering).  Operators, residual, Jacobian (both modes), SpMV, BiCGSTAB/CG with Richardson or Jacobi, Newton,
+ * StationaryLinearProblemSolver, the one-step methods and interpolate(BCExtension) work as for degree 1; SSOR / ILU0 /
+ * AMG, refinement carry-over, output writers and partitioned meshes answer PNP_E_ARG.  One GPU. */
+pnp_status pnp_space_set_degree(pnp_ctx*, int degree);
+/* degree, number of edges (0 for degree 1) and scalar dofs per field */
+pnp_status pnp_space_sizes(pnp_ctx*, int* degree, long* n_edges, long* ndof);
+pnp_status pnp_space_edges(pnp_ctx*, int* va /*[n_edges]*/, int* vb);
 /* packs three 1-field vectors into a 3-field vector / extracts one field */
 pnp_status pnp_vec_pack3(pnp_ctx*, int dst3, int phi, int cp, int cm);
 pnp_status pnp_vec_extract(pnp_ctx*, int src3, int field, int dst1);

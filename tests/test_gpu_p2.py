@@ -1,0 +1,293 @@
+"""GPU parity tests of the quadratic-element path (pnp_space_set_degree(ctx, 2): the reference's -DPDEGREE=2 programs,
+src/Makefile.am:57-110) against the oracle's P2 restatement (oracle/pnp_oracle_p2.hpp) on the same inputs, through the C ABI.
+
+Bars as for linear elements: dof numbering, constraints and pattern bit-exact; residual and Jacobian entries within 1e-12 of
+the entry's scale (sum of |element contributions|); equal Newton iteration counts, converged fields within 1e-8 relative L2."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import util
+from oracle import binding as ora
+
+pytestmark = pytest.mark.gpu
+
+OPS = [ora.OP_PB, ora.OP_POISSON, ora.OP_DIFFUSION, ora.OP_MASS, ora.OP_PNP]
+TOL = 1e-12
+
+
+def _capi():
+    from dune_pnp_b200 import capi
+    return capi
+
+
+def make_ctx(name, levels=0):
+    capi = _capi()
+    a = util.load_mesh_arrays(name)
+    c = capi.Context(0)
+    c.mesh_set(**a)
+    c.params_read(util.cfg_path(name))
+    if levels:
+        c.mesh_refine(levels)
+    c.space_set_degree(2)
+    c.mesh_finalize(True)
+    m = ora.Mesh.from_arrays(**a).refine(levels)
+    p = ora.Params.read(util.cfg_path(name))
+    return c, m, p, ora.P2(m, p)
+
+
+def rel_err(got, want, scale):
+    e = np.abs(got - want)
+    out = np.where(scale > 0, e / np.maximum(scale, 1e-300), e)
+    return out.max() if out.size else 0.0
+
+
+def _state(P, op, seed=0):
+    rng = np.random.RandomState(seed)
+    F = ora.nfields(op)
+    return rng.uniform(-1, 1, F * P.nd), rng.uniform(0, 1, P.nd), rng.uniform(0, 1, P.nd)
+
+
+def _operator(c, op, a0, a1, valency, comp0=0):
+    capi = _capi()
+    h = c.operator(op, comp0)
+    if op == capi.OP_POISSON:
+        c.operator_set_coefficient(h, 0, c.vec(1, a0)); c.operator_set_coefficient(h, 1, c.vec(1, a1))
+    if op == capi.OP_DIFFUSION:
+        c.operator_set_coefficient(h, 0, c.vec(1, a0)); c.operator_set_valency(h, valency)
+    return h
+
+
+@pytest.mark.parametrize("name,levels", [(n, 0) for n in util.MESHES] + [("pore_small", 1)])
+def test_space_pattern_and_constraints_bit_exact(name, levels):
+    capi = _capi()
+    c, m, p, P = make_ctx(name, levels)
+    s = c.space_sizes()
+    assert s == dict(degree=2, n_edges=P.nE, ndof=P.nd)
+    va, vb = c.space_edges()
+    assert np.array_equal(va, P.eva) and np.array_equal(vb, P.evb)
+    for op, F, comp0 in ((capi.OP_PB, 1, 0), (capi.OP_DIFFUSION, 1, 1), (capi.OP_MASS, 1, 2), (capi.OP_PNP, 3, 0)):
+        h = c.operator(op, comp0)
+        assert np.array_equal(c.constraints(h, F), P.dirichlet(F, comp0))
+        rp, col = c.pattern(h, F)
+        rp_o, col_o = P.pattern(F, comp0)
+        assert np.array_equal(rp, rp_o) and np.array_equal(col, col_o)
+
+
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("name,levels", [(n, 0) for n in util.MESHES] + [("pore_small", 1)])
+def test_residual_parity(name, levels, op):
+    c, m, p, P = make_ctx(name, levels)
+    F = ora.nfields(op)
+    u, a0, a1 = _state(P, op)
+    h = _operator(c, op, a0, a1, -1.0)
+    vu, vr = c.vec(F, u), c.vec(F)
+    c.residual(h, vu, vr)
+    r = c.download(vr, F)
+    r_o, ab = P.residual(op, u, a0, a1, valency=-1.0, want_abs=True)
+    assert rel_err(r, r_o, ab) <= TOL
+    d = P.dirichlet(F, 0)
+    assert not r[d].any() and not r_o[d].any()
+    assert np.array_equal(c.download(vu, F), u)   # the upload / download pair is the identity in this numbering
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("name,levels", [("one_wall", 0), ("cylinder", 0), ("pore", 0), ("pore_small", 1)])
+def test_jacobian_parity(name, levels, op, mode):
+    c, m, p, P = make_ctx(name, levels)
+    F = ora.nfields(op)
+    u, a0, a1 = _state(P, op, seed=3)
+    h = _operator(c, op, a0, a1, -1.0)
+    vu, A = c.vec(F, u), c.matrix(h)
+    c.jacobian(h, vu, A, mode, 1e-11)
+    rp, col, val_o, ab = P.jacobian(op, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11, want_abs=True)
+    val = c.matrix_values(h, A, len(col))
+    assert rel_err(val, val_o, ab) <= TOL
+    # same element order, same operation order, no FMA contraction: most entries reproduce the oracle bit for bit
+    assert np.mean(val == val_o) > 0.9
+    # constrained rows are trivial
+    d = P.dirichlet(F, 0)
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    assert np.all(val[d[rows]] == 1.0)
+
+
+@pytest.mark.parametrize("op", [ora.OP_PB, ora.OP_PNP])
+def test_spmv_and_dots(op):
+    c, m, p, P = make_ctx("pore_small", 1)
+    F = ora.nfields(op)
+    u, a0, a1 = _state(P, op, seed=5)
+    h = _operator(c, op, a0, a1, 1.0)
+    vu, A = c.vec(F, u), c.matrix(h)
+    c.jacobian(h, vu, A, 1, 1e-11)
+    rp, col = c.pattern(h, F)
+    J = sp.csr_matrix((c.matrix_values(h, A, len(col)), col, rp))
+    x = np.random.RandomState(1).uniform(-1, 1, F * P.nd)
+    vx, vy = c.vec(F, x), c.vec(F)
+    c.spmv(A, vx, vy)
+    y = c.download(vy, F)
+    scale = abs(J) @ np.abs(x)
+    assert rel_err(y, J @ x, scale) <= 1e-14
+    assert abs(c.dot(vx, vy) - x @ y) <= 1e-12 * np.abs(x) @ np.abs(y)
+    assert abs(c.norm(vy) - np.linalg.norm(y)) <= 1e-13 * np.linalg.norm(y)
+
+
+@pytest.mark.parametrize("kind,prec", [(0, 0), (0, 1), (1, 1)])
+def test_linear_solvers(kind, prec):
+    """BiCGSTAB / CG with Richardson and Jacobi on the (symmetric positive definite) P2 Poisson matrix."""
+    capi = _capi()
+    c, m, p, P = make_ctx("cylinder")
+    z = np.zeros(P.nd)
+    h = _operator(c, capi.OP_POISSON, z, z, 1.0)
+    vu, A = c.vec(1, z), c.matrix(h)
+    c.jacobian(h, vu, A, 1, 1e-11)
+    rp, col = c.pattern(h, 1)
+    J = sp.csr_matrix((c.matrix_values(h, A, len(col)), col, rp))
+    b = np.random.RandomState(2).uniform(-1, 1, P.nd)
+    vz, vb = c.vec(1), c.vec(1, b)
+    res = c.solve(c.solver(kind, prec, 20000), A, vz, vb, 1e-10)
+    assert res.converged
+    zsol = c.download(vz, 1)
+    assert np.linalg.norm(J @ zsol - b) <= 2e-10 * np.linalg.norm(b)
+    assert np.linalg.norm(zsol - spla.spsolve(J.tocsc(), b)) <= 1e-6 * np.linalg.norm(zsol)
+
+
+@pytest.mark.parametrize("name", ["one_wall", "cylinder", "pore_small"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_newton_pb_matches_oracle(name, mode):
+    capi = _capi()
+    c, m, p, P = make_ctx(name)
+    h = c.operator(capi.OP_PB, 0)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 20000)
+    vu = c.vec(1)
+    tight = mode == 1   # (FD noise moves iteration counts at tight tolerances: the tight comparison uses the exact derivative)
+    kw = dict(reduction=1e-11, min_linear_reduction=1e-9) if tight else {}
+    st, res = c.newton(h, vu, s, c.newton_opts(jac_mode=mode, **kw))
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI, jac_mode=mode)
+    opts[12] = 20000
+    if tight:
+        opts[0], opts[2] = 1e-11, 1e-9
+    u_o, res_o = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
+    assert res.converged and res_o["converged"]
+    assert res.iterations == res_o["iterations"]
+    u = c.download(vu, 1)
+    tol = 1e-8 if tight else 10 * p.sys[7]
+    assert np.linalg.norm(u - u_o) <= tol * np.linalg.norm(u_o) + 1e-14
+    assert abs(res.first_defect - res_o["first_defect"]) <= 1e-12 * res_o["first_defect"]
+
+
+@pytest.mark.parametrize("comp", [0, 1, 2])
+@pytest.mark.parametrize("name", ["pore", "sphere"])
+def test_interpolate_bcext(name, comp):
+    c, m, p, P = make_ctx(name)
+    pb = np.sin(0.1 * P.x) * np.cos(0.07 * P.y)
+    vpb, vo = c.vec(1, pb), c.vec(1)
+    c.interpolate_bcext(comp, vpb, vo)
+    got, want = c.download(vo, 1), P.interpolate(comp, pb)
+    assert np.allclose(got, want, rtol=1e-15, atol=0)
+    d = P.dirichlet(1, comp)
+    assert np.array_equal(got[d], want[d])
+
+
+def test_newton_pnp_from_pb_matches_oracle():
+    """The stationary program with quadratic elements (stationary_pnp_from_pb.hh:105-185, :344-360): PB Newton solve, the
+    Boltzmann start from interpolate(BCExtension), then the coupled 3-field Newton solve -- exact derivative, BiCGSTAB + Jacobi."""
+    capi = _capi()
+    c, m, p, P = make_ctx("pore_small")
+    hpb = c.operator(capi.OP_PB, 0)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 50000)
+    vpb = c.vec(1)
+    st, r0 = c.newton(hpb, vpb, s, c.newton_opts(jac_mode=1, reduction=1e-11, min_linear_reduction=1e-9))
+    v = [c.vec(1) for _ in range(3)]
+    for k in range(3):
+        c.interpolate_bcext(k, vpb, v[k])
+    vu = c.vec(3)
+    c.pack3(vu, *v)
+    hp = c.operator(capi.OP_PNP, 0)
+    st, res = c.newton(hp, vu, s, c.newton_opts(jac_mode=1, reduction=1e-10, min_linear_reduction=1e-9))
+    # oracle
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI, jac_mode=1); opts[12] = 50000
+    opts[0], opts[2] = 1e-11, 1e-9
+    pb_o, _ = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
+    u0 = np.concatenate([P.interpolate(k, pb_o) for k in range(3)])
+    assert np.linalg.norm(np.concatenate([c.download(x, 1) for x in v]) - u0) <= 1e-8 * np.linalg.norm(u0)
+    opts[0] = 1e-10
+    u_o, res_o = P.newton(ora.OP_PNP, u0, opts)
+    assert res.converged and res_o["converged"] and res.iterations == res_o["iterations"]
+    u = c.download(vu, 3)
+    assert np.linalg.norm(u - u_o) <= 1e-8 * np.linalg.norm(u_o)
+    # pack / extract are the field blocks
+    w = c.vec(1)
+    for k in range(3):
+        c.extract(vu, k, w)
+        assert np.array_equal(c.download(w, 1), u[k * P.nd:(k + 1) * P.nd])
+
+
+def test_onestep_implicit_euler_is_the_linear_algebra_it_claims():
+    """One implicit-Euler step of the transport equation (OneStepGridOperator<DiffusionOperator, DiffusionTOperator>,
+    instationary_pnp_from_pb_md.hh:368-391) with quadratic elements: both operators are linear, so the new state solves
+    (M + dt A) x = M x_old on the free dofs with the boundary values on the constrained ones; checked with a direct solve
+    on the exported matrices."""
+    capi = _capi()
+    c, m, p, P = make_ctx("pore_small")
+    rng = np.random.RandomState(4)
+    phi = 0.5 * np.sin(3 * P.x) * np.cos(2 * P.y)
+    g = P.interpolate(1, phi)
+    d = P.dirichlet(1, 1)
+    x0 = g * (1 + 0.1 * rng.uniform(-1, 1, P.nd)); x0[d] = g[d]
+    dt = 0.05
+    h0 = _operator(c, capi.OP_DIFFUSION, phi, None, 1.0, comp0=1)
+    h1 = c.operator(capi.OP_MASS, 1)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 20000)
+    vx0, vg, vx1 = c.vec(1, x0), c.vec(1, g), c.vec(1)
+    res = c.onestep(h0, h1, s, dt, vx0, vg, vx1, 1e-12, capi.TIME_IMPLICIT_EULER, 1)
+    assert len(res) == 1 and res[0].converged
+    x1 = c.download(vx1, 1)
+    assert np.array_equal(x1[d], g[d]) and np.array_equal(c.download(vx0, 1), x0)
+    rp, col, a = P.jacobian(ora.OP_DIFFUSION, x0, phi, valency=1.0, mode=1, comp0=1)
+    _, _, b = P.jacobian(ora.OP_MASS, x0, comp0=1, mode=1)
+    A, M = sp.csr_matrix((a, col, rp)), sp.csr_matrix((b, col, rp))
+    # free rows: (M + dt A)(x1) = M x0 where constrained columns (dropped from the pattern) carry g through the residual
+    r1 = P.residual(ora.OP_MASS, x1, comp0=1) - P.residual(ora.OP_MASS, x0, comp0=1) + dt * P.residual(ora.OP_DIFFUSION, x1, phi, valency=1.0, comp0=1)
+    scale = abs(M + dt * A) @ np.abs(x1)
+    assert np.max(np.abs(r1[~d]) / scale[~d]) <= 1e-9
+
+
+def test_solve_on_an_externally_assembled_matrix():
+    capi = _capi()
+    c, m, p, P = make_ctx("cylinder")
+    u, a0, a1 = _state(P, ora.OP_PB, seed=7)
+    rp, col, val = P.jacobian(ora.OP_PB, 0.1 * u, mode=1)
+    h = c.operator(capi.OP_PB, 0)
+    A = c.matrix(h)
+    c.matrix_set_csr(h, A, rp, col, val)
+    assert np.array_equal(c.matrix_values(h, A, len(col)), val)
+    b = np.random.RandomState(3).uniform(-1, 1, P.nd)
+    vz, vb = c.vec(1), c.vec(1, b)
+    assert c.solve(c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 20000), A, vz, vb, 1e-10).converged
+    J = sp.csr_matrix((val, col, rp))
+    assert np.linalg.norm(J @ c.download(vz, 1) - b) <= 2e-10 * np.linalg.norm(b)
+    bad = col.copy(); bad[1] += 1
+    with pytest.raises(capi.PnpError):
+        c.matrix_set_csr(h, A, rp, bad, val)
+
+
+def test_errors_are_reported():
+    capi = _capi()
+    c, m, p, P = make_ctx("one_wall")
+    with pytest.raises(capi.PnpError) as e:
+        c.space_set_degree(1)                       # after finalize
+    assert e.value.status == 8                      # PNP_E_ARG
+    h = c.operator(capi.OP_PB, 0)
+    vu = c.vec(1)
+    for prec in (capi.PREC_SSOR, capi.PREC_ILU0, capi.PREC_AMG):
+        st, res = c.newton(h, vu, c.solver(capi.SOLVER_BCGS, prec, 100), c.newton_opts(), check=False)
+        assert st == 8 and b"quadratic" in capi.lib().pnp_last_error(c._h)
+    with pytest.raises(capi.PnpError):
+        c.write_vtk("/tmp/should_not_exist_p2", [vu], ["u"])
+    with pytest.raises(capi.PnpError):
+        c.residual(h, c.vec(3), vu)                 # field count mismatch
+    c2 = capi.Context(0)
+    with pytest.raises(capi.PnpError):
+        c2.space_set_degree(3)
