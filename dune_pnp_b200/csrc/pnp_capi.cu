@@ -525,7 +525,8 @@ pnp_status pnp_solver_get(pnp_ctx* ctx, int s, const char* name, double* value) 
   API_BEGIN(ctx)
   PNP_REQUIRE(name && value, PNP_E_ARG, "null argument");
   const std::string n(name);
-  if (n == "ssor_levels") *value = sweep_levels(c.solver(s), false);
+  if (c.degree == 2 && (n == "ssor_levels" || n == "ilu0_levels")) *value = c.solver(s).csr_levels;
+  else if (n == "ssor_levels") *value = sweep_levels(c.solver(s), false);
   else if (n == "ilu0_levels") *value = sweep_levels(c.solver(s), true);
   else if (n == "amg_graph") *value = amg_graph_state(c.solver(s));
   else PNP_REQUIRE(false, PNP_E_ARG, "unknown solver fact");

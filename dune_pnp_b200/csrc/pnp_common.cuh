@@ -104,6 +104,7 @@ struct Matrix {
   DBuf<double> vals; // nplanes * nslots (star layout) or csr_nnz (quadratic elements)
   // quadratic elements (pnp_p2.cu): scalar CSR in the reference's dof numbering; the pattern belongs to the space
   const int* csr_rp = nullptr; const int* csr_col = nullptr; long csr_nnz = 0, csr_n = 0;
+  void* csr_pattern = nullptr; // the P2Pattern the pointers belong to (level schedule of the sweeps)
 };
 
 struct Operator {
@@ -145,6 +146,7 @@ struct Solver {
   double opt(const char* name, double dflt) const { auto it = opts.find(name); return it == opts.end() ? dflt : it->second; }
   DBuf<double> w[6]; // Krylov work vectors, sized on first use
   DBuf<double> dinv; // Jacobi: inverse diagonal
+  DBuf<double> csr_lu; int csr_levels = 0; // quadratic elements: ILU0 factor on the CSR pattern; levels of the last sweep set-up
   void ensure(size_t n) { for (auto& b : w) if (b.n != n) b.alloc(n); if (dinv.n != n) dinv.alloc(n); }
 };
 
@@ -323,6 +325,9 @@ void p2_assemble_residual(Ctx&, const Operator&, Vec& u, Vec& r);
 void p2_assemble_jacobian(Ctx&, const Operator&, Vec& u, Matrix& A, int mode, double eps);
 void csr_spmv(Ctx&, const Matrix& A, const double* x, double* y);
 void csr_diag_inverse(Ctx&, const Matrix& A, double* dinv);
+void csr_sweep_setup(Ctx&, Solver&, const Matrix& A, bool ilu);
+void csr_ssor_apply(Ctx&, Solver&, const Matrix& A, const double* d, double* y);
+void csr_ilu0_apply(Ctx&, Solver&, const Matrix& A, const double* d, double* y);
 const unsigned char* p2_dirichlet_flags(Ctx&); // per scalar dof: bit c = Dirichlet for BC component c (device)
 void p2_sizes(Ctx&, long* nE, long* nd);
 void p2_edges(Ctx&, int* eva, int* evb);

@@ -207,9 +207,9 @@ void ilu0_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y);
 namespace {
 void prec_setup(Ctx& c, Solver& S, const Matrix& A) {
   if (A.csr_rp) {
-    PNP_REQUIRE(S.prec == PNP_PREC_NONE || S.prec == PNP_PREC_JACOBI, PNP_E_ARG,
-                "quadratic elements: the preconditioners are none (Richardson) and Jacobi");
+    PNP_REQUIRE(S.prec != PNP_PREC_AMG, PNP_E_ARG, "quadratic elements: the preconditioners are none (Richardson), Jacobi, SSOR and ILU0");
     if (S.prec == PNP_PREC_JACOBI) csr_diag_inverse(c, A, S.dinv.p);
+    if (S.prec == PNP_PREC_SSOR || S.prec == PNP_PREC_ILU0) csr_sweep_setup(c, S, A, S.prec == PNP_PREC_ILU0);
     return;
   }
   switch (S.prec) {
@@ -235,8 +235,8 @@ void prec_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double* y, 
       k_diag_apply<0><<<grid_for(n, RED_BLOCK), RED_BLOCK, 0, c.stream>>>(S.dinv.p, d, y, n, nullptr);
       PNP_CHECK_LAUNCH(); c.launches++; c.acct(Ctx::ACC_BLAS1, 24.0 * n);
       break;
-    case PNP_PREC_SSOR: ssor_apply(c, S, A, d, y); break;
-    case PNP_PREC_ILU0: ilu0_apply(c, S, A, d, y); break;
+    case PNP_PREC_SSOR: if (A.csr_rp) csr_ssor_apply(c, S, A, d, y); else ssor_apply(c, S, A, d, y); break;
+    case PNP_PREC_ILU0: if (A.csr_rp) csr_ilu0_apply(c, S, A, d, y); else ilu0_apply(c, S, A, d, y); break;
     case PNP_PREC_AMG: amg_apply(c, S, A, d, y); break;
     default: break;
   }

@@ -26,6 +26,10 @@ struct P2Pattern {
   long nnz = 0;
   std::vector<int> h_rp, h_col;
   DBuf<int> rp, col;
+  // level schedule of the row-order sweeps (SeqSSOR, SeqILU0), built on first use: rows grouped by level, diagonal positions
+  int nlev = 0;
+  std::vector<int> lev_ptr;
+  DBuf<int> order, diag;
 };
 
 struct P2Space {
@@ -303,7 +307,7 @@ void p2_matrix_init(Ctx& c, Matrix& A, const Operator& op) {
   const int F = op_fields(op.op);
   P2Pattern& Pn = p2_pattern(c, F, F == 3 ? 0 : op.comp0);
   A.op = op.op; A.nplanes = op_planes(op.op); A.comp0 = op.comp0;
-  A.csr_rp = Pn.rp.p; A.csr_col = Pn.col.p; A.csr_nnz = Pn.nnz; A.csr_n = F * space(c).nd;
+  A.csr_rp = Pn.rp.p; A.csr_col = Pn.col.p; A.csr_nnz = Pn.nnz; A.csr_n = F * space(c).nd; A.csr_pattern = &Pn;
   if (A.vals.n != (size_t)Pn.nnz) { A.vals.alloc(Pn.nnz); A.vals.zero(c.stream); }
 }
 
@@ -366,6 +370,129 @@ void csr_diag_inverse(Ctx& c, const Matrix& A, double* dinv) {
 }
 
 const unsigned char* p2_dirichlet_flags(Ctx& c) { return space(c).dir.p; }
+
+// ---- SeqSSOR / SeqILU0 on the CSR matrix (the reference's default backend is BiCGSTAB + SSOR, instationary_pnp_from_pb_md.hh:
+// 188-191).  A row-order sweep only depends on the relative order of COUPLED rows (pnp_sweep.cuh): level(i) = 1 + max level of
+// the coupled rows before i; rows of one level are mutually uncoupled (the pattern is structurally symmetric) and run in
+// parallel, levels in sequence -- ascending for the forward sweep, descending for the backward one.  One launch per level;
+// every row does the oracle's operations in the oracle's order (ascending columns, no FMA), so the application is bit-identical
+// to the sequential sweep.
+namespace {
+__global__ void k_csr_gs_level(const int* __restrict__ rows, int n, const int* __restrict__ rp, const int* __restrict__ col,
+                               const int* __restrict__ diag, const double* __restrict__ vals, const double* __restrict__ d, double* x) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = rows[t];
+    double sum = d[i];
+    for (int k = rp[i]; k < rp[i + 1]; k++) sum -= vals[k] * x[col[k]];
+    x[i] += sum / vals[diag[i]];
+  }
+}
+// bilu0_decomposition of the rows of one level (dune-istl 2.2 ilu.hh; oracle ilu0_decompose)
+__global__ void k_csr_ilu0_level(const int* __restrict__ rows, int n, const int* __restrict__ rp, const int* __restrict__ col,
+                                 const int* __restrict__ diag, double* lu) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = rows[t], r1 = rp[i + 1];
+    for (int kj = rp[i]; kj < r1 && col[kj] < i; kj++) {
+      const int j = col[kj];
+      const double l = lu[kj] * lu[diag[j]];
+      lu[kj] = l;
+      int ki = kj + 1;
+      for (int kk = diag[j] + 1; kk < rp[j + 1]; kk++) {
+        while (ki < r1 && col[ki] < col[kk]) ki++;
+        if (ki < r1 && col[ki] == col[kk]) lu[ki] -= l * lu[kk];
+      }
+    }
+    lu[diag[i]] = 1.0 / lu[diag[i]];
+  }
+}
+__global__ void k_csr_ilu0_forward(const int* __restrict__ rows, int n, const int* __restrict__ rp, const int* __restrict__ col,
+                                   const double* __restrict__ lu, const double* __restrict__ d, double* x) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = rows[t];
+    double sum = d[i];
+    for (int k = rp[i]; k < rp[i + 1] && col[k] < i; k++) sum -= lu[k] * x[col[k]];
+    x[i] = sum;
+  }
+}
+__global__ void k_csr_ilu0_backward(const int* __restrict__ rows, int n, const int* __restrict__ rp, const int* __restrict__ col,
+                                    const int* __restrict__ diag, const double* __restrict__ lu, double* x) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = rows[t];
+    double sum = x[i];
+    for (int k = diag[i] + 1; k < rp[i + 1]; k++) sum -= lu[k] * x[col[k]];
+    x[i] = sum * lu[diag[i]];
+  }
+}
+P2Pattern& pattern_of(const Matrix& A) {
+  PNP_REQUIRE(A.csr_pattern, PNP_E_ARG, "matrix has no CSR pattern");
+  return *static_cast<P2Pattern*>(A.csr_pattern);
+}
+void build_levels(Ctx& c, P2Pattern& Pn) {
+  if (Pn.nlev) return;
+  const long N = (long)Pn.h_rp.size() - 1;
+  std::vector<int> lev(N), dg(N, -1);
+  int nlev = 0;
+  for (long i = 0; i < N; i++) {
+    int l = 0;
+    for (int k = Pn.h_rp[i]; k < Pn.h_rp[i + 1]; k++) {
+      const int j = Pn.h_col[k];
+      if (j < i) l = std::max(l, lev[j] + 1);
+      else if (j == i) dg[i] = k;
+    }
+    PNP_REQUIRE(dg[i] >= 0, PNP_E_ARG, "matrix row without diagonal entry");
+    lev[i] = l; nlev = std::max(nlev, l + 1);
+  }
+  Pn.lev_ptr.assign(nlev + 1, 0);
+  for (long i = 0; i < N; i++) Pn.lev_ptr[lev[i] + 1]++;
+  for (int l = 0; l < nlev; l++) Pn.lev_ptr[l + 1] += Pn.lev_ptr[l];
+  std::vector<int> order(N), fill(Pn.lev_ptr.begin(), Pn.lev_ptr.end() - 1);
+  for (long i = 0; i < N; i++) order[fill[lev[i]]++] = (int)i;
+  Pn.order.alloc(N); Pn.order.upload(order.data(), N, c.stream);
+  Pn.diag.alloc(N); Pn.diag.upload(dg.data(), N, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  Pn.nlev = nlev;
+}
+template <class Fn> void for_levels(Ctx& c, const P2Pattern& Pn, bool ascending, Fn fn) {
+  for (int s = 0; s < Pn.nlev; s++) {
+    const int l = ascending ? s : Pn.nlev - 1 - s, n = Pn.lev_ptr[l + 1] - Pn.lev_ptr[l];
+    fn(Pn.order.p + Pn.lev_ptr[l], n, grid_for(n, 128));
+    PNP_CHECK_LAUNCH(); c.launches++;
+  }
+}
+} // namespace
+
+void csr_sweep_setup(Ctx& c, Solver& S, const Matrix& A, bool ilu) {
+  P2Pattern& Pn = pattern_of(A);
+  build_levels(c, Pn);
+  S.csr_levels = Pn.nlev;
+  if (!ilu) return;
+  if (S.csr_lu.n != (size_t)A.csr_nnz) S.csr_lu.alloc(A.csr_nnz);
+  vec_copy(c, A.vals.p, S.csr_lu.p, A.csr_nnz);
+  for_levels(c, Pn, true, [&](const int* rows, int n, int g) {
+    k_csr_ilu0_level<<<g, 128, 0, c.stream>>>(rows, n, A.csr_rp, A.csr_col, Pn.diag.p, S.csr_lu.p);
+  });
+}
+// v = 0; `prec_steps` x (forward sweep, backward sweep), relaxation factor 1
+void csr_ssor_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double* y) {
+  P2Pattern& Pn = pattern_of(A);
+  vec_zero(c, y, A.csr_n);
+  for (int s = 0; s < S.prec_steps; s++)
+    for (int dir = 0; dir < 2; dir++)
+      for_levels(c, Pn, dir == 0, [&](const int* rows, int n, int g) {
+        k_csr_gs_level<<<g, 128, 0, c.stream>>>(rows, n, A.csr_rp, A.csr_col, Pn.diag.p, A.vals.p, d, y);
+      });
+  c.acct(Ctx::ACC_SPMV_FINE, 2.0 * S.prec_steps * (12.0 * (double)A.csr_nnz + 28.0 * (double)A.csr_n));
+}
+void csr_ilu0_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double* y) {
+  P2Pattern& Pn = pattern_of(A);
+  for_levels(c, Pn, true, [&](const int* rows, int n, int g) {
+    k_csr_ilu0_forward<<<g, 128, 0, c.stream>>>(rows, n, A.csr_rp, A.csr_col, S.csr_lu.p, d, y);
+  });
+  for_levels(c, Pn, false, [&](const int* rows, int n, int g) {
+    k_csr_ilu0_backward<<<g, 128, 0, c.stream>>>(rows, n, A.csr_rp, A.csr_col, Pn.diag.p, S.csr_lu.p, y);
+  });
+  c.acct(Ctx::ACC_SPMV_FINE, 12.0 * (double)A.csr_nnz + 32.0 * (double)A.csr_n);
+}
 
 // ---- the boundary's views of the space ----
 void p2_sizes(Ctx& c, long* nE, long* nd) { P2Space& S = space(c); if (nE) *nE = S.nE; if (nd) *nd = S.nd; }

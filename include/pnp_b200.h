@@ -313,9 +313,10 @@ pnp_status pnp_interpolate_bcext(pnp_ctx*, int component, int pb_vec, int out_ve
  * vertex -- dof k < n_edges sits on edge k (edges ordered by (min vertex, max vertex), pnp_space_edges), dof n_edges + v
  * on vertex v; fields lexicographic.  Vectors (pnp_vec_upload/download), constraints, patterns (pnp_pattern_get: scalar
  * BCRS, ascending columns) and matrix values use that numbering; it is also the device layout (CSR matrices, no
- * renumbering).  Operators, residual, Jacobian (both modes), SpMV, BiCGSTAB/CG with Richardson or Jacobi, Newton,
- * StationaryLinearProblemSolver, the one-step methods and interpolate(BCExtension) work as for degree 1; SSOR / ILU0 /
- * AMG, refinement carry-over, output writers and partitioned meshes answer PNP_E_ARG.  One GPU. */
+ * renumbering).  Operators, residual, Jacobian (both modes), SpMV, BiCGSTAB/CG with Richardson, Jacobi, SSOR(n) or ILU0
+ * (row-order sweeps, level-scheduled), Newton, StationaryLinearProblemSolver, the one-step methods and
+ * interpolate(BCExtension) work as for degree 1; the multigrid preconditioner, refinement carry-over, the output writers
+ * and partitioned meshes answer PNP_E_ARG.  One GPU. */
 pnp_status pnp_space_set_degree(pnp_ctx*, int degree);
 /* degree, number of edges (0 for degree 1) and scalar dofs per field */
 pnp_status pnp_space_sizes(pnp_ctx*, int* degree, long* n_edges, long* ndof);

@@ -15,6 +15,10 @@ pytestmark = pytest.mark.gpu
 
 OPS = [ora.OP_PB, ora.OP_POISSON, ora.OP_DIFFUSION, ora.OP_MASS, ora.OP_PNP]
 TOL = 1e-12
+# exact-derivative mode (not in the reference): the PB entry is stiffness + kappa^2 cosh(u) * mass summed INSIDE one element, and
+# the device's and glibc's cosh differ in the last bit; where the two parts cancel, the per-entry scale `ab` (sum over elements
+# of |element contribution|) does not see the larger terms the rounding acted on.  Same bar as for linear elements.
+TOL_EXACT = 1e-10
 
 
 def _capi():
@@ -104,9 +108,9 @@ def test_jacobian_parity(name, levels, op, mode):
     c.jacobian(h, vu, A, mode, 1e-11)
     rp, col, val_o, ab = P.jacobian(op, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11, want_abs=True)
     val = c.matrix_values(h, A, len(col))
-    assert rel_err(val, val_o, ab) <= TOL
+    assert rel_err(val, val_o, ab) <= (TOL if mode == 0 else TOL_EXACT)
     # same element order, same operation order, no FMA contraction: most entries reproduce the oracle bit for bit
-    assert np.mean(val == val_o) > 0.9
+    assert np.mean(val == val_o) > (0.9 if mode == 0 or op != ora.OP_PB else 0.0)
     # constrained rows are trivial
     d = P.dirichlet(F, 0)
     rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
@@ -153,6 +157,52 @@ def test_linear_solvers(kind, prec):
     assert np.linalg.norm(zsol - spla.spsolve(J.tocsc(), b)) <= 1e-6 * np.linalg.norm(zsol)
 
 
+@pytest.mark.parametrize("prec,steps", [(2, 1), (2, 3), (3, 1)])
+@pytest.mark.parametrize("name,levels,op", [("pore_small", 1, ora.OP_PB), ("pore", 0, ora.OP_PNP), ("cylinder", 0, ora.OP_DIFFUSION)])
+def test_ssor_ilu0_application_equals_sequential_sweep(name, levels, op, prec, steps):
+    """SeqSSOR(n) / SeqILU0 in the row order of the P2 matrix: the level-scheduled device sweep does every row's operations in
+    the sequential sweep's order (ascending columns, no FMA) -- bit-identical to the CPU sweep."""
+    capi = _capi()
+    c, m, p, P = make_ctx(name, levels)
+    F = ora.nfields(op)
+    u, a0, a1 = _state(P, op, seed=9)
+    if op == ora.OP_PNP:
+        u[P.nd:] = 0.06 * (1 + 0.1 * u[P.nd:])
+    h = _operator(c, op, a0, a1, 1.0)
+    vu, A = c.vec(F, 0.3 * u if op != ora.OP_PNP else u), c.matrix(h)
+    c.jacobian(h, vu, A, 1, 1e-11)
+    rp, col = c.pattern(h, F)
+    val = c.matrix_values(h, A, len(col))
+    d = np.random.RandomState(8).uniform(-1, 1, F * P.nd)
+    s = c.solver(capi.SOLVER_BCGS, prec, 100, steps)
+    vd, vv = c.vec(F, d), c.vec(F)
+    c.precond_apply(s, A, vd, vv)
+    v, v_o = c.download(vv, F), ora.prec_apply(rp, col, val, d, prec, steps)
+    assert np.linalg.norm(v - v_o) <= 1e-13 * np.linalg.norm(v_o)
+    assert np.mean(v == v_o) > 0.9
+    nlev = c.solver_get(s, "ssor_levels" if prec == 2 else "ilu0_levels")
+    assert 1 <= nlev <= 400
+
+
+@pytest.mark.parametrize("kind,prec", [(0, 2), (1, 2), (0, 3), (1, 3)])
+def test_krylov_with_ssor_ilu0_matches_oracle_iteration_counts(kind, prec):
+    capi = _capi()
+    c, m, p, P = make_ctx("sphere", 1)
+    z = np.zeros(P.nd)
+    h = _operator(c, capi.OP_POISSON, z, z, 1.0)
+    vu, A = c.vec(1, z), c.matrix(h)
+    c.jacobian(h, vu, A, 1, 1e-11)
+    rp, col = c.pattern(h, 1)
+    val = c.matrix_values(h, A, len(col))
+    b = np.random.RandomState(2).uniform(-1, 1, P.nd)
+    vz, vb = c.vec(1), c.vec(1, b)
+    res = c.solve(c.solver(kind, prec, 2000), A, vz, vb, 1e-10)
+    z_o, res_o = ora.linsolve(rp, col, val, b, 1e-10, 2000, kind, prec)
+    assert res.converged and res_o["converged"]
+    assert abs(res.iterations - res_o["iterations"]) <= 1
+    assert np.linalg.norm(c.download(vz, 1) - z_o) <= 1e-7 * np.linalg.norm(z_o)
+
+
 @pytest.mark.parametrize("name", ["one_wall", "cylinder", "pore_small"])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_newton_pb_matches_oracle(name, mode):
@@ -190,13 +240,15 @@ def test_interpolate_bcext(name, comp):
     assert np.array_equal(got[d], want[d])
 
 
-def test_newton_pnp_from_pb_matches_oracle():
+@pytest.mark.parametrize("prec", [3, 2])
+def test_newton_pnp_from_pb_matches_oracle(prec):
     """The stationary program with quadratic elements (stationary_pnp_from_pb.hh:105-185, :344-360): PB Newton solve, the
-    Boltzmann start from interpolate(BCExtension), then the coupled 3-field Newton solve -- exact derivative, BiCGSTAB + Jacobi."""
+    Boltzmann start from interpolate(BCExtension), then the coupled 3-field Newton solve -- exact derivative, the reference's
+    default backend BiCGSTAB + SSOR(1) (~500 BiCGSTAB iterations per Newton step on this system) and BiCGSTAB + ILU0 (~50)."""
     capi = _capi()
     c, m, p, P = make_ctx("pore_small")
     hpb = c.operator(capi.OP_PB, 0)
-    s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 50000)
+    s = c.solver(capi.SOLVER_BCGS, prec, 50000, 1)
     vpb = c.vec(1)
     st, r0 = c.newton(hpb, vpb, s, c.newton_opts(jac_mode=1, reduction=1e-11, min_linear_reduction=1e-9))
     v = [c.vec(1) for _ in range(3)]
@@ -207,7 +259,7 @@ def test_newton_pnp_from_pb_matches_oracle():
     hp = c.operator(capi.OP_PNP, 0)
     st, res = c.newton(hp, vu, s, c.newton_opts(jac_mode=1, reduction=1e-10, min_linear_reduction=1e-9))
     # oracle
-    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_JACOBI, jac_mode=1); opts[12] = 50000
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=prec, jac_mode=1); opts[12] = 50000
     opts[0], opts[2] = 1e-11, 1e-9
     pb_o, _ = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
     u0 = np.concatenate([P.interpolate(k, pb_o) for k in range(3)])
@@ -281,7 +333,7 @@ def test_errors_are_reported():
     assert e.value.status == 8                      # PNP_E_ARG
     h = c.operator(capi.OP_PB, 0)
     vu = c.vec(1)
-    for prec in (capi.PREC_SSOR, capi.PREC_ILU0, capi.PREC_AMG):
+    for prec in (capi.PREC_AMG,):
         st, res = c.newton(h, vu, c.solver(capi.SOLVER_BCGS, prec, 100), c.newton_opts(), check=False)
         assert st == 8 and b"quadratic" in capi.lib().pnp_last_error(c._h)
     with pytest.raises(capi.PnpError):
