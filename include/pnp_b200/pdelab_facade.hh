@@ -48,7 +48,11 @@ class Grid {
   void readConfigFile(const std::string& cfg) { check(c_, pnp_params_read(c_, cfg.c_str())); }
   void readGmsh(const std::string& msh) { check(c_, pnp_mesh_read_gmsh(c_, msh.c_str())); }
   void globalRefine(int levels) { check(c_, pnp_mesh_refine(c_, levels)); }
+  // Pk2DLocalFiniteElementMap<GV, D, R, PDEGREE> (instationary_pnp_from_pb_md.hh:26-28,125): 1 (default) or 2, before finalize()
+  void setDegree(int pdegree) { check(c_, pnp_space_set_degree(c_, pdegree)); }
   void finalize(bool renumber = true) { check(c_, pnp_mesh_finalize(c_, renumber)); }
+  // gfs.size() per field: vertices, or edges + vertices for quadratic elements
+  long dofs() const { long nd = 0; check(c_, pnp_space_sizes(c_, nullptr, nullptr, &nd)); return nd; }
   long size() const { long nv = 0; pnp_mesh_sizes(c_, &nv, nullptr, nullptr, nullptr); return nv; }
   long ownedSize() const { long n = 0; pnp_mesh_owned(c_, &n); return n; }
   // MPIHelper + grid->loadBalance() (pnp_solver_main.cc:93-108): one process per GPU.  The NCCL id travels through a file
@@ -87,7 +91,7 @@ class Vector {
   ~Vector() { pnp_vec_destroy(g_.ctx(), h_); }
   Vector(const Vector&) = delete;
   void set(const std::vector<double>& host) { check(g_.ctx(), pnp_vec_upload(g_.ctx(), h_, host.data())); }
-  std::vector<double> get() const { std::vector<double> v(fields_ * g_.size()); check(g_.ctx(), pnp_vec_download(g_.ctx(), h_, v.data())); return v; }
+  std::vector<double> get() const { std::vector<double> v(fields_ * g_.dofs()); check(g_.ctx(), pnp_vec_download(g_.ctx(), h_, v.data())); return v; }
   void axpy(double a, const Vector& x) { check(g_.ctx(), pnp_vec_axpy(g_.ctx(), h_, a, x.h_)); }
   double two_norm() const { double n; check(g_.ctx(), pnp_vec_norm(g_.ctx(), h_, &n)); return n; }
   int handle() const { return h_; }

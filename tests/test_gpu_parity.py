@@ -670,12 +670,12 @@ def test_instationary_pnp_md_time_loop_matches_oracle(name, levels, tau, red, mo
 
 
 # ---- the reference's drivers on the C++ facade (include/pnp_b200/drivers.hh, examples/) ----
-def _build_example(name, tmp_path):
+def _build_example(name, tmp_path, flags=()):
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / name)
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", *flags, "-I", os.path.join(root, "include"),
                            os.path.join(root, "examples", name + ".cc"), "-L", os.path.join(root, "dune_pnp_b200"), "-lpnp_b200",
                            "-Wl,-rpath," + os.path.join(root, "dune_pnp_b200"), "-o", exe])
     return exe
@@ -723,12 +723,13 @@ def test_driver_instationary_pnp_md_runs_like_the_reference_binary(tmp_path):
         assert np.allclose(got, want, rtol=1e-9), (i, got, want)
 
 
-@pytest.mark.parametrize("example,args", [("stationary_pnp_from_pb", ["1"]), ("stationary_pnp", [])])
-def test_driver_stationary_examples_converge(example, args, tmp_path):
+@pytest.mark.parametrize("example,args,flags", [("stationary_pnp_from_pb", ["1"], ()), ("stationary_pnp", [], ()),
+                                                ("stationary_pnp_from_pb", [], ("-DPDEGREE=2",))])
+def test_driver_stationary_examples_converge(example, args, flags, tmp_path):
     import subprocess
     a = util.load_mesh_arrays("cylinder")
     util.write_gmsh(str(tmp_path / "cylinder.msh"), a)
-    exe = _build_example(example, tmp_path)
+    exe = _build_example(example, tmp_path, flags)
     out = subprocess.run([exe, util.cfg_path("cylinder"), str(tmp_path / "cylinder.msh")] + args, capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0 and "PNP Newton" in out.stdout, out.stdout + out.stderr
