@@ -603,21 +603,18 @@ pnp_status pnp_onestep_apply(pnp_ctx* ctx, int method, int op_space, int op_time
 }
 pnp_status pnp_ion_flux(pnp_ctx* ctx, int phi, int cp, int cm, double* ip, double* im) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements");
   PNP_REQUIRE(ip && im, PNP_E_ARG, "null output");
   ion_flux(c, c.vec(phi), c.vec(cp), c.vec(cm), ip, im);
   API_END
 }
 pnp_status pnp_write_cell_data(pnp_ctx* ctx, int v, const char* filename) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements");
   PNP_REQUIRE(filename, PNP_E_ARG, "null file name");
   write_cell_data(c, c.vec(v), filename);
   API_END
 }
 pnp_status pnp_write_vtk(pnp_ctx* ctx, const char* name, int n, const int* vec_handles, const char* const* names, int ascii) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements");
   PNP_REQUIRE(name && n >= 0 && (n == 0 || (vec_handles && names)), PNP_E_ARG, "null arguments");
   std::vector<const Vec*> f(n);
   for (int i = 0; i < n; i++) f[i] = &c.vec(vec_handles[i]);

@@ -335,6 +335,9 @@ void p2_constraints_get(Ctx&, const Operator&, char* out);
 long p2_pattern_export(Ctx&, const Operator&, int* rowptr, int* col);
 void p2_matrix_import(Ctx&, const Operator&, Matrix&, const int* rowptr, const int* col, const double* val);
 void p2_interpolate_bcext(Ctx&, int comp, const Vec* pb, Vec& out);
+void p2_ion_flux(Ctx&, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, double* im);
+void p2_write_cell_data(Ctx&, const Vec& u, const std::string& filename);
+void p2_vertex_values(Ctx&, const Vec& u, double* out);
 // pnp_output.cu
 void ion_flux(Ctx&, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, double* im);
 void write_cell_data(Ctx&, const Vec& u, const std::string& filename);

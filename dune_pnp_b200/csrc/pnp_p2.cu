@@ -38,6 +38,7 @@ struct P2Space {
   std::vector<int> h_edge_phys;                           // per edge: surface of a boundary edge, -1 inside
   std::vector<unsigned char> h_dir;                       // per scalar dof: bit c = Dirichlet for BC component c
   DBuf<int> e2d, fphys, inc_ptr, inc;                     // incidence: scalar dof -> (element * 8 + local node), elements ascending
+  std::vector<int> h_bfaces; DBuf<int> bfaces;            // boundary faces, element * 4 + face, in element / intersection order
   DBuf<unsigned char> dir;
   std::map<int, std::unique_ptr<P2Pattern>> patterns;     // key = 4 * F + comp0
   DBuf<double> scratch;
@@ -228,6 +229,9 @@ void p2_build(Ctx& c) {
   for (long d = 0; d < S->nd; d++) ptr[d + 1] += ptr[d];
   { std::vector<int> fill(ptr.begin(), ptr.end() - 1);
     for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) inc[fill[S->h_e2d[NL * e + i]]++] = (int)(e * 8 + i); }
+  { const int order[3] = {0, 2, 1};
+    for (long e = 0; e < nT; e++) for (int fi = 0; fi < 3; fi++) if (S->h_fphys[3 * e + order[fi]] >= 0) S->h_bfaces.push_back((int)(e * 4 + order[fi])); }
+  S->bfaces.alloc(S->h_bfaces.size()); S->bfaces.upload(S->h_bfaces.data(), S->h_bfaces.size(), c.stream);
   S->h_edge_phys.assign(S->nE, -1);
   for (long k = 0; k < S->nE; k++) if (edge_elem1[k] < 0) S->h_edge_phys[k] = edge_phys[k];
   S->e2d.alloc(S->h_e2d.size()); S->e2d.upload(S->h_e2d.data(), S->h_e2d.size(), c.stream);
@@ -520,6 +524,97 @@ void p2_matrix_import(Ctx& c, const Operator& op, Matrix& A, const int* rowptr, 
   PNP_REQUIRE(std::equal(Pn.h_rp.begin(), Pn.h_rp.end(), rowptr) && std::equal(Pn.h_col.begin(), Pn.h_col.end(), col), PNP_E_ARG,
               "CSR pattern differs from the operator's pattern (pnp_pattern_get)");
   A.vals.upload(val, Pn.nnz, c.stream);
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// ---- the time loop's diagnostics with quadratic functions (pnp_output.cu has the linear ones) ----
+namespace {
+// calcIonFlux (ionFlux.hh:51-83): one thread per boundary face; fields and gradients at the face centre
+__global__ void k_p2_ion_flux(const int* __restrict__ faces, int nF, const int* __restrict__ tri, const double* __restrict__ cx,
+                              const double* __restrict__ cy, const int* __restrict__ e2d, const double* __restrict__ phi,
+                              const double* __restrict__ cp, const double* __restrict__ cm, int cylindrical, double PI,
+                              double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nF) return;
+  const int e = faces[t] >> 2, f = faces[t] & 3;
+  const int la = f == 2 ? 1 : 0, lb = f == 0 ? 1 : 2, lc = 3 - la - lb;
+  const int v[3] = {tri[3 * e], tri[3 * e + 1], tri[3 * e + 2]};
+  const p2::Geo2 G = p2::make_geo2(cx[v[0]], cy[v[0]], cx[v[1]], cy[v[1]], cx[v[2]], cy[v[2]]);
+  const double VX[3] = {0.0, 1.0, 0.0}, VY[3] = {0.0, 0.0, 1.0};
+  const double ax = cx[v[la]], ay = cy[v[la]], bx = cx[v[lb]], by = cy[v[lb]];
+  const double ex = 0.5 * (ax + bx), ey = 0.5 * (ay + by);
+  const p2::BasisAt B = p2::basis_at(G, 0.5 * (VX[la] + VX[lb]), 0.5 * (VY[la] + VY[lb]));
+  double vcp = 0, vcm = 0, gphi[2] = {0, 0}, gcp[2] = {0, 0}, gcm[2] = {0, 0};
+  for (int k = 0; k < NL; k++) {
+    const int d = e2d[NL * e + k];
+    vcp += cp[d] * B.phi[k]; vcm += cm[d] * B.phi[k];
+    for (int r = 0; r < 2; r++) { gphi[r] += phi[d] * B.g[k][r]; gcp[r] += cp[d] * B.g[k][r]; gcm[r] += cm[d] * B.g[k][r]; }
+  }
+  const double len = sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
+  double factor = len;
+  if (cylindrical) factor *= 2 * PI * ey;
+  for (int r = 0; r < 2; r++) { gcp[r] *= -factor; gcm[r] *= -factor; gphi[r] *= factor; gphi[r] *= vcp; }
+  double nx = (by - ay) / len, ny = -(bx - ax) / len;
+  if (nx * (cx[v[lc]] - ex) + ny * (cy[v[lc]] - ey) > 0) { nx = -nx; ny = -ny; }
+  out[2 * t] = (gcp[0] + gphi[0]) * nx + (gcp[1] + gphi[1]) * ny;
+  const double ratio = vcm / vcp;
+  for (int r = 0; r < 2; r++) gphi[r] *= ratio;
+  out[2 * t + 1] = (gcm[0] - gphi[0]) * nx + (gcm[1] - gphi[1]) * ny;
+}
+// DataWriter::writeData: centre, value and gradient at the centre of every element
+__global__ void k_p2_cell_data(int nT, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
+                               const int* __restrict__ e2d, const double* __restrict__ u, double* __restrict__ out) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nT; e += gridDim.x * blockDim.x) {
+    const int a = tri[3 * e], b = tri[3 * e + 1], c = tri[3 * e + 2];
+    const p2::Geo2 G = p2::make_geo2(cx[a], cy[a], cx[b], cy[b], cx[c], cy[c]);
+    const p2::BasisAt B = p2::basis_at(G, 1.0 / 3.0, 1.0 / 3.0);
+    double val = 0, gr[2] = {0, 0};
+    for (int k = 0; k < NL; k++) {
+      const double uk = u[e2d[NL * e + k]];
+      val += uk * B.phi[k];
+      for (int d = 0; d < 2; d++) gr[d] += uk * B.g[k][d];
+    }
+    out[5 * (long)e] = (cx[a] + cx[b] + cx[c]) / 3.0; out[5 * (long)e + 1] = (cy[a] + cy[b] + cy[c]) / 3.0;
+    out[5 * (long)e + 2] = val; out[5 * (long)e + 3] = gr[0]; out[5 * (long)e + 4] = gr[1];
+  }
+}
+} // namespace
+
+void p2_ion_flux(Ctx& c, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, double* im) {
+  P2Space& S = space(c);
+  PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "parameters not set");
+  PNP_REQUIRE(phi.fields == 1 && cp.fields == 1 && cm.fields == 1, PNP_E_ARG, "ion flux: three 1-field vectors expected");
+  const int ns = c.params.n_surfaces, nF = (int)S.h_bfaces.size();
+  for (int s = 0; s < ns; s++) ip[s] = im[s] = 0.0;
+  if (!nF) return;
+  DBuf<double> d(2 * (size_t)nF);
+  k_p2_ion_flux<<<(nF + 127) / 128, 128, 0, c.stream>>>(S.bfaces.p, nF, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, phi.d.p, cp.d.p, cm.d.p,
+                                                      c.params.cylindrical, c.params.PI, d.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  const std::vector<double> h = d.to_host(c.stream);
+  for (int t = 0; t < nF; t++) { // per-surface sums in the element loop's order
+    const int pg = S.h_fphys[3 * (S.h_bfaces[t] >> 2) + (S.h_bfaces[t] & 3)];
+    if (pg >= ns) continue;
+    ip[pg] += h[2 * t]; im[pg] += h[2 * t + 1];
+  }
+}
+void p2_write_cell_data(Ctx& c, const Vec& u, const std::string& filename) {
+  P2Space& S = space(c);
+  PNP_REQUIRE(u.fields == 1, PNP_E_ARG, "writeData: a 1-field vector expected");
+  DBuf<double> d(5 * (size_t)S.nT);
+  k_p2_cell_data<<<grid_for(S.nT, 128), 128, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, u.d.p, d.p);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  const std::vector<double> h = d.to_host(c.stream);
+  std::FILE* f = std::fopen(filename.c_str(), "w");
+  PNP_REQUIRE(f, PNP_E_CONFIG, "cannot open " + filename);
+  for (long e = 0; e < S.nT; e++) std::fprintf(f, "%.5e %.5e\t%.5e\t%.5e %.5e\n", h[5 * e], h[5 * e + 1], h[5 * e + 2], h[5 * e + 3], h[5 * e + 4]);
+  std::fclose(f);
+}
+// values at the mesh vertices (what VTKWriter::addVertexData samples), reference numbering
+void p2_vertex_values(Ctx& c, const Vec& u, double* out) {
+  P2Space& S = space(c);
+  PNP_REQUIRE(u.fields == 1, PNP_E_ARG, "a 1-field vector expected");
+  PNP_CUDA(cudaMemcpyAsync(out, u.d.p + S.nE, S.nv * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 

@@ -7,10 +7,6 @@
 
 #include "pnp_b200/drivers.hh"
 
-#ifndef PDEGREE
-#define PDEGREE 1
-#endif
-
 using namespace Dune::PNPB200;
 
 int main(int argc, char** argv) {

@@ -11,6 +11,12 @@
 
 #include "pdelab_facade.hh"
 
+// polynomial degree of the Pk2DLocalFiniteElementMap, a compile-time switch as in the reference
+// (instationary_pnp_from_pb_md.hh:26-28; src/Makefile.am:54-110 builds every program with -DPDEGREE=1,2,3): 1 or 2 here
+#ifndef PDEGREE
+#define PDEGREE 1
+#endif
+
 namespace Dune {
 namespace PNPB200 {
 
@@ -128,6 +134,7 @@ class PnpSolverMain {
     check(grid.ctx(), pnp_params_get(grid.ctx(), nullptr, nullptr, meshfile, (int)sizeof meshfile));
     grid.readGmsh(meshfile);  // path as written in the config, relative to the working directory (sysparams.cc:44)
     if (refinements > 0) grid.globalRefine(refinements);
+    grid.setDegree(PDEGREE);
     grid.finalize();
     Vector uphi(grid, 1), ucp(grid, 1), ucm(grid, 1);
     ISTLBackend_NOVLP_BCGS_SSORk pbls(grid, (unsigned)sysparam(grid, 5), 1, (int)sysparam(grid, 15)); // LINEARSOLVER == 1 (:188-191)

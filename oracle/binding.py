@@ -354,6 +354,15 @@ class P2:
         _chk(lib().ora2_interpolate(self.mesh.h, self.params.h, comp, _d(pb), _d(u)))
         return u
 
+    def ion_flux(self, phi, cp, cm):
+        ns = int(self.params.sys[0])
+        ip = np.zeros(ns); im = np.zeros(ns)
+        _chk(lib().ora2_ion_flux(self.mesh.h, self.params.h, _d(_f64(phi)), _d(_f64(cp)), _d(_f64(cm)), _d(ip), _d(im)))
+        return ip, im
+
+    def write_cell_data(self, u, filename):
+        _chk(lib().ora2_write_cell_data(self.mesh.h, self.params.h, _d(_f64(u)), filename.encode()))
+
     def newton(self, op, u0, opts, aux0=None, aux1=None, valency=1.0, intorder=-1, comp0=0, cap=128):
         u = _f64(u0).copy(); aux0 = _f64(aux0); aux1 = _f64(aux1)
         res = np.zeros(16); hist = np.zeros(cap); lin = np.zeros(cap, dtype=np.int32)

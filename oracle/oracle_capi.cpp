@@ -444,6 +444,20 @@ int ora2_newton(void* mh, void* ph, int op, int comp0, double* u, const double* 
   return 0;
   ORA_CATCH(-1)
 }
+int ora2_ion_flux(void* mh, void* ph, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
+  ORA_TRY
+  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
+  p2::ion_flux2(sp, phi, cp, cm, ip, im);
+  return 0;
+  ORA_CATCH(-1)
+}
+int ora2_write_cell_data(void* mh, void* ph, const double* u, const char* filename) {
+  ORA_TRY
+  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
+  p2::write_cell_data2(sp, u, filename);
+  return 0;
+  ORA_CATCH(-1)
+}
 void ora2_basis(double x, double y, double* phi, double* grad) {
   p2::basis(x, y, phi);
   double g[6][2]; p2::basis_grad(x, y, g);

@@ -390,5 +390,64 @@ inline void interpolate_bcext2(const Space2& sp, int comp, const double* pb, dou
     for (int i = 0; i < NL; i++) u[sp.sdof(e, i)] = bcext_eval2(sp, comp, pb, e, i);
 }
 
+// calcIonFlux (ionFlux.hh:8-96) with quadratic functions: DiscreteGridFunction / DiscreteGridFunctionGradient evaluated at
+// the local coordinates of the face centre -- the basis sum over the element's 6 dofs per field
+inline void ion_flux2(const Space2& sp, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
+  const Mesh& m = *sp.m; const Sysparams& s = *sp.s;
+  static const double VX[3] = {0.0, 1.0, 0.0}, VY[3] = {0.0, 0.0, 1.0}; // reference vertices
+  for (int i = 0; i < s.n_surfaces; i++) { ip[i] = 0; im[i] = 0; }
+  for (int e = 0; e < m.nT; e++) {
+    const ElemGeo g = elem_geo(m, e);
+    const int* tv = &m.tri[3 * e];
+    for (int gi = 0; gi < 3; gi++) {
+      const int f = FACE_ITER[gi];
+      const int seg = m.fseg[3 * e + f];
+      if (seg < 0) continue;
+      const int la = FACE_V[f][0], lb = FACE_V[f][1], lc = 3 - la - lb;
+      const double ax = m.x[tv[la]], ay = m.y[tv[la]], bx = m.x[tv[lb]], by = m.y[tv[lb]];
+      const double ex = 0.5 * (ax + bx), ey = 0.5 * (ay + by);
+      const BasisAt B = basis_at(g, 0.5 * (VX[la] + VX[lb]), 0.5 * (VY[la] + VY[lb]));
+      double vcp = 0, vcm = 0, gphi[2] = {0, 0}, gcp[2] = {0, 0}, gcm[2] = {0, 0};
+      for (int k = 0; k < NL; k++) {
+        const int d = sp.sdof(e, k);
+        vcp += cp[d] * B.phi[k]; vcm += cm[d] * B.phi[k];
+        for (int r = 0; r < 2; r++) { gphi[r] += phi[d] * B.g[k][r]; gcp[r] += cp[d] * B.g[k][r]; gcm[r] += cm[d] * B.g[k][r]; }
+      }
+      const double len = std::sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
+      double factor = len;
+      if (s.cylindrical) factor *= 2 * s.PI * ey;
+      for (int r = 0; r < 2; r++) { gcp[r] *= -factor; gcm[r] *= -factor; gphi[r] *= factor; gphi[r] *= vcp; }
+      double nx = (by - ay) / len, ny = -(bx - ax) / len;
+      if (nx * (m.x[tv[lc]] - ex) + ny * (m.y[tv[lc]] - ey) > 0) { nx = -nx; ny = -ny; }
+      const int pg = m.bphys[seg];
+      ip[pg] += (gcp[0] + gphi[0]) * nx + (gcp[1] + gphi[1]) * ny;
+      const double ratio = vcm / vcp;
+      for (int r = 0; r < 2; r++) gphi[r] *= ratio;
+      im[pg] += (gcm[0] - gphi[0]) * nx + (gcm[1] - gphi[1]) * ny;
+    }
+  }
+}
+
+// DataWriter::writeData (datawriter.hh:45-94) with a quadratic function: value and gradient at the element centre
+inline void write_cell_data2(const Space2& sp, const double* u, const std::string& filename) {
+  const Mesh& m = *sp.m;
+  std::ofstream out(filename.c_str(), std::ios::out);
+  out.precision(5);
+  for (int e = 0; e < m.nT; e++) {
+    const ElemGeo g = elem_geo(m, e);
+    const double cx = (g.x0 + g.x1 + g.x2) / 3.0, cy = (g.y0 + g.y1 + g.y2) / 3.0;
+    const BasisAt B = basis_at(g, 1.0 / 3.0, 1.0 / 3.0);
+    double val = 0, gr[2] = {0, 0};
+    for (int k = 0; k < NL; k++) {
+      const double uk = u[sp.sdof(e, k)];
+      val += uk * B.phi[k];
+      for (int d = 0; d < 2; d++) gr[d] += uk * B.g[k][d];
+    }
+    out << std::left << std::scientific << cx << " " << cy << "\t";
+    out << std::left << val << "\t";
+    out << std::left << gr[0] << " " << gr[1] << std::endl;
+  }
+}
+
 } // namespace p2
 } // namespace pnpo

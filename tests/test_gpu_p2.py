@@ -338,9 +338,84 @@ def test_errors_are_reported():
         st, res = c.newton(h, vu, c.solver(capi.SOLVER_BCGS, prec, 100), c.newton_opts(), check=False)
         assert st == 8 and b"quadratic" in capi.lib().pnp_last_error(c._h)
     with pytest.raises(capi.PnpError):
-        c.write_vtk("/tmp/should_not_exist_p2", [vu], ["u"])
+        c.carry_set([vu])                           # refinement carry-over is built for linear elements
     with pytest.raises(capi.PnpError):
         c.residual(h, c.vec(3), vu)                 # field count mismatch
     c2 = capi.Context(0)
     with pytest.raises(capi.PnpError):
         c2.space_set_degree(3)
+
+
+# ---- the time loop's diagnostics with quadratic functions ----
+def test_outputs_match_oracle(tmp_path):
+    """calcIonFlux, DataWriter::writeData and the VTK vertex data for quadratic functions: fields and gradients are basis sums
+    over the element's 6 dofs at the face / element centre; VTK vertex data are the vertex dofs."""
+    c, m, p, P = make_ctx("pore", 0)
+    phi = np.cos(0.3 * P.x) * np.sin(0.2 * P.y); cp = 0.06 * np.exp(-phi); cm = 0.06 * np.exp(phi)
+    vphi, vcp, vcm = c.vec(1, phi), c.vec(1, cp), c.vec(1, cm)
+    ip, im = c.ion_flux(vphi, vcp, vcm)
+    ip_o, im_o = P.ion_flux(phi, cp, cm)
+    ip_a, im_a = P.ion_flux(np.abs(phi), np.abs(cp), np.abs(cm))
+    scale = np.abs(ip_o).max() + np.abs(im_o).max() + np.abs(ip_a).max() + np.abs(im_a).max()
+    assert np.all(np.abs(ip - ip_o) <= 1e-11 * scale) and np.all(np.abs(im - im_o) <= 1e-11 * scale) and np.any(ip_o != 0)
+    # a quadratic field differs from its vertex interpolant at the face centres: the P1 formula would not pass
+    ip1, _ = ora.ion_flux(m, p, phi[P.nE:], cp[P.nE:], cm[P.nE:])
+    assert np.max(np.abs(ip1 - ip_o)) > 1e-6 * scale
+    c.write_cell_data(vphi, str(tmp_path / "gpu.dat"))
+    P.write_cell_data(phi, str(tmp_path / "ora.dat"))
+    a = open(tmp_path / "gpu.dat").read().splitlines(); b = open(tmp_path / "ora.dat").read().splitlines()
+    assert len(a) == len(b) == m.nT
+    A = np.array([[float(t) for t in l.split()] for l in a]); B = np.array([[float(t) for t in l.split()] for l in b])
+    assert np.allclose(A, B, rtol=2e-5, atol=1e-12)
+    assert sum(la == lb for la, lb in zip(a, b)) >= 0.99 * len(a)
+    for ascii_ in (True, False):
+        g, o = str(tmp_path / ("gpu%d" % ascii_)), str(tmp_path / ("ora%d" % ascii_))
+        c.write_vtk(g, [vphi, vcp], ["phi", "cp"], ascii=ascii_)
+        ora.write_vtk(m, o, [phi[P.nE:], cp[P.nE:]], ["phi", "cp"], ascii=ascii_)
+        assert open(g + ".vtu", "rb").read() == open(o + ".vtu", "rb").read()
+
+
+def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path):
+    """The reference binary built with -DPDEGREE=2 (src/Makefile.am:57-60: dune_pnp_BCGS_SSORk_2): PnpSolverMain::run on
+    one_wall, three time steps with file output; the printed norms equal the same loop driven through the C ABI, the files
+    are what the oracle's writers make of the fields."""
+    import subprocess
+    from test_gpu_parity import _build_example
+    capi = _capi()
+    a = util.load_mesh_arrays("one_wall")
+    util.write_gmsh(str(tmp_path / "one_wall.msh"), a)
+    (tmp_path / "one_wall.cfg").write_text(open(util.cfg_path("one_wall")).read())
+    exe = _build_example("instationary_pnp_md", tmp_path, ("-DPDEGREE=2",))
+    out = subprocess.run([exe, "one_wall.cfg", "1", "3", "files"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l.split() for l in out.stdout.splitlines() if l.startswith("step")]
+    assert len(lines) == 3
+    c, m, p, P = make_ctx("one_wall", 1)
+    ls = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, int(p.sys[5]), 1)
+    vpb = c.vec(1)
+    c.newton(c.operator(capi.OP_PB, 0), vpb, ls, c.newton_opts(jac_mode=0))
+    uphi, ucp, ucm, cpB, cmB, new = (c.vec(1) for _ in range(6))
+    c.interpolate_bcext(0, vpb, uphi)
+    c.interpolate_bcext(1, vpb, ucp); c.interpolate_bcext(1, vpb, cpB)
+    c.interpolate_bcext(2, vpb, ucm); c.interpolate_bcext(2, vpb, cmB)
+    hphi = c.operator(capi.OP_POISSON, 0)
+    c.operator_set_coefficient(hphi, 0, ucp); c.operator_set_coefficient(hphi, 1, ucm)
+    h0p, h0m = c.operator(capi.OP_DIFFUSION, 1), c.operator(capi.OP_DIFFUSION, 1)
+    c.operator_set_coefficient(h0p, 0, uphi); c.operator_set_valency(h0p, 1.0)
+    c.operator_set_coefficient(h0m, 0, uphi); c.operator_set_valency(h0m, -1.0)
+    h1 = c.operator(capi.OP_MASS, 1)
+    for i in range(3):
+        c.onestep(h0p, h1, ls, p.sys[11], ucp, cpB, new, 1e-5); c.vec_copy(ucp, new)
+        c.onestep(h0m, h1, ls, p.sys[11], ucm, cmB, new, 1e-5); c.vec_copy(ucm, new)
+        c.slp(hphi, uphi, ls, 1e-10)
+        got = [float(lines[i][k]) for k in (6, 8, 10)]
+        want = [c.norm(uphi), c.norm(ucp), c.norm(ucm)]
+        assert np.allclose(got, want, rtol=1e-9), (i, got, want)
+    assert c.space_sizes()["ndof"] == P.nd and len(c.download(uphi, 1)) == P.nd
+    P.write_cell_data(c.download(ucp, 1), str(tmp_path / "ora_cp.dat"))
+    a_, b_ = (tmp_path / "cp003.dat").read_text().splitlines(), (tmp_path / "ora_cp.dat").read_text().splitlines()
+    assert len(a_) == len(b_) == m.nT and sum(x == y for x, y in zip(a_, b_)) >= 0.99 * len(a_)
+    cur = (tmp_path / "current.dat").read_text().splitlines()
+    ip_o, im_o = P.ion_flux(c.download(uphi, 1), c.download(ucp, 1), c.download(ucm, 1))
+    last = [float(t) for t in cur[-1].split()]
+    assert np.allclose(last[1::4], ip_o, rtol=1e-5, atol=1e-12) and np.allclose(last[3::4], im_o, rtol=1e-5, atol=1e-12)

@@ -136,3 +136,24 @@ def test_interpolate_bcext_p2():
         bv = np.zeros(m.nv, bool); bv[m.ba] = True; bv[m.bb] = True
         inner = free.copy(); inner[P.nE:][bv] = False; inner[:P.nE][bv[P.eva] | bv[P.evb]] = False
         assert np.allclose(u[inner], want[inner], rtol=1e-15)
+
+
+def test_outputs_reduce_to_the_linear_ones_for_linear_functions(tmp_path):
+    """A P1 function lifted into the quadratic space (edge dof = mean of the end vertices) has the same face-centre values
+    and gradients: calcIonFlux and DataWriter::writeData must agree with the linear-element restatement."""
+    m, p, P = case("pore")
+    lift = lambda v: np.concatenate([0.5 * (v[P.eva] + v[P.evb]), v])  # noqa: E731
+    phi = 0.3 * np.cos(0.2 * m.x) + 0.1 * m.y; cp = 0.06 * np.exp(-phi); cm = 0.06 * np.exp(phi)
+    ip1, im1 = ora.ion_flux(m, p, phi, cp, cm)
+    ip2, im2 = P.ion_flux(lift(phi), lift(cp), lift(cm))
+    scale = np.abs(ip1).max() + np.abs(im1).max()
+    assert np.any(ip1 != 0) and np.allclose(ip1, ip2, rtol=0, atol=1e-12 * scale) and np.allclose(im1, im2, rtol=0, atol=1e-12 * scale)
+    ora.write_cell_data(m, phi, str(tmp_path / "p1.dat")); P.write_cell_data(lift(phi), str(tmp_path / "p2.dat"))
+    A = np.loadtxt(tmp_path / "p1.dat"); B = np.loadtxt(tmp_path / "p2.dat")
+    assert A.shape == (m.nT, 5) and np.allclose(A, B, rtol=2e-5, atol=1e-9)
+    # and a genuinely quadratic field: the centre value is the basis sum (vertex weights -1/9, edge weights 4/9)
+    u = P.x ** 2 - 0.5 * P.x * P.y
+    P.write_cell_data(u, str(tmp_path / "q.dat"))
+    Q = np.loadtxt(tmp_path / "q.dat")
+    assert np.allclose(Q[:, 2], Q[:, 0] ** 2 - 0.5 * Q[:, 0] * Q[:, 1], rtol=1e-4, atol=1e-4 * np.abs(u).max())
+    assert np.allclose(Q[:, 3], 2 * Q[:, 0] - 0.5 * Q[:, 1], rtol=1e-4, atol=1e-4 * np.abs(P.x).max())
