@@ -432,8 +432,16 @@ class Context:
         self._ck(lib().pnp_space_sizes(self._h, C.byref(deg), C.byref(nE), C.byref(nd)))
         return dict(degree=deg.value, n_edges=nE.value, ndof=nd.value)
 
+    def space_offsets(self):
+        eo = C.c_long(); vo = C.c_long()
+        self._ck(lib().pnp_space_offsets(self._h, C.byref(eo), C.byref(vo)))
+        return eo.value, vo.value
+
+    def operator_set_intorder(self, op, intorder):
+        self._ck(lib().pnp_operator_set_intorder(self._h, op, int(intorder)))
+
     def ndof(self):
-        """Scalar dofs per field: vertices (degree 1) or edges + vertices (degree 2)."""
+        """Scalar dofs per field: vertices (degree 1), edges + vertices (2), elements + 2 per edge + vertices (3)."""
         return self.space_sizes()["ndof"]
 
     def space_edges(self):

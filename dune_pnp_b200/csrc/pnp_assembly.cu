@@ -310,7 +310,7 @@ static void coefficient_ptrs(Ctx& c, const Operator& op, const double** a0, cons
 
 void assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built (mesh finalized + parameters set?)");
-  if (c.degree == 2) { p2_assemble_residual(c, op, u, r); return; }
+  if (c.degree >= 2) { p2_assemble_residual(c, op, u, r); return; }
   const int F = op_fields(op.op);
   PNP_REQUIRE(u.fields == F && r.fields == F, PNP_E_ARG, "vector field count does not match the operator");
   const double *a0, *a1;
@@ -340,7 +340,7 @@ void assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
 
 void assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, double eps) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built (mesh finalized + parameters set?)");
-  if (c.degree == 2) { p2_assemble_jacobian(c, op, u, A, mode, eps); return; }
+  if (c.degree >= 2) { p2_assemble_jacobian(c, op, u, A, mode, eps); return; }
   PNP_REQUIRE(u.fields == op_fields(op.op), PNP_E_ARG, "vector field count does not match the operator");
   PNP_REQUIRE(A.op == op.op, PNP_E_ARG, "matrix belongs to another operator type");
   PNP_REQUIRE(mode == JAC_FD_FAITHFUL || mode == JAC_ANALYTIC, PNP_E_ARG, "unknown jacobian mode");

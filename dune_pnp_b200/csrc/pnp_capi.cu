@@ -105,7 +105,7 @@ void pnp_ctx_destroy(pnp_ctx* ctx) {
 }
 pnp_status pnp_mg_push_level(pnp_ctx* ctx, pnp_ctx* child, const int* par0, const int* par1) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements");
+  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "built for linear elements only");
   PNP_REQUIRE(child && par0 && par1, PNP_E_ARG, "null arguments");
   Ctx& f = c.mg.empty() ? c : *c.mg.back().lc;   // the next finer level
   Ctx& k = child->c;
@@ -255,7 +255,7 @@ pnp_status pnp_halo_set(pnp_ctx* ctx, int n_nbr, const int* nbr, const int* send
 }
 pnp_status pnp_halo_exchange(pnp_ctx* ctx, int vec_handle) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements");
+  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "built for linear elements only");
   halo_exchange(c, c.vec(vec_handle).d.p, c.vec(vec_handle).fields);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   API_END
@@ -269,11 +269,11 @@ pnp_status pnp_mesh_read_gmsh(pnp_ctx* ctx, const char* path) {
   API_END
 }
 pnp_status pnp_mesh_refine(pnp_ctx* ctx, int levels) { API_BEGIN(ctx) mesh_refine(c, levels); API_END }
-pnp_status pnp_carry_set(pnp_ctx* ctx, const int* vec_handles, int n) { API_BEGIN(ctx) PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements"); carry_set(c, vec_handles, n); API_END }
-pnp_status pnp_carry_get(pnp_ctx* ctx, int index, int vec_handle) { API_BEGIN(ctx) PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements"); carry_get(c, index, c.vec(vec_handle)); API_END }
+pnp_status pnp_carry_set(pnp_ctx* ctx, const int* vec_handles, int n) { API_BEGIN(ctx) PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "built for linear elements only"); carry_set(c, vec_handles, n); API_END }
+pnp_status pnp_carry_get(pnp_ctx* ctx, int index, int vec_handle) { API_BEGIN(ctx) PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "built for linear elements only"); carry_get(c, index, c.vec(vec_handle)); API_END }
 pnp_status pnp_carry_set_host(pnp_ctx* ctx, int fields, const double* host) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements");
+  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "built for linear elements only");
   PNP_REQUIRE(c.nv > 0 && fields >= 1 && host, PNP_E_ARG, "no mesh / bad field count");
   Vec cf; cf.fields = fields; cf.d.alloc((size_t)fields * c.nv);
   cf.d.upload(host, (size_t)fields * c.nv, c.stream);
@@ -284,7 +284,7 @@ pnp_status pnp_carry_set_host(pnp_ctx* ctx, int fields, const double* host) {
 }
 pnp_status pnp_carry_get_host(pnp_ctx* ctx, int index, double* host) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "not built for quadratic elements");
+  PNP_REQUIRE(c.degree == 1, PNP_E_ARG, "built for linear elements only");
   PNP_REQUIRE(index >= 0 && index < (int)c.carry.size() && host, PNP_E_ARG, "no such carried field");
   c.carry[index].d.download(host, c.carry[index].d.n, c.stream);
   API_END
@@ -379,7 +379,7 @@ pnp_status pnp_constraints_get(pnp_ctx* ctx, int h, char* out) {
   API_BEGIN(ctx)
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built");
   const Operator& op = c.oper(h);
-  if (c.degree == 2) { p2_constraints_get(c, op, out); return PNP_OK; }
+  if (c.degree >= 2) { p2_constraints_get(c, op, out); return PNP_OK; }
   const int F = op_fields(op.op);
   std::vector<unsigned char> m = c.dmask.to_host(c.stream);
   std::vector<int> i2e = c.int2ext.to_host(c.stream);
@@ -445,7 +445,7 @@ pnp_status pnp_vec_pack3(pnp_ctx* ctx, int dst3, int phi, int cp, int cm) {
   API_BEGIN(ctx)
   PNP_REQUIRE(c.vec(dst3).fields == 3 && c.vec(phi).fields == 1 && c.vec(cp).fields == 1 && c.vec(cm).fields == 1,
               PNP_E_ARG, "pack3 needs one 3-field and three 1-field vectors");
-  if (c.degree == 2) { // field-lexicographic layout: three block copies
+  if (c.degree >= 2) { // field-lexicographic layout: three block copies
     const int src[3] = {phi, cp, cm};
     for (int k = 0; k < 3; k++) vec_copy(c, c.vec(src[k]).d.p, c.vec(dst3).d.p + k * c.p2_nd, c.p2_nd);
     return PNP_OK;
@@ -457,7 +457,7 @@ pnp_status pnp_vec_pack3(pnp_ctx* ctx, int dst3, int phi, int cp, int cm) {
 pnp_status pnp_vec_extract(pnp_ctx* ctx, int src3, int field, int dst1) {
   API_BEGIN(ctx)
   PNP_REQUIRE(c.vec(src3).fields == 3 && c.vec(dst1).fields == 1 && field >= 0 && field < 3, PNP_E_ARG, "bad extract arguments");
-  if (c.degree == 2) { vec_copy(c, c.vec(src3).d.p + field * c.p2_nd, c.vec(dst1).d.p, c.p2_nd); return PNP_OK; }
+  if (c.degree >= 2) { vec_copy(c, c.vec(src3).d.p + field * c.p2_nd, c.vec(dst1).d.p, c.p2_nd); return PNP_OK; }
   k_extract<<<grid_for(c.nv, 256), 256, 0, c.stream>>>(c.vec(src3).d.p, c.nv, field, c.vec(dst1).d.p);
   PNP_CHECK_LAUNCH(); c.launches++;
   API_END
@@ -468,7 +468,7 @@ pnp_status pnp_matrix_create(pnp_ctx* ctx, int op_handle, int* handle) {
   PNP_REQUIRE(c.finalized && handle, PNP_E_ARG, "mesh not finalized");
   auto m = std::make_unique<Matrix>();
   m->op = c.oper(op_handle).op; m->nplanes = op_planes(m->op);
-  if (c.degree == 2) { PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built"); p2_matrix_init(c, *m, c.oper(op_handle)); }
+  if (c.degree >= 2) { PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built"); p2_matrix_init(c, *m, c.oper(op_handle)); }
   else { m->vals.alloc((size_t)m->nplanes * c.nslots); m->vals.zero(c.stream); }
   c.mats.push_back(std::move(m));
   *handle = (int)c.mats.size() - 1;
@@ -525,7 +525,7 @@ pnp_status pnp_solver_get(pnp_ctx* ctx, int s, const char* name, double* value) 
   API_BEGIN(ctx)
   PNP_REQUIRE(name && value, PNP_E_ARG, "null argument");
   const std::string n(name);
-  if (c.degree == 2 && (n == "ssor_levels" || n == "ilu0_levels")) *value = c.solver(s).csr_levels;
+  if (c.degree >= 2 && (n == "ssor_levels" || n == "ilu0_levels")) *value = c.solver(s).csr_levels;
   else if (n == "ssor_levels") *value = sweep_levels(c.solver(s), false);
   else if (n == "ilu0_levels") *value = sweep_levels(c.solver(s), true);
   else if (n == "amg_graph") *value = amg_graph_state(c.solver(s));
@@ -629,16 +629,16 @@ pnp_status pnp_mesh_owned(pnp_ctx* ctx, long* n_own) { API_BEGIN(ctx) if (n_own)
 pnp_status pnp_interpolate_bcext(pnp_ctx* ctx, int component, int pb_vec, int out_vec) {
   API_BEGIN(ctx)
   PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "interpolate(BCExtension) follows the global element order: run it before partitioning");
-  if (c.degree == 2) p2_interpolate_bcext(c, component, pb_vec >= 0 ? &c.vec(pb_vec) : nullptr, c.vec(out_vec));
+  if (c.degree >= 2) p2_interpolate_bcext(c, component, pb_vec >= 0 ? &c.vec(pb_vec) : nullptr, c.vec(out_vec));
   else interpolate_bcext(c, component, pb_vec >= 0 ? &c.vec(pb_vec) : nullptr, c.vec(out_vec));
   API_END
 }
 // ---- quadratic elements (-DPDEGREE=2 builds of the reference, src/Makefile.am:57-110) ----
 pnp_status pnp_space_set_degree(pnp_ctx* ctx, int degree) {
   API_BEGIN(ctx)
-  PNP_REQUIRE(degree == 1 || degree == 2, PNP_E_ARG, "polynomial degree must be 1 or 2 (P3 is not built)");
+  PNP_REQUIRE(degree >= 1 && degree <= 3, PNP_E_ARG, "polynomial degree must be 1, 2 or 3");
   PNP_REQUIRE(!c.finalized, PNP_E_ARG, "set the degree before pnp_mesh_finalize");
-  PNP_REQUIRE(degree == 1 || (c.world == 1 && !c.parent), PNP_E_ARG, "quadratic elements run on one GPU");
+  PNP_REQUIRE(degree == 1 || (c.world == 1 && !c.parent), PNP_E_ARG, "quadratic and cubic elements run on one GPU");
   c.degree = degree;
   API_END
 }
@@ -646,10 +646,24 @@ pnp_status pnp_space_sizes(pnp_ctx* ctx, int* degree, long* n_edges, long* ndof)
   API_BEGIN(ctx)
   PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
   if (degree) *degree = c.degree;
-  if (c.degree == 2) p2_sizes(c, n_edges, ndof);
+  if (c.degree >= 2) p2_sizes(c, n_edges, ndof);
   else { if (n_edges) *n_edges = 0; if (ndof) *ndof = c.nv; }
   API_END
 }
 pnp_status pnp_space_edges(pnp_ctx* ctx, int* va, int* vb) { API_BEGIN(ctx) p2_edges(c, va, vb); API_END }
+pnp_status pnp_space_offsets(pnp_ctx* ctx, long* edge_offset, long* vertex_offset) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
+  if (c.degree >= 2) p2_offsets(c, edge_offset, vertex_offset);
+  else { if (edge_offset) *edge_offset = 0; if (vertex_offset) *vertex_offset = 0; }
+  API_END
+}
+pnp_status pnp_operator_set_intorder(pnp_ctx* ctx, int h, int intorder) {
+  API_BEGIN(ctx)
+  PNP_REQUIRE(intorder == 0 || (intorder == 5 && c.degree >= 2), PNP_E_ARG,
+              "quadrature order: 0 (the order the reference's drivers end up with) or, for degree 2 and 3, 5");
+  c.oper(h).intorder = intorder;
+  API_END
+}
 
 } // extern "C"

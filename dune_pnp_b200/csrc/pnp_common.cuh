@@ -112,6 +112,7 @@ struct Operator {
   int comp0 = 0;          // BC component of a scalar operator's BCType
   double valency = 1.0;
   int aux0 = -1, aux1 = -1; // vector handles of coefficient fields
+  int intorder = 0;         // quadrature order (degree 2 / 3 only): 0 = the reference drivers' (3; diffusion 2, mass 5), 5 = 7-point rule
 };
 
 // One coarser level of the refinement hierarchy, captured by mesh_refine(): that level's vertex star (own locality
@@ -164,8 +165,8 @@ struct Ctx {
   // edge + vertex dofs of pnp_p2.cu (p2_nd of them per field; vectors field-lexicographic, matrices CSR)
   int degree = 1; long p2_nd = 0;
   std::shared_ptr<P2Space> p2;
-  long rows() const { return degree == 2 ? p2_nd : n_own; } // dofs per field this rank owns
-  long cols() const { return degree == 2 ? p2_nd : nv; }    // ... and holds (owned + ghosts)
+  long rows() const { return degree >= 2 ? p2_nd : n_own; } // dofs per field this rank owns
+  long cols() const { return degree >= 2 ? p2_nd : nv; }    // ... and holds (owned + ghosts)
   int rank = 0, world = 1;
   void* nccl = nullptr;                 // ncclComm_t
   std::vector<int> halo_nbr, halo_send_ptr, halo_recv_ptr; // per neighbour rank: ranges into send list / ghost block
@@ -330,6 +331,7 @@ void csr_ssor_apply(Ctx&, Solver&, const Matrix& A, const double* d, double* y);
 void csr_ilu0_apply(Ctx&, Solver&, const Matrix& A, const double* d, double* y);
 const unsigned char* p2_dirichlet_flags(Ctx&); // per scalar dof: bit c = Dirichlet for BC component c (device)
 void p2_sizes(Ctx&, long* nE, long* nd);
+void p2_offsets(Ctx&, long* eoff, long* voff);
 void p2_edges(Ctx&, int* eva, int* evb);
 void p2_constraints_get(Ctx&, const Operator&, char* out);
 long p2_pattern_export(Ctx&, const Operator&, int* rowptr, int* col);

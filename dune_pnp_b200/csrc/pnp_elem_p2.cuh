@@ -1,27 +1,94 @@
-// pnp_elem_p2.cuh -- element-level fp64 math of the five local operators with QUADRATIC elements (the reference's
-// -DPDEGREE=2 build: /root/reference/src/Makefile.am:57-110; Pk2DLocalFiniteElementMap<GV,D,R,2>,
+// pnp_elem_p2.cuh -- element-level fp64 math of the five local operators with QUADRATIC and CUBIC elements (the reference's
+// -DPDEGREE=2 / -DPDEGREE=3 builds: /root/reference/src/Makefile.am:54-110; Pk2DLocalFiniteElementMap<GV,D,R,PDEGREE>,
 // instationary_pnp_from_pb_md.hh:26-28,125).  The operator bodies are the reference's alpha_volume / alpha_boundary
 // (pnp_operator.hh:98-194, pb_operator.hh:74-120, poisson_operator.hh:74-126, diffusion_operator.hh:64-111,
-// diffusion_toperator.hh:58-72) evaluated for lfsu.size() = 6; __host__ __device__ like pnp_elem.cuh, compiled without FMA
-// contraction so that the FD Jacobian rounds like the CPU restatement.
+// diffusion_toperator.hh:58-72) evaluated for lfsu.size() = 6 or 10; __host__ __device__ like pnp_elem.cuh, compiled without
+// FMA contraction so that the FD Jacobian rounds like the CPU restatement.
 //
-// Local dof order (Pk2DLocalBasis<D,R,2>): Lagrange nodes (0,0),(1/2,0),(1,0),(0,1/2),(1/2,1/2),(0,1) =
-// vertex0, edge0=(v0,v1), vertex1, edge1=(v0,v2), edge2=(v1,v2), vertex2.
+// Local dof order (Pk2DLocalBasis<D,R,k>): Lagrange nodes (i, j)/k, i + j <= k, lexicographic with j outer.
+// k = 2: (0,0),(1/2,0),(1,0),(0,1/2),(1/2,1/2),(0,1) = vertex0, edge0=(v0,v1), vertex1, edge1=(v0,v2), edge2=(v1,v2), vertex2.
+// k = 3: v0, e0, e0, v1, e1, bubble, e2, e1, e2, v2.
+// NQ is the triangle rule (3, 4 or 7 points: orders 2, 3, 5): the reference's constructors default to order 3 whatever PDEGREE is,
+// which under-integrates the cubic stiffness and mass terms (and makes the matrices indefinite: the order-3 rule has a negative
+// weight); pnp_operator_set_intorder(.., 5) selects the 7-point rule.
 #pragma once
 #include "pnp_elem.cuh"
 
 namespace pnp {
-namespace p2 {
+template <int DEG> struct PkElem {
+  static_assert(DEG == 2 || DEG == 3, "degrees 2 and 3");
 
-constexpr int NL = 6;
+static constexpr int NL = (DEG + 1) * (DEG + 2) / 2;
 
-PNP_HD bool node_is_edge(int i) { return i == 1 || i == 3 || i == 4; }
-PNP_HD int node_sub(int i) { return i == 0 ? 0 : (i == 1 ? 0 : (i == 2 ? 1 : (i == 3 ? 1 : 2))); } // local vertex / local edge
-PNP_HD double node_x(int i) { return i == 2 ? 1.0 : ((i == 1 || i == 4) ? 0.5 : 0.0); }
-PNP_HD double node_y(int i) { return i == 5 ? 1.0 : ((i == 3 || i == 4) ? 0.5 : 0.0); }
+// node n <-> lattice point (i, j); what it sits on: kind 0 vertex (sub = local vertex), 1 edge (sub = local edge, idx = position
+// counted from the edge's first local vertex), 2 element interior
+PNP_HD static void node_ij(int n, int& i, int& j) {
+  int c = 0;
+  for (j = 0; j <= DEG; j++) for (i = 0; i <= DEG - j; i++) if (c++ == n) return;
+}
+PNP_HD static double node_x(int n) { int i, j; node_ij(n, i, j); return (1.0 * i) / DEG; }
+PNP_HD static double node_y(int n) { int i, j; node_ij(n, i, j); return (1.0 * j) / DEG; }
+PNP_HD static void node_key(int n, int& kind, int& sub, int& idx) {
+  int i, j; node_ij(n, i, j);
+  idx = 0;
+  if (i == 0 && j == 0) { kind = 0; sub = 0; }
+  else if (i == DEG) { kind = 0; sub = 1; }
+  else if (j == DEG) { kind = 0; sub = 2; }
+  else if (j == 0) { kind = 1; sub = 0; idx = i - 1; }
+  else if (i == 0) { kind = 1; sub = 1; idx = j - 1; }
+  else if (i + j == DEG) { kind = 1; sub = 2; idx = j - 1; }
+  else { kind = 2; sub = 0; }
+}
+
+// Pk2DLocalBasis<D,R,k>::evaluateFunction / evaluateJacobian for any k: pos[i] = i/k; node (i,j):
+// prod_{a<i} (x-pos[a])/(pos[i]-pos[a]) prod_{b<j} (y-pos[b])/(pos[j]-pos[b]) prod_{g=i+j+1..k} (pos[g]-x-y)/(pos[g]-pos[i]-pos[j]);
+// derivatives by the product rule, factor by factor (the operation sequence of the CPU restatement)
+PNP_HD static void basis_generic(double x, double y, double* phi) {
+  double pos[DEG + 1];
+  for (int i = 0; i <= DEG; i++) pos[i] = (1.0 * i) / DEG;
+  int n = 0;
+  for (int j = 0; j <= DEG; j++) for (int i = 0; i <= DEG - j; i++) {
+    double out = 1.0;
+    for (int a = 0; a < i; a++) out *= (x - pos[a]) / (pos[i] - pos[a]);
+    for (int b = 0; b < j; b++) out *= (y - pos[b]) / (pos[j] - pos[b]);
+    for (int g = i + j + 1; g <= DEG; g++) out *= (pos[g] - x - y) / (pos[g] - pos[i] - pos[j]);
+    phi[n++] = out;
+  }
+}
+PNP_HD static void basis_grad_generic(double x, double y, double (*gr)[2]) {
+  double pos[DEG + 1];
+  for (int i = 0; i <= DEG; i++) pos[i] = (1.0 * i) / DEG;
+  int n = 0;
+  for (int j = 0; j <= DEG; j++) for (int i = 0; i <= DEG - j; i++, n++) {
+    for (int dir = 0; dir < 2; dir++) {
+      const int own = dir == 0 ? i : j, oth = dir == 0 ? j : i;
+      const double z = dir == 0 ? x : y, w = dir == 0 ? y : x;
+      double factor = 1.0, sum = 0.0;
+      for (int b = 0; b < oth; b++) factor *= (w - pos[b]) / (pos[oth] - pos[b]);
+      for (int a = 0; a < own; a++) {
+        double product = factor;
+        for (int al = 0; al < own; al++)
+          if (al == a) product *= 1.0 / (pos[own] - pos[al]);
+          else product *= (z - pos[al]) / (pos[own] - pos[al]);
+        for (int g = i + j + 1; g <= DEG; g++) product *= (pos[g] - x - y) / (pos[g] - pos[i] - pos[j]);
+        sum += product;
+      }
+      for (int c = i + j + 1; c <= DEG; c++) {
+        double product = factor;
+        for (int al = 0; al < own; al++) product *= (z - pos[al]) / (pos[own] - pos[al]);
+        for (int g = i + j + 1; g <= DEG; g++)
+          if (g == c) product *= -1.0 / (pos[g] - pos[i] - pos[j]);
+          else product *= (pos[g] - x - y) / (pos[g] - pos[i] - pos[j]);
+        sum += product;
+      }
+      gr[n][dir] = sum;
+    }
+  }
+}
 
 // Pk2DLocalBasis<D,R,2>::evaluateFunction: node (i,j) -> prod_{a<i}(2x-a)/(i-a) prod_{b<j}(2y-b)/(j-b) prod_{g>i+j}(g-2x-2y)/(g-i-j)
-PNP_HD void basis(double x, double y, double* phi) {
+PNP_HD static void basis(double x, double y, double* phi) {
+  if (DEG != 2) { basis_generic(x, y, phi); return; }
   const double s = 2 * x + 2 * y;
   phi[0] = ((1 - s) / 1) * ((2 - s) / 2);
   phi[1] = (2 * x) * ((2 - s) / 1);
@@ -30,7 +97,8 @@ PNP_HD void basis(double x, double y, double* phi) {
   phi[4] = (2 * x) * (2 * y);
   phi[5] = (2 * y) * ((2 * y - 1) / 2);
 }
-PNP_HD void basis_grad(double x, double y, double (*g)[2]) {
+PNP_HD static void basis_grad(double x, double y, double (*g)[2]) {
+  if (DEG != 2) { basis_grad_generic(x, y, g); return; }
   const double s = 2 * x + 2 * y;
   g[0][0] = (2 * s - 3); g[0][1] = (2 * s - 3);
   g[1][0] = 2 * (2 - s) - 4 * x; g[1][1] = -4 * x;
@@ -42,7 +110,7 @@ PNP_HD void basis_grad(double x, double y, double (*g)[2]) {
 
 // affine geometry: J^{-T}, |det J|, the vertices' y for the cylindrical factor
 struct Geo2 { double jit[2][2], detabs, y0, y1, y2; };
-PNP_HD Geo2 make_geo2(double x0, double y0, double x1, double y1, double x2, double y2) {
+PNP_HD static Geo2 make_geo2(double x0, double y0, double x1, double y1, double x2, double y2) {
   Geo2 G;
   const double j00 = x1 - x0, j01 = x2 - x0, j10 = y1 - y0, j11 = y2 - y0;
   const double det = j00 * j11 - j01 * j10;
@@ -54,7 +122,7 @@ PNP_HD Geo2 make_geo2(double x0, double y0, double x1, double y1, double x2, dou
   return G;
 }
 struct BasisAt { double phi[NL], g[NL][2]; };
-PNP_HD BasisAt basis_at(const Geo2& G, double x, double y) {
+PNP_HD static BasisAt basis_at(const Geo2& G, double x, double y) {
   BasisAt B;
   basis(x, y, B.phi);
   double gh[NL][2];
@@ -73,9 +141,8 @@ PNP_HD BasisAt basis_at(const Geo2& G, double x, double y) {
 
 // alpha_volume: xl[NL*k + i] = local coefficient of field k at node i; caux[a][i] = local coefficients of the operator's
 // coefficient fields (Poisson: c+, c-; diffusion: Phi), P2 functions as well.  ACCUMULATES into rl[NL*k + i].
-template <int OP>
-PNP_HD void alpha_volume(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* rl) {
-  constexpr int NQ = OpTraits<OP>::NQ;
+template <int OP, int NQ>
+PNP_HD static void alpha_volume(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* rl) {
   const double PI = P.PI;
   for (int q = 0; q < NQ; q++) {
     double xi0, xi1, w;
@@ -124,19 +191,22 @@ PNP_HD void alpha_volume(const Geo2& G, const PhysParams& P, const double* xl, c
 }
 
 // alpha_boundary of DUNE face f with end points (ax,ay)->(bx,by) in element order; j[k] = flux of field k, skip[k]: the face
-// is Dirichlet for field k's component.  ACCUMULATES into rl.
-PNP_HD void alpha_boundary(int f, double ax, double ay, double bx, double by, int nfields, const double* j, const bool* skip,
-                           const PhysParams& P, double* rl) {
+// is Dirichlet for field k's component; npts = points of the Gauss-Legendre rule the operator's intorder asks for (2: order 3,
+// 3: order 5).  ACCUMULATES into rl.
+PNP_HD static void alpha_boundary(int f, double ax, double ay, double bx, double by, int nfields, const double* j, const bool* skip,
+                                  const PhysParams& P, int npts, double* rl) {
   const double len = sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
-  const double tq[2] = {0.21132486540518711775, 0.78867513459481288225};
-  for (int q = 0; q < 2; q++) {
-    const double t = tq[q];
+  const double t2[2] = {0.21132486540518711775, 0.78867513459481288225};
+  const double t3[3] = {0.11270166537925831148, 0.5, 0.88729833462074168852};
+  const double w3[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+  for (int q = 0; q < npts; q++) {
+    const double t = npts == 2 ? t2[q] : t3[q];
     double l0, l1;
     if (f == 0) { l0 = t; l1 = 0.0; } else if (f == 1) { l0 = 0.0; l1 = t; } else { l0 = 1.0 - t; l1 = t; }
     double phi[NL];
     basis(l0, l1, phi);
     const double gy = ay + t * (by - ay);
-    double factor = 0.5 * len;
+    double factor = (npts == 2 ? 0.5 : w3[q]) * len;
     if (P.cylindrical) factor *= gy * 2 * P.PI;
     for (int k = 0; k < nfields; k++) {
       if (skip[k]) continue;
@@ -146,27 +216,26 @@ PNP_HD void alpha_boundary(int f, double ax, double ay, double bx, double by, in
 }
 
 // NumericalJacobianVolume: Ae[i*n + j], n = NL * F, ACCUMULATED
-template <int OP>
-PNP_HD void jacobian_fd(const Geo2& G, const PhysParams& P, double* xl, const double (*caux)[NL], double eps, double* Ae) {
+template <int OP, int NQ>
+PNP_HD static void jacobian_fd(const Geo2& G, const PhysParams& P, double* xl, const double (*caux)[NL], double eps, double* Ae) {
   constexpr int n = NL * OpTraits<OP>::F;
   double down[n], up[n];
   for (int i = 0; i < n; i++) down[i] = 0.0;
-  alpha_volume<OP>(G, P, xl, caux, down);
+  alpha_volume<OP, NQ>(G, P, xl, caux, down);
   for (int j = 0; j < n; j++) {
     for (int i = 0; i < n; i++) up[i] = 0.0;
     const double keep = xl[j];
     const double delta = eps * (1.0 + fabs(keep));
     xl[j] = keep + delta;
-    alpha_volume<OP>(G, P, xl, caux, up);
+    alpha_volume<OP, NQ>(G, P, xl, caux, up);
     for (int i = 0; i < n; i++) Ae[i * n + j] += (up[i] - down[i]) / delta;
     xl[j] = keep;
   }
 }
 
 // exact derivative (not in the reference)
-template <int OP>
-PNP_HD void jacobian_exact(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* Ae) {
-  constexpr int NQ = OpTraits<OP>::NQ;
+template <int OP, int NQ>
+PNP_HD static void jacobian_exact(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* Ae) {
   constexpr int n = NL * OpTraits<OP>::F;
   for (int q = 0; q < NQ; q++) {
     double xi0, xi1, w;
@@ -211,5 +280,5 @@ PNP_HD void jacobian_exact(const Geo2& G, const PhysParams& P, const double* xl,
   }
 }
 
-} // namespace p2
+}; // struct PkElem
 } // namespace pnp

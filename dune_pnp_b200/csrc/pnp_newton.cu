@@ -27,7 +27,7 @@ int newton_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, const pnp_newton
   if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); prev_u.d.alloc(nall); }
   r.d.zero(c.stream); z.d.zero(c.stream);
   A.op = op.op; A.nplanes = op_planes(op.op);
-  if (c.degree == 2) p2_matrix_init(c, A, op);
+  if (c.degree >= 2) p2_matrix_init(c, A, op);
   else if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
   const double t_start = now();
   auto sync = [&] { PNP_CUDA(cudaStreamSynchronize(c.stream)); };
@@ -145,7 +145,7 @@ LinResult slp_apply(Ctx& c, const Operator& op, Vec& u, Solver& S, double reduct
   if (r.d.n != (size_t)nall) { r.d.alloc(nall); z.d.alloc(nall); c.ws_prev.d.alloc(nall); }
   r.d.zero(c.stream); z.d.zero(c.stream);
   A.op = op.op; A.nplanes = op_planes(op.op);
-  if (c.degree == 2) p2_matrix_init(c, A, op);
+  if (c.degree >= 2) p2_matrix_init(c, A, op);
   else if (A.vals.n != (size_t)A.nplanes * c.nslots) A.vals.alloc((size_t)A.nplanes * c.nslots);
   assemble_jacobian(c, op, u, A, jac_mode, eps);
   assemble_residual(c, op, u, r);
@@ -205,7 +205,7 @@ int onestep_apply(Ctx& c, int method, const Operator& op0, const Operator& op1, 
   const TimeMethod tm = time_method(method);
   const long n = c.rows(), nall = c.cols();
   const int comp = op0.comp0;
-  const bool p2 = c.degree == 2;
+  const bool p2 = c.degree >= 2;
   for (auto& v : c.ws_stage) { v.fields = 1; if (v.d.n != (size_t)nall) { v.d.alloc(nall); v.d.zero(c.stream); } }
   Vec &x1 = c.ws_stage[0], &x2 = c.ws_stage[1], &cst = c.ws_stage[2], &r0 = c.ws_stage[3], &r1 = c.ws_stage[4];
   Vec &r = c.ws_r, &z = c.ws_z;

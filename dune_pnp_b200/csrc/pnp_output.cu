@@ -56,7 +56,7 @@ __global__ void k_ion_flux(const BFace* __restrict__ faces, int nB, const XY* __
 // ip[s], im[s] for every surface s (ionFlux.hh accumulates into component 0 of ip[pg], im[pg])
 void ion_flux(Ctx& c, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, double* im) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "mesh not finalized / parameters not set");
-  if (c.degree == 2) { p2_ion_flux(c, phi, cp, cm, ip, im); return; }
+  if (c.degree >= 2) { p2_ion_flux(c, phi, cp, cm, ip, im); return; }
   PNP_REQUIRE(phi.fields == 1 && cp.fields == 1 && cm.fields == 1, PNP_E_ARG, "ion flux: three 1-field vectors expected");
   const int ns = c.params.n_surfaces, nB = (int)c.bfaces.size();
   for (int s = 0; s < ns; s++) ip[s] = im[s] = 0.0;
@@ -89,7 +89,7 @@ void ion_flux(Ctx& c, const Vec& phi, const Vec& cp, const Vec& cm, double* ip, 
 void write_cell_data(Ctx& c, const Vec& u, const std::string& filename) {
   PNP_REQUIRE(c.finalized && u.fields == 1, PNP_E_ARG, "writeData: finalized mesh and a 1-field vector expected");
   PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "writeData walks the global element order: one subdomain only");
-  if (c.degree == 2) { p2_write_cell_data(c, u, filename); return; }
+  if (c.degree >= 2) { p2_write_cell_data(c, u, filename); return; }
   std::vector<double> lex((size_t)c.nv);
   vec_download(c, u, lex.data());
   const std::vector<double> x = c.cx.to_host(c.stream), y = c.cy.to_host(c.stream);
@@ -121,7 +121,7 @@ void write_vtk(Ctx& c, const std::string& name, int nfields, const Vec* const* f
   std::vector<std::vector<float>> data(nfields, std::vector<float>((size_t)nv));
   std::vector<double> lex((size_t)nv);
   for (int i = 0; i < nfields; i++) {
-    if (c.degree == 2) p2_vertex_values(c, *fields[i], lex.data()); // vertex data of a quadratic function = its vertex dofs
+    if (c.degree >= 2) p2_vertex_values(c, *fields[i], lex.data()); // vertex data of a quadratic function = its vertex dofs
     else vec_download(c, *fields[i], lex.data());
     for (long v = 0; v < nv; v++) data[i][v] = (float)lex[v];
   }

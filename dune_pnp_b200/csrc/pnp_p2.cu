@@ -1,10 +1,11 @@
-// pnp_p2.cu -- quadratic elements (the reference's -DPDEGREE=2 build, /root/reference/src/Makefile.am:57-110;
-// instationary_pnp_from_pb_md.hh:26-28,125): the grid function space with edge dofs, its constraints and BCRS pattern,
-// residual and Jacobian assembly of the five local operators with 6 local dofs per field, a general CSR SpMV.
+// pnp_p2.cu -- quadratic and cubic elements (the reference's -DPDEGREE=2 / 3 builds, /root/reference/src/Makefile.am:54-110;
+// instationary_pnp_from_pb_md.hh:26-28,125): the grid function space with edge (and element) dofs, its constraints and BCRS
+// pattern, residual and Jacobian assembly of the five local operators with 6 / 10 local dofs per field, a general CSR SpMV.
 //
 // The P1 path lives on the vertex-star layout, which is both mesh and pattern for linear elements only; the P2 couplings
 // (all 6 dofs of an element with each other) do not fit it, so this path uses the reference's own container layout on the
-// device: dofs numbered edges first [0, nE), then vertices [nE, nE + nv), fields lexicographic, matrices in
+// device: dofs numbered codim by codim -- element bubbles (degree 3), then DEG-1 per edge (counted from the end vertex with
+// the smaller index), then vertices -- fields lexicographic, matrices in
 // scalar CSR with ascending columns (ISTLBCRSMatrixBackend<1,1>) -- what pnp_pattern_get returns IS the device layout.
 // Assembly in two phases, deterministic and in the reference's summation order: (1) one thread per element computes the
 // element vector / matrix (alpha_volume + alpha_boundary; NumericalJacobianVolume or the exact derivative) into a scratch
@@ -20,7 +21,6 @@
 
 namespace pnp {
 
-using p2::NL;
 
 struct P2Pattern {
   long nnz = 0;
@@ -33,11 +33,12 @@ struct P2Pattern {
 };
 
 struct P2Space {
-  long nE = 0, nd = 0, nT = 0, nv = 0;
-  std::vector<int> h_eva, h_evb, h_e2d, h_fphys, h_nbr; // edges; element -> 6 scalar dofs; element face -> surface (-1 interior); face neighbours
+  int deg = 2, NL = 6;
+  long nE = 0, nd = 0, nT = 0, nv = 0, eoff = 0, voff = 0; // first edge dof, first vertex dof
+  std::vector<int> h_eva, h_evb, h_e2d, h_fphys, h_nbr; // edges; element -> NL scalar dofs; element face -> surface (-1 interior); face neighbours
   std::vector<int> h_edge_phys;                           // per edge: surface of a boundary edge, -1 inside
   std::vector<unsigned char> h_dir;                       // per scalar dof: bit c = Dirichlet for BC component c
-  DBuf<int> e2d, fphys, inc_ptr, inc;                     // incidence: scalar dof -> (element * 8 + local node), elements ascending
+  DBuf<int> e2d, fphys, inc_ptr, inc;                     // incidence: scalar dof -> (element * 16 + local node), elements ascending
   std::vector<int> h_bfaces; DBuf<int> bfaces;            // boundary faces, element * 4 + face, in element / intersection order
   DBuf<unsigned char> dir;
   std::map<int, std::unique_ptr<P2Pattern>> patterns;     // key = 4 * F + comp0
@@ -48,13 +49,13 @@ namespace {
 
 const int FACE_V2[3][2] = {{0, 1}, {0, 2}, {1, 2}};
 
-template <int OP>
+template <int DEG, int OP>
 __device__ __forceinline__ void p2_gather_element(int e, const int* tri, const double* cx, const double* cy, const int* e2d, long nd,
-                                                  const double* u, const double* aux0, const double* aux1, p2::Geo2& G, double* xl,
-                                                  double (*caux)[NL]) {
-  constexpr int F = OpTraits<OP>::F;
+                                                  const double* u, const double* aux0, const double* aux1,
+                                                  typename PkElem<DEG>::Geo2& G, double* xl, double (*caux)[PkElem<DEG>::NL]) {
+  constexpr int F = OpTraits<OP>::F, NL = PkElem<DEG>::NL;
   const int a = tri[3 * e], b = tri[3 * e + 1], c = tri[3 * e + 2];
-  G = p2::make_geo2(cx[a], cy[a], cx[b], cy[b], cx[c], cy[c]);
+  G = PkElem<DEG>::make_geo2(cx[a], cy[a], cx[b], cy[b], cx[c], cy[c]);
   for (int i = 0; i < NL; i++) {
     const int d = e2d[NL * e + i];
     for (int k = 0; k < F; k++) xl[NL * k + i] = u[(long)k * nd + d];
@@ -64,18 +65,19 @@ __device__ __forceinline__ void p2_gather_element(int e, const int* tri, const d
 }
 
 // phase 1, residual: element vector (alpha_volume + alpha_boundary in intersection order 0, 2, 1) -> scratch[e * n ..]
-template <int OP>
+template <int DEG, int OP, int NQ>
 __global__ void k_p2_elem_residual(int nT, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
                                    const int* __restrict__ e2d, const int* __restrict__ fphys, const double* __restrict__ surf_flux,
-                                   const unsigned char* __restrict__ surf_dir, PhysParams P, long nd, int comp0,
+                                   const unsigned char* __restrict__ surf_dir, PhysParams P, long nd, int comp0, int line_pts,
                                    const double* __restrict__ u, const double* __restrict__ aux0, const double* __restrict__ aux1,
                                    double* __restrict__ out) {
-  constexpr int F = OpTraits<OP>::F, n = NL * F;
+  using E = PkElem<DEG>;
+  constexpr int F = OpTraits<OP>::F, NL = E::NL, n = NL * F;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nT; e += gridDim.x * blockDim.x) {
-    p2::Geo2 G; double xl[n], caux[2][NL], rl[n];
-    p2_gather_element<OP>(e, tri, cx, cy, e2d, nd, u, aux0, aux1, G, xl, caux);
+    typename E::Geo2 G; double xl[n], caux[2][NL], rl[n];
+    p2_gather_element<DEG, OP>(e, tri, cx, cy, e2d, nd, u, aux0, aux1, G, xl, caux);
     for (int i = 0; i < n; i++) rl[i] = 0.0;
-    p2::alpha_volume<OP>(G, P, xl, caux, rl);
+    E::template alpha_volume<OP, NQ>(G, P, xl, caux, rl);
     if (OP == OP_PB || OP == OP_POISSON || OP == OP_PNP) {
       const int order[3] = {0, 2, 1};
       for (int fi = 0; fi < 3; fi++) {
@@ -87,40 +89,41 @@ __global__ void k_p2_elem_residual(int nT, const int* __restrict__ tri, const do
           const int comp = F == 3 ? k : comp0;
           j[k] = surf_flux[3 * ph + comp]; skip[k] = (surf_dir[ph] >> comp) & 1;
         }
-        p2::alpha_boundary(f, cx[va], cy[va], cx[vb], cy[vb], F, j, skip, P, rl);
+        E::alpha_boundary(f, cx[va], cy[va], cx[vb], cy[vb], F, j, skip, P, line_pts, rl);
       }
     }
     for (int i = 0; i < n; i++) out[(long)e * n + i] = rl[i];
   }
 }
 // phase 2, residual: r[(k, d)] = sum over d's elements, ascending; constrained entries zero
-__global__ void k_p2_gather_residual(long nd, int F, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+__global__ void k_p2_gather_residual(long nd, int F, int NL, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                      const unsigned char* __restrict__ dir, const double* __restrict__ scratch, double* __restrict__ r) {
   const int n = NL * F;
   for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < (long)F * nd; g += (long)gridDim.x * blockDim.x) {
     const int k = (int)(g / nd); const long d = g - (long)k * nd;
     double sum = 0.0;
-    for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; t++) sum += scratch[(long)(inc[t] >> 3) * n + NL * k + (inc[t] & 7)];
+    for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; t++) sum += scratch[(long)(inc[t] >> 4) * n + NL * k + (inc[t] & 15)];
     r[g] = ((dir[d] >> (F == 3 ? k : comp0)) & 1u) ? 0.0 : sum;
   }
 }
 // phase 1, Jacobian: element matrix -> scratch[e * n * n ..]
-template <int OP, int MODE>
+template <int DEG, int OP, int NQ, int MODE>
 __global__ void k_p2_elem_jacobian(int nT, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
                                    const int* __restrict__ e2d, PhysParams P, long nd, double eps, const double* __restrict__ u,
                                    const double* __restrict__ aux0, const double* __restrict__ aux1, double* __restrict__ out) {
-  constexpr int F = OpTraits<OP>::F, n = NL * F;
+  using E = PkElem<DEG>;
+  constexpr int F = OpTraits<OP>::F, NL = E::NL, n = NL * F;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nT; e += gridDim.x * blockDim.x) {
-    p2::Geo2 G; double xl[n], caux[2][NL];
-    p2_gather_element<OP>(e, tri, cx, cy, e2d, nd, u, aux0, aux1, G, xl, caux);
+    typename E::Geo2 G; double xl[n], caux[2][NL];
+    p2_gather_element<DEG, OP>(e, tri, cx, cy, e2d, nd, u, aux0, aux1, G, xl, caux);
     double* Ae = out + (long)e * n * n; // accumulated in place (one writer)
     for (int i = 0; i < n * n; i++) Ae[i] = 0.0;
-    if (MODE == 0) p2::jacobian_fd<OP>(G, P, xl, caux, eps, Ae);
-    else p2::jacobian_exact<OP>(G, P, xl, caux, Ae);
+    if (MODE == 0) E::template jacobian_fd<OP, NQ>(G, P, xl, caux, eps, Ae);
+    else E::template jacobian_exact<OP, NQ>(G, P, xl, caux, Ae);
   }
 }
 // phase 2, Jacobian: row (ki, d) of the CSR matrix
-__global__ void k_p2_gather_jacobian(long nd, int F, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+__global__ void k_p2_gather_jacobian(long nd, int F, int NL, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                      const int* __restrict__ e2d, const unsigned char* __restrict__ dir, const int* __restrict__ rp,
                                      const int* __restrict__ col, const double* __restrict__ scratch, double* __restrict__ vals) {
   const int n = NL * F;
@@ -130,7 +133,7 @@ __global__ void k_p2_gather_jacobian(long nd, int F, int comp0, const int* __res
     for (int s = r0; s < r1; s++) vals[s] = 0.0;
     if ((dir[d] >> (F == 3 ? ki : comp0)) & 1u) { vals[r0] = 1.0; continue; } // trivial row (its only entry is the diagonal)
     for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; t++) {
-      const int e = inc[t] >> 3, i = inc[t] & 7;
+      const int e = inc[t] >> 4, i = inc[t] & 15;
       const double* Ae = scratch + (long)e * n * n + (long)(NL * ki + i) * n;
       for (int kj = 0; kj < F; kj++)
         for (int j = 0; j < NL; j++) {
@@ -161,19 +164,53 @@ __global__ void k_csr_diag_inverse(long N, const int* __restrict__ rp, const int
   }
 }
 
-template <int OP> void launch_elem_residual(Ctx& c, P2Space& S, int comp0, const PhysParams& P, const double* u, const double* a0,
-                                            const double* a1) {
+// triangle rule of an operator: the reference drivers' order (OpTraits<OP>::NQ points) or, with intorder 5, the 7-point rule
+template <int DEG, int OP, int NQ> void launch_elem_residual_q(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P,
+                                                               const double* u, const double* a0, const double* a1) {
   const int g = grid_for(S.nT, 128);
-  k_p2_elem_residual<OP><<<g, 128, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, S.fphys.p, c.d_surf.p, c.d_surf_dir.p, P,
-                                                  S.nd, comp0, u, a0, a1, S.scratch.p);
+  k_p2_elem_residual<DEG, OP, NQ><<<g, 128, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, S.fphys.p, c.d_surf.p,
+                                                           c.d_surf_dir.p, P, S.nd, op.comp0, op.intorder == 5 ? 3 : 2, u, a0, a1,
+                                                           S.scratch.p);
   PNP_CHECK_LAUNCH(); c.launches++;
 }
-template <int OP> void launch_elem_jacobian(Ctx& c, P2Space& S, const PhysParams& P, int mode, double eps, const double* u,
-                                            const double* a0, const double* a1) {
+template <int DEG, int OP> void launch_elem_residual(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P, const double* u,
+                                                     const double* a0, const double* a1) {
+  if (op.intorder == 5) launch_elem_residual_q<DEG, OP, 7>(c, S, op, P, u, a0, a1);
+  else launch_elem_residual_q<DEG, OP, OpTraits<OP>::NQ>(c, S, op, P, u, a0, a1);
+}
+template <int DEG, int OP, int NQ> void launch_elem_jacobian_q(Ctx& c, P2Space& S, const PhysParams& P, int mode, double eps,
+                                                               const double* u, const double* a0, const double* a1) {
   const int g = grid_for(S.nT, 64);
-  if (mode == 0) k_p2_elem_jacobian<OP, 0><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
-  else k_p2_elem_jacobian<OP, 1><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
+  if (mode == 0) k_p2_elem_jacobian<DEG, OP, NQ, 0><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
+  else k_p2_elem_jacobian<DEG, OP, NQ, 1><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
   PNP_CHECK_LAUNCH(); c.launches++;
+}
+template <int DEG, int OP> void launch_elem_jacobian(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P, int mode, double eps,
+                                                     const double* u, const double* a0, const double* a1) {
+  if (op.intorder == 5) launch_elem_jacobian_q<DEG, OP, 7>(c, S, P, mode, eps, u, a0, a1);
+  else launch_elem_jacobian_q<DEG, OP, OpTraits<OP>::NQ>(c, S, P, mode, eps, u, a0, a1);
+}
+template <int DEG> void dispatch_residual(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P, const double* u, const double* a0,
+                                          const double* a1) {
+  switch (op.op) {
+    case OP_PB: launch_elem_residual<DEG, OP_PB>(c, S, op, P, u, a0, a1); break;
+    case OP_POISSON: launch_elem_residual<DEG, OP_POISSON>(c, S, op, P, u, a0, a1); break;
+    case OP_DIFFUSION: launch_elem_residual<DEG, OP_DIFFUSION>(c, S, op, P, u, a0, a1); break;
+    case OP_MASS: launch_elem_residual<DEG, OP_MASS>(c, S, op, P, u, a0, a1); break;
+    case OP_PNP: launch_elem_residual<DEG, OP_PNP>(c, S, op, P, u, a0, a1); break;
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
+  }
+}
+template <int DEG> void dispatch_jacobian(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P, int mode, double eps,
+                                          const double* u, const double* a0, const double* a1) {
+  switch (op.op) {
+    case OP_PB: launch_elem_jacobian<DEG, OP_PB>(c, S, op, P, mode, eps, u, a0, a1); break;
+    case OP_POISSON: launch_elem_jacobian<DEG, OP_POISSON>(c, S, op, P, mode, eps, u, a0, a1); break;
+    case OP_DIFFUSION: launch_elem_jacobian<DEG, OP_DIFFUSION>(c, S, op, P, mode, eps, u, a0, a1); break;
+    case OP_MASS: launch_elem_jacobian<DEG, OP_MASS>(c, S, op, P, mode, eps, u, a0, a1); break;
+    case OP_PNP: launch_elem_jacobian<DEG, OP_PNP>(c, S, op, P, mode, eps, u, a0, a1); break;
+    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
+  }
 }
 
 void coefficient_ptrs_p2(Ctx& c, const Operator& op, const double** a0, const double** a1) {
@@ -185,12 +222,22 @@ void coefficient_ptrs_p2(Ctx& c, const Operator& op, const double** a0, const do
 
 } // namespace
 
+// Lagrange nodes of the space's degree (host side)
+struct NodeInfo { int kind, sub, idx; double x, y; };
+static NodeInfo node_info(int deg, int n) {
+  NodeInfo t;
+  if (deg == 2) { PkElem<2>::node_key(n, t.kind, t.sub, t.idx); t.x = PkElem<2>::node_x(n); t.y = PkElem<2>::node_y(n); }
+  else { PkElem<3>::node_key(n, t.kind, t.sub, t.idx); t.x = PkElem<3>::node_x(n); t.y = PkElem<3>::node_y(n); }
+  return t;
+}
+
 // ---- space: edges, element dof map, incidence lists, boundary faces, Dirichlet flags (host, from the canonical mesh) ----
 void p2_build(Ctx& c) {
   PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "quadratic elements work on an unpartitioned mesh");
   auto S = std::make_shared<P2Space>();
   const long nv = c.nv, nT = c.nT, nB = c.nB;
-  S->nT = nT; S->nv = nv;
+  S->nT = nT; S->nv = nv; S->deg = c.degree; S->NL = (c.degree + 1) * (c.degree + 2) / 2;
+  const int NL = S->NL, deg = S->deg;
   const std::vector<int> tri = c.ctri.to_host(c.stream), ba = c.cba.to_host(c.stream), bb = c.cbb.to_host(c.stream),
                          bph = c.cbphys.to_host(c.stream);
   auto key = [](int a, int b) { return ((uint64_t)std::min(a, b) << 32) | (uint64_t)std::max(a, b); };
@@ -198,16 +245,27 @@ void p2_build(Ctx& c) {
   for (long e = 0; e < nT; e++) for (int f = 0; f < 3; f++) keys[3 * e + f] = key(tri[3 * e + FACE_V2[f][0]], tri[3 * e + FACE_V2[f][1]]);
   std::vector<uint64_t> uk(keys);
   std::sort(uk.begin(), uk.end()); uk.erase(std::unique(uk.begin(), uk.end()), uk.end());
-  S->nE = (long)uk.size(); S->nd = S->nE + nv;
-  PNP_REQUIRE(3 * S->nd < (1l << 31), PNP_E_MESH, "too many dofs for 32-bit column indices");
+  S->nE = (long)uk.size();
+  S->eoff = deg == 3 ? nT : 0; S->voff = S->eoff + (deg - 1) * S->nE; S->nd = S->voff + nv; // elements, edges, vertices
+  PNP_REQUIRE(3 * S->nd < (1l << 31) && nT < (1l << 27), PNP_E_MESH, "too many dofs for 32-bit column indices");
   S->h_eva.resize(S->nE); S->h_evb.resize(S->nE);
   for (long k = 0; k < S->nE; k++) { S->h_eva[k] = (int)(uk[k] >> 32); S->h_evb[k] = (int)(uk[k] & 0xffffffffu); }
   std::vector<int> tedge(3 * (size_t)nT);
   for (size_t i = 0; i < keys.size(); i++) tedge[i] = (int)(std::lower_bound(uk.begin(), uk.end(), keys[i]) - uk.begin());
   S->h_e2d.resize(NL * (size_t)nT);
   for (long e = 0; e < nT; e++)
-    for (int i = 0; i < NL; i++)
-      S->h_e2d[NL * e + i] = p2::node_is_edge(i) ? tedge[3 * e + p2::node_sub(i)] : (int)(S->nE + tri[3 * e + p2::node_sub(i)]);
+    for (int i = 0; i < NL; i++) {
+      const NodeInfo t = node_info(deg, i);
+      int d;
+      if (t.kind == 2) d = (int)e;
+      else if (t.kind == 0) d = (int)(S->voff + tri[3 * e + t.sub]);
+      else { // edge dofs are counted from the end vertex with the smaller index (Pk2DLocalFiniteElementMap's variant choice)
+        int idx = t.idx;
+        if (deg == 3 && tri[3 * e + FACE_V2[t.sub][0]] > tri[3 * e + FACE_V2[t.sub][1]]) idx = 1 - idx;
+        d = (int)(S->eoff + (deg - 1) * tedge[3 * e + t.sub] + idx);
+      }
+      S->h_e2d[NL * e + i] = d;
+    }
   // boundary faces: the element face whose edge is a boundary segment carries that segment's surface; neighbours across faces
   std::vector<int> edge_phys(S->nE, -1), edge_elem0(S->nE, -1), edge_elem1(S->nE, -1);
   for (long s = 0; s < nB; s++) {
@@ -228,7 +286,7 @@ void p2_build(Ctx& c) {
   for (size_t i = 0; i < S->h_e2d.size(); i++) ptr[S->h_e2d[i] + 1]++;
   for (long d = 0; d < S->nd; d++) ptr[d + 1] += ptr[d];
   { std::vector<int> fill(ptr.begin(), ptr.end() - 1);
-    for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) inc[fill[S->h_e2d[NL * e + i]]++] = (int)(e * 8 + i); }
+    for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) inc[fill[S->h_e2d[NL * e + i]]++] = (int)(e * 16 + i); }
   { const int order[3] = {0, 2, 1};
     for (long e = 0; e < nT; e++) for (int fi = 0; fi < 3; fi++) if (S->h_fphys[3 * e + order[fi]] >= 0) S->h_bfaces.push_back((int)(e * 4 + order[fi])); }
   S->bfaces.alloc(S->h_bfaces.size()); S->bfaces.upload(S->h_bfaces.data(), S->h_bfaces.size(), c.stream);
@@ -244,7 +302,7 @@ void p2_build(Ctx& c) {
   c.p2 = S; c.p2_nd = S->nd;
 }
 
-// Dirichlet flags (ConformingDirichletConstraints): a Dirichlet face constrains its end vertices and its edge dof
+// Dirichlet flags (ConformingDirichletConstraints): a Dirichlet face constrains its end vertices and its edge dofs
 void p2_constraints(Ctx& c) {
   PNP_REQUIRE(c.p2 && c.params.set, PNP_E_ARG, "quadratic space / parameters not set");
   P2Space& S = *c.p2;
@@ -255,7 +313,8 @@ void p2_constraints(Ctx& c) {
     PNP_REQUIRE(ph < c.params.n_surfaces, PNP_E_CONFIG, "physical tag without [surface_i] section");
     unsigned char m = 0;
     for (int comp = 0; comp < 3; comp++) if (c.params.surfaces[ph].btype[comp] == 0) m |= (unsigned char)(1u << comp);
-    S.h_dir[k] |= m; S.h_dir[S.nE + S.h_eva[k]] |= m; S.h_dir[S.nE + S.h_evb[k]] |= m;
+    for (int l = 0; l < S.deg - 1; l++) S.h_dir[S.eoff + (S.deg - 1) * k + l] |= m;
+    S.h_dir[S.voff + S.h_eva[k]] |= m; S.h_dir[S.voff + S.h_evb[k]] |= m;
   }
   S.dir.upload(S.h_dir.data(), S.nd, c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
@@ -263,7 +322,7 @@ void p2_constraints(Ctx& c) {
 }
 
 static P2Space& space(Ctx& c) {
-  PNP_REQUIRE(c.degree == 2 && c.p2, PNP_E_ARG, "no quadratic space (pnp_space_set_degree(ctx, 2) before pnp_mesh_finalize)");
+  PNP_REQUIRE(c.degree >= 2 && c.p2, PNP_E_ARG, "no quadratic / cubic space (pnp_space_set_degree before pnp_mesh_finalize)");
   return *c.p2;
 }
 
@@ -275,6 +334,7 @@ P2Pattern& p2_pattern(Ctx& c, int F, int comp0) {
   slot = std::make_unique<P2Pattern>();
   P2Pattern& Pn = *slot;
   const long nd = S.nd, nT = S.nT, N = F * nd;
+  const int NL = S.NL;
   auto dirichlet = [&](int k, long d) { return (S.h_dir[d] >> (F == 3 ? k : comp0)) & 1; };
   std::vector<int> cnt(nd + 1, 0);
   for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) cnt[S.h_e2d[NL * e + i] + 1] += NL;
@@ -318,21 +378,15 @@ void p2_matrix_init(Ctx& c, Matrix& A, const Operator& op) {
 void p2_assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
   P2Space& S = space(c);
   PNP_REQUIRE(c.params.set, PNP_E_ARG, "parameters not set");
-  const int F = op_fields(op.op), n = NL * F;
+  const int F = op_fields(op.op), n = S.NL * F;
   PNP_REQUIRE(u.fields == F && r.fields == F, PNP_E_ARG, "vector field count does not match the operator");
   const double *a0, *a1;
   coefficient_ptrs_p2(c, op, &a0, &a1);
   if (S.scratch.n < (size_t)n * S.nT) S.scratch.alloc((size_t)n * S.nT);
   const PhysParams P = c.phys(op.valency);
-  switch (op.op) {
-    case OP_PB: launch_elem_residual<OP_PB>(c, S, op.comp0, P, u.d.p, a0, a1); break;
-    case OP_POISSON: launch_elem_residual<OP_POISSON>(c, S, op.comp0, P, u.d.p, a0, a1); break;
-    case OP_DIFFUSION: launch_elem_residual<OP_DIFFUSION>(c, S, op.comp0, P, u.d.p, a0, a1); break;
-    case OP_MASS: launch_elem_residual<OP_MASS>(c, S, op.comp0, P, u.d.p, a0, a1); break;
-    case OP_PNP: launch_elem_residual<OP_PNP>(c, S, op.comp0, P, u.d.p, a0, a1); break;
-    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
-  }
-  k_p2_gather_residual<<<grid_for(F * S.nd, 256), 256, 0, c.stream>>>(S.nd, F, op.comp0, S.inc_ptr.p, S.inc.p, S.dir.p, S.scratch.p, r.d.p);
+  if (S.deg == 2) dispatch_residual<2>(c, S, op, P, u.d.p, a0, a1);
+  else dispatch_residual<3>(c, S, op, P, u.d.p, a0, a1);
+  k_p2_gather_residual<<<grid_for(F * S.nd, 256), 256, 0, c.stream>>>(S.nd, F, S.NL, op.comp0, S.inc_ptr.p, S.inc.p, S.dir.p, S.scratch.p, r.d.p);
   PNP_CHECK_LAUNCH(); c.launches++;
   c.acct(Ctx::ACC_ASSEMBLY, (double)S.nT * (12 + 24 + 16.0 * n) + (double)F * S.nd * 16.0);
 }
@@ -340,7 +394,7 @@ void p2_assemble_residual(Ctx& c, const Operator& op, Vec& u, Vec& r) {
 void p2_assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mode, double eps) {
   P2Space& S = space(c);
   PNP_REQUIRE(c.params.set, PNP_E_ARG, "parameters not set");
-  const int F = op_fields(op.op), n = NL * F;
+  const int F = op_fields(op.op), n = S.NL * F;
   PNP_REQUIRE(u.fields == F && A.op == op.op, PNP_E_ARG, "vector / matrix do not match the operator");
   PNP_REQUIRE(mode == 0 || mode == 1, PNP_E_ARG, "unknown jacobian mode");
   p2_matrix_init(c, A, op);
@@ -348,15 +402,9 @@ void p2_assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mod
   coefficient_ptrs_p2(c, op, &a0, &a1);
   if (S.scratch.n < (size_t)n * n * S.nT) S.scratch.alloc((size_t)n * n * S.nT);
   const PhysParams P = c.phys(op.valency);
-  switch (op.op) {
-    case OP_PB: launch_elem_jacobian<OP_PB>(c, S, P, mode, eps, u.d.p, a0, a1); break;
-    case OP_POISSON: launch_elem_jacobian<OP_POISSON>(c, S, P, mode, eps, u.d.p, a0, a1); break;
-    case OP_DIFFUSION: launch_elem_jacobian<OP_DIFFUSION>(c, S, P, mode, eps, u.d.p, a0, a1); break;
-    case OP_MASS: launch_elem_jacobian<OP_MASS>(c, S, P, mode, eps, u.d.p, a0, a1); break;
-    case OP_PNP: launch_elem_jacobian<OP_PNP>(c, S, P, mode, eps, u.d.p, a0, a1); break;
-    default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
-  }
-  k_p2_gather_jacobian<<<grid_for(F * S.nd, 128), 128, 0, c.stream>>>(S.nd, F, op.comp0, S.inc_ptr.p, S.inc.p, S.e2d.p, S.dir.p, A.csr_rp,
+  if (S.deg == 2) dispatch_jacobian<2>(c, S, op, P, mode, eps, u.d.p, a0, a1);
+  else dispatch_jacobian<3>(c, S, op, P, mode, eps, u.d.p, a0, a1);
+  k_p2_gather_jacobian<<<grid_for(F * S.nd, 128), 128, 0, c.stream>>>(S.nd, F, S.NL, op.comp0, S.inc_ptr.p, S.inc.p, S.e2d.p, S.dir.p, A.csr_rp,
                                                                       A.csr_col, S.scratch.p, A.vals.p);
   PNP_CHECK_LAUNCH(); c.launches++;
   c.last_u = nullptr; c.last_vals = nullptr; // (no multigrid re-discretisation for quadratic elements)
@@ -500,6 +548,7 @@ void csr_ilu0_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double*
 
 // ---- the boundary's views of the space ----
 void p2_sizes(Ctx& c, long* nE, long* nd) { P2Space& S = space(c); if (nE) *nE = S.nE; if (nd) *nd = S.nd; }
+void p2_offsets(Ctx& c, long* eoff, long* voff) { P2Space& S = space(c); if (eoff) *eoff = S.eoff; if (voff) *voff = S.voff; }
 void p2_edges(Ctx& c, int* eva, int* evb) {
   P2Space& S = space(c);
   if (eva) std::copy(S.h_eva.begin(), S.h_eva.end(), eva);
@@ -530,6 +579,7 @@ void p2_matrix_import(Ctx& c, const Operator& op, Matrix& A, const int* rowptr, 
 // ---- the time loop's diagnostics with quadratic functions (pnp_output.cu has the linear ones) ----
 namespace {
 // calcIonFlux (ionFlux.hh:51-83): one thread per boundary face; fields and gradients at the face centre
+template <int DEG>
 __global__ void k_p2_ion_flux(const int* __restrict__ faces, int nF, const int* __restrict__ tri, const double* __restrict__ cx,
                               const double* __restrict__ cy, const int* __restrict__ e2d, const double* __restrict__ phi,
                               const double* __restrict__ cp, const double* __restrict__ cm, int cylindrical, double PI,
@@ -539,11 +589,13 @@ __global__ void k_p2_ion_flux(const int* __restrict__ faces, int nF, const int* 
   const int e = faces[t] >> 2, f = faces[t] & 3;
   const int la = f == 2 ? 1 : 0, lb = f == 0 ? 1 : 2, lc = 3 - la - lb;
   const int v[3] = {tri[3 * e], tri[3 * e + 1], tri[3 * e + 2]};
-  const p2::Geo2 G = p2::make_geo2(cx[v[0]], cy[v[0]], cx[v[1]], cy[v[1]], cx[v[2]], cy[v[2]]);
+  using E = PkElem<DEG>;
+  constexpr int NL = E::NL;
+  const typename E::Geo2 G = E::make_geo2(cx[v[0]], cy[v[0]], cx[v[1]], cy[v[1]], cx[v[2]], cy[v[2]]);
   const double VX[3] = {0.0, 1.0, 0.0}, VY[3] = {0.0, 0.0, 1.0};
   const double ax = cx[v[la]], ay = cy[v[la]], bx = cx[v[lb]], by = cy[v[lb]];
   const double ex = 0.5 * (ax + bx), ey = 0.5 * (ay + by);
-  const p2::BasisAt B = p2::basis_at(G, 0.5 * (VX[la] + VX[lb]), 0.5 * (VY[la] + VY[lb]));
+  const typename E::BasisAt B = E::basis_at(G, 0.5 * (VX[la] + VX[lb]), 0.5 * (VY[la] + VY[lb]));
   double vcp = 0, vcm = 0, gphi[2] = {0, 0}, gcp[2] = {0, 0}, gcm[2] = {0, 0};
   for (int k = 0; k < NL; k++) {
     const int d = e2d[NL * e + k];
@@ -562,12 +614,15 @@ __global__ void k_p2_ion_flux(const int* __restrict__ faces, int nF, const int* 
   out[2 * t + 1] = (gcm[0] - gphi[0]) * nx + (gcm[1] - gphi[1]) * ny;
 }
 // DataWriter::writeData: centre, value and gradient at the centre of every element
+template <int DEG>
 __global__ void k_p2_cell_data(int nT, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
                                const int* __restrict__ e2d, const double* __restrict__ u, double* __restrict__ out) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nT; e += gridDim.x * blockDim.x) {
     const int a = tri[3 * e], b = tri[3 * e + 1], c = tri[3 * e + 2];
-    const p2::Geo2 G = p2::make_geo2(cx[a], cy[a], cx[b], cy[b], cx[c], cy[c]);
-    const p2::BasisAt B = p2::basis_at(G, 1.0 / 3.0, 1.0 / 3.0);
+    using E = PkElem<DEG>;
+    constexpr int NL = E::NL;
+    const typename E::Geo2 G = E::make_geo2(cx[a], cy[a], cx[b], cy[b], cx[c], cy[c]);
+    const typename E::BasisAt B = E::basis_at(G, 1.0 / 3.0, 1.0 / 3.0);
     double val = 0, gr[2] = {0, 0};
     for (int k = 0; k < NL; k++) {
       const double uk = u[e2d[NL * e + k]];
@@ -588,8 +643,10 @@ void p2_ion_flux(Ctx& c, const Vec& phi, const Vec& cp, const Vec& cm, double* i
   for (int s = 0; s < ns; s++) ip[s] = im[s] = 0.0;
   if (!nF) return;
   DBuf<double> d(2 * (size_t)nF);
-  k_p2_ion_flux<<<(nF + 127) / 128, 128, 0, c.stream>>>(S.bfaces.p, nF, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, phi.d.p, cp.d.p, cm.d.p,
-                                                      c.params.cylindrical, c.params.PI, d.p);
+  if (S.deg == 2) k_p2_ion_flux<2><<<(nF + 127) / 128, 128, 0, c.stream>>>(S.bfaces.p, nF, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, phi.d.p, cp.d.p,
+                                                                         cm.d.p, c.params.cylindrical, c.params.PI, d.p);
+  else k_p2_ion_flux<3><<<(nF + 127) / 128, 128, 0, c.stream>>>(S.bfaces.p, nF, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, phi.d.p, cp.d.p, cm.d.p,
+                                                              c.params.cylindrical, c.params.PI, d.p);
   PNP_CHECK_LAUNCH(); c.launches++;
   const std::vector<double> h = d.to_host(c.stream);
   for (int t = 0; t < nF; t++) { // per-surface sums in the element loop's order
@@ -602,7 +659,8 @@ void p2_write_cell_data(Ctx& c, const Vec& u, const std::string& filename) {
   P2Space& S = space(c);
   PNP_REQUIRE(u.fields == 1, PNP_E_ARG, "writeData: a 1-field vector expected");
   DBuf<double> d(5 * (size_t)S.nT);
-  k_p2_cell_data<<<grid_for(S.nT, 128), 128, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, u.d.p, d.p);
+  if (S.deg == 2) k_p2_cell_data<2><<<grid_for(S.nT, 128), 128, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, u.d.p, d.p);
+  else k_p2_cell_data<3><<<grid_for(S.nT, 128), 128, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, u.d.p, d.p);
   PNP_CHECK_LAUNCH(); c.launches++;
   const std::vector<double> h = d.to_host(c.stream);
   std::FILE* f = std::fopen(filename.c_str(), "w");
@@ -614,7 +672,7 @@ void p2_write_cell_data(Ctx& c, const Vec& u, const std::string& filename) {
 void p2_vertex_values(Ctx& c, const Vec& u, double* out) {
   P2Space& S = space(c);
   PNP_REQUIRE(u.fields == 1, PNP_E_ARG, "a 1-field vector expected");
-  PNP_CUDA(cudaMemcpyAsync(out, u.d.p + S.nE, S.nv * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  PNP_CUDA(cudaMemcpyAsync(out, u.d.p + S.voff, S.nv * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 
@@ -643,9 +701,10 @@ void p2_interpolate_bcext(Ctx& c, int comp, const Vec* pb, Vec& out) {
   const int order[3] = {0, 2, 1};
   for (long e = 0; e < S.nT; e++) {
     const int a = tri[3 * e], b = tri[3 * e + 1], cv = tri[3 * e + 2];
-    for (int i = 0; i < NL; i++) {
-      const double px = x[a] + (x[b] - x[a]) * p2::node_x(i) + (x[cv] - x[a]) * p2::node_y(i);
-      const double py = y[a] + (y[b] - y[a]) * p2::node_x(i) + (y[cv] - y[a]) * p2::node_y(i);
+    for (int i = 0; i < S.NL; i++) {
+      const NodeInfo nt = node_info(S.deg, i);
+      const double px = x[a] + (x[b] - x[a]) * nt.x + (x[cv] - x[a]) * nt.y;
+      const double py = y[a] + (y[b] - y[a]) * nt.x + (y[cv] - y[a]) * nt.y;
       int pg = -1;
       for (int fi = 0; fi < 3; fi++) {
         const int f = order[fi];
@@ -659,7 +718,7 @@ void p2_interpolate_bcext(Ctx& c, int comp, const Vec* pb, Vec& out) {
           }
         }
       }
-      const int d = S.h_e2d[NL * e + i];
+      const int d = S.h_e2d[S.NL * e + i];
       if (pg > -1 && s.surfaces.at(pg).btype[comp] == 0) { u[d] = s.surfaces[pg].dval[comp]; continue; }
       const double yv = pb ? pbh[d] : 0.0;
       u[d] = comp == 0 ? yv : (comp == 1 ? s.c0 * std::exp(-yv) : s.c0 * std::exp(+yv));

@@ -331,7 +331,7 @@ void mesh_finalize(Ctx& c, bool renumber) {
   PNP_CUDA(cudaStreamSynchronize(c.stream));
   c.finalized = true; c.constraints_built = false;
   halo_finalize(c);
-  if (c.degree == 2) p2_build(c);
+  if (c.degree >= 2) p2_build(c);
   if (c.params.set) constraints_build(c);
 }
 
@@ -386,13 +386,13 @@ void constraints_build(Ctx& c) {
   c.d_surf_dir.alloc(sdir.size());
   c.d_surf_dir.upload(sdir.data(), sdir.size(), c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
-  if (c.degree == 2) p2_constraints(c);
+  if (c.degree >= 2) p2_constraints(c);
   c.constraints_built = true;
 }
 
 void vec_upload(Ctx& c, Vec& v, const double* host_lex) {
   PNP_REQUIRE(c.finalized, PNP_E_ARG, "mesh not finalized");
-  if (c.degree == 2) { v.d.upload(host_lex, v.d.n, c.stream); PNP_CUDA(cudaStreamSynchronize(c.stream)); return; } // device layout = the reference's
+  if (c.degree >= 2) { v.d.upload(host_lex, v.d.n, c.stream); PNP_CUDA(cudaStreamSynchronize(c.stream)); return; } // device layout = the reference's
   const long n = c.nv * v.fields;
   // staging buffer kept between calls: allocating and freeing a vector-sized block per transfer costs more than the copy
   DBuf<double>& tmp = c.io_stage;
@@ -402,7 +402,7 @@ void vec_upload(Ctx& c, Vec& v, const double* host_lex) {
   PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 void vec_download(Ctx& c, const Vec& v, double* host_lex) {
-  if (c.degree == 2) { v.d.download(host_lex, v.d.n, c.stream); return; }
+  if (c.degree >= 2) { v.d.download(host_lex, v.d.n, c.stream); return; }
   const long n = c.nv * v.fields;
   DBuf<double>& tmp = c.io_stage;
   if (tmp.n < (size_t)n) tmp.alloc(n);
@@ -452,7 +452,7 @@ long pattern_export(Ctx& c, int op_handle, int* rowptr, int* col) {
   PNP_REQUIRE(c.constraints_built, PNP_E_ARG, "constraints not built");
   PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "pattern export works on an unpartitioned mesh");
   const Operator& op = c.oper(op_handle);
-  if (c.degree == 2) return p2_pattern_export(c, op, rowptr, col);
+  if (c.degree >= 2) return p2_pattern_export(c, op, rowptr, col);
   HostStar h = fetch_star(c);
   const long nv = c.nv;
   return walk_pattern(c, op, h, rowptr, [&](long k, int ki, int kj, int slot, bool) {
@@ -466,7 +466,7 @@ void matrix_export(Ctx& c, int op_handle, const Matrix& A, double* val) {
   PNP_REQUIRE(c.n_own == c.nv, PNP_E_ARG, "matrix export works on an unpartitioned mesh");
   const Operator& op = c.oper(op_handle);
   PNP_REQUIRE(A.op == op.op, PNP_E_ARG, "matrix belongs to another operator type");
-  if (c.degree == 2) { PNP_REQUIRE(A.csr_rp, PNP_E_ARG, "matrix not assembled"); A.vals.download(val, A.csr_nnz, c.stream); return; }
+  if (c.degree >= 2) { PNP_REQUIRE(A.csr_rp, PNP_E_ARG, "matrix not assembled"); A.vals.download(val, A.csr_nnz, c.stream); return; }
   HostStar h = fetch_star(c);
   std::vector<double> v = A.vals.to_host(c.stream);
   const long ns = c.nslots;
@@ -486,7 +486,7 @@ void matrix_import(Ctx& c, int op_handle, Matrix& A, const int* rowptr, const in
   PNP_REQUIRE(rowptr && col && val, PNP_E_ARG, "null CSR arrays");
   const Operator& op = c.oper(op_handle);
   PNP_REQUIRE(A.op == op.op, PNP_E_ARG, "matrix belongs to another operator type");
-  if (c.degree == 2) { p2_matrix_import(c, op, A, rowptr, col, val); return; }
+  if (c.degree >= 2) { p2_matrix_import(c, op, A, rowptr, col, val); return; }
   HostStar h = fetch_star(c);
   const long ns = c.nslots, nv = c.nv;
   std::vector<double> v((size_t)A.nplanes * ns, 0.0);

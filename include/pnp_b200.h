@@ -307,20 +307,29 @@ pnp_status pnp_write_vtk(pnp_ctx*, const char* name, int n, const int* vec_handl
 /* component 0: phi, 1: c+, 2: c-; pb_vec < 0 means a zero PB field; out is a 1-field vector */
 pnp_status pnp_interpolate_bcext(pnp_ctx*, int component, int pb_vec, int out_vec);
 
-/* ---- quadratic elements: the reference's -DPDEGREE=2 programs (src/Makefile.am:57-110; Pk2DLocalFiniteElementMap<..., 
- * PDEGREE>, instationary_pnp_from_pb_md.hh:26-28,125; stationary_pnp.hh:190-193) ----
- * pnp_space_set_degree(ctx, 2) before pnp_mesh_finalize() selects the P2 space: per field one dof per edge, then one per
- * vertex -- dof k < n_edges sits on edge k (edges ordered by (min vertex, max vertex), pnp_space_edges), dof n_edges + v
- * on vertex v; fields lexicographic.  Vectors (pnp_vec_upload/download), constraints, patterns (pnp_pattern_get: scalar
- * BCRS, ascending columns) and matrix values use that numbering; it is also the device layout (CSR matrices, no
+/* ---- quadratic and cubic elements: the reference's -DPDEGREE=2 / -DPDEGREE=3 programs (src/Makefile.am:54-110;
+ * Pk2DLocalFiniteElementMap<..., PDEGREE>, instationary_pnp_from_pb_md.hh:26-28,125; stationary_pnp.hh:190-193) ----
+ * pnp_space_set_degree(ctx, 2 | 3) before pnp_mesh_finalize() selects the Pk space.  Scalar dofs per field, codim by codim
+ * (SURVEY A.4): degree 3 first one bubble per element [0, nT); then degree-1 dofs per edge from `edge_offset` (edges ordered
+ * by (min vertex, max vertex), pnp_space_edges; the dofs of an edge counted from its smaller end vertex); then one per vertex
+ * from `vertex_offset`; fields lexicographic.  Vectors (pnp_vec_upload/download), constraints, patterns (pnp_pattern_get:
+ * scalar BCRS, ascending columns) and matrix values use that numbering; it is also the device layout (CSR matrices, no
  * renumbering).  Operators, residual, Jacobian (both modes), SpMV, BiCGSTAB/CG with Richardson, Jacobi, SSOR(n) or ILU0
- * (row-order sweeps, level-scheduled), Newton, StationaryLinearProblemSolver, the one-step methods and
- * interpolate(BCExtension) work as for degree 1; the multigrid preconditioner, refinement carry-over, the output writers
- * and partitioned meshes answer PNP_E_ARG.  One GPU. */
+ * (row-order sweeps, level-scheduled), Newton, StationaryLinearProblemSolver, the one-step methods,
+ * interpolate(BCExtension), calcIonFlux, writeData and the VTK vertex data work as for degree 1; the multigrid
+ * preconditioner, refinement carry-over and partitioned meshes answer PNP_E_ARG.  One GPU. */
 pnp_status pnp_space_set_degree(pnp_ctx*, int degree);
 /* degree, number of edges (0 for degree 1) and scalar dofs per field */
 pnp_status pnp_space_sizes(pnp_ctx*, int* degree, long* n_edges, long* ndof);
 pnp_status pnp_space_edges(pnp_ctx*, int* va /*[n_edges]*/, int* vb);
+/* first edge dof and first vertex dof of a field's block (degree 2: 0, n_edges; degree 3: nT, nT + 2 n_edges) */
+pnp_status pnp_space_offsets(pnp_ctx*, long* edge_offset, long* vertex_offset);
+/* Quadrature order of an operator (the `intorder` constructor argument, pb_operator.hh:39, pnp_operator.hh:40, ...).
+ * 0 = what the reference's drivers end up with (3; DiffusionOperator 2; DiffusionTOperator 5), whatever PDEGREE is: with
+ * cubic elements that rule under-integrates the element integrals and -- its centre weight being negative -- makes the PB / PNP
+ * matrices indefinite (tests/test_oracle_p2.py); 5 (degree 2 and 3 only) selects the 7-point triangle rule and the 3-point
+ * Gauss rule on faces, as passing intorder = 5 to the reference's constructors would. */
+pnp_status pnp_operator_set_intorder(pnp_ctx*, int op_handle, int intorder);
 /* packs three 1-field vectors into a 3-field vector / extracts one field */
 pnp_status pnp_vec_pack3(pnp_ctx*, int dst3, int phi, int cp, int cm);
 pnp_status pnp_vec_extract(pnp_ctx*, int src3, int field, int dst1);

@@ -48,7 +48,7 @@ class Grid {
   void readConfigFile(const std::string& cfg) { check(c_, pnp_params_read(c_, cfg.c_str())); }
   void readGmsh(const std::string& msh) { check(c_, pnp_mesh_read_gmsh(c_, msh.c_str())); }
   void globalRefine(int levels) { check(c_, pnp_mesh_refine(c_, levels)); }
-  // Pk2DLocalFiniteElementMap<GV, D, R, PDEGREE> (instationary_pnp_from_pb_md.hh:26-28,125): 1 (default) or 2, before finalize()
+  // Pk2DLocalFiniteElementMap<GV, D, R, PDEGREE> (instationary_pnp_from_pb_md.hh:26-28,125): 1 (default), 2 or 3, before finalize()
   void setDegree(int pdegree) { check(c_, pnp_space_set_degree(c_, pdegree)); }
   void finalize(bool renumber = true) { check(c_, pnp_mesh_finalize(c_, renumber)); }
   // gfs.size() per field: vertices, or edges + vertices for quadratic elements
@@ -123,7 +123,14 @@ template <class LOP> class Matrix {
 template <class LOP> class GridOperator {
  public:
   // bcComponent: the BCType<...,component> a scalar operator is built with (btype.hh:5)
-  GridOperator(Grid& g, int bcComponent = 0) : g_(g) { check(g.ctx(), pnp_operator_create(g.ctx(), LOP::op, bcComponent, &h_)); }
+  GridOperator(Grid& g, int bcComponent = 0) : g_(g) {
+    check(g.ctx(), pnp_operator_create(g.ctx(), LOP::op, bcComponent, &h_));
+#ifdef PNP_INTORDER  // build-wide `intorder` of the local operators (their last constructor argument), e.g. -DPDEGREE=3 -DPNP_INTORDER=5
+    setIntegrationOrder(PNP_INTORDER);
+#endif
+  }
+  // the local operator's `intorder` constructor argument (pb_operator.hh:39): 0 = the reference drivers' default, 5 for degree >= 2
+  void setIntegrationOrder(int intorder) { check(g_.ctx(), pnp_operator_set_intorder(g_.ctx(), h_, intorder)); }
   void setCoefficient(int which, const Vector& v) { check(g_.ctx(), pnp_operator_set_coefficient(g_.ctx(), h_, which, v.handle())); }
   void setValency(double z) { check(g_.ctx(), pnp_operator_set_valency(g_.ctx(), h_, z)); }
   void residual(const Vector& u, Vector& r) const { check(g_.ctx(), pnp_residual(g_.ctx(), h_, u.handle(), r.handle())); }

@@ -38,7 +38,7 @@ def lib():
         L.ora_pattern.restype = C.c_long
         L.ora_pattern_sets.restype = C.c_long
         L.ora_bench_create.restype = C.c_void_p
-        L.ora2_pattern.restype = C.c_long
+        L.orak_pattern.restype = C.c_long
         L.ora_bench_nnz.restype = C.c_long
         L.ora_set_threads(1)
         _LIB = L
@@ -311,32 +311,35 @@ def sinh_shared(x):
 # quadratic elements (PDEGREE = 2, pnp_oracle_p2.hpp): dofs = edges [0, nE) then vertices [nE, nE + nv); fields lexicographic
 # ---------------------------------------------------------------------------------------------------------------
 class P2:
-    def __init__(self, mesh, params):
-        self.mesh, self.params = mesh, params
-        sz = (C.c_long * 2)()
-        _chk(lib().ora2_sizes(mesh.h, params.h, sz))
-        self.nE, self.nd = int(sz[0]), int(sz[1])
+    """Pk space, k = degree (2 or 3).  Scalar dofs: [nT element bubbles (k = 3)] + (k-1) per edge from `eoff` + vertices from `voff`."""
+
+    def __init__(self, mesh, params, degree=2):
+        self.mesh, self.params, self.degree = mesh, params, int(degree)
+        self.NL = (degree + 1) * (degree + 2) // 2
+        sz = (C.c_long * 4)()
+        _chk(lib().orak_sizes(self.degree, mesh.h, params.h, sz))
+        self.nE, self.nd, self.voff, self.eoff = int(sz[0]), int(sz[1]), int(sz[2]), int(sz[3])
         self.eva = np.zeros(self.nE, dtype=np.int32); self.evb = np.zeros(self.nE, dtype=np.int32)
         self.tedge = np.zeros((mesh.nT, 3), dtype=np.int32)
         self.x = np.zeros(self.nd); self.y = np.zeros(self.nd)
-        _chk(lib().ora2_space(mesh.h, params.h, _i(self.eva), _i(self.evb), _i(self.tedge), _d(self.x), _d(self.y)))
+        _chk(lib().orak_space(self.degree, mesh.h, params.h, _i(self.eva), _i(self.evb), _i(self.tedge), _d(self.x), _d(self.y)))
 
     def dirichlet(self, fields, comp0=0):
         out = np.zeros(fields * self.nd, dtype=np.int8)
-        _chk(lib().ora2_dirichlet(self.mesh.h, self.params.h, fields, comp0, out.ctypes.data_as(C.c_char_p)))
+        _chk(lib().orak_dirichlet(self.degree, self.mesh.h, self.params.h, fields, comp0, out.ctypes.data_as(C.c_char_p)))
         return out.astype(bool)
 
     def pattern(self, fields, comp0=0):
         rowptr = np.zeros(fields * self.nd + 1, dtype=np.int32)
-        nnz = _chk(lib().ora2_pattern(self.mesh.h, self.params.h, fields, comp0, _i(rowptr), None))
+        nnz = _chk(lib().orak_pattern(self.degree, self.mesh.h, self.params.h, fields, comp0, _i(rowptr), None))
         col = np.zeros(nnz, dtype=np.int32)
-        _chk(lib().ora2_pattern(self.mesh.h, self.params.h, fields, comp0, _i(rowptr), _i(col)))
+        _chk(lib().orak_pattern(self.degree, self.mesh.h, self.params.h, fields, comp0, _i(rowptr), _i(col)))
         return rowptr, col
 
     def residual(self, op, u, aux0=None, aux1=None, valency=1.0, intorder=-1, comp0=0, want_abs=False):
         u = _f64(u); aux0 = _f64(aux0); aux1 = _f64(aux1)
         r = np.zeros_like(u); ab = np.zeros_like(u) if want_abs else None
-        _chk(lib().ora2_residual(self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
+        _chk(lib().orak_residual(self.degree, self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
                                  _d(r), _d(ab)))
         return (r, ab) if want_abs else r
 
@@ -344,29 +347,29 @@ class P2:
         u = _f64(u); aux0 = _f64(aux0); aux1 = _f64(aux1)
         rowptr, col = self.pattern(nfields(op), comp0)
         val = np.zeros(len(col)); ab = np.zeros(len(col)) if want_abs else None
-        _chk(lib().ora2_jacobian(self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
+        _chk(lib().orak_jacobian(self.degree, self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
                                  mode, C.c_double(eps), _d(val), _d(ab)))
         return (rowptr, col, val, ab) if want_abs else (rowptr, col, val)
 
     def interpolate(self, comp, pb=None):
         pb = _f64(pb)
         u = np.zeros(self.nd)
-        _chk(lib().ora2_interpolate(self.mesh.h, self.params.h, comp, _d(pb), _d(u)))
+        _chk(lib().orak_interpolate(self.degree, self.mesh.h, self.params.h, comp, _d(pb), _d(u)))
         return u
 
     def ion_flux(self, phi, cp, cm):
         ns = int(self.params.sys[0])
         ip = np.zeros(ns); im = np.zeros(ns)
-        _chk(lib().ora2_ion_flux(self.mesh.h, self.params.h, _d(_f64(phi)), _d(_f64(cp)), _d(_f64(cm)), _d(ip), _d(im)))
+        _chk(lib().orak_ion_flux(self.degree, self.mesh.h, self.params.h, _d(_f64(phi)), _d(_f64(cp)), _d(_f64(cm)), _d(ip), _d(im)))
         return ip, im
 
     def write_cell_data(self, u, filename):
-        _chk(lib().ora2_write_cell_data(self.mesh.h, self.params.h, _d(_f64(u)), filename.encode()))
+        _chk(lib().orak_write_cell_data(self.degree, self.mesh.h, self.params.h, _d(_f64(u)), filename.encode()))
 
     def newton(self, op, u0, opts, aux0=None, aux1=None, valency=1.0, intorder=-1, comp0=0, cap=128):
         u = _f64(u0).copy(); aux0 = _f64(aux0); aux1 = _f64(aux1)
         res = np.zeros(16); hist = np.zeros(cap); lin = np.zeros(cap, dtype=np.int32)
-        _chk(lib().ora2_newton(self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
+        _chk(lib().orak_newton(self.degree, self.mesh.h, self.params.h, op, comp0, _d(u), _d(aux0), _d(aux1), C.c_double(valency), intorder,
                                _d(_f64(opts)), _d(res), _d(hist), _i(lin), cap))
         keys = ["status", "converged", "iterations", "first_defect", "defect", "reduction", "total_linear_iterations",
                 "total_ls_trials", "jacobian_assemblies", "residual_assemblies", "seconds"]
@@ -378,7 +381,12 @@ class P2:
         return u, out
 
 
-def p2_basis(x, y):
-    phi = np.zeros(6); g = np.zeros(12)
-    lib().ora2_basis(C.c_double(x), C.c_double(y), _d(phi), _d(g))
-    return phi, g.reshape(6, 2)
+def p2_basis(x, y, degree=2):
+    nl = (degree + 1) * (degree + 2) // 2
+    phi = np.zeros(nl); g = np.zeros(2 * nl)
+    lib().orak_basis(int(degree), C.c_double(x), C.c_double(y), _d(phi), _d(g))
+    return phi, g.reshape(nl, 2)
+
+
+def P3(mesh, params):
+    return P2(mesh, params, 3)

@@ -346,85 +346,115 @@ int ora_assembly_par(void* mh, void* ph, int op, const double* u, int threads, i
 
 void ora_sinh_shared(int n, const double* x, double* y) { for (int i = 0; i < n; i++) y[i] = sinh_shared(x[i]); }
 
-// ---- quadratic elements (PDEGREE = 2): pnp_oracle_p2.hpp ----
+// ---- quadratic and cubic elements (PDEGREE = 2, 3): pnp_oracle_p2.hpp; `degree` picks Pk<2> or Pk<3> ----
 static OpCtx make_ctx2(const Mesh* m, const Sysparams* s, int op, const double* a0, const double* a1, double valency, int intorder) {
   return make_ctx(m, s, op, a0, a1, valency, intorder); // (coefficient vectors are P2 vectors of length nE + nv here)
 }
-// sizes[2] = {nE, scalar dofs}
-int ora2_sizes(void* mh, void* ph, long* sizes) {
+// sizes[4] = {nE, scalar dofs, first vertex dof, first edge dof}
+extern "C++" template <class P> int pk_sizes(void* mh, void* ph, long* sizes) {
   ORA_TRY
-  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
-  sizes[0] = sp.nE; sizes[1] = sp.nd;
+  typename P::Space2 sp = P::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
+  sizes[0] = sp.nE; sizes[1] = sp.nd; sizes[2] = sp.voff; sizes[3] = sp.eoff;
   return 0;
   ORA_CATCH(-1)
 }
+int orak_sizes(int degree, void* mh, void* ph, long* sizes) {
+  return degree == 3 ? pk_sizes<p3>(mh, ph, sizes) : pk_sizes<p2>(mh, ph, sizes);
+}
 // edges (end vertices), element -> local edge index, coordinates of the scalar dofs
-int ora2_space(void* mh, void* ph, int* eva, int* evb, int* tedge, double* dx, double* dy) {
+extern "C++" template <class P> int pk_space(void* mh, void* ph, int* eva, int* evb, int* tedge, double* dx, double* dy) {
   ORA_TRY
   const Mesh& m = *(Mesh*)mh;
-  p2::Space2 sp = p2::make_space2(m, ((Params*)ph)->s, 1, 0);
+  typename P::Space2 sp = P::make_space2(m, ((Params*)ph)->s, 1, 0);
   if (eva) std::copy(sp.eva.begin(), sp.eva.end(), eva);
   if (evb) std::copy(sp.evb.begin(), sp.evb.end(), evb);
   if (tedge) std::copy(sp.tedge.begin(), sp.tedge.end(), tedge);
-  if (dx && dy) {
-    for (int k = 0; k < sp.nE; k++) { dx[k] = 0.5 * (m.x[sp.eva[k]] + m.x[sp.evb[k]]); dy[k] = 0.5 * (m.y[sp.eva[k]] + m.y[sp.evb[k]]); }
-    for (int v = 0; v < m.nv; v++) { dx[sp.nE + v] = m.x[v]; dy[sp.nE + v] = m.y[v]; }
-  }
+  if (dx && dy) // position of every scalar dof = its Lagrange node: geometry().global(node) from any element that holds it
+    for (int e = 0; e < m.nT; e++) {
+      const int a = m.tri[3 * e], b = m.tri[3 * e + 1], c = m.tri[3 * e + 2];
+      for (int i = 0; i < P::NL; i++) {
+        const double lx = P::nodes().x[i], ly = P::nodes().y[i];
+        const int d = sp.sdof(e, i);
+        if (P::nodes().kind[i] == 0) { dx[d] = m.x[m.tri[3 * e + P::nodes().sub[i]]]; dy[d] = m.y[m.tri[3 * e + P::nodes().sub[i]]]; continue; }
+        dx[d] = m.x[a] + (m.x[b] - m.x[a]) * lx + (m.x[c] - m.x[a]) * ly;
+        dy[d] = m.y[a] + (m.y[b] - m.y[a]) * lx + (m.y[c] - m.y[a]) * ly;
+      }
+    }
   return 0;
   ORA_CATCH(-1)
 }
-int ora2_dirichlet(void* mh, void* ph, int fields, int comp0, char* out) {
+int orak_space(int degree, void* mh, void* ph, int* eva, int* evb, int* tedge, double* dx, double* dy) {
+  return degree == 3 ? pk_space<p3>(mh, ph, eva, evb, tedge, dx, dy) : pk_space<p2>(mh, ph, eva, evb, tedge, dx, dy);
+}
+extern "C++" template <class P> int pk_dirichlet(void* mh, void* ph, int fields, int comp0, char* out) {
   ORA_TRY
-  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
+  typename P::Space2 sp = P::make_space2(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
   std::copy(sp.dirichlet.begin(), sp.dirichlet.end(), out);
   return 0;
   ORA_CATCH(-1)
 }
-long ora2_pattern(void* mh, void* ph, int fields, int comp0, int* rowptr, int* col) {
+int orak_dirichlet(int degree, void* mh, void* ph, int fields, int comp0, char* out) {
+  return degree == 3 ? pk_dirichlet<p3>(mh, ph, fields, comp0, out) : pk_dirichlet<p2>(mh, ph, fields, comp0, out);
+}
+extern "C++" template <class P> long pk_pattern(void* mh, void* ph, int fields, int comp0, int* rowptr, int* col) {
   ORA_TRY
-  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
-  CSR A = p2::make_pattern2(sp);
+  typename P::Space2 sp = P::make_space2(*(Mesh*)mh, ((Params*)ph)->s, fields, comp0);
+  CSR A = P::make_pattern2(sp);
   if (rowptr) std::copy(A.rowptr.begin(), A.rowptr.end(), rowptr);
   if (col) std::copy(A.col.begin(), A.col.end(), col);
   return (long)A.col.size();
   ORA_CATCH(-1)
 }
-int ora2_residual(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
+long orak_pattern(int degree, void* mh, void* ph, int fields, int comp0, int* rowptr, int* col) {
+  return degree == 3 ? pk_pattern<p3>(mh, ph, fields, comp0, rowptr, col) : pk_pattern<p2>(mh, ph, fields, comp0, rowptr, col);
+}
+extern "C++" template <class P> int pk_residual(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
                   int intorder, double* r, double* absr) {
   ORA_TRY
   const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
-  p2::Space2 sp = p2::make_space2(*m, *s, op_fields(op), comp0);
+  typename P::Space2 sp = P::make_space2(*m, *s, op_fields(op), comp0);
   OpCtx c = make_ctx2(m, s, op, aux0, aux1, valency, intorder);
-  p2::residual2(sp, c, u, r, absr);
+  P::residual2(sp, c, u, r, absr);
   return 0;
   ORA_CATCH(-1)
 }
-int ora2_jacobian(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
+int orak_residual(int degree, void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
+                  int intorder, double* r, double* absr) {
+  return degree == 3 ? pk_residual<p3>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, r, absr) : pk_residual<p2>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, r, absr);
+}
+extern "C++" template <class P> int pk_jacobian(void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
                   int intorder, int mode, double eps, double* val, double* absval) {
   ORA_TRY
   const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
-  p2::Space2 sp = p2::make_space2(*m, *s, op_fields(op), comp0);
+  typename P::Space2 sp = P::make_space2(*m, *s, op_fields(op), comp0);
   OpCtx c = make_ctx2(m, s, op, aux0, aux1, valency, intorder);
-  CSR A = p2::make_pattern2(sp);
+  CSR A = P::make_pattern2(sp);
   std::vector<double> ab;
-  p2::jacobian2(sp, c, u, A, mode, eps, absval ? &ab : nullptr);
+  P::jacobian2(sp, c, u, A, mode, eps, absval ? &ab : nullptr);
   std::copy(A.val.begin(), A.val.end(), val);
   if (absval) std::copy(ab.begin(), ab.end(), absval);
   return 0;
   ORA_CATCH(-1)
 }
-int ora2_interpolate(void* mh, void* ph, int comp, const double* pb, double* u) {
+int orak_jacobian(int degree, void* mh, void* ph, int op, int comp0, const double* u, const double* aux0, const double* aux1, double valency,
+                  int intorder, int mode, double eps, double* val, double* absval) {
+  return degree == 3 ? pk_jacobian<p3>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, mode, eps, val, absval) : pk_jacobian<p2>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, mode, eps, val, absval);
+}
+extern "C++" template <class P> int pk_interpolate(void* mh, void* ph, int comp, const double* pb, double* u) {
   ORA_TRY
-  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, comp);
-  p2::interpolate_bcext2(sp, comp, pb, u);
+  typename P::Space2 sp = P::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, comp);
+  P::interpolate_bcext2(sp, comp, pb, u);
   return 0;
   ORA_CATCH(-1)
 }
-int ora2_newton(void* mh, void* ph, int op, int comp0, double* u, const double* aux0, const double* aux1, double valency,
+int orak_interpolate(int degree, void* mh, void* ph, int comp, const double* pb, double* u) {
+  return degree == 3 ? pk_interpolate<p3>(mh, ph, comp, pb, u) : pk_interpolate<p2>(mh, ph, comp, pb, u);
+}
+extern "C++" template <class P> int pk_newton(void* mh, void* ph, int op, int comp0, double* u, const double* aux0, const double* aux1, double valency,
                 int intorder, const double* opts, double* result, double* hist, int* lin_hist, int cap) {
   ORA_TRY
   const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
-  p2::Space2 sp = p2::make_space2(*m, *s, op_fields(op), comp0);
+  typename P::Space2 sp = P::make_space2(*m, *s, op_fields(op), comp0);
   OpCtx c = make_ctx2(m, s, op, aux0, aux1, valency, intorder);
   NewtonOpts o;
   o.reduction = opts[0]; o.abs_limit = opts[1]; o.min_linear_reduction = opts[2]; o.reassemble_threshold = opts[3];
@@ -432,8 +462,8 @@ int ora2_newton(void* mh, void* ph, int op, int comp0, double* u, const double* 
   o.solver = (int)opts[9]; o.prec = (int)opts[10]; o.prec_steps = (int)opts[11]; o.lin_maxit = (int)opts[12];
   o.verbosity = (int)opts[13]; o.line_search = (int)opts[14];
   auto t0 = std::chrono::steady_clock::now();
-  NewtonResult R = newton_core(sp.N(), p2::make_pattern2(sp), [&](const double* uu, double* r) { p2::residual2(sp, c, uu, r); },
-                               [&](const double* uu, CSR& A) { p2::jacobian2(sp, c, uu, A, o.jac_mode, o.fd_eps); }, u, o);
+  NewtonResult R = newton_core(sp.N(), P::make_pattern2(sp), [&](const double* uu, double* r) { P::residual2(sp, c, uu, r); },
+                               [&](const double* uu, CSR& A) { P::jacobian2(sp, c, uu, A, o.jac_mode, o.fd_eps); }, u, o);
   double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   double v[11] = {(double)R.status, (double)R.converged, (double)R.iterations, R.first_defect, R.defect, R.reduction,
                   (double)R.total_linear_iterations, (double)R.total_ls_trials, (double)R.jacobian_assemblies,
@@ -444,24 +474,37 @@ int ora2_newton(void* mh, void* ph, int op, int comp0, double* u, const double* 
   return 0;
   ORA_CATCH(-1)
 }
-int ora2_ion_flux(void* mh, void* ph, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
+int orak_newton(int degree, void* mh, void* ph, int op, int comp0, double* u, const double* aux0, const double* aux1, double valency,
+                int intorder, const double* opts, double* result, double* hist, int* lin_hist, int cap) {
+  return degree == 3 ? pk_newton<p3>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, opts, result, hist, lin_hist, cap) : pk_newton<p2>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, opts, result, hist, lin_hist, cap);
+}
+extern "C++" template <class P> int pk_ion_flux(void* mh, void* ph, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
   ORA_TRY
-  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
-  p2::ion_flux2(sp, phi, cp, cm, ip, im);
+  typename P::Space2 sp = P::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
+  P::ion_flux2(sp, phi, cp, cm, ip, im);
   return 0;
   ORA_CATCH(-1)
 }
-int ora2_write_cell_data(void* mh, void* ph, const double* u, const char* filename) {
+int orak_ion_flux(int degree, void* mh, void* ph, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
+  return degree == 3 ? pk_ion_flux<p3>(mh, ph, phi, cp, cm, ip, im) : pk_ion_flux<p2>(mh, ph, phi, cp, cm, ip, im);
+}
+extern "C++" template <class P> int pk_write_cell_data(void* mh, void* ph, const double* u, const char* filename) {
   ORA_TRY
-  p2::Space2 sp = p2::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
-  p2::write_cell_data2(sp, u, filename);
+  typename P::Space2 sp = P::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);
+  P::write_cell_data2(sp, u, filename);
   return 0;
   ORA_CATCH(-1)
 }
-void ora2_basis(double x, double y, double* phi, double* grad) {
-  p2::basis(x, y, phi);
-  double g[6][2]; p2::basis_grad(x, y, g);
-  for (int i = 0; i < 6; i++) { grad[2 * i] = g[i][0]; grad[2 * i + 1] = g[i][1]; }
+int orak_write_cell_data(int degree, void* mh, void* ph, const double* u, const char* filename) {
+  return degree == 3 ? pk_write_cell_data<p3>(mh, ph, u, filename) : pk_write_cell_data<p2>(mh, ph, u, filename);
+}
+extern "C++" template <class P> void pk_basis(double x, double y, double* phi, double* grad) {
+  P::basis(x, y, phi);
+  double g[P::NL][2]; P::basis_grad(x, y, g);
+  for (int i = 0; i < P::NL; i++) { grad[2 * i] = g[i][0]; grad[2 * i + 1] = g[i][1]; }
+}
+void orak_basis(int degree, double x, double y, double* phi, double* grad) {
+  if (degree == 3) pk_basis<p3>(x, y, phi, grad); else pk_basis<p2>(x, y, phi, grad);
 }
 
 } // extern "C"

@@ -311,6 +311,14 @@ inline const std::vector<QL>& line_rule3() { // 2-pt Gauss-Legendre on [0,1] (or
   static const std::vector<QL> g = {{0.21132486540518711775, 0.5}, {0.78867513459481288225, 0.5}};
   return g;
 }
+// QuadratureRules<DF,1>::rule(cube, order): Gauss-Legendre on [0,1], n points exact to degree 2n-1 (what the operators get for
+// the faces with their `intorder`: 2 points for the drivers' default 3, 3 points for 5)
+inline const std::vector<QL>& line_rule(int order) {
+  static const std::vector<QL> g3 = {{0.11270166537925831148, 5.0 / 18.0}, {0.5, 8.0 / 18.0}, {0.88729833462074168852, 5.0 / 18.0}};
+  if (order <= 3) return line_rule3();
+  if (order <= 5) return g3;
+  throw std::runtime_error("line quadrature order not tabulated");
+}
 
 // ----------------------------------------------------------------------------
 // Local operators

@@ -14,16 +14,80 @@
 #include "pnp_oracle.hpp"
 
 namespace pnpo {
-namespace p2 {
+template <int DEG> struct Pk {
+  static_assert(DEG == 2 || DEG == 3, "Pk2DLocalFiniteElementMap degrees built here: 2, 3");
 
-constexpr int NL = 6;
-// local node -> reference coordinates, and what it sits on: vertex (sub = local vertex) or edge (sub = local edge)
-static const double NODE_X[NL] = {0.0, 0.5, 1.0, 0.0, 0.5, 0.0};
-static const double NODE_Y[NL] = {0.0, 0.0, 0.0, 0.5, 0.5, 1.0};
-static const int NODE_IS_EDGE[NL] = {0, 1, 0, 1, 1, 0};
-static const int NODE_SUB[NL] = {0, 0, 1, 1, 2, 2};
+static constexpr int NL = (DEG + 1) * (DEG + 2) / 2;
+// Lagrange nodes: lattice points (i, j)/DEG, i + j <= DEG, lexicographic (j outer, i inner).  What a node sits on: kind 0 =
+// vertex (sub = local vertex), 1 = edge (sub = local edge, idx = position counted from the edge's FIRST local vertex),
+// 2 = element interior (degree 3: the bubble at (1/3, 1/3)).
+struct NodeTab { double x[NL], y[NL]; int kind[NL], sub[NL], idx[NL]; };
+static const NodeTab& nodes() {
+  static const NodeTab T = [] {
+    NodeTab t; int n = 0;
+    for (int j = 0; j <= DEG; j++) for (int i = 0; i <= DEG - j; i++, n++) {
+      t.x[n] = (1.0 * i) / DEG; t.y[n] = (1.0 * j) / DEG; t.idx[n] = 0;
+      if (i == 0 && j == 0) { t.kind[n] = 0; t.sub[n] = 0; }
+      else if (i == DEG) { t.kind[n] = 0; t.sub[n] = 1; }
+      else if (j == DEG) { t.kind[n] = 0; t.sub[n] = 2; }
+      else if (j == 0) { t.kind[n] = 1; t.sub[n] = 0; t.idx[n] = i - 1; }      // edge0 = (v0, v1)
+      else if (i == 0) { t.kind[n] = 1; t.sub[n] = 1; t.idx[n] = j - 1; }      // edge1 = (v0, v2)
+      else if (i + j == DEG) { t.kind[n] = 1; t.sub[n] = 2; t.idx[n] = j - 1; } // edge2 = (v1, v2)
+      else { t.kind[n] = 2; t.sub[n] = 0; }
+    }
+    return t;
+  }();
+  return T;
+}
 
-inline void basis(double x, double y, double* phi) {
+// Pk2DLocalBasis<D,R,k>::evaluateFunction / evaluateJacobian for any k [UPSTREAM dune-localfunctions 2.2 pk2dlocalbasis.hh, from
+// memory]: pos[i] = i/k; node (i,j): prod_{a<i} (x-pos[a])/(pos[i]-pos[a]) * prod_{b<j} (y-pos[b])/(pos[j]-pos[b]) *
+// prod_{g=i+j+1..k} (pos[g]-x-y)/(pos[g]-pos[i]-pos[j]); the derivatives by the product rule, factor by factor
+static void basis_generic(double x, double y, double* phi) {
+  double pos[DEG + 1];
+  for (int i = 0; i <= DEG; i++) pos[i] = (1.0 * i) / DEG;
+  int n = 0;
+  for (int j = 0; j <= DEG; j++) for (int i = 0; i <= DEG - j; i++) {
+    double out = 1.0;
+    for (int a = 0; a < i; a++) out *= (x - pos[a]) / (pos[i] - pos[a]);
+    for (int b = 0; b < j; b++) out *= (y - pos[b]) / (pos[j] - pos[b]);
+    for (int g = i + j + 1; g <= DEG; g++) out *= (pos[g] - x - y) / (pos[g] - pos[i] - pos[j]);
+    phi[n++] = out;
+  }
+}
+static void basis_grad_generic(double x, double y, double (*gr)[2]) {
+  double pos[DEG + 1];
+  for (int i = 0; i <= DEG; i++) pos[i] = (1.0 * i) / DEG;
+  int n = 0;
+  for (int j = 0; j <= DEG; j++) for (int i = 0; i <= DEG - j; i++, n++) {
+    for (int dir = 0; dir < 2; dir++) {
+      // the direction's own factors are (dir == 0 ? the alpha product in x : the beta product in y); the other product is a factor
+      const int own = dir == 0 ? i : j, oth = dir == 0 ? j : i;
+      const double z = dir == 0 ? x : y, w = dir == 0 ? y : x;
+      double factor = 1.0, sum = 0.0;
+      for (int b = 0; b < oth; b++) factor *= (w - pos[b]) / (pos[oth] - pos[b]);
+      for (int a = 0; a < own; a++) {
+        double product = factor;
+        for (int al = 0; al < own; al++)
+          if (al == a) product *= 1.0 / (pos[own] - pos[al]);
+          else product *= (z - pos[al]) / (pos[own] - pos[al]);
+        for (int g = i + j + 1; g <= DEG; g++) product *= (pos[g] - x - y) / (pos[g] - pos[i] - pos[j]);
+        sum += product;
+      }
+      for (int c = i + j + 1; c <= DEG; c++) {
+        double product = factor;
+        for (int al = 0; al < own; al++) product *= (z - pos[al]) / (pos[own] - pos[al]);
+        for (int g = i + j + 1; g <= DEG; g++)
+          if (g == c) product *= -1.0 / (pos[g] - pos[i] - pos[j]);
+          else product *= (pos[g] - x - y) / (pos[g] - pos[i] - pos[j]);
+        sum += product;
+      }
+      gr[n][dir] = sum;
+    }
+  }
+}
+static void basis(double x, double y, double* phi) {
+  if (DEG != 2) { basis_generic(x, y, phi); return; }
   const double s = 2 * x + 2 * y;
   phi[0] = ((1 - s) / 1) * ((2 - s) / 2);
   phi[1] = (2 * x) * ((2 - s) / 1);
@@ -33,7 +97,8 @@ inline void basis(double x, double y, double* phi) {
   phi[5] = (2 * y) * ((2 * y - 1) / 2);
 }
 // reference gradients (d/dx, d/dy) of the same products
-inline void basis_grad(double x, double y, double (*g)[2]) {
+static void basis_grad(double x, double y, double (*g)[2]) {
+  if (DEG != 2) { basis_grad_generic(x, y, g); return; }
   const double s = 2 * x + 2 * y;
   // phi0 = (1-s)(2-s)/2 : d/ds = (2s-3)/2, ds/dx = ds/dy = 2
   g[0][0] = (2 * s - 3); g[0][1] = (2 * s - 3);
@@ -53,25 +118,35 @@ struct Space2 {
   const Mesh* m = nullptr;
   const Sysparams* s = nullptr;
   int fields = 1, comp0 = 0;
-  int nE = 0, nd = 0;          // edges; scalar dofs = nE + nv
+  int nE = 0, nd = 0;          // edges; scalar dofs = [nT bubbles (degree 3)] + (DEG-1) per edge + nv
+  int eoff = 0, voff = 0;      // first edge dof, first vertex dof (codim by codim -- elements, edges, vertices)
   std::vector<int> tedge;      // 3*nT: global edge of local edge f = (FACE_V[f][0], FACE_V[f][1])
   std::vector<int> eva, evb;   // edge -> end vertices (min, max)
   std::vector<char> dirichlet; // per dof, lexicographic [field][scalar dof]
   int N() const { return fields * nd; }
   int sdof(int e, int i) const { // scalar dof of local node i of element e
-    return NODE_IS_EDGE[i] ? tedge[3 * e + NODE_SUB[i]] : nE + m->tri[3 * e + NODE_SUB[i]];
+    const NodeTab& T = nodes();
+    if (T.kind[i] == 2) return e;
+    if (T.kind[i] == 0) return voff + m->tri[3 * e + T.sub[i]];
+    // edge dofs are counted from the end vertex with the SMALLER global index (Pk2DLocalFiniteElementMap picks the local
+    // coefficients variant by comparing the global vertex indices, so that neighbours agree on the order) [UPSTREAM]
+    int idx = T.idx[i];
+    const int f = T.sub[i];
+    if (DEG == 3 && m->tri[3 * e + FACE_V[f][0]] > m->tri[3 * e + FACE_V[f][1]]) idx = 1 - idx;
+    return eoff + (DEG - 1) * tedge[3 * e + f] + idx;
   }
   int gdof(int field, int sd) const { return field * nd + sd; }
 };
 
-inline Space2 make_space2(const Mesh& m, const Sysparams& s, int fields, int comp0 = 0) {
+static Space2 make_space2(const Mesh& m, const Sysparams& s, int fields, int comp0 = 0) {
   Space2 sp; sp.m = &m; sp.s = &s; sp.fields = fields; sp.comp0 = comp0;
   auto key = [](int a, int b) { return ((uint64_t)std::min(a, b) << 32) | (uint64_t)std::max(a, b); };
   std::vector<uint64_t> keys; keys.reserve(3 * (size_t)m.nT);
   for (int e = 0; e < m.nT; e++) for (int f = 0; f < 3; f++) keys.push_back(key(m.tri[3 * e + FACE_V[f][0]], m.tri[3 * e + FACE_V[f][1]]));
   std::vector<uint64_t> uk(keys);
   std::sort(uk.begin(), uk.end()); uk.erase(std::unique(uk.begin(), uk.end()), uk.end());
-  sp.nE = (int)uk.size(); sp.nd = sp.nE + m.nv;
+  sp.nE = (int)uk.size();
+  sp.eoff = DEG == 3 ? m.nT : 0; sp.voff = sp.eoff + (DEG - 1) * sp.nE; sp.nd = sp.voff + m.nv;
   sp.tedge.resize(3 * (size_t)m.nT);
   for (size_t i = 0; i < keys.size(); i++) sp.tedge[i] = (int)(std::lower_bound(uk.begin(), uk.end(), keys[i]) - uk.begin());
   sp.eva.resize(sp.nE); sp.evb.resize(sp.nE);
@@ -85,15 +160,15 @@ inline Space2 make_space2(const Mesh& m, const Sysparams& s, int fields, int com
       for (int k = 0; k < fields; k++) {
         const int comp = fields == 3 ? k : comp0;
         if (sf.btype(comp) != 0) continue;
-        for (int l = 0; l < 2; l++) sp.dirichlet[sp.gdof(k, sp.nE + m.tri[3 * e + FACE_V[f][l]])] = 1;
-        sp.dirichlet[sp.gdof(k, sp.tedge[3 * e + f])] = 1;
+        for (int l = 0; l < 2; l++) sp.dirichlet[sp.gdof(k, sp.voff + m.tri[3 * e + FACE_V[f][l]])] = 1;
+        for (int l = 0; l < DEG - 1; l++) sp.dirichlet[sp.gdof(k, sp.eoff + (DEG - 1) * sp.tedge[3 * e + f] + l)] = 1;
       }
     }
   return sp;
 }
 
 // FullVolumePattern: all local pairs of every element; constrained links dropped, constrained rows keep the diagonal
-inline CSR make_pattern2(const Space2& sp) {
+static CSR make_pattern2(const Space2& sp) {
   const Mesh& m = *sp.m;
   const int nd = sp.nd, nf = sp.fields, N = sp.N();
   std::vector<int> cnt(nd + 1, 0);
@@ -132,7 +207,7 @@ inline CSR make_pattern2(const Space2& sp) {
 
 // basis values and transformed gradients at a reference point
 struct BasisAt { double phi[NL], g[NL][2]; };
-inline BasisAt basis_at(const ElemGeo& G, double x, double y) {
+static BasisAt basis_at(const ElemGeo& G, double x, double y) {
   BasisAt B;
   basis(x, y, B.phi);
   double gh[NL][2];
@@ -149,7 +224,7 @@ inline BasisAt basis_at(const ElemGeo& G, double x, double y) {
 
 // alpha_volume with 6 local dofs per field (the operator bodies of pnp_oracle.hpp, lfsu.size() = 6); the coefficient fields
 // of the Poisson / diffusion operators are P2 functions too: caux[a][i] = their local coefficients
-inline void alpha_volume2(const OpCtx& c, int e, const double* xl, const double (*caux)[NL], double* rl) {
+static void alpha_volume2(const OpCtx& c, int e, const double* xl, const double (*caux)[NL], double* rl) {
   const Mesh& m = *c.m; const Sysparams& s = *c.s;
   const ElemGeo G = elem_geo(m, e);
   const double PI = s.PI;
@@ -207,7 +282,7 @@ inline void alpha_volume2(const OpCtx& c, int e, const double* xl, const double 
   }
 }
 
-inline void alpha_boundary2(const OpCtx& c, int e, int f, double* rl) {
+static void alpha_boundary2(const OpCtx& c, int e, int f, double* rl) {
   if (c.op == OP_DIFFUSION || c.op == OP_MASS) return;
   const Mesh& m = *c.m; const Sysparams& s = *c.s;
   const int* tv = &m.tri[3 * e];
@@ -217,7 +292,7 @@ inline void alpha_boundary2(const OpCtx& c, int e, int f, double* rl) {
   const double ax = m.x[va], ay = m.y[va], bx = m.x[vb], by = m.y[vb];
   const double len = std::sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
   const int nf = op_fields(c.op);
-  for (const QL& q : line_rule3()) {
+  for (const QL& q : line_rule(c.order())) {
     double l0, l1;
     if (f == 0) { l0 = q.t; l1 = 0.0; } else if (f == 1) { l0 = 0.0; l1 = q.t; } else { l0 = 1.0 - q.t; l1 = q.t; }
     double phi[NL];
@@ -234,7 +309,7 @@ inline void alpha_boundary2(const OpCtx& c, int e, int f, double* rl) {
   }
 }
 
-inline void jacobian_volume_fd2(const OpCtx& c, int e, const double* xl, const double (*caux)[NL], double* Ae, double eps) {
+static void jacobian_volume_fd2(const OpCtx& c, int e, const double* xl, const double (*caux)[NL], double* Ae, double eps) {
   const int n = NL * op_fields(c.op);
   std::vector<double> u(xl, xl + n), down(n, 0.0), up(n);
   alpha_volume2(c, e, u.data(), caux, down.data());
@@ -249,7 +324,7 @@ inline void jacobian_volume_fd2(const OpCtx& c, int e, const double* xl, const d
 }
 
 // exact derivative of alpha_volume2 (not in the reference; validates the FD path and gives clean Newton comparisons)
-inline void jacobian_volume_exact2(const OpCtx& c, int e, const double* xl, const double (*caux)[NL], double* Ae) {
+static void jacobian_volume_exact2(const OpCtx& c, int e, const double* xl, const double (*caux)[NL], double* Ae) {
   const Mesh& m = *c.m; const Sysparams& s = *c.s;
   const ElemGeo G = elem_geo(m, e);
   const int n = NL * op_fields(c.op);
@@ -296,7 +371,7 @@ inline void jacobian_volume_exact2(const OpCtx& c, int e, const double* xl, cons
 }
 
 // local coefficients of the operator's coefficient fields (c.cp / c.cm / c.uphi: P2 vectors of length nd)
-inline void gather_aux(const Space2& sp, const OpCtx& c, int e, double (*caux)[NL]) {
+static void gather_aux(const Space2& sp, const OpCtx& c, int e, double (*caux)[NL]) {
   for (int i = 0; i < NL; i++) {
     const int d = sp.sdof(e, i);
     caux[0][i] = c.op == OP_POISSON ? c.cp[d] : (c.op == OP_DIFFUSION ? c.uphi[d] : 0.0);
@@ -304,7 +379,7 @@ inline void gather_aux(const Space2& sp, const OpCtx& c, int e, double (*caux)[N
   }
 }
 
-inline void residual2(const Space2& sp, const OpCtx& c, const double* u, double* r, double* absr = nullptr) {
+static void residual2(const Space2& sp, const OpCtx& c, const double* u, double* r, double* absr = nullptr) {
   const Mesh& m = *sp.m;
   const int nf = sp.fields, n = NL * nf, N = sp.N();
   std::fill(r, r + N, 0.0);
@@ -326,7 +401,7 @@ inline void residual2(const Space2& sp, const OpCtx& c, const double* u, double*
   for (int d = 0; d < N; d++) if (sp.dirichlet[d]) r[d] = 0.0;
 }
 
-inline void jacobian2(const Space2& sp, const OpCtx& c, const double* u, CSR& A, int mode = 0, double eps = 1e-11,
+static void jacobian2(const Space2& sp, const OpCtx& c, const double* u, CSR& A, int mode = 0, double eps = 1e-11,
                       std::vector<double>* absA = nullptr) {
   const Mesh& m = *sp.m;
   const int nf = sp.fields, n = NL * nf, N = sp.N();
@@ -357,12 +432,12 @@ inline void jacobian2(const Space2& sp, const OpCtx& c, const double* u, CSR& A,
 
 // BCExtension<component>::evaluate at local node i of element e (dirichlet_bc.hh:54-123): the position is the node's;
 // the PB field is a P2 function, whose value at a Lagrange node is its dof
-inline double bcext_eval2(const Space2& sp, int comp, const double* pb, int e, int i) {
+static double bcext_eval2(const Space2& sp, int comp, const double* pb, int e, int i) {
   const Mesh& m = *sp.m; const Sysparams& s = *sp.s;
   const int a = m.tri[3 * e], b = m.tri[3 * e + 1], cv = m.tri[3 * e + 2];
   // geometry().global(local): v0 + J * local
-  const double px = m.x[a] + (m.x[b] - m.x[a]) * NODE_X[i] + (m.x[cv] - m.x[a]) * NODE_Y[i];
-  const double py = m.y[a] + (m.y[b] - m.y[a]) * NODE_X[i] + (m.y[cv] - m.y[a]) * NODE_Y[i];
+  const double px = m.x[a] + (m.x[b] - m.x[a]) * nodes().x[i] + (m.x[cv] - m.x[a]) * nodes().y[i];
+  const double py = m.y[a] + (m.y[b] - m.y[a]) * nodes().x[i] + (m.y[cv] - m.y[a]) * nodes().y[i];
   int pg = -1;
   auto sticky = [&](int g) { return s.surfaces.at(g).minusDiffusionBtype == 0; };
   for (int fi = 0; fi < 3; fi++) {
@@ -385,14 +460,14 @@ inline double bcext_eval2(const Space2& sp, int comp, const double* pb, int e, i
   if (comp == 1) return s.c0 * std::exp(-yv);
   return s.c0 * std::exp(+yv);
 }
-inline void interpolate_bcext2(const Space2& sp, int comp, const double* pb, double* u) {
+static void interpolate_bcext2(const Space2& sp, int comp, const double* pb, double* u) {
   for (int e = 0; e < sp.m->nT; e++)
     for (int i = 0; i < NL; i++) u[sp.sdof(e, i)] = bcext_eval2(sp, comp, pb, e, i);
 }
 
 // calcIonFlux (ionFlux.hh:8-96) with quadratic functions: DiscreteGridFunction / DiscreteGridFunctionGradient evaluated at
 // the local coordinates of the face centre -- the basis sum over the element's 6 dofs per field
-inline void ion_flux2(const Space2& sp, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
+static void ion_flux2(const Space2& sp, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
   const Mesh& m = *sp.m; const Sysparams& s = *sp.s;
   static const double VX[3] = {0.0, 1.0, 0.0}, VY[3] = {0.0, 0.0, 1.0}; // reference vertices
   for (int i = 0; i < s.n_surfaces; i++) { ip[i] = 0; im[i] = 0; }
@@ -429,7 +504,7 @@ inline void ion_flux2(const Space2& sp, const double* phi, const double* cp, con
 }
 
 // DataWriter::writeData (datawriter.hh:45-94) with a quadratic function: value and gradient at the element centre
-inline void write_cell_data2(const Space2& sp, const double* u, const std::string& filename) {
+static void write_cell_data2(const Space2& sp, const double* u, const std::string& filename) {
   const Mesh& m = *sp.m;
   std::ofstream out(filename.c_str(), std::ios::out);
   out.precision(5);
@@ -449,5 +524,7 @@ inline void write_cell_data2(const Space2& sp, const double* u, const std::strin
   }
 }
 
-} // namespace p2
+}; // struct Pk
+using p2 = Pk<2>;
+using p3 = Pk<3>;
 } // namespace pnpo

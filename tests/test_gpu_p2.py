@@ -1,5 +1,7 @@
-"""GPU parity tests of the quadratic-element path (pnp_space_set_degree(ctx, 2): the reference's -DPDEGREE=2 programs,
-src/Makefile.am:57-110) against the oracle's P2 restatement (oracle/pnp_oracle_p2.hpp) on the same inputs, through the C ABI.
+"""GPU parity tests of the quadratic- and cubic-element path (pnp_space_set_degree(ctx, 2 | 3): the reference's -DPDEGREE=2 / 3
+programs, src/Makefile.am:54-110) against the oracle's Pk restatement (oracle/pnp_oracle_p2.hpp) on the same inputs, through the
+C ABI.  Cubic elements run with the reference drivers' quadrature order (0: assembly parity only -- that rule makes the cubic
+matrices indefinite, tests/test_oracle_p2.py) and with order 5 (solves).
 
 Bars as for linear elements: dof numbering, constraints and pattern bit-exact; residual and Jacobian entries within 1e-12 of
 the entry's scale (sum of |element contributions|); equal Newton iteration counts, converged fields within 1e-8 relative L2."""
@@ -26,7 +28,7 @@ def _capi():
     return capi
 
 
-def make_ctx(name, levels=0):
+def make_ctx(name, levels=0, degree=2):
     capi = _capi()
     a = util.load_mesh_arrays(name)
     c = capi.Context(0)
@@ -34,11 +36,11 @@ def make_ctx(name, levels=0):
     c.params_read(util.cfg_path(name))
     if levels:
         c.mesh_refine(levels)
-    c.space_set_degree(2)
+    c.space_set_degree(degree)
     c.mesh_finalize(True)
     m = ora.Mesh.from_arrays(**a).refine(levels)
     p = ora.Params.read(util.cfg_path(name))
-    return c, m, p, ora.P2(m, p)
+    return c, m, p, ora.P2(m, p, degree)
 
 
 def rel_err(got, want, scale):
@@ -53,9 +55,11 @@ def _state(P, op, seed=0):
     return rng.uniform(-1, 1, F * P.nd), rng.uniform(0, 1, P.nd), rng.uniform(0, 1, P.nd)
 
 
-def _operator(c, op, a0, a1, valency, comp0=0):
+def _operator(c, op, a0, a1, valency, comp0=0, intorder=0):
     capi = _capi()
     h = c.operator(op, comp0)
+    if intorder:
+        c.operator_set_intorder(h, intorder)
     if op == capi.OP_POISSON:
         c.operator_set_coefficient(h, 0, c.vec(1, a0)); c.operator_set_coefficient(h, 1, c.vec(1, a1))
     if op == capi.OP_DIFFUSION:
@@ -63,12 +67,13 @@ def _operator(c, op, a0, a1, valency, comp0=0):
     return h
 
 
+@pytest.mark.parametrize("degree", [2, 3])
 @pytest.mark.parametrize("name,levels", [(n, 0) for n in util.MESHES] + [("pore_small", 1)])
-def test_space_pattern_and_constraints_bit_exact(name, levels):
+def test_space_pattern_and_constraints_bit_exact(name, levels, degree):
     capi = _capi()
-    c, m, p, P = make_ctx(name, levels)
+    c, m, p, P = make_ctx(name, levels, degree)
     s = c.space_sizes()
-    assert s == dict(degree=2, n_edges=P.nE, ndof=P.nd)
+    assert s == dict(degree=degree, n_edges=P.nE, ndof=P.nd) and c.space_offsets() == (P.eoff, P.voff)
     va, vb = c.space_edges()
     assert np.array_equal(va, P.eva) and np.array_equal(vb, P.evb)
     for op, F, comp0 in ((capi.OP_PB, 1, 0), (capi.OP_DIFFUSION, 1, 1), (capi.OP_MASS, 1, 2), (capi.OP_PNP, 3, 0)):
@@ -79,34 +84,43 @@ def test_space_pattern_and_constraints_bit_exact(name, levels):
         assert np.array_equal(rp, rp_o) and np.array_equal(col, col_o)
 
 
+DEG_ORDER = [(2, 0), (2, 5), (3, 0), (3, 5)]   # (degree, intorder): 0 = the reference drivers' order
+
+
+@pytest.mark.parametrize("degree,intorder", DEG_ORDER)
 @pytest.mark.parametrize("op", OPS)
 @pytest.mark.parametrize("name,levels", [(n, 0) for n in util.MESHES] + [("pore_small", 1)])
-def test_residual_parity(name, levels, op):
-    c, m, p, P = make_ctx(name, levels)
+def test_residual_parity(name, levels, op, degree, intorder):
+    if (degree, intorder) != (2, 0) and name not in ("pore", "cylinder", "one_wall"):
+        pytest.skip("the full mesh list runs for the reference configuration")
+    c, m, p, P = make_ctx(name, levels, degree)
     F = ora.nfields(op)
     u, a0, a1 = _state(P, op)
-    h = _operator(c, op, a0, a1, -1.0)
+    h = _operator(c, op, a0, a1, -1.0, intorder=intorder)
     vu, vr = c.vec(F, u), c.vec(F)
     c.residual(h, vu, vr)
     r = c.download(vr, F)
-    r_o, ab = P.residual(op, u, a0, a1, valency=-1.0, want_abs=True)
+    r_o, ab = P.residual(op, u, a0, a1, valency=-1.0, want_abs=True, intorder=intorder or -1)
     assert rel_err(r, r_o, ab) <= TOL
     d = P.dirichlet(F, 0)
     assert not r[d].any() and not r_o[d].any()
     assert np.array_equal(c.download(vu, F), u)   # the upload / download pair is the identity in this numbering
 
 
+@pytest.mark.parametrize("degree,intorder", DEG_ORDER)
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("op", OPS)
 @pytest.mark.parametrize("name,levels", [("one_wall", 0), ("cylinder", 0), ("pore", 0), ("pore_small", 1)])
-def test_jacobian_parity(name, levels, op, mode):
-    c, m, p, P = make_ctx(name, levels)
+def test_jacobian_parity(name, levels, op, mode, degree, intorder):
+    if (degree, intorder) != (2, 0) and name not in ("one_wall", "pore"):
+        pytest.skip("the full mesh list runs for the reference configuration")
+    c, m, p, P = make_ctx(name, levels, degree)
     F = ora.nfields(op)
     u, a0, a1 = _state(P, op, seed=3)
-    h = _operator(c, op, a0, a1, -1.0)
+    h = _operator(c, op, a0, a1, -1.0, intorder=intorder)
     vu, A = c.vec(F, u), c.matrix(h)
     c.jacobian(h, vu, A, mode, 1e-11)
-    rp, col, val_o, ab = P.jacobian(op, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11, want_abs=True)
+    rp, col, val_o, ab = P.jacobian(op, u, a0, a1, valency=-1.0, mode=mode, eps=1e-11, want_abs=True, intorder=intorder or -1)
     val = c.matrix_values(h, A, len(col))
     assert rel_err(val, val_o, ab) <= (TOL if mode == 0 else TOL_EXACT)
     # same element order, same operation order, no FMA contraction: most entries reproduce the oracle bit for bit
@@ -157,18 +171,19 @@ def test_linear_solvers(kind, prec):
     assert np.linalg.norm(zsol - spla.spsolve(J.tocsc(), b)) <= 1e-6 * np.linalg.norm(zsol)
 
 
+@pytest.mark.parametrize("degree", [2, 3])
 @pytest.mark.parametrize("prec,steps", [(2, 1), (2, 3), (3, 1)])
 @pytest.mark.parametrize("name,levels,op", [("pore_small", 1, ora.OP_PB), ("pore", 0, ora.OP_PNP), ("cylinder", 0, ora.OP_DIFFUSION)])
-def test_ssor_ilu0_application_equals_sequential_sweep(name, levels, op, prec, steps):
+def test_ssor_ilu0_application_equals_sequential_sweep(name, levels, op, prec, steps, degree):
     """SeqSSOR(n) / SeqILU0 in the row order of the P2 matrix: the level-scheduled device sweep does every row's operations in
     the sequential sweep's order (ascending columns, no FMA) -- bit-identical to the CPU sweep."""
     capi = _capi()
-    c, m, p, P = make_ctx(name, levels)
+    c, m, p, P = make_ctx(name, levels, degree)
     F = ora.nfields(op)
     u, a0, a1 = _state(P, op, seed=9)
     if op == ora.OP_PNP:
         u[P.nd:] = 0.06 * (1 + 0.1 * u[P.nd:])
-    h = _operator(c, op, a0, a1, 1.0)
+    h = _operator(c, op, a0, a1, 1.0, intorder=5 if degree == 3 else 0)
     vu, A = c.vec(F, 0.3 * u if op != ora.OP_PNP else u), c.matrix(h)
     c.jacobian(h, vu, A, 1, 1e-11)
     rp, col = c.pattern(h, F)
@@ -204,12 +219,16 @@ def test_krylov_with_ssor_ilu0_matches_oracle_iteration_counts(kind, prec):
     assert np.linalg.norm(c.download(vz, 1) - z_o) <= 1e-7 * np.linalg.norm(z_o)
 
 
+@pytest.mark.parametrize("degree", [2, 3])
 @pytest.mark.parametrize("name", ["one_wall", "cylinder", "pore_small"])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_newton_pb_matches_oracle(name, mode):
+def test_newton_pb_matches_oracle(name, mode, degree):
     capi = _capi()
-    c, m, p, P = make_ctx(name)
+    c, m, p, P = make_ctx(name, 0, degree)
     h = c.operator(capi.OP_PB, 0)
+    intorder = 5 if degree == 3 else 0
+    if intorder:
+        c.operator_set_intorder(h, intorder)
     s = c.solver(capi.SOLVER_BCGS, capi.PREC_JACOBI, 20000)
     vu = c.vec(1)
     tight = mode == 1   # (FD noise moves iteration counts at tight tolerances: the tight comparison uses the exact derivative)
@@ -219,7 +238,7 @@ def test_newton_pb_matches_oracle(name, mode):
     opts[12] = 20000
     if tight:
         opts[0], opts[2] = 1e-11, 1e-9
-    u_o, res_o = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
+    u_o, res_o = P.newton(ora.OP_PB, np.zeros(P.nd), opts, intorder=intorder or -1)
     assert res.converged and res_o["converged"]
     assert res.iterations == res_o["iterations"]
     u = c.download(vu, 1)
@@ -228,10 +247,11 @@ def test_newton_pb_matches_oracle(name, mode):
     assert abs(res.first_defect - res_o["first_defect"]) <= 1e-12 * res_o["first_defect"]
 
 
+@pytest.mark.parametrize("degree", [2, 3])
 @pytest.mark.parametrize("comp", [0, 1, 2])
 @pytest.mark.parametrize("name", ["pore", "sphere"])
-def test_interpolate_bcext(name, comp):
-    c, m, p, P = make_ctx(name)
+def test_interpolate_bcext(name, comp, degree):
+    c, m, p, P = make_ctx(name, 0, degree)
     pb = np.sin(0.1 * P.x) * np.cos(0.07 * P.y)
     vpb, vo = c.vec(1, pb), c.vec(1)
     c.interpolate_bcext(comp, vpb, vo)
@@ -241,14 +261,15 @@ def test_interpolate_bcext(name, comp):
     assert np.array_equal(got[d], want[d])
 
 
-@pytest.mark.parametrize("prec", [3, 2])
-def test_newton_pnp_from_pb_matches_oracle(prec):
+@pytest.mark.parametrize("degree,prec", [(2, 3), (2, 2), (3, 3)])
+def test_newton_pnp_from_pb_matches_oracle(prec, degree):
     """The stationary program with quadratic elements (stationary_pnp_from_pb.hh:105-185, :344-360): PB Newton solve, the
     Boltzmann start from interpolate(BCExtension), then the coupled 3-field Newton solve -- exact derivative, the reference's
     default backend BiCGSTAB + SSOR(1) (~500 BiCGSTAB iterations per Newton step on this system) and BiCGSTAB + ILU0 (~50)."""
     capi = _capi()
-    c, m, p, P = make_ctx("pore_small")
-    hpb = c.operator(capi.OP_PB, 0)
+    c, m, p, P = make_ctx("pore_small", 0, degree)
+    io = 5 if degree == 3 else 0
+    hpb = _operator(c, capi.OP_PB, None, None, 1.0, intorder=io)
     s = c.solver(capi.SOLVER_BCGS, prec, 50000, 1)
     vpb = c.vec(1)
     st, r0 = c.newton(hpb, vpb, s, c.newton_opts(jac_mode=1, reduction=1e-11, min_linear_reduction=1e-9))
@@ -257,16 +278,16 @@ def test_newton_pnp_from_pb_matches_oracle(prec):
         c.interpolate_bcext(k, vpb, v[k])
     vu = c.vec(3)
     c.pack3(vu, *v)
-    hp = c.operator(capi.OP_PNP, 0)
+    hp = _operator(c, capi.OP_PNP, None, None, 1.0, intorder=io)
     st, res = c.newton(hp, vu, s, c.newton_opts(jac_mode=1, reduction=1e-10, min_linear_reduction=1e-9))
     # oracle
     opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=prec, jac_mode=1); opts[12] = 50000
     opts[0], opts[2] = 1e-11, 1e-9
-    pb_o, _ = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
+    pb_o, _ = P.newton(ora.OP_PB, np.zeros(P.nd), opts, intorder=io or -1)
     u0 = np.concatenate([P.interpolate(k, pb_o) for k in range(3)])
     assert np.linalg.norm(np.concatenate([c.download(x, 1) for x in v]) - u0) <= 1e-8 * np.linalg.norm(u0)
     opts[0] = 1e-10
-    u_o, res_o = P.newton(ora.OP_PNP, u0, opts)
+    u_o, res_o = P.newton(ora.OP_PNP, u0, opts, intorder=io or -1)
     assert res.converged and res_o["converged"] and res.iterations == res_o["iterations"]
     u = c.download(vu, 3)
     assert np.linalg.norm(u - u_o) <= 1e-8 * np.linalg.norm(u_o)
@@ -343,14 +364,20 @@ def test_errors_are_reported():
         c.residual(h, c.vec(3), vu)                 # field count mismatch
     c2 = capi.Context(0)
     with pytest.raises(capi.PnpError):
-        c2.space_set_degree(3)
+        c2.space_set_degree(4)
+    with pytest.raises(capi.PnpError):
+        c.operator_set_intorder(h, 4)               # tabulated: the reference drivers' order and 5
+    c3, m3, p3 = __import__("test_gpu_parity").make_ctx("one_wall")
+    with pytest.raises(capi.PnpError):
+        c3.operator_set_intorder(c3.operator(capi.OP_PB, 0), 5)   # linear elements keep the drivers' order
 
 
 # ---- the time loop's diagnostics with quadratic functions ----
-def test_outputs_match_oracle(tmp_path):
+@pytest.mark.parametrize("degree", [2, 3])
+def test_outputs_match_oracle(tmp_path, degree):
     """calcIonFlux, DataWriter::writeData and the VTK vertex data for quadratic functions: fields and gradients are basis sums
     over the element's 6 dofs at the face / element centre; VTK vertex data are the vertex dofs."""
-    c, m, p, P = make_ctx("pore", 0)
+    c, m, p, P = make_ctx("pore", 0, degree)
     phi = np.cos(0.3 * P.x) * np.sin(0.2 * P.y); cp = 0.06 * np.exp(-phi); cm = 0.06 * np.exp(phi)
     vphi, vcp, vcm = c.vec(1, phi), c.vec(1, cp), c.vec(1, cm)
     ip, im = c.ion_flux(vphi, vcp, vcm)
@@ -359,7 +386,7 @@ def test_outputs_match_oracle(tmp_path):
     scale = np.abs(ip_o).max() + np.abs(im_o).max() + np.abs(ip_a).max() + np.abs(im_a).max()
     assert np.all(np.abs(ip - ip_o) <= 1e-11 * scale) and np.all(np.abs(im - im_o) <= 1e-11 * scale) and np.any(ip_o != 0)
     # a quadratic field differs from its vertex interpolant at the face centres: the P1 formula would not pass
-    ip1, _ = ora.ion_flux(m, p, phi[P.nE:], cp[P.nE:], cm[P.nE:])
+    ip1, _ = ora.ion_flux(m, p, phi[P.voff:], cp[P.voff:], cm[P.voff:])
     assert np.max(np.abs(ip1 - ip_o)) > 1e-6 * scale
     c.write_cell_data(vphi, str(tmp_path / "gpu.dat"))
     P.write_cell_data(phi, str(tmp_path / "ora.dat"))
@@ -371,11 +398,12 @@ def test_outputs_match_oracle(tmp_path):
     for ascii_ in (True, False):
         g, o = str(tmp_path / ("gpu%d" % ascii_)), str(tmp_path / ("ora%d" % ascii_))
         c.write_vtk(g, [vphi, vcp], ["phi", "cp"], ascii=ascii_)
-        ora.write_vtk(m, o, [phi[P.nE:], cp[P.nE:]], ["phi", "cp"], ascii=ascii_)
+        ora.write_vtk(m, o, [phi[P.voff:], cp[P.voff:]], ["phi", "cp"], ascii=ascii_)
         assert open(g + ".vtu", "rb").read() == open(o + ".vtu", "rb").read()
 
 
-def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path):
+@pytest.mark.parametrize("degree", [2, 3])
+def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path, degree):
     """The reference binary built with -DPDEGREE=2 (src/Makefile.am:57-60: dune_pnp_BCGS_SSORk_2): PnpSolverMain::run on
     one_wall, three time steps with file output; the printed norms equal the same loop driven through the C ABI, the files
     are what the oracle's writers make of the fields."""
@@ -385,15 +413,16 @@ def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path):
     a = util.load_mesh_arrays("one_wall")
     util.write_gmsh(str(tmp_path / "one_wall.msh"), a)
     (tmp_path / "one_wall.cfg").write_text(open(util.cfg_path("one_wall")).read())
-    exe = _build_example("instationary_pnp_md", tmp_path, ("-DPDEGREE=2",))
+    io = 5 if degree == 3 else 0
+    exe = _build_example("instationary_pnp_md", tmp_path, ("-DPDEGREE=%d" % degree,) + (("-DPNP_INTORDER=5",) if io else ()))
     out = subprocess.run([exe, "one_wall.cfg", "1", "3", "files"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = [l.split() for l in out.stdout.splitlines() if l.startswith("step")]
     assert len(lines) == 3
-    c, m, p, P = make_ctx("one_wall", 1)
+    c, m, p, P = make_ctx("one_wall", 1, degree)
     ls = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, int(p.sys[5]), 1)
     vpb = c.vec(1)
-    c.newton(c.operator(capi.OP_PB, 0), vpb, ls, c.newton_opts(jac_mode=0))
+    c.newton(_operator(c, capi.OP_PB, None, None, 1.0, intorder=io), vpb, ls, c.newton_opts(jac_mode=0))
     uphi, ucp, ucm, cpB, cmB, new = (c.vec(1) for _ in range(6))
     c.interpolate_bcext(0, vpb, uphi)
     c.interpolate_bcext(1, vpb, ucp); c.interpolate_bcext(1, vpb, cpB)
@@ -404,6 +433,9 @@ def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path):
     c.operator_set_coefficient(h0p, 0, uphi); c.operator_set_valency(h0p, 1.0)
     c.operator_set_coefficient(h0m, 0, uphi); c.operator_set_valency(h0m, -1.0)
     h1 = c.operator(capi.OP_MASS, 1)
+    if io:
+        for h in (hphi, h0p, h0m, h1):
+            c.operator_set_intorder(h, io)
     for i in range(3):
         c.onestep(h0p, h1, ls, p.sys[11], ucp, cpB, new, 1e-5); c.vec_copy(ucp, new)
         c.onestep(h0m, h1, ls, p.sys[11], ucm, cmB, new, 1e-5); c.vec_copy(ucm, new)

@@ -157,3 +157,111 @@ def test_outputs_reduce_to_the_linear_ones_for_linear_functions(tmp_path):
     Q = np.loadtxt(tmp_path / "q.dat")
     assert np.allclose(Q[:, 2], Q[:, 0] ** 2 - 0.5 * Q[:, 0] * Q[:, 1], rtol=1e-4, atol=1e-4 * np.abs(u).max())
     assert np.allclose(Q[:, 3], 2 * Q[:, 0] - 0.5 * Q[:, 1], rtol=1e-4, atol=1e-4 * np.abs(P.x).max())
+
+
+# ---- cubic elements (-DPDEGREE=3, src/Makefile.am:62,74,86,98,110) ----
+def case3(name, levels=0):
+    m = ora.Mesh.from_arrays(**util.load_mesh_arrays(name)).refine(levels)
+    p = ora.Params.read(util.cfg_path(name))
+    return m, p, ora.P3(m, p)
+
+
+def test_cubic_basis_is_the_lagrange_basis_on_the_lattice():
+    nodes = [(i / 3, j / 3) for j in range(4) for i in range(4 - j)]      # lexicographic, j outer (Pk2DLocalBasis)
+    for k, (x, y) in enumerate(nodes):
+        phi, _ = ora.p2_basis(x, y, 3)
+        assert np.allclose(phi, np.eye(10)[k], atol=1e-14)
+    rng = np.random.RandomState(0)
+    q = lambda a, b: 1 + 2 * a - b + 3 * a * a - a * b + 0.5 * b * b + a ** 3 - 2 * a * a * b + b ** 3  # noqa: E731
+    for x, y in rng.uniform(0, 0.5, (20, 2)):
+        phi, g = ora.p2_basis(x, y, 3)
+        assert abs(phi.sum() - 1) < 1e-13 and np.allclose(g.sum(0), 0, atol=1e-12)
+        h = 1e-6
+        px, _ = ora.p2_basis(x + h, y, 3); mx, _ = ora.p2_basis(x - h, y, 3)
+        py, _ = ora.p2_basis(x, y + h, 3); my, _ = ora.p2_basis(x, y - h, 3)
+        assert np.allclose((px - mx) / (2 * h), g[:, 0], atol=1e-7) and np.allclose((py - my) / (2 * h), g[:, 1], atol=1e-7)
+        assert abs(sum(q(*n) * phi[i] for i, n in enumerate(nodes)) - q(x, y)) < 1e-12   # cubics are reproduced
+    # the generic product formula reproduces the hard-coded quadratic basis (same functions, possibly other rounding)
+    # -- checked through the degree-2 Lagrange property in test_basis_is_the_quadratic_lagrange_basis
+
+
+@pytest.mark.parametrize("name", util.MESHES)
+def test_cubic_dof_numbering_pattern_and_constraints(name):
+    m, p, P = case3(name)
+    assert (P.eoff, P.voff, P.nd) == (m.nT, m.nT + 2 * P.nE, m.nT + 2 * P.nE + m.nv)   # bubbles, 2 per edge, vertices
+    for F, comp0 in ((1, 0), (1, 1), (3, 0)):
+        d = P.dirichlet(F, comp0)
+        d1 = ora.dirichlet(m, p, F, comp0)
+        keys = (P.eva.astype(np.int64) << 32) | P.evb
+        bkey = (np.minimum(m.ba, m.bb).astype(np.int64) << 32) | np.maximum(m.ba, m.bb)
+        pos = np.searchsorted(keys, bkey)
+        for k in range(F):
+            blk = d[k * P.nd:(k + 1) * P.nd]
+            assert not blk[:m.nT].any()                                    # bubbles are never constrained
+            assert np.array_equal(blk[P.voff:], d1[k * m.nv:(k + 1) * m.nv])
+            comp = k if F == 3 else comp0
+            want = np.zeros(P.nE, dtype=bool)
+            want[pos] = p.surf[m.bphys, 3 * comp] == 0
+            assert np.array_equal(blk[P.eoff:P.voff], np.repeat(want, 2))  # both dofs of a Dirichlet edge
+        rp, col = P.pattern(F, comp0)
+        assert rp[-1] == len(col) and np.all(np.diff(rp) >= 1) and np.all(np.diff(rp)[d] == 1)
+        free_bubble = 0                                                    # a bubble row couples to its element's free dofs only
+        assert np.diff(rp)[free_bubble] <= 10 * F
+    # edge dofs are counted from the end vertex with the smaller index: the dof coordinates say so
+    e = np.arange(P.nE)
+    xa, xb = m.x[P.eva], m.x[P.evb]
+    assert np.allclose(P.x[P.eoff + 2 * e], xa + (xb - xa) / 3, atol=1e-12 * np.abs(m.x).max())
+    assert np.allclose(P.x[P.eoff + 2 * e + 1], xa + 2 * (xb - xa) / 3, atol=1e-12 * np.abs(m.x).max())
+
+
+def test_cubic_patch_test_and_the_reference_quadrature():
+    """u = x^3 - 3 x y^2 is harmonic and lies in the P3 space: with a rule that integrates the degree-4 integrand exactly
+    (order 5) the Laplace residual vanishes at every dof away from the boundary -- which also pins the edge-dof orientation,
+    since a wrong order on one side of an edge would break continuity.  With the order the reference hard-codes
+    (poisson_operator.hh: 3) the P3 stiffness integrals are under-integrated: the restatement keeps that."""
+    m, p, P = case3("cylinder")
+    u = P.x ** 3 - 3 * P.x * P.y ** 2
+    z = np.zeros(P.nd)
+    bv = np.zeros(m.nv, bool); bv[m.ba] = True; bv[m.bb] = True
+    interior = np.ones(P.nd, bool)
+    interior[P.voff:][bv] = False
+    interior[P.eoff:P.voff][np.repeat(bv[P.eva] | bv[P.evb], 2)] = False
+    r5, ab = P.residual(ora.OP_POISSON, u, z, z, want_abs=True, intorder=5)
+    assert np.abs(r5[interior]).max() <= 1e-12 * ab.max() and np.abs(r5[~interior]).max() > 1e-3 * ab.max()
+    r3 = P.residual(ora.OP_POISSON, u, z, z)
+    assert 1e-5 * ab.max() < np.abs(r3[interior]).max() < 1e-2 * ab.max()
+
+
+@pytest.mark.parametrize("op", [ora.OP_PB, ora.OP_POISSON, ora.OP_DIFFUSION, ora.OP_MASS, ora.OP_PNP])
+def test_cubic_fd_jacobian_agrees_with_exact_derivative(op):
+    m, p, P = case3("pore_small")
+    rng = np.random.RandomState(1)
+    F = ora.nfields(op)
+    u = 0.3 * rng.uniform(-1, 1, F * P.nd)
+    if op == ora.OP_PNP:
+        u[P.nd:] = 0.06 * (1 + 0.1 * rng.uniform(-1, 1, 2 * P.nd))
+    a0, a1 = rng.uniform(0, 1, P.nd), rng.uniform(0, 1, P.nd)
+    rp, col, v0 = P.jacobian(op, u, a0, a1, valency=-1.0, mode=0, eps=1e-7)
+    _, _, v1 = P.jacobian(op, u, a0, a1, valency=-1.0, mode=1)
+    assert np.max(np.abs(v0 - v1)) <= 1e-6 * np.max(np.abs(v1))
+    z = 1e-6 * rng.uniform(-1, 1, F * P.nd)
+    d = P.dirichlet(F, 0)
+    z[d] = 0
+    import scipy.sparse as sp
+    J = sp.csr_matrix((v1, col, rp))
+    lhs = P.residual(op, u + z, a0, a1, valency=-1.0) - P.residual(op, u, a0, a1, valency=-1.0)
+    assert np.linalg.norm((lhs - J @ z)[~d]) <= 1e-4 * np.linalg.norm((J @ z)[~d])
+
+
+def test_cubic_newton_and_interpolation():
+    m, p, P = case3("one_wall")
+    opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, jac_mode=1); opts[12] = 20000
+    opts[0], opts[2] = 1e-11, 1e-9
+    u3, r3 = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
+    u1, r1 = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
+    assert r3["converged"] and np.linalg.norm(u3[P.voff:] - u1) <= 0.05 * np.linalg.norm(u1)   # same problem, finer space
+    for comp in range(3):
+        g = P.interpolate(comp, u3)
+        d = P.dirichlet(1, comp)
+        assert np.array_equal(g[P.voff:], ora.interpolate(m, p, comp, u3[P.voff:]))
+        assert not d[:m.nT].any() and np.all(np.isfinite(g))
