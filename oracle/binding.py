@@ -29,8 +29,9 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "liboracle.so")
-        if not os.path.exists(so):
-            build()
+        srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "pnp_oracle.hpp", "pnp_oracle_p2.hpp")]
+        if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) + 1.0 for f in srcs if os.path.exists(f)):
+            build()  # (a stale library would silently test yesterday's restatement)
         L = C.CDLL(so)
         L.ora_last_error.restype = C.c_char_p
         for f in ("ora_mesh_create", "ora_mesh_read_gmsh", "ora_mesh_refine", "ora_params_read", "ora_params_create"):

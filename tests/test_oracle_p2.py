@@ -254,10 +254,18 @@ def test_cubic_fd_jacobian_agrees_with_exact_derivative(op):
 
 
 def test_cubic_newton_and_interpolation():
+    """With the quadrature order the reference's drivers use whatever PDEGREE is (3: four points, negative centre weight) the
+    cubic PB matrix is INDEFINITE and the Krylov solve fails -- the -DPDEGREE=3 programs of the reference inherit that; with
+    order 5 the same operators give a positive definite matrix and the Newton solve converges to the P1 / P2 answer."""
+    import scipy.sparse as sp
     m, p, P = case3("one_wall")
+    rp, col, v = P.jacobian(ora.OP_PB, np.zeros(P.nd), mode=1)
+    w = np.linalg.eigvalsh(sp.csr_matrix((v, col, rp)).toarray()); assert w[0] < -1.0
+    rp, col, v = P.jacobian(ora.OP_PB, np.zeros(P.nd), mode=1, intorder=5)
+    w = np.linalg.eigvalsh(sp.csr_matrix((v, col, rp)).toarray()); assert w[0] > 0.0
     opts = ora.newton_opts(p, solver=ora.SOLVER_BCGS, prec=ora.PREC_SSOR, jac_mode=1); opts[12] = 20000
     opts[0], opts[2] = 1e-11, 1e-9
-    u3, r3 = P.newton(ora.OP_PB, np.zeros(P.nd), opts)
+    u3, r3 = P.newton(ora.OP_PB, np.zeros(P.nd), opts, intorder=5)
     u1, r1 = ora.newton(m, p, ora.OP_PB, np.zeros(m.nv), opts)
     assert r3["converged"] and np.linalg.norm(u3[P.voff:] - u1) <= 0.05 * np.linalg.norm(u1)   # same problem, finer space
     for comp in range(3):
