@@ -412,7 +412,11 @@ def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path, degree):
     capi = _capi()
     a = util.load_mesh_arrays("one_wall")
     util.write_gmsh(str(tmp_path / "one_wall.msh"), a)
-    (tmp_path / "one_wall.cfg").write_text(open(util.cfg_path("one_wall")).read())
+    cfg = open(util.cfg_path("one_wall")).read()
+    if degree == 3:   # the cfg's 50 Krylov iterations are not enough for the cubic system on the refined mesh
+        cfg = cfg.replace("linearSolverIterations=50", "linearSolverIterations=2000")
+        assert "linearSolverIterations=2000" in cfg
+    (tmp_path / "one_wall.cfg").write_text(cfg)
     io = 5 if degree == 3 else 0
     exe = _build_example("instationary_pnp_md", tmp_path, ("-DPDEGREE=%d" % degree,) + (("-DPNP_INTORDER=5",) if io else ()))
     out = subprocess.run([exe, "one_wall.cfg", "1", "3", "files"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
@@ -420,7 +424,7 @@ def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path, degree):
     lines = [l.split() for l in out.stdout.splitlines() if l.startswith("step")]
     assert len(lines) == 3
     c, m, p, P = make_ctx("one_wall", 1, degree)
-    ls = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, int(p.sys[5]), 1)
+    ls = c.solver(capi.SOLVER_BCGS, capi.PREC_SSOR, 2000 if degree == 3 else int(p.sys[5]), 1)
     vpb = c.vec(1)
     c.newton(_operator(c, capi.OP_PB, None, None, 1.0, intorder=io), vpb, ls, c.newton_opts(jac_mode=0))
     uphi, ucp, ucm, cpB, cmB, new = (c.vec(1) for _ in range(6))
