@@ -25,7 +25,7 @@ def lib():
     global _LIB
     if _LIB is None:
         csrc = os.path.join(_HERE, "..", "dune_pnp_b200", "csrc")
-        deps = [_SRC] + [os.path.join(csrc, f) for f in ("pnp_elem.cuh", "pnp_star.cuh", "pnp_setup_algos.cuh", "pnp_sweep.cuh")]
+        deps = [_SRC] + [os.path.join(csrc, f) for f in ("pnp_elem.cuh", "pnp_star.cuh", "pnp_setup_algos.cuh", "pnp_sweep.cuh", "pnp_elem_p2.cuh")]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
                                    _SRC, "-o", _SO])
@@ -184,3 +184,23 @@ class Star:
         d = self.to_internal(d_lex, F); x = np.zeros_like(d)
         lib().hh_ilu0_apply(self.h, F, _d(lu), _d(d), _d(x))
         return self.to_external(x, F)
+
+
+def pk_element(degree, op, intorder, xy, phys, xl, caux, fflag, fflux, fdir, comp0=0, mode=0, eps=1e-11):
+    """The product's quadratic / cubic element functions on one triangle: (element vector, element matrix)."""
+    nl = (degree + 1) * (degree + 2) // 2
+    n = nl * (3 if op == 4 else 1)
+    r = np.zeros(n); A = np.zeros(n * n)
+    xy = np.ascontiguousarray(xy, dtype=np.float64); phys = np.ascontiguousarray(phys, dtype=np.float64)
+    xl = np.ascontiguousarray(xl, dtype=np.float64); caux = np.ascontiguousarray(caux, dtype=np.float64)
+    fflag = np.ascontiguousarray(fflag, dtype=np.int32); fdir = np.ascontiguousarray(fdir, dtype=np.int32)
+    fflux = np.ascontiguousarray(fflux, dtype=np.float64)
+    lib().hh_pk_element(degree, op, intorder, _d(xy), _d(phys), _d(xl), _d(caux), _i(fflag), _d(fflux), _i(fdir), comp0, mode,
+                        C.c_double(eps), _d(r), _d(A))
+    return r, A.reshape(n, n)
+
+
+def pk_node(degree, n):
+    key = np.zeros(3, dtype=np.int32); xy = np.zeros(2)
+    lib().hh_pk_node(degree, n, _i(key), _d(xy))
+    return tuple(int(k) for k in key), (xy[0], xy[1])

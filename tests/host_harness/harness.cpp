@@ -10,6 +10,7 @@
 
 #include "../../dune_pnp_b200/csrc/pnp_star.cuh"
 #include "../../dune_pnp_b200/csrc/pnp_sweep.cuh"
+#include "../../dune_pnp_b200/csrc/pnp_elem_p2.cuh"
 
 using namespace pnp;
 
@@ -256,3 +257,61 @@ void hh_ilu0_apply(void* h, int F, double* lu, const double* d, double* x) {
 
 // the device's pnp_sinh compiled for the host (-ffp-contract=off): must equal the oracle's sinh_shared bit for bit
 extern "C" void hh_sinh(int n, const double* x, double* y) { for (int i = 0; i < n; i++) y[i] = pnp::pnp_sinh(x[i]); }
+
+// ---- quadratic / cubic elements: the product's element functions (pnp_elem_p2.cuh) on ONE triangle --------------------------
+// xy[6] = vertex coordinates; xl = local coefficients (field-major, NL per field); caux = 2 x NL coefficient-field values;
+// face f (DUNE order) is a boundary face when fflag[f] != 0 with fluxes fflux[3*f + k] and Dirichlet bits fdir[f];
+// out_r (NL*F) = alpha_volume + alpha_boundary in intersection order 0, 2, 1; out_A (n*n) = the element matrix (mode 0: FD, 1: exact).
+namespace {
+template <int DEG, int OP, int NQ>
+void pk_element_t(const double* xy, const PhysParams& P, const double* xl_in, const double* caux_in, const int* fflag, const double* fflux,
+                  const int* fdir, int comp0, int line_pts, int mode, double eps, double* out_r, double* out_A) {
+  using E = PkElem<DEG>;
+  constexpr int F = OpTraits<OP>::F, NL = E::NL, n = NL * F;
+  const typename E::Geo2 G = E::make_geo2(xy[0], xy[1], xy[2], xy[3], xy[4], xy[5]);
+  double xl[n], caux[2][NL], rl[n];
+  for (int i = 0; i < n; i++) { xl[i] = xl_in[i]; rl[i] = 0.0; }
+  for (int a = 0; a < 2; a++) for (int i = 0; i < NL; i++) caux[a][i] = caux_in[a * NL + i];
+  E::template alpha_volume<OP, NQ>(G, P, xl, caux, rl);
+  if (OP == OP_PB || OP == OP_POISSON || OP == OP_PNP) {
+    const int order[3] = {0, 2, 1};
+    for (int fi = 0; fi < 3; fi++) {
+      const int f = order[fi];
+      if (!fflag[f]) continue;
+      const int la = f == 2 ? 1 : 0, lb = f == 0 ? 1 : 2;
+      double j[3]; bool skip[3];
+      for (int k = 0; k < F; k++) { const int comp = F == 3 ? k : comp0; j[k] = fflux[3 * f + comp]; skip[k] = (fdir[f] >> comp) & 1; }
+      E::alpha_boundary(f, xy[2 * la], xy[2 * la + 1], xy[2 * lb], xy[2 * lb + 1], F, j, skip, P, line_pts, rl);
+    }
+  }
+  for (int i = 0; i < n; i++) out_r[i] = rl[i];
+  for (int i = 0; i < n * n; i++) out_A[i] = 0.0;
+  if (mode == 0) E::template jacobian_fd<OP, NQ>(G, P, xl, caux, eps, out_A);
+  else E::template jacobian_exact<OP, NQ>(G, P, xl, caux, out_A);
+}
+template <int DEG, int OP, class... A> void pk_nq(int intorder, A... a) {
+  if (intorder == 5) pk_element_t<DEG, OP, 7>(a...); else pk_element_t<DEG, OP, OpTraits<OP>::NQ>(a...);
+}
+template <int DEG, class... A> void pk_op(int op, int intorder, A... a) {
+  switch (op) {
+    case OP_PB: pk_nq<DEG, OP_PB>(intorder, a...); break;
+    case OP_POISSON: pk_nq<DEG, OP_POISSON>(intorder, a...); break;
+    case OP_DIFFUSION: pk_nq<DEG, OP_DIFFUSION>(intorder, a...); break;
+    case OP_MASS: pk_nq<DEG, OP_MASS>(intorder, a...); break;
+    default: pk_nq<DEG, OP_PNP>(intorder, a...); break;
+  }
+}
+} // namespace
+extern "C" void hh_pk_element(int degree, int op, int intorder, const double* xy, const double* phys, const double* xl, const double* caux,
+                              const int* fflag, const double* fflux, const int* fdir, int comp0, int mode, double eps, double* out_r,
+                              double* out_A) {
+  const PhysParams P = mkphys(phys);
+  const int line_pts = intorder == 5 ? 3 : 2;
+  if (degree == 2) pk_op<2>(op, intorder, xy, P, xl, caux, fflag, fflux, fdir, comp0, line_pts, mode, eps, out_r, out_A);
+  else pk_op<3>(op, intorder, xy, P, xl, caux, fflag, fflux, fdir, comp0, line_pts, mode, eps, out_r, out_A);
+}
+// local node -> (kind, sub, idx, x, y) of the product's node table
+extern "C" void hh_pk_node(int degree, int n, int* key, double* xy) {
+  if (degree == 2) { PkElem<2>::node_key(n, key[0], key[1], key[2]); xy[0] = PkElem<2>::node_x(n); xy[1] = PkElem<2>::node_y(n); }
+  else { PkElem<3>::node_key(n, key[0], key[1], key[2]); xy[0] = PkElem<3>::node_x(n); xy[1] = PkElem<3>::node_y(n); }
+}
