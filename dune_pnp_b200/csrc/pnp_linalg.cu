@@ -156,6 +156,7 @@ void finish_reduce(Ctx& c, int nblocks, int nr, double* out) {
 // y = A x with optional fused dots; returns them in dots[0..ndot)
 void spmv_dots(Ctx& c, const Matrix& A, double* x, double* y, int ndot, const double* w1, double* dots) {
   ensure_red(c);
+  PNP_REQUIRE(c.degree == 1 || A.csr_rp, PNP_E_ARG, "matrix not assembled (or detached by a parameter change): assemble it first");
   if (A.csr_rp) { // quadratic elements: CSR rows, the dots as separate reductions
     csr_spmv(c, A, x, y);
     if (ndot >= 1) dots[0] = vec_dot(c, y, w1, A.csr_n);
@@ -206,6 +207,7 @@ void ilu0_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y);
 
 namespace {
 void prec_setup(Ctx& c, Solver& S, const Matrix& A) {
+  PNP_REQUIRE(c.degree == 1 || A.csr_rp, PNP_E_ARG, "matrix not assembled (or detached by a parameter change): assemble it first");
   if (A.csr_rp) {
     PNP_REQUIRE(S.prec != PNP_PREC_AMG, PNP_E_ARG, "quadratic elements: the preconditioners are none (Richardson), Jacobi, SSOR and ILU0");
     if (S.prec == PNP_PREC_JACOBI) csr_diag_inverse(c, A, S.dinv.p);

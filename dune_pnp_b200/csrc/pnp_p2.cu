@@ -318,7 +318,12 @@ void p2_constraints(Ctx& c) {
   }
   S.dir.upload(S.h_dir.data(), S.nd, c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
-  S.patterns.clear(); // (matrices created before a parameter change hold stale pattern pointers: like the P1 path, re-create them)
+  // the patterns depend on the constraints: drop them, and detach every matrix that points into one (it is re-initialised
+  // by the next assembly / import; using it before that is an error, not a read of freed memory)
+  S.patterns.clear();
+  auto detach = [](Matrix& A) { A.csr_rp = nullptr; A.csr_col = nullptr; A.csr_pattern = nullptr; A.csr_nnz = 0; A.csr_n = 0; A.vals.release(); };
+  for (auto& m : c.mats) if (m) detach(*m);
+  detach(c.ws_A); detach(c.ws_B);
 }
 
 static P2Space& space(Ctx& c) {

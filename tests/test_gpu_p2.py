@@ -362,6 +362,16 @@ def test_errors_are_reported():
         c.carry_set([vu])                           # refinement carry-over is built for linear elements
     with pytest.raises(capi.PnpError):
         c.residual(h, c.vec(3), vu)                 # field count mismatch
+    # a parameter change rebuilds the constraints and with them the patterns: matrices are detached, not left dangling
+    A = c.matrix(h)
+    c.jacobian(h, vu, A, 1, 1e-11)
+    vx, vy = c.vec(1), c.vec(1)
+    c.spmv(A, vx, vy)
+    c.params_read(util.cfg_path("one_wall"))
+    with pytest.raises(capi.PnpError):
+        c.spmv(A, vx, vy)
+    c.jacobian(h, vu, A, 1, 1e-11)
+    c.spmv(A, vx, vy)
     c2 = capi.Context(0)
     with pytest.raises(capi.PnpError):
         c2.space_set_degree(4)
