@@ -23,8 +23,13 @@
 
 #include "pnp_common.cuh"
 #include "pnp_spmv_tma.cuh"
+#include "pnp_sweep.cuh"
 
 namespace pnp {
+
+// pnp_precond.cu: level schedule of a row-order sweep on a star-layout matrix, one Gauss-Seidel sweep along / against it
+std::shared_ptr<SweepPlan> sweep_plan_build(Ctx&, const SweepView&, int F);
+void sweep_gs(Ctx&, const SweepPlan&, const SweepView&, const double* vals, long stride, const double* d, double* x, int dir);
 
 namespace {
 
@@ -56,6 +61,7 @@ struct Level {
   // gathered from the finest level, state u injected) instead of the Galerkin product
   bool redisc = false;
   DBuf<XY> xy_own; DBuf<unsigned char> dmask_own;
+  std::shared_ptr<SweepPlan> gs_plan; // Gauss-Seidel smoother: level schedule of this level's rows (built on first use)
 };
 
 } // namespace
@@ -70,7 +76,7 @@ struct Amg {
   int coarse_sweeps = 40;
   int gamma = 1;          // 1: V-cycle, 2: W-cycle ...
   int wlevels = 99;       // ... on the first `wlevels` levels only (V below): bounds the visits of the small levels
-  int smoother = 0;       // 0: damped Jacobi, 1: Chebyshev on [lmax/cheb_ratio, lmax] of D^-1 A
+  int smoother = 0;       // 0: damped Jacobi, 1: Chebyshev on [lmax/cheb_ratio, lmax] of D^-1 A, 2: symmetric Gauss-Seidel (SSOR, w = 1)
   double cheb_ratio = 8.0;
   int comp0 = 0;
   int pre_steps = -1, post_steps = -1; // smoothing steps before / after the coarse correction (-1: the solver's prec_steps)
@@ -942,6 +948,21 @@ void smooth(Ctx& c, Amg& A, Level& l, int steps, bool zero) {
     for (; s < steps; s++) { level_op<2>(c, A, l, l.x.p, l.b.p, l.x2.p); std::swap(l.x.p, l.x2.p); }
     return;
   }
+  if (A.smoother == 2) {
+    // SeqSSOR(w = 1) as ISTL's AMG applies it (ISTLBackend_NOVLP_CG_AMG_SSOR, instationary_pnp_from_pb_md.hh:208-211): a step is a
+    // forward and a backward Gauss-Seidel sweep over the level's rows, in place; the finest level sweeps in the reference's
+    // row order (the order of the SSOR preconditioner), the coarser ones in their own.  Level-scheduled like pnp_precond.cu.
+    const bool finest = &l == A.L[0].get();
+    const SweepView V{l.rp, l.col, finest ? c.int2ext.p : nullptr, l.nv};
+    if (!l.gs_plan) l.gs_plan = sweep_plan_build(c, V, A.F);
+    if (zero) PNP_CUDA(cudaMemsetAsync(l.x.p, 0, n * sizeof(double), c.stream));
+    for (int s = 0; s < steps; s++) {
+      sweep_gs(c, *l.gs_plan, V, l.vals, l.nslots, l.b.p, l.x.p, +1);
+      sweep_gs(c, *l.gs_plan, V, l.vals, l.nslots, l.b.p, l.x.p, -1);
+    }
+    c.acct(finest ? Ctx::ACC_SPMV_FINE : Ctx::ACC_SPMV_COARSE, 2.0 * steps * ((8.0 * A.NP + 4.0) * (double)l.nslots + 24.0 * n));
+    return;
+  }
   // Chebyshev polynomial smoother for D^-1 A on [lmax/ratio, 1.1*lmax]; l.r holds the direction d
   const double lmx = 1.1 * l.lmax, lmn = l.lmax / A.cheb_ratio;
   const double theta = 0.5 * (lmx + lmn), delta = 0.5 * (lmx - lmn), sigma = theta / delta;
@@ -1132,6 +1153,8 @@ void amg_setup(Ctx& c, Solver& S, const Matrix& M) {
   const auto t_num0 = std::chrono::steady_clock::now();
   A.omega = S.opt("amg_omega", 0.7); A.gamma = (int)S.opt("amg_gamma", 1); A.wlevels = (int)S.opt("amg_wlevels", 99);
   A.coarse_sweeps = (int)S.opt("amg_coarse_sweeps", 40); A.smoother = (int)S.opt("amg_smoother", 0);
+  PNP_REQUIRE(A.smoother >= 0 && A.smoother <= 2, PNP_E_ARG, "amg_smoother: 0 damped Jacobi, 1 Chebyshev, 2 symmetric Gauss-Seidel");
+  PNP_REQUIRE(A.smoother != 2 || !A.distributed, PNP_E_ARG, "the Gauss-Seidel smoother sweeps the rows of one GPU: use Jacobi / Chebyshev on a partitioned mesh");
   A.cheb_ratio = S.opt("amg_cheb_ratio", 8.0);
   A.pre_steps = (int)S.opt("amg_pre_steps", -1); A.post_steps = (int)S.opt("amg_post_steps", -1);
   numeric(c, A, comp0);
@@ -1156,7 +1179,7 @@ void amg_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y) {
     // result lands in y: no vector copies around the cycle (2 x 2.3 GB of traffic per application at k = 7).
     double *keep_b = l0.b.p, *keep_x = l0.x.p, *keep_x2 = l0.x2.p;
     const int pre = A.pre_steps >= 0 ? A.pre_steps : nu, post = A.post_steps >= 0 ? A.post_steps : nu;
-    const int swaps = (pre > 0 ? pre - 1 : 0) + post;
+    const int swaps = A.smoother == 2 ? 0 : (pre > 0 ? pre - 1 : 0) + post; // (Gauss-Seidel sweeps work in place)
     struct Restore { // the level's buffers own their memory: put the pointers back whatever happens in the cycle
       Level& l; double *b, *x, *x2;
       ~Restore() { l.b.p = b; l.x.p = x; l.x2.p = x2; }

@@ -138,6 +138,7 @@ struct MgLevelRef {
 struct Amg; // pnp_amg.cu
 struct P2Space; // pnp_p2.cu
 struct SweepPrec; // pnp_precond.cu: level schedules of the SSOR / ILU0 sweeps, ILU0 factor
+struct SweepPlan; // pnp_precond.cu: one level schedule
 
 struct Solver {
   int kind = PNP_SOLVER_BCGS, prec = PNP_PREC_NONE, maxit = 5000, prec_steps = 1, verbosity = 0;

@@ -97,16 +97,15 @@ __global__ void k_planes_7_to_9(const double* __restrict__ vals, long stride, do
 
 SweepView view_of(const Ctx& c) { return SweepView{c.rp.p, c.adj.p, c.int2ext.p, (int)c.n_own}; }
 
-std::shared_ptr<SweepPlan> build_plan(Ctx& c, int F, bool full) {
+std::shared_ptr<SweepPlan> build_plan_view(Ctx& c, const SweepView& S, int F, bool full) {
   auto P = std::make_shared<SweepPlan>();
-  P->F = F; P->full = full; P->n = (long)F * c.n_own;
+  P->F = F; P->full = full; P->n = (long)F * S.n_own;
   const int n = (int)P->n;
   PNP_REQUIRE(P->n < (1l << 31), PNP_E_MESH, "too many dofs for a level-scheduled sweep");
   DBuf<int> lev(n), changed(1);
   lev.zero(c.stream);
   int* h_changed = nullptr;
   PNP_CUDA(cudaMallocHost(&h_changed, sizeof(int)));
-  const SweepView S = view_of(c);
   const int g = grid_for(n, 256);
   for (int pass = 0;; pass++) {
     changed.zero(c.stream);
@@ -153,6 +152,8 @@ std::shared_ptr<SweepPlan> build_plan(Ctx& c, int F, bool full) {
   }
   return P;
 }
+
+std::shared_ptr<SweepPlan> build_plan(Ctx& c, int F, bool full) { return build_plan_view(c, view_of(c), F, full); }
 
 template <int F, int FN> void run_sweep(Ctx& c, const SweepPlan& P, const SweepArgs& a, int dir) {
   const int ns = (int)P.seg.size();
@@ -215,6 +216,15 @@ void ilu0_apply(Ctx& c, Solver& S, const Matrix&, const double* d, double* y) {
   SweepArgs a{view_of(c), nullptr, W.lu.p, c.nslots, d, y};
   run_sweep_f<FN_ILU_FWD>(c, *W.plan_ilu, a, +1);
   run_sweep_f<FN_ILU_BWD>(c, *W.plan_ilu, a, -1);
+}
+
+// ---- the same sweeps on any star-layout matrix: the multigrid's Gauss-Seidel smoother (pnp_amg.cu) ----
+std::shared_ptr<SweepPlan> sweep_plan_build(Ctx& c, const SweepView& S, int F) { return build_plan_view(c, S, F, false); }
+int sweep_plan_levels(const SweepPlan& P) { return P.nlev; }
+// one Gauss-Seidel sweep x_i += (d_i - sum_k A_ik x_k) / A_ii over the rows in sweep order (dir > 0) or against it (dir < 0)
+void sweep_gs(Ctx& c, const SweepPlan& P, const SweepView& S, const double* vals, long stride, const double* d, double* x, int dir) {
+  SweepArgs a{S, vals, nullptr, stride, d, x};
+  run_sweep_f<FN_GS>(c, P, a, dir);
 }
 
 // number of levels of the sweep schedule (diagnostics / tests); 0 if the solver has none

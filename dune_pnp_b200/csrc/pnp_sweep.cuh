@@ -16,7 +16,7 @@ namespace pnp {
 struct SweepView {
   const int* rp;        // n_own + 1
   const unsigned* adj;  // nslots (column vertex in the low 27 bits)
-  const int* int2ext;   // nv: reference index of an internal vertex
+  const int* int2ext;   // nv: reference index of an internal vertex (null: the row order itself is the sweep order)
   int n_own;            // rows; columns >= n_own are ghosts and are skipped (the preconditioner acts on the local block)
 };
 
@@ -30,11 +30,11 @@ PNP_HD int pnp_plane7(int f, int g) {
 template <int F>
 PNP_HD int sweep_level_relax(const SweepView& S, const int* lev, int v, int f, bool full) {
   int best = -1;
-  const int ev = S.int2ext[v];
+  const int ev = S.int2ext ? S.int2ext[v] : v;
   for (int s = S.rp[v]; s < S.rp[v + 1]; s++) {
     const int w = (int)(S.adj[s] & STAR_VMASK);
     if (w >= S.n_own) continue;
-    const bool before = S.int2ext[w] < ev;
+    const bool before = (S.int2ext ? S.int2ext[w] : w) < ev;
 #pragma unroll
     for (int g = 0; g < F; g++) {
       if (g > f || (g == f && !before)) continue;
@@ -60,7 +60,7 @@ PNP_HD void gs_update(const SweepView& S, const double* vals, long stride, const
     else sum -= vals[(2 * f + 1) * stride + s] * x[3 * w] + vals[(2 * f + 2) * stride + s] * x[3 * w + f];
   }
   const double diag = vals[(NP == 1 ? 0 : (f == 0 ? 0 : 2 * f + 2)) * stride + s0];
-  x[(long)F * v + f] += sum / diag;
+  if (diag != 0.0) x[(long)F * v + f] += sum / diag; // (a multigrid level may hold an empty row: an all-constrained aggregate)
 }
 
 // slot of column vertex x in row v, or -1
