@@ -175,7 +175,14 @@ struct ISTLBackend_NOVLP_BCGS_SSORk : LinearSolverBackend {
   ISTLBackend_NOVLP_BCGS_SSORk(Grid& g, unsigned maxiter = 5000, int steps = 5, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_BCGS, PNP_PREC_SSOR, maxiter, steps, verbose) {}
 };
 struct ISTLBackend_NOVLP_CG_AMG_SSOR : LinearSolverBackend {
-  ISTLBackend_NOVLP_CG_AMG_SSOR(Grid& g, int smoothsteps = 2, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_CG, PNP_PREC_AMG, maxiter, smoothsteps, verbose) {}
+  // the backend's smoother is SeqSSOR: on one GPU the multigrid smooths with it (amg_smoother = 2); a partitioned grid keeps the
+  // damped point-block Jacobi smoother (a Gauss-Seidel sweep is sequential over one GPU's rows).  setSmoother(0) for the fast one.
+  ISTLBackend_NOVLP_CG_AMG_SSOR(Grid& g, int smoothsteps = 2, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_CG, PNP_PREC_AMG, maxiter, smoothsteps, verbose), grid_(g) {
+    if (g.ownedSize() == g.size()) setSmoother(2);
+  }
+  void setSmoother(int kind) { check(grid_.ctx(), pnp_solver_set_option(grid_.ctx(), handle(), "amg_smoother", (double)kind)); }
+ private:
+  Grid& grid_;
 };
 struct ISTLBackend_NOVLP_BCGS_AMG : LinearSolverBackend {  // new: what bench.py runs for the non-symmetric PNP system
   ISTLBackend_NOVLP_BCGS_AMG(Grid& g, int smoothsteps = 2, unsigned maxiter = 5000, int verbose = 1) : LinearSolverBackend(g, PNP_SOLVER_BCGS, PNP_PREC_AMG, maxiter, smoothsteps, verbose) {}
