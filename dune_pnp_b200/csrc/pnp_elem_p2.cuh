@@ -139,19 +139,29 @@ PNP_HD static BasisAt basis_at(const Geo2& G, double x, double y) {
   return B;
 }
 
-// alpha_volume: xl[NL*k + i] = local coefficient of field k at node i; caux[a][i] = local coefficients of the operator's
-// coefficient fields (Poisson: c+, c-; diffusion: Phi), P2 functions as well.  ACCUMULATES into rl[NL*k + i].
+// basis values / transformed gradients and integration factor (weight * |det J| [* 2 pi r]) at every point of the operator's rule
+template <int NQ> struct QuadData { BasisAt B[NQ]; double factor[NQ]; };
 template <int OP, int NQ>
-PNP_HD static void alpha_volume(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* rl) {
-  const double PI = P.PI;
+PNP_HD static void quad_data(const Geo2& G, const PhysParams& P, QuadData<NQ>& Q) {
   for (int q = 0; q < NQ; q++) {
     double xi0, xi1, w;
     quad_point<NQ>(q, xi0, xi1, w);
-    const BasisAt B = basis_at(G, xi0, xi1);
+    Q.B[q] = basis_at(G, xi0, xi1);
     const double gy = G.y0 + (G.y1 - G.y0) * xi0 + (G.y2 - G.y0) * xi1;
     double factor = w * G.detabs;
+    if ((OP == OP_PNP || OP == OP_PB || OP == OP_POISSON) && P.cylindrical) factor *= gy * 2 * P.PI;
+    Q.factor[q] = factor;
+  }
+}
+// alpha_volume: xl[NL*k + i] = local coefficient of field k at node i; caux[a][i] = local coefficients of the operator's
+// coefficient fields (Poisson: c+, c-; diffusion: Phi), Pk functions as well.  ACCUMULATES into rl[NL*k + i].
+template <int OP, int NQ>
+PNP_HD static void alpha_volume_q(const QuadData<NQ>& Q, const PhysParams& P, const double* xl, const double (*caux)[NL], double* rl) {
+  const double PI = P.PI;
+  for (int q = 0; q < NQ; q++) {
+    const BasisAt& B = Q.B[q];
+    const double factor = Q.factor[q];
     if (OP == OP_PNP) {
-      if (P.cylindrical) factor *= gy * 2 * PI;
       double u[3], gu[3][2];
       for (int k = 0; k < 3; k++) {
         u[k] = 0.0; gu[k][0] = 0.0; gu[k][1] = 0.0;
@@ -162,7 +172,6 @@ PNP_HD static void alpha_volume(const Geo2& G, const PhysParams& P, const double
       for (int i = 0; i < NL; i++) rl[NL + i] += (dot2(gu[1], B.g[i]) - u[1] * dot2(gu[0], B.g[i])) * factor;
       for (int i = 0; i < NL; i++) rl[2 * NL + i] += (dot2(gu[2], B.g[i]) + u[2] * dot2(gu[0], B.g[i])) * factor;
     } else if (OP == OP_PB || OP == OP_POISSON) {
-      if (P.cylindrical) factor *= gy * 2 * PI;
       double u = 0.0, gu[2] = {0.0, 0.0};
       for (int i = 0; i < NL; i++) u += xl[i] * B.phi[i];
       for (int i = 0; i < NL; i++) { gu[0] += xl[i] * B.g[i][0]; gu[1] += xl[i] * B.g[i][1]; }
@@ -188,6 +197,12 @@ PNP_HD static void alpha_volume(const Geo2& G, const PhysParams& P, const double
       for (int i = 0; i < NL; i++) rl[i] += u * B.phi[i] * factor;
     }
   }
+}
+template <int OP, int NQ>
+PNP_HD static void alpha_volume(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* rl) {
+  QuadData<NQ> Q;
+  quad_data<OP, NQ>(G, P, Q);
+  alpha_volume_q<OP, NQ>(Q, P, xl, caux, rl);
 }
 
 // alpha_boundary of DUNE face f with end points (ax,ay)->(bx,by) in element order; j[k] = flux of field k, skip[k]: the face
@@ -220,63 +235,84 @@ template <int OP, int NQ>
 PNP_HD static void jacobian_fd(const Geo2& G, const PhysParams& P, double* xl, const double (*caux)[NL], double eps, double* Ae) {
   constexpr int n = NL * OpTraits<OP>::F;
   double down[n], up[n];
+  QuadData<NQ> Q; // the n + 1 evaluations share the basis tables (they do not depend on the state)
+  quad_data<OP, NQ>(G, P, Q);
   for (int i = 0; i < n; i++) down[i] = 0.0;
-  alpha_volume<OP, NQ>(G, P, xl, caux, down);
+  alpha_volume_q<OP, NQ>(Q, P, xl, caux, down);
   for (int j = 0; j < n; j++) {
     for (int i = 0; i < n; i++) up[i] = 0.0;
     const double keep = xl[j];
     const double delta = eps * (1.0 + fabs(keep));
     xl[j] = keep + delta;
-    alpha_volume<OP, NQ>(G, P, xl, caux, up);
+    alpha_volume_q<OP, NQ>(Q, P, xl, caux, up);
     for (int i = 0; i < n; i++) Ae[i * n + j] += (up[i] - down[i]) / delta;
     xl[j] = keep;
   }
 }
 
-// exact derivative (not in the reference)
+// exact derivative (not in the reference).  Every entry is the sum over the quadrature points, in point order, of the same terms
+// the point-by-point accumulation adds -- summed in a register and added to Ae once.
 template <int OP, int NQ>
 PNP_HD static void jacobian_exact(const Geo2& G, const PhysParams& P, const double* xl, const double (*caux)[NL], double* Ae) {
   constexpr int n = NL * OpTraits<OP>::F;
-  for (int q = 0; q < NQ; q++) {
-    double xi0, xi1, w;
-    quad_point<NQ>(q, xi0, xi1, w);
-    const BasisAt B = basis_at(G, xi0, xi1);
-    const double gy = G.y0 + (G.y1 - G.y0) * xi0 + (G.y2 - G.y0) * xi1;
-    double factor = w * G.detabs;
-    if ((OP == OP_PNP || OP == OP_PB || OP == OP_POISSON) && P.cylindrical) factor *= gy * 2 * P.PI;
-    if (OP == OP_PNP) {
-      double u[3] = {0, 0, 0}, gP[2] = {0, 0};
+  QuadData<NQ> Q;
+  quad_data<OP, NQ>(G, P, Q);
+  if (OP == OP_PNP) {
+    double u1[NQ], u2[NQ], gP[NQ][2];
+    for (int q = 0; q < NQ; q++) {
+      const BasisAt& B = Q.B[q];
+      double u[3] = {0, 0, 0};
       for (int k = 0; k < 3; k++) for (int i = 0; i < NL; i++) u[k] += xl[NL * k + i] * B.phi[i];
-      for (int i = 0; i < NL; i++) { gP[0] += xl[i] * B.g[i][0]; gP[1] += xl[i] * B.g[i][1]; }
-      const double kap = 4 * P.PI * P.l_b;
-      for (int i = 0; i < NL; i++) {
-        const double dPi = gP[0] * B.g[i][0] + gP[1] * B.g[i][1];
-        for (int j = 0; j < NL; j++) {
-          const double K = B.g[j][0] * B.g[i][0] + B.g[j][1] * B.g[i][1];
-          Ae[i * n + j] += K * factor;
-          Ae[i * n + NL + j] += kap * B.phi[j] * B.phi[i] * factor;
-          Ae[i * n + 2 * NL + j] -= kap * B.phi[j] * B.phi[i] * factor;
-          Ae[(NL + i) * n + j] -= u[1] * K * factor;
-          Ae[(NL + i) * n + NL + j] += (K - B.phi[j] * dPi) * factor;
-          Ae[(2 * NL + i) * n + j] += u[2] * K * factor;
-          Ae[(2 * NL + i) * n + 2 * NL + j] += (K + B.phi[j] * dPi) * factor;
-        }
-      }
-    } else {
-      double u = 0, gP[2] = {0, 0};
-      for (int i = 0; i < NL; i++) u += xl[i] * B.phi[i];
-      if (OP == OP_DIFFUSION) for (int i = 0; i < NL; i++) { gP[0] += caux[0][i] * B.g[i][0]; gP[1] += caux[0][i] * B.g[i][1]; }
-      const double ch = OP == OP_PB ? 8 * P.PI * P.l_b * P.c0 * cosh(u) : 0.0;
-      for (int i = 0; i < NL; i++) for (int j = 0; j < NL; j++) {
-        const double K = B.g[j][0] * B.g[i][0] + B.g[j][1] * B.g[i][1];
-        double v;
-        if (OP == OP_PB) v = K + ch * B.phi[j] * B.phi[i];
-        else if (OP == OP_POISSON) v = K;
-        else if (OP == OP_DIFFUSION) v = K + B.phi[j] * P.valency * (gP[0] * B.g[i][0] + gP[1] * B.g[i][1]);
-        else v = B.phi[j] * B.phi[i];
-        Ae[i * n + j] += v * factor;
-      }
+      u1[q] = u[1]; u2[q] = u[2];
+      gP[q][0] = 0; gP[q][1] = 0;
+      for (int i = 0; i < NL; i++) { gP[q][0] += xl[i] * B.g[i][0]; gP[q][1] += xl[i] * B.g[i][1]; }
     }
+    const double kap = 4 * P.PI * P.l_b;
+    for (int i = 0; i < NL; i++)
+      for (int j = 0; j < NL; j++) {
+        double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a20 = 0, a22 = 0;
+        for (int q = 0; q < NQ; q++) {
+          const BasisAt& B = Q.B[q];
+          const double factor = Q.factor[q];
+          const double dPi = gP[q][0] * B.g[i][0] + gP[q][1] * B.g[i][1];
+          const double K = B.g[j][0] * B.g[i][0] + B.g[j][1] * B.g[i][1];
+          a00 += K * factor;
+          a01 += kap * B.phi[j] * B.phi[i] * factor;
+          a02 -= kap * B.phi[j] * B.phi[i] * factor;
+          a10 -= u1[q] * K * factor;
+          a11 += (K - B.phi[j] * dPi) * factor;
+          a20 += u2[q] * K * factor;
+          a22 += (K + B.phi[j] * dPi) * factor;
+        }
+        Ae[i * n + j] += a00; Ae[i * n + NL + j] += a01; Ae[i * n + 2 * NL + j] += a02;
+        Ae[(NL + i) * n + j] += a10; Ae[(NL + i) * n + NL + j] += a11;
+        Ae[(2 * NL + i) * n + j] += a20; Ae[(2 * NL + i) * n + 2 * NL + j] += a22;
+      }
+  } else {
+    double ch[NQ], gP[NQ][2];
+    for (int q = 0; q < NQ; q++) {
+      const BasisAt& B = Q.B[q];
+      double u = 0;
+      for (int i = 0; i < NL; i++) u += xl[i] * B.phi[i];
+      gP[q][0] = 0; gP[q][1] = 0;
+      if (OP == OP_DIFFUSION) for (int i = 0; i < NL; i++) { gP[q][0] += caux[0][i] * B.g[i][0]; gP[q][1] += caux[0][i] * B.g[i][1]; }
+      ch[q] = OP == OP_PB ? 8 * P.PI * P.l_b * P.c0 * cosh(u) : 0.0;
+    }
+    for (int i = 0; i < NL; i++)
+      for (int j = 0; j < NL; j++) {
+        double acc = 0;
+        for (int q = 0; q < NQ; q++) {
+          const BasisAt& B = Q.B[q];
+          const double K = B.g[j][0] * B.g[i][0] + B.g[j][1] * B.g[i][1];
+          double v;
+          if (OP == OP_PB) v = K + ch[q] * B.phi[j] * B.phi[i];
+          else if (OP == OP_POISSON) v = K;
+          else if (OP == OP_DIFFUSION) v = K + B.phi[j] * P.valency * (gP[q][0] * B.g[i][0] + gP[q][1] * B.g[i][1]);
+          else v = B.phi[j] * B.phi[i];
+          acc += v * Q.factor[q];
+        }
+        Ae[i * n + j] += acc;
+      }
   }
 }
 
