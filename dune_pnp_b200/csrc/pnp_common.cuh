@@ -70,6 +70,7 @@ struct Tune {
   long tma_min_rows = -1; // smallest level the streaming SpMV serves (-1: two tiles per SM)
   int graph = 1;          // the multigrid's coarse correction is replayed from a CUDA graph
   int fd_warp = 1;        // FD-faithful Jacobian: warp-cooperative kernel (0: one thread per vertex)
+  long p2_chunk = 0;      // quadratic / cubic elements: elements per scratch block of the Jacobian assembly (0: 2 GB worth)
 };
 inline Tune& tune() { static Tune t; return t; }
 

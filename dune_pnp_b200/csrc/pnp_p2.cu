@@ -108,33 +108,36 @@ __global__ void k_p2_gather_residual(long nd, int F, int NL, int comp0, const in
 }
 // phase 1, Jacobian: element matrix -> scratch[e * n * n ..]
 template <int DEG, int OP, int NQ, int MODE>
-__global__ void k_p2_elem_jacobian(int nT, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
+__global__ void k_p2_elem_jacobian(int e0, int ne, const int* __restrict__ tri, const double* __restrict__ cx, const double* __restrict__ cy,
                                    const int* __restrict__ e2d, PhysParams P, long nd, double eps, const double* __restrict__ u,
                                    const double* __restrict__ aux0, const double* __restrict__ aux1, double* __restrict__ out) {
   using E = PkElem<DEG>;
   constexpr int F = OpTraits<OP>::F, NL = E::NL, n = NL * F;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nT; e += gridDim.x * blockDim.x) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ne; t += gridDim.x * blockDim.x) {
+    const int e = e0 + t;
     typename E::Geo2 G; double xl[n], caux[2][NL];
     p2_gather_element<DEG, OP>(e, tri, cx, cy, e2d, nd, u, aux0, aux1, G, xl, caux);
-    double* Ae = out + (long)e * n * n; // accumulated in place (one writer)
+    double* Ae = out + (long)t * n * n; // accumulated in place (one writer)
     for (int i = 0; i < n * n; i++) Ae[i] = 0.0;
     if (MODE == 0) E::template jacobian_fd<OP, NQ>(G, P, xl, caux, eps, Ae);
     else E::template jacobian_exact<OP, NQ>(G, P, xl, caux, Ae);
   }
 }
-// phase 2, Jacobian: row (ki, d) of the CSR matrix
-__global__ void k_p2_gather_jacobian(long nd, int F, int NL, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+// phase 2, Jacobian: row (ki, d) of the CSR matrix receives the contributions of the elements [e0, e1) (the scratch block
+// holds that chunk); chunks come in ascending order, the first one (e0 == 0) initialises the row
+__global__ void k_p2_gather_jacobian(int e0, int e1, long nd, int F, int NL, int comp0, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                      const int* __restrict__ e2d, const unsigned char* __restrict__ dir, const int* __restrict__ rp,
                                      const int* __restrict__ col, const double* __restrict__ scratch, double* __restrict__ vals) {
   const int n = NL * F;
   for (long gi = blockIdx.x * (long)blockDim.x + threadIdx.x; gi < (long)F * nd; gi += (long)gridDim.x * blockDim.x) {
     const int ki = (int)(gi / nd); const long d = gi - (long)ki * nd;
     const int r0 = rp[gi], r1 = rp[gi + 1];
-    for (int s = r0; s < r1; s++) vals[s] = 0.0;
+    if (e0 == 0) for (int s = r0; s < r1; s++) vals[s] = 0.0;
     if ((dir[d] >> (F == 3 ? ki : comp0)) & 1u) { vals[r0] = 1.0; continue; } // trivial row (its only entry is the diagonal)
     for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; t++) {
       const int e = inc[t] >> 4, i = inc[t] & 15;
-      const double* Ae = scratch + (long)e * n * n + (long)(NL * ki + i) * n;
+      if (e < e0 || e >= e1) continue;
+      const double* Ae = scratch + (long)(e - e0) * n * n + (long)(NL * ki + i) * n;
       for (int kj = 0; kj < F; kj++)
         for (int j = 0; j < NL; j++) {
           const long dj = e2d[NL * e + j];
@@ -178,17 +181,17 @@ template <int DEG, int OP> void launch_elem_residual(Ctx& c, P2Space& S, const O
   if (op.intorder == 5) launch_elem_residual_q<DEG, OP, 7>(c, S, op, P, u, a0, a1);
   else launch_elem_residual_q<DEG, OP, OpTraits<OP>::NQ>(c, S, op, P, u, a0, a1);
 }
-template <int DEG, int OP, int NQ> void launch_elem_jacobian_q(Ctx& c, P2Space& S, const PhysParams& P, int mode, double eps,
+template <int DEG, int OP, int NQ> void launch_elem_jacobian_q(Ctx& c, P2Space& S, int e0, int ne, const PhysParams& P, int mode, double eps,
                                                                const double* u, const double* a0, const double* a1) {
-  const int g = grid_for(S.nT, 64);
-  if (mode == 0) k_p2_elem_jacobian<DEG, OP, NQ, 0><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
-  else k_p2_elem_jacobian<DEG, OP, NQ, 1><<<g, 64, 0, c.stream>>>((int)S.nT, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
+  const int g = grid_for(ne, 64);
+  if (mode == 0) k_p2_elem_jacobian<DEG, OP, NQ, 0><<<g, 64, 0, c.stream>>>(e0, ne, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
+  else k_p2_elem_jacobian<DEG, OP, NQ, 1><<<g, 64, 0, c.stream>>>(e0, ne, c.ctri.p, c.cx.p, c.cy.p, S.e2d.p, P, S.nd, eps, u, a0, a1, S.scratch.p);
   PNP_CHECK_LAUNCH(); c.launches++;
 }
-template <int DEG, int OP> void launch_elem_jacobian(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P, int mode, double eps,
-                                                     const double* u, const double* a0, const double* a1) {
-  if (op.intorder == 5) launch_elem_jacobian_q<DEG, OP, 7>(c, S, P, mode, eps, u, a0, a1);
-  else launch_elem_jacobian_q<DEG, OP, OpTraits<OP>::NQ>(c, S, P, mode, eps, u, a0, a1);
+template <int DEG, int OP> void launch_elem_jacobian(Ctx& c, P2Space& S, int e0, int ne, const Operator& op, const PhysParams& P, int mode,
+                                                     double eps, const double* u, const double* a0, const double* a1) {
+  if (op.intorder == 5) launch_elem_jacobian_q<DEG, OP, 7>(c, S, e0, ne, P, mode, eps, u, a0, a1);
+  else launch_elem_jacobian_q<DEG, OP, OpTraits<OP>::NQ>(c, S, e0, ne, P, mode, eps, u, a0, a1);
 }
 template <int DEG> void dispatch_residual(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P, const double* u, const double* a0,
                                           const double* a1) {
@@ -201,14 +204,14 @@ template <int DEG> void dispatch_residual(Ctx& c, P2Space& S, const Operator& op
     default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
   }
 }
-template <int DEG> void dispatch_jacobian(Ctx& c, P2Space& S, const Operator& op, const PhysParams& P, int mode, double eps,
+template <int DEG> void dispatch_jacobian(Ctx& c, P2Space& S, int e0, int ne, const Operator& op, const PhysParams& P, int mode, double eps,
                                           const double* u, const double* a0, const double* a1) {
   switch (op.op) {
-    case OP_PB: launch_elem_jacobian<DEG, OP_PB>(c, S, op, P, mode, eps, u, a0, a1); break;
-    case OP_POISSON: launch_elem_jacobian<DEG, OP_POISSON>(c, S, op, P, mode, eps, u, a0, a1); break;
-    case OP_DIFFUSION: launch_elem_jacobian<DEG, OP_DIFFUSION>(c, S, op, P, mode, eps, u, a0, a1); break;
-    case OP_MASS: launch_elem_jacobian<DEG, OP_MASS>(c, S, op, P, mode, eps, u, a0, a1); break;
-    case OP_PNP: launch_elem_jacobian<DEG, OP_PNP>(c, S, op, P, mode, eps, u, a0, a1); break;
+    case OP_PB: launch_elem_jacobian<DEG, OP_PB>(c, S, e0, ne, op, P, mode, eps, u, a0, a1); break;
+    case OP_POISSON: launch_elem_jacobian<DEG, OP_POISSON>(c, S, e0, ne, op, P, mode, eps, u, a0, a1); break;
+    case OP_DIFFUSION: launch_elem_jacobian<DEG, OP_DIFFUSION>(c, S, e0, ne, op, P, mode, eps, u, a0, a1); break;
+    case OP_MASS: launch_elem_jacobian<DEG, OP_MASS>(c, S, e0, ne, op, P, mode, eps, u, a0, a1); break;
+    case OP_PNP: launch_elem_jacobian<DEG, OP_PNP>(c, S, e0, ne, op, P, mode, eps, u, a0, a1); break;
     default: PNP_REQUIRE(false, PNP_E_ARG, "unknown operator");
   }
 }
@@ -405,13 +408,20 @@ void p2_assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mod
   p2_matrix_init(c, A, op);
   const double *a0, *a1;
   coefficient_ptrs_p2(c, op, &a0, &a1);
-  if (S.scratch.n < (size_t)n * n * S.nT) S.scratch.alloc((size_t)n * n * S.nT);
+  // the element matrices (n*n doubles each: 2.6 KB for the quadratic, 7.2 KB for the cubic 3-field operator) pass through a
+  // scratch block of bounded size: chunks of elements in ascending order, each gathered into the rows before the next
+  long chunk = tune().p2_chunk > 0 ? tune().p2_chunk : (long)(2e9 / (8.0 * n * n));
+  chunk = std::max(1l, std::min(chunk, S.nT));
+  if (S.scratch.n < (size_t)n * n * chunk) S.scratch.alloc((size_t)n * n * chunk);
   const PhysParams P = c.phys(op.valency);
-  if (S.deg == 2) dispatch_jacobian<2>(c, S, op, P, mode, eps, u.d.p, a0, a1);
-  else dispatch_jacobian<3>(c, S, op, P, mode, eps, u.d.p, a0, a1);
-  k_p2_gather_jacobian<<<grid_for(F * S.nd, 128), 128, 0, c.stream>>>(S.nd, F, S.NL, op.comp0, S.inc_ptr.p, S.inc.p, S.e2d.p, S.dir.p, A.csr_rp,
-                                                                      A.csr_col, S.scratch.p, A.vals.p);
-  PNP_CHECK_LAUNCH(); c.launches++;
+  for (long e0 = 0; e0 < S.nT; e0 += chunk) {
+    const int ne = (int)std::min(chunk, S.nT - e0);
+    if (S.deg == 2) dispatch_jacobian<2>(c, S, (int)e0, ne, op, P, mode, eps, u.d.p, a0, a1);
+    else dispatch_jacobian<3>(c, S, (int)e0, ne, op, P, mode, eps, u.d.p, a0, a1);
+    k_p2_gather_jacobian<<<grid_for(F * S.nd, 128), 128, 0, c.stream>>>((int)e0, (int)e0 + ne, S.nd, F, S.NL, op.comp0, S.inc_ptr.p, S.inc.p,
+                                                                        S.e2d.p, S.dir.p, A.csr_rp, A.csr_col, S.scratch.p, A.vals.p);
+    PNP_CHECK_LAUNCH(); c.launches++;
+  }
   c.last_u = nullptr; c.last_vals = nullptr; // (no multigrid re-discretisation for quadratic elements)
   c.acct(Ctx::ACC_ASSEMBLY, (double)S.nT * 16.0 * n * n + 12.0 * (double)A.csr_nnz);
 }

@@ -465,3 +465,24 @@ def test_driver_instationary_pnp_md_with_quadratic_elements(tmp_path, degree):
     ip_o, im_o = P.ion_flux(c.download(uphi, 1), c.download(ucp, 1), c.download(ucm, 1))
     last = [float(t) for t in cur[-1].split()]
     assert np.allclose(last[1::4], ip_o, rtol=1e-5, atol=1e-12) and np.allclose(last[3::4], im_o, rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("degree,mode", [(2, 0), (3, 1)])
+def test_jacobian_scratch_chunks_give_the_same_bits(degree, mode):
+    """The element matrices pass through a scratch block of bounded size (2 GB by default): chunks of elements in ascending order
+    leave every entry's summation order unchanged."""
+    capi = _capi()
+    c, m, p, P = make_ctx("pore_small", 0, degree)
+    u, a0, a1 = _state(P, ora.OP_PNP, seed=4)
+    h = _operator(c, ora.OP_PNP, a0, a1, 1.0, intorder=5 if degree == 3 else 0)
+    vu, A = c.vec(3, u), c.matrix(h)
+    rp, col = c.pattern(h, 3)
+    c.jacobian(h, vu, A, mode, 1e-11)
+    ref = c.matrix_values(h, A, len(col))
+    try:
+        for chunk in (1, 37, m.nT - 1):
+            capi.tune("p2_chunk", chunk)
+            c.jacobian(h, vu, A, mode, 1e-11)
+            assert np.array_equal(c.matrix_values(h, A, len(col)), ref)
+    finally:
+        capi.tune("p2_chunk", 0)
