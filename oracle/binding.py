@@ -358,6 +358,16 @@ class P2:
         _chk(lib().orak_interpolate(self.degree, self.mesh.h, self.params.h, comp, _d(pb), _d(u)))
         return u
 
+    def onestep(self, xold, g, phi, valency, dt, reduction=1e-5, method=0, solver=SOLVER_BCGS, prec=PREC_SSOR, steps=1, maxit=5000,
+                jac_mode=0, eps=1e-11, comp0=1, intorder=-1):
+        """OneStepMethod::apply (method 0: Alexander2, 1: implicit Euler) for the transport of one species on this space."""
+        xnew = np.zeros(self.nd); res = np.zeros(8)
+        _chk(lib().orak_onestep(self.degree, self.mesh.h, self.params.h, comp0, method, C.c_double(dt), _d(_f64(xold)), _d(_f64(g)),
+                                _d(_f64(phi)), C.c_double(valency), intorder, _d(xnew), C.c_double(reduction), solver, prec, steps,
+                                maxit, jac_mode, C.c_double(eps), _d(res)))
+        nst = 1 if method == 1 else 2
+        return xnew, [dict(converged=bool(res[2 * k]), iterations=int(res[2 * k + 1])) for k in range(nst)]
+
     def ion_flux(self, phi, cp, cm):
         ns = int(self.params.sys[0])
         ip = np.zeros(ns); im = np.zeros(ns)

@@ -478,6 +478,26 @@ int orak_newton(int degree, void* mh, void* ph, int op, int comp0, double* u, co
                 int intorder, const double* opts, double* result, double* hist, int* lin_hist, int cap) {
   return degree == 3 ? pk_newton<p3>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, opts, result, hist, lin_hist, cap) : pk_newton<p2>(mh, ph, op, comp0, u, aux0, aux1, valency, intorder, opts, result, hist, lin_hist, cap);
 }
+extern "C++" template <class P> int pk_onestep(void* mh, void* ph, int comp0, int method, double dt, const double* xold, const double* g,
+                                               const double* phi, double valency, int intorder, double* xnew, double reduction, int solver,
+                                               int prec, int steps, int maxit, int jac_mode, double eps, double* result) {
+  ORA_TRY
+  const Mesh* m = (Mesh*)mh; const Sysparams* s = &((Params*)ph)->s;
+  typename P::Space2 sp = P::make_space2(*m, *s, 1, comp0);
+  OpCtx c0 = make_ctx2(m, s, OP_DIFFUSION, phi, nullptr, valency, intorder);
+  OpCtx c1 = make_ctx2(m, s, OP_MASS, nullptr, nullptr, 1.0, intorder);
+  TimeMethod tm = method == 1 ? implicit_euler() : alexander2();
+  OneStepResult R = P::onestep2(sp, c0, c1, tm, dt, xold, g, xnew, reduction, solver, prec, steps, maxit, jac_mode, eps);
+  for (size_t k = 0; k < R.stage.size(); k++) { result[2 * k] = R.stage[k].converged; result[2 * k + 1] = R.stage[k].iterations; }
+  return 0;
+  ORA_CATCH(-1)
+}
+int orak_onestep(int degree, void* mh, void* ph, int comp0, int method, double dt, const double* xold, const double* g, const double* phi,
+                 double valency, int intorder, double* xnew, double reduction, int solver, int prec, int steps, int maxit, int jac_mode,
+                 double eps, double* result) {
+  return degree == 3 ? pk_onestep<p3>(mh, ph, comp0, method, dt, xold, g, phi, valency, intorder, xnew, reduction, solver, prec, steps, maxit, jac_mode, eps, result)
+                     : pk_onestep<p2>(mh, ph, comp0, method, dt, xold, g, phi, valency, intorder, xnew, reduction, solver, prec, steps, maxit, jac_mode, eps, result);
+}
 extern "C++" template <class P> int pk_ion_flux(void* mh, void* ph, const double* phi, const double* cp, const double* cm, double* ip, double* im) {
   ORA_TRY
   typename P::Space2 sp = P::make_space2(*(Mesh*)mh, ((Params*)ph)->s, 1, 0);

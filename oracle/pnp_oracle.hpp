@@ -1165,42 +1165,53 @@ struct OneStepResult { std::vector<LinResult> stage; };
 // xold -> xnew over one step of size dt.  c0: spatial operator (DiffusionOperator), c1: temporal operator
 // (DiffusionTOperator); g: Dirichlet values (interpolate(f, ...) at the constrained dofs; the reference's boundary
 // function cpB is time independent); the stage problems are solved by StationaryLinearProblemSolver (one linear solve).
-inline OneStepResult onestep_apply(const Space& sp, const OpCtx& c0, const OpCtx& c1, const TimeMethod& tm, double dt,
-                                   const double* xold, const double* g, double* xnew, double reduction, int solver,
-                                   int prec, int steps, int maxit, int jac_mode = 0, double eps = 1e-11) {
-  const int N = sp.N();
+// (the method itself, for any discrete space: N dofs, their Dirichlet flags, the BCRS pattern, residual and Jacobian of the
+// spatial (0) and the temporal (1) operator)
+template <class Res0, class Res1, class Jac0, class Jac1>
+inline OneStepResult onestep_core(int N, const std::vector<char>& dirichlet, const CSR& pattern, Res0 residual0, Res1 residual1,
+                                  Jac0 jacobian0, Jac1 jacobian1, const TimeMethod& tm, double dt, const double* xold,
+                                  const double* g, double* xnew, double reduction, int solver, int prec, int steps, int maxit) {
   OneStepResult out;
   std::vector<std::vector<double>> x(tm.s + 1, std::vector<double>(N));
   std::copy(xold, xold + N, x[0].begin());
-  CSR A = make_pattern(sp), B = make_pattern(sp);
+  CSR A = pattern, B = pattern;
   std::vector<double> cst(N), r0(N), r1(N), res(N), z(N);
   for (int r = 1; r <= tm.s; r++) {
     // preStage: constant part of the residual from the earlier stages
     std::fill(cst.begin(), cst.end(), 0.0);
     for (int i = 0; i < r; i++) {
       const double ai = tm.a[r - 1][i], bi = tm.b[r - 1][i];
-      if (std::fabs(ai) > 1e-6) { residual(sp, c1, x[i].data(), r1.data()); for (int k = 0; k < N; k++) cst[k] += ai * r1[k]; }
-      if (std::fabs(bi) > 1e-6) { residual(sp, c0, x[i].data(), r0.data()); for (int k = 0; k < N; k++) cst[k] += bi * dt * r0[k]; }
+      if (std::fabs(ai) > 1e-6) { residual1(x[i].data(), r1.data()); for (int k = 0; k < N; k++) cst[k] += ai * r1[k]; }
+      if (std::fabs(bi) > 1e-6) { residual0(x[i].data(), r0.data()); for (int k = 0; k < N; k++) cst[k] += bi * dt * r0[k]; }
     }
     // initial guess: previous stage; Dirichlet dofs from the boundary function, the rest copied (copy_nonconstrained_dofs)
     std::vector<double>& xn = x[r];
     xn = x[r - 1];
-    for (int k = 0; k < N; k++) if (sp.dirichlet[k]) xn[k] = g[k];
+    for (int k = 0; k < N; k++) if (dirichlet[k]) xn[k] = g[k];
     // StationaryLinearProblemSolver on the one-step operator
     const double ar = tm.a[r - 1][r], br = tm.b[r - 1][r];
-    jacobian(sp, c1, xn.data(), A, jac_mode, eps);
-    jacobian(sp, c0, xn.data(), B, jac_mode, eps);
+    jacobian1(xn.data(), A);
+    jacobian0(xn.data(), B);
     for (size_t k = 0; k < A.val.size(); k++) A.val[k] = ar * A.val[k] + br * dt * B.val[k];
-    for (int k = 0; k < N; k++) if (sp.dirichlet[k]) A.val[A.find(k, k)] = 1.0; // constrained rows are trivial
-    residual(sp, c1, xn.data(), r1.data());
-    residual(sp, c0, xn.data(), r0.data());
-    for (int k = 0; k < N; k++) res[k] = sp.dirichlet[k] ? 0.0 : cst[k] + ar * r1[k] + br * dt * r0[k];
+    for (int k = 0; k < N; k++) if (dirichlet[k]) A.val[A.find(k, k)] = 1.0; // constrained rows are trivial
+    residual1(xn.data(), r1.data());
+    residual0(xn.data(), r0.data());
+    for (int k = 0; k < N; k++) res[k] = dirichlet[k] ? 0.0 : cst[k] + ar * r1[k] + br * dt * r0[k];
     std::fill(z.begin(), z.end(), 0.0);
     out.stage.push_back(lin_solve(solver, A, z.data(), res.data(), reduction, maxit, prec, steps));
     for (int k = 0; k < N; k++) xn[k] -= z[k];
   }
   std::copy(x[tm.s].begin(), x[tm.s].end(), xnew);
   return out;
+}
+inline OneStepResult onestep_apply(const Space& sp, const OpCtx& c0, const OpCtx& c1, const TimeMethod& tm, double dt,
+                                   const double* xold, const double* g, double* xnew, double reduction, int solver,
+                                   int prec, int steps, int maxit, int jac_mode = 0, double eps = 1e-11) {
+  return onestep_core(sp.N(), sp.dirichlet, make_pattern(sp),
+                      [&](const double* x, double* r) { residual(sp, c0, x, r); }, [&](const double* x, double* r) { residual(sp, c1, x, r); },
+                      [&](const double* x, CSR& A) { jacobian(sp, c0, x, A, jac_mode, eps); },
+                      [&](const double* x, CSR& A) { jacobian(sp, c1, x, A, jac_mode, eps); }, tm, dt, xold, g, xnew, reduction, solver,
+                      prec, steps, maxit);
 }
 
 // ----------------------------------------------------------------------------

@@ -465,6 +465,17 @@ static void interpolate_bcext2(const Space2& sp, int comp, const double* pb, dou
     for (int i = 0; i < NL; i++) u[sp.sdof(e, i)] = bcext_eval2(sp, comp, pb, e, i);
 }
 
+// OneStepMethod on OneStepGridOperator<DiffusionOperator, DiffusionTOperator> (instationary_pnp_from_pb_md.hh:368-391,421-425)
+static OneStepResult onestep2(const Space2& sp, const OpCtx& c0, const OpCtx& c1, const TimeMethod& tm, double dt, const double* xold,
+                              const double* g, double* xnew, double reduction, int solver, int prec, int steps, int maxit,
+                              int jac_mode = 0, double eps = 1e-11) {
+  return onestep_core(sp.N(), sp.dirichlet, make_pattern2(sp),
+                      [&](const double* x, double* r) { residual2(sp, c0, x, r); }, [&](const double* x, double* r) { residual2(sp, c1, x, r); },
+                      [&](const double* x, CSR& A) { jacobian2(sp, c0, x, A, jac_mode, eps); },
+                      [&](const double* x, CSR& A) { jacobian2(sp, c1, x, A, jac_mode, eps); }, tm, dt, xold, g, xnew, reduction, solver,
+                      prec, steps, maxit);
+}
+
 // calcIonFlux (ionFlux.hh:8-96) with quadratic functions: DiscreteGridFunction / DiscreteGridFunctionGradient evaluated at
 // the local coordinates of the face centre -- the basis sum over the element's 6 dofs per field
 static void ion_flux2(const Space2& sp, const double* phi, const double* cp, const double* cm, double* ip, double* im) {

@@ -486,3 +486,31 @@ def test_jacobian_scratch_chunks_give_the_same_bits(degree, mode):
             assert np.array_equal(c.matrix_values(h, A, len(col)), ref)
     finally:
         capi.tune("p2_chunk", 0)
+
+
+@pytest.mark.parametrize("degree,method,mode", [(2, 0, 0), (2, 1, 1), (3, 0, 1)])
+def test_onestep_transport_matches_oracle(degree, method, mode):
+    """One time step of the split scheme's ion transport (instationary_pnp_from_pb_md.hh:421-425) on the Pk spaces: SDIRK stages,
+    each a StationaryLinearProblemSolver on a*M + b*dt*J0 with BiCGSTAB + ILU0, against the oracle's OneStepMethod."""
+    capi = _capi()
+    c, m, p, P = make_ctx("pore_small", 1, degree)
+    io = 5 if degree == 3 else 0
+    rng = np.random.RandomState(11)
+    phi = 0.5 * np.sin(3 * P.x) * np.cos(2 * P.y)
+    g = P.interpolate(1, phi)
+    d = P.dirichlet(1, 1)
+    x0 = g * (1 + 0.1 * rng.uniform(-1, 1, P.nd)); x0[d] = g[d]
+    dt = p.sys[11]
+    h0 = _operator(c, capi.OP_DIFFUSION, phi, None, 1.0, comp0=1, intorder=io)
+    h1 = _operator(c, capi.OP_MASS, None, None, 1.0, comp0=1, intorder=io)
+    s = c.solver(capi.SOLVER_BCGS, capi.PREC_ILU0, 5000, 1)
+    vx0, vg, vx1 = c.vec(1, x0), c.vec(1, g), c.vec(1)
+    res = c.onestep(h0, h1, s, dt, vx0, vg, vx1, 1e-10, method, mode)
+    x1 = c.download(vx1, 1)
+    x1_o, res_o = P.onestep(x0, g, phi, 1.0, dt, 1e-10, method, prec=ora.PREC_ILU0, maxit=5000, jac_mode=mode, comp0=1, intorder=io or -1)
+    assert len(res) == len(res_o)
+    for a, b in zip(res, res_o):
+        assert a.converged and b["converged"] and abs(a.iterations - b["iterations"]) <= 1
+    tol = 1e-6 if mode == 1 else 1e-3   # (FD Jacobian: 1e-5 relative noise in the matrix, amplified through the stage solves)
+    assert np.linalg.norm(x1 - x1_o) <= tol * np.linalg.norm(x1_o - x0) + 1e-12 * np.linalg.norm(x1_o)
+    assert np.array_equal(x1[d], g[d]) and np.array_equal(c.download(vx0, 1), x0)

@@ -273,3 +273,41 @@ def test_cubic_newton_and_interpolation():
         d = P.dirichlet(1, comp)
         assert np.array_equal(g[P.voff:], ora.interpolate(m, p, comp, u3[P.voff:]))
         assert not d[:m.nT].any() and np.all(np.isfinite(g))
+
+
+@pytest.mark.parametrize("degree,method,order", [(2, 0, 2), (2, 1, 1), (3, 0, 2)])
+def test_onestep_on_quadratic_and_cubic_spaces(degree, method, order):
+    """The one-step method on the Pk spaces (the same stage algebra as for linear elements, on the Pk residuals and matrices):
+    (1) one implicit-Euler step of the linear transport problem solves (M + dt K) x1 = M x0 on the free dofs -- checked
+    through the residuals; (2) convergence order in time against expm(-T M^-1 K) x0 (dense reference, cylinder.msh)."""
+    import scipy.linalg
+    import scipy.sparse as sp
+    m, p, P = case("cylinder") if degree == 2 else case3("cylinder")
+    io = 5 if degree == 3 else -1
+    phi = 0.5 * np.sin(3 * P.x) * np.cos(2 * P.y)
+    d = P.dirichlet(1, 1)
+    rng = np.random.RandomState(5)
+    x0 = rng.uniform(0.5, 1.5, P.nd); x0[d] = 0.0
+    g = np.zeros(P.nd)
+    rp, col, kv = P.jacobian(ora.OP_DIFFUSION, x0, phi, valency=1.0, comp0=1, mode=1, intorder=io)
+    _, _, mv = P.jacobian(ora.OP_MASS, x0, comp0=1, mode=1, intorder=io)
+    K = sp.csr_matrix((kv, col, rp), shape=(P.nd, P.nd)); M = sp.csr_matrix((mv, col, rp), shape=(P.nd, P.nd))
+    f = ~d
+    dt = 0.05
+    x1, res = P.onestep(x0, g, phi, 1.0, dt, 1e-13, 1, prec=ora.PREC_ILU0, maxit=20000, jac_mode=1, intorder=io)
+    r = (P.residual(ora.OP_MASS, x1, comp0=1, intorder=io) - P.residual(ora.OP_MASS, x0, comp0=1, intorder=io)
+         + dt * P.residual(ora.OP_DIFFUSION, x1, phi, valency=1.0, comp0=1, intorder=io))
+    assert res[0]["converged"] and np.max(np.abs(r[f]) / (abs(M + dt * K) @ np.abs(x1))[f]) <= 1e-11
+    T = 0.4
+    Kd, Md = K.toarray()[np.ix_(f, f)], M.toarray()[np.ix_(f, f)]
+    exact = scipy.linalg.expm(-T * np.linalg.solve(Md, Kd)) @ x0[f]
+    errs = []
+    for n in (4, 8, 16):
+        x = x0.copy()
+        for _ in range(n):
+            x, res = P.onestep(x, g, phi, 1.0, T / n, 1e-13, method, prec=ora.PREC_ILU0, maxit=20000, jac_mode=1, intorder=io)
+            assert all(q["converged"] for q in res)
+        assert np.all(x[d] == 0.0)
+        errs.append(np.linalg.norm(x[f] - exact))
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert abs(rates[-1] - order) < 0.3, (errs, rates)
