@@ -40,3 +40,8 @@ python scripts/entrywise_parity.py
 # python -m pytest tests/test_gpu_nccl.py -m gpu -q
 # python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
 #     bench.py --gpus N --steps 3 --warmup 2 --no-cpu
+
+# 9. quadratic / cubic elements: kernel timings -> profiles/pk_bench_r02.json; device vs host probe of the
+#    element functions (scripts/probes/pk_probe.cu, built with nvcc -fmad=false like pnp_p2.cu)
+# python scripts/bench_pk.py --levels 3 > gpurun_out/pk_bench_r02.json
+# nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -fmad=false --expt-relaxed-constexpr scripts/probes/pk_probe.cu -o scripts/probes/pk_probe && scripts/probes/pk_probe
