@@ -43,6 +43,26 @@ using namespace pnp;
   } catch (const pnp::Error& e) { c.err = e.what(); return e.code; } \
   catch (const std::exception& e) { c.err = e.what(); return PNP_E_ARG; }
 
+namespace pnp {
+Ctx* ctx_make_owned_child(Ctx& p) {
+  pnp_ctx* h = new pnp_ctx;
+  h->c.device = p.device; h->c.stream = p.stream; h->c.owns_stream = false; h->c.sm_count = p.sm_count;
+  h->c.params = p.params;
+  h->c.parent = &p; p.children.push_back(&h->c);
+  p.owned_children.push_back(h);
+  return &h->c;
+}
+void ctx_destroy_owned_child(Ctx& p, Ctx* child) {
+  for (size_t i = 0; i < p.owned_children.size(); i++) {
+    pnp_ctx* h = (pnp_ctx*)p.owned_children[i];
+    if (&h->c != child) continue;
+    p.owned_children.erase(p.owned_children.begin() + i);
+    pnp_ctx_destroy(h);
+    return;
+  }
+}
+} // namespace pnp
+
 extern "C" {
 
 pnp_status pnp_ctx_create(int device, pnp_ctx** out) {

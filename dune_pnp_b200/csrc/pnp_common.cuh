@@ -150,6 +150,7 @@ struct Solver {
   DBuf<double> w[6]; // Krylov work vectors, sized on first use
   DBuf<double> dinv; // Jacobi: inverse diagonal
   DBuf<double> csr_lu; int csr_levels = 0; // quadratic elements: ILU0 factor on the CSR pattern; levels of the last sweep set-up
+  std::shared_ptr<void> pmg;               // quadratic / cubic elements: p-multigrid state (pnp_p2.cu)
   void ensure(size_t n) { for (auto& b : w) if (b.n != n) b.alloc(n); if (dinv.n != n) dinv.alloc(n); }
 };
 
@@ -295,6 +296,10 @@ void carry_set(Ctx&, const int* handles, int n);
 void carry_get(Ctx&, int i, Vec& out);
 void vec_upload(Ctx&, Vec&, const double* host_lex);
 void vec_download(Ctx&, const Vec&, double* host_lex);
+void vec_from_lex_device(Ctx&, Vec&, const double* d_lex);
+void vec_to_lex_device(Ctx&, const Vec&, double* d_lex);
+Ctx* ctx_make_owned_child(Ctx& parent); // pnp_capi.cu: a context on the parent's stream, destroyed with the parent ...
+void ctx_destroy_owned_child(Ctx& parent, Ctx* child); // ... or earlier
 long pattern_export(Ctx&, int op_handle, int* rowptr, int* col);
 void matrix_export(Ctx&, int op_handle, const Matrix&, double* val);
 void matrix_import(Ctx&, int op_handle, Matrix&, const int* rowptr, const int* col, const double* val);
@@ -331,6 +336,8 @@ void csr_diag_inverse(Ctx&, const Matrix& A, double* dinv);
 void csr_sweep_setup(Ctx&, Solver&, const Matrix& A, bool ilu);
 void csr_ssor_apply(Ctx&, Solver&, const Matrix& A, const double* d, double* y);
 void csr_ilu0_apply(Ctx&, Solver&, const Matrix& A, const double* d, double* y);
+void pmg_setup(Ctx&, Solver&, const Matrix& A);
+void pmg_apply(Ctx&, Solver&, const Matrix& A, const double* d, double* y);
 const unsigned char* p2_dirichlet_flags(Ctx&); // per scalar dof: bit c = Dirichlet for BC component c (device)
 void p2_sizes(Ctx&, long* nE, long* nd);
 void p2_offsets(Ctx&, long* eoff, long* voff);

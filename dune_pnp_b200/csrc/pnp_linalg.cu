@@ -209,7 +209,7 @@ namespace {
 void prec_setup(Ctx& c, Solver& S, const Matrix& A) {
   PNP_REQUIRE(c.degree == 1 || A.csr_rp, PNP_E_ARG, "matrix not assembled (or detached by a parameter change): assemble it first");
   if (A.csr_rp) {
-    PNP_REQUIRE(S.prec != PNP_PREC_AMG, PNP_E_ARG, "quadratic elements: the preconditioners are none (Richardson), Jacobi, SSOR and ILU0");
+    if (S.prec == PNP_PREC_AMG) pmg_setup(c, S, A);
     if (S.prec == PNP_PREC_JACOBI) csr_diag_inverse(c, A, S.dinv.p);
     if (S.prec == PNP_PREC_SSOR || S.prec == PNP_PREC_ILU0) csr_sweep_setup(c, S, A, S.prec == PNP_PREC_ILU0);
     return;
@@ -239,7 +239,7 @@ void prec_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double* y, 
       break;
     case PNP_PREC_SSOR: if (A.csr_rp) csr_ssor_apply(c, S, A, d, y); else ssor_apply(c, S, A, d, y); break;
     case PNP_PREC_ILU0: if (A.csr_rp) csr_ilu0_apply(c, S, A, d, y); else ilu0_apply(c, S, A, d, y); break;
-    case PNP_PREC_AMG: amg_apply(c, S, A, d, y); break;
+    case PNP_PREC_AMG: if (A.csr_rp) pmg_apply(c, S, A, d, y); else amg_apply(c, S, A, d, y); break;
     default: break;
   }
 }

@@ -422,7 +422,7 @@ void p2_assemble_jacobian(Ctx& c, const Operator& op, Vec& u, Matrix& A, int mod
                                                                         S.e2d.p, S.dir.p, A.csr_rp, A.csr_col, S.scratch.p, A.vals.p);
     PNP_CHECK_LAUNCH(); c.launches++;
   }
-  c.last_u = nullptr; c.last_vals = nullptr; // (no multigrid re-discretisation for quadratic elements)
+  c.last_u = u.d.p; c.last_op = op; c.last_mode = mode; c.last_eps = eps; c.last_vals = A.vals.p; // (what the p-multigrid re-discretises)
   c.acct(Ctx::ACC_ASSEMBLY, (double)S.nT * 16.0 * n * n + 12.0 * (double)A.csr_nnz);
 }
 
@@ -589,6 +589,153 @@ void p2_matrix_import(Ctx& c, const Operator& op, Matrix& A, const int* rowptr, 
               "CSR pattern differs from the operator's pattern (pnp_pattern_get)");
   A.vals.upload(val, Pn.nnz, c.stream);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// ---- p-multigrid (ISTLBackend_NOVLP_CG_AMG_SSOR with -DPDEGREE=2,3: src/Makefile.am:106-110) ----
+// V-cycle on two spaces: SSOR smoothing on the Pk matrix (the level-scheduled sweep above), coarse correction in the P1 space of
+// the same mesh -- the P1 operator re-discretised at the vertex values of the state the Pk Jacobian was assembled at (the star
+// path's own assembly on a child context), one cycle of the star path's multigrid as its solver.  Transfers: P = the P1
+// interpolant at the Pk nodes (vertex dof: the vertex; edge dof: its two end vertices; bubble: the three vertices), stored per
+// field as a CSR matrix with the rows of constrained Pk dofs empty, and its transpose with the rows of constrained vertices
+// empty; both are applied by the CSR SpMV kernel.  Nothing here has a counterpart in ISTL's aggregation AMG beyond the role
+// (a multigrid-preconditioned Krylov method for the higher-degree programs); the bar is convergence, as for the P1 multigrid.
+void amg_setup(Ctx&, Solver&, const Matrix&);                        // pnp_amg.cu
+void amg_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y);
+namespace {
+struct PMg {
+  Ctx* parent = nullptr; Ctx* child = nullptr; // the P1 context lives as long as this object (a solver of the parent)
+  ~PMg() { if (parent && child) ctx_destroy_owned_child(*parent, child); }
+  int F = 0, comp0 = -1;
+  Operator op1; Vec u1, b1, e1; Matrix A1; Solver S1;
+  DBuf<int> P_rp[3], P_col[3], PT_rp[3], PT_col[3];
+  DBuf<double> P_val[3], PT_val[3];
+  long P_nnz[3] = {0, 0, 0};
+  DBuf<double> r, t, z, lex1;
+};
+void upload_csr(Ctx& c, const std::vector<int>& rp, const std::vector<int>& col, const std::vector<double>& val, DBuf<int>& drp,
+                DBuf<int>& dcol, DBuf<double>& dval) {
+  drp.alloc(rp.size()); drp.upload(rp.data(), rp.size(), c.stream);
+  dcol.alloc(std::max<size_t>(1, col.size())); if (!col.empty()) dcol.upload(col.data(), col.size(), c.stream);
+  dval.alloc(std::max<size_t>(1, val.size())); if (!val.empty()) dval.upload(val.data(), val.size(), c.stream);
+}
+// y[rows] = M x through the CSR SpMV kernel
+void apply_csr(Ctx& c, long rows, const DBuf<int>& rp, const DBuf<int>& col, const DBuf<double>& val, long nnz, const double* x, double* y) {
+  k_csr_spmv<<<grid_for(rows, 256), 256, 0, c.stream>>>(rows, rp.p, col.p, val.p, x, y);
+  PNP_CHECK_LAUNCH(); c.launches++;
+  c.acct(Ctx::ACC_TRANSFER, 12.0 * (double)nnz + 20.0 * (double)rows);
+}
+void build_transfers(Ctx& c, P2Space& S, PMg& M, int F, int comp0) {
+  const long nd = S.nd, nv = S.nv, nT = S.nT;
+  const std::vector<int> tri = c.ctri.to_host(c.stream);
+  for (int k = 0; k < F; k++) {
+    const int comp = F == 3 ? k : comp0;
+    auto fixed = [&](long d) { return (S.h_dir[d] >> comp) & 1; };
+    // rows of P: (column, weight) lists per Pk dof
+    std::vector<int> rp(nd + 1, 0), col; std::vector<double> val;
+    col.reserve(3 * (size_t)nd); val.reserve(3 * (size_t)nd);
+    for (long d = 0; d < nd; d++) {
+      if (!fixed(d)) {
+        if (d >= S.voff) { col.push_back((int)(d - S.voff)); val.push_back(1.0); }
+        else if (d >= S.eoff) {
+          const long e = (d - S.eoff) / (S.deg - 1); const int idx = (int)((d - S.eoff) % (S.deg - 1));
+          const double t = (idx + 1.0) / S.deg; // distance from the smaller end vertex, in edge lengths
+          col.push_back(S.h_eva[e]); val.push_back(1.0 - t);
+          col.push_back(S.h_evb[e]); val.push_back(t);
+        } else {
+          int v[3] = {tri[3 * d], tri[3 * d + 1], tri[3 * d + 2]};
+          std::sort(v, v + 3);
+          for (int i = 0; i < 3; i++) { col.push_back(v[i]); val.push_back(1.0 / 3.0); }
+        }
+      }
+      rp[d + 1] = (int)col.size();
+    }
+    M.P_nnz[k] = (long)col.size();
+    upload_csr(c, rp, col, val, M.P_rp[k], M.P_col[k], M.P_val[k]);
+    // transpose, rows of constrained vertices empty
+    std::vector<int> trp(nv + 1, 0), tcol(col.size()); std::vector<double> tval(col.size());
+    for (size_t i = 0; i < col.size(); i++) if (!fixed(S.voff + col[i])) trp[col[i] + 1]++;
+    for (long v = 0; v < nv; v++) trp[v + 1] += trp[v];
+    std::vector<int> fill(trp.begin(), trp.end() - 1);
+    for (long d = 0; d < nd; d++)
+      for (int i = rp[d]; i < rp[d + 1]; i++) if (!fixed(S.voff + col[i])) { const int o = fill[col[i]]++; tcol[o] = (int)d; tval[o] = val[i]; }
+    tcol.resize(trp[nv]); tval.resize(trp[nv]);
+    upload_csr(c, trp, tcol, tval, M.PT_rp[k], M.PT_col[k], M.PT_val[k]);
+  }
+  (void)nT;
+  PNP_CUDA(cudaStreamSynchronize(c.stream));
+  M.F = F; M.comp0 = comp0;
+}
+PMg& pmg_of(Solver& S) { return *static_cast<PMg*>(S.pmg.get()); }
+} // namespace
+
+void pmg_setup(Ctx& c, Solver& S, const Matrix& A) {
+  P2Space& Sp = space(c);
+  PNP_REQUIRE(c.last_u && c.last_vals == A.vals.p, PNP_E_ARG,
+              "quadratic / cubic elements: the multigrid re-discretises the last assembled Jacobian (assemble, then solve; combined "
+              "or imported matrices take SSOR / ILU0)");
+  if (!S.pmg) S.pmg = std::shared_ptr<void>(new PMg, [](void* p) { delete static_cast<PMg*>(p); });
+  PMg& M = pmg_of(S);
+  const Operator& op = c.last_op;
+  const int F = op_fields(op.op), comp0 = F == 3 ? 0 : op.comp0;
+  const long nd = Sp.nd, nv = Sp.nv;
+  if (!M.child) { // the P1 space of the same mesh, on the star layout
+    M.parent = &c; M.child = ctx_make_owned_child(c);
+    const std::vector<double> x = c.cx.to_host(c.stream), y = c.cy.to_host(c.stream);
+    const std::vector<int> tri = c.ctri.to_host(c.stream), ba = c.cba.to_host(c.stream), bb = c.cbb.to_host(c.stream),
+                           bph = c.cbphys.to_host(c.stream);
+    mesh_set(*M.child, nv, x.data(), y.data(), c.nT, tri.data(), c.nB, ba.data(), bb.data(), bph.data(), nv);
+    mesh_finalize(*M.child, true);
+    M.F = 0;
+  }
+  Ctx& c1 = *M.child;
+  if (M.F != F || M.comp0 != comp0) {
+    build_transfers(c, Sp, M, F, comp0);
+    M.u1.fields = M.b1.fields = M.e1.fields = F;
+    M.u1.d.alloc((size_t)F * nv); M.b1.d.alloc((size_t)F * nv); M.e1.d.alloc((size_t)F * nv);
+    M.r.alloc((size_t)F * nd); M.t.alloc((size_t)F * nd); M.z.alloc((size_t)F * nd); M.lex1.alloc((size_t)F * nv);
+    c1.vecs.clear();
+    for (int a = 0; a < 2; a++) { auto v = std::make_unique<Vec>(); v->fields = 1; v->d.alloc(nv); v->d.zero(c.stream); c1.vecs.push_back(std::move(v)); }
+  }
+  // inject the state and the operator's coefficient fields: their vertex values
+  auto inject = [&](const double* pk, int fields, Vec& dst) {
+    for (int k = 0; k < fields; k++)
+      PNP_CUDA(cudaMemcpyAsync(M.lex1.p + (long)k * nv, pk + (long)k * nd + Sp.voff, nv * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    vec_from_lex_device(c1, dst, M.lex1.p);
+  };
+  inject(c.last_u, F, M.u1);
+  M.op1 = op; M.op1.intorder = 0; M.op1.aux0 = M.op1.aux1 = -1;
+  if (op.aux0 >= 0) { inject(c.vec(op.aux0).d.p, 1, *c1.vecs[0]); M.op1.aux0 = 0; }
+  if (op.aux1 >= 0) { inject(c.vec(op.aux1).d.p, 1, *c1.vecs[1]); M.op1.aux1 = 1; }
+  M.A1.op = op.op; M.A1.nplanes = op_planes(op.op);
+  if (M.A1.vals.n != (size_t)M.A1.nplanes * c1.nslots) M.A1.vals.alloc((size_t)M.A1.nplanes * c1.nslots);
+  assemble_jacobian(c1, M.op1, M.u1, M.A1, JAC_ANALYTIC, 1e-11);
+  M.S1.prec = PNP_PREC_AMG; M.S1.prec_steps = (int)S.opt("pmg_coarse_steps", 2); M.S1.verbosity = S.verbosity;
+  M.S1.opts = S.opts; // amg_* options reach the P1 multigrid
+  amg_setup(c1, M.S1, M.A1);
+  csr_sweep_setup(c, S, A, false);
+  c.absorb(c1);
+}
+
+// y = M^-1 d: SSOR(prec_steps) from zero, coarse correction, SSOR(prec_steps) on the new defect
+void pmg_apply(Ctx& c, Solver& S, const Matrix& A, const double* d, double* y) {
+  P2Space& Sp = space(c);
+  PMg& M = pmg_of(S);
+  Ctx& c1 = *M.child;
+  const long nd = Sp.nd, nv = Sp.nv, n = (long)M.F * nd;
+  csr_ssor_apply(c, S, A, d, y);
+  csr_spmv(c, A, y, M.t.p);
+  vec_copy(c, d, M.r.p, n); vec_axpy(c, -1.0, M.t.p, M.r.p, n);
+  for (int k = 0; k < M.F; k++) apply_csr(c, nv, M.PT_rp[k], M.PT_col[k], M.PT_val[k], M.P_nnz[k], M.r.p + (long)k * nd, M.lex1.p + (long)k * nv);
+  vec_from_lex_device(c1, M.b1, M.lex1.p);
+  amg_apply(c1, M.S1, M.A1, M.b1.d.p, M.e1.d.p);
+  vec_to_lex_device(c1, M.e1, M.lex1.p);
+  for (int k = 0; k < M.F; k++) apply_csr(c, nd, M.P_rp[k], M.P_col[k], M.P_val[k], M.P_nnz[k], M.lex1.p + (long)k * nv, M.t.p + (long)k * nd);
+  vec_axpy(c, 1.0, M.t.p, y, n);
+  csr_spmv(c, A, y, M.t.p);
+  vec_copy(c, d, M.r.p, n); vec_axpy(c, -1.0, M.t.p, M.r.p, n);
+  csr_ssor_apply(c, S, A, M.r.p, M.z.p);
+  vec_axpy(c, 1.0, M.z.p, y, n);
+  c.absorb(c1);
 }
 
 // ---- the time loop's diagnostics with quadratic functions (pnp_output.cu has the linear ones) ----

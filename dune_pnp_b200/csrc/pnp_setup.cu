@@ -401,6 +401,13 @@ void vec_upload(Ctx& c, Vec& v, const double* host_lex) {
   LAUNCH(c, k_vec_to_internal, n, tmp.p, c.int2ext.p, c.nv, v.fields, v.d.p);
   PNP_CUDA(cudaStreamSynchronize(c.stream));
 }
+// the same conversions between device buffers (linear elements; the p-multigrid of pnp_p2.cu moves vertex values this way)
+void vec_from_lex_device(Ctx& c, Vec& v, const double* d_lex) {
+  LAUNCH(c, k_vec_to_internal, c.nv * v.fields, d_lex, c.int2ext.p, c.nv, v.fields, v.d.p);
+}
+void vec_to_lex_device(Ctx& c, const Vec& v, double* d_lex) {
+  LAUNCH(c, k_vec_to_external, c.nv * v.fields, v.d.p, c.int2ext.p, c.nv, v.fields, d_lex);
+}
 void vec_download(Ctx& c, const Vec& v, double* host_lex) {
   if (c.degree >= 2) { v.d.download(host_lex, v.d.n, c.stream); return; }
   const long n = c.nv * v.fields;

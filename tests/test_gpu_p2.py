@@ -355,9 +355,13 @@ def test_errors_are_reported():
     assert e.value.status == 8                      # PNP_E_ARG
     h = c.operator(capi.OP_PB, 0)
     vu = c.vec(1)
-    for prec in (capi.PREC_AMG,):
-        st, res = c.newton(h, vu, c.solver(capi.SOLVER_BCGS, prec, 100), c.newton_opts(), check=False)
-        assert st == 8 and b"quadratic" in capi.lib().pnp_last_error(c._h)
+    # the p-multigrid re-discretises the last assembled Jacobian: an imported matrix is not one
+    rp_, col_, val_ = P.jacobian(ora.OP_PB, np.zeros(P.nd), mode=1)
+    Ai = c.matrix(h)
+    c.matrix_set_csr(h, Ai, rp_, col_, val_)
+    with pytest.raises(capi.PnpError) as e:
+        c.solve(c.solver(capi.SOLVER_BCGS, capi.PREC_AMG, 100, 1), Ai, c.vec(1), c.vec(1, np.ones(P.nd)), 1e-8)
+    assert e.value.status == 8 and "last assembled Jacobian" in str(e.value)
     with pytest.raises(capi.PnpError):
         c.carry_set([vu])                           # refinement carry-over is built for linear elements
     with pytest.raises(capi.PnpError):
@@ -514,3 +518,48 @@ def test_onestep_transport_matches_oracle(degree, method, mode):
     tol = 1e-6 if mode == 1 else 1e-3   # (FD Jacobian: 1e-5 relative noise in the matrix, amplified through the stage solves)
     assert np.linalg.norm(x1 - x1_o) <= tol * np.linalg.norm(x1_o - x0) + 1e-12 * np.linalg.norm(x1_o)
     assert np.array_equal(x1[d], g[d]) and np.array_equal(c.download(vx0, 1), x0)
+
+
+@pytest.mark.parametrize("degree,op,kind", [(2, ora.OP_PB, 1), (3, ora.OP_PB, 1), (2, ora.OP_PNP, 0), (3, ora.OP_PNP, 0)])
+def test_p_multigrid(degree, op, kind):
+    """ISTLBackend_NOVLP_CG_AMG_SSOR with -DPDEGREE=2,3 (src/Makefile.am:106-110): SSOR smoothing on the Pk matrix, coarse correction
+    in the P1 space of the same mesh through the star path's multigrid.  Bar: the preconditioned Krylov method solves the assembled
+    system in a number of iterations that does not grow with the mesh, far below SSOR alone."""
+    capi = _capi()
+    its = {}
+    for levels in (1, 2):
+        c, m, p, P = make_ctx("pore", levels, degree)
+        F = ora.nfields(op)
+        h = _operator(c, op, None, None, 1.0, intorder=5 if degree == 3 else 0)
+        u0 = np.full(F * P.nd, 0.05)
+        vu, A = c.vec(F, u0), c.matrix(h)
+        c.jacobian(h, vu, A, 1, 1e-11)
+        b = np.random.RandomState(0).uniform(-1, 1, F * P.nd)
+        b[c.constraints(h, F)] = 0.0
+        s = c.solver(kind, capi.PREC_AMG, 500, 1)
+        z, r = c.vec(F), c.vec(F, b)
+        res = c.solve(s, A, z, r, 1e-9)
+        assert res.converged
+        its[levels] = res.iterations
+        y = c.vec(F)
+        c.spmv(A, z, y)
+        assert np.linalg.norm(c.download(y, F) - b) <= 2e-9 * np.linalg.norm(b)
+        if levels == 1:
+            z2, r2 = c.vec(F), c.vec(F, b)
+            res2 = c.solve(c.solver(kind, capi.PREC_SSOR, 20000, 1), A, z2, r2, 1e-9)
+            assert res2.converged and res.iterations * 3 <= res2.iterations, (res.iterations, res2.iterations)
+    assert its[2] <= its[1] + 4 and its[2] <= 30, its
+
+
+def test_newton_pb_with_p_multigrid():
+    capi = _capi()
+    c, m, p, P = make_ctx("pore", 1, 2)
+    h = c.operator(capi.OP_PB, 0)
+    vu = c.vec(1)
+    st, res = c.newton(h, vu, c.solver(capi.SOLVER_CG, capi.PREC_AMG, 500, 1), c.newton_opts(jac_mode=1, reduction=1e-10, min_linear_reduction=1e-8))
+    vw = c.vec(1)
+    st2, res2 = c.newton(h, vw, c.solver(capi.SOLVER_BCGS, capi.PREC_ILU0, 5000, 1), c.newton_opts(jac_mode=1, reduction=1e-10, min_linear_reduction=1e-8))
+    assert res.converged and res2.converged and res.iterations == res2.iterations
+    assert res.linear_iterations <= 12 * res.iterations
+    u, w = c.download(vu, 1), c.download(vw, 1)
+    assert np.linalg.norm(u - w) <= 1e-7 * np.linalg.norm(w)
