@@ -597,7 +597,9 @@ void p2_matrix_import(Ctx& c, const Operator& op, Matrix& A, const int* rowptr, 
 // path's own assembly on a child context), one cycle of the star path's multigrid as its solver.  Transfers: P = the P1
 // interpolant at the Pk nodes (vertex dof: the vertex; edge dof: its two end vertices; bubble: the three vertices), stored per
 // field as a CSR matrix with the rows of constrained Pk dofs empty, and its transpose with the rows of constrained vertices
-// empty; both are applied by the CSR SpMV kernel.  Nothing here has a counterpart in ISTL's aggregation AMG beyond the role
+// empty; both are applied by the CSR SpMV kernel.  Scalar operators only: with the 3-field PNP system the preconditioned BiCGSTAB
+// broke down in the first measurements (not understood yet), so that combination answers PNP_E_ARG instead of failing late.
+// Nothing here has a counterpart in ISTL's aggregation AMG beyond the role
 // (a multigrid-preconditioned Krylov method for the higher-degree programs); the bar is convergence, as for the P1 multigrid.
 void amg_setup(Ctx&, Solver&, const Matrix&);                        // pnp_amg.cu
 void amg_apply(Ctx&, Solver&, const Matrix&, const double* d, double* y);
@@ -673,6 +675,9 @@ void pmg_setup(Ctx& c, Solver& S, const Matrix& A) {
   PNP_REQUIRE(c.last_u && c.last_vals == A.vals.p, PNP_E_ARG,
               "quadratic / cubic elements: the multigrid re-discretises the last assembled Jacobian (assemble, then solve; combined "
               "or imported matrices take SSOR / ILU0)");
+  PNP_REQUIRE(op_fields(c.last_op.op) == 1, PNP_E_ARG,
+              "quadratic / cubic elements: the multigrid serves the scalar operators (PB, Poisson, transport, mass); the 3-field system "
+              "takes SSOR / ILU0");
   if (!S.pmg) S.pmg = std::shared_ptr<void>(new PMg, [](void* p) { delete static_cast<PMg*>(p); });
   PMg& M = pmg_of(S);
   const Operator& op = c.last_op;

@@ -316,8 +316,10 @@ pnp_status pnp_interpolate_bcext(pnp_ctx*, int component, int pb_vec, int out_ve
  * scalar BCRS, ascending columns) and matrix values use that numbering; it is also the device layout (CSR matrices, no
  * renumbering).  Operators, residual, Jacobian (both modes), SpMV, BiCGSTAB/CG with Richardson, Jacobi, SSOR(n) or ILU0
  * (row-order sweeps, level-scheduled), Newton, StationaryLinearProblemSolver, the one-step methods,
- * interpolate(BCExtension), calcIonFlux, writeData and the VTK vertex data work as for degree 1; the multigrid
- * preconditioner, refinement carry-over and partitioned meshes answer PNP_E_ARG.  One GPU. */
+ * interpolate(BCExtension), calcIonFlux, writeData and the VTK vertex data work as for degree 1.  PNP_PREC_AMG is a
+ * p-multigrid (SSOR on the Pk matrix, coarse correction in the P1 space through the multigrid of the linear-element path) for
+ * the scalar operators on the last assembled Jacobian; the 3-field system, refinement carry-over and partitioned meshes answer
+ * PNP_E_ARG.  One GPU. */
 pnp_status pnp_space_set_degree(pnp_ctx*, int degree);
 /* degree, number of edges (0 for degree 1) and scalar dofs per field */
 pnp_status pnp_space_sizes(pnp_ctx*, int* degree, long* n_edges, long* ndof);
