@@ -344,6 +344,7 @@ P2Pattern& p2_pattern(Ctx& c, int F, int comp0) {
   const long nd = S.nd, nT = S.nT, N = F * nd;
   const int NL = S.NL;
   auto dirichlet = [&](int k, long d) { return (S.h_dir[d] >> (F == 3 ? k : comp0)) & 1; };
+  PNP_REQUIRE((long)NL * NL * nT < (1l << 31), PNP_E_MESH, "too many element couplings for 32-bit pattern offsets");
   std::vector<int> cnt(nd + 1, 0);
   for (long e = 0; e < nT; e++) for (int i = 0; i < NL; i++) cnt[S.h_e2d[NL * e + i] + 1] += NL;
   for (long d = 0; d < nd; d++) cnt[d + 1] += cnt[d];
@@ -361,6 +362,9 @@ P2Pattern& p2_pattern(Ctx& c, int F, int comp0) {
     else for (int kj = 0; kj < F; kj++) for (int t = nptr[d]; t < nptr[d + 1]; t++) len += !dirichlet(kj, nbr[t]);
     Pn.h_rp[ki * nd + d + 1] = len;
   }
+  { long total = 0;
+    for (long r = 0; r < N; r++) total += Pn.h_rp[r + 1];
+    PNP_REQUIRE(total < (1l << 31), PNP_E_MESH, "too many matrix entries for 32-bit CSR offsets"); }
   for (long r = 0; r < N; r++) Pn.h_rp[r + 1] += Pn.h_rp[r];
   Pn.nnz = Pn.h_rp[N];
   Pn.h_col.resize(Pn.nnz);
